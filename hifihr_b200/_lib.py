@@ -1,0 +1,169 @@
+"""ctypes binding of libhifihr_b200.so (the C-ABI declared in include/hifihr_b200.h).
+
+This is the whole "extension": tensors are unpacked to raw device pointers and the
+current CUDA stream; there is no CPU fallback — if the library is missing, or a
+tensor is not a contiguous CUDA tensor of the expected dtype, the call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhifihr_b200.so")
+
+vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+
+
+class HfrHandModel(C.Structure):
+    _fields_ = [("V", i32), ("NJ", i32), ("NS", i32), ("NPC", i32), ("NW", i32), ("NT", i32),
+                ("center_joint", i32), ("C3", i32),
+                ("dirs", vp), ("v_template", vp), ("J_template", vp), ("J_shapedirs", vp),
+                ("pca_comps", vp), ("pose_mean", vp), ("parents", vp), ("skin_idx", vp), ("skin_w", vp),
+                ("tip_verts", vp), ("joint_order", vp)]
+
+
+class HfrManoFwdArgs(C.Structure):
+    _fields_ = [("B", i32), ("pose", vp), ("betas", vp), ("trans", vp), ("verts", vp), ("joints", vp)]
+
+
+class HfrManoBwdArgs(C.Structure):
+    _fields_ = [("B", i32), ("pose", vp), ("betas", vp), ("trans", vp), ("g_verts", vp), ("g_joints", vp),
+                ("g_pose", vp), ("g_betas", vp), ("g_trans", vp)]
+
+
+class HfrTopology(C.Structure):
+    _fields_ = [("V", i32), ("F", i32), ("faces", vp), ("vf_ptr", vp), ("vf_idx", vp),
+                ("NJR", i32), ("NOUT", i32), ("jr_ptr", vp), ("jr_col", vp), ("jr_val", vp),
+                ("vj_ptr", vp), ("vj_row", vp), ("vj_val", vp), ("out_src", vp)]
+
+
+class HfrGeomFwdArgs(C.Structure):
+    _fields_ = [("B", i32), ("root_out", i32), ("verts", vp), ("root_xyz", vp), ("focal", vp), ("prp", vp),
+                ("joints", vp), ("verts_rel", vp), ("verts_view", vp), ("verts_ndc", vp), ("vnormals", vp)]
+
+
+class HfrGeomBwdArgs(C.Structure):
+    _fields_ = [("B", i32), ("root_out", i32), ("verts", vp), ("root_xyz", vp), ("focal", vp), ("prp", vp),
+                ("g_joints", vp), ("g_verts_rel", vp), ("g_verts_view", vp), ("g_verts_ndc", vp),
+                ("g_vnormals", vp), ("g_verts", vp)]
+
+
+class HfrRasterArgs(C.Structure):
+    _fields_ = [("N", i32), ("H", i32), ("W", i32), ("K", i32), ("Ftot", i64), ("face_verts", vp),
+                ("mesh_first", vp), ("mesh_nfaces", vp), ("blur_radius", f32),
+                ("perspective_correct", i32), ("clip_barycentric", i32), ("cull_backfaces", i32),
+                ("pix_to_face", vp), ("zbuf", vp), ("bary", vp), ("dists", vp), ("workspace", vp)]
+
+
+class HfrRasterBwdArgs(C.Structure):
+    _fields_ = [("N", i32), ("H", i32), ("W", i32), ("K", i32), ("Ftot", i64), ("face_verts", vp),
+                ("pix_to_face", vp), ("g_zbuf", vp), ("g_bary", vp), ("g_dists", vp), ("blur_radius", f32),
+                ("perspective_correct", i32), ("clip_barycentric", i32), ("g_face_verts", vp)]
+
+
+class HfrShadeParams(C.Structure):
+    _fields_ = [("N", i32), ("H", i32), ("W", i32), ("K", i32), ("F", i32), ("V", i32), ("blend", i32),
+                ("shade", i32), ("sigma", f32), ("gamma", f32), ("znear", f32), ("zfar", f32),
+                ("background", f32 * 3), ("light_ambient", f32 * 3), ("light_specular", f32 * 3),
+                ("mat_ambient", f32 * 3), ("mat_diffuse", f32 * 3), ("mat_specular", f32 * 3),
+                ("shininess", f32), ("tex_n", i32), ("tex_h", i32), ("tex_w", i32), ("VT", i32)]
+
+
+class HfrShadeFwdArgs(C.Structure):
+    _fields_ = [("p", HfrShadeParams), ("pix_to_face", vp), ("zbuf", vp), ("bary", vp), ("dists", vp),
+                ("faces", vp), ("verts_view", vp), ("vnormals", vp), ("faces_uvs", vp), ("verts_uvs", vp),
+                ("texture", vp), ("light_dir", vp), ("light_color", vp), ("image", vp)]
+
+
+class HfrShadeBwdArgs(C.Structure):
+    _fields_ = [("f", HfrShadeFwdArgs), ("g_image", vp), ("g_zbuf", vp), ("g_bary", vp), ("g_dists", vp),
+                ("verts_ndc", vp), ("g_verts_ndc", vp), ("blur_radius", f32), ("perspective_correct", i32),
+                ("clip_barycentric", i32), ("g_verts_view", vp), ("g_vnormals", vp), ("g_texture", vp),
+                ("g_light_dir", vp), ("g_light_color", vp)]
+
+
+class HfrRasterShadeArgs(C.Structure):
+    _fields_ = [("r", HfrRasterArgs), ("s", HfrShadeFwdArgs)]
+
+
+class HfrPoolArgs(C.Structure):
+    _fields_ = [("N", i32), ("H", i32), ("W", i32), ("aa", i32), ("binarize", i32), ("image", vp),
+                ("images_in", vp), ("re_img", vp), ("re_sil", vp), ("mask_rgbs", vp)]
+
+
+class HfrPoolBwdArgs(C.Structure):
+    _fields_ = [("N", i32), ("H", i32), ("W", i32), ("aa", i32), ("binarize", i32), ("g_re_img", vp),
+                ("g_re_sil", vp), ("g_image", vp)]
+
+
+class HfrLossArgs(C.Structure):
+    _fields_ = [("N", i32), ("H", i32), ("W", i32), ("sil_scale", f32), ("want_ssim", i32), ("want_grad", i32),
+                ("re_img", vp), ("re_sil", vp), ("imgs", vp), ("seg", vp), ("sums", vp), ("gauss", vp), ("dmaps", vp)]
+
+
+class HfrLossBwdArgs(C.Structure):
+    _fields_ = [("f", HfrLossArgs), ("w", vp), ("gauss", vp), ("count_global", i64), ("n_global", i32), ("g_re_img", vp), ("g_re_sil", vp)]
+
+
+LOSS_NSUMS = 8
+ENTRY_POINTS = [
+    "hfr_last_error", "hfr_abi_version", "hfr_device_ok", "hfr_mano_forward", "hfr_mano_backward",
+    "hfr_geom_forward", "hfr_geom_backward", "hfr_raster_workspace_bytes", "hfr_raster_forward",
+    "hfr_raster_backward", "hfr_shade_forward", "hfr_shade_backward", "hfr_raster_shade_forward",
+    "hfr_pool_forward", "hfr_pool_backward", "hfr_loss_forward", "hfr_loss_backward",
+]
+
+_lib = None
+
+
+class HfrError(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    """Load the CUDA library; raise loudly if it was not built (no fallback exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise HfrError(f"{LIB_PATH} is missing: run `python -m hifihr_b200.build` (or "
+                           "__graft_entry__.build()); hifihr_b200 has no CPU or PyTorch fallback")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.hfr_last_error.restype = C.c_char_p
+        _lib.hfr_raster_workspace_bytes.restype = C.c_int64
+        _lib.hfr_raster_workspace_bytes.argtypes = [C.c_int64]
+        if _lib.hfr_abi_version() != 1:
+            raise HfrError("libhifihr_b200.so ABI version mismatch")
+    return _lib
+
+
+def call(name: str, *structs):
+    """Invoke an entry point on the current torch CUDA stream; map error codes to exceptions
+    (HFR_EINVAL -> ValueError as PyTorch3D does for bad settings, others -> RuntimeError)."""
+    L = lib()
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    rc = getattr(L, name)(*[C.byref(s) for s in structs], stream)
+    if rc != 0:
+        msg = L.hfr_last_error().decode()
+        if rc == 1:
+            raise ValueError(msg)
+        raise HfrError(f"{name} failed (code {rc}): {msg}")
+
+
+def ptr(t: torch.Tensor | None, dtype=None, name="tensor"):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise HfrError(f"{name} must be a CUDA tensor: hifihr_b200 has no CPU path")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    return t.data_ptr()
+
+
+def f3(v):
+    return (f32 * 3)(*[float(x) for x in v])

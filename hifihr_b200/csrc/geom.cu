@@ -1,0 +1,258 @@
+// Per-sample geometry between the hand layer and the rasterizer (sm_100a), forward + backward.
+//
+//   joints  = reorder(J_regressor @ posed verts, tips)      Freihand_trainer_mano_fullsup.py:175-215
+//   root    = joints[root_id]; joints -= root; verts_rel = verts - root        models_res_nimble.py:159-166
+//   view    = verts_rel + root_xyz (two offset_verts_ calls)                     models_res_nimble.py:203-205
+//   ndc.xy  = ([X,Y,Z,1] K).xy / Z, ndc.z = Z                                     PerspectiveCameras + MeshRasterizer.transform
+//   normals = normalize(sum of corner cross products of incident faces)          Meshes.verts_normals_packed
+//
+// One CTA per sample, everything staged in shared memory; all scatter patterns of the
+// reference (index_add for normals, J_regressor^T in the backward) are turned into gathers
+// over precomputed CSR incidence lists, so there are no atomics and results are deterministic.
+#include "common.cuh"
+
+namespace {
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ void cross3(const float* u, const float* w, float* o) {
+  o[0] = u[1] * w[2] - u[2] * w[1];
+  o[1] = u[2] * w[0] - u[0] * w[2];
+  o[2] = u[0] * w[1] - u[1] * w[0];
+}
+
+// raw (un-normalised) vertex normal: sum over incident (face, corner) of the corner cross product
+__device__ __forceinline__ void raw_normal(const HfrTopology& t, const float* sv, int v, float* n) {
+  n[0] = n[1] = n[2] = 0.0f;
+  for (int e = t.vf_ptr[v]; e < t.vf_ptr[v + 1]; ++e) {
+    const int code = t.vf_idx[e], f = code >> 2, c = code & 3;
+    const int ia = t.faces[3 * f + c], ib = t.faces[3 * f + (c + 1) % 3], ic = t.faces[3 * f + (c + 2) % 3];
+    float u[3], w[3], x[3];
+    for (int k = 0; k < 3; ++k) { u[k] = sv[3 * ib + k] - sv[3 * ia + k]; w[k] = sv[3 * ic + k] - sv[3 * ia + k]; }
+    cross3(u, w, x);
+    n[0] += x[0]; n[1] += x[1]; n[2] += x[2];
+  }
+}
+
+// Shared by fwd/bwd: stage verts, regress joints, find root; leaves view-space verts in s_view.
+// s_pos (NOUT*3) holds un-shifted output joints, s_root[3] the predicted root.
+__device__ void geom_stage(const HfrTopology& t, int B, int b, int root_out, const float* __restrict__ verts,
+                           const float* __restrict__ root_xyz, float* s_v, float* s_view, float* s_j, float* s_pos,
+                           float* s_root) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, V = t.V;
+  const float* vin = verts + (size_t)b * V * 3;
+  for (int i = tid; i < 3 * V; i += kThreads) s_v[i] = vin[i];
+  if (tid < 3) s_root[tid] = 0.0f;
+  __syncthreads();
+  if (root_out >= 0) {
+    for (int j = warp; j < t.NJR; j += kThreads / 32) {
+      float ax = 0.f, ay = 0.f, az = 0.f;
+      for (int e = t.jr_ptr[j] + lane; e < t.jr_ptr[j + 1]; e += 32) {
+        const int v = t.jr_col[e];
+        const float w = t.jr_val[e];
+        ax += w * s_v[3 * v]; ay += w * s_v[3 * v + 1]; az += w * s_v[3 * v + 2];
+      }
+      ax = warp_sum(ax); ay = warp_sum(ay); az = warp_sum(az);
+      if (lane == 0) { s_j[3 * j] = ax; s_j[3 * j + 1] = ay; s_j[3 * j + 2] = az; }
+    }
+    __syncthreads();
+    for (int i = tid; i < t.NOUT * 3; i += kThreads) {
+      const int k = i / 3, c = i % 3, src = t.out_src[k];
+      s_pos[i] = src >= 0 ? s_j[3 * src + c] : s_v[3 * (-(src + 1)) + c];
+    }
+    __syncthreads();
+    if (tid < 3) s_root[tid] = s_pos[3 * root_out + tid];
+    __syncthreads();
+  }
+  const float* rx = root_xyz ? root_xyz + (size_t)b * 3 : nullptr;
+  for (int i = tid; i < 3 * V; i += kThreads) {
+    const int c = i % 3;
+    const float rel = s_v[i] - s_root[c];
+    s_view[i] = rx ? rel + rx[c] : rel;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kThreads) geom_fwd_kernel(HfrTopology t, HfrGeomFwdArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int b = blockIdx.x, tid = threadIdx.x, V = t.V;
+  float* s_v = smem;
+  float* s_view = s_v + 3 * V;
+  float* s_j = s_view + 3 * V;           // NJR*3
+  float* s_pos = s_j + 3 * (t.NJR > 0 ? t.NJR : 1);  // NOUT*3
+  float* s_root = s_pos + 3 * (t.NOUT > 0 ? t.NOUT : 1);
+  geom_stage(t, a.B, b, a.root_out, a.verts, a.root_xyz, s_v, s_view, s_j, s_pos, s_root);
+  const size_t base = (size_t)b * V * 3;
+  if (a.joints && a.root_out >= 0)
+    for (int i = tid; i < t.NOUT * 3; i += kThreads) a.joints[(size_t)b * t.NOUT * 3 + i] = s_pos[i] - s_root[i % 3];
+  if (a.verts_rel)
+    for (int i = tid; i < 3 * V; i += kThreads) a.verts_rel[base + i] = s_v[i] - s_root[i % 3];
+  if (a.verts_view)
+    for (int i = tid; i < 3 * V; i += kThreads) a.verts_view[base + i] = s_view[i];
+  if (a.verts_ndc) {
+    const float fx = a.focal[2 * b], fy = a.focal[2 * b + 1], px = a.prp[2 * b], py = a.prp[2 * b + 1];
+    for (int v = tid; v < V; v += kThreads) {
+      const float X = s_view[3 * v], Y = s_view[3 * v + 1], Z = s_view[3 * v + 2];
+      a.verts_ndc[base + 3 * v + 0] = XDIV(XADD(XMUL(fx, X), XMUL(px, Z)), Z);
+      a.verts_ndc[base + 3 * v + 1] = XDIV(XADD(XMUL(fy, Y), XMUL(py, Z)), Z);
+      a.verts_ndc[base + 3 * v + 2] = Z;
+    }
+  }
+  if (a.vnormals) {
+    for (int v = tid; v < V; v += kThreads) {
+      float n[3];
+      raw_normal(t, s_view, v, n);
+      const float len = fmaxf(sqrtf(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]), 1e-6f);
+      a.vnormals[base + 3 * v + 0] = n[0] / len;
+      a.vnormals[base + 3 * v + 1] = n[1] / len;
+      a.vnormals[base + 3 * v + 2] = n[2] / len;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) geom_bwd_kernel(HfrTopology t, HfrGeomBwdArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, V = t.V;
+  float* s_v = smem;
+  float* s_view = s_v + 3 * V;
+  float* s_gN = s_view + 3 * V;          // grads wrt raw normals
+  float* s_g = s_gN + 3 * V;             // accumulated grads wrt view / rel verts
+  float* s_j = s_g + 3 * V;
+  float* s_pos = s_j + 3 * (t.NJR > 0 ? t.NJR : 1);
+  float* s_root = s_pos + 3 * (t.NOUT > 0 ? t.NOUT : 1);
+  float* s_red = s_root + 4;             // 8 warps * 3 + 3
+  float* s_gj = s_red + 28;              // NJR*3 grads wrt regressed joints
+  geom_stage(t, a.B, b, a.root_out, a.verts, a.root_xyz, s_v, s_view, s_j, s_pos, s_root);
+  const size_t base = (size_t)b * V * 3;
+  // 1. raw-normal grads
+  for (int v = tid; v < V; v += kThreads) {
+    float g[3] = {0.f, 0.f, 0.f};
+    if (a.g_vnormals) {
+      float n[3];
+      raw_normal(t, s_view, v, n);
+      const float len = sqrtf(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+      const float gx = a.g_vnormals[base + 3 * v], gy = a.g_vnormals[base + 3 * v + 1],
+                  gz = a.g_vnormals[base + 3 * v + 2];
+      if (len >= 1e-6f) {
+        const float hx = n[0] / len, hy = n[1] / len, hz = n[2] / len;
+        const float d = hx * gx + hy * gy + hz * gz;
+        g[0] = (gx - hx * d) / len; g[1] = (gy - hy * d) / len; g[2] = (gz - hz * d) / len;
+      } else {
+        g[0] = gx / 1e-6f; g[1] = gy / 1e-6f; g[2] = gz / 1e-6f;
+      }
+    }
+    s_gN[3 * v] = g[0]; s_gN[3 * v + 1] = g[1]; s_gN[3 * v + 2] = g[2];
+  }
+  __syncthreads();
+  // 2. per-vertex gather of every grad that lands on view-space verts
+  float sx = 0.f, sy = 0.f, sz = 0.f;
+  const float fx = a.g_verts_ndc ? a.focal[2 * b] : 0.f, fy = a.g_verts_ndc ? a.focal[2 * b + 1] : 0.f;
+  for (int v = tid; v < V; v += kThreads) {
+    float g[3] = {0.f, 0.f, 0.f};
+    if (a.g_verts_view) { g[0] = a.g_verts_view[base + 3 * v]; g[1] = a.g_verts_view[base + 3 * v + 1]; g[2] = a.g_verts_view[base + 3 * v + 2]; }
+    if (a.g_verts_ndc) {
+      const float X = s_view[3 * v], Y = s_view[3 * v + 1], Z = s_view[3 * v + 2];
+      const float gx = a.g_verts_ndc[base + 3 * v], gy = a.g_verts_ndc[base + 3 * v + 1], gz = a.g_verts_ndc[base + 3 * v + 2];
+      // x = (fx X + px Z)/Z = fx X / Z + px
+      g[0] += gx * fx / Z;
+      g[1] += gy * fy / Z;
+      g[2] += gz - (gx * fx * X + gy * fy * Y) / (Z * Z);
+    }
+    if (a.g_vnormals) {
+      for (int e = t.vf_ptr[v]; e < t.vf_ptr[v + 1]; ++e) {
+        const int code = t.vf_idx[e], f = code >> 2, c = code & 3;
+        const int ia = t.faces[3 * f + c], ib = t.faces[3 * f + (c + 1) % 3], ic = t.faces[3 * f + (c + 2) % 3];
+        // corner terms: N_a += (b-a)x(c-a);  N_b += (c-b)x(a-b);  N_c += (a-c)x(b-c)
+        float u[3], w[3], x[3];
+        const float *ga = s_gN + 3 * ia, *gb = s_gN + 3 * ib, *gc = s_gN + 3 * ic;
+        // from N_a: u=b-a, w=c-a : dL/da = -(w x ga) - (ga x u)
+        for (int k = 0; k < 3; ++k) { u[k] = s_view[3 * ib + k] - s_view[3 * ia + k]; w[k] = s_view[3 * ic + k] - s_view[3 * ia + k]; }
+        cross3(w, ga, x); g[0] -= x[0]; g[1] -= x[1]; g[2] -= x[2];
+        cross3(ga, u, x); g[0] -= x[0]; g[1] -= x[1]; g[2] -= x[2];
+        // from N_b: u'=c-b, w'=a-b : dL/da = gb x u'
+        for (int k = 0; k < 3; ++k) u[k] = s_view[3 * ic + k] - s_view[3 * ib + k];
+        cross3(gb, u, x); g[0] += x[0]; g[1] += x[1]; g[2] += x[2];
+        // from N_c: u''=a-c, w''=b-c : dL/da = w'' x gc
+        for (int k = 0; k < 3; ++k) w[k] = s_view[3 * ib + k] - s_view[3 * ic + k];
+        cross3(w, gc, x); g[0] += x[0]; g[1] += x[1]; g[2] += x[2];
+      }
+    }
+    if (a.g_verts_rel) { g[0] += a.g_verts_rel[base + 3 * v]; g[1] += a.g_verts_rel[base + 3 * v + 1]; g[2] += a.g_verts_rel[base + 3 * v + 2]; }
+    s_g[3 * v] = g[0]; s_g[3 * v + 1] = g[1]; s_g[3 * v + 2] = g[2];
+    sx += g[0]; sy += g[1]; sz += g[2];
+  }
+  if (a.root_out < 0) {
+    __syncthreads();
+    for (int i = tid; i < 3 * V; i += kThreads) a.g_verts[base + i] = s_g[i];
+    return;
+  }
+  // 3. root / joints: rel = v - root, joints_out = pos - root
+  const float* gj_in = a.g_joints ? a.g_joints + (size_t)b * t.NOUT * 3 : nullptr;
+  if (gj_in)
+    for (int i = tid; i < t.NOUT * 3; i += kThreads) {
+      const float g = gj_in[i];
+      const int c = i % 3;
+      if (c == 0) sx += g; else if (c == 1) sy += g; else sz += g;
+    }
+  sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
+  if (lane == 0) { s_red[warp * 3] = sx; s_red[warp * 3 + 1] = sy; s_red[warp * 3 + 2] = sz; }
+  for (int i = tid; i < 3 * t.NJR; i += kThreads) s_gj[i] = 0.0f;
+  __syncthreads();
+  if (tid == 0) {
+    float groot[3] = {0.f, 0.f, 0.f};
+    for (int w = 0; w < kThreads / 32; ++w) { groot[0] -= s_red[w * 3]; groot[1] -= s_red[w * 3 + 1]; groot[2] -= s_red[w * 3 + 2]; }
+    for (int k = 0; k < t.NOUT; ++k) {
+      const int src = t.out_src[k];
+      for (int c = 0; c < 3; ++c) {
+        float g = gj_in ? gj_in[3 * k + c] : 0.0f;
+        if (k == a.root_out) g += groot[c];
+        if (src >= 0) s_gj[3 * src + c] += g; else s_g[3 * (-(src + 1)) + c] += g;
+      }
+    }
+  }
+  __syncthreads();
+  for (int v = tid; v < V; v += kThreads) {
+    float g0 = s_g[3 * v], g1 = s_g[3 * v + 1], g2 = s_g[3 * v + 2];
+    for (int e = t.vj_ptr[v]; e < t.vj_ptr[v + 1]; ++e) {
+      const int j = t.vj_row[e];
+      const float w = t.vj_val[e];
+      g0 += w * s_gj[3 * j]; g1 += w * s_gj[3 * j + 1]; g2 += w * s_gj[3 * j + 2];
+    }
+    a.g_verts[base + 3 * v] = g0; a.g_verts[base + 3 * v + 1] = g1; a.g_verts[base + 3 * v + 2] = g2;
+  }
+}
+
+static int check_topo(const HfrTopology* t, int need_joints) {
+  HFR_CHECK_ARG(t && t->V > 0 && t->F > 0 && t->faces && t->vf_ptr && t->vf_idx, "topology: null/empty");
+  if (need_joints)
+    HFR_CHECK_ARG(t->NJR > 0 && t->NOUT > 0 && t->NOUT <= 64 && t->jr_ptr && t->jr_col && t->jr_val && t->vj_ptr &&
+                      t->vj_row && t->vj_val && t->out_src,
+                  "topology: joint regressor tables missing");
+  return HFR_OK;
+}
+}  // namespace
+
+extern "C" int hfr_geom_forward(const HfrTopology* t, const HfrGeomFwdArgs* a, void* stream) {
+  HFR_CHECK_ARG(a && a->verts, "geom_forward: null argument");
+  if (int rc = check_topo(t, a->root_out >= 0)) return rc;
+  HFR_CHECK_ARG(!a->verts_ndc || (a->focal && a->prp), "geom_forward: verts_ndc needs focal/prp");
+  if (a->B == 0) return HFR_OK;
+  const size_t smem = (size_t)(6 * t->V + 3 * (t->NJR > 0 ? t->NJR : 1) + 3 * (t->NOUT > 0 ? t->NOUT : 1) + 8) * sizeof(float);
+  HFR_CHECK_ARG(smem <= 227 * 1024, "geom_forward: mesh too large for shared memory");
+  if (smem > 48 * 1024) cudaFuncSetAttribute(geom_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  geom_fwd_kernel<<<a->B, kThreads, smem, (cudaStream_t)stream>>>(*t, *a);
+  HFR_CHECK_LAUNCH("geom_forward");
+  return HFR_OK;
+}
+
+extern "C" int hfr_geom_backward(const HfrTopology* t, const HfrGeomBwdArgs* a, void* stream) {
+  HFR_CHECK_ARG(a && a->verts && a->g_verts, "geom_backward: null argument");
+  if (int rc = check_topo(t, a->root_out >= 0)) return rc;
+  HFR_CHECK_ARG(!a->g_verts_ndc || (a->focal && a->prp), "geom_backward: g_verts_ndc needs focal/prp");
+  if (a->B == 0) return HFR_OK;
+  const size_t smem = (size_t)(12 * t->V + 6 * (t->NJR > 0 ? t->NJR : 1) + 3 * (t->NOUT > 0 ? t->NOUT : 1) + 40) * sizeof(float);
+  HFR_CHECK_ARG(smem <= 227 * 1024, "geom_backward: mesh too large for shared memory");
+  if (smem > 48 * 1024) cudaFuncSetAttribute(geom_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  geom_bwd_kernel<<<a->B, kThreads, smem, (cudaStream_t)stream>>>(*t, *a);
+  HFR_CHECK_LAUNCH("geom_backward");
+  return HFR_OK;
+}

@@ -1,0 +1,446 @@
+// Articulated hand model (MANO / NIMBLE-shaped) forward + backward for sm_100a.
+//
+// Replaces ManoLayer.forward (utils/my_mano.py:315-483): pose PCA -> axis-angle ->
+// Rodrigues (utils/manopth/rodrigues_layer.py) -> pose map -> shape/pose blendshapes ->
+// joint regression -> kinematic chain -> linear blend skinning -> tips / reorder / centring,
+// and its autograd.  One CTA per sample; the blend basis is stored coefficient-major and
+// padded to float4 so every thread streams 128-bit, fully coalesced rows out of L2 (the
+// 1.36 MB MANO basis stays L2-resident).  No atomics; reductions are warp shuffles.
+#include <stdarg.h>
+
+#include "common.cuh"
+#include "mano_math.cuh"
+
+static thread_local char g_err[512] = "";
+void hfr_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+extern "C" const char* hfr_last_error(void) { return g_err; }
+extern "C" int hfr_abi_version(void) { return HFR_ABI_VERSION; }
+extern "C" int hfr_device_ok(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  cudaDeviceProp p;
+  if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return 0;
+  return p.major == 10 ? 1 : 0;
+}
+
+namespace {
+
+constexpr int kThreads = 256;
+
+struct ManoSmem {
+  float* full;   // 3*NJ axis-angle
+  float* R;      // NJ*9
+  float* coef;   // NS + 9(NJ-1): betas then pose map
+  float* J;      // NJ*3
+  float* G;      // NJ*12
+  float* A;      // NJ*12
+  float* misc;   // 64 scratch
+  float* vp;     // C3 (posed rest verts)
+  float* gv;     // C3 (backward only)
+};
+
+__device__ __forceinline__ ManoSmem carve(float* s, const HfrHandModel& m, bool bwd) {
+  ManoSmem o;
+  const int NJ = m.NJ;
+  auto up4 = [](int x) { return (x + 3) & ~3; };
+  o.full = s; s += up4(3 * NJ);
+  o.R = s; s += up4(9 * NJ);
+  o.coef = s; s += up4(m.NS + 9 * (NJ - 1));
+  o.J = s; s += up4(3 * NJ);
+  o.G = s; s += 12 * NJ;
+  o.A = s; s += 12 * NJ;
+  o.misc = s; s += 64;
+  o.vp = s; s += m.C3;
+  o.gv = bwd ? s : nullptr;
+  return o;
+}
+
+static size_t mano_smem_bytes(const HfrHandModel& m, bool bwd) {
+  auto up4 = [](int x) { return (x + 3) & ~3; };
+  size_t f = up4(3 * m.NJ) + up4(9 * m.NJ) + up4(m.NS + 9 * (m.NJ - 1)) + up4(3 * m.NJ) + 24 * m.NJ + 64;
+  f += (size_t)m.C3 * (bwd ? 2 : 1);
+  return f * sizeof(float);
+}
+
+// Phases 1-3 shared by forward and backward: pose -> R, pose map, J, G, A.
+__device__ void mano_setup(const HfrHandModel& m, const ManoSmem& s, const float* __restrict__ pose,
+                           const float* __restrict__ betas) {
+  const int tid = threadIdx.x, NJ = m.NJ, NPOSE = 3 * (NJ - 1);
+  for (int i = tid; i < 3 * NJ; i += kThreads) {
+    float v;
+    if (i < 3) {
+      v = pose[i];
+    } else {
+      const int o = i - 3;
+      v = m.pose_mean ? m.pose_mean[o] : 0.0f;
+      if (m.NPC > 0) {
+        float h = 0.0f;
+        for (int k = 0; k < m.NPC; ++k) h += pose[3 + k] * m.pca_comps[k * NPOSE + o];
+        v += h;
+      } else {
+        v += pose[3 + o];
+      }
+    }
+    s.full[i] = v;
+  }
+  for (int i = tid; i < m.NS; i += kThreads) s.coef[i] = betas ? betas[i] : 0.0f;
+  __syncthreads();
+  if (tid < NJ) hfr_rodrigues_fwd(s.full + 3 * tid, s.R + 9 * tid);
+  for (int i = tid; i < 3 * NJ; i += kThreads) {
+    float acc = m.J_template[i];
+    for (int k = 0; k < m.NS; ++k) acc += m.J_shapedirs[i * m.NS + k] * s.coef[k];
+    s.J[i] = acc;
+  }
+  __syncthreads();
+  for (int i = tid; i < 9 * (NJ - 1); i += kThreads) {
+    const int e = i % 9;
+    s.coef[m.NS + i] = s.R[9 + i] - ((e == 0 || e == 4 || e == 8) ? 1.0f : 0.0f);
+  }
+  if (tid < 32) {  // kinematic chain: 12 lanes cooperate on one 3x4 product per joint
+    const int r = tid >> 2, c = tid & 3;
+    for (int j = 0; j < NJ; ++j) {
+      const int p = m.parents[j];
+      if (tid < 12) {
+        float val;
+        const float* Rj = s.R + 9 * j;
+        if (p < 0) {
+          val = c < 3 ? Rj[r * 3 + c] : s.J[3 * j + r];
+        } else {
+          const float* P = s.G + 12 * p;
+          if (c < 3) {
+            val = P[r * 4 + 0] * Rj[0 * 3 + c] + P[r * 4 + 1] * Rj[1 * 3 + c] + P[r * 4 + 2] * Rj[2 * 3 + c];
+          } else {
+            const float t0 = s.J[3 * j + 0] - s.J[3 * p + 0], t1 = s.J[3 * j + 1] - s.J[3 * p + 1],
+                        t2 = s.J[3 * j + 2] - s.J[3 * p + 2];
+            val = P[r * 4 + 0] * t0 + P[r * 4 + 1] * t1 + P[r * 4 + 2] * t2 + P[r * 4 + 3];
+          }
+        }
+        s.G[12 * j + tid] = val;
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < 3 * NJ; i += kThreads) {  // A_j = G_j with the rest joint removed
+    const int j = i / 3, r = i % 3;
+    const float* G = s.G + 12 * j;
+    const float* Jj = s.J + 3 * j;
+    float* A = s.A + 12 * j;
+    A[r * 4 + 0] = G[r * 4 + 0];
+    A[r * 4 + 1] = G[r * 4 + 1];
+    A[r * 4 + 2] = G[r * 4 + 2];
+    A[r * 4 + 3] = G[r * 4 + 3] - (G[r * 4 + 0] * Jj[0] + G[r * 4 + 1] * Jj[1] + G[r * 4 + 2] * Jj[2]);
+  }
+  __syncthreads();
+}
+
+// Phase 4: v_posed = template + sum_k coef_k * dirs_k, 128-bit coalesced rows.
+__device__ void mano_blend(const HfrHandModel& m, const ManoSmem& s) {
+  const int C4 = m.C3 >> 2, NK = m.NS + 9 * (m.NJ - 1);
+  const float4* __restrict__ dirs4 = reinterpret_cast<const float4*>(m.dirs);
+  const float4* __restrict__ vt4 = reinterpret_cast<const float4*>(m.v_template);
+  float4* vp4 = reinterpret_cast<float4*>(s.vp);
+  for (int c4 = threadIdx.x; c4 < C4; c4 += kThreads) {
+    float4 acc = vt4[c4];
+#pragma unroll 8
+    for (int k = 0; k < NK; ++k) {
+      const float w = s.coef[k];
+      const float4 d = __ldg(dirs4 + (size_t)k * C4 + c4);
+      acc.x += w * d.x; acc.y += w * d.y; acc.z += w * d.z; acc.w += w * d.w;
+    }
+    vp4[c4] = acc;
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void skin_matrix(const HfrHandModel& m, const float* A, int v, float* T) {
+#pragma unroll
+  for (int e = 0; e < 12; ++e) T[e] = 0.0f;
+  for (int i = 0; i < m.NW; ++i) {
+    const float w = m.skin_w[i * m.V + v];
+    if (w != 0.0f) {
+      const float* Aj = A + 12 * m.skin_idx[i * m.V + v];
+#pragma unroll
+      for (int e = 0; e < 12; ++e) T[e] += w * Aj[e];
+    }
+  }
+}
+
+__device__ __forceinline__ void skin_vertex(const HfrHandModel& m, const ManoSmem& s, int v, float* out) {
+  float T[12];
+  skin_matrix(m, s.A, v, T);
+  const float x = s.vp[3 * v], y = s.vp[3 * v + 1], z = s.vp[3 * v + 2];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) out[r] = T[r * 4 + 0] * x + T[r * 4 + 1] * y + T[r * 4 + 2] * z + T[r * 4 + 3];
+}
+
+__global__ void __launch_bounds__(kThreads) mano_fwd_kernel(HfrHandModel m, HfrManoFwdArgs a, int pose_dim) {
+  extern __shared__ __align__(16) float smem[];
+  const ManoSmem s = carve(smem, m, false);
+  const int b = blockIdx.x, tid = threadIdx.x, NJ = m.NJ;
+  mano_setup(m, s, a.pose + (size_t)b * pose_dim, a.betas ? a.betas + (size_t)b * m.NS : nullptr);
+  mano_blend(m, s);
+  float* tips = s.misc;        // NT*3
+  float* off = s.misc + 48;    // 3
+  if (tid < m.NT) skin_vertex(m, s, m.tip_verts[tid], tips + 3 * tid);
+  __syncthreads();
+  if (tid < 3) {
+    float o = 0.0f;
+    if (a.trans) {
+      o = a.trans[(size_t)b * 3 + tid];
+    } else if (m.center_joint >= 0) {
+      const int src = m.joint_order[m.center_joint];
+      o = -(src < NJ ? s.G[12 * src + tid * 4 + 3] : tips[3 * (src - NJ) + tid]);
+    }
+    off[tid] = o;
+  }
+  __syncthreads();
+  float* vout = a.verts + (size_t)b * m.V * 3;
+  for (int v = tid; v < m.V; v += kThreads) {
+    float p[3];
+    skin_vertex(m, s, v, p);
+    vout[3 * v + 0] = p[0] + off[0];
+    vout[3 * v + 1] = p[1] + off[1];
+    vout[3 * v + 2] = p[2] + off[2];
+  }
+  if (a.joints) {
+    float* jout = a.joints + (size_t)b * (NJ + m.NT) * 3;
+    for (int i = tid; i < (NJ + m.NT) * 3; i += kThreads) {
+      const int k = i / 3, c = i % 3, src = m.joint_order[k];
+      const float p = src < NJ ? s.G[12 * src + c * 4 + 3] : tips[3 * (src - NJ) + c];
+      jout[i] = p + off[c];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) mano_bwd_kernel(HfrHandModel m, HfrManoBwdArgs a, int pose_dim) {
+  extern __shared__ __align__(16) float smem[];
+  const ManoSmem s = carve(smem, m, true);
+  const int b = blockIdx.x, tid = threadIdx.x, NJ = m.NJ, V = m.V, NJO = NJ + m.NT;
+  const int lane = tid & 31, warp = tid >> 5, nwarps = kThreads / 32;
+  const int NK = m.NS + 9 * (NJ - 1), NPOSE = 3 * (NJ - 1);
+  const float* pose = a.pose + (size_t)b * pose_dim;
+  mano_setup(m, s, pose, a.betas ? a.betas + (size_t)b * m.NS : nullptr);
+  mano_blend(m, s);
+  // backward-only shared arrays live in the tail of the dynamic allocation (after gv)
+  float* gA = s.gv + m.C3;        // NJ*12, later reused as gG
+  float* gJ = gA + 12 * NJ;       // NJ*3
+  float* gR = gJ + 3 * NJ;        // NJ*9
+  float* gcoef = gR + 9 * NJ;     // NK
+  float* gfull = gcoef + ((NK + 3) & ~3);  // 3*NJ
+  float* red = s.misc;            // 8 warps * 3 partials, then [24..26] = total
+  // ---- load upstream grads, fold tips / centre ------------------------------------------
+  const float* gv_in = a.g_verts + (size_t)b * V * 3;
+  float sx = 0.f, sy = 0.f, sz = 0.f;
+  for (int i = tid; i < m.C3; i += kThreads) {
+    const float g = i < 3 * V ? gv_in[i] : 0.0f;
+    s.gv[i] = g;
+    const int c = i % 3;
+    if (c == 0) sx += g; else if (c == 1) sy += g; else sz += g;
+  }
+  const float* gj_in = a.g_joints ? a.g_joints + (size_t)b * NJO * 3 : nullptr;
+  if (gj_in) {
+    for (int i = tid; i < NJO * 3; i += kThreads) {
+      const float g = gj_in[i];
+      const int c = i % 3;
+      if (c == 0) sx += g; else if (c == 1) sy += g; else sz += g;
+    }
+  }
+  sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
+  if (lane == 0) { red[warp * 3] = sx; red[warp * 3 + 1] = sy; red[warp * 3 + 2] = sz; }
+  for (int i = tid; i < 12 * NJ + 3 * NJ; i += kThreads) gA[i] = 0.0f;  // gA and gJ
+  __syncthreads();
+  if (tid < 3) {
+    float t = 0.f;
+    for (int w = 0; w < nwarps; ++w) t += red[w * 3 + tid];
+    red[24 + tid] = t;
+  }
+  __syncthreads();
+  // gGt: translation-column grads that bypass A (chain joint outputs, centre)
+  float* gGt = s.misc + 28;  // NJ*3 <= 36... keep NJ<=12? no: use gfull region temporarily (3*NJ floats)
+  gGt = gfull;
+  for (int i = tid; i < 3 * NJ; i += kThreads) gGt[i] = 0.0f;
+  __syncthreads();
+  if (tid == 0) {
+    if (gj_in) {
+      for (int k = 0; k < NJO; ++k) {
+        const int src = m.joint_order[k];
+        for (int c = 0; c < 3; ++c) {
+          if (src < NJ) gGt[3 * src + c] += gj_in[3 * k + c];
+          else s.gv[3 * m.tip_verts[src - NJ] + c] += gj_in[3 * k + c];
+        }
+      }
+    }
+    if (a.trans) {
+      if (a.g_trans) for (int c = 0; c < 3; ++c) a.g_trans[(size_t)b * 3 + c] = red[24 + c];
+    } else if (m.center_joint >= 0) {
+      const int src = m.joint_order[m.center_joint];
+      for (int c = 0; c < 3; ++c) {
+        if (src < NJ) gGt[3 * src + c] -= red[24 + c];
+        else s.gv[3 * m.tip_verts[src - NJ] + c] -= red[24 + c];
+      }
+    }
+  }
+  __syncthreads();
+  // ---- gA[j] = sum_v w_vj * g_v (x) [vp;1]   (warp per joint, lanes stride over vertices)
+  for (int j = warp; j < NJ; j += nwarps) {
+    float acc[12];
+#pragma unroll
+    for (int e = 0; e < 12; ++e) acc[e] = 0.0f;
+    for (int v = lane; v < V; v += 32) {
+      float w = 0.0f;
+      for (int i = 0; i < m.NW; ++i)
+        if (m.skin_idx[i * V + v] == j) w += m.skin_w[i * V + v];
+      if (w != 0.0f) {
+        const float x = s.vp[3 * v], y = s.vp[3 * v + 1], z = s.vp[3 * v + 2];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const float g = w * s.gv[3 * v + r];
+          acc[r * 4 + 0] += g * x; acc[r * 4 + 1] += g * y; acc[r * 4 + 2] += g * z; acc[r * 4 + 3] += g;
+        }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 12; ++e) acc[e] = warp_sum(acc[e]);
+    if (lane == 0) {
+#pragma unroll
+      for (int e = 0; e < 12; ++e) gA[12 * j + e] = acc[e];
+    }
+  }
+  __syncthreads();
+  // ---- g_vp = T_rot^T g_v, in place
+  for (int v = tid; v < V; v += kThreads) {
+    float T[12];
+    skin_matrix(m, s.A, v, T);
+    const float g0 = s.gv[3 * v], g1 = s.gv[3 * v + 1], g2 = s.gv[3 * v + 2];
+    s.gv[3 * v + 0] = T[0] * g0 + T[4] * g1 + T[8] * g2;
+    s.gv[3 * v + 1] = T[1] * g0 + T[5] * g1 + T[9] * g2;
+    s.gv[3 * v + 2] = T[2] * g0 + T[6] * g1 + T[10] * g2;
+  }
+  __syncthreads();
+  // ---- transposed blend contraction: g_coef[k] = <dirs_k, g_vp>  (warp per coefficient row)
+  {
+    const int C4 = m.C3 >> 2;
+    const float4* __restrict__ dirs4 = reinterpret_cast<const float4*>(m.dirs);
+    const float4* gv4 = reinterpret_cast<const float4*>(s.gv);
+    for (int k = warp; k < NK; k += nwarps) {
+      float acc = 0.0f;
+      const float4* row = dirs4 + (size_t)k * C4;
+      for (int c4 = lane; c4 < C4; c4 += 32) {
+        const float4 d = __ldg(row + c4);
+        const float4 g = gv4[c4];
+        acc += d.x * g.x + d.y * g.y + d.z * g.z + d.w * g.w;
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) gcoef[k] = acc;
+    }
+  }
+  __syncthreads();
+  // ---- chain backward (serial over joints, leaves to root)
+  if (tid == 0) {
+    float* gG = gA;  // converted in place: gG.R = gA.R - gA.t (x) J ; gG.t = gA.t (+ direct joint grads)
+    for (int j = 0; j < NJ; ++j) {
+      const float* G = s.G + 12 * j;
+      const float* Jj = s.J + 3 * j;
+      for (int r = 0; r < 3; ++r) {
+        const float gt = gA[12 * j + r * 4 + 3];
+        for (int k = 0; k < 3; ++k) {
+          gJ[3 * j + k] -= G[r * 4 + k] * gt;
+          gG[12 * j + r * 4 + k] -= gt * Jj[k];
+        }
+        gG[12 * j + r * 4 + 3] = gt + gGt[3 * j + r];
+      }
+    }
+    for (int j = NJ - 1; j >= 0; --j) {
+      const int p = m.parents[j];
+      if (p >= 0) {
+        float tl[3] = {s.J[3 * j] - s.J[3 * p], s.J[3 * j + 1] - s.J[3 * p + 1], s.J[3 * j + 2] - s.J[3 * p + 2]};
+        float gtl[3];
+        hfr_rigid_compose_bwd(s.G + 12 * p, s.R + 9 * j, tl, gG + 12 * j, gG + 12 * p, gR + 9 * j, gtl);
+        for (int k = 0; k < 3; ++k) { gJ[3 * j + k] += gtl[k]; gJ[3 * p + k] -= gtl[k]; }
+      } else {
+        for (int r = 0; r < 3; ++r) {
+          for (int c = 0; c < 3; ++c) gR[9 * j + r * 3 + c] = gG[12 * j + r * 4 + c];
+          gJ[3 * j + r] += gG[12 * j + r * 4 + 3];
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // ---- Rodrigues backward (thread per joint) and shape grads
+  if (tid < NJ) {
+    float g[9];
+    for (int e = 0; e < 9; ++e) g[e] = gR[9 * tid + e] + (tid >= 1 ? gcoef[m.NS + 9 * (tid - 1) + e] : 0.0f);
+    float gvv[3];
+    hfr_rodrigues_bwd(s.full + 3 * tid, g, gvv);
+    __syncwarp();
+    // gfull aliases gGt, which thread 0 finished reading before the barrier above
+    gfull[3 * tid] = gvv[0]; gfull[3 * tid + 1] = gvv[1]; gfull[3 * tid + 2] = gvv[2];
+  }
+  if (a.g_betas && a.betas) {
+    for (int k = tid; k < m.NS; k += kThreads) {
+      float acc = gcoef[k];
+      for (int i = 0; i < 3 * NJ; ++i) acc += m.J_shapedirs[i * m.NS + k] * gJ[i];
+      a.g_betas[(size_t)b * m.NS + k] = acc;
+    }
+  }
+  __syncthreads();
+  float* gp = a.g_pose + (size_t)b * pose_dim;
+  if (tid < 3) gp[tid] = gfull[tid];
+  if (m.NPC > 0) {
+    for (int k = tid; k < m.NPC; k += kThreads) {
+      float acc = 0.0f;
+      for (int o = 0; o < NPOSE; ++o) acc += m.pca_comps[k * NPOSE + o] * gfull[3 + o];
+      gp[3 + k] = acc;
+    }
+  } else {
+    for (int o = tid; o < NPOSE; o += kThreads) gp[3 + o] = gfull[3 + o];
+  }
+}
+
+static int check_model(const HfrHandModel* m) {
+  HFR_CHECK_ARG(m && m->V > 0 && m->NJ >= 1 && m->NJ <= HFR_MAX_JOINTS, "hand model: bad V/NJ");
+  HFR_CHECK_ARG(m->NS >= 0 && m->NS <= 64 && m->NW >= 1 && m->NW <= 8 && m->NT >= 0 && m->NT <= 16,
+                "hand model: bad NS/NW/NT");
+  HFR_CHECK_ARG(m->C3 >= 3 * m->V && (m->C3 & 3) == 0, "hand model: C3 must be >= 3V and a multiple of 4");
+  HFR_CHECK_ARG(m->dirs && m->v_template && m->J_template && m->J_shapedirs && m->parents && m->skin_idx &&
+                    m->skin_w && m->joint_order,
+                "hand model: null constant pointer");
+  HFR_CHECK_ARG(m->NPC == 0 || m->pca_comps, "hand model: NPC>0 needs pca_comps");
+  return HFR_OK;
+}
+
+}  // namespace
+
+extern "C" int hfr_mano_forward(const HfrHandModel* m, const HfrManoFwdArgs* a, void* stream) {
+  if (int rc = check_model(m)) return rc;
+  HFR_CHECK_ARG(a && a->B >= 0 && a->pose && a->verts, "mano_forward: null argument");
+  if (a->B == 0) return HFR_OK;
+  const int pose_dim = 3 + (m->NPC > 0 ? m->NPC : 3 * (m->NJ - 1));
+  const size_t smem = mano_smem_bytes(*m, false);
+  HFR_CHECK_ARG(smem <= 227 * 1024, "mano_forward: model too large for shared memory (%zu B)", smem);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(mano_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  mano_fwd_kernel<<<a->B, kThreads, smem, (cudaStream_t)stream>>>(*m, *a, pose_dim);
+  HFR_CHECK_LAUNCH("mano_forward");
+  return HFR_OK;
+}
+
+extern "C" int hfr_mano_backward(const HfrHandModel* m, const HfrManoBwdArgs* a, void* stream) {
+  if (int rc = check_model(m)) return rc;
+  HFR_CHECK_ARG(a && a->B >= 0 && a->pose && a->g_verts && a->g_pose, "mano_backward: null argument");
+  if (a->B == 0) return HFR_OK;
+  const int pose_dim = 3 + (m->NPC > 0 ? m->NPC : 3 * (m->NJ - 1));
+  const int NK = m->NS + 9 * (m->NJ - 1);
+  const size_t extra = (size_t)(12 * m->NJ + 3 * m->NJ + 9 * m->NJ + ((NK + 3) & ~3) + 3 * m->NJ + 8) * sizeof(float);
+  const size_t smem = mano_smem_bytes(*m, true) + extra;
+  HFR_CHECK_ARG(smem <= 227 * 1024, "mano_backward: model too large for shared memory (%zu B)", smem);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(mano_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  mano_bwd_kernel<<<a->B, kThreads, smem, (cudaStream_t)stream>>>(*m, *a, pose_dim);
+  HFR_CHECK_LAUNCH("mano_backward");
+  return HFR_OK;
+}

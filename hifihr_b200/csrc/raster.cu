@@ -1,0 +1,140 @@
+// Mesh rasterizer for sm_100a: face setup, tile-binned forward (Fragments), backward.
+//
+// Replaces pytorch3d._C.rasterize_meshes / rasterize_meshes_backward as reached from
+// MeshRasterizer.forward (models_res_nimble.py:208) — semantics in SURVEY.md Appendix A.2-A.5.
+// Outputs are bit-identical to the scalar CPU oracle (oracle/raster_naive.c): same fp32
+// operation order, no FMA contraction in the coverage / depth / distance math.
+#include "common.cuh"
+#include "raster_tile.cuh"
+
+namespace hfr {
+
+// One thread per packed face: conservative range of 16x16 tiles its dilated bbox can touch.
+__global__ void __launch_bounds__(256) raster_setup_kernel(HfrRasterArgs a, uint32_t* __restrict__ ranges) {
+  const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= a.Ftot) return;
+  float v[9];
+#pragma unroll
+  for (int e = 0; e < 9; ++e) v[e] = __ldg(a.face_verts + f * 9 + e);
+  uint32_t out = kEmptyRange;
+  if (hfr_face_valid(v, a.cull_backfaces)) {
+    const float r = sqrtf(a.blur_radius);
+    const float xmin = hfr_min3(v[0], v[3], v[6]) - r, xmax = hfr_max3(v[0], v[3], v[6]) + r;
+    const float ymin = hfr_min3(v[1], v[4], v[7]) - r, ymax = hfr_max3(v[1], v[4], v[7]) + r;
+    // invert hfr_pix_to_ndc: i = ((x + off) * S1 - off) / range ; pixel column = S1 - 1 - i
+    const float rx = a.W > a.H ? 2.0f * a.W / a.H : 2.0f, ry = a.H > a.W ? 2.0f * a.H / a.W : 2.0f;
+    const float ox = 0.5f * rx, oy = 0.5f * ry;
+    const float ix_hi = ((xmax + ox) * a.W - ox) / rx, ix_lo = ((xmin + ox) * a.W - ox) / rx;
+    const float iy_hi = ((ymax + oy) * a.H - oy) / ry, iy_lo = ((ymin + oy) * a.H - oy) / ry;
+    // one extra pixel of slack on each side absorbs the rounding of this inverse map
+    float cx0 = floorf((float)(a.W - 1) - ix_hi) - 1.0f, cx1 = ceilf((float)(a.W - 1) - ix_lo) + 1.0f;
+    float cy0 = floorf((float)(a.H - 1) - iy_hi) - 1.0f, cy1 = ceilf((float)(a.H - 1) - iy_lo) + 1.0f;
+    if (cx1 >= 0.0f && cy1 >= 0.0f && cx0 <= (float)(a.W - 1) && cy0 <= (float)(a.H - 1) && cx0 == cx0 &&
+        cx1 == cx1 && cy0 == cy0 && cy1 == cy1) {
+      const int x0 = (int)fmaxf(cx0, 0.0f), x1 = (int)fminf(cx1, (float)(a.W - 1));
+      const int y0 = (int)fmaxf(cy0, 0.0f), y1 = (int)fminf(cy1, (float)(a.H - 1));
+      out = pack_tile_range(x0 / kTileW, x1 / kTileW, y0 / kTileH, y1 / kTileH);
+    }
+  }
+  ranges[f] = out;
+}
+
+template <int KMAX>
+__global__ void __launch_bounds__(kRasterThreads) raster_fwd_kernel(HfrRasterArgs a, const uint32_t* __restrict__ ranges) {
+  __shared__ RasterSmem sm;
+  const PixelCtx c = make_pixel_ctx(a.H, a.W);
+  TopK<KMAX> top;
+  raster_tile<KMAX>(a, ranges, sm, c.n, c.tx, c.ty, c.xf, c.yf, c.pix_active, c.warp_active, c.wx_lo, c.wx_hi,
+                    c.wy_lo, c.wy_hi, top);
+  if (c.pix_active) {
+    int64_t id[KMAX];
+    float z[KMAX], d[KMAX], b[KMAX * 3];
+    compute_fragments<KMAX>(a, c.xf, c.yf, top, id, z, d, b);
+    store_fragments<KMAX>(a, ((size_t)c.n * a.H + c.yi) * a.W + c.xi, id, z, d, b);
+  }
+}
+
+// Backward: one thread per pixel, K fragments each; 9 reductions per fragment into the packed
+// per-face gradient (the upstream contract).  The fused path (shade.cu) scatters per vertex.
+__global__ void __launch_bounds__(256) raster_bwd_kernel(HfrRasterBwdArgs a) {
+  const size_t P = (size_t)a.N * a.H * a.W;
+  for (size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x; pix < P; pix += (size_t)gridDim.x * blockDim.x) {
+    const int xi = (int)(pix % a.W), yi = (int)((pix / a.W) % a.H);
+    const float xf = hfr_pix_to_ndc(a.W - 1 - xi, a.W, a.H), yf = hfr_pix_to_ndc(a.H - 1 - yi, a.H, a.W);
+    for (int k = 0; k < a.K; ++k) {
+      const int64_t f = a.pix_to_face[pix * a.K + k];
+      if (f < 0) continue;
+      float v[9];
+#pragma unroll
+      for (int e = 0; e < 9; ++e) v[e] = __ldg(a.face_verts + f * 9 + e);
+      float gb[3] = {0.f, 0.f, 0.f};
+      if (a.g_bary) { gb[0] = a.g_bary[(pix * a.K + k) * 3]; gb[1] = a.g_bary[(pix * a.K + k) * 3 + 1]; gb[2] = a.g_bary[(pix * a.K + k) * 3 + 2]; }
+      const float gz = a.g_zbuf ? a.g_zbuf[pix * a.K + k] : 0.0f;
+      const float gd = a.g_dists ? a.g_dists[pix * a.K + k] : 0.0f;
+      float gv[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      hfr_raster_eval_bwd(xf, yf, v, a.perspective_correct, a.clip_barycentric, gb, gz, gd, gv);
+#pragma unroll
+      for (int e = 0; e < 9; ++e)
+        if (gv[e] != 0.0f) atomicAdd(a.g_face_verts + f * 9 + e, gv[e]);
+    }
+  }
+}
+
+int check_raster(const HfrRasterArgs* a, const char* who) {
+  HFR_CHECK_ARG(a && a->N >= 0 && a->H > 0 && a->W > 0, "%s: bad image size", who);
+  HFR_CHECK_ARG(a->K >= 1 && a->K <= HFR_MAX_K, "%s: faces_per_pixel must be in [1,%d], got %d", who, HFR_MAX_K, a->K);
+  HFR_CHECK_ARG((a->W + kTileW - 1) / kTileW <= 255 && (a->H + kTileH - 1) / kTileH <= 255,
+                "%s: image side above %d px unsupported", who, 255 * kTileW);
+  HFR_CHECK_ARG(a->Ftot >= 0 && a->Ftot < (1ll << 31), "%s: bad face count", who);
+  HFR_CHECK_ARG(a->blur_radius >= 0.0f, "%s: blur_radius must be >= 0", who);
+  HFR_CHECK_ARG(a->N == 0 || (a->face_verts && a->mesh_first && a->mesh_nfaces && a->pix_to_face && a->zbuf &&
+                               a->bary && a->dists && a->workspace),
+                "%s: null pointer", who);
+  return HFR_OK;
+}
+
+int launch_raster_setup(const HfrRasterArgs& a, uint32_t* ranges, cudaStream_t s) {
+  if (a.Ftot > 0) {
+    raster_setup_kernel<<<(unsigned)((a.Ftot + 255) / 256), 256, 0, s>>>(a, ranges);
+    HFR_CHECK_LAUNCH("raster_setup");
+  }
+  return HFR_OK;
+}
+
+template <int KMAX>
+static void launch_fwd(const HfrRasterArgs& a, const uint32_t* ranges, cudaStream_t s) {
+  dim3 grid((a.W + kTileW - 1) / kTileW, (a.H + kTileH - 1) / kTileH, a.N);
+  raster_fwd_kernel<KMAX><<<grid, kRasterThreads, 0, s>>>(a, ranges);
+}
+
+}  // namespace hfr
+
+extern "C" int64_t hfr_raster_workspace_bytes(int64_t Ftot) { return (Ftot + 64) * 4; }
+
+extern "C" int hfr_raster_forward(const HfrRasterArgs* a, void* stream) {
+  using namespace hfr;
+  if (int rc = check_raster(a, "raster_forward")) return rc;
+  if (a->N == 0) return HFR_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  uint32_t* ranges = reinterpret_cast<uint32_t*>(a->workspace);
+  if (int rc = launch_raster_setup(*a, ranges, s)) return rc;
+  if (a->K == 1) launch_fwd<1>(*a, ranges, s);
+  else if (a->K == 2) launch_fwd<2>(*a, ranges, s);
+  else if (a->K <= 4) launch_fwd<4>(*a, ranges, s);
+  else if (a->K <= 8) launch_fwd<8>(*a, ranges, s);
+  else launch_fwd<16>(*a, ranges, s);
+  HFR_CHECK_LAUNCH("raster_forward");
+  return HFR_OK;
+}
+
+extern "C" int hfr_raster_backward(const HfrRasterBwdArgs* a, void* stream) {
+  using namespace hfr;
+  HFR_CHECK_ARG(a && a->N >= 0 && a->H > 0 && a->W > 0 && a->K >= 1 && a->K <= HFR_MAX_K, "raster_backward: bad dims");
+  if (a->N == 0) return HFR_OK;
+  HFR_CHECK_ARG(a->face_verts && a->pix_to_face && a->g_face_verts, "raster_backward: null pointer");
+  const size_t P = (size_t)a->N * a->H * a->W;
+  const unsigned blocks = (unsigned)((P + 255) / 256 < 148u * 32u ? (P + 255) / 256 : 148u * 32u);
+  raster_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(*a);
+  HFR_CHECK_LAUNCH("raster_backward");
+  return HFR_OK;
+}

@@ -1,0 +1,85 @@
+// Device-side per-pixel shading: gather the face attributes of the K fragments of one pixel,
+// interpolate, sample the UV texture, light, blend.  Shared by the standalone shader kernels
+// (shade.cu) and the fused rasterize+shade forward (raster_shade.cu).
+#pragma once
+#include "shade_math.cuh"
+
+namespace hfr {
+
+struct FragGeom {        // per-fragment gathered attributes
+  int vid[3];            // vertex ids (within the mesh)
+  float X[9], Nv[9];     // view-space positions / vertex normals of the 3 corners
+  float uv[6];           // corner uvs
+};
+
+HFR_HD void gather_frag(const HfrShadeFwdArgs& a, int n, int fl, FragGeom& g) {
+  const int V = a.p.V;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int vid = HFR_LDG(a.faces + 3 * fl + i);
+    g.vid[i] = vid;
+    const float* __restrict__ x = a.verts_view + ((size_t)n * V + vid) * 3;
+    const float* __restrict__ nn = a.vnormals + ((size_t)n * V + vid) * 3;
+    g.X[3 * i] = HFR_LDG(x); g.X[3 * i + 1] = HFR_LDG(x + 1); g.X[3 * i + 2] = HFR_LDG(x + 2);
+    g.Nv[3 * i] = HFR_LDG(nn); g.Nv[3 * i + 1] = HFR_LDG(nn + 1); g.Nv[3 * i + 2] = HFR_LDG(nn + 2);
+    const int t = HFR_LDG(a.faces_uvs + 3 * fl + i);
+    g.uv[2 * i] = HFR_LDG(a.verts_uvs + 2 * t); g.uv[2 * i + 1] = HFR_LDG(a.verts_uvs + 2 * t + 1);
+  }
+}
+
+HFR_HD void interp3(const float* bc, const float* A, float* o) {
+#pragma unroll
+  for (int c = 0; c < 3; ++c) o[c] = bc[0] * A[c] + bc[1] * A[3 + c] + bc[2] * A[6 + c];
+}
+
+HFR_HD void light_dir_hat(const HfrShadeFwdArgs& a, int n, float* dhat, float* len) {
+  const float d[3] = {a.light_dir[3 * n], a.light_dir[3 * n + 1], a.light_dir[3 * n + 2]};
+  hfr_normalize_eps(d, dhat, len);
+}
+
+// colour of one fragment (Phong x UV texel).  `tap` and `ctx` are kept for the backward.
+HFR_HD void shade_fragment(const HfrShadeFwdArgs& a, int n, const FragGeom& g, const float* bc,
+                                               const float* dhat, const float* lcol, float* color, HfrTexTap* tap,
+                                               HfrPhongCtx* ctx, float* texel) {
+  float P[3], Nn[3];
+  interp3(bc, g.X, P);
+  interp3(bc, g.Nv, Nn);
+  const float u = bc[0] * g.uv[0] + bc[1] * g.uv[2] + bc[2] * g.uv[4];
+  const float v = bc[0] * g.uv[1] + bc[1] * g.uv[3] + bc[2] * g.uv[5];
+  hfr_tex_tap(a.p.tex_h, a.p.tex_w, u, v, tap);
+  const float* tex = a.texture + (a.p.tex_n == 1 ? 0 : (size_t)n * a.p.tex_h * a.p.tex_w * 3);
+  hfr_tex_fetch(tex, tap, texel);
+  hfr_phong_fwd(a.p, P, Nn, dhat, lcol, texel, color, ctx);
+}
+
+// Full forward for one pixel given its K fragments.
+template <int KMAX>
+HFR_HD void shade_pixel(const HfrShadeFwdArgs& a, int n, const int64_t* id, const float* z,
+                                            const float* d, const float* b, float* rgba) {
+  const int K = a.p.K;
+  bool valid[KMAX];
+  float colors[KMAX * 3];
+  float dhat[3], dlen;
+  float lcol[3] = {0.f, 0.f, 0.f};
+  const bool phong = a.p.shade == HFR_SHADE_PHONG_UV;
+  if (phong) {
+    light_dir_hat(a, n, dhat, &dlen);
+    lcol[0] = a.light_color[3 * n]; lcol[1] = a.light_color[3 * n + 1]; lcol[2] = a.light_color[3 * n + 2];
+  }
+  // hard blending only looks at the nearest fragment
+  const int kshade = a.p.blend == HFR_BLEND_SOFTMAX ? K : 1;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    valid[k] = k < K && id[k] >= 0;
+    colors[3 * k] = colors[3 * k + 1] = colors[3 * k + 2] = 1.0f;
+    if (phong && valid[k] && k < kshade) {
+      FragGeom g;
+      gather_frag(a, n, (int)(id[k] - (int64_t)n * a.p.F), g);
+      HfrTexTap tap; HfrPhongCtx ctx; float texel[3];
+      shade_fragment(a, n, g, b + 3 * k, dhat, lcol, colors + 3 * k, &tap, &ctx, texel);
+    }
+  }
+  hfr_blend_fwd<KMAX>(a.p, K, valid, z, d, colors, rgba);
+}
+
+}  // namespace hfr

@@ -1,0 +1,303 @@
+/* hifihr_b200 — C-ABI of the B200-native hand-render hot path.
+ *
+ * Plain pointers and sizes only (no torch types).  All pointers are DEVICE pointers
+ * unless a field says "host".  Every entry point enqueues work on `stream`
+ * (a cudaStream_t passed as void*), never allocates, never synchronises, and
+ * returns 0 on success or an HFR_E* code; hfr_last_error() gives the message of
+ * the calling thread's last failure.
+ *
+ * The reference has no FFI of its own (it is pure Python over PyTorch and
+ * PyTorch3D).  Each entry point cites the reference call / upstream native
+ * function it replaces; INTEGRATION.md shows the ctypes binding a maintainer adds.
+ */
+#ifndef HIFIHR_B200_H
+#define HIFIHR_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HFR_OK 0
+#define HFR_EINVAL 1    /* bad argument (shape, K out of range, null pointer)      */
+#define HFR_ECUDA 2     /* CUDA runtime error at launch                            */
+#define HFR_EUNSUPPORTED 3
+#define HFR_ABI_VERSION 1
+
+#define HFR_MAX_JOINTS 32
+#define HFR_MAX_K 16
+
+const char* hfr_last_error(void);
+int hfr_abi_version(void);
+/* 1 when a CUDA device of compute capability 10.x is current; else 0. */
+int hfr_device_ok(void);
+
+/* ------------------------------------------------------------------ articulated hand model
+ * Constants of an LBS hand model (MANO: utils/my_mano.py:283-313 buffers; the
+ * NIMBLE-shaped stand-in uses the same struct).  Built once by the host. */
+typedef struct HfrHandModel {
+  int32_t V;             /* vertices (778)                                               */
+  int32_t NJ;            /* chain joints (16), joint 0 is the root                       */
+  int32_t NS;            /* shape coefficients (10)                                      */
+  int32_t NPC;           /* pose PCA coefficients consumed after the 3 root values (45); 0 = no PCA */
+  int32_t NW;            /* skinning influences stored per vertex (<= 8)                 */
+  int32_t NT;            /* tip vertices appended to the chain joints (5)                */
+  int32_t center_joint;  /* index into the OUTPUT joint order to centre on (9), -1 = none */
+  int32_t C3;            /* row pitch of `dirs` in floats (>= 3V, multiple of 4)          */
+  const float* dirs;       /* (NS + 9(NJ-1), C3): shape then pose blend basis, coefficient-major */
+  const float* v_template; /* (3V)                                                        */
+  const float* J_template; /* (NJ,3)   = J_regressor @ v_template                         */
+  const float* J_shapedirs;/* (NJ,3,NS)= J_regressor @ shapedirs                          */
+  const float* pca_comps;  /* (NPC, 3(NJ-1)) selected components, or NULL                 */
+  const float* pose_mean;  /* (3(NJ-1)) hands_mean, or NULL                              */
+  const int32_t* parents;  /* (NJ) parent joint, -1 for the root                          */
+  const int32_t* skin_idx; /* (NW, V) joint index per influence                           */
+  const float* skin_w;     /* (NW, V) weight per influence (0 padded)                     */
+  const int32_t* tip_verts;/* (NT)                                                        */
+  const int32_t* joint_order; /* (NJ+NT) output joint k = chain∪tips[joint_order[k]]     */
+} HfrHandModel;
+
+/* Replaces ManoLayer.forward (utils/my_mano.py:315-483) / MyMANOLayer.forward (:39-54).
+ * pose (B, 3+NPC) [or (B, 3*NJ) when NPC==0], betas (B,NS) or NULL (mean shape);
+ * trans (B,3) or NULL (then centre on center_joint).  verts (B,V,3), joints (B,NJ+NT,3). */
+typedef struct HfrManoFwdArgs {
+  int32_t B;
+  const float* pose;
+  const float* betas;
+  const float* trans;
+  float* verts;
+  float* joints;
+} HfrManoFwdArgs;
+int hfr_mano_forward(const HfrHandModel* m, const HfrManoFwdArgs* a, void* stream);
+
+/* Backward of the above (autograd of my_mano.py:315-483).  g_joints may be NULL.
+ * Outputs g_pose (B,3+NPC), g_betas (B,NS) (may be NULL), g_trans (B,3) (may be NULL). */
+typedef struct HfrManoBwdArgs {
+  int32_t B;
+  const float* pose;
+  const float* betas;
+  const float* trans;
+  const float* g_verts;
+  const float* g_joints;
+  float* g_pose;
+  float* g_betas;
+  float* g_trans;
+} HfrManoBwdArgs;
+int hfr_mano_backward(const HfrHandModel* m, const HfrManoBwdArgs* a, void* stream);
+
+/* ------------------------------------------------------------------ per-sample geometry
+ * Joint regression from POSED verts + FreiHAND reorder (xyz_from_vertice,
+ * utils/Freihand_GNN_mano/Freihand_trainer_mano_fullsup.py:175-215), root shift
+ * (models_res_nimble.py:159-166, 203-205), NDC projection (PerspectiveCameras + the
+ * z overwrite of MeshRasterizer.transform; intrinsics from :228-235) and area-weighted
+ * vertex normals (Meshes.verts_normals_packed).  Topology is shared by the batch. */
+typedef struct HfrTopology {
+  int32_t V, F;
+  const int32_t* faces;       /* (F,3) vertex ids                                       */
+  const int32_t* vf_ptr;      /* (V+1) CSR: incident (face*4+corner) entries per vertex  */
+  const int32_t* vf_idx;      /* (3F)                                                    */
+  /* sparse joint regressor on posed verts; NULL/0 when unused */
+  int32_t NJR;                /* regressed joints (16)                                   */
+  int32_t NOUT;               /* output joints (21)                                      */
+  const int32_t* jr_ptr;      /* (NJR+1) CSR over joints                                 */
+  const int32_t* jr_col;      /* (nnz) vertex ids                                        */
+  const float* jr_val;        /* (nnz)                                                   */
+  const int32_t* vj_ptr;      /* (V+1) CSC view for the backward                         */
+  const int32_t* vj_row;      /* (nnz) joint ids                                         */
+  const float* vj_val;        /* (nnz)                                                   */
+  const int32_t* out_src;     /* (NOUT) >=0: regressed joint id; <0: -(vertex id)-1      */
+} HfrTopology;
+
+typedef struct HfrGeomFwdArgs {
+  int32_t B;
+  int32_t root_out;           /* output joint used as predicted root (9); -1 = no joints / no shift */
+  const float* verts;         /* (B,V,3) hand-layer verts                                */
+  const float* root_xyz;      /* (B,3) GT root in camera frame, or NULL                  */
+  const float* focal;         /* (B,2) NDC focal as given to the camera (reference: -fcl) */
+  const float* prp;           /* (B,2) NDC principal point                               */
+  float* joints;              /* (B,NOUT,3) root-relative joints, or NULL                */
+  float* verts_rel;           /* (B,V,3) verts - pred_root, or NULL                      */
+  float* verts_view;          /* (B,V,3) verts - pred_root + root_xyz                    */
+  float* verts_ndc;           /* (B,V,3) x_ndc, y_ndc, view z; or NULL                   */
+  float* vnormals;            /* (B,V,3) or NULL                                         */
+} HfrGeomFwdArgs;
+int hfr_geom_forward(const HfrTopology* t, const HfrGeomFwdArgs* a, void* stream);
+
+typedef struct HfrGeomBwdArgs {
+  int32_t B;
+  int32_t root_out;
+  const float* verts;         /* forward input                                           */
+  const float* root_xyz;
+  const float* focal;
+  const float* prp;
+  const float* g_joints;      /* any of the g_* inputs may be NULL                       */
+  const float* g_verts_rel;
+  const float* g_verts_view;
+  const float* g_verts_ndc;
+  const float* g_vnormals;
+  float* g_verts;             /* (B,V,3)                                                 */
+} HfrGeomBwdArgs;
+int hfr_geom_backward(const HfrTopology* t, const HfrGeomBwdArgs* a, void* stream);
+
+/* ------------------------------------------------------------------ rasterizer
+ * Replaces pytorch3d._C.rasterize_meshes / rasterize_meshes_backward as reached from
+ * MeshRasterizer.forward (models_res_nimble.py:208).  Packed face_verts (Ftot,3,3) in
+ * NDC with view-space z; outputs are the four Fragments tensors, -1 filled.
+ * K <= HFR_MAX_K.  `workspace` needs hfr_raster_workspace_bytes(Ftot) bytes. */
+typedef struct HfrRasterArgs {
+  int32_t N, H, W, K;
+  int64_t Ftot;
+  const float* face_verts;          /* (Ftot,3,3)                                         */
+  const int64_t* mesh_first;        /* (N) first packed face of each mesh                 */
+  const int64_t* mesh_nfaces;       /* (N)                                                */
+  float blur_radius;
+  int32_t perspective_correct, clip_barycentric, cull_backfaces;
+  int64_t* pix_to_face;             /* (N,H,W,K)                                          */
+  float* zbuf;                      /* (N,H,W,K)                                          */
+  float* bary;                      /* (N,H,W,K,3)                                        */
+  float* dists;                     /* (N,H,W,K)                                          */
+  void* workspace;
+} HfrRasterArgs;
+int64_t hfr_raster_workspace_bytes(int64_t Ftot);
+int hfr_raster_forward(const HfrRasterArgs* a, void* stream);
+
+typedef struct HfrRasterBwdArgs {
+  int32_t N, H, W, K;
+  int64_t Ftot;
+  const float* face_verts;
+  const int64_t* pix_to_face;
+  const float* g_zbuf;              /* (N,H,W,K)   may be NULL                            */
+  const float* g_bary;              /* (N,H,W,K,3) may be NULL                            */
+  const float* g_dists;             /* (N,H,W,K)   may be NULL                            */
+  float blur_radius;
+  int32_t perspective_correct, clip_barycentric;
+  float* g_face_verts;              /* (Ftot,3,3), ACCUMULATED into (caller zeroes)       */
+} HfrRasterBwdArgs;
+int hfr_raster_backward(const HfrRasterBwdArgs* a, void* stream);
+
+/* ------------------------------------------------------------------ shading + blending
+ * Replaces HardPhongShader / SoftPhongShader / SoftSilhouetteShader forward (+backward):
+ * TexturesUV.sample_textures, interpolate_face_attributes, phong_shading,
+ * DirectionalLights, Materials and hard_rgb_blend / sigmoid_alpha_blend /
+ * softmax_rgb_blend (reference construction models_res_nimble.py:79-96, 187-190). */
+#define HFR_BLEND_HARD 0
+#define HFR_BLEND_SIGMOID_ALPHA 1   /* SoftSilhouetteShader (colour = ones unless shading on) */
+#define HFR_BLEND_SOFTMAX 2
+#define HFR_SHADE_ONES 0            /* silhouette shader: colours are 1                   */
+#define HFR_SHADE_PHONG_UV 1        /* Phong lighting x UV texture                        */
+
+typedef struct HfrShadeParams {
+  int32_t N, H, W, K;
+  int32_t F, V;                     /* per-mesh faces / verts (shared topology)            */
+  int32_t blend, shade;
+  float sigma, gamma, znear, zfar;
+  float background[3];
+  float light_ambient[3], light_specular[3];
+  float mat_ambient[3], mat_diffuse[3], mat_specular[3];
+  float shininess;
+  int32_t tex_n, tex_h, tex_w;      /* texture maps (tex_n = 1 shared, or N)               */
+  int32_t VT;                       /* number of uv vertices                               */
+} HfrShadeParams;
+
+typedef struct HfrShadeFwdArgs {
+  HfrShadeParams p;
+  const int64_t* pix_to_face; const float* zbuf; const float* bary; const float* dists;
+  const int32_t* faces;             /* (F,3)                                               */
+  const float* verts_view;          /* (N,V,3)                                             */
+  const float* vnormals;            /* (N,V,3)                                             */
+  const int32_t* faces_uvs;         /* (F,3)                                               */
+  const float* verts_uvs;           /* (VT,2)                                              */
+  const float* texture;             /* (tex_n,tex_h,tex_w,3)                               */
+  const float* light_dir;           /* (N,3)                                               */
+  const float* light_color;         /* (N,3) diffuse colour                                */
+  float* image;                     /* (N,H,W,4)                                           */
+} HfrShadeFwdArgs;
+int hfr_shade_forward(const HfrShadeFwdArgs* a, void* stream);
+
+typedef struct HfrShadeBwdArgs {
+  HfrShadeFwdArgs f;                /* forward inputs (image unused)                       */
+  const float* g_image;             /* (N,H,W,4)                                           */
+  /* dense per-fragment grads for the modular (autograd) path; any may be NULL */
+  float* g_zbuf; float* g_bary; float* g_dists;
+  /* fused path: when g_verts_ndc != NULL the rasterizer backward is applied in the same
+   * kernel and accumulated per vertex (needs face_verts_ndc = verts_ndc, (N,V,3)). */
+  const float* verts_ndc; float* g_verts_ndc;
+  float blur_radius; int32_t perspective_correct, clip_barycentric;
+  /* accumulated (caller zeroes) */
+  float* g_verts_view;              /* (N,V,3)                                             */
+  float* g_vnormals;                /* (N,V,3)                                             */
+  float* g_texture;                 /* (tex_n,tex_h,tex_w,3)                               */
+  float* g_light_dir;               /* (N,3)                                               */
+  float* g_light_color;             /* (N,3)                                               */
+} HfrShadeBwdArgs;
+int hfr_shade_backward(const HfrShadeBwdArgs* a, void* stream);
+
+/* Fused rasterize + shade forward: writes Fragments AND the image in one pass. */
+typedef struct HfrRasterShadeArgs {
+  HfrRasterArgs r;
+  HfrShadeFwdArgs s;                /* its Fragments pointers are ignored (taken from r)   */
+} HfrRasterShadeArgs;
+int hfr_raster_shade_forward(const HfrRasterShadeArgs* a, void* stream);
+
+/* ------------------------------------------------------------------ SSAA pooling + output split
+ * models_res_nimble.py:210-220: NHWC->NCHW, avg_pool2d(aa,aa), split RGB / alpha,
+ * optional in-place binarisation of alpha>0 to 255, maskRGBs = images*(re_sil>0). */
+typedef struct HfrPoolArgs {
+  int32_t N, H, W, aa;              /* H,W = OUTPUT size; input is (N,H*aa,W*aa,4)          */
+  int32_t binarize;
+  const float* image;               /* (N,H*aa,W*aa,4)                                     */
+  const float* images_in;           /* (N,3,H,W) network input for maskRGBs, or NULL       */
+  float* re_img;                    /* (N,3,H,W)                                           */
+  float* re_sil;                    /* (N,1,H,W)                                           */
+  float* mask_rgbs;                 /* (N,3,H,W) or NULL                                   */
+} HfrPoolArgs;
+int hfr_pool_forward(const HfrPoolArgs* a, void* stream);
+typedef struct HfrPoolBwdArgs {
+  int32_t N, H, W, aa;
+  int32_t binarize;                 /* when set, no gradient reaches alpha (reference mode) */
+  const float* g_re_img;            /* (N,3,H,W) or NULL                                   */
+  const float* g_re_sil;            /* (N,1,H,W) or NULL                                   */
+  float* g_image;                   /* (N,H*aa,W*aa,4)                                     */
+} HfrPoolBwdArgs;
+int hfr_pool_backward(const HfrPoolBwdArgs* a, void* stream);
+
+/* ------------------------------------------------------------------ losses
+ * losses.py:355-378 (texture, mrgb, ssim_tex), :399-408 (sil, iou) with
+ * utils/losses_util.py:366-378 and utils/pytorch_ssim/__init__.py:17-37.
+ * Two phases so the global means of `mrgb` are known before gradients are formed:
+ *   hfr_loss_forward : partial sums -> sums[HFR_LOSS_NSUMS + 2N] (caller zeroes), plus the
+ *                      SSIM derivative maps needed by the backward (dmaps, 9 floats/pixel).
+ *   hfr_loss_backward: reads sums (optionally all-reduced across ranks) -> g_re_img, g_re_sil.
+ * Layout: re_img (N,3,H,W), re_sil (N,1,H,W), imgs (N,3,H,W), seg (N,H,W) float. */
+#define HFR_LOSS_L1 0        /* sum |rim - target|            */
+#define HFR_LOSS_SUM_R 1     /* sum rim                       */
+#define HFR_LOSS_SUM_T 2     /* sum target                    */
+#define HFR_LOSS_SIL 3       /* sum |re_sil - seg|            */
+#define HFR_LOSS_SSIM 4      /* sum ssim_map                  */
+#define HFR_LOSS_NSUMS 8     /* then per-sample: mul[N], add[N] for IoU */
+typedef struct HfrLossArgs {
+  int32_t N, H, W;
+  float sil_scale;                  /* 255 (reference, binarised) or 1 (soft alpha)        */
+  int32_t want_ssim, want_grad;
+  const float* re_img; const float* re_sil; const float* imgs; const float* seg;
+  float* sums;                      /* (HFR_LOSS_NSUMS + 2N)                               */
+  const float* gauss;               /* DEVICE pointer to the 11 fp32 Gaussian taps, or NULL when !want_ssim */
+  float* dmaps;                     /* (N,9,H,W) or NULL when !want_ssim || !want_grad      */
+} HfrLossArgs;
+int hfr_loss_forward(const HfrLossArgs* a, void* stream);
+typedef struct HfrLossBwdArgs {
+  HfrLossArgs f;
+  /* DEVICE pointer to 5 floats: d(total)/d(term) for texture, mrgb, ssim_tex, sil, iou
+   * (lambda x upstream grad; kept on the device so the backward needs no host sync) */
+  const float* w;
+  const float* gauss;               /* DEVICE pointer to the 11 fp32 Gaussian taps (sigma 1.5) */
+  int64_t count_global;             /* N_global*3*H*W for the means (multi-GPU aware)      */
+  int32_t n_global;                 /* global batch for the IoU mean                       */
+  float* g_re_img; float* g_re_sil; /* (N,3,H,W), (N,1,H,W)                                */
+} HfrLossBwdArgs;
+int hfr_loss_backward(const HfrLossBwdArgs* a, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HIFIHR_B200_H */
