@@ -42,7 +42,8 @@ class HfrTopology(C.Structure):
 
 class HfrGeomFwdArgs(C.Structure):
     _fields_ = [("B", i32), ("root_out", i32), ("verts", vp), ("root_xyz", vp), ("focal", vp), ("prp", vp),
-                ("joints", vp), ("verts_rel", vp), ("verts_view", vp), ("verts_ndc", vp), ("vnormals", vp)]
+                ("joints", vp), ("verts_rel", vp), ("verts_view", vp), ("verts_ndc", vp), ("vnormals", vp),
+                ("face_verts", vp)]
 
 
 class HfrGeomBwdArgs(C.Structure):
@@ -100,7 +101,7 @@ class HfrPoolBwdArgs(C.Structure):
 
 
 class HfrLossArgs(C.Structure):
-    _fields_ = [("N", i32), ("H", i32), ("W", i32), ("sil_scale", f32), ("want_ssim", i32), ("want_grad", i32),
+    _fields_ = [("N", i32), ("H", i32), ("W", i32), ("sil_scale", f32), ("want_ssim", i32), ("want_grad", i32), ("nhwc", i32),
                 ("re_img", vp), ("re_sil", vp), ("imgs", vp), ("seg", vp), ("sums", vp), ("gauss", vp), ("dmaps", vp)]
 
 

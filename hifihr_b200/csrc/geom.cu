@@ -96,6 +96,21 @@ __global__ void __launch_bounds__(kThreads) geom_fwd_kernel(HfrTopology t, HfrGe
       a.verts_ndc[base + 3 * v + 1] = XDIV(XADD(XMUL(fy, Y), XMUL(py, Z)), Z);
       a.verts_ndc[base + 3 * v + 2] = Z;
     }
+    if (a.face_verts) {   // gather the packed (F,3,3) rasterizer input from shared memory
+      __syncthreads();    // everyone is done reading s_v (verts_rel above)
+      for (int v = tid; v < V; v += kThreads) {
+        const float X = s_view[3 * v], Y = s_view[3 * v + 1], Z = s_view[3 * v + 2];
+        s_v[3 * v + 0] = XDIV(XADD(XMUL(fx, X), XMUL(px, Z)), Z);
+        s_v[3 * v + 1] = XDIV(XADD(XMUL(fy, Y), XMUL(py, Z)), Z);
+        s_v[3 * v + 2] = Z;
+      }
+      __syncthreads();
+      float* fv = a.face_verts + (size_t)b * t.F * 9;
+      for (int i = tid; i < t.F * 9; i += kThreads) {
+        const int f = i / 9, e = i % 9;
+        fv[i] = s_v[3 * t.faces[3 * f + e / 3] + e % 3];
+      }
+    }
   }
   if (a.vnormals) {
     for (int v = tid; v < V; v += kThreads) {

@@ -60,6 +60,14 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(HfrPoolBwdArgs a) {
 // ------------------------------------------------------------------------------------- losses
 constexpr int kT = 16, kR = 5, kHalo = kT + 2 * kR;   // 16x16 tile, 11-tap window
 
+// rendered colour / silhouette of pixel p of sample n in either layout
+__device__ __forceinline__ float ld_rgb(const HfrLossArgs& a, int n, int c, size_t p, size_t hw) {
+  return a.nhwc ? a.re_img[((size_t)n * hw + p) * 4 + c] : a.re_img[((size_t)n * 3 + c) * hw + p];
+}
+__device__ __forceinline__ float ld_sil(const HfrLossArgs& a, int n, size_t p, size_t hw) {
+  return a.nhwc ? a.re_img[((size_t)n * hw + p) * 4 + 3] : a.re_sil[(size_t)n * hw + p];
+}
+
 __device__ __forceinline__ float block_sum(float v, float* scratch) {
   v = warp_sum(v);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -89,10 +97,10 @@ __global__ void __launch_bounds__(256) loss_fwd_kernel(HfrLossArgs a) {
   float l1 = 0.f, sr = 0.f, st = 0.f, sl = 0.f, ss = 0.f, mul = 0.f, add = 0.f;
   if (in) {
     const size_t p = (size_t)y * a.W + x;
-    const float sil = a.re_sil[n * hw + p], seg = a.seg[n * hw + p];
+    const float sil = ld_sil(a, n, p, hw), seg = a.seg[n * hw + p];
     const float s = sil / a.sil_scale;
     for (int c = 0; c < 3; ++c) {
-      const float rim = a.re_img[((size_t)n * 3 + c) * hw + p] * s;
+      const float rim = ld_rgb(a, n, c, p, hw) * s;
       const float tgt = seg * a.imgs[((size_t)n * 3 + c) * hw + p];
       l1 += fabsf(rim - tgt); sr += rim; st += tgt;
     }
@@ -107,7 +115,7 @@ __global__ void __launch_bounds__(256) loss_fwd_kernel(HfrLossArgs a) {
         float vx = 0.f, vy = 0.f;
         if (gx >= 0 && gx < a.W && gy >= 0 && gy < a.H) {
           const size_t p = (size_t)gy * a.W + gx;
-          vx = a.re_img[((size_t)n * 3 + c) * hw + p] * (a.re_sil[n * hw + p] / a.sil_scale);
+          vx = ld_rgb(a, n, c, p, hw) * (ld_sil(a, n, p, hw) / a.sil_scale);
           vy = a.seg[n * hw + p] * a.imgs[((size_t)n * 3 + c) * hw + p];
         }
         sx[hy][hx] = vx; sy[hy][hx] = vy;
@@ -178,7 +186,7 @@ __global__ void __launch_bounds__(256) loss_bwd_kernel(HfrLossBwdArgs b) {
   size_t p = 0;
   if (in) {
     p = (size_t)y * a.W + x;
-    sil = a.re_sil[n * hw + p]; seg = a.seg[n * hw + p];
+    sil = ld_sil(a, n, p, hw); seg = a.seg[n * hw + p];
     s = sil / a.sil_scale;
     const float d = sil - seg;
     gsil = w_sil * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) / ((float)b.n_global * (float)hw);
@@ -189,7 +197,7 @@ __global__ void __launch_bounds__(256) loss_bwd_kernel(HfrLossBwdArgs b) {
   for (int c = 0; c < 3; ++c) {
     float gS = 0.0f, xv = 0.f, yv = 0.f, rimg = 0.f;
     if (in) {
-      rimg = a.re_img[((size_t)n * 3 + c) * hw + p];
+      rimg = ld_rgb(a, n, c, p, hw);
       xv = rimg * s;
       yv = seg * a.imgs[((size_t)n * 3 + c) * hw + p];
     }
@@ -218,11 +226,15 @@ __global__ void __launch_bounds__(256) loss_bwd_kernel(HfrLossBwdArgs b) {
     if (in) {
       const float d = xv - yv;
       float grim = w_tex * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) / cnt + k_mrgb + w_ssim * (-1.0f / cnt) * gS;
-      b.g_re_img[((size_t)n * 3 + c) * hw + p] = grim * s;
+      if (a.nhwc) b.g_re_img[((size_t)n * hw + p) * 4 + c] = grim * s;
+      else b.g_re_img[((size_t)n * 3 + c) * hw + p] = grim * s;
       gsil += grim * rimg / a.sil_scale;
     }
   }
-  if (in) b.g_re_sil[n * hw + p] = gsil;
+  if (in) {
+    if (a.nhwc) b.g_re_img[((size_t)n * hw + p) * 4 + 3] = gsil;
+    else b.g_re_sil[n * hw + p] = gsil;
+  }
 }
 
 }  // namespace hfr
@@ -253,7 +265,7 @@ extern "C" int hfr_loss_forward(const HfrLossArgs* a, void* stream) {
   using namespace hfr;
   HFR_CHECK_ARG(a && a->N >= 0 && a->H > 0 && a->W > 0 && a->sil_scale > 0.f, "loss_forward: bad dims");
   if (a->N == 0) return HFR_OK;
-  HFR_CHECK_ARG(a->re_img && a->re_sil && a->imgs && a->seg && a->sums, "loss_forward: null pointer");
+  HFR_CHECK_ARG(a->re_img && (a->nhwc || a->re_sil) && a->imgs && a->seg && a->sums, "loss_forward: null pointer");
   HFR_CHECK_ARG(!a->want_ssim || a->gauss, "loss_forward: SSIM needs the Gaussian taps");
   dim3 grid((a->W + kT - 1) / kT, (a->H + kT - 1) / kT, a->N);
   loss_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*a);
@@ -265,7 +277,7 @@ extern "C" int hfr_loss_backward(const HfrLossBwdArgs* a, void* stream) {
   using namespace hfr;
   HFR_CHECK_ARG(a && a->f.N >= 0 && a->f.H > 0 && a->f.W > 0, "loss_backward: bad dims");
   if (a->f.N == 0) return HFR_OK;
-  HFR_CHECK_ARG(a->f.re_img && a->f.re_sil && a->f.imgs && a->f.seg && a->f.sums && a->w && a->g_re_img && a->g_re_sil,
+  HFR_CHECK_ARG(a->f.re_img && (a->f.nhwc || (a->f.re_sil && a->g_re_sil)) && a->f.imgs && a->f.seg && a->f.sums && a->w && a->g_re_img,
                 "loss_backward: null pointer");
   HFR_CHECK_ARG(!(a->f.want_ssim && a->f.dmaps) || a->gauss, "loss_backward: SSIM needs the Gaussian taps");
   HFR_CHECK_ARG(a->count_global > 0 && a->n_global > 0, "loss_backward: bad global counts");

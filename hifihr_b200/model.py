@@ -1,0 +1,211 @@
+"""The hot path of Model.forward (models_res_nimble.py:133-223) without the CNN encoders.
+
+HandRenderModel   — modular drop-in built from the reference-named objects (hand layer,
+                    xyz_from_vertice, root shift, PerspectiveCameras, MeshRenderer, avg-pool,
+                    output dict), differentiable through torch autograd bridges.
+FusedHandStep     — the same computation as ONE forward+backward sequence of raw kernel
+                    launches on preallocated buffers (10 launches per step, CUDA-graph
+                    capturable): MANO -> geometry -> rasterize+shade -> loss | loss' ->
+                    shade'+rasterize' -> geometry' -> MANO'.  This is what bench.py times.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _lib as L
+from . import ops
+from .mano import MyMANOLayer, xyz_from_vertice
+from .renderer import (BlendParams, DirectionalLights, HardPhongShader, Materials, MeshRasterizer, MeshRenderer,
+                       PerspectiveCameras, RasterizationSettings, SoftPhongShader, TexturesUV)
+
+F32, I32, I64 = torch.float32, torch.int32, torch.int64
+
+
+def get_ndc_fx_fy_cx_cy(Ks):
+    """models_res_nimble.py:228-235 (the 224/112 constants are the reference's)."""
+    ndc_fx = Ks[:, 0, 0] * 2 / 224.0
+    ndc_fy = Ks[:, 1, 1] * 2 / 224.0
+    ndc_px = -(Ks[:, 0, 2] - 112.0) * 2 / 224.0
+    ndc_py = -(Ks[:, 1, 2] - 112.0) * 2 / 224.0
+    return torch.stack([ndc_fx, ndc_fy], dim=-1), torch.stack([ndc_px, ndc_py], dim=-1)
+
+
+def mano_synthetic_uvs(v_template, faces):
+    """MANO_RIGHT.pkl has no UVs: planar map of the template's x/z extent (§8d)."""
+    xz = np.asarray(v_template, np.float64)[:, [0, 2]]
+    uv = (xz - xz.min(0)) / (xz.max(0) - xz.min(0))
+    return uv.astype(np.float32), np.asarray(faces, np.int64)
+
+
+class HandRenderModel(nn.Module):
+    """hand layer -> joints -> root shift -> camera -> render -> pool -> outputs (reference order)."""
+
+    def __init__(self, ifRender=True, device="cuda", hand_model="mano", root_id=9, image_size=224, aa_factor=3,
+                 blur_radius=0.0, faces_per_pixel=1, soft=False, binarize=True, texture_size=512, mano_root=None,
+                 blend_params=None):
+        super().__init__()
+        if hand_model != "mano":
+            raise NotImplementedError("use hifihr_b200.nimble.MyNIMBLELayer for the NIMBLE-shaped stand-in")
+        self.root_id = root_id
+        self.ifRender = ifRender
+        self.aa_factor = aa_factor
+        self.binarize = binarize
+        self.ncomps = [10, 48, None]
+        self.hand_layer = MyMANOLayer(ifRender, device, shape_ncomp=10, pose_ncomp=48, tex_ncomp=None,
+                                      mano_root=mano_root)
+        d = self.hand_layer.mano_layer._mano
+        uv, fuv = mano_synthetic_uvs(d["v_template"], d["f"])
+        self.register_buffer("verts_uvs", torch.tensor(uv))
+        self.register_buffer("faces_uvs", torch.tensor(fuv))
+        g = torch.Generator().manual_seed(20231)
+        self.texture = nn.Parameter(torch.rand(1, texture_size, texture_size, 3, generator=g))
+        self.mano_face = self.hand_layer.mesh_face
+        if ifRender:
+            rs = RasterizationSettings(image_size=image_size * aa_factor, blur_radius=blur_radius,
+                                       faces_per_pixel=faces_per_pixel)
+            materials = Materials(diffuse_color=((0.8, 0.8, 0.8),), specular_color=((0.2, 0.2, 0.2),), shininess=30,
+                                  device=device)
+            shader_cls = SoftPhongShader if soft else HardPhongShader
+            self.renderer_p3d = MeshRenderer(rasterizer=MeshRasterizer(raster_settings=rs),
+                                             shader=shader_cls(materials=materials, device=device,
+                                                               blend_params=blend_params))
+
+    def forward(self, hand_params, light_params=None, Ks=None, root_xyz=None, images=None):
+        outputs = self.hand_layer(hand_params, handle_collision=False)
+        outputs.update(hand_params)
+        verts = outputs["mano_verts"]
+        dev = verts.device
+        topo = self.hand_layer.topology(dev)
+        joints, verts_rel = xyz_from_vertice(topo, verts, root_id=self.root_id)
+        outputs["joints"] = joints
+        outputs["mano_verts"] = verts_rel
+        B = verts.shape[0]
+        if self.ifRender:
+            fcl, prp = get_ndc_fx_fy_cx_cy(Ks)
+            cameras = PerspectiveCameras(focal_length=-fcl, principal_point=prp, device=dev)
+            lighting = DirectionalLights(diffuse_color=light_params["colors"], direction=light_params["directions"],
+                                         device=dev)
+            meshes = outputs["skin_meshes"]
+            pred_root = (verts - verts_rel)[:, :1]            # = joints[:, root_id] before the shift
+            verts_num = verts.shape[1]                        # = meshes._num_verts_per_mesh[0], without a host sync
+            meshes.offset_verts_(-pred_root.repeat(1, verts_num, 1).view(verts_num * B, 3))
+            meshes.offset_verts_(root_xyz.reshape(B, 1, 3).repeat(1, verts_num, 1).view(verts_num * B, 3))
+            meshes.textures = TexturesUV(self.texture, self.faces_uvs, self.verts_uvs)
+            rendered = self.renderer_p3d(meshes, cameras=cameras, lights=lighting)
+            re_img, re_sil, mask = ops.PoolFunction.apply(rendered, self.aa_factor, self.binarize, images)
+            outputs["re_img"], outputs["re_sil"] = re_img, re_sil
+            if images is not None:
+                outputs["maskRGBs"] = mask
+        outputs["mano_faces"] = self.mano_face.to(dev).repeat(B, 1, 1)
+        return outputs
+
+
+class FusedHandStep:
+    """Forward + backward of the whole hot path as raw launches on preallocated buffers.
+
+    Inputs (device, fp32, contiguous): pose (B,48), betas (B,10), focal (B,2), prp (B,2), root_xyz (B,3),
+    light_dir (B,3), light_color (B,3), imgs (B,3,S,S), seg (B,S,S).  The shared texture (1,T,T,3) and the
+    loss weights live in the object.  After `step()`: `sums` holds the loss partial sums, and g_pose, g_betas,
+    g_texture, g_light_dir, g_light_color the gradients of  sum_k lambda_k * term_k.
+    """
+
+    def __init__(self, B, image_size=224, faces_per_pixel=4, blur_radius=None, sigma=1e-4, gamma=1e-4, soft=True,
+                 texture_size=512, lambdas=None, device="cuda", mano_root=None, n_global=None, sil_scale=1.0):
+        dev = torch.device(device)
+        self.B, self.S, self.K, self.dev = B, image_size, faces_per_pixel, dev
+        self.soft = soft
+        self.blur = (np.log(1.0 / 1e-4 - 1.0) * sigma if soft else 0.0) if blur_radius is None else blur_radius
+        self.layer = MyMANOLayer(True, dev, shape_ncomp=10, pose_ncomp=48, tex_ncomp=None, mano_root=mano_root)
+        self.hm = self.layer.mano_layer.consts(dev)
+        self.topo = self.layer.topology(dev)
+        d = self.layer.mano_layer._mano
+        uv, fuv = mano_synthetic_uvs(d["v_template"], d["f"])
+        self.verts_uvs = torch.tensor(uv, device=dev)
+        self.faces_uvs = torch.tensor(fuv, device=dev, dtype=I32)
+        g = torch.Generator().manual_seed(20231)
+        self.texture = torch.rand(1, texture_size, texture_size, 3, generator=g).to(dev)
+        lam = dict(texture=1.0, mrgb=1.0, ssim_tex=1.0, sil=1.0, iou=0.0)
+        lam.update(lambdas or {})
+        self.lambdas = lam
+        self.w = torch.tensor([lam["texture"], lam["mrgb"], lam["ssim_tex"], lam["sil"], lam["iou"]], device=dev)
+        self.n_global = n_global or B
+        self.sil_scale = sil_scale
+        V, Fm, S, K = self.hm.V, self.topo.F, self.S, self.K
+        e = lambda *s, dt=F32: torch.empty(*s, dtype=dt, device=dev)  # noqa: E731
+        self.verts, self.joints = e(B, V, 3), e(B, 21, 3)
+        self.verts_rel, self.verts_view, self.verts_ndc, self.vnormals = e(B, V, 3), e(B, V, 3), e(B, V, 3), e(B, V, 3)
+        self.face_verts = e(B * Fm, 3, 3)
+        self.p2f = e(B, S, S, K, dt=I64)
+        self.zbuf, self.bary, self.dists = e(B, S, S, K), e(B, S, S, K, 3), e(B, S, S, K)
+        self.image, self.g_image = e(B, S, S, 4), e(B, S, S, 4)
+        self.dmaps = e(B, 9, S, S)
+        self.sums = e(L.LOSS_NSUMS + 2 * B)
+        self.ws = ops.raster_workspace(B * Fm, dev)
+        self.mesh_first = (torch.arange(B, device=dev, dtype=I64) * Fm).contiguous()
+        self.mesh_nf = torch.full((B,), Fm, device=dev, dtype=I64)
+        # every accumulated gradient lives in one flat buffer so a single memset clears them
+        n_acc = 3 * B * V * 3 + self.texture.numel() + 6 * B
+        self.acc = torch.zeros(n_acc, dtype=F32, device=dev)
+        o = 0
+        def take(n, shape):
+            nonlocal o
+            t = self.acc[o:o + n].view(*shape)
+            o += n
+            return t
+        self.g_ndc, self.g_view, self.g_vn = take(B * V * 3, (B, V, 3)), take(B * V * 3, (B, V, 3)), take(B * V * 3, (B, V, 3))
+        self.g_texture = take(self.texture.numel(), self.texture.shape)
+        self.g_light_dir, self.g_light_color = take(3 * B, (B, 3)), take(3 * B, (B, 3))
+        self.g_verts, self.g_pose, self.g_betas = e(B, V, 3), e(B, 48), e(B, 10)
+        self.gauss = ops.gauss_taps(dev)
+        self.params = ops.shade_params(B, S, S, K, Fm, V, 2 if soft else 0, 1, sigma, gamma, (1.0, 1.0, 1.0),
+                                       (0.5, 0.5, 0.5), (0.2, 0.2, 0.2), (1.0, 1.0, 1.0), (0.8, 0.8, 0.8),
+                                       (0.2, 0.2, 0.2), 30.0, tex_shape=self.texture.shape[:3], VT=self.verts_uvs.shape[0])
+        self.launches_per_step = 11   # kernels of ours per step() (setup, mano, geom, raster+shade, loss | 5 bwd) + 1 memset
+
+    # ---------------------------------------------------------------------------------------
+    def forward(self, pose, betas, focal, prp, root_xyz, light_dir, light_color, imgs, seg):
+        B, S, K = self.B, self.S, self.K
+        ops.mano_forward_raw(self.hm, pose, betas, None, self.verts, None)
+        ops.geom_forward_raw(self.topo, self.verts, 9, root_xyz, focal, prp, self.joints, self.verts_rel,
+                             self.verts_view, self.verts_ndc, self.vnormals, self.face_verts)
+        r = ops.raster_args(self.face_verts, self.mesh_first, self.mesh_nf, S, S, K, self.blur, True, self.blur > 0,
+                            False, self.p2f, self.zbuf, self.bary, self.dists, self.ws)
+        s = ops.shade_fwd_args(self.params, (self.p2f, self.zbuf, self.bary, self.dists), self.topo.faces,
+                               self.verts_view, self.vnormals, self.faces_uvs, self.verts_uvs, self.texture,
+                               light_dir, light_color, self.image)
+        L.call("hfr_raster_shade_forward", L.HfrRasterShadeArgs(r, s))
+        self.sums.zero_()
+        self._loss_args = L.HfrLossArgs(B, S, S, self.sil_scale, 1, 1, 1, L.ptr(self.image), None, L.ptr(imgs, F32),
+                                        L.ptr(seg, F32), L.ptr(self.sums), L.ptr(self.gauss), L.ptr(self.dmaps))
+        L.call("hfr_loss_forward", self._loss_args)
+        self._shade_args = s
+
+    def backward(self, pose, betas, focal, prp, root_xyz):
+        B, S = self.B, self.S
+        a = L.HfrLossBwdArgs(self._loss_args, L.ptr(self.w), L.ptr(self.gauss), self.n_global * 3 * S * S,
+                             self.n_global, L.ptr(self.g_image), None)
+        L.call("hfr_loss_backward", a)
+        self.acc.zero_()
+        sb = L.HfrShadeBwdArgs(self._shade_args, L.ptr(self.g_image), None, None, None, L.ptr(self.verts_ndc),
+                               L.ptr(self.g_ndc), float(self.blur), 1, int(self.blur > 0), L.ptr(self.g_view),
+                               L.ptr(self.g_vn), L.ptr(self.g_texture), L.ptr(self.g_light_dir),
+                               L.ptr(self.g_light_color))
+        L.call("hfr_shade_backward", sb)
+        ops.geom_backward_raw(self.topo, self.verts, 9, root_xyz, focal, prp, None, None, self.g_view, self.g_ndc,
+                              self.g_vn, self.g_verts)
+        ops.mano_backward_raw(self.hm, pose, betas, None, self.g_verts, None, self.g_pose, self.g_betas, None)
+
+    def step(self, pose, betas, focal, prp, root_xyz, light_dir, light_color, imgs, seg):
+        self.forward(pose, betas, focal, prp, root_xyz, light_dir, light_color, imgs, seg)
+        self.backward(pose, betas, focal, prp, root_xyz)
+
+    def loss_terms(self, sums=None):
+        """[texture, mrgb, ssim_tex, sil, iou] (unweighted) from the partial sums (device tensor ops)."""
+        s = self.sums if sums is None else sums
+        B, S = self.B, self.S
+        cnt = float(self.n_global * 3 * S * S)
+        mul, add = s[L.LOSS_NSUMS:L.LOSS_NSUMS + B], s[L.LOSS_NSUMS + B:]
+        return torch.stack([s[0] / cnt, (s[2] / cnt - s[1] / cnt) ** 2, 1 - s[4] / cnt,
+                            s[3] / float(self.n_global * S * S), 1 - (mul / (add - mul)).sum() / self.n_global])

@@ -1,0 +1,422 @@
+"""Device constants + autograd bridges over the C-ABI (hifihr_b200._lib).
+
+Every function here launches hand-written sm_100a kernels on the current torch
+stream.  torch is used for memory, streams and autograd bookkeeping only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+F32, I32, I64 = torch.float32, torch.int32, torch.int64
+
+
+def _cu(t, dtype=F32):
+    return t.to(dtype).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# constants
+# ------------------------------------------------------------------------------------------------
+class HandModelConsts:
+    """Device-resident constants of an LBS hand model in the layout the kernels want
+    (HfrHandModel).  Built from the arrays ManoLayer.__init__ reads (utils/my_mano.py:277-313)."""
+
+    def __init__(self, *, v_template, shapedirs, posedirs, J_regressor, weights, parents, pca_comps=None,
+                 pose_mean=None, tip_verts=(), joint_order=None, center_joint=-1, max_influences=8, device="cuda"):
+        v_template = np.asarray(v_template, np.float64)
+        shapedirs = np.asarray(shapedirs, np.float64)
+        posedirs = np.asarray(posedirs, np.float64)
+        Jreg = np.asarray(J_regressor, np.float64)
+        weights = np.asarray(weights, np.float64)
+        V, NS = v_template.shape[0], shapedirs.shape[2]
+        NJ = Jreg.shape[0]
+        assert posedirs.shape[2] == 9 * (NJ - 1), "posedirs must have 9*(NJ-1) columns"
+        C3 = (3 * V + 3) // 4 * 4
+        dirs = np.zeros((NS + 9 * (NJ - 1), C3), np.float32)
+        dirs[:NS, :3 * V] = shapedirs.reshape(3 * V, NS).T
+        dirs[NS:, :3 * V] = posedirs.reshape(3 * V, -1).T
+        vt = np.zeros(C3, np.float32)
+        vt[:3 * V] = v_template.reshape(-1)
+        nw = int(min(max_influences, max(1, (weights != 0).sum(1).max())))
+        order = np.argsort(-np.abs(weights), axis=1)[:, :nw]
+        skin_idx = order.T.astype(np.int32).copy()                       # (NW,V)
+        skin_w = np.take_along_axis(weights, order, 1).T.astype(np.float32).copy()
+        self.V, self.NJ, self.NS, self.NW, self.C3 = V, NJ, NS, nw, C3
+        self.NPC = 0 if pca_comps is None else int(np.asarray(pca_comps).shape[0])
+        self.NT = len(tip_verts)
+        self.center_joint = int(center_joint)
+        if joint_order is None:
+            joint_order = list(range(NJ + self.NT))
+        dev = torch.device(device)
+        t = lambda a, dt=F32: torch.as_tensor(np.ascontiguousarray(a)).to(dt).to(dev).contiguous()  # noqa: E731
+        self.dirs = t(dirs)
+        self.v_template = t(vt)
+        self.J_template = t(Jreg @ v_template)
+        self.J_shapedirs = t(np.einsum("jv,vck->jck", Jreg, shapedirs))
+        self.pca_comps = None if pca_comps is None else t(np.asarray(pca_comps, np.float64))
+        self.pose_mean = None if pose_mean is None else t(np.asarray(pose_mean, np.float64).reshape(-1))
+        self.parents = t(np.asarray(parents, np.int64), I32)
+        self.skin_idx = t(skin_idx, I32)
+        self.skin_w = t(skin_w)
+        self.tip_verts = t(np.asarray(list(tip_verts) or [0], np.int64), I32)
+        self.joint_order = t(np.asarray(joint_order, np.int64), I32)
+        self.pose_dim = 3 + (self.NPC if self.NPC > 0 else 3 * (NJ - 1))
+        self.n_out_joints = NJ + self.NT
+        s = L.HfrHandModel()
+        s.V, s.NJ, s.NS, s.NPC, s.NW, s.NT, s.center_joint, s.C3 = V, NJ, NS, self.NPC, nw, self.NT, self.center_joint, C3
+        s.dirs, s.v_template = self.dirs.data_ptr(), self.v_template.data_ptr()
+        s.J_template, s.J_shapedirs = self.J_template.data_ptr(), self.J_shapedirs.data_ptr()
+        s.pca_comps = None if self.pca_comps is None else self.pca_comps.data_ptr()
+        s.pose_mean = None if self.pose_mean is None else self.pose_mean.data_ptr()
+        s.parents, s.skin_idx, s.skin_w = self.parents.data_ptr(), self.skin_idx.data_ptr(), self.skin_w.data_ptr()
+        s.tip_verts, s.joint_order = self.tip_verts.data_ptr(), self.joint_order.data_ptr()
+        self.struct = s
+        self.device = dev
+
+
+class TopologyConsts:
+    """Shared mesh topology + (optional) sparse joint regressor on posed verts (HfrTopology)."""
+
+    def __init__(self, faces, V, J_regressor=None, out_src=None, device="cuda"):
+        faces = np.asarray(faces, np.int64)
+        F = faces.shape[0]
+        inc = [[] for _ in range(V)]
+        for f in range(F):
+            for c in range(3):
+                inc[faces[f, c]].append(f * 4 + c)
+        vf_ptr = np.zeros(V + 1, np.int64)
+        vf_ptr[1:] = np.cumsum([len(x) for x in inc])
+        vf_idx = np.asarray([e for x in inc for e in x] or [0], np.int64)
+        dev = torch.device(device)
+        t = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a)).to(dt).to(dev).contiguous()  # noqa: E731
+        self.V, self.F = int(V), int(F)
+        self.faces = t(faces, I32)
+        self.faces_long = t(faces, I64)
+        self.vf_ptr, self.vf_idx = t(vf_ptr, I32), t(vf_idx, I32)
+        s = L.HfrTopology()
+        s.V, s.F = self.V, self.F
+        s.faces, s.vf_ptr, s.vf_idx = self.faces.data_ptr(), self.vf_ptr.data_ptr(), self.vf_idx.data_ptr()
+        self.NJR = self.NOUT = 0
+        if J_regressor is not None:
+            J = np.asarray(J_regressor, np.float64)
+            NJR = J.shape[0]
+            jr_ptr, jr_col, jr_val = [0], [], []
+            for j in range(NJR):
+                nz = np.nonzero(J[j])[0]
+                jr_col += nz.tolist()
+                jr_val += J[j, nz].tolist()
+                jr_ptr.append(len(jr_col))
+            vj_ptr, vj_row, vj_val = [0], [], []
+            for v in range(V):
+                nz = np.nonzero(J[:, v])[0]
+                vj_row += nz.tolist()
+                vj_val += J[nz, v].tolist()
+                vj_ptr.append(len(vj_row))
+            self.jr_ptr, self.jr_col, self.jr_val = t(jr_ptr, I32), t(jr_col, I32), t(jr_val, F32)
+            self.vj_ptr, self.vj_row, self.vj_val = t(vj_ptr, I32), t(vj_row, I32), t(vj_val, F32)
+            self.out_src = t(np.asarray(out_src, np.int64), I32)
+            self.NJR, self.NOUT = NJR, len(out_src)
+            s.NJR, s.NOUT = self.NJR, self.NOUT
+            s.jr_ptr, s.jr_col, s.jr_val = self.jr_ptr.data_ptr(), self.jr_col.data_ptr(), self.jr_val.data_ptr()
+            s.vj_ptr, s.vj_row, s.vj_val = self.vj_ptr.data_ptr(), self.vj_row.data_ptr(), self.vj_val.data_ptr()
+            s.out_src = self.out_src.data_ptr()
+        self.struct = s
+        self.device = dev
+
+
+# ------------------------------------------------------------------------------------------------
+# raw launches (no autograd) — also used by the fused step
+# ------------------------------------------------------------------------------------------------
+def mano_forward_raw(hm: HandModelConsts, pose, betas, trans, verts, joints):
+    a = L.HfrManoFwdArgs(pose.shape[0], L.ptr(pose, F32, "pose"), L.ptr(betas, F32, "betas"),
+                         L.ptr(trans, F32, "trans"), L.ptr(verts, F32), L.ptr(joints, F32))
+    L.call("hfr_mano_forward", hm.struct, a)
+
+
+def mano_backward_raw(hm, pose, betas, trans, g_verts, g_joints, g_pose, g_betas, g_trans):
+    a = L.HfrManoBwdArgs(pose.shape[0], L.ptr(pose, F32), L.ptr(betas, F32), L.ptr(trans, F32),
+                         L.ptr(g_verts, F32), L.ptr(g_joints, F32), L.ptr(g_pose, F32), L.ptr(g_betas, F32),
+                         L.ptr(g_trans, F32))
+    L.call("hfr_mano_backward", hm.struct, a)
+
+
+def geom_forward_raw(topo, verts, root_out, root_xyz, focal, prp, joints, verts_rel, verts_view, verts_ndc, vnormals,
+                     face_verts=None):
+    a = L.HfrGeomFwdArgs(verts.shape[0], root_out, L.ptr(verts, F32, "verts"), L.ptr(root_xyz, F32), L.ptr(focal, F32),
+                         L.ptr(prp, F32), L.ptr(joints, F32), L.ptr(verts_rel, F32), L.ptr(verts_view, F32),
+                         L.ptr(verts_ndc, F32), L.ptr(vnormals, F32), L.ptr(face_verts, F32))
+    L.call("hfr_geom_forward", topo.struct, a)
+
+
+def geom_backward_raw(topo, verts, root_out, root_xyz, focal, prp, g_joints, g_rel, g_view, g_ndc, g_vn, g_verts):
+    a = L.HfrGeomBwdArgs(verts.shape[0], root_out, L.ptr(verts, F32), L.ptr(root_xyz, F32), L.ptr(focal, F32),
+                         L.ptr(prp, F32), L.ptr(g_joints, F32), L.ptr(g_rel, F32), L.ptr(g_view, F32),
+                         L.ptr(g_ndc, F32), L.ptr(g_vn, F32), L.ptr(g_verts, F32))
+    L.call("hfr_geom_backward", topo.struct, a)
+
+
+def raster_args(face_verts, mesh_first, mesh_nf, H, W, K, blur_radius, perspective_correct, clip_bary, cull,
+                pix_to_face, zbuf, bary, dists, workspace):
+    N = mesh_first.shape[0]
+    return L.HfrRasterArgs(N, H, W, K, face_verts.shape[0], L.ptr(face_verts, F32, "face_verts"),
+                           L.ptr(mesh_first, I64, "mesh_to_face_first_idx"), L.ptr(mesh_nf, I64, "num_faces_per_mesh"),
+                           float(blur_radius), int(perspective_correct), int(clip_bary), int(cull),
+                           L.ptr(pix_to_face, I64), L.ptr(zbuf, F32), L.ptr(bary, F32), L.ptr(dists, F32),
+                           L.ptr(workspace))
+
+
+def raster_workspace(Ftot, device):
+    nbytes = int(L.lib().hfr_raster_workspace_bytes(int(Ftot)))
+    return torch.empty(nbytes, dtype=torch.uint8, device=device)
+
+
+def shade_params(N, H, W, K, F, V, blend, shade, sigma, gamma, background, light_ambient, light_specular,
+                 mat_ambient, mat_diffuse, mat_specular, shininess, tex_shape=(1, 1, 1), VT=0, znear=1.0, zfar=100.0):
+    p = L.HfrShadeParams()
+    p.N, p.H, p.W, p.K, p.F, p.V, p.blend, p.shade = N, H, W, K, F, V, blend, shade
+    p.sigma, p.gamma, p.znear, p.zfar = float(sigma), float(gamma), float(znear), float(zfar)
+    p.background = L.f3(background)
+    p.light_ambient, p.light_specular = L.f3(light_ambient), L.f3(light_specular)
+    p.mat_ambient, p.mat_diffuse, p.mat_specular = L.f3(mat_ambient), L.f3(mat_diffuse), L.f3(mat_specular)
+    p.shininess = float(shininess)
+    p.tex_n, p.tex_h, p.tex_w, p.VT = int(tex_shape[0]), int(tex_shape[1]), int(tex_shape[2]), int(VT)
+    return p
+
+
+def shade_fwd_args(p, frags, faces, verts_view, vnormals, faces_uvs, verts_uvs, texture, light_dir, light_color, image):
+    p2f, zbuf, bary, dists = frags
+    return L.HfrShadeFwdArgs(p, L.ptr(p2f, I64), L.ptr(zbuf, F32), L.ptr(bary, F32), L.ptr(dists, F32),
+                             L.ptr(faces, I32), L.ptr(verts_view, F32), L.ptr(vnormals, F32), L.ptr(faces_uvs, I32),
+                             L.ptr(verts_uvs, F32), L.ptr(texture, F32), L.ptr(light_dir, F32), L.ptr(light_color, F32),
+                             L.ptr(image, F32))
+
+
+_GAUSS = {}
+
+
+def gauss_taps(device):
+    """The 11 fp32 taps of utils/pytorch_ssim/__init__.py:7-9 (sigma 1.5), built the same way."""
+    key = str(device)
+    if key not in _GAUSS:
+        g = torch.tensor([math.exp(-(x - 5) ** 2 / float(2 * 1.5 ** 2)) for x in range(11)])
+        _GAUSS[key] = (g / g.sum()).to(F32).to(device).contiguous()
+    return _GAUSS[key]
+
+
+# ------------------------------------------------------------------------------------------------
+# autograd bridges
+# ------------------------------------------------------------------------------------------------
+class ManoFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, hm: HandModelConsts, pose, betas, trans):
+        pose = _cu(pose)
+        betas = None if betas is None else _cu(betas)
+        trans = None if trans is None else _cu(trans)
+        B = pose.shape[0]
+        verts = torch.empty(B, hm.V, 3, device=pose.device, dtype=F32)
+        joints = torch.empty(B, hm.n_out_joints, 3, device=pose.device, dtype=F32)
+        mano_forward_raw(hm, pose, betas, trans, verts, joints)
+        ctx.hm = hm
+        ctx.save_for_backward(pose, betas, trans)
+        return verts, joints
+
+    @staticmethod
+    def backward(ctx, g_verts, g_joints):
+        pose, betas, trans = ctx.saved_tensors
+        hm = ctx.hm
+        g_verts = pose.new_zeros(pose.shape[0], hm.V, 3) if g_verts is None else _cu(g_verts)
+        g_joints = None if g_joints is None else _cu(g_joints)
+        g_pose = torch.empty_like(pose)
+        g_betas = None if betas is None else torch.empty_like(betas)
+        g_trans = None if trans is None else torch.empty_like(trans)
+        mano_backward_raw(hm, pose, betas, trans, g_verts, g_joints, g_pose, g_betas, g_trans)
+        return None, g_pose, g_betas, g_trans
+
+
+class GeomFunction(torch.autograd.Function):
+    """verts -> (joints, verts_rel, verts_view, verts_ndc, vnormals); see hfr_geom_forward."""
+
+    @staticmethod
+    def forward(ctx, topo: TopologyConsts, verts, root_out, root_xyz, focal, prp, want_normals):
+        verts = _cu(verts)
+        B, V = verts.shape[0], verts.shape[1]
+        dev = verts.device
+        root_xyz = None if root_xyz is None else _cu(root_xyz.reshape(B, 3))
+        focal = None if focal is None else _cu(focal)
+        prp = None if prp is None else _cu(prp)
+        joints = torch.empty(B, max(topo.NOUT, 1), 3, device=dev, dtype=F32) if root_out >= 0 else None
+        rel = torch.empty_like(verts)
+        view = torch.empty_like(verts)
+        ndc = torch.empty_like(verts) if focal is not None else None
+        vn = torch.empty_like(verts) if want_normals else None
+        geom_forward_raw(topo, verts, root_out, root_xyz, focal, prp, joints, rel, view, ndc, vn)
+        ctx.topo, ctx.root_out = topo, root_out
+        ctx.save_for_backward(verts, root_xyz, focal, prp)
+        outs = (joints if joints is not None else verts.new_zeros(0), rel, view,
+                ndc if ndc is not None else verts.new_zeros(0), vn if vn is not None else verts.new_zeros(0))
+        return outs
+
+    @staticmethod
+    def backward(ctx, g_joints, g_rel, g_view, g_ndc, g_vn):
+        verts, root_xyz, focal, prp = ctx.saved_tensors
+        fix = lambda g, ok=True: None if (g is None or not ok or g.numel() == 0) else _cu(g)  # noqa: E731
+        g_verts = torch.empty_like(verts)
+        geom_backward_raw(ctx.topo, verts, ctx.root_out, root_xyz, focal, prp, fix(g_joints, ctx.root_out >= 0),
+                          fix(g_rel), fix(g_view), fix(g_ndc, focal is not None), fix(g_vn), g_verts)
+        return None, g_verts, None, None, None, None, None
+
+
+class RasterizeFunction(torch.autograd.Function):
+    """Same contract as pytorch3d._C.rasterize_meshes / rasterize_meshes_backward."""
+
+    @staticmethod
+    def forward(ctx, face_verts, mesh_first, mesh_nf, image_size, blur_radius, K, perspective_correct, clip_bary,
+                cull_backfaces):
+        face_verts = _cu(face_verts)
+        H, W = image_size
+        N = mesh_first.shape[0]
+        dev = face_verts.device
+        p2f = torch.empty(N, H, W, K, dtype=I64, device=dev)
+        zbuf = torch.empty(N, H, W, K, dtype=F32, device=dev)
+        bary = torch.empty(N, H, W, K, 3, dtype=F32, device=dev)
+        dists = torch.empty(N, H, W, K, dtype=F32, device=dev)
+        ws = raster_workspace(face_verts.shape[0], dev)
+        a = raster_args(face_verts, mesh_first, mesh_nf, H, W, K, blur_radius, perspective_correct, clip_bary,
+                        cull_backfaces, p2f, zbuf, bary, dists, ws)
+        L.call("hfr_raster_forward", a)
+        ctx.cfg = (H, W, K, float(blur_radius), int(perspective_correct), int(clip_bary))
+        ctx.save_for_backward(face_verts, p2f)
+        ctx.mark_non_differentiable(p2f)
+        return p2f, zbuf, bary, dists
+
+    @staticmethod
+    def backward(ctx, _g_p2f, g_zbuf, g_bary, g_dists):
+        face_verts, p2f = ctx.saved_tensors
+        H, W, K, blur, pc, clip = ctx.cfg
+        g_fv = torch.zeros_like(face_verts)
+        fix = lambda g: None if g is None else _cu(g)  # noqa: E731
+        a = L.HfrRasterBwdArgs(p2f.shape[0], H, W, K, face_verts.shape[0], L.ptr(face_verts, F32), L.ptr(p2f, I64),
+                               L.ptr(fix(g_zbuf), F32), L.ptr(fix(g_bary), F32), L.ptr(fix(g_dists), F32), blur, pc, clip,
+                               L.ptr(g_fv, F32))
+        L.call("hfr_raster_backward", a)
+        return g_fv, None, None, None, None, None, None, None, None
+
+
+class ShadeFunction(torch.autograd.Function):
+    """Fragments + mesh attributes + texture + lights -> RGBA image (N,H,W,4)."""
+
+    @staticmethod
+    def forward(ctx, params, p2f, zbuf, bary, dists, faces, verts_view, vnormals, faces_uvs, verts_uvs, texture,
+                light_dir, light_color):
+        N, H, W, K = p2f.shape
+        cu = lambda t: None if t is None else _cu(t)  # noqa: E731
+        zbuf, bary, dists = cu(zbuf), cu(bary), cu(dists)
+        verts_view, vnormals, texture = cu(verts_view), cu(vnormals), cu(texture)
+        light_dir, light_color, verts_uvs = cu(light_dir), cu(light_color), cu(verts_uvs)
+        image = torch.empty(N, H, W, 4, dtype=F32, device=p2f.device)
+        a = shade_fwd_args(params, (p2f, zbuf, bary, dists), faces, verts_view, vnormals, faces_uvs, verts_uvs,
+                           texture, light_dir, light_color, image)
+        L.call("hfr_shade_forward", a)
+        ctx.params = params
+        ctx.save_for_backward(p2f, zbuf, bary, dists, faces, verts_view, vnormals, faces_uvs, verts_uvs, texture,
+                              light_dir, light_color)
+        return image
+
+    @staticmethod
+    def backward(ctx, g_image):
+        (p2f, zbuf, bary, dists, faces, verts_view, vnormals, faces_uvs, verts_uvs, texture, light_dir,
+         light_color) = ctx.saved_tensors
+        p = ctx.params
+        g_image = _cu(g_image)
+        f = shade_fwd_args(p, (p2f, zbuf, bary, dists), faces, verts_view, vnormals, faces_uvs, verts_uvs, texture,
+                           light_dir, light_color, None)
+        g_zbuf, g_bary, g_dists = torch.empty_like(zbuf), torch.empty_like(bary), torch.empty_like(dists)
+        z = lambda t: None if t is None else torch.zeros_like(t)  # noqa: E731
+        g_vv, g_vn, g_tex, g_ld, g_lc = z(verts_view), z(vnormals), z(texture), z(light_dir), z(light_color)
+        a = L.HfrShadeBwdArgs(f, L.ptr(g_image, F32), L.ptr(g_zbuf, F32), L.ptr(g_bary, F32), L.ptr(g_dists, F32),
+                              None, None, 0.0, 1, 0, L.ptr(g_vv, F32), L.ptr(g_vn, F32), L.ptr(g_tex, F32),
+                              L.ptr(g_ld, F32), L.ptr(g_lc, F32))
+        L.call("hfr_shade_backward", a)
+        return None, None, g_zbuf, g_bary, g_dists, None, g_vv, g_vn, None, None, g_tex, g_ld, g_lc
+
+
+class PoolFunction(torch.autograd.Function):
+    """(N,H*aa,W*aa,4) -> re_img (N,3,H,W), re_sil (N,1,H,W), maskRGBs; models_res_nimble.py:210-220."""
+
+    @staticmethod
+    def forward(ctx, image, aa, binarize, images_in):
+        image = _cu(image)
+        N, Hi, Wi, _ = image.shape
+        H, W = Hi // aa, Wi // aa
+        dev = image.device
+        re_img = torch.empty(N, 3, H, W, dtype=F32, device=dev)
+        re_sil = torch.empty(N, 1, H, W, dtype=F32, device=dev)
+        images_in = None if images_in is None else _cu(images_in)
+        mask = torch.empty(N, 3, H, W, dtype=F32, device=dev) if images_in is not None else None
+        a = L.HfrPoolArgs(N, H, W, aa, int(binarize), L.ptr(image, F32), L.ptr(images_in, F32), L.ptr(re_img, F32),
+                          L.ptr(re_sil, F32), L.ptr(mask, F32))
+        L.call("hfr_pool_forward", a)
+        ctx.cfg = (N, H, W, aa, int(binarize))
+        if mask is None:
+            mask = image.new_zeros(0)
+        ctx.mark_non_differentiable(mask)
+        return re_img, re_sil, mask
+
+    @staticmethod
+    def backward(ctx, g_img, g_sil, _g_mask):
+        N, H, W, aa, binarize = ctx.cfg
+        ref = g_img if g_img is not None else g_sil
+        g_image = torch.empty(N, H * aa, W * aa, 4, dtype=F32, device=ref.device)
+        fix = lambda g: None if g is None else _cu(g)  # noqa: E731
+        a = L.HfrPoolBwdArgs(N, H, W, aa, binarize, L.ptr(fix(g_img), F32), L.ptr(fix(g_sil), F32), L.ptr(g_image, F32))
+        L.call("hfr_pool_backward", a)
+        return g_image, None, None, None
+
+
+class RenderLossFunction(torch.autograd.Function):
+    """Five render-dependent loss terms (unweighted) from one pass; returns a (5,) tensor
+    [texture, mrgb, ssim_tex, sil, iou] following losses.py:355-378, 399-408."""
+
+    @staticmethod
+    def forward(ctx, re_img, re_sil, imgs, seg, sil_scale, want_ssim):
+        re_img, re_sil, imgs, seg = _cu(re_img), _cu(re_sil), _cu(imgs), _cu(seg)
+        N, _, H, W = re_img.shape
+        dev = re_img.device
+        sums = torch.zeros(L.LOSS_NSUMS + 2 * N, dtype=F32, device=dev)
+        need_grad = re_img.requires_grad or re_sil.requires_grad
+        dmaps = torch.empty(N, 9, H, W, dtype=F32, device=dev) if (want_ssim and need_grad) else None
+        gauss = gauss_taps(dev)
+        a = L.HfrLossArgs(N, H, W, float(sil_scale), int(want_ssim), int(need_grad), 0, L.ptr(re_img, F32),
+                          L.ptr(re_sil, F32), L.ptr(imgs, F32), L.ptr(seg, F32), L.ptr(sums, F32), L.ptr(gauss, F32),
+                          L.ptr(dmaps, F32))
+        L.call("hfr_loss_forward", a)
+        cnt = float(N * 3 * H * W)
+        tex = sums[0] / cnt
+        mrgb = (sums[2] / cnt - sums[1] / cnt) ** 2
+        ssim = 1 - sums[4] / cnt
+        sil = sums[3] / float(N * H * W)
+        mul, add = sums[L.LOSS_NSUMS:L.LOSS_NSUMS + N], sums[L.LOSS_NSUMS + N:]
+        iou = 1 - (mul / (add - mul)).mean()
+        ctx.cfg = (N, H, W, float(sil_scale), int(want_ssim))
+        ctx.save_for_backward(re_img, re_sil, imgs, seg, sums, dmaps if dmaps is not None else sums.new_zeros(0))
+        return torch.stack([tex, mrgb, ssim, sil, iou])
+
+    @staticmethod
+    def backward(ctx, g):
+        re_img, re_sil, imgs, seg, sums, dmaps = ctx.saved_tensors
+        N, H, W, sil_scale, want_ssim = ctx.cfg
+        dmaps = dmaps if dmaps.numel() else None
+        gauss = gauss_taps(re_img.device)
+        f = L.HfrLossArgs(N, H, W, sil_scale, want_ssim, 1, 0, L.ptr(re_img, F32), L.ptr(re_sil, F32), L.ptr(imgs, F32),
+                          L.ptr(seg, F32), L.ptr(sums, F32), L.ptr(gauss, F32), L.ptr(dmaps, F32))
+        g_img, g_sil = torch.empty_like(re_img), torch.empty_like(re_sil)
+        w = _cu(g)
+        a = L.HfrLossBwdArgs(f, L.ptr(w, F32), L.ptr(gauss, F32), N * 3 * H * W, N, L.ptr(g_img, F32), L.ptr(g_sil, F32))
+        L.call("hfr_loss_backward", a)
+        return g_img, g_sil, None, None, None, None

@@ -120,6 +120,7 @@ typedef struct HfrGeomFwdArgs {
   float* verts_view;          /* (B,V,3) verts - pred_root + root_xyz                    */
   float* verts_ndc;           /* (B,V,3) x_ndc, y_ndc, view z; or NULL                   */
   float* vnormals;            /* (B,V,3) or NULL                                         */
+  float* face_verts;          /* (B,F,3,3) packed NDC face verts for the rasterizer, or NULL (needs verts_ndc) */
 } HfrGeomFwdArgs;
 int hfr_geom_forward(const HfrTopology* t, const HfrGeomFwdArgs* a, void* stream);
 
@@ -279,6 +280,8 @@ typedef struct HfrLossArgs {
   int32_t N, H, W;
   float sil_scale;                  /* 255 (reference, binarised) or 1 (soft alpha)        */
   int32_t want_ssim, want_grad;
+  int32_t nhwc;                     /* 1: re_img points at the shader's RGBA image (N,H,W,4), re_sil is ignored,
+                                       and the backward writes g_re_img as (N,H,W,4) (fused path, no pooling) */
   const float* re_img; const float* re_sil; const float* imgs; const float* seg;
   float* sums;                      /* (HFR_LOSS_NSUMS + 2N)                               */
   const float* gauss;               /* DEVICE pointer to the 11 fp32 Gaussian taps, or NULL when !want_ssim */

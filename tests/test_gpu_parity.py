@@ -1,0 +1,406 @@
+"""GPU parity tests: every kernel, through the C-ABI, against the CPU oracle on the same seeded inputs.
+
+Tolerances (fp32 path): verts 1e-6 m abs; pix_to_face / zbuf / bary / dists BIT-EXACT against the
+scalar C oracle; images 2e-5 abs; losses 1e-5 rel; gradients 2e-3 of the tensor's max magnitude vs the fp32
+oracle autograd (accumulation-order noise of fp32 sums over ~10^4 fragments).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import losses as olosses  # noqa: E402
+from oracle import p3d, raster_c  # noqa: E402
+from oracle import pipeline as P  # noqa: E402
+from oracle.mano import ManoOracle  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+DEV = "cuda"
+
+
+def rel_err(got, ref):
+    ref = ref.detach().cpu().double()
+    got = got.detach().cpu().double()
+    return float((got - ref).abs().max() / max(1e-12, ref.abs().max()))
+
+
+@pytest.fixture(scope="module")
+def hf():
+    import hifihr_b200
+    assert os.path.isfile(hifihr_b200.LIB_PATH), "libhifihr_b200.so missing: the CUDA path is the only path"
+    from hifihr_b200 import _lib
+    assert _lib.lib().hfr_device_ok() == 1, "expected a compute-capability 10.x device"
+    return hifihr_b200
+
+
+# ------------------------------------------------------------------------------------------ MANO
+def test_mano_matches_reference_golden(hf):
+    z = np.load(os.path.join(GOLD, "mano_reference.npz"))
+    layer = hf.ManoLayer(center_idx=9, flat_hand_mean=False, side="right", use_pca=True, ncomps=48)
+    pose = torch.tensor(z["pose"], device=DEV, requires_grad=True)
+    beta = torch.tensor(z["beta"], device=DEV, requires_grad=True)
+    v, j = layer(pose, beta)
+    assert (v.detach().cpu() - torch.tensor(z["verts"])).abs().max() < 1e-6
+    assert (j.detach().cpu() - torch.tensor(z["joints"])).abs().max() < 1e-6
+    ((v * torch.tensor(z["g_verts"], device=DEV)).sum() + (j * torch.tensor(z["g_joints"], device=DEV)).sum()).backward()
+    assert rel_err(pose.grad, torch.tensor(z["g_pose"])) < 1e-3
+    assert rel_err(beta.grad, torch.tensor(z["g_beta"])) < 1e-3
+    v0, j0 = layer(torch.zeros(1, 48, device=DEV), torch.zeros(1, 10, device=DEV))
+    assert (v0.cpu() - torch.tensor(z["verts_zero"])).abs().max() < 1e-6
+    assert j0[0, 9].abs().max() == 0
+
+
+def test_mano_vs_oracle_many_samples(hf, mano):
+    orc = ManoOracle(mano)
+    layer = hf.ManoLayer(center_idx=9, flat_hand_mean=False, ncomps=48)
+    inp = P.synthetic_inputs(257, S=8, seed=21)
+    v, j = layer(inp["pose"].to(DEV), inp["betas"].to(DEV))
+    vo, jo = orc(inp["pose"], inp["betas"])
+    assert (v.cpu() - vo).abs().max() < 1e-6 and (j.cpu() - jo).abs().max() < 1e-6
+    # mean shape (th_betas omitted) and explicit translation
+    v2, j2 = layer(inp["pose"][:4].to(DEV))
+    vo2, _ = orc(inp["pose"][:4], torch.zeros(4, 10))
+    assert (v2.cpu() - vo2).abs().max() < 1e-6
+    tr = torch.randn(4, 3)
+    v3, j3 = layer(inp["pose"][:4].to(DEV), inp["betas"][:4].to(DEV), tr.to(DEV))
+    vo3, jo3 = orc(inp["pose"][:4], inp["betas"][:4], trans=tr)
+    assert (v3.cpu() - vo3).abs().max() < 2e-6 and (j3.cpu() - jo3).abs().max() < 2e-6
+    # empty batch
+    ve, je = layer(torch.zeros(0, 48, device=DEV), torch.zeros(0, 10, device=DEV))
+    assert ve.shape == (0, 778, 3) and je.shape == (0, 21, 3)
+
+
+def test_mano_state_dict_names(hf):
+    layer = hf.ManoLayer(center_idx=9, flat_hand_mean=False, ncomps=48)
+    names = set(layer.state_dict().keys())
+    for k in ("th_betas", "th_shapedirs", "th_posedirs", "th_v_template", "th_J_regressor", "th_weights", "th_faces",
+              "th_hands_mean", "th_comps", "th_selected_comps"):
+        assert k in names
+    assert layer.th_selected_comps.shape == (45, 45) and layer.th_faces.shape == (1538, 3)
+    assert layer.kintree_parents[1:] == [0, 1, 2, 0, 4, 5, 0, 7, 8, 0, 10, 11, 0, 13, 14]
+
+
+# ------------------------------------------------------------------------------------------ geometry
+def test_geometry_forward_backward(hf, mano):
+    from hifihr_b200 import ops
+    orc = ManoOracle(mano)
+    B = 5
+    inp = P.synthetic_inputs(B, S=8, seed=4)
+    verts_cpu, _ = orc(inp["pose"], inp["betas"])
+    verts_cpu = verts_cpu.detach().requires_grad_(True)
+    joints = orc.xyz_from_vertice(verts_cpu)
+    root = joints[:, 9:10]
+    view = (verts_cpu + (-root)) + inp["root_xyz"][:, None]
+    fcl, prp = p3d.ndc_intrinsics(inp["Ks"])
+    ndc = p3d.project_ndc(view, -fcl, prp)
+    vn = p3d.vertex_normals(view, orc.faces)
+    layer = hf.MyMANOLayer(True, DEV, shape_ncomp=10, pose_ncomp=48, tex_ncomp=None)
+    topo = layer.topology(DEV)
+    vg = verts_cpu.detach().to(DEV).requires_grad_(True)
+    outs = ops.GeomFunction.apply(topo, vg, 9, inp["root_xyz"].to(DEV), (-fcl).to(DEV), prp.to(DEV), True)
+    j_g, rel_g, view_g, ndc_g, vn_g = outs
+    assert (j_g.cpu() - (joints - root)).abs().max() < 1e-6
+    assert (rel_g.cpu() - (verts_cpu - root)).abs().max() < 1e-6
+    assert (view_g.cpu() - view).abs().max() < 1e-6
+    assert (ndc_g.cpu() - ndc).abs().max() < 1e-5
+    assert (vn_g.cpu() - vn).abs().max() < 2e-4
+    g = torch.Generator().manual_seed(0)
+    ws = [torch.randn(t.shape, generator=g) for t in (joints, verts_cpu, view, ndc, vn)]
+    ((joints - root) * ws[0]).sum().add((verts_cpu - root).mul(ws[1]).sum()).add((view * ws[2]).sum()).add(
+        (ndc * ws[3]).sum()).add((vn * ws[4]).sum()).backward()
+    (j_g * ws[0].to(DEV)).sum().add((rel_g * ws[1].to(DEV)).sum()).add((view_g * ws[2].to(DEV)).sum()).add(
+        (ndc_g * ws[3].to(DEV)).sum()).add((vn_g * ws[4].to(DEV)).sum()).backward()
+    assert rel_err(vg.grad, verts_cpu.grad) < 2e-3
+
+
+# ------------------------------------------------------------------------------------------ rasterizer
+def _face_verts(mano, B, seed, S=224):
+    inp = P.synthetic_inputs(B, S=8, seed=seed)
+    orc = ManoOracle(mano)
+    verts, _ = orc(inp["pose"], inp["betas"])
+    joints = orc.xyz_from_vertice(verts)
+    view = (verts - joints[:, 9:10]) + inp["root_xyz"][:, None]
+    fcl, prp = p3d.ndc_intrinsics(inp["Ks"])
+    ndc = p3d.project_ndc(view, -fcl, prp)
+    fv = ndc[:, orc.faces].reshape(-1, 3, 3).contiguous()
+    Fm = orc.faces.shape[0]
+    return fv, [i * Fm for i in range(B)], [Fm] * B
+
+
+@pytest.mark.parametrize("H,W,K,blur,B", [(64, 64, 1, 0.0, 2), (224, 224, 4, 9.21e-4, 2), (48, 80, 2, 9.21e-4, 1),
+                                          (96, 96, 3, 9.21e-4, 1), (128, 128, 8, 9.21e-4, 1), (100, 100, 16, 2e-3, 1),
+                                          (672, 672, 1, 0.0, 1), (37, 53, 1, 0.0, 3)])
+def test_rasterizer_bit_exact(hf, mano, H, W, K, blur, B):
+    fv, first, nf = _face_verts(mano, B, seed=H + K)
+    ref = raster_c.rasterize_naive(fv, first, nf, (H, W), blur, K, threads=8)
+    out = hf.rasterize_meshes(fv.to(DEV), (H, W), blur, K, perspective_correct=True, clip_barycentric_coords=blur > 0,
+                              mesh_to_face_first_idx=torch.tensor(first, device=DEV),
+                              num_faces_per_mesh=torch.tensor(nf, device=DEV))
+    names = ["pix_to_face", "zbuf", "bary_coords", "dists"]
+    for name, g, r in zip(names, out, ref):
+        bad = (g.cpu() != r)
+        assert not bad.any(), f"{name}: {int(bad.sum())} mismatching entries of {bad.numel()}"
+    assert out[0].dtype == torch.int64 and out[0].shape == (B, H, W, K)
+    cov = out[0][..., 0] >= 0
+    assert 0.02 < cov.float().mean() < 0.6          # the hand is in view
+    # zbuf sorted ascending over valid slots
+    z = out[1].cpu()
+    valid = out[0].cpu() >= 0
+    zz = torch.where(valid, z, torch.full_like(z, float("inf")))
+    assert (zz[..., 1:] >= zz[..., :-1]).all()
+
+
+def test_rasterizer_golden_and_edge_cases(hf):
+    z = np.load(os.path.join(GOLD, "raster_oracle.npz"))
+    fv = torch.tensor(z["face_verts"], device=DEV)
+    first, nf = torch.zeros(1, dtype=torch.int64, device=DEV), torch.tensor([fv.shape[0]], device=DEV)
+    out = hf.rasterize_meshes(fv, 32, 9.21e-4, 2, perspective_correct=True, clip_barycentric_coords=True,
+                              mesh_to_face_first_idx=first, num_faces_per_mesh=nf)
+    assert (out[0].cpu().numpy() == z["pix_to_face"]).all() and (out[1].cpu().numpy() == z["zbuf"]).all()
+    assert (out[2].cpu().numpy() == z["bary"]).all() and (out[3].cpu().numpy() == z["dists"]).all()
+    # everything off screen / behind the camera / degenerate -> all -1
+    bad = torch.tensor([[[5.0, 5.0, 1.0], [6.0, 5.0, 1.0], [5.0, 6.0, 1.0]],
+                        [[-0.9, -0.9, -1.0], [0.9, -0.9, 2.0], [0.0, 0.9, 2.0]],
+                        [[0.1, 0.1, 1.0], [0.1, 0.1, 1.0], [0.2, 0.2, 1.0]]], device=DEV)
+    o = hf.rasterize_meshes(bad, 16, 1e-3, 2, mesh_to_face_first_idx=first, num_faces_per_mesh=torch.tensor([3], device=DEV))
+    assert (o[0] == -1).all() and (o[1] == -1).all() and (o[2] == -1).all() and (o[3] == -1).all()
+    # ties: coincident faces resolve to the smaller index, nearer face first (matches the CPU oracle)
+    tri = [[-0.9, -0.9, 2.0], [0.9, -0.9, 2.0], [0.0, 0.9, 2.0]]
+    near = [[-0.9, -0.9, 1.5], [0.9, -0.9, 1.5], [0.0, 0.9, 1.5]]
+    t3 = torch.tensor([tri, tri, near], device=DEV)
+    o = hf.rasterize_meshes(t3, 8, 0.0, 3, perspective_correct=True, mesh_to_face_first_idx=first,
+                            num_faces_per_mesh=torch.tensor([3], device=DEV))
+    r = raster_c.rasterize_naive(t3.cpu(), [0], [3], 8, 0.0, 3)
+    assert (o[0].cpu() == r[0]).all()
+    # an empty mesh in the batch and an empty batch
+    two_first = torch.tensor([0, 3], dtype=torch.int64, device=DEV)
+    o = hf.rasterize_meshes(t3, 8, 0.0, 1, mesh_to_face_first_idx=two_first, num_faces_per_mesh=torch.tensor([3, 0], device=DEV))
+    assert (o[0][1] == -1).all() and (o[0][0] >= 0).any()
+    # argument errors surface as Python exceptions (PyTorch3D raises ValueError for bad settings)
+    with pytest.raises(ValueError):
+        hf.rasterize_meshes(t3, 8, 0.0, 17, mesh_to_face_first_idx=first, num_faces_per_mesh=torch.tensor([3], device=DEV))
+    with pytest.raises(Exception):
+        hf.rasterize_meshes(t3.cpu(), 8, 0.0, 1, mesh_to_face_first_idx=first, num_faces_per_mesh=torch.tensor([3], device=DEV))
+
+
+def test_rasterizer_many_faces_in_one_tile(hf, mano):
+    """A far-away hand: all 1538 faces land in one or two tiles (exercises batched list staging)."""
+    fv, first, nf = _face_verts(mano, 1, seed=77)
+    fv = fv.clone()
+    fv[..., :2] = fv[..., :2] * 0.08
+    ref = raster_c.rasterize_naive(fv, first, nf, 64, 9.21e-4, 8)
+    out = hf.rasterize_meshes(fv.to(DEV), 64, 9.21e-4, 8, perspective_correct=True, clip_barycentric_coords=True,
+                              mesh_to_face_first_idx=torch.tensor(first, device=DEV), num_faces_per_mesh=torch.tensor(nf, device=DEV))
+    for g, r in zip(out, ref):
+        assert (g.cpu() == r).all()
+
+
+def test_rasterizer_backward(hf, mano):
+    fv, first, nf = _face_verts(mano, 1, seed=5)
+    H = W = 64
+    for K, blur in [(1, 0.0), (4, 9.21e-4)]:
+        f_cpu = fv.clone().requires_grad_(True)
+        fr = p3d.rasterize_meshes(f_cpu, first, nf, (H, W), blur, K)
+        g = torch.Generator().manual_seed(K)
+        gz, gb, gd = torch.randn(fr.zbuf.shape, generator=g), torch.randn(fr.bary_coords.shape, generator=g), torch.randn(fr.dists.shape, generator=g) * 1e-2
+        mk = (fr.pix_to_face >= 0).float()
+        ((fr.zbuf * gz * mk).sum() + (fr.bary_coords * gb * mk[..., None]).sum() + (fr.dists * gd * mk).sum()).backward()
+        f_gpu = fv.clone().to(DEV).requires_grad_(True)
+        o = hf.rasterize_meshes(f_gpu, (H, W), blur, K, perspective_correct=True, clip_barycentric_coords=blur > 0,
+                                mesh_to_face_first_idx=torch.tensor(first, device=DEV), num_faces_per_mesh=torch.tensor(nf, device=DEV))
+        mkg = (o[0] >= 0).float()
+        ((o[1] * gz.to(DEV) * mkg).sum() + (o[2] * gb.to(DEV) * mkg[..., None]).sum() + (o[3] * gd.to(DEV) * mkg).sum()).backward()
+        assert rel_err(f_gpu.grad, f_cpu.grad) < 1e-3
+
+
+# ------------------------------------------------------------------------------------------ renderer API + shading
+def _render_modular(hf, inp, texture, S, aa, K, blur, soft, binarize, requires_grad=True):
+    model = hf.HandRenderModel(True, DEV, image_size=S, aa_factor=aa, blur_radius=blur, faces_per_pixel=K, soft=soft,
+                               binarize=binarize, texture_size=texture.shape[1]).to(DEV)
+    with torch.no_grad():
+        model.texture.copy_(texture.to(DEV))
+    pose = inp["pose"].to(DEV).requires_grad_(requires_grad)
+    betas = inp["betas"].to(DEV).requires_grad_(requires_grad)
+    ldir = inp["light_dir"].to(DEV).requires_grad_(requires_grad)
+    lcol = inp["light_color"].to(DEV).requires_grad_(requires_grad)
+    out = model({"pose_params": pose, "shape_params": betas}, {"colors": lcol, "directions": ldir},
+                Ks=inp["Ks"].to(DEV), root_xyz=inp["root_xyz"].to(DEV)[:, None], images=inp["imgs"].to(DEV))
+    return model, out, dict(pose=pose, betas=betas, light_dir=ldir, light_color=lcol)
+
+
+@pytest.mark.parametrize("S,aa,K,blur,soft,binarize,sil_scale", [(48, 1, 4, 9.21e-4, True, False, 1.0),
+                                                                 (32, 3, 1, 0.0, False, True, 255.0)])
+def test_full_path_modular_vs_oracle(hf, mano, S, aa, K, blur, soft, binarize, sil_scale):
+    """hand layer -> joints -> root shift -> camera -> rasterize -> Phong/UV -> blend -> pool -> losses, fwd + bwd,
+    through the reference-named objects.  Second case = the reference's own setting (SSAA 3x, K=1, hard, binarised)."""
+    B = 2
+    inp = P.synthetic_inputs(B, S=S, seed=31)
+    tex = P.synthetic_texture(64)
+    lam = dict(texture=1.0, mrgb=0.5, ssim_tex=0.7, sil=0.3, iou=0.2)
+    # oracle
+    oi = {k: v.clone() for k, v in inp.items()}
+    for k in ("pose", "betas", "light_dir", "light_color"):
+        oi[k].requires_grad_(True)
+    tex_o = tex.clone().requires_grad_(True)
+    ro = P.render_path(mano, oi, tex_o, image_size=S, aa=aa, K=K, blur_radius=blur, soft=soft, binarize=binarize)
+    loss_o, terms_o = P.total_loss(ro, oi, lam, sil_scale)
+    loss_o.backward()
+    # product
+    model, out, leaves = _render_modular(hf, inp, tex, S, aa, K, blur, soft, binarize)
+    assert (out["joints"].cpu() - ro["joints"]).abs().max() < 1e-6
+    assert (out["mano_verts"].cpu() - ro["verts_rel"]).abs().max() < 1e-6
+    assert out["re_img"].shape == (B, 3, S, S) and out["re_sil"].shape == (B, 1, S, S)
+    assert out["mano_faces"].shape == (B, 1538, 3) and out["maskRGBs"].shape == (B, 3, S, S)
+    # a handful of edge pixels may pick a different face because the projected verts differ in the last bit
+    diff_img = (out["re_img"].cpu() - ro["re_img"]).abs().amax(1)
+    assert (diff_img > 1e-4).float().mean() < 2e-3
+    assert (out["re_sil"].cpu() - ro["re_sil"]).abs().max() < (1e-3 if not binarize else 256)
+
+    class A:
+        lambda_texture, lambda_mrgb, lambda_ssim_tex, lambda_silhouette, lambda_iou = (lam["texture"], lam["mrgb"],
+                                                                                        lam["ssim_tex"], lam["sil"], lam["iou"])
+    lf = hf.LossFunction(sil_scale=sil_scale)
+    ld = lf({"imgs": inp["imgs"].to(DEV), "segms_gt": inp["segms_gt"].to(DEV)}, out, ["sil", "iou"], "FreiHAND", A)
+    for k in lam:
+        assert abs(float(ld[k]) - float(terms_o[k])) < 2e-4 * max(1.0, abs(float(terms_o[k]))), k
+    sum(ld.values()).backward()
+    assert rel_err(leaves["pose"].grad, oi["pose"].grad) < 2e-2
+    assert rel_err(leaves["betas"].grad, oi["betas"].grad) < 2e-2
+    assert rel_err(model.texture.grad, tex_o.grad) < 2e-2
+    assert rel_err(leaves["light_color"].grad, oi["light_color"].grad) < 2e-2
+    assert rel_err(leaves["light_dir"].grad, oi["light_dir"].grad) < 2e-2
+
+
+def test_shader_forward_backward_on_oracle_fragments(hf, mano):
+    """Shading + blending in isolation: identical Fragments in, image and all gradients compared."""
+    from hifihr_b200 import ops
+    B, S, K = 2, 40, 4
+    inp = P.synthetic_inputs(B, S=S, seed=8)
+    tex = P.synthetic_texture(32)
+    ro = P.render_path(mano, inp, tex, image_size=S, K=K, blur_radius=9.21e-4, soft=True)
+    fr = ro["fragments"]
+    faces = torch.tensor(np.asarray(mano["f"], np.int64))
+    uvs, fuv = P.mano_uvs(mano)
+    leaves_o = [t.detach().clone().requires_grad_(True) for t in
+                (fr.zbuf, fr.bary_coords, fr.dists, ro["verts_view"], tex, inp["light_dir"], inp["light_color"])]
+    z, b, d, vv, tx, ldir, lcol = leaves_o
+    fro = p3d.Fragments(fr.pix_to_face, z, b, d)
+    img_o = p3d.softmax_rgb_blend(p3d.phong_shading(fro, vv, faces, p3d.sample_textures_uv(fro, tx, fuv, uvs), ldir, lcol), fro)
+    g = torch.Generator().manual_seed(2)
+    gi = torch.randn(img_o.shape, generator=g)
+    (img_o * gi).sum().backward()
+    layer = hf.MyMANOLayer(True, DEV, shape_ncomp=10, pose_ncomp=48, tex_ncomp=None)
+    leaves_g = [t.detach().clone().to(DEV).requires_grad_(True) for t in leaves_o]
+    zg, bg, dg, vvg, txg, ldg, lcg = leaves_g
+    meshes = hf.Meshes(vvg, layer.mesh_face, topology=layer.topology(DEV))
+    meshes.textures = hf.TexturesUV(txg, fuv.to(DEV), uvs.to(DEV))
+    shader = hf.SoftPhongShader(materials=hf.Materials(diffuse_color=((0.8, 0.8, 0.8),), specular_color=((0.2, 0.2, 0.2),), shininess=30))
+    img_g = shader(hf.Fragments(fr.pix_to_face.to(DEV), zg, bg, dg), meshes,
+                   lights=hf.DirectionalLights(diffuse_color=lcg, direction=ldg, device=DEV))
+    assert (img_g.cpu() - img_o).abs().max() < 2e-5
+    (img_g * gi.to(DEV)).sum().backward()
+    for name, a, o in zip(("zbuf", "bary", "dists", "verts", "texture", "light_dir", "light_color"), leaves_g, leaves_o):
+        assert rel_err(a.grad, o.grad) < 5e-3, name
+    # silhouette shader
+    sil = hf.SoftSilhouetteShader()(hf.Fragments(fr.pix_to_face.to(DEV), zg.detach(), bg.detach(), dg.detach()), meshes)
+    sil_o = p3d.sigmoid_alpha_blend(torch.ones_like(fr.bary_coords), fr)
+    assert (sil.cpu() - sil_o).abs().max() < 1e-5
+
+
+# ------------------------------------------------------------------------------------------ losses
+@pytest.mark.parametrize("sil_scale", [1.0, 255.0])
+def test_losses_forward_backward(hf, sil_scale):
+    from hifihr_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    N, S = 3, 45
+    re_img = torch.rand(N, 3, S, S, generator=g)
+    re_sil = torch.rand(N, 1, S, S, generator=g) * sil_scale
+    imgs = torch.rand(N, 3, S, S, generator=g)
+    seg = (torch.rand(N, S, S, generator=g) > 0.5).long()
+    lam = dict(texture=1.0, mrgb=2.0, ssim_tex=0.5, sil=0.25, iou=0.75)
+    a, b = re_img.clone().requires_grad_(True), re_sil.clone().requires_grad_(True)
+    terms = olosses.render_losses(a, b, imgs, seg, lam, sil_scale=sil_scale)
+    sum(terms.values()).backward()
+    ag, bg = re_img.to(DEV).requires_grad_(True), re_sil.to(DEV).requires_grad_(True)
+    t = ops.RenderLossFunction.apply(ag, bg, imgs.to(DEV), seg.float().to(DEV), sil_scale, True)
+    w = torch.tensor([lam["texture"], lam["mrgb"], lam["ssim_tex"], lam["sil"], lam["iou"]], device=DEV)
+    for i, k in enumerate(("texture", "mrgb", "ssim_tex", "sil", "iou")):
+        assert abs(float(t[i]) * lam[k] - float(terms[k])) < 1e-5 * max(1.0, abs(float(terms[k]))), k
+    (t * w).sum().backward()
+    assert rel_err(ag.grad, a.grad) < 1e-3
+    assert rel_err(bg.grad, b.grad) < 1e-3
+
+
+# ------------------------------------------------------------------------------------------ fused step
+def test_fused_step_vs_oracle(hf, mano):
+    B, S, K = 3, 64, 4
+    inp = P.synthetic_inputs(B, S=S, seed=12)
+    lam = dict(texture=1.0, mrgb=1.0, ssim_tex=1.0, sil=1.0, iou=0.5)
+    step = hf.FusedHandStep(B, image_size=S, faces_per_pixel=K, soft=True, texture_size=64, lambdas=lam, device=DEV)
+    tex = step.texture.detach().cpu().clone()
+    oi = {k: v.clone() for k, v in inp.items()}
+    for k in ("pose", "betas", "light_dir", "light_color"):
+        oi[k].requires_grad_(True)
+    tex_o = tex.clone().requires_grad_(True)
+    ro = P.render_path(mano, oi, tex_o, image_size=S, K=K, blur_radius=step.blur, soft=True)
+    loss_o, terms_o = P.total_loss(ro, oi, lam, 1.0)
+    loss_o.backward()
+    fcl, prp = p3d.ndc_intrinsics(inp["Ks"])
+    d = lambda t: t.to(DEV).contiguous()  # noqa: E731
+    args = (d(inp["pose"]), d(inp["betas"]), d(-fcl), d(prp), d(inp["root_xyz"]), d(inp["light_dir"]),
+            d(inp["light_color"]), d(inp["imgs"]), d(inp["segms_gt"].float()))
+    step.step(*args)
+    torch.cuda.synchronize()
+    # Fragments from the fused kernel are bit-exact against the C oracle run on the kernel's own face_verts
+    fv = step.face_verts.cpu()
+    Fm = 1538
+    ref = raster_c.rasterize_naive(fv, [i * Fm for i in range(B)], [Fm] * B, S, step.blur, K, threads=8)
+    assert (step.p2f.cpu() == ref[0]).all() and (step.zbuf.cpu() == ref[1]).all()
+    assert (step.bary.cpu() == ref[2]).all() and (step.dists.cpu() == ref[3]).all()
+    terms = step.loss_terms().cpu()
+    for i, k in enumerate(("texture", "mrgb", "ssim_tex", "sil", "iou")):
+        assert abs(float(terms[i]) * lam[k] - float(terms_o[k])) < 5e-4 * max(1.0, abs(float(terms_o[k]))), k
+    assert rel_err(step.g_pose, oi["pose"].grad) < 2e-2
+    assert rel_err(step.g_betas, oi["betas"].grad) < 2e-2
+    assert rel_err(step.g_texture, tex_o.grad) < 2e-2
+    assert rel_err(step.g_light_color, oi["light_color"].grad) < 2e-2
+    assert rel_err(step.g_light_dir, oi["light_dir"].grad) < 2e-2
+    # running the step again gives the same Fragments (determinism of the forward)
+    p2f0, z0 = step.p2f.clone(), step.zbuf.clone()
+    step.step(*args)
+    torch.cuda.synchronize()
+    assert (step.p2f == p2f0).all() and (step.zbuf == z0).all()
+
+
+def test_full_size_properties_c2(hf, mano):
+    """BASELINE config 2 sizes (B=64, 224^2, K=4, soft): size-independent properties + a sampled bit-exact check."""
+    B, S, K = 64, 224, 4
+    inp = P.synthetic_inputs(B, S=S, seed=1234)
+    step = hf.FusedHandStep(B, image_size=S, faces_per_pixel=K, soft=True, texture_size=512, device=DEV)
+    fcl, prp = p3d.ndc_intrinsics(inp["Ks"])
+    d = lambda t: t.to(DEV).contiguous()  # noqa: E731
+    args = (d(inp["pose"]), d(inp["betas"]), d(-fcl), d(prp), d(inp["root_xyz"]), d(inp["light_dir"]),
+            d(inp["light_color"]), d(inp["imgs"]), d(inp["segms_gt"].float()))
+    step.step(*args)
+    torch.cuda.synchronize()
+    p2f, z = step.p2f, step.zbuf
+    valid = p2f >= 0
+    n_idx = torch.arange(B, device=DEV).view(B, 1, 1, 1)
+    assert ((p2f[valid] // 1538) == n_idx.expand_as(p2f)[valid]).all()      # packed ids stay inside their mesh
+    zz = torch.where(valid, z, torch.full_like(z, float("inf")))
+    assert (zz[..., 1:] >= zz[..., :-1]).all()                              # sorted by depth
+    assert (valid[..., 1:] <= valid[..., :-1]).all()                        # no holes before filled slots
+    assert (step.bary[valid].sum(-1) - 1).abs().max() < 1e-4                # clipped barycentrics sum to 1
+    img = step.image
+    assert torch.isfinite(img).all() and (img[..., 3] >= 0).all() and (img[..., 3] <= 1).all()
+    assert ((img[..., 3] > 0) == valid.any(-1)).all()
+    for t in (step.g_pose, step.g_betas, step.g_texture, step.g_light_dir, step.g_light_color):
+        assert torch.isfinite(t).all() and t.abs().sum() > 0
+    for n in (0, 37, 63):                                                    # sampled bit-exact check
+        fv = step.face_verts[n * 1538:(n + 1) * 1538].cpu()
+        ref = raster_c.rasterize_naive(fv, [0], [1538], S, step.blur, K, threads=8)
+        assert ((p2f[n].cpu() - n * 1538).where(p2f[n].cpu() >= 0, torch.tensor(-1)) == ref[0][0]).all()
+        assert (z[n].cpu() == ref[1][0]).all() and (step.dists[n].cpu() == ref[3][0]).all()

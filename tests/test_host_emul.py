@@ -1,0 +1,191 @@
+"""No-GPU checks of the kernels' per-element math (the *_math.cuh headers compiled for the host by
+tests/host_emul) against the oracle.  Test-only: the product has no CPU path."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from hifihr_b200 import _lib as L
+from oracle import p3d, raster_c
+from oracle import pipeline as P
+from oracle.mano import rodrigues
+from tests.host_emul import load
+
+lib = load()
+ptr = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+
+
+def _scene(mano, B=1, S=48, K=4, blur=9.21e-4, soft=True, seed=7):
+    inp = P.synthetic_inputs(B, S=S, seed=seed)
+    tex = P.synthetic_texture(64)
+    out = P.render_path(mano, inp, tex, image_size=S, aa=1, K=K, blur_radius=blur, soft=soft)
+    return inp, tex, out
+
+
+def test_rodrigues_fwd_bwd():
+    g = torch.Generator().manual_seed(0)
+    v = torch.randn(64, 3, generator=g)
+    v[0] = 0
+    v[1] = 1e-6
+    R = rodrigues(v).reshape(64, 9).numpy()
+    vn, Rn = v.numpy().copy(), np.zeros((64, 9), np.float32)
+    lib.emul_rodrigues_fwd(ptr(vn), ptr(Rn), 64)
+    assert np.abs(Rn - R).max() < 5e-7
+    v64 = v.double().requires_grad_(True)
+    gR = torch.randn(64, 3, 3, generator=g)
+    (rodrigues(v64) * gR.double()).sum().backward()
+    gRn, gvn = gR.reshape(64, 9).numpy().copy(), np.zeros((64, 3), np.float32)
+    lib.emul_rodrigues_bwd(ptr(vn), ptr(gRn), ptr(gvn), 64)
+    assert np.abs(gvn - v64.grad.numpy()).max() < 5e-6
+
+
+@pytest.mark.parametrize("H,W,K,blur", [(64, 64, 1, 0.0), (40, 56, 4, 9.21e-4)])
+def test_raster_math_bit_exact_and_grad(mano, H, W, K, blur):
+    inp = P.synthetic_inputs(1, S=64, seed=3)
+    out = P.render_path(mano, inp, P.synthetic_texture(16), image_size=64, K=1)
+    faces = torch.tensor(np.asarray(mano["f"], np.int64))
+    fv = out["verts_ndc"][:, faces].reshape(-1, 3, 3).contiguous()
+    Fm = fv.shape[0]
+    c = raster_c.rasterize_naive(fv, [0], [Fm], (H, W), blur, K)
+    p2f = np.zeros((H, W, K), np.int64)
+    zb, ba, ds = np.zeros((H, W, K), np.float32), np.zeros((H, W, K, 3), np.float32), np.zeros((H, W, K), np.float32)
+    fvn = fv.numpy()
+    lib.emul_raster(ptr(fvn), C.c_int64(Fm), H, W, K, C.c_float(blur), 1, int(blur > 0), 0, ptr(p2f), ptr(zb), ptr(ba), ptr(ds))
+    assert (p2f == c[0][0].numpy()).all()
+    assert (zb == c[1][0].numpy()).all() and (ba == c[2][0].numpy()).all() and (ds == c[3][0].numpy()).all()
+    # backward against fp64 autograd of the oracle
+    g = torch.Generator().manual_seed(1)
+    f64 = fv.double().clone().requires_grad_(True)
+    fr = p3d.rasterize_meshes(f64, [0], [Fm], (H, W), blur, K)
+    if not (fr.pix_to_face[0].numpy() == p2f).all():
+        pytest.skip("fp64 oracle picks different faces at a tie")
+    gz, gb, gd = (torch.randn(fr.zbuf.shape, generator=g), torch.randn(fr.bary_coords.shape, generator=g),
+                  torch.randn(fr.dists.shape, generator=g) * 1e-2)
+    mk = (fr.pix_to_face >= 0).double()
+    ((fr.zbuf * gz * mk).sum() + (fr.bary_coords * gb * mk[..., None]).sum() + (fr.dists * gd * mk).sum()).backward()
+    gfv = np.zeros((Fm, 9), np.float32)
+    lib.emul_raster_bwd(ptr(fvn), ptr(p2f), ptr(gz[0].numpy().copy()), ptr(gb[0].numpy().copy()),
+                        ptr(gd[0].numpy().copy()), H, W, K, 1, int(blur > 0), ptr(gfv))
+    ref = f64.grad.reshape(-1, 9).numpy()
+    assert np.abs(gfv - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max())
+
+
+def _shade_args(mano, inp, tex, out, K, soft, keep):
+    fr = out["fragments"]
+    N, H, W, _ = fr.pix_to_face.shape
+    faces = np.ascontiguousarray(np.asarray(mano["f"], np.int32))
+    uvs, fuv = P.mano_uvs(mano)
+    vn = p3d.vertex_normals(out["verts_view"], torch.tensor(faces.astype(np.int64)))
+    arrs = dict(p2f=fr.pix_to_face.numpy().copy(), z=fr.zbuf.detach().numpy().copy(),
+                b=fr.bary_coords.detach().numpy().copy(), d=fr.dists.detach().numpy().copy(), faces=faces,
+                vv=out["verts_view"].detach().numpy().copy(), vn=vn.detach().numpy().copy(),
+                fuv=fuv.numpy().astype(np.int32).copy(), uvs=uvs.numpy().copy(), tex=tex.detach().numpy().copy(),
+                ld=inp["light_dir"].numpy().copy(), lc=inp["light_color"].numpy().copy(),
+                img=np.zeros((N, H, W, 4), np.float32))
+    keep.append(arrs)
+    p = L.HfrShadeParams()
+    p.N, p.H, p.W, p.K, p.F, p.V = N, H, W, K, faces.shape[0], 778
+    p.blend, p.shade = (2 if soft else 0), 1
+    p.sigma, p.gamma, p.znear, p.zfar = 1e-4, 1e-4, 1.0, 100.0
+    p.background = L.f3((1, 1, 1)); p.light_ambient = L.f3((.5, .5, .5)); p.light_specular = L.f3((.2, .2, .2))
+    p.mat_ambient = L.f3((1, 1, 1)); p.mat_diffuse = L.f3((.8, .8, .8)); p.mat_specular = L.f3((.2, .2, .2))
+    p.shininess = 30.0
+    p.tex_n, p.tex_h, p.tex_w, p.VT = 1, tex.shape[1], tex.shape[2], 778
+    a = L.HfrShadeFwdArgs(p, *[arrs[k].ctypes.data for k in ("p2f", "z", "b", "d", "faces", "vv", "vn", "fuv", "uvs",
+                                                              "tex", "ld", "lc", "img")])
+    return a, arrs
+
+
+@pytest.mark.parametrize("soft,K,blur", [(True, 4, 9.21e-4), (False, 1, 0.0)])
+def test_shade_forward_matches_oracle(mano, soft, K, blur):
+    inp, tex, out = _scene(mano, B=2, S=40, K=K, blur=blur, soft=soft)
+    keep = []
+    a, arrs = _shade_args(mano, inp, tex, out, K, soft, keep)
+    lib.emul_shade_fwd(C.byref(a))
+    ref = out["image"].detach().numpy()
+    assert np.abs(arrs["img"] - ref).max() < 2e-5
+
+
+def test_blend_backward_matches_autograd(mano):
+    inp, tex, out = _scene(mano, B=1, S=40, K=4)
+    fr = out["fragments"]
+    Pn = 40 * 40
+    g = torch.Generator().manual_seed(5)
+    # fp32 oracle: with gamma = 1e-4 the exponent (z_inv - z_max)/gamma amplifies fp32 rounding of z_inv to
+    # ~1e-3 relative, so the like-for-like comparison is against the fp32 autograd of the same formulas
+    colors = torch.rand(1, 40, 40, 4, 3, generator=g).requires_grad_(True)
+    z = fr.zbuf.detach().clone().requires_grad_(True)
+    d = fr.dists.detach().clone().requires_grad_(True)
+    frd = p3d.Fragments(fr.pix_to_face, z, fr.bary_coords.detach(), d)
+    img = p3d.softmax_rgb_blend(colors, frd)
+    grgba = torch.randn(img.shape, generator=g)
+    (img * grgba).sum().backward()
+    p = L.HfrShadeParams()
+    p.K, p.blend, p.sigma, p.gamma, p.znear, p.zfar = 4, 2, 1e-4, 1e-4, 1.0, 100.0
+    p.background = L.f3((1, 1, 1))
+    idn = fr.pix_to_face.numpy().reshape(Pn, 4).copy()
+    zn, dn = z.detach().float().numpy().reshape(Pn, 4).copy(), d.detach().float().numpy().reshape(Pn, 4).copy()
+    cn = colors.detach().float().numpy().reshape(Pn, 4, 3).copy()
+    gn = grgba.float().numpy().reshape(Pn, 4).copy()
+    gc, gz, gd = np.zeros((Pn, 4, 3), np.float32), np.zeros((Pn, 4), np.float32), np.zeros((Pn, 4), np.float32)
+    lib.emul_blend_bwd(C.byref(p), Pn, ptr(idn), ptr(zn), ptr(dn), ptr(cn), ptr(gn), ptr(gc), ptr(gz), ptr(gd))
+    mk = (idn >= 0)
+    rc = colors.grad.numpy().reshape(Pn, 4, 3) * mk[..., None]
+    rz, rd = z.grad.numpy().reshape(Pn, 4), d.grad.numpy().reshape(Pn, 4)
+    assert np.abs(gc - rc).max() < 1e-4 * max(1, np.abs(rc).max())
+    assert np.abs(gd - rd).max() < 2e-3 * max(1, np.abs(rd).max())
+    assert np.abs(gz - rz).max() < 2e-3 * max(1, np.abs(rz).max())
+
+
+def test_phong_and_texture_backward_match_autograd():
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(11)
+    M = 200
+    Pp = (torch.randn(M, 3, generator=g, dtype=torch.float64) * 0.1 + torch.tensor([0, 0, 0.6])).requires_grad_(True)
+    Nn = torch.randn(M, 3, generator=g, dtype=torch.float64).requires_grad_(True)
+    ld = torch.randn(3, generator=g, dtype=torch.float64).requires_grad_(True)
+    lc = (torch.rand(3, generator=g, dtype=torch.float64) * 0.8 + 0.2).requires_grad_(True)
+    tx = torch.rand(M, 3, generator=g, dtype=torch.float64).requires_grad_(True)
+    n_hat = F.normalize(Nn, eps=1e-6, dim=-1)
+    d_hat = F.normalize(ld, eps=1e-6, dim=-1)
+    cosang = (n_hat * d_hat).sum(-1)
+    diffuse = lc * F.relu(cosang)[:, None]
+    view = F.normalize(-Pp, eps=1e-6, dim=-1)
+    refl = -d_hat + 2 * cosang[:, None] * n_hat
+    alpha = F.relu((view * refl).sum(-1)) * (cosang > 0).double()
+    spec = 0.2 * torch.pow(alpha, 30.0)[:, None]
+    color = (0.5 + 0.8 * diffuse) * tx + 0.2 * spec
+    gcol = torch.randn(M, 3, generator=g, dtype=torch.float64)
+    (color * gcol).sum().backward()
+    p = L.HfrShadeParams()
+    p.light_ambient = L.f3((.5, .5, .5)); p.light_specular = L.f3((.2, .2, .2))
+    p.mat_ambient = L.f3((1, 1, 1)); p.mat_diffuse = L.f3((.8, .8, .8)); p.mat_specular = L.f3((.2, .2, .2))
+    p.shininess = 30.0
+    f = lambda t: t.detach().float().numpy().copy()  # noqa: E731
+    dh = f(d_hat)
+    out, gP, gN, gT = (np.zeros((M, 3), np.float32) for _ in range(4))
+    gdh, glc = np.zeros(3, np.float32), np.zeros(3, np.float32)
+    lib.emul_phong(C.byref(p), M, ptr(f(Pp)), ptr(f(Nn)), ptr(dh), ptr(f(lc)), ptr(f(tx)), ptr(f(gcol)), ptr(out),
+                   ptr(gP), ptr(gN), ptr(gT), ptr(gdh), ptr(glc))
+    assert np.abs(out - f(color)).max() < 1e-5
+    for got, ref in ((gP, Pp.grad), (gN, Nn.grad), (gT, tx.grad), (glc, lc.grad)):
+        assert np.abs(got - ref.numpy()).max() < 1e-4 * max(1, ref.abs().max().item())
+    # g_dhat -> g_dir through the normalisation
+    dl = ld.detach().norm().item()
+    gdir = (gdh - dh * (dh @ gdh)) / dl
+    assert np.abs(gdir - ld.grad.numpy()).max() < 1e-4 * max(1, ld.grad.abs().max().item())
+    # texture sampling
+    Ht, Wt = 12, 16
+    tex = torch.rand(1, Ht, Wt, 3, generator=g, dtype=torch.float64).requires_grad_(True)
+    uv = (torch.rand(M, 2, generator=g, dtype=torch.float64) * 1.2 - 0.1).requires_grad_(True)
+    grid = (uv * 2 - 1).view(1, M, 1, 2)
+    tm = torch.flip(tex.permute(0, 3, 1, 2), [2])
+    smp = F.grid_sample(tm, grid, mode="bilinear", align_corners=True, padding_mode="border")[0, :, :, 0].T
+    gs = torch.randn(M, 3, generator=g, dtype=torch.float64)
+    (smp * gs).sum().backward()
+    o, guv, gtex = np.zeros((M, 3), np.float32), np.zeros((M, 2), np.float32), np.zeros((Ht, Wt, 3), np.float32)
+    lib.emul_tex(ptr(f(tex)), Ht, Wt, M, ptr(f(uv)), ptr(f(gs)), ptr(o), ptr(guv), ptr(gtex))
+    assert np.abs(o - f(smp)).max() < 1e-5
+    assert np.abs(guv - uv.grad.numpy()).max() < 1e-3 * max(1, uv.grad.abs().max().item())
+    assert np.abs(gtex - tex.grad[0].numpy()).max() < 1e-4 * max(1, tex.grad.abs().max().item())

@@ -1,0 +1,166 @@
+"""CPU: pin the oracle (golden vectors from the unmodified reference, known answers, two independent
+restatements agreeing) and check the C-ABI library exports what include/hifihr_b200.h declares."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import losses as olosses
+from oracle import p3d, raster_c, ref_mano
+from oracle import pipeline as P
+from oracle.mano import ManoOracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def test_mano_oracle_matches_reference_golden(mano):
+    z = np.load(os.path.join(GOLD, "mano_reference.npz"))
+    orc = ManoOracle(mano)
+    pose = torch.tensor(z["pose"], requires_grad=True)
+    beta = torch.tensor(z["beta"], requires_grad=True)
+    v, j = orc(pose, beta)
+    assert (v.detach() - torch.tensor(z["verts"])).abs().max() < 1e-7
+    assert (j.detach() - torch.tensor(z["joints"])).abs().max() < 1e-7
+    ((v * torch.tensor(z["g_verts"])).sum() + (j * torch.tensor(z["g_joints"])).sum()).backward()
+    assert (pose.grad - torch.tensor(z["g_pose"])).abs().max() < 2e-5 * np.abs(z["g_pose"]).max()
+    assert (beta.grad - torch.tensor(z["g_beta"])).abs().max() < 2e-5 * np.abs(z["g_beta"]).max()
+
+
+def test_mano_known_answers_appendix_c(mano):
+    """SURVEY.md Appendix C (values printed by the reference ManoLayer, torch CPU fp32)."""
+    orc = ManoOracle(mano)
+    v, j = orc(torch.zeros(1, 48), torch.zeros(1, 10))
+    assert np.allclose(v[0, 0].numpy(), [0.04507172852754593, -0.01613779366016388, 0.01835748739540577], atol=1e-8)
+    assert abs(v.double().sum().item() - (-16.718705629871693)) < 1e-4
+    assert np.allclose(j[0, 0].numpy(), [0.09466041624546051, 0.0014789639972150326, 0.0033575384877622128], atol=1e-8)
+    assert j[0, 9].abs().max() == 0
+    g = torch.Generator().manual_seed(1234)
+    pose = torch.randn(4, 48, generator=g) * 0.5
+    beta = torch.randn(4, 10, generator=g) * 0.5
+    v, j = orc(pose, beta)
+    assert abs(v.double().sum().item() - (-70.60127041395754)) < 1e-4
+    assert np.allclose(j[3, 20].numpy(), [0.06128855049610138, -0.04273726046085358, 0.000701904296875], atol=1e-7)
+
+
+@pytest.mark.skipif(not ref_mano.available(), reason="reference tree not present (GPU box)")
+def test_mano_oracle_vs_live_reference(mano):
+    ref = ref_mano.reference_mano_layer()
+    orc = ManoOracle(mano)
+    g = torch.Generator().manual_seed(5)
+    pose = torch.cat([torch.randn(8, 3, generator=g) * 1.5, torch.randn(8, 45, generator=g) * 0.5], 1)
+    beta = torch.randn(8, 10, generator=g) * 0.5
+    v, j = ref(pose, beta)
+    vo, jo = orc(pose, beta)
+    assert (v - vo).abs().max() < 1e-7 and (j - jo).abs().max() < 1e-7
+
+
+def test_ssim_oracle_matches_reference_golden():
+    z = np.load(os.path.join(GOLD, "ssim_reference.npz"))
+    a, b = torch.tensor(z["a"]), torch.tensor(z["b"])
+    assert abs(float(olosses.ssim(a, b)) - float(z["ssim"])) < 1e-6
+    assert abs(float(olosses.ssim(a, a)) - float(z["ssim_same"])) < 1e-6
+
+
+def test_raster_two_restatements_agree_and_golden():
+    z = np.load(os.path.join(GOLD, "raster_oracle.npz"))
+    fv = torch.tensor(z["face_verts"])
+    Fm = fv.shape[0]
+    c = raster_c.rasterize_naive(fv, [0], [Fm], 32, 9.21e-4, 2)
+    t = p3d.rasterize_meshes(fv, [0], [Fm], 32, 9.21e-4, 2)
+    assert (c[0] == t.pix_to_face).all() and (c[1] == t.zbuf).all() and (c[2] == t.bary_coords).all() and (c[3] == t.dists).all()
+    assert (c[0].numpy() == z["pix_to_face"]).all() and (c[1].numpy() == z["zbuf"]).all()
+    assert (c[2].numpy() == z["bary"]).all() and (c[3].numpy() == z["dists"]).all()
+
+
+def test_raster_known_answers_single_triangle():
+    """Analytic cases: one front-facing triangle, z=2 plane, 8x8 image."""
+    fv = torch.tensor([[[-0.9, -0.9, 2.0], [0.9, -0.9, 2.0], [0.0, 0.9, 2.0]]])
+    p2f, zb, ba, ds = raster_c.rasterize_naive(fv, [0], [1], 8, 0.0, 1, perspective_correct=True)
+    cov = p2f[0, ..., 0] >= 0
+    assert cov.any() and (zb[0, ..., 0][cov] - 2.0).abs().max() < 1e-6          # constant depth
+    assert (ba[0, ..., 0, :][cov].sum(-1) - 1).abs().max() < 1e-6               # barycentrics sum to 1
+    assert (ba[0, ..., 0, :][cov] > 0).all() and (ds[0, ..., 0][cov] < 0).all()  # strictly inside, negative dist
+    # NDC +x is LEFT and +y is UP: the apex (y=+0.9) must be in the top rows, the base in the bottom rows
+    rows = cov.any(1).nonzero().flatten()
+    assert cov[rows[0]].sum() < cov[rows[-1]].sum()
+    # a pixel centre exactly on an edge belongs to no face (strict >): triangle with an edge through x=0.125
+    fv2 = torch.tensor([[[0.125, -1.0, 1.0], [0.125, 1.0, 1.0], [-1.0, 0.0, 1.0]]])
+    p2 = raster_c.rasterize_naive(fv2, [0], [1], 8, 0.0, 1)[0][0, ..., 0]
+    xf = p3d.pixel_centers(8, 8)[1]
+    col = int((xf == 0.125).nonzero()[0])
+    assert (p2[:, col] == -1).all()
+    # depth order + tie: two coincident faces -> smaller index wins; nearer face wins
+    tri = [[-0.9, -0.9, 2.0], [0.9, -0.9, 2.0], [0.0, 0.9, 2.0]]
+    near = [[-0.9, -0.9, 1.5], [0.9, -0.9, 1.5], [0.0, 0.9, 1.5]]
+    p3 = raster_c.rasterize_naive(torch.tensor([tri, tri, near]), [0], [3], 8, 0.0, 3)[0][0]
+    c3 = p3[..., 0] >= 0
+    assert (p3[..., 0][c3] == 2).all() and (p3[..., 1][c3] == 0).all() and (p3[..., 2][c3] == 1).all()
+    # behind the camera / degenerate faces never rasterize
+    bad = torch.tensor([[[-0.9, -0.9, -1.0], [0.9, -0.9, 2.0], [0.0, 0.9, 2.0]],
+                        [[0.1, 0.1, 1.0], [0.1, 0.1, 1.0], [0.2, 0.2, 1.0]]])
+    assert (raster_c.rasterize_naive(bad, [0], [2], 8, 1e-3, 2)[0] == -1).all()
+
+
+def test_soft_blend_known_answer():
+    """One fragment exactly on an edge (dist 0): prob 0.5 -> alpha 0.5; empty pixel -> background, alpha 0."""
+    p2f = torch.tensor([[[[0, -1]], [[-1, -1]]]])
+    fr = p3d.Fragments(p2f, torch.tensor([[[[0.5, -1.0]], [[-1.0, -1.0]]]]), torch.zeros(1, 2, 1, 2, 3),
+                       torch.tensor([[[[0.0, -1.0]], [[-1.0, -1.0]]]]))
+    col = torch.zeros(1, 2, 1, 2, 3)
+    img = p3d.softmax_rgb_blend(col, fr)
+    assert abs(float(img[0, 0, 0, 3]) - 0.5) < 1e-6 and float(img[0, 1, 0, 3]) == 0
+    assert (img[0, 1, 0, :3] - 1).abs().max() < 1e-6 and img[0, 0, 0, :3].abs().max() < 1e-3
+    sil = p3d.sigmoid_alpha_blend(torch.ones(1, 2, 1, 2, 3), fr)
+    assert abs(float(sil[0, 0, 0, 3]) - 0.5) < 1e-6
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "hifihr_b200.h")).read()
+    declared = set(re.findall(r"\b(hfr_[a-z_0-9]+)\s*\(", hdr))
+    from hifihr_b200 import _lib
+    from hifihr_b200.build import build
+    lib = ctypes.CDLL(build())
+    assert declared == set(_lib.ENTRY_POINTS), declared ^ set(_lib.ENTRY_POINTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.hfr_abi_version() == 1
+
+
+def test_ctypes_struct_sizes_match_header():
+    """sizeof() of every ctypes mirror against a C translation unit compiled from the header."""
+    import subprocess
+    import tempfile
+    from hifihr_b200 import _lib
+    names = ["HfrHandModel", "HfrManoFwdArgs", "HfrManoBwdArgs", "HfrTopology", "HfrGeomFwdArgs", "HfrGeomBwdArgs",
+             "HfrRasterArgs", "HfrRasterBwdArgs", "HfrShadeParams", "HfrShadeFwdArgs", "HfrShadeBwdArgs",
+             "HfrRasterShadeArgs", "HfrPoolArgs", "HfrPoolBwdArgs", "HfrLossArgs", "HfrLossBwdArgs"]
+    src = '#include <stdio.h>\n#include "hifihr_b200.h"\nint main(){' + "".join(
+        f'printf("%zu\\n", sizeof({n}));' for n in names) + "return 0;}"
+    with tempfile.TemporaryDirectory() as td:
+        c = os.path.join(td, "s.c")
+        open(c, "w").write(src)
+        exe = os.path.join(td, "s")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
+        sizes = [int(x) for x in subprocess.check_output([exe]).split()]
+    for n, sz in zip(names, sizes):
+        assert ctypes.sizeof(getattr(_lib, n)) == sz, (n, ctypes.sizeof(getattr(_lib, n)), sz)
+
+
+def test_product_has_no_cpu_path():
+    import hifihr_b200
+    layer = hifihr_b200.ManoLayer(center_idx=9, flat_hand_mean=False, ncomps=48)
+    with pytest.raises(RuntimeError):
+        layer(torch.zeros(1, 48), torch.zeros(1, 10))
+    with pytest.raises(Exception):
+        hifihr_b200.rasterize_meshes(torch.zeros(1, 3, 3), 8, mesh_to_face_first_idx=torch.zeros(1, dtype=torch.int64),
+                                     num_faces_per_mesh=torch.ones(1, dtype=torch.int64))
+    # the product never imports the oracle
+    import sys
+    pkg = os.path.join(ROOT, "hifihr_b200")
+    for f in os.listdir(pkg):
+        if f.endswith(".py"):
+            assert "oracle" not in open(os.path.join(pkg, f)).read().replace("no oracle", ""), f
