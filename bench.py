@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py — hand renders/sec (forward+backward) of the HiFiHR render hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W          # ours (hand-written sm_100a kernels)
+    python bench.py --impl reference --steps K --warmup W  # the reference CPU path (oracle port) on host cores
+
+Workload (N=1): BASELINE.json configs[1] = "C2": MANO LBS + soft rasterization (K=4, blur 9.21e-4) + Phong x UV
+texture (512^2, shared) + softmax blend + sil/texture/mrgb/SSIM losses with full backward, batch 64 per GPU,
+224x224, synthetic inputs.  One step = MANO -> geometry -> rasterize+shade -> loss ->
+loss' -> shade'+rasterize' -> geometry' -> MANO' over one batch.  N>1: one process per GPU (torchrun), the batch
+shards by sample (weak scaling, 64 per GPU); NCCL all-reduces the loss partial sums (needed by the mean-RGB term
+before its gradient) and the shared-texture gradient.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+CONFIGS = {
+    # name: (per-GPU batch, image size, K, soft, texture size)
+    "c2": dict(B=64, S=224, K=4, soft=True, T=512, desc="C2 MANO soft-raster K=4 + Phong/UV texture + losses, 224^2, B=64/GPU"),
+    "c4": dict(B=None, S=224, K=4, soft=True, T=512, desc="C4 as C2 with global batch 4096 sharded over the GPUs"),
+    "c5": dict(B=32, S=512, K=8, soft=True, T=512, desc="C5 soft raster 512^2 K=8, B=32/GPU (256 global at 8 GPUs)"),
+    "r": dict(B=48, S=672, K=1, soft=False, T=512, desc="reference setting 672^2 K=1 hard Phong (no pooling stage), B=48"),
+}
+LAMBDAS = dict(texture=1.0, mrgb=1.0, ssim_tex=1.0, sil=1.0, iou=0.0)
+
+
+def algorithmic_bytes_per_sample(S, K, V=778, T=512, B=64, n_params=58):
+    """Fragments written+read (56 B/pixel/K), image-side traffic (64 B/pixel), vertex streams,
+    parameters, shared texture read + grad write amortised over the per-GPU batch."""
+    P = S * S
+    return 56 * P * K + 64 * P + 48 * V + 8 * n_params + 24 * T * T / B
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json copy bandwidth)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(args, cfg):
+    """The reference's CPU implementation of the path, restated (oracle/): reference-identical MANO in torch,
+    scalar C naive rasterizer (all host threads), torch CPU shading / blending / losses, autograd backward.
+    PyTorch3D's CPU kernel is restated — upstream binary unavailable in this image."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from hifihr_b200.mano_assets import load_mano
+    from oracle import pipeline as P
+    from oracle import raster_c
+    raster_c.build()
+    mano = load_mano()
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    Bs = 2                                      # bounded sample per step
+    S, K = cfg["S"], cfg["K"]
+    blur = 9.21034e-4 if cfg["soft"] else 0.0
+    tex = P.synthetic_texture(cfg["T"])
+
+    def one_step(seed):
+        inp = P.synthetic_inputs(Bs, S=S, seed=seed)
+        inp["pose"].requires_grad_(True)
+        inp["betas"].requires_grad_(True)
+        t = tex.clone().requires_grad_(True)
+        out = P.render_path(mano, inp, t, image_size=S, K=K, blur_radius=blur, soft=cfg["soft"], c_select=True,
+                            threads=cores)
+        loss, _ = P.total_loss(out, inp, {k: v for k, v in LAMBDAS.items() if v}, 1.0)
+        loss.backward()
+        return float(loss.detach())
+
+    for w in range(args.warmup):
+        one_step(100 + w)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        one_step(200 + k)
+    dt = time.perf_counter() - t0
+    val = Bs * args.steps / dt
+    sample = f"{Bs} samples/step of {cfg['desc']} (fwd+bwd), {args.steps} steps"
+    line = {"impl": "reference", "metric": "hand renders/sec (fwd+bwd)", "value": val, "unit": "samples/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": cfg["desc"], "image_size": S, "faces_per_pixel": K, "sample_batch": Bs},
+            "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args, cfg):
+    import torch.distributed as dist
+    import hifihr_b200 as hf
+    from hifihr_b200 import _lib as L
+    from hifihr_b200 import dist as hdist
+    from hifihr_b200.synthetic import synthetic_inputs
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = cfg["B"] if cfg["B"] is not None else 4096 // world
+    if args.batch:
+        B = args.batch
+    S, K = cfg["S"], cfg["K"]
+    step = hf.FusedHandStep(B, image_size=S, faces_per_pixel=K, soft=cfg["soft"], texture_size=cfg["T"],
+                            lambdas=LAMBDAS, device=dev, n_global=B * world, sil_scale=1.0)
+    inp = synthetic_inputs(B, S=S, seed=1234 + rank)
+    fcl, prp = hf.get_ndc_fx_fy_cx_cy(inp["Ks"])
+    host = [inp["pose"], inp["betas"], -fcl, prp, inp["root_xyz"], inp["light_dir"], inp["light_color"], inp["imgs"],
+            inp["segms_gt"].float()]
+    host = [t.contiguous().pin_memory() for t in host]
+    devt = [t.to(dev, non_blocking=True) for t in host]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host)
+    sums_host = torch.empty(step.sums.shape, dtype=torch.float32).pin_memory()
+    gp_host = torch.empty(B, 48).pin_memory()
+    gb_host = torch.empty(B, 10).pin_memory()
+    d2h_bytes = sum(t.numel() * 4 for t in (sums_host, gp_host, gb_host))
+
+    def one_step(tensors):
+        pose, betas, focal, prpp, root, ldir, lcol, imgs, seg = tensors
+        step.forward(pose, betas, focal, prpp, root, ldir, lcol, imgs, seg)
+        hdist.all_reduce_loss_sums(step.sums)          # global means for the mean-RGB term (no-op at N=1)
+        step.backward(pose, betas, focal, prpp, root)
+        hdist.all_reduce_shared_grads(step.g_texture)  # gradient of the shared texture (no-op at N=1)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ----------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        one_step(devt)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            one_step(devt)
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    # ---- end to end: pinned host inputs in, loss + per-sample grads out, every step ----------------
+    def e2e_step():
+        t = [h.to(dev, non_blocking=True) for h in host]
+        one_step(t)
+        sums_host.copy_(step.sums, non_blocking=True)
+        gp_host.copy_(step.g_pose, non_blocking=True)
+        gb_host.copy_(step.g_betas, non_blocking=True)
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    # ---- per-kernel durations (CUDA events around each launch group, same stream) -----------------
+    names = ["mano_fwd", "geom_fwd", "raster_shade_fwd", "loss_fwd", "loss_bwd", "shade_raster_bwd", "geom_bwd", "mano_bwd"]
+    acc = {n: 0.0 for n in names}
+    reps = min(args.steps, 10)
+    pose, betas, focal, prpp, root, ldir, lcol, imgs, seg = devt
+
+    def timed(name, fn):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        return name, a, b
+
+    from hifihr_b200 import ops
+    for _ in range(reps):
+        ev = []
+        ev.append(timed("mano_fwd", lambda: ops.mano_forward_raw(step.hm, pose, betas, None, step.verts, None)))
+        ev.append(timed("geom_fwd", lambda: ops.geom_forward_raw(step.topo, step.verts, 9, root, focal, prpp, step.joints,
+                                                                 step.verts_rel, step.verts_view, step.verts_ndc,
+                                                                 step.vnormals, step.face_verts)))
+        def rs():
+            r = ops.raster_args(step.face_verts, step.mesh_first, step.mesh_nf, S, S, K, step.blur, True, step.blur > 0,
+                                False, step.p2f, step.zbuf, step.bary, step.dists, step.ws)
+            L.call("hfr_raster_shade_forward", L.HfrRasterShadeArgs(r, step._shade_args))
+        ev.append(timed("raster_shade_fwd", rs))
+        step.sums.zero_()
+        ev.append(timed("loss_fwd", lambda: L.call("hfr_loss_forward", step._loss_args)))
+        lb = L.HfrLossBwdArgs(step._loss_args, L.ptr(step.w), L.ptr(step.gauss), step.n_global * 3 * S * S, step.n_global,
+                              L.ptr(step.g_image), None)
+        ev.append(timed("loss_bwd", lambda: L.call("hfr_loss_backward", lb)))
+        step.acc.zero_()
+        sb = L.HfrShadeBwdArgs(step._shade_args, L.ptr(step.g_image), None, None, None, L.ptr(step.verts_ndc),
+                               L.ptr(step.g_ndc), float(step.blur), 1, int(step.blur > 0), L.ptr(step.g_view),
+                               L.ptr(step.g_vn), L.ptr(step.g_texture), L.ptr(step.g_light_dir), L.ptr(step.g_light_color))
+        ev.append(timed("shade_raster_bwd", lambda: L.call("hfr_shade_backward", sb)))
+        ev.append(timed("geom_bwd", lambda: ops.geom_backward_raw(step.topo, step.verts, 9, root, focal, prpp, None, None,
+                                                                  step.g_view, step.g_ndc, step.g_vn, step.g_verts)))
+        ev.append(timed("mano_bwd", lambda: ops.mano_backward_raw(step.hm, pose, betas, None, step.g_verts, None,
+                                                                  step.g_pose, step.g_betas, None)))
+        torch.cuda.synchronize()
+        for n, a, b in ev:
+            acc[n] += a.elapsed_time(b)
+    kern_ms = {n: acc[n] / reps for n in names}
+    # ---- reduce over ranks (max time) -------------------------------------------------------------
+    t = torch.tensor([ms, ms_e2e], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    if rank == 0:
+        total = B * world * args.steps
+        value = total / (ms * 1e-3)
+        e2e = total / (ms_e2e * 1e-3)
+        peak, peak_src = peaks()
+        top = max(kern_ms, key=kern_ms.get)
+        P_ = S * S
+        alg = {  # algorithmic bytes per launch of each big kernel
+            "raster_shade_fwd": B * (28 * K + 16) * P_,          # Fragments + RGBA written once
+            "shade_raster_bwd": B * (28 * K + 16) * P_,          # Fragments + image gradient read once
+            "loss_fwd": B * (16 + 12 + 4 + 36) * P_,             # RGBA, target, mask read; 9 derivative maps written
+            "loss_bwd": B * (16 + 12 + 4 + 36 + 16) * P_,        # the same read again + image gradient written
+        }
+        ach = alg.get(top, 0) / (kern_ms[top] * 1e-3) / 1e9
+        step_bytes = algorithmic_bytes_per_sample(S, K, T=cfg["T"], B=B) * B
+        line = {
+            "metric": "hand renders/sec (fwd+bwd)", "value": value, "unit": "samples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak" if cfg["B"] is not None else "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": cfg["desc"], "batch_per_gpu": B, "global_batch": B * world, "image_size": S,
+                       "faces_per_pixel": K, "blur_radius": step.blur, "texture": cfg["T"],
+                       "parallelism": f"dp{world} (batch shards by sample; NCCL all-reduce of loss sums + texture grad)",
+                       "l2": f"no flush: per-step working set ({(28 * K + 32) * P_ * B / 1e6:.0f} MB Fragments+images) exceeds the 126 MB L2"},
+            "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": step.launches_per_step * args.steps,
+            "clocks": clk.summary(),
+            "roofline": {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel_ms": kern_ms,
+                         "step": {"algorithmic_MB_per_sample": step_bytes / B / 1e6,
+                                  "achieved": step_bytes / (ms / args.steps * 1e-3) / 1e9,
+                                  "frac": step_bytes / (ms / args.steps * 1e-3) / 1e9 / peak}},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(cfg)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(cfg):
+    """Oracle port timed on this box's host cores on a bounded sample of the same workload (rank 0, N=1)."""
+    from hifihr_b200.mano_assets import load_mano
+    from oracle import pipeline as P
+    from oracle import raster_c
+    raster_c.build()
+    mano = load_mano()
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    S, K = cfg["S"], cfg["K"]
+    blur = 9.21034e-4 if cfg["soft"] else 0.0
+    Bs, n, t_used = 2, 0, 0.0
+    tex = P.synthetic_texture(cfg["T"])
+    while t_used < 12.0 and n < 8:
+        inp = P.synthetic_inputs(Bs, S=S, seed=500 + n)
+        inp["pose"].requires_grad_(True)
+        t = tex.clone().requires_grad_(True)
+        t0 = time.perf_counter()
+        out = P.render_path(mano, inp, t, image_size=S, K=K, blur_radius=blur, soft=cfg["soft"], c_select=True, threads=cores)
+        loss, _ = P.total_loss(out, inp, {k: v for k, v in LAMBDAS.items() if v}, 1.0)
+        loss.backward()
+        dt = time.perf_counter() - t0
+        if n > 0:
+            t_used += dt
+        n += 1
+    done = max(n - 1, 1)
+    return {"value": Bs * done / max(t_used, 1e-9), "unit": "samples/s", "cores": cores, "kind": "port",
+            "sample": f"{done} x {Bs} samples of the same workload, fwd+bwd (reference-identical MANO in torch, scalar C naive "
+                      f"rasterizer on {cores} threads, torch CPU shading/losses; PyTorch3D CPU kernel restated - upstream binary unavailable)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    if args.impl == "reference":
+        run_reference(args, cfg)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; hifihr_b200 has no CPU path (use --impl reference for the CPU arm)")
+        run_ours(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

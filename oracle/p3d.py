@@ -142,7 +142,8 @@ def face_pixel_terms(px, py, v, blur_radius: float, perspective_correct: bool, c
 def rasterize_meshes(face_verts: torch.Tensor, mesh_to_face_first_idx, num_faces_per_mesh,
                      image_size, blur_radius: float = 0.0, faces_per_pixel: int = 1,
                      perspective_correct: bool = True, clip_barycentric_coords: Optional[bool] = None,
-                     cull_backfaces: bool = False, pixel_chunk: int = 2048) -> Fragments:
+                     cull_backfaces: bool = False, pixel_chunk: int = 2048,
+                     pix_to_face: Optional[torch.Tensor] = None) -> Fragments:
     """Naive O(P·F) rasterizer (A.2-A.4) with autograd through zbuf / bary / dists (A.5).
 
     A no-grad dense pass picks, per pixel, the K smallest (z, face index); the
@@ -160,7 +161,9 @@ def rasterize_meshes(face_verts: torch.Tensor, mesh_to_face_first_idx, num_faces
     P = H * W
     p2f = torch.full((N, P, K), -1, dtype=torch.int64)
     fv_det = face_verts.detach()
-    for n in range(N):
+    if pix_to_face is not None:      # selection already done (e.g. by the scalar C oracle): only differentiate
+        p2f = pix_to_face.reshape(N, P, K).clone()
+    for n in range(N if pix_to_face is None else 0):
         f0, nf = int(mesh_to_face_first_idx[n]), int(num_faces_per_mesh[n])
         if nf == 0:
             continue

@@ -164,3 +164,9 @@ def test_product_has_no_cpu_path():
     for f in os.listdir(pkg):
         if f.endswith(".py"):
             assert "oracle" not in open(os.path.join(pkg, f)).read().replace("no oracle", ""), f
+
+
+def test_product_and_oracle_synthetic_inputs_agree():
+    from hifihr_b200.synthetic import synthetic_inputs
+    a, b = synthetic_inputs(3, S=16, seed=9), P.synthetic_inputs(3, S=16, seed=9)
+    assert a.keys() == b.keys() and all(torch.equal(a[k], b[k]) for k in a)
