@@ -262,8 +262,7 @@ __global__ void __launch_bounds__(kThreads) mano_bwd_kernel(HfrHandModel m, HfrM
   }
   __syncthreads();
   // gGt: translation-column grads that bypass A (chain joint outputs, centre)
-  float* gGt = s.misc + 28;  // NJ*3 <= 36... keep NJ<=12? no: use gfull region temporarily (3*NJ floats)
-  gGt = gfull;
+  float* gGt = gfull;  // the gfull region (3*NJ floats) is free until the Rodrigues backward
   for (int i = tid; i < 3 * NJ; i += kThreads) gGt[i] = 0.0f;
   __syncthreads();
   if (tid == 0) {
@@ -378,7 +377,6 @@ __global__ void __launch_bounds__(kThreads) mano_bwd_kernel(HfrHandModel m, HfrM
     for (int e = 0; e < 9; ++e) g[e] = gR[9 * tid + e] + (tid >= 1 ? gcoef[m.NS + 9 * (tid - 1) + e] : 0.0f);
     float gvv[3];
     hfr_rodrigues_bwd(s.full + 3 * tid, g, gvv);
-    __syncwarp();
     // gfull aliases gGt, which thread 0 finished reading before the barrier above
     gfull[3 * tid] = gvv[0]; gfull[3 * tid + 1] = gvv[1]; gfull[3 * tid + 2] = gvv[2];
   }
