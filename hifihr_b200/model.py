@@ -36,7 +36,7 @@ def mano_synthetic_uvs(v_template, faces):
     """MANO_RIGHT.pkl has no UVs: planar map of the template's x/z extent (§8d)."""
     xz = np.asarray(v_template, np.float64)[:, [0, 2]]
     uv = (xz - xz.min(0)) / (xz.max(0) - xz.min(0))
-    return uv.astype(np.float32), np.asarray(faces, np.int64)
+    return np.ascontiguousarray(uv, dtype=np.float32), np.ascontiguousarray(faces, dtype=np.int64)
 
 
 class HandRenderModel(nn.Module):
