@@ -247,7 +247,9 @@ static int check_topo(const HfrTopology* t, int need_joints) {
 }  // namespace
 
 extern "C" int hfr_geom_forward(const HfrTopology* t, const HfrGeomFwdArgs* a, void* stream) {
-  HFR_CHECK_ARG(a && a->verts, "geom_forward: null argument");
+  HFR_CHECK_ARG(a && a->B >= 0, "geom_forward: null argument");
+  if (a->B == 0) return HFR_OK;
+  HFR_CHECK_ARG(a->verts, "geom_forward: null pointer");
   if (int rc = check_topo(t, a->root_out >= 0)) return rc;
   HFR_CHECK_ARG(!a->verts_ndc || (a->focal && a->prp), "geom_forward: verts_ndc needs focal/prp");
   if (a->B == 0) return HFR_OK;
@@ -260,7 +262,9 @@ extern "C" int hfr_geom_forward(const HfrTopology* t, const HfrGeomFwdArgs* a, v
 }
 
 extern "C" int hfr_geom_backward(const HfrTopology* t, const HfrGeomBwdArgs* a, void* stream) {
-  HFR_CHECK_ARG(a && a->verts && a->g_verts, "geom_backward: null argument");
+  HFR_CHECK_ARG(a && a->B >= 0, "geom_backward: null argument");
+  if (a->B == 0) return HFR_OK;
+  HFR_CHECK_ARG(a->verts && a->g_verts, "geom_backward: null pointer");
   if (int rc = check_topo(t, a->root_out >= 0)) return rc;
   HFR_CHECK_ARG(!a->g_verts_ndc || (a->focal && a->prp), "geom_backward: g_verts_ndc needs focal/prp");
   if (a->B == 0) return HFR_OK;

@@ -417,8 +417,9 @@ static int check_model(const HfrHandModel* m) {
 
 extern "C" int hfr_mano_forward(const HfrHandModel* m, const HfrManoFwdArgs* a, void* stream) {
   if (int rc = check_model(m)) return rc;
-  HFR_CHECK_ARG(a && a->B >= 0 && a->pose && a->verts, "mano_forward: null argument");
+  HFR_CHECK_ARG(a && a->B >= 0, "mano_forward: null argument");
   if (a->B == 0) return HFR_OK;
+  HFR_CHECK_ARG(a->pose && a->verts, "mano_forward: null pointer");
   const int pose_dim = 3 + (m->NPC > 0 ? m->NPC : 3 * (m->NJ - 1));
   const size_t smem = mano_smem_bytes(*m, false);
   HFR_CHECK_ARG(smem <= 227 * 1024, "mano_forward: model too large for shared memory (%zu B)", smem);
@@ -430,8 +431,9 @@ extern "C" int hfr_mano_forward(const HfrHandModel* m, const HfrManoFwdArgs* a, 
 
 extern "C" int hfr_mano_backward(const HfrHandModel* m, const HfrManoBwdArgs* a, void* stream) {
   if (int rc = check_model(m)) return rc;
-  HFR_CHECK_ARG(a && a->B >= 0 && a->pose && a->g_verts && a->g_pose, "mano_backward: null argument");
+  HFR_CHECK_ARG(a && a->B >= 0, "mano_backward: null argument");
   if (a->B == 0) return HFR_OK;
+  HFR_CHECK_ARG(a->pose && a->g_verts && a->g_pose, "mano_backward: null pointer");
   const int pose_dim = 3 + (m->NPC > 0 ? m->NPC : 3 * (m->NJ - 1));
   const int NK = m->NS + 9 * (m->NJ - 1);
   const size_t extra = (size_t)(12 * m->NJ + 3 * m->NJ + 9 * m->NJ + ((NK + 3) & ~3) + 3 * m->NJ + 8) * sizeof(float);

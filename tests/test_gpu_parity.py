@@ -58,8 +58,11 @@ def test_mano_vs_oracle_many_samples(hf, mano):
     layer = hf.ManoLayer(center_idx=9, flat_hand_mean=False, ncomps=48)
     inp = P.synthetic_inputs(257, S=8, seed=21)
     v, j = layer(inp["pose"].to(DEV), inp["betas"].to(DEV))
-    vo, jo = orc(inp["pose"], inp["betas"])
-    assert (v.cpu() - vo).abs().max() < 1e-6 and (j.cpu() - jo).abs().max() < 1e-6
+    # truth = the fp64 oracle (the fp32 CPU oracle's own error depends on the host's BLAS: 5e-8 here, 1e-5 seen
+    # on one GPU box); tolerance 1e-6 m abs as SURVEY.md §8d states
+    o64 = ManoOracle(mano, dtype=torch.float64)
+    vo, jo = o64(inp["pose"].double(), inp["betas"].double())
+    assert (v.cpu().double() - vo).abs().max() < 1e-6 and (j.cpu().double() - jo).abs().max() < 1e-6
     # mean shape (th_betas omitted) and explicit translation
     v2, j2 = layer(inp["pose"][:4].to(DEV))
     vo2, _ = orc(inp["pose"][:4], torch.zeros(4, 10))
