@@ -1,0 +1,71 @@
+#!/usr/bin/env python
+"""Summarise an .ncu-rep (read here, no GPU needed) and a launch-list CSV into profiles/<tag>_*.{md,csv}.
+usage: python tools/ncu_summary.py <tag> [note]"""
+import csv, os, subprocess, sys, collections
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tag = sys.argv[1]
+note = sys.argv[2] if len(sys.argv) > 2 else ""
+rep = os.path.join(ROOT, "gpurun_out", f"{tag}_prof.ncu-rep")
+lau = os.path.join(ROOT, "gpurun_out", f"{tag}_launches.csv")
+out = os.path.join(ROOT, "profiles", f"{tag}_summary.md")
+WANT = [("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "dram rd"), ("dram__bytes_write.sum", "dram wr"),
+        ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram %"),
+        ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm %"),
+        ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue %"),
+        ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps act %"),
+        ("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "fma pipe %"),
+        ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor pipe %"),
+        ("smsp__inst_executed.sum", "warp insts"), ("smsp__thread_inst_executed_per_inst_executed.ratio", "thr/inst"),
+        ("launch__registers_per_thread", "regs"), ("launch__grid_size", "grid"), ("launch__block_size", "block"),
+        ("lts__t_bytes.sum", "L2 bytes")]
+lines = [f"# ncu summary `{tag}`", "", note, ""]
+if os.path.isfile(rep):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    seen = set()
+    lines += ["## `ncu --set full --clock-control none` (one launch per kernel; cold-cache, serialised)", "",
+              "| kernel | " + " | ".join(n for _, n in WANT) + " |", "|---|" + "---|" * len(WANT)]
+    for r in rows[2:]:
+        k = r[idx["Kernel Name"]]
+        if k in seen:
+            continue
+        seen.add(k)
+        cells = []
+        for m, _ in WANT:
+            if m in idx:
+                v = r[idx[m]]
+                try:
+                    v = f"{float(v):.4g}"
+                except ValueError:
+                    pass
+                cells.append(f"{v} {units[idx[m]]}".strip())
+            else:
+                cells.append("-")
+        short = k.split("(")[0].replace("void ", "").replace("hfr::", "").replace("<unnamed>::", "")
+        lines.append(f"| `{short}` | " + " | ".join(cells) + " |")
+    lines.append("")
+if os.path.isfile(lau):
+    rows = [r for r in csv.reader(open(lau)) if r and r[0].isdigit() or (r and r[0] == "ID")]
+    hdr = rows[0]
+    ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
+    ui = hdr.index("Metric Unit")
+    agg = collections.OrderedDict()
+    for r in rows[1:]:
+        v = float(r[vi].replace(",", ""))
+        u = r[ui]
+        v_us = v / 1e3 if u in ("ns", "nsecond") else (v if u in ("us", "usecond") else v * 1e3 if u in ("ms", "msecond") else v)
+        k = r[ki].split("(")[0].replace("void ", "")
+        a = agg.setdefault(k, [0, 0.0])
+        a[0] += 1
+        a[1] += v_us
+    tot = sum(a[1] for a in agg.values())
+    lines += ["## launch list (`--metrics gpu__time_duration.sum`, first 400 launches of `bench.py --steps 3 --warmup 3`)", "",
+              "| kernel | launches | total us | avg us | share |", "|---|---|---|---|---|"]
+    for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        lines.append(f"| `{k}` | {n} | {t:.1f} | {t / n:.1f} | {100 * t / tot:.1f}% |")
+    import shutil
+    shutil.copy(lau, os.path.join(ROOT, "profiles", f"{tag}_launches.csv"))
+open(out, "w").write("\n".join(lines) + "\n")
+print(open(out).read())
