@@ -37,6 +37,21 @@
 #define XDIV(a, b) ((a) / (b))
 #endif
 
+// Fast (few-ulp) variants for math that does NOT have to be bit-exact against the oracle: shading,
+// blending and every backward formula (tolerances in DESIGN.md §5).  The host build keeps the
+// plain operators.
+#if defined(__CUDA_ARCH__)
+#define HFR_FDIV(a, b) __fdividef((a), (b))
+#define HFR_RCP(x) __frcp_rn(x)
+#define HFR_EXP(x) __expf(x)
+#define HFR_POW(x, y) __powf((x), (y))
+#else
+#define HFR_FDIV(a, b) ((a) / (b))
+#define HFR_RCP(x) (1.0f / (x))
+#define HFR_EXP(x) expf(x)
+#define HFR_POW(x, y) powf((x), (y))
+#endif
+
 HFR_HD float hfr_min3(float a, float b, float c) { return fminf(fminf(a, b), c); }
 HFR_HD float hfr_max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 HFR_HD float hfr_clamp01(float t) { return fminf(fmaxf(t, 0.0f), 1.0f); }

@@ -104,7 +104,7 @@ HFR_HD void hfr_seg_dist2_bwd(float px, float py, float ax, float ay, float bx, 
     return;
   }
   const float pax = px - ax, pay = py - ay;
-  const float t = (bax * pax + bay * pay) / l2;
+  const float t = HFR_FDIV(bax * pax + bay * pay, l2);
   const float tt = hfr_clamp01(t);
   const float qx = ax + tt * bax, qy = ay + tt * bay;
   const float gqx = 2.0f * (qx - px) * g, gqy = 2.0f * (qy - py) * g;
@@ -112,7 +112,7 @@ HFR_HD void hfr_seg_dist2_bwd(float px, float py, float ax, float ay, float bx, 
   float gbax = tt * gqx, gbay = tt * gqy;
   const float gtt = gqx * bax + gqy * bay;
   const float gt = (t >= 0.0f && t <= 1.0f) ? gtt : 0.0f;
-  const float gnum = gt / l2, gl2 = -gt * t / l2;
+  const float gnum = HFR_FDIV(gt, l2), gl2 = -gnum * t;
   gbax += gnum * pax + 2.0f * gl2 * bax;
   gbay += gnum * pay + 2.0f * gl2 * bay;
   gax -= gnum * bax; gay -= gnum * bay;             // pa = p - a
@@ -129,13 +129,15 @@ HFR_HD void hfr_raster_eval_bwd(float px, float py, const float* v, int pc, int 
   const float area = hfr_edge(x2, y2, x0, y0, x1, y1) + HFR_KEPS;
   const float E0 = hfr_edge(px, py, x1, y1, x2, y2), E1 = hfr_edge(px, py, x2, y2, x0, y0),
               E2 = hfr_edge(px, py, x0, y0, x1, y1);
-  const float w0 = E0 / area, w1 = E1 / area, w2 = E2 / area;
+  const float ia = HFR_RCP(area);
+  const float w0 = E0 * ia, w1 = E1 * ia, w2 = E2 * ia;
   float b0 = w0, b1 = w1, b2 = w2, t0 = 0.f, t1 = 0.f, t2 = 0.f, tsum = 0.f, den = 1.f;
   if (pc) {
     t0 = w0 * z1 * z2; t1 = z0 * w1 * z2; t2 = z0 * z1 * w2;
     tsum = t0 + t1 + t2;
     den = fmaxf(tsum, HFR_KEPS);
-    b0 = t0 / den; b1 = t1 / den; b2 = t2 / den;
+    const float id = HFR_RCP(den);
+    b0 = t0 * id; b1 = t1 * id; b2 = t2 * id;
   }
   const bool inside = b0 > 0.0f && b1 > 0.0f && b2 > 0.0f;
   float c0 = b0, c1 = b1, c2 = b2, csum = 1.f, s = 1.f;
@@ -144,29 +146,31 @@ HFR_HD void hfr_raster_eval_bwd(float px, float py, const float* v, int pc, int 
     csum = c0 + c1 + c2;
     s = fmaxf(csum, 1e-5f);
   }
-  const float bc0 = c0 / s, bc1 = c1 / s, bc2 = c2 / s;
+  const float is = HFR_RCP(s);
+  const float bc0 = c0 * is, bc1 = c1 * is, bc2 = c2 * is;
   // pz = sum bc_i z_i
   float gbc0 = g_bc[0] + g_pz * z0, gbc1 = g_bc[1] + g_pz * z1, gbc2 = g_bc[2] + g_pz * z2;
   float gz0 = g_pz * bc0, gz1 = g_pz * bc1, gz2 = g_pz * bc2;
   float gb0 = gbc0, gb1 = gbc1, gb2 = gbc2;
   if (clip) {
-    const float gs = (csum >= 1e-5f) ? -(gbc0 * c0 + gbc1 * c1 + gbc2 * c2) / (s * s) : 0.0f;
-    const float gc0 = gbc0 / s + gs, gc1 = gbc1 / s + gs, gc2 = gbc2 / s + gs;
+    const float gs = (csum >= 1e-5f) ? -(gbc0 * c0 + gbc1 * c1 + gbc2 * c2) * (is * is) : 0.0f;
+    const float gc0 = gbc0 * is + gs, gc1 = gbc1 * is + gs, gc2 = gbc2 * is + gs;
     gb0 = (b0 >= 0.0f && b0 <= 1.0f) ? gc0 : 0.0f;
     gb1 = (b1 >= 0.0f && b1 <= 1.0f) ? gc1 : 0.0f;
     gb2 = (b2 >= 0.0f && b2 <= 1.0f) ? gc2 : 0.0f;
   }
   float gw0 = gb0, gw1 = gb1, gw2 = gb2;
   if (pc) {
-    const float gden = (tsum >= HFR_KEPS) ? -(gb0 * t0 + gb1 * t1 + gb2 * t2) / (den * den) : 0.0f;
-    const float gt0 = gb0 / den + gden, gt1 = gb1 / den + gden, gt2 = gb2 / den + gden;
+    const float id = HFR_RCP(den);
+    const float gden = (tsum >= HFR_KEPS) ? -(gb0 * t0 + gb1 * t1 + gb2 * t2) * (id * id) : 0.0f;
+    const float gt0 = gb0 * id + gden, gt1 = gb1 * id + gden, gt2 = gb2 * id + gden;
     gw0 = gt0 * z1 * z2; gz1 += gt0 * w0 * z2; gz2 += gt0 * w0 * z1;
     gw1 = gt1 * z0 * z2; gz0 += gt1 * w1 * z2; gz2 += gt1 * z0 * w1;
     gw2 = gt2 * z0 * z1; gz0 += gt2 * z1 * w2; gz1 += gt2 * z0 * w2;
   }
   // w_i = E_i / area
-  const float gE0 = gw0 / area, gE1 = gw1 / area, gE2 = gw2 / area;
-  const float garea = -(gw0 * w0 + gw1 * w1 + gw2 * w2) / area;
+  const float gE0 = gw0 * ia, gE1 = gw1 * ia, gE2 = gw2 * ia;
+  const float garea = -(gw0 * w0 + gw1 * w1 + gw2 * w2) * ia;
   float gx0 = 0.f, gy0 = 0.f, gx1 = 0.f, gy1 = 0.f, gx2 = 0.f, gy2 = 0.f;
   // E(p;a,b): dE/dax = py-by, dE/day = bx-px, dE/dbx = -(py-ay), dE/dby = px-ax
   // E0 = E(p; v1, v2)

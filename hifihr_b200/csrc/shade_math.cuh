@@ -73,17 +73,18 @@ HFR_HD void hfr_tex_uv_grad(const float* tex, const HfrTexTap* t, const float* g
 // ---------------------------------------------------------------------------------- lighting
 HFR_HD void hfr_normalize_eps(const float* x, float* o, float* len_out) {
   const float len = sqrtf(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
-  const float d = fmaxf(len, 1e-6f);
-  o[0] = x[0] / d; o[1] = x[1] / d; o[2] = x[2] / d;
+  const float inv = HFR_RCP(fmaxf(len, 1e-6f));
+  o[0] = x[0] * inv; o[1] = x[1] * inv; o[2] = x[2] * inv;
   *len_out = len;
 }
 // backward of o = x / max(|x|, eps)
 HFR_HD void hfr_normalize_eps_bwd(const float* o, float len, const float* g, float* gx) {
   if (len >= 1e-6f) {
     const float d = o[0] * g[0] + o[1] * g[1] + o[2] * g[2];
-    gx[0] = (g[0] - o[0] * d) / len; gx[1] = (g[1] - o[1] * d) / len; gx[2] = (g[2] - o[2] * d) / len;
+    const float inv = HFR_RCP(len);
+    gx[0] = (g[0] - o[0] * d) * inv; gx[1] = (g[1] - o[1] * d) * inv; gx[2] = (g[2] - o[2] * d) * inv;
   } else {
-    gx[0] = g[0] / 1e-6f; gx[1] = g[1] / 1e-6f; gx[2] = g[2] / 1e-6f;
+    gx[0] = g[0] * 1e6f; gx[1] = g[1] * 1e6f; gx[2] = g[2] * 1e6f;
   }
 }
 
@@ -105,7 +106,7 @@ HFR_HD void hfr_phong_fwd(const HfrShadeParams& p, const float* P, const float* 
   for (int k = 0; k < 3; ++k) c->refl[k] = -dhat[k] + 2.0f * (c->cosang * c->nh[k]);
   c->vr = c->view[0] * c->refl[0] + c->view[1] * c->refl[1] + c->view[2] * c->refl[2];
   c->alpha = fmaxf(c->vr, 0.0f) * mask;
-  c->spec = powf(c->alpha, p.shininess);
+  c->spec = HFR_POW(c->alpha, p.shininess);
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     const float amb = p.mat_ambient[k] * p.light_ambient[k];
@@ -135,7 +136,7 @@ HFR_HD void hfr_phong_bwd(const HfrShadeParams& p, const float* dhat, const floa
   float g_cos = g_relu * mask;
   // spec = alpha^s ; alpha = relu(vr) * mask
   float g_alpha = 0.0f;
-  if (c->alpha > 0.0f) g_alpha = g_specs * p.shininess * powf(c->alpha, p.shininess - 1.0f);
+  if (c->alpha > 0.0f) g_alpha = g_specs * p.shininess * HFR_POW(c->alpha, p.shininess - 1.0f);
   const float g_vr = (c->vr > 0.0f) ? g_alpha * mask : 0.0f;
   float g_view[3], g_refl[3], g_nh[3];
 #pragma unroll
@@ -155,7 +156,7 @@ HFR_HD void hfr_phong_bwd(const HfrShadeParams& p, const float* dhat, const floa
 }
 
 // ---------------------------------------------------------------------------------- blending
-HFR_HD float hfr_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
+HFR_HD float hfr_sigmoid(float x) { return HFR_FDIV(1.0f, 1.0f + HFR_EXP(-x)); }
 
 // colors: K*3 (ignored for entries with valid[k]==0).  Returns rgba[4].
 template <int KMAX>
@@ -171,7 +172,7 @@ HFR_HD void hfr_blend_fwd(const HfrShadeParams& p, int K, const bool* valid, con
 #pragma unroll
   for (int k = 0; k < KMAX; ++k) {
     prob[k] = 0.0f;
-    if (k < K && valid[k]) prob[k] = hfr_sigmoid(-d[k] / p.sigma);
+    if (k < K && valid[k]) prob[k] = hfr_sigmoid(HFR_FDIV(-d[k], p.sigma));
     if (k < K) prod *= (1.0f - prob[k]);
   }
   rgba[3] = 1.0f - prod;
@@ -185,7 +186,7 @@ HFR_HD void hfr_blend_fwd(const HfrShadeParams& p, int K, const bool* valid, con
 #pragma unroll
   for (int k = 0; k < KMAX; ++k) {
     zinv[k] = 0.0f;
-    if (k < K && valid[k]) zinv[k] = (p.zfar - z[k]) / zr;
+    if (k < K && valid[k]) zinv[k] = (p.zfar - z[k]) / zr;   // IEEE divide: 1 ulp of z_inv is amplified by 1/gamma
     if (k < K) zmax = (k == 0) ? zinv[k] : fmaxf(zmax, zinv[k]);
   }
   zmax = fmaxf(zmax, eps);
@@ -193,15 +194,15 @@ HFR_HD void hfr_blend_fwd(const HfrShadeParams& p, int K, const bool* valid, con
 #pragma unroll
   for (int k = 0; k < KMAX; ++k) {
     if (k < K) {
-      const float w = prob[k] * expf((zinv[k] - zmax) / p.gamma);
+      const float w = prob[k] * HFR_EXP(HFR_FDIV(zinv[k] - zmax, p.gamma));
       wsum += w;
       if (valid[k]) { acc[0] += w * colors[3 * k]; acc[1] += w * colors[3 * k + 1]; acc[2] += w * colors[3 * k + 2]; }
     }
   }
-  const float delta = fmaxf(expf((eps - zmax) / p.gamma), eps);
+  const float delta = fmaxf(HFR_EXP(HFR_FDIV(eps - zmax, p.gamma)), eps);
   const float den = wsum + delta;
 #pragma unroll
-  for (int c = 0; c < 3; ++c) rgba[c] = (acc[c] + delta * p.background[c]) / den;
+  for (int c = 0; c < 3; ++c) rgba[c] = HFR_FDIV(acc[c] + delta * p.background[c], den);
 }
 
 // g_rgba[4] -> g_colors (K*3), g_z (K), g_d (K).
@@ -219,7 +220,7 @@ HFR_HD void hfr_blend_bwd(const HfrShadeParams& p, int K, const bool* valid, con
 #pragma unroll
   for (int k = 0; k < KMAX; ++k) {
     prob[k] = 0.0f; gprob[k] = 0.0f;
-    if (k < K && valid[k]) prob[k] = hfr_sigmoid(-d[k] / p.sigma);
+    if (k < K && valid[k]) prob[k] = hfr_sigmoid(HFR_FDIV(-d[k], p.sigma));
   }
   // alpha channel = 1 - prod(1 - p_k): d/dp_k = prod_{j != k}(1 - p_j)
 #pragma unroll
@@ -243,7 +244,7 @@ HFR_HD void hfr_blend_bwd(const HfrShadeParams& p, int K, const bool* valid, con
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) {
       zinv[k] = 0.0f;
-      if (k < K && valid[k]) zinv[k] = (p.zfar - z[k]) / zr;
+      if (k < K && valid[k]) zinv[k] = (p.zfar - z[k]) / zr;   // IEEE divide: 1 ulp of z_inv is amplified by 1/gamma
       if (k < K && (k == 0 || zinv[k] > zmax_raw)) { zmax_raw = zinv[k]; kmax = k; }
     }
     const float zmax = fmaxf(zmax_raw, eps);
@@ -252,22 +253,22 @@ HFR_HD void hfr_blend_bwd(const HfrShadeParams& p, int K, const bool* valid, con
     for (int k = 0; k < KMAX; ++k) {
       e[k] = 0.0f;
       if (k < K) {
-        e[k] = expf((zinv[k] - zmax) / p.gamma);
+        e[k] = HFR_EXP(HFR_FDIV(zinv[k] - zmax, p.gamma));
         const float w = prob[k] * e[k];
         wsum += w;
         if (valid[k]) { acc[0] += w * colors[3 * k]; acc[1] += w * colors[3 * k + 1]; acc[2] += w * colors[3 * k + 2]; }
       }
     }
-    const float dexp = expf((eps - zmax) / p.gamma);
+    const float dexp = HFR_EXP(HFR_FDIV(eps - zmax, p.gamma));
     const float delta = fmaxf(dexp, eps);
     const float den = wsum + delta;
     float rgb[3], gnum[3];
     float gden = 0.0f, gdelta = 0.0f;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      rgb[c] = (acc[c] + delta * p.background[c]) / den;
-      gnum[c] = g_rgba[c] / den;
-      gden -= g_rgba[c] * rgb[c] / den;
+      rgb[c] = HFR_FDIV(acc[c] + delta * p.background[c], den);
+      gnum[c] = HFR_FDIV(g_rgba[c], den);
+      gden -= gnum[c] * rgb[c];
       gdelta += gnum[c] * p.background[c];
     }
     gdelta += gden;
@@ -284,12 +285,12 @@ HFR_HD void hfr_blend_bwd(const HfrShadeParams& p, int K, const bool* valid, con
           g_colors[3 * k] = w * gnum[0]; g_colors[3 * k + 1] = w * gnum[1]; g_colors[3 * k + 2] = w * gnum[2];
         }
         gprob[k] += gw * e[k];
-        const float ge = gw * prob[k] * e[k] / p.gamma;   // d/d((zinv - zmax))
+        const float ge = HFR_FDIV(gw * prob[k] * e[k], p.gamma);   // d/d((zinv - zmax))
         gzinv[k] = ge;
         gzmax -= ge;
       }
     }
-    if (dexp >= eps) gzmax -= gdelta * delta / p.gamma;
+    if (dexp >= eps) gzmax -= HFR_FDIV(gdelta * delta, p.gamma);
     if (zmax_raw >= eps) {
 #pragma unroll
       for (int k = 0; k < KMAX; ++k)
@@ -297,13 +298,13 @@ HFR_HD void hfr_blend_bwd(const HfrShadeParams& p, int K, const bool* valid, con
     }
 #pragma unroll
     for (int k = 0; k < KMAX; ++k)
-      if (k < K && valid[k]) g_z[k] = -gzinv[k] / zr;
+      if (k < K && valid[k]) g_z[k] = HFR_FDIV(-gzinv[k], zr);
   }
 #pragma unroll
   for (int k = 0; k < KMAX; ++k) {
     if (k < K && valid[k]) {
       const float s = prob[k];
-      g_d[k] = -gprob[k] * s * (1.0f - s) / p.sigma;
+      g_d[k] = HFR_FDIV(-gprob[k] * s * (1.0f - s), p.sigma);
     }
   }
 }
