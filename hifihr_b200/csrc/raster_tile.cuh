@@ -23,13 +23,13 @@
 namespace hfr {
 
 constexpr int kTileW = 16, kTileH = 16, kRasterThreads = 256;
-constexpr int kListCap = 512;   // faces per staged batch
-constexpr int kRecFloats = 16;  // 64-byte record
+constexpr int kListCap = 256;   // faces per staged batch
+constexpr int kRecFloats = 16;  // 64-byte record: 9 vertex floats, dilated bbox, area, zmin, face id
+constexpr int kChunk = 32 * kRasterThreads;  // faces handled per coarse pass (one hit bit per face per thread)
 
 struct RasterSmem {
-  int list[kListCap];
   __align__(16) float rec[kListCap * kRecFloats];
-  int wcount[2][kRasterThreads / 32];
+  int wsum[kRasterThreads / 32];
 };
 
 __device__ __forceinline__ uint32_t pack_tile_range(int txmin, int txmax, int tymin, int tymax) {
@@ -61,6 +61,16 @@ struct TopK {
 
 // Coarse + stage + fine for one tile.  On return `top` holds, per thread (= pixel), the KMAX
 // nearest valid faces as packed face ids (sorted by (z, id)).
+//
+//   coarse: thread t owns a CONTIGUOUS chunk of faces and keeps one hit bit per face from a
+//           single pass over the packed tile ranges; one block-wide scan of the hit counts then
+//           gives every thread its slot in the tile list, which therefore stays sorted by face
+//           index (z-ties resolve to the smaller index with a strict `<`, the CPU reference's
+//           (z, face) order).  A tile no face touches leaves after that scan.
+//   stage:  listed faces are gathered once per tile into 64-byte shared records.
+//   fine:   each warp culls the list against its own 8x4 block (one ballot per 32 faces), then
+//           all lanes walk the survivors together (broadcast LDS.128); a lane skips a face whose
+//           nearest vertex is not in front of its current K-th depth before doing any division.
 template <int KMAX>
 __device__ __forceinline__ void raster_tile(const HfrRasterArgs& a, const uint32_t* __restrict__ tile_ranges,
                                             RasterSmem& sm, int n, int tx, int ty, float xf, float yf,
@@ -71,95 +81,120 @@ __device__ __forceinline__ void raster_tile(const HfrRasterArgs& a, const uint32
   const int nf = (int)a.mesh_nfaces[n];
   const float blur = a.blur_radius, rblur = sqrtf(a.blur_radius);
   const int pc = a.perspective_correct, clip = a.clip_barycentric;
+  // pz is a convex combination of the vertex depths unless an outside pixel keeps unclipped
+  // barycentrics (blur > 0 without clipping): only then the zmin early-out is not exact
+  const bool zcull = clip || !(blur > 0.0f);
   top.init();
-  int count = 0;
 
-  auto process = [&](int cnt) {
-    __syncthreads();  // list complete
-    for (int i = tid; i < cnt; i += kRasterThreads) {
-      const float* __restrict__ v = a.face_verts + (size_t)sm.list[i] * 9;
-      float r[9];
-#pragma unroll
-      for (int e = 0; e < 9; ++e) r[e] = __ldg(v + e);
-      float4* dst = reinterpret_cast<float4*>(sm.rec + i * kRecFloats);
-      const float xmin = XSUB(hfr_min3(r[0], r[3], r[6]), rblur), xmax = XADD(hfr_max3(r[0], r[3], r[6]), rblur);
-      const float ymin = XSUB(hfr_min3(r[1], r[4], r[7]), rblur), ymax = XADD(hfr_max3(r[1], r[4], r[7]), rblur);
-      const float area = XADD(hfr_edge(r[6], r[7], r[0], r[1], r[3], r[4]), HFR_KEPS);
-      dst[0] = make_float4(r[0], r[1], r[2], r[3]);
-      dst[1] = make_float4(r[4], r[5], r[6], r[7]);
-      dst[2] = make_float4(r[8], xmin, xmax, ymin);
-      dst[3] = make_float4(ymax, area, 0.f, 0.f);
+  for (int cbase = 0; cbase < nf; cbase += kChunk) {
+    const int cn = min(nf - cbase, kChunk);
+    const int per = (cn + kRasterThreads - 1) / kRasterThreads;   // <= 32
+    const int first = cbase + tid * per;
+    uint32_t hits = 0;
+    for (int j = 0; j < per; ++j) {
+      const int fi = first + j;
+      if (fi < cbase + cn) {
+        const uint32_t w = __ldg(tile_ranges + f0 + fi);
+        const int txmin = w & 255, txmax = (w >> 8) & 255, tymin = (w >> 16) & 255, tymax = w >> 24;
+        if (tx >= txmin && tx <= txmax && ty >= tymin && ty <= tymax) hits |= 1u << j;
+      }
     }
+    // block-wide exclusive scan of the per-thread hit counts
+    const int cnt = __popc(hits);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    __syncthreads();   // previous chunk's records consumed, wsum free
+    if (lane == 31) sm.wsum[warp] = incl;
     __syncthreads();
-    if (warp_active) {
-      for (int b0 = 0; b0 < cnt; b0 += 32) {
-        const int i = b0 + lane;
-        bool ok = false;
-        if (i < cnt) {
-          const float4 q2 = *reinterpret_cast<const float4*>(sm.rec + i * kRecFloats + 8);
-          const float ymax = sm.rec[i * kRecFloats + 12];
-          ok = !(q2.z < wx_lo || q2.y > wx_hi || ymax < wy_lo || q2.w > wy_hi);
-        }
-        unsigned m = __ballot_sync(0xffffffffu, ok);
+    int before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kRasterThreads / 32; ++w) {
+      const int c = sm.wsum[w];
+      before += (w < warp) ? c : 0;
+      total += c;
+    }
+    if (total == 0) continue;
+    const int my0 = before + incl - cnt;   // list position of this thread's first hit
+
+    for (int lbase = 0; lbase < total; lbase += kListCap) {
+      const int bcnt = min(total - lbase, kListCap);
+      if (lbase > 0) __syncthreads();   // previous batch consumed
+      // stage: every thread writes the records of its own hits that fall into this batch
+      {
+        uint32_t m = hits;
+        int pos = my0;
         while (m) {
           const int j = __ffs(m) - 1;
           m &= m - 1;
-          const float4* r4 = reinterpret_cast<const float4*>(sm.rec + (b0 + j) * kRecFloats);
-          const float4 q0 = r4[0], q1 = r4[1], q2 = r4[2], q3 = r4[3];
-          if (pix_active && !(xf < q2.y || xf > q2.z || yf < q2.w || yf > q3.x)) {
-            const float v[9] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x};
-            float pz, bc[3];
-            bool inside;
-            if (hfr_raster_bary(xf, yf, v, q3.y, pc, clip, &pz, bc, &inside)) {
-              if (pz < top.worst()) {
-                bool keep = inside;
-                if (!keep) keep = hfr_tri_dist2(xf, yf, v) < blur;
-                if (keep) top.insert(pz, sm.list[b0 + j]);
+          if (pos >= lbase && pos < lbase + bcnt) {
+            const int face = (int)(f0 + first + j);
+            const float* __restrict__ v = a.face_verts + (size_t)face * 9;
+            float r[9];
+#pragma unroll
+            for (int e = 0; e < 9; ++e) r[e] = __ldg(v + e);
+            float4* dst = reinterpret_cast<float4*>(sm.rec + (pos - lbase) * kRecFloats);
+            const float xmin = XSUB(hfr_min3(r[0], r[3], r[6]), rblur), xmax = XADD(hfr_max3(r[0], r[3], r[6]), rblur);
+            const float ymin = XSUB(hfr_min3(r[1], r[4], r[7]), rblur), ymax = XADD(hfr_max3(r[1], r[4], r[7]), rblur);
+            const float area = XADD(hfr_edge(r[6], r[7], r[0], r[1], r[3], r[4]), HFR_KEPS);
+            dst[0] = make_float4(r[0], r[1], r[2], r[3]);
+            dst[1] = make_float4(r[4], r[5], r[6], r[7]);
+            dst[2] = make_float4(r[8], xmin, xmax, ymin);
+            // zmin shrunk by 1e-5: the rounded pz of a convex combination can undershoot the smallest z by a few ulp
+            dst[3] = make_float4(ymax, area, hfr_min3(r[2], r[5], r[8]) * 0.99999f, __int_as_float(face));
+          }
+          ++pos;
+        }
+      }
+      __syncthreads();
+      if (warp_active) {
+        for (int b0 = 0; b0 < bcnt; b0 += 32) {
+          const int i = b0 + lane;
+          bool ok = false;
+          if (i < bcnt) {
+            const float4 q2 = *reinterpret_cast<const float4*>(sm.rec + i * kRecFloats + 8);
+            const float ymax = sm.rec[i * kRecFloats + 12];
+            ok = !(q2.z < wx_lo || q2.y > wx_hi || ymax < wy_lo || q2.w > wy_hi);
+          }
+          unsigned m = __ballot_sync(0xffffffffu, ok);
+          while (m) {
+            const int j = __ffs(m) - 1;
+            m &= m - 1;
+            const float4* r4 = reinterpret_cast<const float4*>(sm.rec + (b0 + j) * kRecFloats);
+            const float4 q2 = r4[2], q3 = r4[3];
+            bool want = pix_active && !(xf < q2.y || xf > q2.z || yf < q2.w || yf > q3.x);
+            if (zcull) want = want && (q3.z < top.worst());
+            if (want) {
+              const float4 q0 = r4[0], q1 = r4[1];
+              const float v[9] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x};
+              float pz, bc[3];
+              bool inside;
+              if (hfr_raster_bary(xf, yf, v, q3.y, pc, clip, &pz, bc, &inside)) {
+                if (pz < top.worst()) {
+                  bool keep = inside;
+                  if (!keep) keep = hfr_tri_dist2(xf, yf, v) < blur;
+                  if (keep) top.insert(pz, __float_as_int(q3.w));
+                }
               }
             }
           }
         }
       }
     }
-    __syncthreads();  // records consumed before the list is rebuilt
-  };
-
-  for (int base = 0; base < nf; base += kRasterThreads) {
-    const int fi = base + tid;
-    bool hit = false;
-    if (fi < nf) {
-      const uint32_t w = __ldg(tile_ranges + f0 + fi);
-      const int txmin = w & 255, txmax = (w >> 8) & 255, tymin = (w >> 16) & 255, tymax = w >> 24;
-      hit = tx >= txmin && tx <= txmax && ty >= tymin && ty <= tymax;
-    }
-    const unsigned bal = __ballot_sync(0xffffffffu, hit);
-    const int par = (base / kRasterThreads) & 1;
-    if (lane == 0) sm.wcount[par][warp] = __popc(bal);
-    __syncthreads();
-    int prefix = 0, total = 0;
-#pragma unroll
-    for (int w = 0; w < kRasterThreads / 32; ++w) {
-      const int c = sm.wcount[par][w];
-      prefix += (w < warp) ? c : 0;
-      total += c;
-    }
-    if (hit) sm.list[count + prefix + __popc(bal & ((1u << lane) - 1))] = (int)(f0 + fi);
-    count += total;
-    if (count > kListCap - kRasterThreads) {
-      process(count);
-      count = 0;
-    }
   }
-  if (count > 0) process(count);
 }
 
 
-// Recompute the winners' barycentrics / depth / distance from the packed face floats.
+// Recompute the winners' barycentrics / depth / distance from the packed face floats (the winner
+// already passed the validity, bbox and blur tests in the fine pass; the formulas are the same
+// X* sequences, so z is reproduced bit for bit).
 template <int KMAX>
 __device__ __forceinline__ void compute_fragments(const HfrRasterArgs& a, float xf, float yf, const TopK<KMAX>& top,
                                                   int64_t* id, float* z, float* d, float* b) {
   const int K = a.K;
-  const float rblur = sqrtf(a.blur_radius);
 #pragma unroll
   for (int k = 0; k < KMAX; ++k) {
     id[k] = -1; z[k] = -1.0f; d[k] = -1.0f; b[3 * k] = b[3 * k + 1] = b[3 * k + 2] = -1.0f;
@@ -168,11 +203,13 @@ __device__ __forceinline__ void compute_fragments(const HfrRasterArgs& a, float 
       const float* __restrict__ src = a.face_verts + (size_t)top.f[k] * 9;
 #pragma unroll
       for (int e = 0; e < 9; ++e) v[e] = __ldg(src + e);
-      float pz, bc[3], sd;
-      if (hfr_raster_eval(xf, yf, v, a.blur_radius, rblur, a.perspective_correct, a.clip_barycentric,
-                          a.cull_backfaces, &pz, bc, &sd)) {
-        id[k] = top.f[k]; z[k] = pz; d[k] = sd; b[3 * k] = bc[0]; b[3 * k + 1] = bc[1]; b[3 * k + 2] = bc[2];
-      }
+      const float area = XADD(hfr_edge(v[6], v[7], v[0], v[1], v[3], v[4]), HFR_KEPS);
+      float pz, bc[3];
+      bool inside;
+      hfr_raster_bary(xf, yf, v, area, a.perspective_correct, a.clip_barycentric, &pz, bc, &inside);
+      const float dd = hfr_tri_dist2(xf, yf, v);
+      id[k] = top.f[k]; z[k] = pz; d[k] = inside ? -dd : dd;
+      b[3 * k] = bc[0]; b[3 * k + 1] = bc[1]; b[3 * k + 2] = bc[2];
     }
   }
 }
@@ -213,6 +250,11 @@ struct PixelCtx {
   bool pix_active, warp_active;
 };
 
+// hfr_pix_to_ndc with the per-axis range / offset hoisted (same X* sequence, same bits)
+__device__ __forceinline__ float pix_to_ndc_pre(int i, float range, float offset, int S1) {
+  return XADD(-offset, XDIV(XADD(XMUL(range, (float)i), offset), (float)S1));
+}
+
 __device__ __forceinline__ PixelCtx make_pixel_ctx(int H, int W) {
   PixelCtx c;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -222,13 +264,16 @@ __device__ __forceinline__ PixelCtx make_pixel_ctx(int H, int W) {
   c.yi = wy0 + (lane >> 3);
   c.pix_active = c.xi < W && c.yi < H;
   c.warp_active = wx0 < W && wy0 < H;
-  c.xf = hfr_pix_to_ndc(W - 1 - c.xi, W, H);
-  c.yf = hfr_pix_to_ndc(H - 1 - c.yi, H, W);
+  const float rx = W > H ? XDIV(XMUL(2.0f, (float)W), (float)H) : 2.0f, ox = XDIV(rx, 2.0f);
+  const float ry = H > W ? XDIV(XMUL(2.0f, (float)H), (float)W) : 2.0f, oy = XDIV(ry, 2.0f);
+  c.xf = pix_to_ndc_pre(W - 1 - c.xi, rx, ox, W);
+  c.yf = pix_to_ndc_pre(H - 1 - c.yi, ry, oy, H);
+  // bounds of the warp's 8x4 block = sample points of its corner pixels
   const int wx1 = min(wx0 + 7, W - 1), wy1 = min(wy0 + 3, H - 1);
-  c.wx_hi = hfr_pix_to_ndc(W - 1 - wx0, W, H);
-  c.wx_lo = hfr_pix_to_ndc(W - 1 - wx1, W, H);
-  c.wy_hi = hfr_pix_to_ndc(H - 1 - wy0, H, W);
-  c.wy_lo = hfr_pix_to_ndc(H - 1 - wy1, H, W);
+  c.wx_hi = pix_to_ndc_pre(W - 1 - wx0, rx, ox, W);
+  c.wx_lo = pix_to_ndc_pre(W - 1 - wx1, rx, ox, W);
+  c.wy_hi = pix_to_ndc_pre(H - 1 - wy0, ry, oy, H);
+  c.wy_lo = pix_to_ndc_pre(H - 1 - wy1, ry, oy, H);
   return c;
 }
 

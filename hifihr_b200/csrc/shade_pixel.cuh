@@ -57,6 +57,17 @@ template <int KMAX>
 HFR_HD void shade_pixel(const HfrShadeFwdArgs& a, int n, const int64_t* id, const float* z,
                                             const float* d, const float* b, float* rgba) {
   const int K = a.p.K;
+  {   // empty pixel: the blends reduce to the background (alpha 0); silhouette colour stays 1
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) any = any || (k < K && id[k] >= 0);
+    if (!any) {
+      const bool ones = a.p.blend == HFR_BLEND_SIGMOID_ALPHA;
+      rgba[0] = ones ? 1.0f : a.p.background[0]; rgba[1] = ones ? 1.0f : a.p.background[1];
+      rgba[2] = ones ? 1.0f : a.p.background[2]; rgba[3] = 0.0f;
+      return;
+    }
+  }
   bool valid[KMAX];
   float colors[KMAX * 3];
   float dhat[3], dlen;
