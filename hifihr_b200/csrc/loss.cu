@@ -4,7 +4,7 @@
 //   loss : losses.py:355-378 (texture L1, mean-RGB, SSIM), :399-408 (silhouette L1, IoU) with
 //          utils/losses_util.py:366-378 and utils/pytorch_ssim/__init__.py:17-37.
 //
-// SSIM is a separable 11x11 Gaussian stencil evaluated per 16x16 tile out of shared memory
+// SSIM is a separable 11x11 Gaussian stencil evaluated per 32x32 tile out of shared memory
 // (zero padding as F.conv2d(padding=5)); its backward is the same stencil applied to three
 // per-pixel derivative maps, so the whole photometric loss costs two passes over the image.
 #include "common.cuh"
@@ -58,182 +58,289 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(HfrPoolBwdArgs a) {
 }
 
 // ------------------------------------------------------------------------------------- losses
-constexpr int kT = 16, kR = 5, kHalo = kT + 2 * kR;   // 16x16 tile, 11-tap window
+// One CTA = one 32x32 pixel tile of one sample, one colour channel at a time.  The separable
+// 11-tap Gaussian runs out of shared memory with register strips: in the horizontal pass a thread
+// owns 8 consecutive outputs of one halo row (18 inputs read once as 128-bit LDS, 5 moment maps x
+// 8 x 11 FMAs), in the vertical pass 4 consecutive rows of one column (14 inputs per map), so the
+// stencil is FMA-bound instead of LDS-bound.
+constexpr int kLT = 32, kR = 5, kLH = kLT + 2 * kR;     // tile, radius, halo (42)
+constexpr int kXP = 44;                                  // pitch of the halo arrays (float4-aligned strips)
+constexpr int kHP = 36;                                  // pitch of the horizontally blurred maps
+constexpr int kLossThreads = 256;
+constexpr int kHTasks = kLH * (kLT / 8);                 // 168 (row, strip-of-8) tasks
 
 // rendered colour / silhouette of pixel p of sample n in either layout
 __device__ __forceinline__ float ld_rgb(const HfrLossArgs& a, int n, int c, size_t p, size_t hw) {
-  return a.nhwc ? a.re_img[((size_t)n * hw + p) * 4 + c] : a.re_img[((size_t)n * 3 + c) * hw + p];
+  return a.nhwc ? __ldg(a.re_img + ((size_t)n * hw + p) * 4 + c) : __ldg(a.re_img + ((size_t)n * 3 + c) * hw + p);
 }
 __device__ __forceinline__ float ld_sil(const HfrLossArgs& a, int n, size_t p, size_t hw) {
-  return a.nhwc ? a.re_img[((size_t)n * hw + p) * 4 + 3] : a.re_sil[(size_t)n * hw + p];
+  return a.nhwc ? __ldg(a.re_img + ((size_t)n * hw + p) * 4 + 3) : __ldg(a.re_sil + (size_t)n * hw + p);
 }
 
-__device__ __forceinline__ float block_sum(float v, float* scratch) {
-  v = warp_sum(v);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  __syncthreads();
-  if (lane == 0) scratch[warp] = v;
-  __syncthreads();
-  float t = 0.f;
-  if (threadIdx.x < 32) {
-    t = threadIdx.x < (blockDim.x >> 5) ? scratch[threadIdx.x] : 0.f;
-    t = warp_sum(t);
+// 8 outputs of an 11-tap row filter from 18 inputs, `NM` maps at once: out[o] += g[j-o] * in[j]
+template <int NM>
+__device__ __forceinline__ void tap_accumulate(float (&acc)[8][NM], const float (&val)[NM], int j, const float (&g)[11]) {
+#pragma unroll
+  for (int o = 0; o < 8; ++o) {
+    const int t = j - o;
+    if (t >= 0 && t < 11) {
+#pragma unroll
+      for (int m = 0; m < NM; ++m) acc[o][m] = fmaf(g[t], val[m], acc[o][m]);
+    }
   }
-  return t;  // valid in warp 0
 }
 
-// grid (tiles_x, tiles_y, N), 256 threads = one 16x16 tile.  Pointwise sums + SSIM.
-__global__ void __launch_bounds__(256) loss_fwd_kernel(HfrLossArgs a) {
-  __shared__ float sx[kHalo][kHalo + 1], sy[kHalo][kHalo + 1];
-  __shared__ float hbuf[5][kHalo][kT + 1];
-  __shared__ float g[11];
-  __shared__ float scratch[8];
-  const int n = blockIdx.z, tx = threadIdx.x % kT, ty = threadIdx.x / kT;
-  const int x0 = blockIdx.x * kT, y0 = blockIdx.y * kT;
-  const int x = x0 + tx, y = y0 + ty;
-  const bool in = x < a.W && y < a.H;
+__global__ void __launch_bounds__(kLossThreads) loss_fwd_kernel(HfrLossArgs a) {
+  __shared__ __align__(16) float xs[kLH][kXP], ys[kLH][kXP];
+  __shared__ __align__(16) float hb[5][kLH][kHP];
+  __shared__ float red[kLossThreads / 32][8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = blockIdx.z, x0 = blockIdx.x * kLT, y0 = blockIdx.y * kLT;
   const size_t hw = (size_t)a.H * a.W;
-  if (threadIdx.x < 11 && a.want_ssim) g[threadIdx.x] = a.gauss[threadIdx.x];
-  float l1 = 0.f, sr = 0.f, st = 0.f, sl = 0.f, ss = 0.f, mul = 0.f, add = 0.f;
-  if (in) {
-    const size_t p = (size_t)y * a.W + x;
-    const float sil = ld_sil(a, n, p, hw), seg = a.seg[n * hw + p];
-    const float s = sil / a.sil_scale;
-    for (int c = 0; c < 3; ++c) {
-      const float rim = ld_rgb(a, n, c, p, hw) * s;
-      const float tgt = seg * a.imgs[((size_t)n * 3 + c) * hw + p];
-      l1 += fabsf(rim - tgt); sr += rim; st += tgt;
-    }
-    sl = fabsf(sil - seg); mul = sil * seg; add = sil + seg;
-  }
+  const float inv_scale = 1.0f / a.sil_scale;
+  float g[11];
   if (a.want_ssim) {
-    const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
-    for (int c = 0; c < 3; ++c) {
-      __syncthreads();
-      for (int i = threadIdx.x; i < kHalo * kHalo; i += 256) {
-        const int hx = i % kHalo, hy = i / kHalo, gx = x0 + hx - kR, gy = y0 + hy - kR;
-        float vx = 0.f, vy = 0.f;
-        if (gx >= 0 && gx < a.W && gy >= 0 && gy < a.H) {
-          const size_t p = (size_t)gy * a.W + gx;
-          vx = ld_rgb(a, n, c, p, hw) * (ld_sil(a, n, p, hw) / a.sil_scale);
-          vy = a.seg[n * hw + p] * a.imgs[((size_t)n * 3 + c) * hw + p];
-        }
-        sx[hy][hx] = vx; sy[hy][hx] = vy;
-      }
-      __syncthreads();
-      for (int i = threadIdx.x; i < kHalo * kT; i += 256) {   // horizontal pass
-        const int ox = i % kT, hy = i / kT;
-        float m1 = 0.f, m2 = 0.f, e11 = 0.f, e22 = 0.f, e12 = 0.f;
 #pragma unroll
-        for (int t = 0; t < 11; ++t) {
-          const float w = g[t], vx = sx[hy][ox + t], vy = sy[hy][ox + t];
-          m1 += w * vx; m2 += w * vy; e11 += w * (vx * vx); e22 += w * (vy * vy); e12 += w * (vx * vy);
+    for (int t = 0; t < 11; ++t) g[t] = __ldg(a.gauss + t);
+  }
+  float l1 = 0.f, sr = 0.f, st = 0.f, sl = 0.f, ss = 0.f, mul = 0.f, add = 0.f;
+  const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
+  for (int c = 0; c < 3; ++c) {
+    if (c > 0) __syncthreads();   // previous channel's hb / xs consumed
+    // ---- halo load (zero padding as F.conv2d(padding=5)) + pointwise sums over the interior -----
+    for (int i = tid; i < kLH * kLH; i += kLossThreads) {
+      const int hy = i / kLH, hx = i - hy * kLH, gx = x0 + hx - kR, gy = y0 + hy - kR;
+      float vx = 0.f, vy = 0.f;
+      if (gx >= 0 && gx < a.W && gy >= 0 && gy < a.H) {
+        const size_t p = (size_t)gy * a.W + gx;
+        const float sil = ld_sil(a, n, p, hw), seg = __ldg(a.seg + n * hw + p);
+        vx = ld_rgb(a, n, c, p, hw) * (sil * inv_scale);
+        vy = seg * __ldg(a.imgs + ((size_t)n * 3 + c) * hw + p);
+        if (hx >= kR && hx < kR + kLT && hy >= kR && hy < kR + kLT) {
+          l1 += fabsf(vx - vy); sr += vx; st += vy;
+          if (c == 0) { sl += fabsf(sil - seg); mul += sil * seg; add += sil + seg; }
         }
-        hbuf[0][hy][ox] = m1; hbuf[1][hy][ox] = m2; hbuf[2][hy][ox] = e11; hbuf[3][hy][ox] = e22; hbuf[4][hy][ox] = e12;
       }
-      __syncthreads();
-      float m1 = 0.f, m2 = 0.f, e11 = 0.f, e22 = 0.f, e12 = 0.f;
+      xs[hy][hx] = vx; ys[hy][hx] = vy;
+    }
+    if (!a.want_ssim) continue;
+    __syncthreads();
+    // ---- horizontal pass: (halo row, strip of 8 outputs) per thread ------------------------------
+    if (tid < kHTasks) {
+      const int row = tid >> 2, strip = tid & 3;
+      float acc[8][5];
 #pragma unroll
-      for (int t = 0; t < 11; ++t) {                           // vertical pass
-        const float w = g[t];
-        m1 += w * hbuf[0][ty + t][tx]; m2 += w * hbuf[1][ty + t][tx]; e11 += w * hbuf[2][ty + t][tx];
-        e22 += w * hbuf[3][ty + t][tx]; e12 += w * hbuf[4][ty + t][tx];
+      for (int o = 0; o < 8; ++o)
+#pragma unroll
+        for (int m = 0; m < 5; ++m) acc[o][m] = 0.f;
+      const float4* xr = reinterpret_cast<const float4*>(&xs[row][strip * 8]);
+      const float4* yr = reinterpret_cast<const float4*>(&ys[row][strip * 8]);
+#pragma unroll
+      for (int q = 0; q < 5; ++q) {
+        const float4 xv = xr[q], yv = yr[q];
+        const float xa[4] = {xv.x, xv.y, xv.z, xv.w}, ya[4] = {yv.x, yv.y, yv.z, yv.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = 4 * q + e;
+          if (j < 18) {
+            const float val[5] = {xa[e], ya[e], xa[e] * xa[e], ya[e] * ya[e], xa[e] * ya[e]};
+            tap_accumulate<5>(acc, val, j, g);
+          }
+        }
       }
-      if (in) {
-        const float m11 = m1 * m1, m22 = m2 * m2, m12 = m1 * m2;
-        const float s1 = e11 - m11, s2 = e22 - m22, s12 = e12 - m12;
-        const float A1 = 2.f * m12 + C1, A2 = 2.f * s12 + C2, B1 = m11 + m22 + C1, B2 = s1 + s2 + C2;
-        const float S = (A1 * A2) / (B1 * B2);
-        ss += S;
-        if (a.dmaps) {
-          const float ib = 1.0f / (B1 * B2);
-          const float dm1 = 2.f * m2 * A2 * ib - 2.f * m2 * A1 * ib - S * 2.f * m1 / B1 + S * 2.f * m1 / B2;
-          const float de11 = -S / B2, de12 = 2.f * A1 * ib;
-          const size_t p = (size_t)y * a.W + x;
-          a.dmaps[((size_t)n * 9 + c * 3 + 0) * hw + p] = dm1;
-          a.dmaps[((size_t)n * 9 + c * 3 + 1) * hw + p] = de11;
-          a.dmaps[((size_t)n * 9 + c * 3 + 2) * hw + p] = de12;
+#pragma unroll
+      for (int m = 0; m < 5; ++m) {
+        float4* dst = reinterpret_cast<float4*>(&hb[m][row][strip * 8]);
+        dst[0] = make_float4(acc[0][m], acc[1][m], acc[2][m], acc[3][m]);
+        dst[1] = make_float4(acc[4][m], acc[5][m], acc[6][m], acc[7][m]);
+      }
+    }
+    __syncthreads();
+    // ---- vertical pass: (column, strip of 4 rows) per thread, then the SSIM map --------------------
+    {
+      const int x = lane, rs = warp;       // 8 warps x 4 rows = 32 rows
+      float acc[4][5];
+#pragma unroll
+      for (int o = 0; o < 4; ++o)
+#pragma unroll
+        for (int m = 0; m < 5; ++m) acc[o][m] = 0.f;
+#pragma unroll
+      for (int j = 0; j < 14; ++j) {
+        float val[5];
+#pragma unroll
+        for (int m = 0; m < 5; ++m) val[m] = hb[m][rs * 4 + j][x];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+          const int t = j - o;
+          if (t >= 0 && t < 11) {
+#pragma unroll
+            for (int m = 0; m < 5; ++m) acc[o][m] = fmaf(g[t], val[m], acc[o][m]);
+          }
+        }
+      }
+      const int gx = x0 + x;
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        const int gy = y0 + rs * 4 + o;
+        if (gx < a.W && gy < a.H) {
+          const float m1 = acc[o][0], m2 = acc[o][1], e11 = acc[o][2], e22 = acc[o][3], e12 = acc[o][4];
+          const float m11 = m1 * m1, m22 = m2 * m2, m12 = m1 * m2;
+          const float s1 = e11 - m11, s2 = e22 - m22, s12 = e12 - m12;
+          const float A1 = 2.f * m12 + C1, A2 = 2.f * s12 + C2, B1 = m11 + m22 + C1, B2 = s1 + s2 + C2;
+          const float ib1 = 1.0f / B1, ib2 = 1.0f / B2;
+          const float S = (A1 * A2) * (ib1 * ib2);
+          ss += S;
+          if (a.dmaps) {
+            const float ib = ib1 * ib2;
+            const float dm1 = 2.f * m2 * (A2 - A1) * ib + 2.f * m1 * S * (ib2 - ib1);
+            const float de11 = -S * ib2, de12 = 2.f * A1 * ib;
+            const size_t p = (size_t)gy * a.W + gx;
+            a.dmaps[((size_t)n * 9 + c * 3 + 0) * hw + p] = dm1;
+            a.dmaps[((size_t)n * 9 + c * 3 + 1) * hw + p] = de11;
+            a.dmaps[((size_t)n * 9 + c * 3 + 2) * hw + p] = de12;
+          }
         }
       }
     }
   }
-  const float vals[7] = {l1, sr, st, sl, ss, mul, add};
-  const int dst[7] = {HFR_LOSS_L1, HFR_LOSS_SUM_R, HFR_LOSS_SUM_T, HFR_LOSS_SIL, HFR_LOSS_SSIM,
-                      HFR_LOSS_NSUMS + n, HFR_LOSS_NSUMS + a.N + n};
-  for (int i = 0; i < 7; ++i) {
-    const float t = block_sum(vals[i], scratch);
-    if (threadIdx.x == 0 && t != 0.0f) atomicAdd(a.sums + dst[i], t);
+  // ---- block reduction of the 7 partial sums: one atomic each per CTA -------------------------------
+  float vals[7] = {l1, sr, st, sl, ss, mul, add};
+#pragma unroll
+  for (int i = 0; i < 7; ++i) vals[i] = warp_sum(vals[i]);
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 7; ++i) red[warp][i] = vals[i];
+  }
+  __syncthreads();
+  if (tid < 7) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < kLossThreads / 32; ++w) t += red[w][tid];
+    const int dst = tid < 5 ? tid : (tid == 5 ? HFR_LOSS_NSUMS + n : HFR_LOSS_NSUMS + a.N + n);
+    if (t != 0.0f) atomicAdd(a.sums + dst, t);
   }
 }
 
-__global__ void __launch_bounds__(256) loss_bwd_kernel(HfrLossBwdArgs b) {
+__global__ void __launch_bounds__(kLossThreads) loss_bwd_kernel(HfrLossBwdArgs b) {
   const HfrLossArgs& a = b.f;
-  __shared__ float sd[3][kHalo][kHalo + 1];
-  __shared__ float hbuf[3][kHalo][kT + 1];
-  __shared__ float g[11];
-  const int n = blockIdx.z, tx = threadIdx.x % kT, ty = threadIdx.x / kT;
-  const int x0 = blockIdx.x * kT, y0 = blockIdx.y * kT;
-  const int x = x0 + tx, y = y0 + ty;
-  const bool in = x < a.W && y < a.H;
+  __shared__ __align__(16) float sd[3][kLH][kXP];
+  __shared__ __align__(16) float hb[3][kLH][kHP];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = blockIdx.z, x0 = blockIdx.x * kLT, y0 = blockIdx.y * kLT;
   const size_t hw = (size_t)a.H * a.W;
   const bool ssim = a.want_ssim && a.dmaps;
-  if (threadIdx.x < 11 && ssim) g[threadIdx.x] = b.gauss[threadIdx.x];
-  const float w_tex = b.w[0], w_mrgb = b.w[1], w_ssim = b.w[2], w_sil = b.w[3], w_iou = b.w[4];
-  const float cnt = (float)b.count_global;
-  const float mR = a.sums[HFR_LOSS_SUM_R] / cnt, mT = a.sums[HFR_LOSS_SUM_T] / cnt;
-  const float k_mrgb = w_mrgb * 2.0f * (mT - mR) * (-1.0f / cnt);
-  float sil = 0.f, seg = 0.f, s = 0.f, gsil = 0.f;
-  size_t p = 0;
-  if (in) {
-    p = (size_t)y * a.W + x;
-    sil = ld_sil(a, n, p, hw); seg = a.seg[n * hw + p];
-    s = sil / a.sil_scale;
-    const float d = sil - seg;
-    gsil = w_sil * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) / ((float)b.n_global * (float)hw);
-    const float mul = a.sums[HFR_LOSS_NSUMS + n], add = a.sums[HFR_LOSS_NSUMS + a.N + n];
-    const float den = add - mul;
-    gsil += w_iou * (-1.0f / (float)b.n_global) * (seg * den - mul * (1.0f - seg)) / (den * den);
+  float g[11];
+  if (ssim) {
+#pragma unroll
+    for (int t = 0; t < 11; ++t) g[t] = __ldg(b.gauss + t);
+  }
+  const float w_tex = __ldg(b.w), w_mrgb = __ldg(b.w + 1), w_ssim = __ldg(b.w + 2), w_sil = __ldg(b.w + 3), w_iou = __ldg(b.w + 4);
+  const float cnt = (float)b.count_global, icnt = 1.0f / cnt;
+  const float mR = a.sums[HFR_LOSS_SUM_R] * icnt, mT = a.sums[HFR_LOSS_SUM_T] * icnt;
+  const float k_mrgb = w_mrgb * 2.0f * (mT - mR) * (-icnt);
+  const float inv_scale = 1.0f / a.sil_scale;
+  // this thread's 4 pixels: column x0+lane, rows y0 + warp*4 + o
+  const int gx = x0 + lane;
+  float sil[4], seg[4], s[4], gsil[4], grgb[4][3];
+  bool in[4];
+  const float mulv = a.sums[HFR_LOSS_NSUMS + n], addv = a.sums[HFR_LOSS_NSUMS + a.N + n];
+  const float den = addv - mulv;
+#pragma unroll
+  for (int o = 0; o < 4; ++o) {
+    const int gy = y0 + warp * 4 + o;
+    in[o] = gx < a.W && gy < a.H;
+    sil[o] = seg[o] = s[o] = gsil[o] = 0.f;
+    if (in[o]) {
+      const size_t p = (size_t)gy * a.W + gx;
+      sil[o] = ld_sil(a, n, p, hw); seg[o] = __ldg(a.seg + n * hw + p);
+      s[o] = sil[o] * inv_scale;
+      const float d = sil[o] - seg[o];
+      gsil[o] = w_sil * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) / ((float)b.n_global * (float)hw);
+      gsil[o] += w_iou * (-1.0f / (float)b.n_global) * (seg[o] * den - mulv * (1.0f - seg[o])) / (den * den);
+    }
   }
   for (int c = 0; c < 3; ++c) {
-    float gS = 0.0f, xv = 0.f, yv = 0.f, rimg = 0.f;
-    if (in) {
-      rimg = ld_rgb(a, n, c, p, hw);
-      xv = rimg * s;
-      yv = seg * a.imgs[((size_t)n * 3 + c) * hw + p];
-    }
+    float r[4][3];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) r[o][0] = r[o][1] = r[o][2] = 0.f;
     if (ssim) {
-      __syncthreads();
-      for (int i = threadIdx.x; i < kHalo * kHalo; i += 256) {
-        const int hx = i % kHalo, hy = i / kHalo, gx = x0 + hx - kR, gy = y0 + hy - kR;
-        const bool ok = gx >= 0 && gx < a.W && gy >= 0 && gy < a.H;
-        const size_t q = ok ? (size_t)gy * a.W + gx : 0;
-        for (int m = 0; m < 3; ++m) sd[m][hy][hx] = ok ? a.dmaps[((size_t)n * 9 + c * 3 + m) * hw + q] : 0.f;
+      if (c > 0) __syncthreads();
+      for (int i = tid; i < kLH * kLH; i += kLossThreads) {
+        const int hy = i / kLH, hx = i - hy * kLH, qx = x0 + hx - kR, qy = y0 + hy - kR;
+        const bool ok = qx >= 0 && qx < a.W && qy >= 0 && qy < a.H;
+        const size_t q = ok ? (size_t)qy * a.W + qx : 0;
+#pragma unroll
+        for (int m = 0; m < 3; ++m) sd[m][hy][hx] = ok ? __ldg(a.dmaps + ((size_t)n * 9 + c * 3 + m) * hw + q) : 0.f;
       }
       __syncthreads();
-      for (int i = threadIdx.x; i < kHalo * kT; i += 256) {
-        const int ox = i % kT, hy = i / kT;
-        float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+      if (tid < kHTasks) {
+        const int row = tid >> 2, strip = tid & 3;
+        float acc[8][3];
 #pragma unroll
-        for (int t = 0; t < 11; ++t) { const float w = g[t]; r0 += w * sd[0][hy][ox + t]; r1 += w * sd[1][hy][ox + t]; r2 += w * sd[2][hy][ox + t]; }
-        hbuf[0][hy][ox] = r0; hbuf[1][hy][ox] = r1; hbuf[2][hy][ox] = r2;
+        for (int o = 0; o < 8; ++o) acc[o][0] = acc[o][1] = acc[o][2] = 0.f;
+        const float4* r0 = reinterpret_cast<const float4*>(&sd[0][row][strip * 8]);
+        const float4* r1 = reinterpret_cast<const float4*>(&sd[1][row][strip * 8]);
+        const float4* r2 = reinterpret_cast<const float4*>(&sd[2][row][strip * 8]);
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+          const float4 v0 = r0[q], v1 = r1[q], v2 = r2[q];
+          const float a0[4] = {v0.x, v0.y, v0.z, v0.w}, a1[4] = {v1.x, v1.y, v1.z, v1.w}, a2[4] = {v2.x, v2.y, v2.z, v2.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int j = 4 * q + e;
+            if (j < 18) {
+              const float val[3] = {a0[e], a1[e], a2[e]};
+              tap_accumulate<3>(acc, val, j, g);
+            }
+          }
+        }
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+          float4* dst = reinterpret_cast<float4*>(&hb[m][row][strip * 8]);
+          dst[0] = make_float4(acc[0][m], acc[1][m], acc[2][m], acc[3][m]);
+          dst[1] = make_float4(acc[4][m], acc[5][m], acc[6][m], acc[7][m]);
+        }
       }
       __syncthreads();
-      float r0 = 0.f, r1 = 0.f, r2 = 0.f;
 #pragma unroll
-      for (int t = 0; t < 11; ++t) { const float w = g[t]; r0 += w * hbuf[0][ty + t][tx]; r1 += w * hbuf[1][ty + t][tx]; r2 += w * hbuf[2][ty + t][tx]; }
-      gS = r0 + 2.0f * xv * r1 + yv * r2;
+      for (int j = 0; j < 14; ++j) {
+        const float v0 = hb[0][warp * 4 + j][lane], v1 = hb[1][warp * 4 + j][lane], v2 = hb[2][warp * 4 + j][lane];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+          const int t = j - o;
+          if (t >= 0 && t < 11) {
+            r[o][0] = fmaf(g[t], v0, r[o][0]); r[o][1] = fmaf(g[t], v1, r[o][1]); r[o][2] = fmaf(g[t], v2, r[o][2]);
+          }
+        }
+      }
     }
-    if (in) {
-      const float d = xv - yv;
-      float grim = w_tex * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) / cnt + k_mrgb + w_ssim * (-1.0f / cnt) * gS;
-      if (a.nhwc) b.g_re_img[((size_t)n * hw + p) * 4 + c] = grim * s;
-      else b.g_re_img[((size_t)n * 3 + c) * hw + p] = grim * s;
-      gsil += grim * rimg / a.sil_scale;
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      grgb[o][c] = 0.f;
+      if (in[o]) {
+        const size_t p = (size_t)(y0 + warp * 4 + o) * a.W + gx;
+        const float rimg = ld_rgb(a, n, c, p, hw);
+        const float xv = rimg * s[o], yv = seg[o] * __ldg(a.imgs + ((size_t)n * 3 + c) * hw + p);
+        const float gS = r[o][0] + 2.0f * xv * r[o][1] + yv * r[o][2];
+        const float d = xv - yv;
+        const float grim = w_tex * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) * icnt + k_mrgb + w_ssim * (-icnt) * gS;
+        grgb[o][c] = grim * s[o];
+        gsil[o] += grim * rimg * inv_scale;
+      }
     }
   }
-  if (in) {
-    if (a.nhwc) b.g_re_img[((size_t)n * hw + p) * 4 + 3] = gsil;
-    else b.g_re_sil[n * hw + p] = gsil;
+#pragma unroll
+  for (int o = 0; o < 4; ++o) {
+    if (in[o]) {
+      const size_t p = (size_t)(y0 + warp * 4 + o) * a.W + gx;
+      if (a.nhwc) {
+        *reinterpret_cast<float4*>(b.g_re_img + ((size_t)n * hw + p) * 4) = make_float4(grgb[o][0], grgb[o][1], grgb[o][2], gsil[o]);
+      } else {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) b.g_re_img[((size_t)n * 3 + c) * hw + p] = grgb[o][c];
+        b.g_re_sil[n * hw + p] = gsil[o];
+      }
+    }
   }
 }
 
@@ -267,8 +374,8 @@ extern "C" int hfr_loss_forward(const HfrLossArgs* a, void* stream) {
   if (a->N == 0) return HFR_OK;
   HFR_CHECK_ARG(a->re_img && (a->nhwc || a->re_sil) && a->imgs && a->seg && a->sums, "loss_forward: null pointer");
   HFR_CHECK_ARG(!a->want_ssim || a->gauss, "loss_forward: SSIM needs the Gaussian taps");
-  dim3 grid((a->W + kT - 1) / kT, (a->H + kT - 1) / kT, a->N);
-  loss_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*a);
+  dim3 grid((a->W + kLT - 1) / kLT, (a->H + kLT - 1) / kLT, a->N);
+  loss_fwd_kernel<<<grid, kLossThreads, 0, (cudaStream_t)stream>>>(*a);
   HFR_CHECK_LAUNCH("loss_forward");
   return HFR_OK;
 }
@@ -281,8 +388,8 @@ extern "C" int hfr_loss_backward(const HfrLossBwdArgs* a, void* stream) {
                 "loss_backward: null pointer");
   HFR_CHECK_ARG(!(a->f.want_ssim && a->f.dmaps) || a->gauss, "loss_backward: SSIM needs the Gaussian taps");
   HFR_CHECK_ARG(a->count_global > 0 && a->n_global > 0, "loss_backward: bad global counts");
-  dim3 grid((a->f.W + kT - 1) / kT, (a->f.H + kT - 1) / kT, a->f.N);
-  loss_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*a);
+  dim3 grid((a->f.W + kLT - 1) / kLT, (a->f.H + kLT - 1) / kLT, a->f.N);
+  loss_bwd_kernel<<<grid, kLossThreads, 0, (cudaStream_t)stream>>>(*a);
   HFR_CHECK_LAUNCH("loss_backward");
   return HFR_OK;
 }
