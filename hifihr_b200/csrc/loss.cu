@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(kLossThreads) loss_fwd_kernel(HfrLossArgs a) {
   }
 }
 
-__global__ void __launch_bounds__(kLossThreads) loss_bwd_kernel(HfrLossBwdArgs b) {
+__global__ void __launch_bounds__(kLossThreads, 3) loss_bwd_kernel(HfrLossBwdArgs b) {
   const HfrLossArgs& a = b.f;
   __shared__ __align__(16) float sd[3][kLH][kXP];
   __shared__ __align__(16) float hb[3][kLH][kHP];

@@ -62,7 +62,11 @@ HFR_HD bool hfr_raster_bary(float px, float py, const float* v, float area, int 
   if (clip) {
     c0 = hfr_clamp01(b0); c1 = hfr_clamp01(b1); c2 = hfr_clamp01(b2);
     const float s = fmaxf(XADD(XADD(c0, c1), c2), 1e-5f);
-    c0 = XDIV(c0, s); c1 = XDIV(c1, s); c2 = XDIV(c2, s);
+    // a clipped coordinate is very often exactly 0, and 0/s would take div.rn's slow path (FCHK): divide a
+    // stand-in instead and select the exact +0 afterwards (s > 0, so 0/s = +0)
+    const float q0 = XDIV(c0 == 0.0f ? 1.0f : c0, s), q1 = XDIV(c1 == 0.0f ? 1.0f : c1, s),
+                q2 = XDIV(c2 == 0.0f ? 1.0f : c2, s);
+    c0 = c0 == 0.0f ? 0.0f : q0; c1 = c1 == 0.0f ? 0.0f : q1; c2 = c2 == 0.0f ? 0.0f : q2;
   }
   bc[0] = c0; bc[1] = c1; bc[2] = c2;
   *pz = XADD(XADD(XMUL(c0, z0), XMUL(c1, z1)), XMUL(c2, z2));

@@ -36,36 +36,12 @@ __device__ __forceinline__ int selk_i(const int (&a)[KMAX], int k) {
   return r;
 }
 
-// Sum v[c] over the lanes with `mine` set; lane L returns the total of component L (c < 32).
-// Transposed butterfly: 16+8+4+2+1 = 31 shuffles instead of 32 x 5.
-__device__ __forceinline__ float warp_transpose_sum(const float (&v)[32], bool mine, int lane) {
-  float w[16];
-  {
-    const bool hi = (lane & 16) != 0;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const float lo_v = mine ? v[i] : 0.f, hi_v = mine ? v[i + 16] : 0.f;
-      const float send = hi ? lo_v : hi_v;
-      const float keep = hi ? hi_v : lo_v;
-      w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    }
-  }
-#pragma unroll
-  for (int s = 8; s >= 1; s >>= 1) {
-    const bool hi = (lane & s) != 0;
-#pragma unroll
-    for (int i = 0; i < s; ++i) {
-      const float send = hi ? w[i] : w[i + s];
-      const float keep = hi ? w[i + s] : w[i];
-      w[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-    }
-  }
-  return w[0];
-}
-
 template <int KMAX>
 __global__ void __launch_bounds__(kBwdThreads) shade_bwd_kernel(HfrShadeBwdArgs a) {
   __shared__ float s_light[kBwdThreads / 32][6];
+  // per-warp staging of the 27 per-fragment components, pitch 33: lane L writes column L (bank j+L),
+  // lane j later sums row j over the lanes of one face group (bank j+m) - both conflict-free
+  __shared__ float s_red[kBwdThreads / 32][27][33];
   const HfrShadeFwdArgs& f = a.f;
   const HfrShadeParams& P = f.p;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -168,9 +144,9 @@ __global__ void __launch_bounds__(kBwdThreads) shade_bwd_kernel(HfrShadeBwdArgs 
       }
       if (!todo) continue;
       const int face = vk ? selk_i<KMAX>(fl, k) : -1;
-      float v27[32];
+      float v27[27];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v27[i] = 0.f;
+      for (int i = 0; i < 27; ++i) v27[i] = 0.f;
       int vid[3] = {0, 0, 0};
       if (vk) {
         const float* __restrict__ bp = f.bary + (pix * K + k) * 3;
@@ -231,22 +207,37 @@ __global__ void __launch_bounds__(kBwdThreads) shade_bwd_kernel(HfrShadeBwdArgs 
       }
       if (!(a.g_verts_ndc || (k < kshade && (a.g_verts_view || a.g_vnormals)))) continue;
       if (P.blend == HFR_BLEND_HARD && k >= kshade) continue;   // nothing flows through the hidden slots
-      // segmented reduction: one pass per distinct face among the lanes of this warp
+      // segmented reduction: stage the components in shared memory, then per distinct face among the
+      // lanes of this warp lane j sums component j over the group's lanes and issues one RED
+      if (vk) {
+#pragma unroll
+        for (int i = 0; i < 27; ++i) s_red[warp][i][lane] = v27[i];
+      }
+      __syncwarp();
       while (todo) {
         const int leader = __ffs(todo) - 1;
         const int lf = __shfl_sync(0xffffffffu, face, leader);
-        const bool mine = vk && face == lf;
-        todo &= ~__ballot_sync(0xffffffffu, mine);
-        const float total = warp_transpose_sum(v27, mine, lane);
+        const unsigned grp = __ballot_sync(0xffffffffu, vk && face == lf);
+        todo &= ~grp;
         const int l0 = __shfl_sync(0xffffffffu, vid[0], leader), l1 = __shfl_sync(0xffffffffu, vid[1], leader),
                   l2 = __shfl_sync(0xffffffffu, vid[2], leader);
-        if (lane < 27 && total != 0.f) {
-          const int corner = lane / 9, r = lane - 9 * corner, which = r / 3, c = r - 3 * which;
-          const int vv = corner == 0 ? l0 : (corner == 1 ? l1 : l2);
-          float* base = which == 0 ? a.g_verts_ndc : (which == 1 ? a.g_verts_view : a.g_vnormals);
-          if (base) atomicAdd(base + ((size_t)n * V + vv) * 3 + c, total);
+        if (lane < 27) {
+          float total = 0.f;
+          unsigned g2 = grp;
+          while (g2) {
+            const int m = __ffs(g2) - 1;
+            g2 &= g2 - 1;
+            total += s_red[warp][lane][m];
+          }
+          if (total != 0.f) {
+            const int corner = lane / 9, r = lane - 9 * corner, which = r / 3, c = r - 3 * which;
+            const int vv = corner == 0 ? l0 : (corner == 1 ? l1 : l2);
+            float* base = which == 0 ? a.g_verts_ndc : (which == 1 ? a.g_verts_view : a.g_vnormals);
+            if (base) atomicAdd(base + ((size_t)n * V + vv) * 3 + c, total);
+          }
         }
       }
+      __syncwarp();
     }
   }
   else if (dense && active) {   // no fragment in this warp: the dense per-fragment gradients are zero
