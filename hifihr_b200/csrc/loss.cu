@@ -90,9 +90,13 @@ __device__ __forceinline__ void tap_accumulate(float (&acc)[8][NM], const float 
   }
 }
 
-__global__ void __launch_bounds__(kLossThreads) loss_fwd_kernel(HfrLossArgs a) {
-  __shared__ __align__(16) float xs[kLH][kXP], ys[kLH][kXP];
-  __shared__ __align__(16) float hb[5][kLH][kHP];
+constexpr size_t kLossFwdSmem = (size_t)(6 * kLH * kXP + 5 * kLH * kHP) * sizeof(float);
+
+__global__ void __launch_bounds__(kLossThreads, 3) loss_fwd_kernel(HfrLossArgs a) {
+  extern __shared__ __align__(16) float lsm[];
+  float (*xs3)[kLH][kXP] = reinterpret_cast<float (*)[kLH][kXP]>(lsm);                       // [3]
+  float (*ys3)[kLH][kXP] = reinterpret_cast<float (*)[kLH][kXP]>(lsm + 3 * kLH * kXP);         // [3]
+  float (*hb)[kLH][kHP] = reinterpret_cast<float (*)[kLH][kHP]>(lsm + 6 * kLH * kXP);          // [5]
   __shared__ float red[kLossThreads / 32][8];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = blockIdx.z, x0 = blockIdx.x * kLT, y0 = blockIdx.y * kLT;
@@ -105,24 +109,38 @@ __global__ void __launch_bounds__(kLossThreads) loss_fwd_kernel(HfrLossArgs a) {
   }
   float l1 = 0.f, sr = 0.f, st = 0.f, sl = 0.f, ss = 0.f, mul = 0.f, add = 0.f;
   const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
-  for (int c = 0; c < 3; ++c) {
-    if (c > 0) __syncthreads();   // previous channel's hb / xs consumed
-    // ---- halo load (zero padding as F.conv2d(padding=5)) + pointwise sums over the interior -----
-    for (int i = tid; i < kLH * kLH; i += kLossThreads) {
-      const int hy = i / kLH, hx = i - hy * kLH, gx = x0 + hx - kR, gy = y0 + hy - kR;
-      float vx = 0.f, vy = 0.f;
-      if (gx >= 0 && gx < a.W && gy >= 0 && gy < a.H) {
-        const size_t p = (size_t)gy * a.W + gx;
-        const float sil = ld_sil(a, n, p, hw), seg = __ldg(a.seg + n * hw + p);
-        vx = ld_rgb(a, n, c, p, hw) * (sil * inv_scale);
-        vy = seg * __ldg(a.imgs + ((size_t)n * 3 + c) * hw + p);
-        if (hx >= kR && hx < kR + kLT && hy >= kR && hy < kR + kLT) {
-          l1 += fabsf(vx - vy); sr += vx; st += vy;
-          if (c == 0) { sl += fabsf(sil - seg); mul += sil * seg; add += sil + seg; }
-        }
+  // ---- halo load, all three channels at once (zero padding as F.conv2d(padding=5)) + the pointwise
+  //      sums over the tile's interior
+  for (int i = tid; i < kLH * kLH; i += kLossThreads) {
+    const int hy = i / kLH, hx = i - hy * kLH, gx = x0 + hx - kR, gy = y0 + hy - kR;
+    float vx[3] = {0.f, 0.f, 0.f}, vy[3] = {0.f, 0.f, 0.f};
+    if (gx >= 0 && gx < a.W && gy >= 0 && gy < a.H) {
+      const size_t p = (size_t)gy * a.W + gx;
+      float rgb[3], sil;
+      if (a.nhwc) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(a.re_img + ((size_t)n * hw + p) * 4));
+        rgb[0] = q.x; rgb[1] = q.y; rgb[2] = q.z; sil = q.w;
+      } else {
+        sil = __ldg(a.re_sil + (size_t)n * hw + p);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) rgb[c] = __ldg(a.re_img + ((size_t)n * 3 + c) * hw + p);
       }
-      xs[hy][hx] = vx; ys[hy][hx] = vy;
+      const float seg = __ldg(a.seg + n * hw + p), s = sil * inv_scale;
+      const bool interior = hx >= kR && hx < kR + kLT && hy >= kR && hy < kR + kLT;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        vx[c] = rgb[c] * s;
+        vy[c] = seg * __ldg(a.imgs + ((size_t)n * 3 + c) * hw + p);
+        if (interior) { l1 += fabsf(vx[c] - vy[c]); sr += vx[c]; st += vy[c]; }
+      }
+      if (interior) { sl += fabsf(sil - seg); mul += sil * seg; add += sil + seg; }
     }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { xs3[c][hy][hx] = vx[c]; ys3[c][hy][hx] = vy[c]; }
+  }
+  for (int c = 0; c < 3; ++c) {
+    float (*xs)[kXP] = xs3[c];
+    float (*ys)[kXP] = ys3[c];
     if (!a.want_ssim) continue;
     __syncthreads();
     // ---- horizontal pass: (halo row, strip of 8 outputs) per thread ------------------------------
@@ -265,12 +283,29 @@ __global__ void __launch_bounds__(kLossThreads, 3) loss_bwd_kernel(HfrLossBwdArg
     for (int o = 0; o < 4; ++o) r[o][0] = r[o][1] = r[o][2] = 0.f;
     if (ssim) {
       if (c > 0) __syncthreads();
-      for (int i = tid; i < kLH * kLH; i += kLossThreads) {
-        const int hy = i / kLH, hx = i - hy * kLH, qx = x0 + hx - kR, qy = y0 + hy - kR;
-        const bool ok = qx >= 0 && qx < a.W && qy >= 0 && qy < a.H;
-        const size_t q = ok ? (size_t)qy * a.W + qx : 0;
+      if ((a.W & 3) == 0) {
+        // rows are loaded as 12 aligned float4 covering columns x0-8 .. x0+39 (halo = x0-5 .. x0+36)
+        for (int i = tid; i < 3 * kLH * 12; i += kLossThreads) {
+          const int m = i / (kLH * 12), rem = i - m * (kLH * 12), hy = rem / 12, q = rem - hy * 12;
+          const int qy = y0 + hy - kR, qx = x0 - 8 + 4 * q;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (qy >= 0 && qy < a.H && qx >= 0 && qx < a.W)
+            v = __ldg(reinterpret_cast<const float4*>(a.dmaps + ((size_t)n * 9 + c * 3 + m) * hw + (size_t)qy * a.W + qx));
+          const float e[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int m = 0; m < 3; ++m) sd[m][hy][hx] = ok ? __ldg(a.dmaps + ((size_t)n * 9 + c * 3 + m) * hw + q) : 0.f;
+          for (int t = 0; t < 4; ++t) {
+            const int hx = 4 * q + t - 3;
+            if (hx >= 0 && hx < kLH) sd[m][hy][hx] = e[t];
+          }
+        }
+      } else {
+        for (int i = tid; i < kLH * kLH; i += kLossThreads) {
+          const int hy = i / kLH, hx = i - hy * kLH, qx = x0 + hx - kR, qy = y0 + hy - kR;
+          const bool ok = qx >= 0 && qx < a.W && qy >= 0 && qy < a.H;
+          const size_t q = ok ? (size_t)qy * a.W + qx : 0;
+#pragma unroll
+          for (int m = 0; m < 3; ++m) sd[m][hy][hx] = ok ? __ldg(a.dmaps + ((size_t)n * 9 + c * 3 + m) * hw + q) : 0.f;
+        }
       }
       __syncthreads();
       if (tid < kHTasks) {
@@ -375,7 +410,12 @@ extern "C" int hfr_loss_forward(const HfrLossArgs* a, void* stream) {
   HFR_CHECK_ARG(a->re_img && (a->nhwc || a->re_sil) && a->imgs && a->seg && a->sums, "loss_forward: null pointer");
   HFR_CHECK_ARG(!a->want_ssim || a->gauss, "loss_forward: SSIM needs the Gaussian taps");
   dim3 grid((a->W + kLT - 1) / kLT, (a->H + kLT - 1) / kLT, a->N);
-  loss_fwd_kernel<<<grid, kLossThreads, 0, (cudaStream_t)stream>>>(*a);
+  static bool attr_set = false;   // benign race: the attribute is idempotent
+  if (!attr_set) {
+    cudaFuncSetAttribute(loss_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLossFwdSmem);
+    attr_set = true;
+  }
+  loss_fwd_kernel<<<grid, kLossThreads, kLossFwdSmem, (cudaStream_t)stream>>>(*a);
   HFR_CHECK_LAUNCH("loss_forward");
   return HFR_OK;
 }

@@ -37,11 +37,16 @@ __device__ __forceinline__ int selk_i(const int (&a)[KMAX], int k) {
 }
 
 template <int KMAX>
-__global__ void __launch_bounds__(kBwdThreads) shade_bwd_kernel(HfrShadeBwdArgs a) {
+__global__ void __launch_bounds__(kBwdThreads, 2) shade_bwd_kernel(HfrShadeBwdArgs a) {
   __shared__ float s_light[kBwdThreads / 32][6];
   // per-warp staging of the 27 per-fragment components, pitch 33: lane L writes column L (bank j+L),
   // lane j later sums row j over the lanes of one face group (bank j+m) - both conflict-free
   __shared__ float s_red[kBwdThreads / 32][27][33];
+  // per-thread fragment table [KMAX][4][threads]: face id, sigmoid prob, softmax exponent, prod_{j!=k}(1-p_j).
+  // Indexed by the runtime slot k in the loop below (register arrays would need select chains).
+  extern __shared__ float s_frag[];
+  float* my_frag = s_frag + threadIdx.x;
+#define FRAG(k, field) my_frag[((k) * 4 + (field)) * kBwdThreads]
   const HfrShadeFwdArgs& f = a.f;
   const HfrShadeParams& P = f.p;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -88,9 +93,15 @@ __global__ void __launch_bounds__(kBwdThreads) shade_bwd_kernel(HfrShadeBwdArgs 
   }
 
   if (warp_any) {
-    float g_colors[KMAX * 3], g_z[KMAX], g_d[KMAX];
+    // ---- per-pixel blend state.  The blend is differentiated WITHOUT the fragments' colours: the
+    //      forward image (rgb = (sum_k w_k c_k + delta bg) / den) is an input, so den, d/d(rgb) and the
+    //      coupling through z_max follow from (z, d) and the stored pixel alone; a fragment's own
+    //      colour is only needed when that fragment is shaded in the loop below.
+    float prob[KMAX], wexp[KMAX], others[KMAX];   // sigmoid prob, exp((zinv-zmax)/gamma), prod_{j!=k}(1-p_j)
+    float gnum[3] = {0.f, 0.f, 0.f}, gden = 0.f, gzmax = 0.f, g_alpha = 0.f;
+    int kmax = -1;
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k) { g_z[k] = 0.f; g_d[k] = 0.f; g_colors[3 * k] = g_colors[3 * k + 1] = g_colors[3 * k + 2] = 0.f; }
+    for (int k = 0; k < KMAX; ++k) { prob[k] = 0.f; wexp[k] = 0.f; others[k] = 1.f; }
     if (any) {
       if (K == KMAX && (KMAX % 4) == 0) {
 #pragma unroll
@@ -105,29 +116,63 @@ __global__ void __launch_bounds__(kBwdThreads) shade_bwd_kernel(HfrShadeBwdArgs 
         for (int k = 0; k < KMAX; ++k)
           if (k < K) { z[k] = __ldg(f.zbuf + pix * K + k); d[k] = __ldg(f.dists + pix * K + k); }
       }
-      // forward colours of the shaded slots (recomputed: cheaper than storing K*3 floats per pixel)
-      float colors[KMAX * 3];
-#pragma unroll
-      for (int k = 0; k < KMAX * 3; ++k) colors[k] = 1.0f;
-#pragma unroll 1
-      for (int k = 0; k < kshade; ++k) {
-        if (!((vmask >> k) & 1u)) continue;
-        const float* __restrict__ bp = f.bary + (pix * K + k) * 3;
-        const float bc[3] = {__ldg(bp), __ldg(bp + 1), __ldg(bp + 2)};
-        FragGeom g;
-        gather_frag(f, n, selk_i<KMAX>(fl, k), g);
-        HfrTexTap tap; HfrPhongCtx ctx; float texel[3], col[3];
-        shade_fragment(f, n, g, bc, dhat, lcol, col, &tap, &ctx, texel);
-#pragma unroll
-        for (int kk = 0; kk < KMAX; ++kk)
-          if (kk == k) { colors[3 * kk] = col[0]; colors[3 * kk + 1] = col[1]; colors[3 * kk + 2] = col[2]; }
-      }
       const float4 g4 = __ldg(reinterpret_cast<const float4*>(a.g_image + pix * 4));
-      const float g_rgba[4] = {g4.x, g4.y, g4.z, g4.w};
-      bool valid[KMAX];
+      g_alpha = g4.w;
+      if (P.blend == HFR_BLEND_HARD) {
+        gnum[0] = g4.x; gnum[1] = g4.y; gnum[2] = g4.z;     // g_colour of slot 0, nothing else flows
+      } else {
 #pragma unroll
-      for (int k = 0; k < KMAX; ++k) valid[k] = (vmask >> k) & 1u;
-      hfr_blend_bwd<KMAX>(P, K, valid, z, d, colors, g_rgba, g_colors, g_z, g_d);
+        for (int k = 0; k < KMAX; ++k)
+          if ((vmask >> k) & 1u) prob[k] = hfr_sigmoid(HFR_FDIV(-d[k], P.sigma));
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+          float o = 1.0f;
+#pragma unroll
+          for (int jj = 0; jj < KMAX; ++jj)
+            if (jj != k) o *= (1.0f - prob[jj]);
+          others[k] = o;
+        }
+        if (P.blend == HFR_BLEND_SIGMOID_ALPHA) {
+          gnum[0] = g4.x; gnum[1] = g4.y; gnum[2] = g4.z;   // colour of slot 0 passes straight through
+        } else {
+          const float eps = 1e-10f, zr = P.zfar - P.znear;
+          float zinv[KMAX], zmax_raw = 0.0f;
+#pragma unroll
+          for (int k = 0; k < KMAX; ++k) {
+            zinv[k] = 0.0f;
+            if ((vmask >> k) & 1u) zinv[k] = (P.zfar - z[k]) / zr;   // IEEE divide, as the forward
+            if (k < K && (k == 0 || zinv[k] > zmax_raw)) { zmax_raw = zinv[k]; kmax = k; }
+          }
+          const float zmax = fmaxf(zmax_raw, eps);
+          float wsum = 0.0f;
+#pragma unroll
+          for (int k = 0; k < KMAX; ++k) {
+            if (k < K) { wexp[k] = HFR_EXP(HFR_FDIV(zinv[k] - zmax, P.gamma)); wsum += prob[k] * wexp[k]; }
+          }
+          const float dexp = HFR_EXP(HFR_FDIV(eps - zmax, P.gamma));
+          const float delta = fmaxf(dexp, eps);
+          const float den = wsum + delta, iden = HFR_RCP(den);
+          const float4 im = __ldg(reinterpret_cast<const float4*>(f.image + pix * 4));
+          const float rgb[3] = {im.x, im.y, im.z}, gin[3] = {g4.x, g4.y, g4.z};
+          float gdelta = 0.0f, gacc = 0.0f;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            gnum[c] = gin[c] * iden;
+            gden -= gnum[c] * rgb[c];
+            gdelta += gnum[c] * P.background[c];
+            gacc += gnum[c] * (rgb[c] * den - delta * P.background[c]);   // gnum . sum_k w_k c_k
+          }
+          gdelta += gden;
+          // sum_k d/d(zinv_k - zmax) = (gden * wsum + gnum . acc) / gamma
+          gzmax = -HFR_FDIV(gden * wsum + gacc, P.gamma);
+          if (dexp >= eps) gzmax -= HFR_FDIV(gdelta * delta, P.gamma);
+          if (!(zmax_raw >= eps)) kmax = -1;
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      FRAG(k, 0) = __int_as_float(fl[k]); FRAG(k, 1) = prob[k]; FRAG(k, 2) = wexp[k]; FRAG(k, 3) = others[k];
     }
     const float xf = hfr_pix_to_ndc(P.W - 1 - xi, P.W, P.H), yf = hfr_pix_to_ndc(P.H - 1 - yi, P.H, P.W);
     const size_t tbase = (P.tex_n == 1 ? 0 : (size_t)n * P.tex_h * P.tex_w * 3);
@@ -143,7 +188,15 @@ __global__ void __launch_bounds__(kBwdThreads) shade_bwd_kernel(HfrShadeBwdArgs 
         if (a.g_dists) a.g_dists[pix * K + k] = 0.f;
       }
       if (!todo) continue;
-      const int face = vk ? selk_i<KMAX>(fl, k) : -1;
+      if (P.blend == HFR_BLEND_HARD && k > 0) {   // hidden slots of a hard blend carry no gradient
+        if (dense && vk) {
+          if (a.g_bary) { float* o = a.g_bary + (pix * K + k) * 3; o[0] = 0.f; o[1] = 0.f; o[2] = 0.f; }
+          if (a.g_zbuf) a.g_zbuf[pix * K + k] = 0.f;
+          if (a.g_dists) a.g_dists[pix * K + k] = 0.f;
+        }
+        continue;
+      }
+      const int face = vk ? __float_as_int(FRAG(k, 0)) : -1;
       float v27[27];
 #pragma unroll
       for (int i = 0; i < 27; ++i) v27[i] = 0.f;
@@ -151,21 +204,28 @@ __global__ void __launch_bounds__(kBwdThreads) shade_bwd_kernel(HfrShadeBwdArgs 
       if (vk) {
         const float* __restrict__ bp = f.bary + (pix * K + k) * 3;
         const float bc[3] = {__ldg(bp), __ldg(bp + 1), __ldg(bp + 2)};
-        const float gz = selk<KMAX>(g_z, k), gd = selk<KMAX>(g_d, k);
+        const float pk = FRAG(k, 1), ek = FRAG(k, 2);
+        float gprob = g_alpha * FRAG(k, 3), gz = 0.f;
         float g_bc[3] = {0.f, 0.f, 0.f};
+        float col[3] = {1.0f, 1.0f, 1.0f}, gcol[3];
+        FragGeom g;
+        HfrTexTap tap; HfrPhongCtx ctx; float texel[3];
         if (k < kshade) {
-          float gcol[3];
-          {
-            float c0[KMAX], c1[KMAX], c2[KMAX];
-#pragma unroll
-            for (int kk = 0; kk < KMAX; ++kk) { c0[kk] = g_colors[3 * kk]; c1[kk] = g_colors[3 * kk + 1]; c2[kk] = g_colors[3 * kk + 2]; }
-            gcol[0] = selk<KMAX>(c0, k); gcol[1] = selk<KMAX>(c1, k); gcol[2] = selk<KMAX>(c2, k);
-          }
-          FragGeom g;
           gather_frag(f, n, face, g);
           vid[0] = g.vid[0]; vid[1] = g.vid[1]; vid[2] = g.vid[2];
-          HfrTexTap tap; HfrPhongCtx ctx; float texel[3], col[3];
           shade_fragment(f, n, g, bc, dhat, lcol, col, &tap, &ctx, texel);
+        }
+        if (P.blend == HFR_BLEND_SOFTMAX) {
+          const float wk = pk * ek;
+          const float gw = gden + gnum[0] * col[0] + gnum[1] * col[1] + gnum[2] * col[2];
+          gcol[0] = wk * gnum[0]; gcol[1] = wk * gnum[1]; gcol[2] = wk * gnum[2];
+          gprob += gw * ek;
+          const float gzinv = HFR_FDIV(gw * wk, P.gamma) + (k == kmax ? gzmax : 0.f);
+          gz = HFR_FDIV(-gzinv, P.zfar - P.znear);
+        } else {
+          gcol[0] = gnum[0]; gcol[1] = gnum[1]; gcol[2] = gnum[2];
+        }
+        if (k < kshade) {
           float gP[3], gNn[3], gtex[3];
           hfr_phong_bwd(P, dhat, lcol, texel, &ctx, gcol, gP, gNn, gtex, acc_dhat, acc_lcol);
           float gu = 0.f, gv = 0.f;
@@ -190,6 +250,7 @@ __global__ void __launch_bounds__(kBwdThreads) shade_bwd_kernel(HfrShadeBwdArgs 
         } else if (a.g_verts_ndc) {
           vid[0] = __ldg(f.faces + 3 * face); vid[1] = __ldg(f.faces + 3 * face + 1); vid[2] = __ldg(f.faces + 3 * face + 2);
         }
+        const float gd = P.blend == HFR_BLEND_HARD ? 0.f : HFR_FDIV(-gprob * pk * (1.0f - pk), P.sigma);
         if (a.g_bary) { float* o = a.g_bary + (pix * K + k) * 3; o[0] = g_bc[0]; o[1] = g_bc[1]; o[2] = g_bc[2]; }
         if (a.g_zbuf) a.g_zbuf[pix * K + k] = gz;
         if (a.g_dists) a.g_dists[pix * K + k] = gd;
@@ -206,7 +267,6 @@ __global__ void __launch_bounds__(kBwdThreads) shade_bwd_kernel(HfrShadeBwdArgs 
         }
       }
       if (!(a.g_verts_ndc || (k < kshade && (a.g_verts_view || a.g_vnormals)))) continue;
-      if (P.blend == HFR_BLEND_HARD && k >= kshade) continue;   // nothing flows through the hidden slots
       // segmented reduction: stage the components in shared memory, then per distinct face among the
       // lanes of this warp lane j sums component j over the group's lanes and issues one RED
       if (vk) {
@@ -282,16 +342,24 @@ extern "C" int hfr_shade_backward(const HfrShadeBwdArgs* a, void* stream) {
   if (int rc = check_shade(&a->f, "shade_backward")) return rc;
   if (a->f.p.N == 0) return HFR_OK;
   HFR_CHECK_ARG(a->g_image, "shade_backward: null g_image");
+  HFR_CHECK_ARG(a->f.p.blend != HFR_BLEND_SOFTMAX || a->f.image, "shade_backward: the softmax blend needs the forward image");
   HFR_CHECK_ARG(!a->g_verts_ndc || (a->verts_ndc && a->f.faces && a->f.p.F > 0 && a->f.p.V > 0),
                 "shade_backward: fused raster backward needs verts_ndc and faces");
   const HfrShadeParams& p = a->f.p;
   dim3 grid((p.W + kBwdTileW - 1) / kBwdTileW, (p.H + kBwdTileH - 1) / kBwdTileH, p.N);
   cudaStream_t st = (cudaStream_t)stream;
-  if (p.K == 1) shade_bwd_kernel<1><<<grid, kBwdThreads, 0, st>>>(*a);
-  else if (p.K == 2) shade_bwd_kernel<2><<<grid, kBwdThreads, 0, st>>>(*a);
-  else if (p.K <= 4) shade_bwd_kernel<4><<<grid, kBwdThreads, 0, st>>>(*a);
-  else if (p.K <= 8) shade_bwd_kernel<8><<<grid, kBwdThreads, 0, st>>>(*a);
-  else shade_bwd_kernel<16><<<grid, kBwdThreads, 0, st>>>(*a);
+#define HFR_LAUNCH_BWD(KM)                                                                              \
+  do {                                                                                                  \
+    const size_t sm = (size_t)(KM) * 4 * kBwdThreads * sizeof(float);                                   \
+    cudaFuncSetAttribute(shade_bwd_kernel<KM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);   \
+    shade_bwd_kernel<KM><<<grid, kBwdThreads, sm, st>>>(*a);                                            \
+  } while (0)
+  if (p.K == 1) HFR_LAUNCH_BWD(1);
+  else if (p.K == 2) HFR_LAUNCH_BWD(2);
+  else if (p.K <= 4) HFR_LAUNCH_BWD(4);
+  else if (p.K <= 8) HFR_LAUNCH_BWD(8);
+  else HFR_LAUNCH_BWD(16);
+#undef HFR_LAUNCH_BWD
   HFR_CHECK_LAUNCH("shade_backward");
   return HFR_OK;
 }

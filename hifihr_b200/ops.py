@@ -325,17 +325,17 @@ class ShadeFunction(torch.autograd.Function):
         L.call("hfr_shade_forward", a)
         ctx.params = params
         ctx.save_for_backward(p2f, zbuf, bary, dists, faces, verts_view, vnormals, faces_uvs, verts_uvs, texture,
-                              light_dir, light_color)
+                              light_dir, light_color, image)
         return image
 
     @staticmethod
     def backward(ctx, g_image):
         (p2f, zbuf, bary, dists, faces, verts_view, vnormals, faces_uvs, verts_uvs, texture, light_dir,
-         light_color) = ctx.saved_tensors
+         light_color, image) = ctx.saved_tensors
         p = ctx.params
         g_image = _cu(g_image)
         f = shade_fwd_args(p, (p2f, zbuf, bary, dists), faces, verts_view, vnormals, faces_uvs, verts_uvs, texture,
-                           light_dir, light_color, None)
+                           light_dir, light_color, image)
         g_zbuf, g_bary, g_dists = torch.empty_like(zbuf), torch.empty_like(bary), torch.empty_like(dists)
         z = lambda t: None if t is None else torch.zeros_like(t)  # noqa: E731
         g_vv, g_vn, g_tex, g_ld, g_lc = z(verts_view), z(vnormals), z(texture), z(light_dir), z(light_color)

@@ -216,7 +216,7 @@ typedef struct HfrShadeFwdArgs {
 int hfr_shade_forward(const HfrShadeFwdArgs* a, void* stream);
 
 typedef struct HfrShadeBwdArgs {
-  HfrShadeFwdArgs f;                /* forward inputs (image unused)                       */
+  HfrShadeFwdArgs f;                /* forward inputs; f.image = the forward OUTPUT (read by the softmax blend) */
   const float* g_image;             /* (N,H,W,4)                                           */
   /* dense per-fragment grads for the modular (autograd) path; any may be NULL */
   float* g_zbuf; float* g_bary; float* g_dists;
