@@ -30,7 +30,9 @@ extern "C" int hfr_device_ok(void) {
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 1024;   // one CTA per sample: enough threads to cover every vertex / basis column and to keep
+                                 // >100 independent L2 loads in flight per SM (the kernels are latency-bound)
+constexpr int kMisc = 160;        // scratch floats (32 warps x 3 partial sums + totals; tips + centre offset)
 
 struct ManoSmem {
   float* full;   // 3*NJ axis-angle
@@ -39,7 +41,7 @@ struct ManoSmem {
   float* J;      // NJ*3
   float* G;      // NJ*12
   float* A;      // NJ*12
-  float* misc;   // 64 scratch
+  float* misc;   // kMisc scratch
   float* vp;     // C3 (posed rest verts)
   float* gv;     // C3 (backward only)
 };
@@ -54,7 +56,7 @@ __device__ __forceinline__ ManoSmem carve(float* s, const HfrHandModel& m, bool 
   o.J = s; s += up4(3 * NJ);
   o.G = s; s += 12 * NJ;
   o.A = s; s += 12 * NJ;
-  o.misc = s; s += 64;
+  o.misc = s; s += kMisc;
   o.vp = s; s += m.C3;
   o.gv = bwd ? s : nullptr;
   return o;
@@ -62,7 +64,7 @@ __device__ __forceinline__ ManoSmem carve(float* s, const HfrHandModel& m, bool 
 
 static size_t mano_smem_bytes(const HfrHandModel& m, bool bwd) {
   auto up4 = [](int x) { return (x + 3) & ~3; };
-  size_t f = up4(3 * m.NJ) + up4(9 * m.NJ) + up4(m.NS + 9 * (m.NJ - 1)) + up4(3 * m.NJ) + 24 * m.NJ + 64;
+  size_t f = up4(3 * m.NJ) + up4(9 * m.NJ) + up4(m.NS + 9 * (m.NJ - 1)) + up4(3 * m.NJ) + 24 * m.NJ + kMisc;
   f += (size_t)m.C3 * (bwd ? 2 : 1);
   return f * sizeof(float);
 }
@@ -233,7 +235,7 @@ __global__ void __launch_bounds__(kThreads) mano_bwd_kernel(HfrHandModel m, HfrM
   float* gR = gJ + 3 * NJ;        // NJ*9
   float* gcoef = gR + 9 * NJ;     // NK
   float* gfull = gcoef + ((NK + 3) & ~3);  // 3*NJ
-  float* red = s.misc;            // 8 warps * 3 partials, then [24..26] = total
+  float* red = s.misc;            // nwarps * 3 partials, then [3*nwarps ..] = total
   // ---- load upstream grads, fold tips / centre ------------------------------------------
   const float* gv_in = a.g_verts + (size_t)b * V * 3;
   float sx = 0.f, sy = 0.f, sz = 0.f;
@@ -258,7 +260,7 @@ __global__ void __launch_bounds__(kThreads) mano_bwd_kernel(HfrHandModel m, HfrM
   if (tid < 3) {
     float t = 0.f;
     for (int w = 0; w < nwarps; ++w) t += red[w * 3 + tid];
-    red[24 + tid] = t;
+    red[3 * nwarps + tid] = t;
   }
   __syncthreads();
   // gGt: translation-column grads that bypass A (chain joint outputs, centre)
@@ -276,39 +278,56 @@ __global__ void __launch_bounds__(kThreads) mano_bwd_kernel(HfrHandModel m, HfrM
       }
     }
     if (a.trans) {
-      if (a.g_trans) for (int c = 0; c < 3; ++c) a.g_trans[(size_t)b * 3 + c] = red[24 + c];
+      if (a.g_trans) for (int c = 0; c < 3; ++c) a.g_trans[(size_t)b * 3 + c] = red[3 * nwarps + c];
     } else if (m.center_joint >= 0) {
       const int src = m.joint_order[m.center_joint];
       for (int c = 0; c < 3; ++c) {
-        if (src < NJ) gGt[3 * src + c] -= red[24 + c];
-        else s.gv[3 * m.tip_verts[src - NJ] + c] -= red[24 + c];
+        if (src < NJ) gGt[3 * src + c] -= red[3 * nwarps + c];
+        else s.gv[3 * m.tip_verts[src - NJ] + c] -= red[3 * nwarps + c];
       }
     }
   }
   __syncthreads();
-  // ---- gA[j] = sum_v w_vj * g_v (x) [vp;1]   (warp per joint, lanes stride over vertices)
-  for (int j = warp; j < NJ; j += nwarps) {
-    float acc[12];
+  // ---- gA[j] = sum_v w_vj * g_v (x) [vp;1]: a thread per vertex keeps its <= NW influences in
+  //      registers; per joint the 12 components are summed inside the warp (joints no lane touches are
+  //      skipped) and one lane adds them to the shared accumulator
+  for (int v0 = warp * 32; v0 < V; v0 += kThreads) {
+    const int v = v0 + lane;
+    int ji[8];
+    float jw[8];
 #pragma unroll
-    for (int e = 0; e < 12; ++e) acc[e] = 0.0f;
-    for (int v = lane; v < V; v += 32) {
-      float w = 0.0f;
-      for (int i = 0; i < m.NW; ++i)
-        if (m.skin_idx[i * V + v] == j) w += m.skin_w[i * V + v];
-      if (w != 0.0f) {
-        const float x = s.vp[3 * v], y = s.vp[3 * v + 1], z = s.vp[3 * v + 2];
+    for (int i = 0; i < 8; ++i) { ji[i] = -1; jw[i] = 0.0f; }
+    float x = 0.f, y = 0.f, z = 0.f, g0 = 0.f, g1 = 0.f, g2 = 0.f;
+    unsigned jmask = 0;
+    if (v < V) {
 #pragma unroll
-        for (int r = 0; r < 3; ++r) {
-          const float g = w * s.gv[3 * v + r];
-          acc[r * 4 + 0] += g * x; acc[r * 4 + 1] += g * y; acc[r * 4 + 2] += g * z; acc[r * 4 + 3] += g;
+      for (int i = 0; i < 8; ++i) {
+        if (i < m.NW) {
+          jw[i] = m.skin_w[i * V + v];
+          ji[i] = jw[i] != 0.0f ? m.skin_idx[i * V + v] : -1;
+          if (ji[i] >= 0) jmask |= 1u << ji[i];
         }
       }
+      x = s.vp[3 * v]; y = s.vp[3 * v + 1]; z = s.vp[3 * v + 2];
+      g0 = s.gv[3 * v]; g1 = s.gv[3 * v + 1]; g2 = s.gv[3 * v + 2];
     }
 #pragma unroll
-    for (int e = 0; e < 12; ++e) acc[e] = warp_sum(acc[e]);
-    if (lane == 0) {
+    for (int o = 16; o > 0; o >>= 1) jmask |= __shfl_xor_sync(0xffffffffu, jmask, o);
+    while (jmask) {
+      const int j = __ffs(jmask) - 1;
+      jmask &= jmask - 1;
+      float w = 0.0f;
 #pragma unroll
-      for (int e = 0; e < 12; ++e) gA[12 * j + e] = acc[e];
+      for (int i = 0; i < 8; ++i) w += (ji[i] == j) ? jw[i] : 0.0f;
+      const float gr[3] = {w * g0, w * g1, w * g2};
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const float t0 = warp_sum(gr[r] * x), t1 = warp_sum(gr[r] * y), t2 = warp_sum(gr[r] * z), t3 = warp_sum(gr[r]);
+        if (lane == 0) {
+          atomicAdd(&gA[12 * j + r * 4 + 0], t0); atomicAdd(&gA[12 * j + r * 4 + 1], t1);
+          atomicAdd(&gA[12 * j + r * 4 + 2], t2); atomicAdd(&gA[12 * j + r * 4 + 3], t3);
+        }
+      }
     }
   }
   __syncthreads();
@@ -330,7 +349,8 @@ __global__ void __launch_bounds__(kThreads) mano_bwd_kernel(HfrHandModel m, HfrM
     for (int k = warp; k < NK; k += nwarps) {
       float acc = 0.0f;
       const float4* row = dirs4 + (size_t)k * C4;
-      for (int c4 = lane; c4 < C4; c4 += 32) {
+#pragma unroll 8
+      for (int c4 = lane; c4 < C4; c4 += 32) {   // independent 128-bit loads, 8 in flight per lane
         const float4 d = __ldg(row + c4);
         const float4 g = gv4[c4];
         acc += d.x * g.x + d.y * g.y + d.z * g.z + d.w * g.w;
