@@ -30,6 +30,7 @@ constexpr int kChunk = 32 * kRasterThreads;  // faces handled per coarse pass (o
 struct RasterSmem {
   __align__(16) float rec[kListCap * kRecFloats];
   int wsum[kRasterThreads / 32];
+  uint16_t order[kListCap];   // record indices sorted front to back (by the faces' nearest vertex)
 };
 
 __device__ __forceinline__ uint32_t pack_tile_range(int txmin, int txmax, int tymin, int tymax) {
@@ -46,12 +47,17 @@ struct TopK {
     for (int i = 0; i < KMAX; ++i) { z[i] = INFINITY; f[i] = -1; }
   }
   __device__ __forceinline__ float worst() const { return z[KMAX - 1]; }
-  // replace the worst slot and bubble towards the front; strict < keeps earlier faces first on ties
+  // does (pz, face) beat the current K-th entry in the reference's (z, face index) order?
+  __device__ __forceinline__ bool beats_worst(float pz, int face) const {
+    return pz < z[KMAX - 1] || (pz == z[KMAX - 1] && face < f[KMAX - 1]);
+  }
+  // replace the worst slot and bubble towards the front, ordered by (z, face index): faces may arrive in
+  // any order (the tile list is depth-sorted), ties still resolve to the smaller packed face index
   __device__ __forceinline__ void insert(float pz, int face) {
     z[KMAX - 1] = pz; f[KMAX - 1] = face;
 #pragma unroll
     for (int i = KMAX - 1; i > 0; --i) {
-      if (z[i] < z[i - 1]) {
+      if (z[i] < z[i - 1] || (z[i] == z[i - 1] && f[i] < f[i - 1])) {
         const float tz = z[i]; z[i] = z[i - 1]; z[i - 1] = tz;
         const int tf = f[i]; f[i] = f[i - 1]; f[i - 1] = tf;
       }
@@ -64,13 +70,15 @@ struct TopK {
 //
 //   coarse: thread t owns a CONTIGUOUS chunk of faces and keeps one hit bit per face from a
 //           single pass over the packed tile ranges; one block-wide scan of the hit counts then
-//           gives every thread its slot in the tile list, which therefore stays sorted by face
-//           index (z-ties resolve to the smaller index with a strict `<`, the CPU reference's
-//           (z, face) order).  A tile no face touches leaves after that scan.
-//   stage:  listed faces are gathered once per tile into 64-byte shared records.
-//   fine:   each warp culls the list against its own 8x4 block (one ballot per 32 faces), then
-//           all lanes walk the survivors together (broadcast LDS.128); a lane skips a face whose
-//           nearest vertex is not in front of its current K-th depth before doing any division.
+//           gives every thread its slot in the tile list.  A tile no face touches leaves after
+//           that scan.
+//   stage:  listed faces are gathered once per tile into 64-byte shared records and ranked front
+//           to back by their nearest vertex (rank sort in shared memory).
+//   fine:   each warp culls the depth-ordered list against its own 8x4 block (one ballot per 32
+//           faces), then all lanes walk the survivors together (broadcast LDS.128); a lane skips
+//           a face whose nearest vertex is not in front of its current K-th depth before doing
+//           any division, and the warp stops as soon as that holds for all its pixels.  The top-K
+//           is ordered by (z, packed face index), the CPU reference's order, ties included.
 template <int KMAX>
 __device__ __forceinline__ void raster_tile(const HfrRasterArgs& a, const uint32_t* __restrict__ tile_ranges,
                                             RasterSmem& sm, int n, int tx, int ty, float xf, float yf,
@@ -150,33 +158,57 @@ __device__ __forceinline__ void raster_tile(const HfrRasterArgs& a, const uint32
         }
       }
       __syncthreads();
+      // depth order: rank of every record by (shrunk zmin, list position); faces nearest to the camera are
+      // visited first, so a pixel's K-th depth drops quickly and most faces behind it fail the zmin test
+      if (tid < bcnt) {
+        int rank = tid;
+        if (zcull) {
+          const float zi = sm.rec[tid * kRecFloats + 14];
+          rank = 0;
+          for (int j = 0; j < bcnt; ++j) {
+            const float zj = sm.rec[j * kRecFloats + 14];
+            rank += (zj < zi || (zj == zi && j < tid)) ? 1 : 0;
+          }
+        }
+        sm.order[rank] = (uint16_t)tid;
+      }
+      __syncthreads();
       if (warp_active) {
         for (int b0 = 0; b0 < bcnt; b0 += 32) {
           const int i = b0 + lane;
+          int ri = 0;
           bool ok = false;
           if (i < bcnt) {
-            const float4 q2 = *reinterpret_cast<const float4*>(sm.rec + i * kRecFloats + 8);
-            const float ymax = sm.rec[i * kRecFloats + 12];
+            ri = sm.order[i];
+            const float4 q2 = *reinterpret_cast<const float4*>(sm.rec + ri * kRecFloats + 8);
+            const float ymax = sm.rec[ri * kRecFloats + 12];
             ok = !(q2.z < wx_lo || q2.y > wx_hi || ymax < wy_lo || q2.w > wy_hi);
+          }
+          if (zcull) {
+            // every remaining face has zmin >= this chunk's first: stop once no pixel of the warp can take one
+            const float zfirst = sm.rec[__shfl_sync(0xffffffffu, ri, 0) * kRecFloats + 14];
+            if (__all_sync(0xffffffffu, !pix_active || !(zfirst < top.worst()))) break;
           }
           unsigned m = __ballot_sync(0xffffffffu, ok);
           while (m) {
             const int j = __ffs(m) - 1;
             m &= m - 1;
-            const float4* r4 = reinterpret_cast<const float4*>(sm.rec + (b0 + j) * kRecFloats);
+            const int rj = __shfl_sync(0xffffffffu, ri, j);
+            const float4* r4 = reinterpret_cast<const float4*>(sm.rec + rj * kRecFloats);
             const float4 q2 = r4[2], q3 = r4[3];
             bool want = pix_active && !(xf < q2.y || xf > q2.z || yf < q2.w || yf > q3.x);
             if (zcull) want = want && (q3.z < top.worst());
             if (want) {
               const float4 q0 = r4[0], q1 = r4[1];
               const float v[9] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x};
+              const int face = __float_as_int(q3.w);
               float pz, bc[3];
               bool inside;
               if (hfr_raster_bary(xf, yf, v, q3.y, pc, clip, &pz, bc, &inside)) {
-                if (pz < top.worst()) {
+                if (top.beats_worst(pz, face)) {
                   bool keep = inside;
                   if (!keep) keep = hfr_tri_dist2(xf, yf, v) < blur;
-                  if (keep) top.insert(pz, __float_as_int(q3.w));
+                  if (keep) top.insert(pz, face);
                 }
               }
             }
