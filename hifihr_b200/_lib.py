@@ -12,7 +12,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhifihr_b200.so")
+LIB_PATH = os.environ.get("HFR_B200_LIB") or os.path.join(_HERE, "libhifihr_b200.so")   # env: tuning builds only
 
 vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 

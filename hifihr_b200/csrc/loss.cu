@@ -239,7 +239,10 @@ __global__ void __launch_bounds__(kLossThreads, 3) loss_fwd_kernel(HfrLossArgs a
   }
 }
 
-__global__ void __launch_bounds__(kLossThreads, 3) loss_bwd_kernel(HfrLossBwdArgs b) {
+#ifndef HFR_LOSSB_MINB
+#define HFR_LOSSB_MINB 5
+#endif
+__global__ void __launch_bounds__(kLossThreads, HFR_LOSSB_MINB) loss_bwd_kernel(HfrLossBwdArgs b) {
   const HfrLossArgs& a = b.f;
   __shared__ __align__(16) float sd[3][kLH][kXP];
   __shared__ __align__(16) float hb[3][kLH][kHP];

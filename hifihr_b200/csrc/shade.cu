@@ -36,8 +36,11 @@ __global__ void __launch_bounds__(256) shade_fwd_kernel(HfrShadeFwdArgs a) {
 }
 
 // Fused rasterize + shade forward: Fragments and the RGBA image leave the SM in the same pass.
+#ifndef HFR_RASTER_MINB
+#define HFR_RASTER_MINB 4
+#endif
 template <int KMAX>
-__global__ void __launch_bounds__(kRasterThreads) raster_shade_fwd_kernel(HfrRasterArgs r, HfrShadeFwdArgs s,
+__global__ void __launch_bounds__(kRasterThreads, (KMAX <= 4 ? HFR_RASTER_MINB : 1)) raster_shade_fwd_kernel(HfrRasterArgs r, HfrShadeFwdArgs s,
                                                                           const uint32_t* __restrict__ ranges) {
   __shared__ RasterSmem sm;
   const PixelCtx c = make_pixel_ctx(r.H, r.W);

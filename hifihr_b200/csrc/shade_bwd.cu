@@ -36,8 +36,11 @@ __device__ __forceinline__ int selk_i(const int (&a)[KMAX], int k) {
   return r;
 }
 
+#ifndef HFR_BWD_MINB
+#define HFR_BWD_MINB 4
+#endif
 template <int KMAX>
-__global__ void __launch_bounds__(kBwdThreads, 2) shade_bwd_kernel(HfrShadeBwdArgs a) {
+__global__ void __launch_bounds__(kBwdThreads, (KMAX <= 4 ? HFR_BWD_MINB : 1)) shade_bwd_kernel(HfrShadeBwdArgs a) {
   __shared__ float s_light[kBwdThreads / 32][6];
   // per-warp staging of the 27 per-fragment components, pitch 33: lane L writes column L (bank j+L),
   // lane j later sums row j over the lanes of one face group (bank j+m) - both conflict-free
