@@ -12,7 +12,7 @@
 #include "common.cuh"
 
 namespace {
-constexpr int kThreads = 256;
+constexpr int kThreads = 1024;   // one CTA per sample; every per-vertex loop runs in a single round (latency-bound gathers)
 
 __device__ __forceinline__ void cross3(const float* u, const float* w, float* o) {
   o[0] = u[1] * w[2] - u[2] * w[1];
@@ -134,8 +134,8 @@ __global__ void __launch_bounds__(kThreads) geom_bwd_kernel(HfrTopology t, HfrGe
   float* s_j = s_g + 3 * V;
   float* s_pos = s_j + 3 * (t.NJR > 0 ? t.NJR : 1);
   float* s_root = s_pos + 3 * (t.NOUT > 0 ? t.NOUT : 1);
-  float* s_red = s_root + 4;             // 8 warps * 3 + 3
-  float* s_gj = s_red + 28;              // NJR*3 grads wrt regressed joints
+  float* s_red = s_root + 4;             // kThreads/32 warps * 3 + 3
+  float* s_gj = s_red + 3 * (kThreads / 32) + 4;              // NJR*3 grads wrt regressed joints
   geom_stage(t, a.B, b, a.root_out, a.verts, a.root_xyz, s_v, s_view, s_j, s_pos, s_root);
   const size_t base = (size_t)b * V * 3;
   // 1. raw-normal grads
@@ -268,7 +268,7 @@ extern "C" int hfr_geom_backward(const HfrTopology* t, const HfrGeomBwdArgs* a, 
   if (int rc = check_topo(t, a->root_out >= 0)) return rc;
   HFR_CHECK_ARG(!a->g_verts_ndc || (a->focal && a->prp), "geom_backward: g_verts_ndc needs focal/prp");
   if (a->B == 0) return HFR_OK;
-  const size_t smem = (size_t)(12 * t->V + 6 * (t->NJR > 0 ? t->NJR : 1) + 3 * (t->NOUT > 0 ? t->NOUT : 1) + 40) * sizeof(float);
+  const size_t smem = (size_t)(12 * t->V + 6 * (t->NJR > 0 ? t->NJR : 1) + 3 * (t->NOUT > 0 ? t->NOUT : 1) + 16 + 3 * (kThreads / 32)) * sizeof(float);
   HFR_CHECK_ARG(smem <= 227 * 1024, "geom_backward: mesh too large for shared memory");
   if (smem > 48 * 1024) cudaFuncSetAttribute(geom_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   geom_bwd_kernel<<<a->B, kThreads, smem, (cudaStream_t)stream>>>(*t, *a);

@@ -9,42 +9,77 @@
 
 namespace hfr {
 
-// One thread per packed face: conservative range of 16x16 tiles its dilated bbox can touch.
-__global__ void __launch_bounds__(256) raster_setup_kernel(HfrRasterArgs a, uint32_t* __restrict__ ranges) {
+// One thread per packed face: conservative range of 16x16 tiles its dilated bbox can touch, and the
+// union of those ranges per mesh (4 min-reduced words per mesh, the two upper bounds stored as 255 - x,
+// initialised to 0xff by a memset), so that tiles outside a mesh's footprint skip the coarse scan.
+__global__ void __launch_bounds__(256) raster_setup_kernel(HfrRasterArgs a, uint32_t* __restrict__ ranges,
+                                                           uint32_t* __restrict__ mesh_box) {
   const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= a.Ftot) return;
-  float v[9];
-#pragma unroll
-  for (int e = 0; e < 9; ++e) v[e] = __ldg(a.face_verts + f * 9 + e);
+  const bool live = f < a.Ftot;
   uint32_t out = kEmptyRange;
-  if (hfr_face_valid(v, a.cull_backfaces)) {
-    const float r = sqrtf(a.blur_radius);
-    const float xmin = hfr_min3(v[0], v[3], v[6]) - r, xmax = hfr_max3(v[0], v[3], v[6]) + r;
-    const float ymin = hfr_min3(v[1], v[4], v[7]) - r, ymax = hfr_max3(v[1], v[4], v[7]) + r;
-    // invert hfr_pix_to_ndc: i = ((x + off) * S1 - off) / range ; pixel column = S1 - 1 - i
-    const float rx = a.W > a.H ? 2.0f * a.W / a.H : 2.0f, ry = a.H > a.W ? 2.0f * a.H / a.W : 2.0f;
-    const float ox = 0.5f * rx, oy = 0.5f * ry;
-    const float ix_hi = ((xmax + ox) * a.W - ox) / rx, ix_lo = ((xmin + ox) * a.W - ox) / rx;
-    const float iy_hi = ((ymax + oy) * a.H - oy) / ry, iy_lo = ((ymin + oy) * a.H - oy) / ry;
-    // one extra pixel of slack on each side absorbs the rounding of this inverse map
-    float cx0 = floorf((float)(a.W - 1) - ix_hi) - 1.0f, cx1 = ceilf((float)(a.W - 1) - ix_lo) + 1.0f;
-    float cy0 = floorf((float)(a.H - 1) - iy_hi) - 1.0f, cy1 = ceilf((float)(a.H - 1) - iy_lo) + 1.0f;
-    if (cx1 >= 0.0f && cy1 >= 0.0f && cx0 <= (float)(a.W - 1) && cy0 <= (float)(a.H - 1) && cx0 == cx0 &&
-        cx1 == cx1 && cy0 == cy0 && cy1 == cy1) {
-      const int x0 = (int)fmaxf(cx0, 0.0f), x1 = (int)fminf(cx1, (float)(a.W - 1));
-      const int y0 = (int)fmaxf(cy0, 0.0f), y1 = (int)fminf(cy1, (float)(a.H - 1));
-      out = pack_tile_range(x0 / kTileW, x1 / kTileW, y0 / kTileH, y1 / kTileH);
+  int tx0 = 255, tx1 = 0, ty0 = 255, ty1 = 0;
+  if (live) {
+    float v[9];
+#pragma unroll
+    for (int e = 0; e < 9; ++e) v[e] = __ldg(a.face_verts + f * 9 + e);
+    if (hfr_face_valid(v, a.cull_backfaces)) {
+      const float r = sqrtf(a.blur_radius);
+      const float xmin = hfr_min3(v[0], v[3], v[6]) - r, xmax = hfr_max3(v[0], v[3], v[6]) + r;
+      const float ymin = hfr_min3(v[1], v[4], v[7]) - r, ymax = hfr_max3(v[1], v[4], v[7]) + r;
+      // invert hfr_pix_to_ndc: i = ((x + off) * S1 - off) / range ; pixel column = S1 - 1 - i
+      const float rx = a.W > a.H ? 2.0f * a.W / a.H : 2.0f, ry = a.H > a.W ? 2.0f * a.H / a.W : 2.0f;
+      const float ox = 0.5f * rx, oy = 0.5f * ry;
+      const float ix_hi = ((xmax + ox) * a.W - ox) / rx, ix_lo = ((xmin + ox) * a.W - ox) / rx;
+      const float iy_hi = ((ymax + oy) * a.H - oy) / ry, iy_lo = ((ymin + oy) * a.H - oy) / ry;
+      // one extra pixel of slack on each side absorbs the rounding of this inverse map
+      float cx0 = floorf((float)(a.W - 1) - ix_hi) - 1.0f, cx1 = ceilf((float)(a.W - 1) - ix_lo) + 1.0f;
+      float cy0 = floorf((float)(a.H - 1) - iy_hi) - 1.0f, cy1 = ceilf((float)(a.H - 1) - iy_lo) + 1.0f;
+      if (cx1 >= 0.0f && cy1 >= 0.0f && cx0 <= (float)(a.W - 1) && cy0 <= (float)(a.H - 1) && cx0 == cx0 &&
+          cx1 == cx1 && cy0 == cy0 && cy1 == cy1) {
+        const int x0 = (int)fmaxf(cx0, 0.0f), x1 = (int)fminf(cx1, (float)(a.W - 1));
+        const int y0 = (int)fmaxf(cy0, 0.0f), y1 = (int)fminf(cy1, (float)(a.H - 1));
+        tx0 = x0 / kTileW; tx1 = x1 / kTileW; ty0 = y0 / kTileH; ty1 = y1 / kTileH;
+        out = pack_tile_range(tx0, tx1, ty0, ty1);
+      }
     }
+    ranges[f] = out;
   }
-  ranges[f] = out;
+  if (mesh_box == nullptr) return;
+  // mesh of this face: last n with mesh_first[n] <= f (meshes are packed in order)
+  int n = -1;
+  if (live && out != kEmptyRange) {
+    int lo = 0, hi = a.N - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (__ldg(a.mesh_first + mid) <= f) lo = mid; else hi = mid - 1;
+    }
+    n = lo;
+    if (f >= __ldg(a.mesh_first + n) + __ldg(a.mesh_nfaces + n)) n = -1;   // a gap between meshes
+  }
+  const int n0 = __shfl_sync(0xffffffffu, n, 0);
+  if (__all_sync(0xffffffffu, n == n0 || n < 0)) {   // the common case: one mesh per warp -> 4 atomics per warp
+    const unsigned m0 = __reduce_min_sync(0xffffffffu, (unsigned)(n < 0 ? 255 : tx0));
+    const unsigned m1 = __reduce_min_sync(0xffffffffu, (unsigned)(n < 0 ? 255 : 255 - tx1));
+    const unsigned m2 = __reduce_min_sync(0xffffffffu, (unsigned)(n < 0 ? 255 : ty0));
+    const unsigned m3 = __reduce_min_sync(0xffffffffu, (unsigned)(n < 0 ? 255 : 255 - ty1));
+    const int nn = __reduce_max_sync(0xffffffffu, n);
+    if ((threadIdx.x & 31) == 0 && nn >= 0) {
+      atomicMin(mesh_box + 4 * nn, m0); atomicMin(mesh_box + 4 * nn + 1, m1);
+      atomicMin(mesh_box + 4 * nn + 2, m2); atomicMin(mesh_box + 4 * nn + 3, m3);
+    }
+  } else if (n >= 0) {
+    atomicMin(mesh_box + 4 * n, (unsigned)tx0); atomicMin(mesh_box + 4 * n + 1, (unsigned)(255 - tx1));
+    atomicMin(mesh_box + 4 * n + 2, (unsigned)ty0); atomicMin(mesh_box + 4 * n + 3, (unsigned)(255 - ty1));
+  }
 }
 
 template <int KMAX>
-__global__ void __launch_bounds__(kRasterThreads) raster_fwd_kernel(HfrRasterArgs a, const uint32_t* __restrict__ ranges) {
+__global__ void __launch_bounds__(kRasterThreads) raster_fwd_kernel(HfrRasterArgs a, const uint32_t* __restrict__ ranges,
+                                                                    const uint32_t* __restrict__ mesh_box) {
   __shared__ RasterSmem sm;
   const PixelCtx c = make_pixel_ctx(a.H, a.W);
   TopK<KMAX> top;
-  raster_tile<KMAX>(a, ranges, sm, c.n, c.tx, c.ty, c.xf, c.yf, c.pix_active, c.warp_active, c.wx_lo, c.wx_hi,
+  raster_tile<KMAX>(a, ranges, mesh_box, sm, c.n, c.tx, c.ty, c.xf, c.yf, c.pix_active, c.warp_active, c.wx_lo, c.wx_hi,
                     c.wy_lo, c.wy_hi, top);
   if (c.pix_active) {
     int64_t id[KMAX];
@@ -93,9 +128,17 @@ int check_raster(const HfrRasterArgs* a, const char* who) {
   return HFR_OK;
 }
 
+// workspace layout: [Ftot + 64 words: packed tile range per face][4 words per mesh: tile box], the box only
+// when N <= Ftot (hfr_raster_workspace_bytes sizes the buffer for that)
+const uint32_t* raster_mesh_box(const HfrRasterArgs& a) {
+  return (a.N <= a.Ftot) ? reinterpret_cast<const uint32_t*>(a.workspace) + ((a.Ftot + 64 + 3) & ~(int64_t)3) : nullptr;   // 16-byte aligned
+}
+
 int launch_raster_setup(const HfrRasterArgs& a, uint32_t* ranges, cudaStream_t s) {
   if (a.Ftot > 0) {
-    raster_setup_kernel<<<(unsigned)((a.Ftot + 255) / 256), 256, 0, s>>>(a, ranges);
+    uint32_t* box = const_cast<uint32_t*>(raster_mesh_box(a));
+    if (box) cudaMemsetAsync(box, 0xff, (size_t)a.N * 4 * sizeof(uint32_t), s);
+    raster_setup_kernel<<<(unsigned)((a.Ftot + 255) / 256), 256, 0, s>>>(a, ranges, box);
     HFR_CHECK_LAUNCH("raster_setup");
   }
   return HFR_OK;
@@ -104,12 +147,12 @@ int launch_raster_setup(const HfrRasterArgs& a, uint32_t* ranges, cudaStream_t s
 template <int KMAX>
 static void launch_fwd(const HfrRasterArgs& a, const uint32_t* ranges, cudaStream_t s) {
   dim3 grid((a.W + kTileW - 1) / kTileW, (a.H + kTileH - 1) / kTileH, a.N);
-  raster_fwd_kernel<KMAX><<<grid, kRasterThreads, 0, s>>>(a, ranges);
+  raster_fwd_kernel<KMAX><<<grid, kRasterThreads, 0, s>>>(a, ranges, raster_mesh_box(a));
 }
 
 }  // namespace hfr
 
-extern "C" int64_t hfr_raster_workspace_bytes(int64_t Ftot) { return (Ftot + 64) * 4; }
+extern "C" int64_t hfr_raster_workspace_bytes(int64_t Ftot) { return (5 * Ftot + 80) * 4; }
 
 extern "C" int hfr_raster_forward(const HfrRasterArgs* a, void* stream) {
   using namespace hfr;

@@ -81,7 +81,7 @@ struct TopK {
 //           is ordered by (z, packed face index), the CPU reference's order, ties included.
 template <int KMAX>
 __device__ __forceinline__ void raster_tile(const HfrRasterArgs& a, const uint32_t* __restrict__ tile_ranges,
-                                            RasterSmem& sm, int n, int tx, int ty, float xf, float yf,
+                                            const uint32_t* __restrict__ mesh_box, RasterSmem& sm, int n, int tx, int ty, float xf, float yf,
                                             bool pix_active, bool warp_active, float wx_lo, float wx_hi, float wy_lo, float wy_hi,
                                             TopK<KMAX>& top) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -93,6 +93,10 @@ __device__ __forceinline__ void raster_tile(const HfrRasterArgs& a, const uint32
   // barycentrics (blur > 0 without clipping): only then the zmin early-out is not exact
   const bool zcull = clip || !(blur > 0.0f);
   top.init();
+  if (mesh_box) {   // tile outside the mesh's footprint (union of its faces' tile ranges): nothing to do
+    const uint4 bx = __ldg(reinterpret_cast<const uint4*>(mesh_box) + n);
+    if (tx < (int)bx.x || tx > 255 - (int)bx.y || ty < (int)bx.z || ty > 255 - (int)bx.w) return;
+  }
 
   for (int cbase = 0; cbase < nf; cbase += kChunk) {
     const int cn = min(nf - cbase, kChunk);
@@ -311,6 +315,7 @@ __device__ __forceinline__ PixelCtx make_pixel_ctx(int H, int W) {
 
 // host helpers defined in raster.cu
 int launch_raster_setup(const HfrRasterArgs& a, uint32_t* ranges, cudaStream_t s);
+const uint32_t* raster_mesh_box(const HfrRasterArgs& a);
 int check_raster(const HfrRasterArgs* a, const char* who);
 
 }  // namespace hfr

@@ -41,11 +41,12 @@ __global__ void __launch_bounds__(256) shade_fwd_kernel(HfrShadeFwdArgs a) {
 #endif
 template <int KMAX>
 __global__ void __launch_bounds__(kRasterThreads, (KMAX <= 4 ? HFR_RASTER_MINB : 1)) raster_shade_fwd_kernel(HfrRasterArgs r, HfrShadeFwdArgs s,
-                                                                          const uint32_t* __restrict__ ranges) {
+                                                                          const uint32_t* __restrict__ ranges,
+                                                                          const uint32_t* __restrict__ mesh_box) {
   __shared__ RasterSmem sm;
   const PixelCtx c = make_pixel_ctx(r.H, r.W);
   TopK<KMAX> top;
-  raster_tile<KMAX>(r, ranges, sm, c.n, c.tx, c.ty, c.xf, c.yf, c.pix_active, c.warp_active, c.wx_lo, c.wx_hi,
+  raster_tile<KMAX>(r, ranges, mesh_box, sm, c.n, c.tx, c.ty, c.xf, c.yf, c.pix_active, c.warp_active, c.wx_lo, c.wx_hi,
                     c.wy_lo, c.wy_hi, top);
   if (c.pix_active) {
     int64_t id[KMAX];
@@ -114,7 +115,7 @@ extern "C" int hfr_raster_shade_forward(const HfrRasterShadeArgs* a, void* strea
   uint32_t* ranges = reinterpret_cast<uint32_t*>(a->r.workspace);
   if (int rc = launch_raster_setup(a->r, ranges, st)) return rc;
   dim3 grid((a->r.W + kTileW - 1) / kTileW, (a->r.H + kTileH - 1) / kTileH, a->r.N);
-#define CALL(KM) raster_shade_fwd_kernel<KM><<<grid, kRasterThreads, 0, st>>>(a->r, s, ranges)
+#define CALL(KM) raster_shade_fwd_kernel<KM><<<grid, kRasterThreads, 0, st>>>(a->r, s, ranges, raster_mesh_box(a->r))
   HFR_DISPATCH_K(a->r.K, CALL);
 #undef CALL
   HFR_CHECK_LAUNCH("raster_shade_forward");
