@@ -36,6 +36,11 @@ __global__ void __launch_bounds__(256) shade_fwd_kernel(HfrShadeFwdArgs a) {
 }
 
 // Fused rasterize + shade forward: Fragments and the RGBA image leave the SM in the same pass.
+//
+// Epilogue: ONE runtime loop over the K winners of a pixel (a single copy of the exact fragment math,
+// the gathers, the texture fetch and the Phong code - the kernel stays inside the instruction cache).
+// The blends need no second pass: winners are sorted by depth, so the softmax reference depth
+// z_max belongs to slot 0 and weights accumulate on the fly.
 #ifndef HFR_RASTER_MINB
 #define HFR_RASTER_MINB 4
 #endif
@@ -48,16 +53,110 @@ __global__ void __launch_bounds__(kRasterThreads, (KMAX <= 4 ? HFR_RASTER_MINB :
   TopK<KMAX> top;
   raster_tile<KMAX>(r, ranges, mesh_box, sm, c.n, c.tx, c.ty, c.xf, c.yf, c.pix_active, c.warp_active, c.wx_lo, c.wx_hi,
                     c.wy_lo, c.wy_hi, top);
-  if (c.pix_active) {
-    int64_t id[KMAX];
-    float z[KMAX], d[KMAX], b[KMAX * 3];
-    compute_fragments<KMAX>(r, c.xf, c.yf, top, id, z, d, b);
-    const size_t pix = ((size_t)c.n * r.H + c.yi) * r.W + c.xi;
-    store_fragments<KMAX>(r, pix, id, z, d, b);
-    float rgba[4];
-    shade_pixel<KMAX>(s, c.n, id, z, d, b, rgba);
-    *reinterpret_cast<float4*>(s.image + pix * 4) = make_float4(rgba[0], rgba[1], rgba[2], rgba[3]);
+  if (!c.pix_active) return;
+  const HfrShadeParams& P = s.p;
+  const int K = r.K;
+  const size_t pix = ((size_t)c.n * r.H + c.yi) * r.W + c.xi;
+  const bool ones = P.blend == HFR_BLEND_SIGMOID_ALPHA;
+  int64_t id[KMAX];
+  float z[KMAX], d[KMAX];
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) { id[k] = -1; z[k] = -1.0f; d[k] = -1.0f; }
+  float* __restrict__ ba = r.bary + pix * K * 3;
+  float rgba[4] = {ones ? 1.0f : P.background[0], ones ? 1.0f : P.background[1], ones ? 1.0f : P.background[2], 0.0f};
+  if (top.f[0] < 0) {
+    // empty pixel (winners are sorted, slot 0 empty = all empty): -1 fill, background colour, alpha 0
+    if (K == KMAX && (KMAX % 4) == 0) {
+#pragma unroll
+      for (int e = 0; e < KMAX * 3; e += 4) st_cs_f4(ba + e, -1.0f, -1.0f, -1.0f, -1.0f);
+    } else {
+      for (int e = 0; e < K * 3; ++e) ba[e] = -1.0f;
+    }
+  } else {
+    const bool phong = P.shade == HFR_SHADE_PHONG_UV;
+    const int kshade = phong ? (P.blend == HFR_BLEND_SOFTMAX ? K : 1) : 0;
+    float dhat[3] = {0.f, 0.f, 0.f}, dlen, lcol[3] = {0.f, 0.f, 0.f};
+    if (phong) {
+      light_dir_hat(s, c.n, dhat, &dlen);
+      lcol[0] = __ldg(s.light_color + 3 * c.n); lcol[1] = __ldg(s.light_color + 3 * c.n + 1); lcol[2] = __ldg(s.light_color + 3 * c.n + 2);
+    }
+    const float eps = 1e-10f, zr = P.zfar - P.znear;
+    const float zmax = fmaxf((P.zfar - top.z[0]) / zr, eps);   // slot 0 is the nearest winner
+    float prod = 1.0f, wsum = 0.0f, acc[3] = {0.f, 0.f, 0.f}, col0[3] = {1.0f, 1.0f, 1.0f};
+#pragma unroll 1
+    for (int k = 0; k < K; ++k) {
+      int face = top.f[0];
+#pragma unroll
+      for (int i = 1; i < KMAX; ++i) face = (k == i) ? top.f[i] : face;
+      if (face < 0) {
+        ba[3 * k] = -1.0f; ba[3 * k + 1] = -1.0f; ba[3 * k + 2] = -1.0f;
+        continue;
+      }
+      float v[9];
+      const float* __restrict__ src = r.face_verts + (size_t)face * 9;
+#pragma unroll
+      for (int e = 0; e < 9; ++e) v[e] = __ldg(src + e);
+      const float area = XADD(hfr_edge(v[6], v[7], v[0], v[1], v[3], v[4]), HFR_KEPS);
+      float pz, bc[3];
+      bool inside;
+      hfr_raster_bary(c.xf, c.yf, v, area, r.perspective_correct, r.clip_barycentric, &pz, bc, &inside);
+      const float dd = hfr_tri_dist2(c.xf, c.yf, v);
+      const float sd = inside ? -dd : dd;
+      ba[3 * k] = bc[0]; ba[3 * k + 1] = bc[1]; ba[3 * k + 2] = bc[2];
+#pragma unroll
+      for (int i = 0; i < KMAX; ++i)
+        if (i == k) { id[i] = face; z[i] = pz; d[i] = sd; }
+      float col[3] = {1.0f, 1.0f, 1.0f};
+      if (k < kshade) {
+        FragGeom g;
+        gather_frag(s, c.n, (int)(face - (int64_t)c.n * P.F), g);
+        HfrTexTap tap; HfrPhongCtx ctx; float texel[3];
+        shade_fragment(s, c.n, g, bc, dhat, lcol, col, &tap, &ctx, texel);
+      }
+      if (k == 0) { col0[0] = col[0]; col0[1] = col[1]; col0[2] = col[2]; }
+      if (P.blend != HFR_BLEND_HARD) {
+        const float prob = hfr_sigmoid(HFR_FDIV(-sd, P.sigma));
+        prod *= (1.0f - prob);
+        if (P.blend == HFR_BLEND_SOFTMAX) {
+          const float zinv = (P.zfar - pz) / zr;   // IEEE divide: 1 ulp of z_inv is amplified by 1/gamma
+          const float w = prob * HFR_EXP(HFR_FDIV(zinv - zmax, P.gamma));
+          wsum += w;
+          acc[0] += w * col[0]; acc[1] += w * col[1]; acc[2] += w * col[2];
+        }
+      }
+    }
+    if (P.blend == HFR_BLEND_HARD) {
+      rgba[0] = col0[0]; rgba[1] = col0[1]; rgba[2] = col0[2]; rgba[3] = 1.0f;
+    } else if (P.blend == HFR_BLEND_SIGMOID_ALPHA) {
+      rgba[0] = col0[0]; rgba[1] = col0[1]; rgba[2] = col0[2]; rgba[3] = 1.0f - prod;
+    } else {
+      const float delta = fmaxf(HFR_EXP(HFR_FDIV(eps - zmax, P.gamma)), eps);
+      const float den = wsum + delta;
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) rgba[ch] = HFR_FDIV(acc[ch] + delta * P.background[ch], den);
+      rgba[3] = 1.0f - prod;
+    }
   }
+  // Fragments ids / depths / distances: 128-bit evict-first stores when K allows
+  {
+    int64_t* p2f = r.pix_to_face + pix * K;
+    float* zb = r.zbuf + pix * K;
+    float* ds = r.dists + pix * K;
+    if (K == KMAX && (KMAX % 4) == 0) {
+#pragma unroll
+      for (int k = 0; k < KMAX; k += 2) st_cs_i64x2(p2f + k, id[k], id[k + 1]);
+#pragma unroll
+      for (int k = 0; k < KMAX; k += 4) {
+        st_cs_f4(zb + k, z[k], z[k + 1], z[k + 2], z[k + 3]);
+        st_cs_f4(ds + k, d[k], d[k + 1], d[k + 2], d[k + 3]);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k)
+        if (k < K) { p2f[k] = id[k]; zb[k] = z[k]; ds[k] = d[k]; }
+    }
+  }
+  *reinterpret_cast<float4*>(s.image + pix * 4) = make_float4(rgba[0], rgba[1], rgba[2], rgba[3]);
 }
 
 int check_shade(const HfrShadeFwdArgs* a, const char* who) {
