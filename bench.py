@@ -272,7 +272,8 @@ def run_ours(args, cfg):
         step.acc.zero_()
         sb = L.HfrShadeBwdArgs(step._shade_args, L.ptr(step.g_image), None, None, None, L.ptr(step.verts_ndc),
                                L.ptr(step.g_ndc), float(step.blur), 1, int(step.blur > 0), L.ptr(step.g_view),
-                               L.ptr(step.g_vn), L.ptr(step.g_texture), L.ptr(step.g_light_dir), L.ptr(step.g_light_color))
+                               L.ptr(step.g_vn), L.ptr(step.g_texture), L.ptr(step.g_light_dir), L.ptr(step.g_light_color),
+                               ops.raster_tile_box(step.ws, B * step.topo.F, B))
         ev.append(timed("shade_raster_bwd", lambda: L.call("hfr_shade_backward", sb)))
         ev.append(timed("geom_bwd", lambda: ops.geom_backward_raw(step.topo, step.verts, 9, root, focal, prpp, None, None,
                                                                   step.g_view, step.g_ndc, step.g_vn, step.g_verts)))

@@ -83,7 +83,7 @@ class HfrShadeBwdArgs(C.Structure):
     _fields_ = [("f", HfrShadeFwdArgs), ("g_image", vp), ("g_zbuf", vp), ("g_bary", vp), ("g_dists", vp),
                 ("verts_ndc", vp), ("g_verts_ndc", vp), ("blur_radius", f32), ("perspective_correct", i32),
                 ("clip_barycentric", i32), ("g_verts_view", vp), ("g_vnormals", vp), ("g_texture", vp),
-                ("g_light_dir", vp), ("g_light_color", vp)]
+                ("g_light_dir", vp), ("g_light_color", vp), ("tile_box", vp)]
 
 
 class HfrRasterShadeArgs(C.Structure):
@@ -102,7 +102,8 @@ class HfrPoolBwdArgs(C.Structure):
 
 class HfrLossArgs(C.Structure):
     _fields_ = [("N", i32), ("H", i32), ("W", i32), ("sil_scale", f32), ("want_ssim", i32), ("want_grad", i32), ("nhwc", i32),
-                ("re_img", vp), ("re_sil", vp), ("imgs", vp), ("seg", vp), ("sums", vp), ("gauss", vp), ("dmaps", vp)]
+                ("re_img", vp), ("re_sil", vp), ("imgs", vp), ("seg", vp), ("sums", vp), ("gauss", vp), ("dmaps", vp),
+                ("tile_flags", vp)]
 
 
 class HfrLossBwdArgs(C.Structure):
@@ -113,7 +114,7 @@ LOSS_NSUMS = 8
 ENTRY_POINTS = [
     "hfr_last_error", "hfr_abi_version", "hfr_device_ok", "hfr_mano_forward", "hfr_mano_backward",
     "hfr_geom_forward", "hfr_geom_backward", "hfr_raster_workspace_bytes", "hfr_raster_forward",
-    "hfr_raster_backward", "hfr_shade_forward", "hfr_shade_backward", "hfr_raster_shade_forward",
+    "hfr_raster_backward", "hfr_raster_tile_box", "hfr_shade_forward", "hfr_shade_backward", "hfr_raster_shade_forward",
     "hfr_pool_forward", "hfr_pool_backward", "hfr_loss_forward", "hfr_loss_backward",
 ]
 
@@ -135,6 +136,8 @@ def lib() -> C.CDLL:
         _lib.hfr_last_error.restype = C.c_char_p
         _lib.hfr_raster_workspace_bytes.restype = C.c_int64
         _lib.hfr_raster_workspace_bytes.argtypes = [C.c_int64]
+        _lib.hfr_raster_tile_box.restype = C.c_void_p
+        _lib.hfr_raster_tile_box.argtypes = [C.c_void_p, C.c_int64, C.c_int32]
         if _lib.hfr_abi_version() != 1:
             raise HfrError("libhifihr_b200.so ABI version mismatch")
     return _lib

@@ -90,6 +90,24 @@ __device__ __forceinline__ void tap_accumulate(float (&acc)[8][NM], const float 
   }
 }
 
+// SSIM of one pixel from its five windowed moments, and its derivatives wrt (mu_x, E[x^2], E[xy])
+// (utils/pytorch_ssim/__init__.py:17-37).  One copy, so that the all-zero-tile shortcut below yields
+// the same bits as the full stencil.
+__device__ __forceinline__ float ssim_point(float m1, float m2, float e11, float e22, float e12, float* dm1, float* de11,
+                                            float* de12) {
+  const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
+  const float m11 = m1 * m1, m22 = m2 * m2, m12 = m1 * m2;
+  const float s1 = e11 - m11, s2 = e22 - m22, s12 = e12 - m12;
+  const float A1 = 2.f * m12 + C1, A2 = 2.f * s12 + C2, B1 = m11 + m22 + C1, B2 = s1 + s2 + C2;
+  const float ib1 = 1.0f / B1, ib2 = 1.0f / B2;
+  const float S = (A1 * A2) * (ib1 * ib2);
+  const float ib = ib1 * ib2;
+  *dm1 = 2.f * m2 * (A2 - A1) * ib + 2.f * m1 * S * (ib2 - ib1);
+  *de11 = -S * ib2;
+  *de12 = 2.f * A1 * ib;
+  return S;
+}
+
 constexpr size_t kLossFwdSmem = (size_t)(6 * kLH * kXP + 5 * kLH * kHP) * sizeof(float);
 
 __global__ void __launch_bounds__(kLossThreads, 3) loss_fwd_kernel(HfrLossArgs a) {
@@ -108,12 +126,16 @@ __global__ void __launch_bounds__(kLossThreads, 3) loss_fwd_kernel(HfrLossArgs a
     for (int t = 0; t < 11; ++t) g[t] = __ldg(a.gauss + t);
   }
   float l1 = 0.f, sr = 0.f, st = 0.f, sl = 0.f, ss = 0.f, mul = 0.f, add = 0.f;
-  const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
+  bool nz_halo = false;   // any non-zero x / y sample in the tile's halo
+  __shared__ unsigned char sub_nz[16];   // per 8x8 block of the interior: holds a non-zero sample
+  if (tid < 16) sub_nz[tid] = 0;
+  __syncthreads();
   // ---- halo load, all three channels at once (zero padding as F.conv2d(padding=5)) + the pointwise
   //      sums over the tile's interior
   for (int i = tid; i < kLH * kLH; i += kLossThreads) {
     const int hy = i / kLH, hx = i - hy * kLH, gx = x0 + hx - kR, gy = y0 + hy - kR;
     float vx[3] = {0.f, 0.f, 0.f}, vy[3] = {0.f, 0.f, 0.f};
+    bool nz_in = false;
     if (gx >= 0 && gx < a.W && gy >= 0 && gy < a.H) {
       const size_t p = (size_t)gy * a.W + gx;
       float rgb[3], sil;
@@ -131,18 +153,51 @@ __global__ void __launch_bounds__(kLossThreads, 3) loss_fwd_kernel(HfrLossArgs a
       for (int c = 0; c < 3; ++c) {
         vx[c] = rgb[c] * s;
         vy[c] = seg * __ldg(a.imgs + ((size_t)n * 3 + c) * hw + p);
-        if (interior) { l1 += fabsf(vx[c] - vy[c]); sr += vx[c]; st += vy[c]; }
+        const bool nzv = vx[c] != 0.0f || vy[c] != 0.0f;
+        nz_halo |= nzv;
+        if (interior) { l1 += fabsf(vx[c] - vy[c]); sr += vx[c]; st += vy[c]; nz_in |= nzv; }
       }
+      if (nz_in) sub_nz[((hy - kR) >> 3) * 4 + ((hx - kR) >> 3)] = 1;   // benign race: every writer stores 1
       if (interior) { sl += fabsf(sil - seg); mul += sil * seg; add += sil + seg; }
     }
 #pragma unroll
     for (int c = 0; c < 3; ++c) { xs3[c][hy][hx] = vx[c]; ys3[c][hy][hx] = vy[c]; }
   }
+  // Both SSIM inputs are masked images (x = rgb * alpha, y = target * seg): wherever the hand and the target
+  // mask are absent the whole 42x42 halo is exactly zero, every windowed moment is +0 and the stencil
+  // can be skipped - the SSIM value and derivative maps of such a tile are the constants of ssim_point(0...).
+  const int any_halo = __syncthreads_or(nz_halo);   // also orders the sub_nz writes
+  if (a.tile_flags && tid < 16) {
+    const int by = blockIdx.y * 4 + (tid >> 2), bx = blockIdx.x * 4 + (tid & 3);
+    const int FH = (a.H + 7) >> 3, FW = (a.W + 7) >> 3;
+    if (by < FH && bx < FW) a.tile_flags[((size_t)n * FH + by) * FW + bx] = sub_nz[tid];
+  }
+  if (a.want_ssim && !any_halo) {
+    float dm1, de11, de12;
+    const float S = ssim_point(0.f, 0.f, 0.f, 0.f, 0.f, &dm1, &de11, &de12);
+    const int gx = x0 + lane;
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      const int gy = y0 + warp * 4 + o;
+      if (gx < a.W && gy < a.H) {
+        const size_t p = (size_t)gy * a.W + gx;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          ss += S;
+          if (a.dmaps) {
+            a.dmaps[((size_t)n * 9 + c * 3 + 0) * hw + p] = dm1;
+            a.dmaps[((size_t)n * 9 + c * 3 + 1) * hw + p] = de11;
+            a.dmaps[((size_t)n * 9 + c * 3 + 2) * hw + p] = de12;
+          }
+        }
+      }
+    }
+  }
   for (int c = 0; c < 3; ++c) {
     float (*xs)[kXP] = xs3[c];
     float (*ys)[kXP] = ys3[c];
-    if (!a.want_ssim) continue;
-    __syncthreads();
+    if (!a.want_ssim || !any_halo) continue;
+    if (c > 0) __syncthreads();
     // ---- horizontal pass: (halo row, strip of 8 outputs) per thread ------------------------------
     if (tid < kHTasks) {
       const int row = tid >> 2, strip = tid & 3;
@@ -201,17 +256,9 @@ __global__ void __launch_bounds__(kLossThreads, 3) loss_fwd_kernel(HfrLossArgs a
       for (int o = 0; o < 4; ++o) {
         const int gy = y0 + rs * 4 + o;
         if (gx < a.W && gy < a.H) {
-          const float m1 = acc[o][0], m2 = acc[o][1], e11 = acc[o][2], e22 = acc[o][3], e12 = acc[o][4];
-          const float m11 = m1 * m1, m22 = m2 * m2, m12 = m1 * m2;
-          const float s1 = e11 - m11, s2 = e22 - m22, s12 = e12 - m12;
-          const float A1 = 2.f * m12 + C1, A2 = 2.f * s12 + C2, B1 = m11 + m22 + C1, B2 = s1 + s2 + C2;
-          const float ib1 = 1.0f / B1, ib2 = 1.0f / B2;
-          const float S = (A1 * A2) * (ib1 * ib2);
-          ss += S;
+          float dm1, de11, de12;
+          ss += ssim_point(acc[o][0], acc[o][1], acc[o][2], acc[o][3], acc[o][4], &dm1, &de11, &de12);
           if (a.dmaps) {
-            const float ib = ib1 * ib2;
-            const float dm1 = 2.f * m2 * (A2 - A1) * ib + 2.f * m1 * S * (ib2 - ib1);
-            const float de11 = -S * ib2, de12 = 2.f * A1 * ib;
             const size_t p = (size_t)gy * a.W + gx;
             a.dmaps[((size_t)n * 9 + c * 3 + 0) * hw + p] = dm1;
             a.dmaps[((size_t)n * 9 + c * 3 + 1) * hw + p] = de11;
@@ -249,7 +296,19 @@ __global__ void __launch_bounds__(kLossThreads, HFR_LOSSB_MINB) loss_bwd_kernel(
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = blockIdx.z, x0 = blockIdx.x * kLT, y0 = blockIdx.y * kLT;
   const size_t hw = (size_t)a.H * a.W;
-  const bool ssim = a.want_ssim && a.dmaps;
+  bool ssim = a.want_ssim && a.dmaps;
+  if (ssim && a.tile_flags) {
+    // d(SSIM)/dx at a pixel is r0 + 2 x r1 + y r2 with r = Gauss * dmaps: when x and y vanish within 16 pixels
+    // of the tile (>= the 10-pixel reach of the two stacked stencils) dm1 is 0 on the whole halo, so r0 = 0
+    // and the other two terms are multiplied by x = y = 0: the stencil contributes exactly nothing.
+    int live = 0;
+    if (tid < 64) {   // the 8x8 blocks of 8x8 pixels covering the tile and 16 pixels around it
+      const int by = (int)blockIdx.y * 4 - 2 + (tid >> 3), bx = (int)blockIdx.x * 4 - 2 + (tid & 7);
+      const int FH = (a.H + 7) >> 3, FW = (a.W + 7) >> 3;
+      if (by >= 0 && by < FH && bx >= 0 && bx < FW) live = a.tile_flags[((size_t)n * FH + by) * FW + bx];
+    }
+    ssim = __syncthreads_or(live) != 0;
+  }
   float g[11];
   if (ssim) {
 #pragma unroll

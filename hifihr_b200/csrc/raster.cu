@@ -154,6 +154,11 @@ static void launch_fwd(const HfrRasterArgs& a, const uint32_t* ranges, cudaStrea
 
 extern "C" int64_t hfr_raster_workspace_bytes(int64_t Ftot) { return (5 * Ftot + 80) * 4; }
 
+extern "C" const uint32_t* hfr_raster_tile_box(const void* workspace, int64_t Ftot, int32_t N) {
+  if (!workspace || N <= 0 || N > Ftot) return nullptr;
+  return reinterpret_cast<const uint32_t*>(workspace) + ((Ftot + 64 + 3) & ~(int64_t)3);
+}
+
 extern "C" int hfr_raster_forward(const HfrRasterArgs* a, void* stream) {
   using namespace hfr;
   if (int rc = check_raster(a, "raster_forward")) return rc;

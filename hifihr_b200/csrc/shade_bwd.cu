@@ -61,6 +61,11 @@ __global__ void __launch_bounds__(kBwdThreads, (KMAX <= 4 ? HFR_BWD_MINB : 1)) s
   const int kshade = phong ? (P.blend == HFR_BLEND_SOFTMAX ? K : 1) : 0;
   const size_t pix = ((size_t)n * P.H + yi) * P.W + xi;
   const bool dense = a.g_bary || a.g_zbuf || a.g_dists;
+  if (a.tile_box && !dense) {   // tile outside this mesh's footprint: no fragment, no gradient
+    const uint4 bx = __ldg(reinterpret_cast<const uint4*>(a.tile_box) + n);
+    const int tx = blockIdx.x, ty = blockIdx.y;
+    if (tx < (int)bx.x || tx > 255 - (int)bx.y || ty < (int)bx.z || ty > 255 - (int)bx.w) return;
+  }
 
   // ---- fragments of this pixel -----------------------------------------------------------
   int fl[KMAX];            // face id within the mesh, -1 = empty slot

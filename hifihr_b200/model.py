@@ -141,6 +141,7 @@ class FusedHandStep:
         self.zbuf, self.bary, self.dists = e(B, S, S, K), e(B, S, S, K, 3), e(B, S, S, K)
         self.image, self.g_image = e(B, S, S, 4), e(B, S, S, 4)
         self.dmaps = e(B, 9, S, S)
+        self.tile_flags = torch.zeros(B, (S + 7) // 8, (S + 7) // 8, dtype=torch.uint8, device=dev)
         self.sums = e(L.LOSS_NSUMS + 2 * B)
         self.ws = ops.raster_workspace(B * Fm, dev)
         self.mesh_first = (torch.arange(B, device=dev, dtype=I64) * Fm).contiguous()
@@ -178,7 +179,8 @@ class FusedHandStep:
         L.call("hfr_raster_shade_forward", L.HfrRasterShadeArgs(r, s))
         self.sums.zero_()
         self._loss_args = L.HfrLossArgs(B, S, S, self.sil_scale, 1, 1, 1, L.ptr(self.image), None, L.ptr(imgs, F32),
-                                        L.ptr(seg, F32), L.ptr(self.sums), L.ptr(self.gauss), L.ptr(self.dmaps))
+                                        L.ptr(seg, F32), L.ptr(self.sums), L.ptr(self.gauss), L.ptr(self.dmaps),
+                                        L.ptr(self.tile_flags))
         L.call("hfr_loss_forward", self._loss_args)
         self._shade_args = s
 
@@ -191,7 +193,7 @@ class FusedHandStep:
         sb = L.HfrShadeBwdArgs(self._shade_args, L.ptr(self.g_image), None, None, None, L.ptr(self.verts_ndc),
                                L.ptr(self.g_ndc), float(self.blur), 1, int(self.blur > 0), L.ptr(self.g_view),
                                L.ptr(self.g_vn), L.ptr(self.g_texture), L.ptr(self.g_light_dir),
-                               L.ptr(self.g_light_color))
+                               L.ptr(self.g_light_color), ops.raster_tile_box(self.ws, B * self.topo.F, B))
         L.call("hfr_shade_backward", sb)
         ops.geom_backward_raw(self.topo, self.verts, 9, root_xyz, focal, prp, None, None, self.g_view, self.g_ndc,
                               self.g_vn, self.g_verts)

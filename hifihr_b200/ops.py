@@ -176,6 +176,11 @@ def raster_workspace(Ftot, device):
     return torch.empty(nbytes, dtype=torch.uint8, device=device)
 
 
+def raster_tile_box(ws, Ftot, N):
+    """Device address of the per-mesh tile box inside a filled rasterizer workspace (None if absent)."""
+    return L.lib().hfr_raster_tile_box(ws.data_ptr(), int(Ftot), int(N))
+
+
 def shade_params(N, H, W, K, F, V, blend, shade, sigma, gamma, background, light_ambient, light_specular,
                  mat_ambient, mat_diffuse, mat_specular, shininess, tex_shape=(1, 1, 1), VT=0, znear=1.0, zfar=100.0):
     p = L.HfrShadeParams()
@@ -392,9 +397,10 @@ class RenderLossFunction(torch.autograd.Function):
         need_grad = re_img.requires_grad or re_sil.requires_grad
         dmaps = torch.empty(N, 9, H, W, dtype=F32, device=dev) if (want_ssim and need_grad) else None
         gauss = gauss_taps(dev)
+        flags = torch.zeros(N, (H + 7) // 8, (W + 7) // 8, dtype=torch.uint8, device=dev)
         a = L.HfrLossArgs(N, H, W, float(sil_scale), int(want_ssim), int(need_grad), 0, L.ptr(re_img, F32),
                           L.ptr(re_sil, F32), L.ptr(imgs, F32), L.ptr(seg, F32), L.ptr(sums, F32), L.ptr(gauss, F32),
-                          L.ptr(dmaps, F32))
+                          L.ptr(dmaps, F32), L.ptr(flags))
         L.call("hfr_loss_forward", a)
         cnt = float(N * 3 * H * W)
         tex = sums[0] / cnt
@@ -404,17 +410,17 @@ class RenderLossFunction(torch.autograd.Function):
         mul, add = sums[L.LOSS_NSUMS:L.LOSS_NSUMS + N], sums[L.LOSS_NSUMS + N:]
         iou = 1 - (mul / (add - mul)).mean()
         ctx.cfg = (N, H, W, float(sil_scale), int(want_ssim))
-        ctx.save_for_backward(re_img, re_sil, imgs, seg, sums, dmaps if dmaps is not None else sums.new_zeros(0))
+        ctx.save_for_backward(re_img, re_sil, imgs, seg, sums, dmaps if dmaps is not None else sums.new_zeros(0), flags)
         return torch.stack([tex, mrgb, ssim, sil, iou])
 
     @staticmethod
     def backward(ctx, g):
-        re_img, re_sil, imgs, seg, sums, dmaps = ctx.saved_tensors
+        re_img, re_sil, imgs, seg, sums, dmaps, flags = ctx.saved_tensors
         N, H, W, sil_scale, want_ssim = ctx.cfg
         dmaps = dmaps if dmaps.numel() else None
         gauss = gauss_taps(re_img.device)
         f = L.HfrLossArgs(N, H, W, sil_scale, want_ssim, 1, 0, L.ptr(re_img, F32), L.ptr(re_sil, F32), L.ptr(imgs, F32),
-                          L.ptr(seg, F32), L.ptr(sums, F32), L.ptr(gauss, F32), L.ptr(dmaps, F32))
+                          L.ptr(seg, F32), L.ptr(sums, F32), L.ptr(gauss, F32), L.ptr(dmaps, F32), L.ptr(flags))
         g_img, g_sil = torch.empty_like(re_img), torch.empty_like(re_sil)
         w = _cu(g)
         a = L.HfrLossBwdArgs(f, L.ptr(w, F32), L.ptr(gauss, F32), N * 3 * H * W, N, L.ptr(g_img, F32), L.ptr(g_sil, F32))

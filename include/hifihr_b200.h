@@ -230,8 +230,15 @@ typedef struct HfrShadeBwdArgs {
   float* g_texture;                 /* (tex_n,tex_h,tex_w,3)                               */
   float* g_light_dir;               /* (N,3)                                               */
   float* g_light_color;             /* (N,3)                                               */
+  /* optional: per-mesh tile box the rasterizer's setup pass left in its workspace (hfr_raster_tile_box);
+   * tiles outside a mesh's footprint then leave without reading the Fragments.  NULL disables. */
+  const uint32_t* tile_box;
 } HfrShadeBwdArgs;
 int hfr_shade_backward(const HfrShadeBwdArgs* a, void* stream);
+/* Address of the (N,4) uint32 tile box {txmin, 255-txmax, tymin, 255-tymax} (16x16-pixel tiles) inside a
+ * rasterizer workspace that hfr_raster_forward / hfr_raster_shade_forward filled for N meshes and Ftot packed
+ * faces; NULL when the workspace holds none (N > Ftot). */
+const uint32_t* hfr_raster_tile_box(const void* workspace, int64_t Ftot, int32_t N);
 
 /* Fused rasterize + shade forward: writes Fragments AND the image in one pass. */
 typedef struct HfrRasterShadeArgs {
@@ -286,6 +293,9 @@ typedef struct HfrLossArgs {
   float* sums;                      /* (HFR_LOSS_NSUMS + 2N)                               */
   const float* gauss;               /* DEVICE pointer to the 11 fp32 Gaussian taps, or NULL when !want_ssim */
   float* dmaps;                     /* (N,9,H,W) or NULL when !want_ssim || !want_grad      */
+  uint8_t* tile_flags;              /* optional (N, ceil(H/8), ceil(W/8)): written by the forward (1 = that 8x8 pixel
+                                       block holds a non-zero masked-image sample), read by the backward to skip the
+                                       SSIM stencil where it contributes exactly nothing; NULL disables the skip */
 } HfrLossArgs;
 int hfr_loss_forward(const HfrLossArgs* a, void* stream);
 typedef struct HfrLossBwdArgs {

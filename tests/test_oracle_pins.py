@@ -30,6 +30,26 @@ def test_mano_oracle_matches_reference_golden(mano):
     assert (beta.grad - torch.tensor(z["g_beta"])).abs().max() < 2e-5 * np.abs(z["g_beta"]).max()
 
 
+def test_generic_lbs_oracle_matches_mano_oracle(mano):
+    """oracle/lbs.py (any skeleton; used for the NIMBLE-shaped layer) restricted to MANO's constants must be the
+    pinned MANO oracle."""
+    from oracle.lbs import LBSOracle
+    from oracle.mano import JOINT_REORDER, PARENTS, TIP_VERTS_RIGHT
+    inp = P.synthetic_inputs(6, S=8, seed=3)
+    for dt, tol in ((torch.float64, 1e-12), (torch.float32, 1e-6)):
+        o = ManoOracle(mano, dtype=dt)
+        g = LBSOracle(mano["v_template"], mano["shapedirs"], mano["posedirs"], mano["J_regressor"], mano["weights"],
+                      PARENTS, pca_comps=mano["hands_components"][:45], pose_mean=mano["hands_mean"],
+                      tip_verts=TIP_VERTS_RIGHT, joint_order=JOINT_REORDER, center_joint=9, dtype=dt)
+        v, j = o(inp["pose"].to(dt), inp["betas"].to(dt))
+        v2, j2 = g(inp["pose"].to(dt), inp["betas"].to(dt))
+        assert (v - v2).abs().max() < tol and (j - j2).abs().max() < tol
+        tr = torch.randn(6, 3, dtype=dt)
+        v, j = o(inp["pose"].to(dt), inp["betas"].to(dt), trans=tr)
+        v2, j2 = g(inp["pose"].to(dt), inp["betas"].to(dt), trans=tr)
+        assert (v - v2).abs().max() < tol and (j - j2).abs().max() < tol
+
+
 def test_mano_known_answers_appendix_c(mano):
     """SURVEY.md Appendix C (values printed by the reference ManoLayer, torch CPU fp32)."""
     orc = ManoOracle(mano)
