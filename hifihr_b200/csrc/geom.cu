@@ -130,8 +130,8 @@ __global__ void __launch_bounds__(kThreads) geom_bwd_kernel(HfrTopology t, HfrGe
   float* s_v = smem;
   float* s_view = s_v + 3 * V;
   float* s_gN = s_view + 3 * V;          // grads wrt raw normals
-  float* s_g = s_gN + 3 * V;             // accumulated grads wrt view / rel verts
-  float* s_j = s_g + 3 * V;
+  float* s_g = s_v;                      // accumulated grads wrt view / rel verts (s_v is dead after geom_stage)
+  float* s_j = s_gN + 3 * V;
   float* s_pos = s_j + 3 * (t.NJR > 0 ? t.NJR : 1);
   float* s_root = s_pos + 3 * (t.NOUT > 0 ? t.NOUT : 1);
   float* s_red = s_root + 4;             // kThreads/32 warps * 3 + 3
@@ -268,7 +268,7 @@ extern "C" int hfr_geom_backward(const HfrTopology* t, const HfrGeomBwdArgs* a, 
   if (int rc = check_topo(t, a->root_out >= 0)) return rc;
   HFR_CHECK_ARG(!a->g_verts_ndc || (a->focal && a->prp), "geom_backward: g_verts_ndc needs focal/prp");
   if (a->B == 0) return HFR_OK;
-  const size_t smem = (size_t)(12 * t->V + 6 * (t->NJR > 0 ? t->NJR : 1) + 3 * (t->NOUT > 0 ? t->NOUT : 1) + 16 + 3 * (kThreads / 32)) * sizeof(float);
+  const size_t smem = (size_t)(9 * t->V + 6 * (t->NJR > 0 ? t->NJR : 1) + 3 * (t->NOUT > 0 ? t->NOUT : 1) + 16 + 3 * (kThreads / 32)) * sizeof(float);
   HFR_CHECK_ARG(smem <= 227 * 1024, "geom_backward: mesh too large for shared memory");
   if (smem > 48 * 1024) cudaFuncSetAttribute(geom_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   geom_bwd_kernel<<<a->B, kThreads, smem, (cudaStream_t)stream>>>(*t, *a);

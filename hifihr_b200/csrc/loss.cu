@@ -127,8 +127,8 @@ __global__ void __launch_bounds__(kLossThreads, 3) loss_fwd_kernel(HfrLossArgs a
   }
   float l1 = 0.f, sr = 0.f, st = 0.f, sl = 0.f, ss = 0.f, mul = 0.f, add = 0.f;
   bool nz_halo = false;   // any non-zero x / y sample in the tile's halo
-  __shared__ unsigned char sub_nz[16];   // per 8x8 block of the interior: holds a non-zero sample
-  if (tid < 16) sub_nz[tid] = 0;
+  __shared__ unsigned char sub_nz[64];   // per 4x4 block of the interior: holds a non-zero sample
+  if (tid < 64) sub_nz[tid] = 0;
   __syncthreads();
   // ---- halo load, all three channels at once (zero padding as F.conv2d(padding=5)) + the pointwise
   //      sums over the tile's interior
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(kLossThreads, 3) loss_fwd_kernel(HfrLossArgs a
         nz_halo |= nzv;
         if (interior) { l1 += fabsf(vx[c] - vy[c]); sr += vx[c]; st += vy[c]; nz_in |= nzv; }
       }
-      if (nz_in) sub_nz[((hy - kR) >> 3) * 4 + ((hx - kR) >> 3)] = 1;   // benign race: every writer stores 1
+      if (nz_in) sub_nz[((hy - kR) >> 2) * 8 + ((hx - kR) >> 2)] = 1;   // benign race: every writer stores 1
       if (interior) { sl += fabsf(sil - seg); mul += sil * seg; add += sil + seg; }
     }
 #pragma unroll
@@ -167,9 +167,9 @@ __global__ void __launch_bounds__(kLossThreads, 3) loss_fwd_kernel(HfrLossArgs a
   // mask are absent the whole 42x42 halo is exactly zero, every windowed moment is +0 and the stencil
   // can be skipped - the SSIM value and derivative maps of such a tile are the constants of ssim_point(0...).
   const int any_halo = __syncthreads_or(nz_halo);   // also orders the sub_nz writes
-  if (a.tile_flags && tid < 16) {
-    const int by = blockIdx.y * 4 + (tid >> 2), bx = blockIdx.x * 4 + (tid & 3);
-    const int FH = (a.H + 7) >> 3, FW = (a.W + 7) >> 3;
+  if (a.tile_flags && tid < 64) {
+    const int by = blockIdx.y * 8 + (tid >> 3), bx = blockIdx.x * 8 + (tid & 7);
+    const int FH = (a.H + 3) >> 2, FW = (a.W + 3) >> 2;
     if (by < FH && bx < FW) a.tile_flags[((size_t)n * FH + by) * FW + bx] = sub_nz[tid];
   }
   if (a.want_ssim && !any_halo) {
@@ -298,13 +298,13 @@ __global__ void __launch_bounds__(kLossThreads, HFR_LOSSB_MINB) loss_bwd_kernel(
   const size_t hw = (size_t)a.H * a.W;
   bool ssim = a.want_ssim && a.dmaps;
   if (ssim && a.tile_flags) {
-    // d(SSIM)/dx at a pixel is r0 + 2 x r1 + y r2 with r = Gauss * dmaps: when x and y vanish within 16 pixels
+    // d(SSIM)/dx at a pixel is r0 + 2 x r1 + y r2 with r = Gauss * dmaps: when x and y vanish within 12 pixels
     // of the tile (>= the 10-pixel reach of the two stacked stencils) dm1 is 0 on the whole halo, so r0 = 0
     // and the other two terms are multiplied by x = y = 0: the stencil contributes exactly nothing.
     int live = 0;
-    if (tid < 64) {   // the 8x8 blocks of 8x8 pixels covering the tile and 16 pixels around it
-      const int by = (int)blockIdx.y * 4 - 2 + (tid >> 3), bx = (int)blockIdx.x * 4 - 2 + (tid & 7);
-      const int FH = (a.H + 7) >> 3, FW = (a.W + 7) >> 3;
+    if (tid < 14 * 14) {   // the 14x14 blocks of 4x4 pixels covering the tile and 12 pixels around it
+      const int by = (int)blockIdx.y * 8 - 3 + tid / 14, bx = (int)blockIdx.x * 8 - 3 + tid % 14;
+      const int FH = (a.H + 3) >> 2, FW = (a.W + 3) >> 2;
       if (by >= 0 && by < FH && bx >= 0 && bx < FW) live = a.tile_flags[((size_t)n * FH + by) * FW + bx];
     }
     ssim = __syncthreads_or(live) != 0;

@@ -77,10 +77,9 @@ template <int KMAX>
 __global__ void __launch_bounds__(kRasterThreads) raster_fwd_kernel(HfrRasterArgs a, const uint32_t* __restrict__ ranges,
                                                                     const uint32_t* __restrict__ mesh_box) {
   __shared__ RasterSmem sm;
-  const PixelCtx c = make_pixel_ctx(a.H, a.W);
+  PixelCtx c = make_pixel_ctx(a.H, a.W);
   TopK<KMAX> top;
-  raster_tile<KMAX>(a, ranges, mesh_box, sm, c.n, c.tx, c.ty, c.xf, c.yf, c.pix_active, c.warp_active, c.wx_lo, c.wx_hi,
-                    c.wy_lo, c.wy_hi, top);
+  raster_tile<KMAX>(a, ranges, mesh_box, sm, c, top);
   if (c.pix_active) {
     int64_t id[KMAX];
     float z[KMAX], d[KMAX], b[KMAX * 3];

@@ -14,9 +14,11 @@
 //           strict `<` (the CPU reference's (z, face) ordering).
 //   stage:  the listed faces' 9 floats are gathered once per tile into 64-byte shared records
 //           together with the dilated bbox and the barycentric denominator.
-//   fine:   each warp first culls the tile list against its own 8x4 block (one ballot per 32
-//           faces), then all lanes walk the surviving faces together; records are read with
-//           broadcast LDS.128.
+//   fine:   per 32 list entries, lane i builds the 32-bit mask of the warp's 8x4 pixels that lie in
+//           face i's dilated bbox; a 5-step shuffle transpose turns the 32 masks into one mask per
+//           PIXEL of the faces it has to look at.  Every lane then walks ITS OWN faces (front to
+//           back), so the expensive exact coverage / depth / distance math runs on dense warps
+//           instead of idling the lanes a face does not touch.
 #pragma once
 #include "raster_math.cuh"
 
@@ -24,14 +26,28 @@ namespace hfr {
 
 constexpr int kTileW = 16, kTileH = 16, kRasterThreads = 256;
 constexpr int kListCap = 256;   // faces per staged batch
-constexpr int kRecFloats = 16;  // 64-byte record: 9 vertex floats, dilated bbox, area, zmin, face id
+constexpr int kRecFloats = 20;  // 80-byte record (9 vertex floats, dilated bbox, area, zmin, face id, pad): the 20-word
+                                // stride spreads the per-lane LDS.128 of the fine pass over all bank groups
 constexpr int kChunk = 32 * kRasterThreads;  // faces handled per coarse pass (one hit bit per face per thread)
 
 struct RasterSmem {
   __align__(16) float rec[kListCap * kRecFloats];
+  uint32_t wmask[kRasterThreads / 32][kListCap / 32][32];   // per warp, per 32 list entries: one face mask per lane (pixel)
+  float tabx[kTileW], taby[kTileH];                          // NDC sample positions of the tile's columns / rows
   int wsum[kRasterThreads / 32];
   uint16_t order[kListCap];   // record indices sorted front to back (by the faces' nearest vertex)
 };
+
+// 32x32 bit-matrix transpose across the warp: on return bit i of lane L = bit L of lane i's input
+__device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, int lane) {
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) {
+    const uint32_t m = d == 16 ? 0x0000ffffu : d == 8 ? 0x00ff00ffu : d == 4 ? 0x0f0f0f0fu : d == 2 ? 0x33333333u : 0x55555555u;
+    const uint32_t y = __shfl_xor_sync(0xffffffffu, x, d);
+    x = (lane & d) ? ((x & ~m) | ((y >> d) & m)) : ((x & m) | ((y << d) & ~m));
+  }
+  return x;
+}
 
 __device__ __forceinline__ uint32_t pack_tile_range(int txmin, int txmax, int tymin, int tymax) {
   return (uint32_t)txmin | ((uint32_t)txmax << 8) | ((uint32_t)tymin << 16) | ((uint32_t)tymax << 24);
@@ -65,6 +81,30 @@ struct TopK {
   }
 };
 
+struct PixelCtx {
+  int n, tx, ty, xi, yi;
+  float xf, yf;          // NDC sample position; filled by raster_tile (tiles outside the mesh never need it)
+  bool pix_active, warp_active;
+};
+
+__device__ __forceinline__ PixelCtx make_pixel_ctx(int H, int W) {
+  PixelCtx c;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  c.n = blockIdx.z; c.tx = blockIdx.x; c.ty = blockIdx.y;
+  const int wx0 = c.tx * kTileW + (warp & 1) * 8, wy0 = c.ty * kTileH + (warp >> 1) * 4;
+  c.xi = wx0 + (lane & 7);
+  c.yi = wy0 + (lane >> 3);
+  c.pix_active = c.xi < W && c.yi < H;
+  c.warp_active = wx0 < W && wy0 < H;
+  c.xf = 0.0f; c.yf = 0.0f;
+  return c;
+}
+
+// hfr_pix_to_ndc with the per-axis range / offset hoisted (same X* sequence, same bits)
+__device__ __forceinline__ float pix_to_ndc_pre(int i, float range, float offset, int S1) {
+  return XADD(-offset, XDIV(XADD(XMUL(range, (float)i), offset), (float)S1));
+}
+
 // Coarse + stage + fine for one tile.  On return `top` holds, per thread (= pixel), the KMAX
 // nearest valid faces as packed face ids (sorted by (z, id)).
 //
@@ -72,18 +112,19 @@ struct TopK {
 //           single pass over the packed tile ranges; one block-wide scan of the hit counts then
 //           gives every thread its slot in the tile list.  A tile no face touches leaves after
 //           that scan.
-//   stage:  listed faces are gathered once per tile into 64-byte shared records and ranked front
+//   stage:  listed faces are gathered once per tile into 80-byte shared records and ranked front
 //           to back by their nearest vertex (rank sort in shared memory).
-//   fine:   each warp culls the depth-ordered list against its own 8x4 block (one ballot per 32
-//           faces), then all lanes walk the survivors together (broadcast LDS.128); a lane skips
-//           a face whose nearest vertex is not in front of its current K-th depth before doing
-//           any division, and the warp stops as soon as that holds for all its pixels.  The top-K
-//           is ordered by (z, packed face index), the CPU reference's order, ties included.
+//   fine:   per 32 list entries lane i computes which of the warp's 8x4 pixels lie in face i's dilated
+//           bbox; the 32 masks are transposed (5 shuffles) into one face mask per pixel.  Each lane then
+//           walks its own faces front to back (per-lane LDS.128 of the record) and stops at the first face
+//           whose nearest vertex is not in front of its current K-th depth, so the exact coverage / depth /
+//           distance math runs on densely populated warps.  The top-K is ordered by (z, packed face index),
+//           the CPU reference's order, ties included.
 template <int KMAX>
 __device__ __forceinline__ void raster_tile(const HfrRasterArgs& a, const uint32_t* __restrict__ tile_ranges,
-                                            const uint32_t* __restrict__ mesh_box, RasterSmem& sm, int n, int tx, int ty, float xf, float yf,
-                                            bool pix_active, bool warp_active, float wx_lo, float wx_hi, float wy_lo, float wy_hi,
-                                            TopK<KMAX>& top) {
+                                            const uint32_t* __restrict__ mesh_box, RasterSmem& sm, PixelCtx& c, TopK<KMAX>& top) {
+  const int n = c.n, tx = c.tx, ty = c.ty;
+  const bool pix_active = c.pix_active, warp_active = c.warp_active;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t f0 = a.mesh_first[n];
   const int nf = (int)a.mesh_nfaces[n];
@@ -97,6 +138,22 @@ __device__ __forceinline__ void raster_tile(const HfrRasterArgs& a, const uint32
     const uint4 bx = __ldg(reinterpret_cast<const uint4*>(mesh_box) + n);
     if (tx < (int)bx.x || tx > 255 - (int)bx.y || ty < (int)bx.z || ty > 255 - (int)bx.w) return;
   }
+  // NDC sample positions of this tile's columns / rows (the same X* sequence as the oracle's pixel centres)
+  if (tid < kTileW + kTileH) {
+    const int H = a.H, W = a.W;
+    if (tid < kTileW) {
+      const float rx = W > H ? XDIV(XMUL(2.0f, (float)W), (float)H) : 2.0f, ox = XDIV(rx, 2.0f);
+      sm.tabx[tid] = pix_to_ndc_pre(W - 1 - (tx * kTileW + tid), rx, ox, W);
+    } else {
+      const float ry = H > W ? XDIV(XMUL(2.0f, (float)H), (float)W) : 2.0f, oy = XDIV(ry, 2.0f);
+      sm.taby[tid - kTileW] = pix_to_ndc_pre(H - 1 - (ty * kTileH + tid - kTileW), ry, oy, H);
+    }
+  }
+  __syncthreads();
+  const int lx0 = (warp & 1) * 8, ly0 = (warp >> 1) * 4;
+  const float xf = sm.tabx[lx0 + (lane & 7)], yf = sm.taby[ly0 + (lane >> 3)];
+  c.xf = xf; c.yf = yf;
+  const uint32_t active_mask = __ballot_sync(0xffffffffu, pix_active);
 
   for (int cbase = 0; cbase < nf; cbase += kChunk) {
     const int cn = min(nf - cbase, kChunk);
@@ -178,42 +235,63 @@ __device__ __forceinline__ void raster_tile(const HfrRasterArgs& a, const uint32
       }
       __syncthreads();
       if (warp_active) {
-        for (int b0 = 0; b0 < bcnt; b0 += 32) {
-          const int i = b0 + lane;
-          int ri = 0;
-          bool ok = false;
+        const int nch = (bcnt + 31) >> 5;
+        // A. which faces does each pixel of this warp have to look at?
+        for (int ch = 0; ch < nch; ++ch) {
+          const int i = ch * 32 + lane;
+          uint32_t M = 0;
           if (i < bcnt) {
-            ri = sm.order[i];
-            const float4 q2 = *reinterpret_cast<const float4*>(sm.rec + ri * kRecFloats + 8);
-            const float ymax = sm.rec[ri * kRecFloats + 12];
-            ok = !(q2.z < wx_lo || q2.y > wx_hi || ymax < wy_lo || q2.w > wy_hi);
+            const float* rp = sm.rec + (int)sm.order[i] * kRecFloats;
+            const float4 q2 = *reinterpret_cast<const float4*>(rp + 8);   // (z2, xmin, xmax, ymin)
+            const float ymax = rp[12];
+            uint32_t xm = 0, ym = 0;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { const float x = sm.tabx[lx0 + e]; xm |= (x < q2.y || x > q2.z) ? 0u : (1u << e); }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { const float y = sm.taby[ly0 + e]; ym |= (y < q2.w || y > ymax) ? 0u : (1u << (8 * e)); }
+            M = (xm * ym) & active_mask;   // lane = 8 * row + column; the four row copies of xm cannot carry into each other
           }
-          if (zcull) {
-            // every remaining face has zmin >= this chunk's first: stop once no pixel of the warp can take one
-            const float zfirst = sm.rec[__shfl_sync(0xffffffffu, ri, 0) * kRecFloats + 14];
-            if (__all_sync(0xffffffffu, !pix_active || !(zfirst < top.worst()))) break;
+          sm.wmask[warp][ch][lane] = warp_transpose32(M, lane);
+        }
+        __syncwarp();
+        // B. every lane walks its own faces, front to back; a lane is finished at the end of its list or at the
+        //    first face whose nearest vertex is not in front of its K-th depth (the list is depth-ordered)
+        int ch = 0;
+        uint32_t Wc = sm.wmask[warp][0][lane];
+        bool done = false;
+        while (true) {
+          int ri = -1;
+          if (!done) {
+            while (Wc == 0 && ++ch < nch) Wc = sm.wmask[warp][ch][lane];
+            if (Wc == 0) {
+              done = true;
+            } else {
+              const int j = __ffs(Wc) - 1;
+              Wc &= Wc - 1;
+              ri = sm.order[ch * 32 + j];
+            }
           }
-          unsigned m = __ballot_sync(0xffffffffu, ok);
-          while (m) {
-            const int j = __ffs(m) - 1;
-            m &= m - 1;
-            const int rj = __shfl_sync(0xffffffffu, ri, j);
-            const float4* r4 = reinterpret_cast<const float4*>(sm.rec + rj * kRecFloats);
-            const float4 q2 = r4[2], q3 = r4[3];
-            bool want = pix_active && !(xf < q2.y || xf > q2.z || yf < q2.w || yf > q3.x);
-            if (zcull) want = want && (q3.z < top.worst());
-            if (want) {
-              const float4 q0 = r4[0], q1 = r4[1];
-              const float v[9] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x};
-              const int face = __float_as_int(q3.w);
-              float pz, bc[3];
-              bool inside;
-              if (hfr_raster_bary(xf, yf, v, q3.y, pc, clip, &pz, bc, &inside)) {
-                if (top.beats_worst(pz, face)) {
-                  bool keep = inside;
-                  if (!keep) keep = hfr_tri_dist2(xf, yf, v) < blur;
-                  if (keep) top.insert(pz, face);
-                }
+          float4 q3 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ri >= 0) {
+            q3 = *reinterpret_cast<const float4*>(sm.rec + ri * kRecFloats + 12);   // (ymax, area, zmin, face)
+            if (zcull && !(q3.z < top.worst())) { ri = -1; done = true; }
+          }
+          if (!__any_sync(0xffffffffu, ri >= 0)) {
+            if (__all_sync(0xffffffffu, done)) break;
+            continue;
+          }
+          if (ri >= 0) {
+            const float4* r4 = reinterpret_cast<const float4*>(sm.rec + ri * kRecFloats);
+            const float4 q0 = r4[0], q1 = r4[1];
+            const float v[9] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, sm.rec[ri * kRecFloats + 8]};
+            const int face = __float_as_int(q3.w);
+            float pz, bc[3];
+            bool inside;
+            if (hfr_raster_bary(xf, yf, v, q3.y, pc, clip, &pz, bc, &inside)) {
+              if (top.beats_worst(pz, face)) {
+                bool keep = inside;
+                if (!keep) keep = hfr_tri_dist2(xf, yf, v) < blur;
+                if (keep) top.insert(pz, face);
               }
             }
           }
@@ -278,39 +356,6 @@ __device__ __forceinline__ void store_fragments(const HfrRasterArgs& a, size_t p
       }
     }
   }
-}
-
-struct PixelCtx {
-  int n, tx, ty, xi, yi;
-  float xf, yf, wx_lo, wx_hi, wy_lo, wy_hi;
-  bool pix_active, warp_active;
-};
-
-// hfr_pix_to_ndc with the per-axis range / offset hoisted (same X* sequence, same bits)
-__device__ __forceinline__ float pix_to_ndc_pre(int i, float range, float offset, int S1) {
-  return XADD(-offset, XDIV(XADD(XMUL(range, (float)i), offset), (float)S1));
-}
-
-__device__ __forceinline__ PixelCtx make_pixel_ctx(int H, int W) {
-  PixelCtx c;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  c.n = blockIdx.z; c.tx = blockIdx.x; c.ty = blockIdx.y;
-  const int wx0 = c.tx * kTileW + (warp & 1) * 8, wy0 = c.ty * kTileH + (warp >> 1) * 4;
-  c.xi = wx0 + (lane & 7);
-  c.yi = wy0 + (lane >> 3);
-  c.pix_active = c.xi < W && c.yi < H;
-  c.warp_active = wx0 < W && wy0 < H;
-  const float rx = W > H ? XDIV(XMUL(2.0f, (float)W), (float)H) : 2.0f, ox = XDIV(rx, 2.0f);
-  const float ry = H > W ? XDIV(XMUL(2.0f, (float)H), (float)W) : 2.0f, oy = XDIV(ry, 2.0f);
-  c.xf = pix_to_ndc_pre(W - 1 - c.xi, rx, ox, W);
-  c.yf = pix_to_ndc_pre(H - 1 - c.yi, ry, oy, H);
-  // bounds of the warp's 8x4 block = sample points of its corner pixels
-  const int wx1 = min(wx0 + 7, W - 1), wy1 = min(wy0 + 3, H - 1);
-  c.wx_hi = pix_to_ndc_pre(W - 1 - wx0, rx, ox, W);
-  c.wx_lo = pix_to_ndc_pre(W - 1 - wx1, rx, ox, W);
-  c.wy_hi = pix_to_ndc_pre(H - 1 - wy0, ry, oy, H);
-  c.wy_lo = pix_to_ndc_pre(H - 1 - wy1, ry, oy, H);
-  return c;
 }
 
 // host helpers defined in raster.cu

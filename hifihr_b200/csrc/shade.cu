@@ -49,10 +49,9 @@ __global__ void __launch_bounds__(kRasterThreads, (KMAX <= 4 ? HFR_RASTER_MINB :
                                                                           const uint32_t* __restrict__ ranges,
                                                                           const uint32_t* __restrict__ mesh_box) {
   __shared__ RasterSmem sm;
-  const PixelCtx c = make_pixel_ctx(r.H, r.W);
+  PixelCtx c = make_pixel_ctx(r.H, r.W);
   TopK<KMAX> top;
-  raster_tile<KMAX>(r, ranges, mesh_box, sm, c.n, c.tx, c.ty, c.xf, c.yf, c.pix_active, c.warp_active, c.wx_lo, c.wx_hi,
-                    c.wy_lo, c.wy_hi, top);
+  raster_tile<KMAX>(r, ranges, mesh_box, sm, c, top);
   if (!c.pix_active) return;
   const HfrShadeParams& P = s.p;
   const int K = r.K;

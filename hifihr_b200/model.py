@@ -141,7 +141,7 @@ class FusedHandStep:
         self.zbuf, self.bary, self.dists = e(B, S, S, K), e(B, S, S, K, 3), e(B, S, S, K)
         self.image, self.g_image = e(B, S, S, 4), e(B, S, S, 4)
         self.dmaps = e(B, 9, S, S)
-        self.tile_flags = torch.zeros(B, (S + 7) // 8, (S + 7) // 8, dtype=torch.uint8, device=dev)
+        self.tile_flags = torch.zeros(B, (S + 3) // 4, (S + 3) // 4, dtype=torch.uint8, device=dev)
         self.sums = e(L.LOSS_NSUMS + 2 * B)
         self.ws = ops.raster_workspace(B * Fm, dev)
         self.mesh_first = (torch.arange(B, device=dev, dtype=I64) * Fm).contiguous()

@@ -397,7 +397,7 @@ class RenderLossFunction(torch.autograd.Function):
         need_grad = re_img.requires_grad or re_sil.requires_grad
         dmaps = torch.empty(N, 9, H, W, dtype=F32, device=dev) if (want_ssim and need_grad) else None
         gauss = gauss_taps(dev)
-        flags = torch.zeros(N, (H + 7) // 8, (W + 7) // 8, dtype=torch.uint8, device=dev)
+        flags = torch.zeros(N, (H + 3) // 4, (W + 3) // 4, dtype=torch.uint8, device=dev)
         a = L.HfrLossArgs(N, H, W, float(sil_scale), int(want_ssim), int(need_grad), 0, L.ptr(re_img, F32),
                           L.ptr(re_sil, F32), L.ptr(imgs, F32), L.ptr(seg, F32), L.ptr(sums, F32), L.ptr(gauss, F32),
                           L.ptr(dmaps, F32), L.ptr(flags))

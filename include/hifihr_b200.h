@@ -293,7 +293,7 @@ typedef struct HfrLossArgs {
   float* sums;                      /* (HFR_LOSS_NSUMS + 2N)                               */
   const float* gauss;               /* DEVICE pointer to the 11 fp32 Gaussian taps, or NULL when !want_ssim */
   float* dmaps;                     /* (N,9,H,W) or NULL when !want_ssim || !want_grad      */
-  uint8_t* tile_flags;              /* optional (N, ceil(H/8), ceil(W/8)): written by the forward (1 = that 8x8 pixel
+  uint8_t* tile_flags;              /* optional (N, ceil(H/4), ceil(W/4)): written by the forward (1 = that 4x4 pixel
                                        block holds a non-zero masked-image sample), read by the backward to skip the
                                        SSIM stencil where it contributes exactly nothing; NULL disables the skip */
 } HfrLossArgs;
