@@ -302,6 +302,15 @@ def run_ours(args, cfg):
             "loss_bwd": B * (16 + 12 + 4 + 36 + 16) * P_,        # the same read again + image gradient written
         }
         ach = alg.get(top, 0) / (kern_ms[top] * 1e-3) / 1e9
+        # DRAM bytes of one launch of that kernel from the committed `ncu --set full` capture (same workload only)
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        kname = {"raster_shade_fwd": "raster_shade_fwd_kernel", "shade_raster_bwd": "shade_bwd_kernel",
+                 "loss_fwd": "loss_fwd_kernel", "loss_bwd": "loss_bwd_kernel"}.get(top)
+        if args.config == "c2" and B == 64 and kname and os.path.isfile(tpath):
+            tj = json.load(open(tpath))
+            traffic = tj.get("dram_bytes_per_launch", {}).get(kname)
+            traffic_src = tj.get("source")
         step_bytes = algorithmic_bytes_per_sample(S, K, T=cfg["T"], B=B) * B
         line = {
             "metric": "hand renders/sec (fwd+bwd)", "value": value, "unit": "samples/s", "n_gpus": world,
@@ -317,7 +326,8 @@ def run_ours(args, cfg):
             "gpu_launches": step.launches_per_step * args.steps,
             "clocks": clk.summary(),
             "roofline": {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel_ms": kern_ms,
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "algorithmic_bytes_per_launch": alg.get(top, 0), "peak_source": peak_src, "kernel_ms": kern_ms,
                          "step": {"algorithmic_MB_per_sample": step_bytes / B / 1e6,
                                   "achieved": step_bytes / (ms / args.steps * 1e-3) / 1e9,
                                   "frac": step_bytes / (ms / args.steps * 1e-3) / 1e9 / peak}},

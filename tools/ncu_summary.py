@@ -25,6 +25,7 @@ if os.path.isfile(rep):
     hdr, units = rows[0], rows[1]
     idx = {h: i for i, h in enumerate(hdr)}
     seen = set()
+    traffic = {}
     lines += ["## `ncu --set full --clock-control none` (one launch per kernel; cold-cache, serialised)", "",
               "| kernel | " + " | ".join(n for _, n in WANT) + " |", "|---|" + "---|" * len(WANT)]
     for r in rows[2:]:
@@ -44,8 +45,17 @@ if os.path.isfile(rep):
             else:
                 cells.append("-")
         short = k.split("(")[0].replace("void ", "").replace("hfr::", "").replace("<unnamed>::", "")
+        try:   # DRAM bytes of this launch (read + write), for bench.py's roofline.traffic
+            mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            rd, wr = idx["dram__bytes_read.sum"], idx["dram__bytes_write.sum"]
+            traffic[short.split("<")[0]] = float(r[rd]) * mult[units[rd]] + float(r[wr]) * mult[units[wr]]
+        except (KeyError, ValueError):
+            pass
         lines.append(f"| `{short}` | " + " | ".join(cells) + " |")
     lines.append("")
+    import json
+    json.dump({"tag": tag, "source": f"profiles/{tag}_summary.md (ncu --set full, one launch, C2 B=64)",
+               "dram_bytes_per_launch": traffic}, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
 if os.path.isfile(lau):
     rows = [r for r in csv.reader(open(lau)) if r and r[0].isdigit() or (r and r[0] == "ID")]
     hdr = rows[0]
