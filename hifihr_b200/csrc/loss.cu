@@ -132,36 +132,61 @@ __global__ void __launch_bounds__(kLossThreads, 3) loss_fwd_kernel(HfrLossArgs a
   __syncthreads();
   // ---- halo load, all three channels at once (zero padding as F.conv2d(padding=5)) + the pointwise
   //      sums over the tile's interior
-  for (int i = tid; i < kLH * kLH; i += kLossThreads) {
-    const int hy = i / kLH, hx = i - hy * kLH, gx = x0 + hx - kR, gy = y0 + hy - kR;
-    float vx[3] = {0.f, 0.f, 0.f}, vy[3] = {0.f, 0.f, 0.f};
-    bool nz_in = false;
-    if (gx >= 0 && gx < a.W && gy >= 0 && gy < a.H) {
-      const size_t p = (size_t)gy * a.W + gx;
-      float rgb[3], sil;
-      if (a.nhwc) {
-        const float4 q = __ldg(reinterpret_cast<const float4*>(a.re_img + ((size_t)n * hw + p) * 4));
-        rgb[0] = q.x; rgb[1] = q.y; rgb[2] = q.z; sil = q.w;
-      } else {
-        sil = __ldg(a.re_sil + (size_t)n * hw + p);
+  // The loads of kHaloBatch halo positions are issued back to back before any of them is consumed, so a thread
+  // has 5 x kHaloBatch requests in flight instead of paying one round trip per position.
+  constexpr int kHaloIters = (kLH * kLH + kLossThreads - 1) / kLossThreads;   // 7
+  constexpr int kHaloBatch = 4;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) rgb[c] = __ldg(a.re_img + ((size_t)n * 3 + c) * hw + p);
-      }
-      const float seg = __ldg(a.seg + n * hw + p), s = sil * inv_scale;
-      const bool interior = hx >= kR && hx < kR + kLT && hy >= kR && hy < kR + kLT;
+  for (int b0 = 0; b0 < kHaloIters; b0 += kHaloBatch) {
+    float4 q[kHaloBatch];
+    float sg[kHaloBatch], im[kHaloBatch][3];
+    bool ok[kHaloBatch];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        vx[c] = rgb[c] * s;
-        vy[c] = seg * __ldg(a.imgs + ((size_t)n * 3 + c) * hw + p);
-        const bool nzv = vx[c] != 0.0f || vy[c] != 0.0f;
-        nz_halo |= nzv;
-        if (interior) { l1 += fabsf(vx[c] - vy[c]); sr += vx[c]; st += vy[c]; nz_in |= nzv; }
+    for (int u = 0; u < kHaloBatch; ++u) {
+      const int i = tid + (b0 + u) * kLossThreads;
+      const int hy = i / kLH, hx = i - hy * kLH, gx = x0 + hx - kR, gy = y0 + hy - kR;
+      ok[u] = (b0 + u) < kHaloIters && i < kLH * kLH && gx >= 0 && gx < a.W && gy >= 0 && gy < a.H;
+      q[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      sg[u] = im[u][0] = im[u][1] = im[u][2] = 0.f;
+      if (ok[u]) {
+        const size_t p = (size_t)gy * a.W + gx;
+        if (a.nhwc) {
+          q[u] = __ldg(reinterpret_cast<const float4*>(a.re_img + ((size_t)n * hw + p) * 4));
+        } else {
+          q[u].w = __ldg(a.re_sil + (size_t)n * hw + p);
+          q[u].x = __ldg(a.re_img + ((size_t)n * 3 + 0) * hw + p);
+          q[u].y = __ldg(a.re_img + ((size_t)n * 3 + 1) * hw + p);
+          q[u].z = __ldg(a.re_img + ((size_t)n * 3 + 2) * hw + p);
+        }
+        sg[u] = __ldg(a.seg + n * hw + p);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) im[u][c] = __ldg(a.imgs + ((size_t)n * 3 + c) * hw + p);
       }
-      if (nz_in) sub_nz[((hy - kR) >> 2) * 8 + ((hx - kR) >> 2)] = 1;   // benign race: every writer stores 1
-      if (interior) { sl += fabsf(sil - seg); mul += sil * seg; add += sil + seg; }
     }
 #pragma unroll
-    for (int c = 0; c < 3; ++c) { xs3[c][hy][hx] = vx[c]; ys3[c][hy][hx] = vy[c]; }
+    for (int u = 0; u < kHaloBatch; ++u) {
+      const int i = tid + (b0 + u) * kLossThreads;
+      if ((b0 + u) >= kHaloIters || i >= kLH * kLH) continue;
+      const int hy = i / kLH, hx = i - hy * kLH;
+      float vx[3] = {0.f, 0.f, 0.f}, vy[3] = {0.f, 0.f, 0.f};
+      if (ok[u]) {
+        const float rgb[3] = {q[u].x, q[u].y, q[u].z}, sil = q[u].w, seg = sg[u], s = sil * inv_scale;
+        const bool interior = hx >= kR && hx < kR + kLT && hy >= kR && hy < kR + kLT;
+        bool nz_in = false;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          vx[c] = rgb[c] * s;
+          vy[c] = seg * im[u][c];
+          const bool nzv = vx[c] != 0.0f || vy[c] != 0.0f;
+          nz_halo |= nzv;
+          if (interior) { l1 += fabsf(vx[c] - vy[c]); sr += vx[c]; st += vy[c]; nz_in |= nzv; }
+        }
+        if (nz_in) sub_nz[((hy - kR) >> 2) * 8 + ((hx - kR) >> 2)] = 1;   // benign race: every writer stores 1
+        if (interior) { sl += fabsf(sil - seg); mul += sil * seg; add += sil + seg; }
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { xs3[c][hy][hx] = vx[c]; ys3[c][hy][hx] = vy[c]; }
+    }
   }
   // Both SSIM inputs are masked images (x = rgb * alpha, y = target * seg): wherever the hand and the target
   // mask are absent the whole 42x42 halo is exactly zero, every windowed moment is +0 and the stencil
@@ -286,8 +311,11 @@ __global__ void __launch_bounds__(kLossThreads, 3) loss_fwd_kernel(HfrLossArgs a
   }
 }
 
+#ifndef HFR_LOSSB_UNROLLC
+#define HFR_LOSSB_UNROLLC 1
+#endif
 #ifndef HFR_LOSSB_MINB
-#define HFR_LOSSB_MINB 5
+#define HFR_LOSSB_MINB 3
 #endif
 __global__ void __launch_bounds__(kLossThreads, HFR_LOSSB_MINB) loss_bwd_kernel(HfrLossBwdArgs b) {
   const HfrLossArgs& a = b.f;
@@ -319,26 +347,51 @@ __global__ void __launch_bounds__(kLossThreads, HFR_LOSSB_MINB) loss_bwd_kernel(
   const float mR = a.sums[HFR_LOSS_SUM_R] * icnt, mT = a.sums[HFR_LOSS_SUM_T] * icnt;
   const float k_mrgb = w_mrgb * 2.0f * (mT - mR) * (-icnt);
   const float inv_scale = 1.0f / a.sil_scale;
-  // this thread's 4 pixels: column x0+lane, rows y0 + warp*4 + o
+  // this thread's 4 pixels: column x0+lane, rows y0 + warp*4 + o.  Everything the pointwise part needs (rendered
+  // RGBA, mask, target) is requested up front for all channels, so the round trips overlap each other and, on
+  // tiles with a live SSIM stencil, the halo loads and the stencil itself.
   const int gx = x0 + lane;
-  float sil[4], seg[4], s[4], gsil[4], grgb[4][3];
+  float sil[4], seg[4], rimg[4][3], timg[4][3];
   bool in[4];
-  const float mulv = a.sums[HFR_LOSS_NSUMS + n], addv = a.sums[HFR_LOSS_NSUMS + a.N + n];
-  const float den = addv - mulv;
 #pragma unroll
   for (int o = 0; o < 4; ++o) {
     const int gy = y0 + warp * 4 + o;
     in[o] = gx < a.W && gy < a.H;
-    sil[o] = seg[o] = s[o] = gsil[o] = 0.f;
+    sil[o] = seg[o] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) rimg[o][c] = timg[o][c] = 0.f;
     if (in[o]) {
       const size_t p = (size_t)gy * a.W + gx;
-      sil[o] = ld_sil(a, n, p, hw); seg[o] = __ldg(a.seg + n * hw + p);
-      s[o] = sil[o] * inv_scale;
+      if (a.nhwc) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(a.re_img + ((size_t)n * hw + p) * 4));
+        rimg[o][0] = q.x; rimg[o][1] = q.y; rimg[o][2] = q.z; sil[o] = q.w;
+      } else {
+        sil[o] = __ldg(a.re_sil + (size_t)n * hw + p);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) rimg[o][c] = __ldg(a.re_img + ((size_t)n * 3 + c) * hw + p);
+      }
+      seg[o] = __ldg(a.seg + n * hw + p);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) timg[o][c] = __ldg(a.imgs + ((size_t)n * 3 + c) * hw + p);
+    }
+  }
+  const float mulv = a.sums[HFR_LOSS_NSUMS + n], addv = a.sums[HFR_LOSS_NSUMS + a.N + n];
+  const float den = addv - mulv;
+  float gsil[4], grgb[4][3];
+#pragma unroll
+  for (int o = 0; o < 4; ++o) {
+    gsil[o] = 0.f;
+    if (in[o]) {
       const float d = sil[o] - seg[o];
       gsil[o] = w_sil * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) / ((float)b.n_global * (float)hw);
       gsil[o] += w_iou * (-1.0f / (float)b.n_global) * (seg[o] * den - mulv * (1.0f - seg[o])) / (den * den);
     }
   }
+#if HFR_LOSSB_UNROLLC
+#pragma unroll
+#else
+#pragma unroll 1
+#endif
   for (int c = 0; c < 3; ++c) {
     float r[4][3];
 #pragma unroll
@@ -346,18 +399,30 @@ __global__ void __launch_bounds__(kLossThreads, HFR_LOSSB_MINB) loss_bwd_kernel(
     if (ssim) {
       if (c > 0) __syncthreads();
       if ((a.W & 3) == 0) {
-        // rows are loaded as 12 aligned float4 covering columns x0-8 .. x0+39 (halo = x0-5 .. x0+36)
-        for (int i = tid; i < 3 * kLH * 12; i += kLossThreads) {
+        // rows are loaded as 12 aligned float4 covering columns x0-8 .. x0+39 (halo = x0-5 .. x0+36); all of a
+        // thread's requests go out before the first one is stored to shared memory
+        constexpr int kTot = 3 * kLH * 12, kIt = (kTot + kLossThreads - 1) / kLossThreads;   // 1512, 6
+        float4 v[kIt];
+#pragma unroll
+        for (int u = 0; u < kIt; ++u) {
+          const int i = tid + u * kLossThreads;
           const int m = i / (kLH * 12), rem = i - m * (kLH * 12), hy = rem / 12, q = rem - hy * 12;
           const int qy = y0 + hy - kR, qx = x0 - 8 + 4 * q;
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (qy >= 0 && qy < a.H && qx >= 0 && qx < a.W)
-            v = __ldg(reinterpret_cast<const float4*>(a.dmaps + ((size_t)n * 9 + c * 3 + m) * hw + (size_t)qy * a.W + qx));
-          const float e[4] = {v.x, v.y, v.z, v.w};
+          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (i < kTot && qy >= 0 && qy < a.H && qx >= 0 && qx < a.W)
+            v[u] = __ldg(reinterpret_cast<const float4*>(a.dmaps + ((size_t)n * 9 + c * 3 + m) * hw + (size_t)qy * a.W + qx));
+        }
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const int hx = 4 * q + t - 3;
-            if (hx >= 0 && hx < kLH) sd[m][hy][hx] = e[t];
+        for (int u = 0; u < kIt; ++u) {
+          const int i = tid + u * kLossThreads;
+          if (i < kTot) {
+            const int m = i / (kLH * 12), rem = i - m * (kLH * 12), hy = rem / 12, q = rem - hy * 12;
+            const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const int hx = 4 * q + t - 3;
+              if (hx >= 0 && hx < kLH) sd[m][hy][hx] = e[t];
+            }
           }
         }
       } else {
@@ -413,17 +478,17 @@ __global__ void __launch_bounds__(kLossThreads, HFR_LOSSB_MINB) loss_bwd_kernel(
     }
 #pragma unroll
     for (int o = 0; o < 4; ++o) {
-      grgb[o][c] = 0.f;
-      if (in[o]) {
-        const size_t p = (size_t)(y0 + warp * 4 + o) * a.W + gx;
-        const float rimg = ld_rgb(a, n, c, p, hw);
-        const float xv = rimg * s[o], yv = seg[o] * __ldg(a.imgs + ((size_t)n * 3 + c) * hw + p);
-        const float gS = r[o][0] + 2.0f * xv * r[o][1] + yv * r[o][2];
-        const float d = xv - yv;
-        const float grim = w_tex * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) * icnt + k_mrgb + w_ssim * (-icnt) * gS;
-        grgb[o][c] = grim * s[o];
-        gsil[o] += grim * rimg * inv_scale;
-      }
+      // channel c of the per-pixel registers (select chain: c is a runtime index)
+      const float rim = c == 0 ? rimg[o][0] : (c == 1 ? rimg[o][1] : rimg[o][2]);
+      const float tim = c == 0 ? timg[o][0] : (c == 1 ? timg[o][1] : timg[o][2]);
+      const float so = sil[o] * inv_scale;
+      const float xv = rim * so, yv = seg[o] * tim;
+      const float gS = r[o][0] + 2.0f * xv * r[o][1] + yv * r[o][2];
+      const float d = xv - yv;
+      const float grim = w_tex * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) * icnt + k_mrgb + w_ssim * (-icnt) * gS;
+      const float gc = in[o] ? grim * so : 0.f;
+      if (c == 0) grgb[o][0] = gc; else if (c == 1) grgb[o][1] = gc; else grgb[o][2] = gc;
+      if (in[o]) gsil[o] += grim * rim * inv_scale;
     }
   }
 #pragma unroll

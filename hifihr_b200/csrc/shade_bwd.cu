@@ -19,7 +19,11 @@
 
 namespace hfr {
 
-constexpr int kBwdThreads = 256, kBwdTileW = 16, kBwdTileH = 16;
+#ifndef HFR_BWD_THREADS
+#define HFR_BWD_THREADS 128
+#endif
+// CTA = 16 x (threads/16) pixels; the tile box from the rasterizer is in 16x16 tiles
+constexpr int kBwdThreads = HFR_BWD_THREADS, kBwdTileW = 16, kBwdTileH = kBwdThreads / 16;
 
 template <int KMAX>
 __device__ __forceinline__ float selk(const float (&a)[KMAX], int k) {
@@ -36,8 +40,11 @@ __device__ __forceinline__ int selk_i(const int (&a)[KMAX], int k) {
   return r;
 }
 
+#ifndef HFR_BWD_WARP_LIGHT
+#define HFR_BWD_WARP_LIGHT 0
+#endif
 #ifndef HFR_BWD_MINB
-#define HFR_BWD_MINB 4
+#define HFR_BWD_MINB (1024 / HFR_BWD_THREADS)
 #endif
 template <int KMAX>
 __global__ void __launch_bounds__(kBwdThreads, (KMAX <= 4 ? HFR_BWD_MINB : 1)) shade_bwd_kernel(HfrShadeBwdArgs a) {
@@ -63,7 +70,7 @@ __global__ void __launch_bounds__(kBwdThreads, (KMAX <= 4 ? HFR_BWD_MINB : 1)) s
   const bool dense = a.g_bary || a.g_zbuf || a.g_dists;
   if (a.tile_box && !dense) {   // tile outside this mesh's footprint: no fragment, no gradient
     const uint4 bx = __ldg(reinterpret_cast<const uint4*>(a.tile_box) + n);
-    const int tx = blockIdx.x, ty = blockIdx.y;
+    const int tx = blockIdx.x, ty = (blockIdx.y * kBwdTileH) >> 4;
     if (tx < (int)bx.x || tx > 255 - (int)bx.y || ty < (int)bx.z || ty > 255 - (int)bx.w) return;
   }
 
@@ -319,6 +326,19 @@ __global__ void __launch_bounds__(kBwdThreads, (KMAX <= 4 ? HFR_BWD_MINB : 1)) s
   if (phong && (a.g_light_dir || a.g_light_color)) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) { acc_dhat[c] = warp_sum(acc_dhat[c]); acc_lcol[c] = warp_sum(acc_lcol[c]); }
+#if HFR_BWD_WARP_LIGHT
+    // one set of atomics per warp, no CTA barrier: warps of a partially covered tile finish independently
+    if (lane == 0 && warp_any) {
+      const float t[6] = {acc_dhat[0], acc_dhat[1], acc_dhat[2], acc_lcol[0], acc_lcol[1], acc_lcol[2]};
+      float gd[3];
+      hfr_normalize_eps_bwd(dhat, dlen, t, gd);   // linear in t, so per-warp application sums to the same gradient
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        if (a.g_light_dir && gd[c] != 0.f) atomicAdd(a.g_light_dir + 3 * n + c, gd[c]);
+        if (a.g_light_color && t[3 + c] != 0.f) atomicAdd(a.g_light_color + 3 * n + c, t[3 + c]);
+      }
+    }
+#else
     if (lane == 0) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) { s_light[warp][c] = acc_dhat[c]; s_light[warp][3 + c] = acc_lcol[c]; }
@@ -337,6 +357,7 @@ __global__ void __launch_bounds__(kBwdThreads, (KMAX <= 4 ? HFR_BWD_MINB : 1)) s
         if (a.g_light_color && t[3 + c] != 0.f) atomicAdd(a.g_light_color + 3 * n + c, t[3 + c]);
       }
     }
+#endif
   }
 }
 
