@@ -22,16 +22,18 @@ class HfrHandModel(C.Structure):
                 ("center_joint", i32), ("C3", i32),
                 ("dirs", vp), ("v_template", vp), ("J_template", vp), ("J_shapedirs", vp),
                 ("pca_comps", vp), ("pose_mean", vp), ("parents", vp), ("skin_idx", vp), ("skin_w", vp),
-                ("tip_verts", vp), ("joint_order", vp)]
+                ("tip_verts", vp), ("joint_order", vp), ("palm_verts", i32 * 2)]
 
 
 class HfrManoFwdArgs(C.Structure):
-    _fields_ = [("B", i32), ("pose", vp), ("betas", vp), ("trans", vp), ("verts", vp), ("joints", vp)]
+    _fields_ = [("B", i32), ("pose", vp), ("betas", vp), ("trans", vp), ("verts", vp), ("joints", vp),
+                ("rots", vp), ("n_rot_in", i32), ("pose_off", i32), ("root_palm", i32)]
 
 
 class HfrManoBwdArgs(C.Structure):
     _fields_ = [("B", i32), ("pose", vp), ("betas", vp), ("trans", vp), ("g_verts", vp), ("g_joints", vp),
-                ("g_pose", vp), ("g_betas", vp), ("g_trans", vp)]
+                ("g_pose", vp), ("g_betas", vp), ("g_trans", vp),
+                ("rots", vp), ("n_rot_in", i32), ("pose_off", i32), ("root_palm", i32), ("g_rots", vp)]
 
 
 class HfrTopology(C.Structure):
@@ -138,7 +140,7 @@ def lib() -> C.CDLL:
         _lib.hfr_raster_workspace_bytes.argtypes = [C.c_int64]
         _lib.hfr_raster_tile_box.restype = C.c_void_p
         _lib.hfr_raster_tile_box.argtypes = [C.c_void_p, C.c_int64, C.c_int32]
-        if _lib.hfr_abi_version() != 1:
+        if _lib.hfr_abi_version() != 2:
             raise HfrError("libhifihr_b200.so ABI version mismatch")
     return _lib
 

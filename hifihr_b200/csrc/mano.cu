@@ -70,29 +70,39 @@ static size_t mano_smem_bytes(const HfrHandModel& m, bool bwd) {
 }
 
 // Phases 1-3 shared by forward and backward: pose -> R, pose map, J, G, A.
+// The first n_rot joints take their rotation matrix from `rots` (rot6d root / rotmat joints,
+// my_mano.py:355-373); the hand coefficients start at pose[poff].
 __device__ void mano_setup(const HfrHandModel& m, const ManoSmem& s, const float* __restrict__ pose,
-                           const float* __restrict__ betas) {
+                           const float* __restrict__ betas, const float* __restrict__ rots, int n_rot, int poff) {
   const int tid = threadIdx.x, NJ = m.NJ, NPOSE = 3 * (NJ - 1);
-  for (int i = tid; i < 3 * NJ; i += kThreads) {
-    float v;
-    if (i < 3) {
-      v = pose[i];
-    } else {
-      const int o = i - 3;
-      v = m.pose_mean ? m.pose_mean[o] : 0.0f;
-      if (m.NPC > 0) {
-        float h = 0.0f;
-        for (int k = 0; k < m.NPC; ++k) h += pose[3 + k] * m.pca_comps[k * NPOSE + o];
-        v += h;
+  if (n_rot < NJ) {
+    for (int i = tid; i < 3 * NJ; i += kThreads) {
+      float v;
+      if (i < 3) {
+        v = n_rot > 0 ? 0.0f : pose[i];
       } else {
-        v += pose[3 + o];
+        const int o = i - 3;
+        v = m.pose_mean ? m.pose_mean[o] : 0.0f;
+        if (m.NPC > 0) {
+          float h = 0.0f;
+          for (int k = 0; k < m.NPC; ++k) h += pose[poff + k] * m.pca_comps[k * NPOSE + o];
+          v += h;
+        } else {
+          v += pose[poff + o];
+        }
       }
+      s.full[i] = v;
     }
-    s.full[i] = v;
   }
   for (int i = tid; i < m.NS; i += kThreads) s.coef[i] = betas ? betas[i] : 0.0f;
   __syncthreads();
-  if (tid < NJ) hfr_rodrigues_fwd(s.full + 3 * tid, s.R + 9 * tid);
+  if (tid < NJ) {
+    if (tid < n_rot) {
+      for (int e = 0; e < 9; ++e) s.R[9 * tid + e] = rots[9 * tid + e];
+    } else {
+      hfr_rodrigues_fwd(s.full + 3 * tid, s.R + 9 * tid);
+    }
+  }
   for (int i = tid; i < 3 * NJ; i += kThreads) {
     float acc = m.J_template[i];
     for (int k = 0; k < m.NS; ++k) acc += m.J_shapedirs[i * m.NS + k] * s.coef[k];
@@ -185,19 +195,28 @@ __global__ void __launch_bounds__(kThreads) mano_fwd_kernel(HfrHandModel m, HfrM
   extern __shared__ __align__(16) float smem[];
   const ManoSmem s = carve(smem, m, false);
   const int b = blockIdx.x, tid = threadIdx.x, NJ = m.NJ;
-  mano_setup(m, s, a.pose + (size_t)b * pose_dim, a.betas ? a.betas + (size_t)b * m.NS : nullptr);
+  const int poff = a.pose_off > 0 ? a.pose_off : 3;
+  mano_setup(m, s, a.pose ? a.pose + (size_t)b * pose_dim : nullptr, a.betas ? a.betas + (size_t)b * m.NS : nullptr,
+             a.rots ? a.rots + (size_t)b * a.n_rot_in * 9 : nullptr, a.rots ? a.n_rot_in : 0, poff);
   mano_blend(m, s);
   float* tips = s.misc;        // NT*3
   float* off = s.misc + 48;    // 3
+  float* palm = s.misc + 52;   // 2*3: the two palm vertices (root_palm mode)
   if (tid < m.NT) skin_vertex(m, s, m.tip_verts[tid], tips + 3 * tid);
+  else if (a.root_palm && tid >= 32 && tid < 34) skin_vertex(m, s, m.palm_verts[tid - 32], palm + 3 * (tid - 32));
   __syncthreads();
+  // output joint value by source id: chain joint (its global translation), tip vertex, or the palm midpoint
+  auto joint_src = [&](int src, int c) -> float {
+    if (src >= NJ) return tips[3 * (src - NJ) + c];
+    if (src == 0 && a.root_palm) return (palm[c] + palm[3 + c]) / 2.0f;
+    return s.G[12 * src + c * 4 + 3];
+  };
   if (tid < 3) {
     float o = 0.0f;
     if (a.trans) {
       o = a.trans[(size_t)b * 3 + tid];
     } else if (m.center_joint >= 0) {
-      const int src = m.joint_order[m.center_joint];
-      o = -(src < NJ ? s.G[12 * src + tid * 4 + 3] : tips[3 * (src - NJ) + tid]);
+      o = -joint_src(m.joint_order[m.center_joint], tid);
     }
     off[tid] = o;
   }
@@ -213,9 +232,8 @@ __global__ void __launch_bounds__(kThreads) mano_fwd_kernel(HfrHandModel m, HfrM
   if (a.joints) {
     float* jout = a.joints + (size_t)b * (NJ + m.NT) * 3;
     for (int i = tid; i < (NJ + m.NT) * 3; i += kThreads) {
-      const int k = i / 3, c = i % 3, src = m.joint_order[k];
-      const float p = src < NJ ? s.G[12 * src + c * 4 + 3] : tips[3 * (src - NJ) + c];
-      jout[i] = p + off[c];
+      const int k = i / 3, c = i % 3;
+      jout[i] = joint_src(m.joint_order[k], c) + off[c];
     }
   }
 }
@@ -226,8 +244,10 @@ __global__ void __launch_bounds__(kThreads) mano_bwd_kernel(HfrHandModel m, HfrM
   const int b = blockIdx.x, tid = threadIdx.x, NJ = m.NJ, V = m.V, NJO = NJ + m.NT;
   const int lane = tid & 31, warp = tid >> 5, nwarps = kThreads / 32;
   const int NK = m.NS + 9 * (NJ - 1), NPOSE = 3 * (NJ - 1);
-  const float* pose = a.pose + (size_t)b * pose_dim;
-  mano_setup(m, s, pose, a.betas ? a.betas + (size_t)b * m.NS : nullptr);
+  const float* pose = a.pose ? a.pose + (size_t)b * pose_dim : nullptr;
+  const int poff = a.pose_off > 0 ? a.pose_off : 3, n_rot = a.rots ? a.n_rot_in : 0;
+  mano_setup(m, s, pose, a.betas ? a.betas + (size_t)b * m.NS : nullptr,
+             a.rots ? a.rots + (size_t)b * a.n_rot_in * 9 : nullptr, n_rot, poff);
   mano_blend(m, s);
   // backward-only shared arrays live in the tail of the dynamic allocation (after gv)
   float* gA = s.gv + m.C3;        // NJ*12, later reused as gG
@@ -268,23 +288,25 @@ __global__ void __launch_bounds__(kThreads) mano_bwd_kernel(HfrHandModel m, HfrM
   for (int i = tid; i < 3 * NJ; i += kThreads) gGt[i] = 0.0f;
   __syncthreads();
   if (tid == 0) {
-    if (gj_in) {
-      for (int k = 0; k < NJO; ++k) {
-        const int src = m.joint_order[k];
-        for (int c = 0; c < 3; ++c) {
-          if (src < NJ) gGt[3 * src + c] += gj_in[3 * k + c];
-          else s.gv[3 * m.tip_verts[src - NJ] + c] += gj_in[3 * k + c];
-        }
+    // route a gradient on output-joint source `src` to what produced it (chain joint, tip vertex, palm midpoint)
+    auto route = [&](int src, int c, float g) {
+      if (src >= NJ) {
+        s.gv[3 * m.tip_verts[src - NJ] + c] += g;
+      } else if (src == 0 && a.root_palm) {
+        s.gv[3 * m.palm_verts[0] + c] += 0.5f * g;
+        s.gv[3 * m.palm_verts[1] + c] += 0.5f * g;
+      } else {
+        gGt[3 * src + c] += g;
       }
+    };
+    if (gj_in) {
+      for (int k = 0; k < NJO; ++k)
+        for (int c = 0; c < 3; ++c) route(m.joint_order[k], c, gj_in[3 * k + c]);
     }
     if (a.trans) {
       if (a.g_trans) for (int c = 0; c < 3; ++c) a.g_trans[(size_t)b * 3 + c] = red[3 * nwarps + c];
     } else if (m.center_joint >= 0) {
-      const int src = m.joint_order[m.center_joint];
-      for (int c = 0; c < 3; ++c) {
-        if (src < NJ) gGt[3 * src + c] -= red[3 * nwarps + c];
-        else s.gv[3 * m.tip_verts[src - NJ] + c] -= red[3 * nwarps + c];
-      }
+      for (int c = 0; c < 3; ++c) route(m.joint_order[m.center_joint], c, -red[3 * nwarps + c]);
     }
   }
   __syncthreads();
@@ -395,8 +417,12 @@ __global__ void __launch_bounds__(kThreads) mano_bwd_kernel(HfrHandModel m, HfrM
   if (tid < NJ) {
     float g[9];
     for (int e = 0; e < 9; ++e) g[e] = gR[9 * tid + e] + (tid >= 1 ? gcoef[m.NS + 9 * (tid - 1) + e] : 0.0f);
-    float gvv[3];
-    hfr_rodrigues_bwd(s.full + 3 * tid, g, gvv);
+    float gvv[3] = {0.f, 0.f, 0.f};
+    if (tid < n_rot) {
+      if (a.g_rots) for (int e = 0; e < 9; ++e) a.g_rots[((size_t)b * n_rot + tid) * 9 + e] = g[e];
+    } else {
+      hfr_rodrigues_bwd(s.full + 3 * tid, g, gvv);
+    }
     // gfull aliases gGt, which thread 0 finished reading before the barrier above
     gfull[3 * tid] = gvv[0]; gfull[3 * tid + 1] = gvv[1]; gfull[3 * tid + 2] = gvv[2];
   }
@@ -408,16 +434,17 @@ __global__ void __launch_bounds__(kThreads) mano_bwd_kernel(HfrHandModel m, HfrM
     }
   }
   __syncthreads();
+  if (!a.g_pose || n_rot >= NJ) return;
   float* gp = a.g_pose + (size_t)b * pose_dim;
-  if (tid < 3) gp[tid] = gfull[tid];
+  if (tid < poff) gp[tid] = (n_rot == 0 && tid < 3) ? gfull[tid] : 0.0f;   // a matrix-driven root gets its gradient via g_rots
   if (m.NPC > 0) {
     for (int k = tid; k < m.NPC; k += kThreads) {
       float acc = 0.0f;
       for (int o = 0; o < NPOSE; ++o) acc += m.pca_comps[k * NPOSE + o] * gfull[3 + o];
-      gp[3 + k] = acc;
+      gp[poff + k] = acc;
     }
   } else {
-    for (int o = tid; o < NPOSE; o += kThreads) gp[3 + o] = gfull[3 + o];
+    for (int o = tid; o < NPOSE; o += kThreads) gp[poff + o] = gfull[3 + o];
   }
 }
 
@@ -439,8 +466,11 @@ extern "C" int hfr_mano_forward(const HfrHandModel* m, const HfrManoFwdArgs* a, 
   if (int rc = check_model(m)) return rc;
   HFR_CHECK_ARG(a && a->B >= 0, "mano_forward: null argument");
   if (a->B == 0) return HFR_OK;
-  HFR_CHECK_ARG(a->pose && a->verts, "mano_forward: null pointer");
-  const int pose_dim = 3 + (m->NPC > 0 ? m->NPC : 3 * (m->NJ - 1));
+  HFR_CHECK_ARG(a->verts && (a->pose || (a->rots && a->n_rot_in == m->NJ)), "mano_forward: null pointer");
+  HFR_CHECK_ARG(!a->rots || a->n_rot_in == 1 || a->n_rot_in == m->NJ, "mano_forward: n_rot_in must be 1 or NJ");
+  HFR_CHECK_ARG(!a->root_palm || (m->palm_verts[0] >= 0 && m->palm_verts[0] < m->V && m->palm_verts[1] >= 0 &&
+                                  m->palm_verts[1] < m->V), "mano_forward: root_palm needs palm_verts");
+  const int pose_dim = (a->pose_off > 0 ? a->pose_off : 3) + (m->NPC > 0 ? m->NPC : 3 * (m->NJ - 1));
   const size_t smem = mano_smem_bytes(*m, false);
   HFR_CHECK_ARG(smem <= 227 * 1024, "mano_forward: model too large for shared memory (%zu B)", smem);
   if (smem > 48 * 1024) cudaFuncSetAttribute(mano_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -453,8 +483,12 @@ extern "C" int hfr_mano_backward(const HfrHandModel* m, const HfrManoBwdArgs* a,
   if (int rc = check_model(m)) return rc;
   HFR_CHECK_ARG(a && a->B >= 0, "mano_backward: null argument");
   if (a->B == 0) return HFR_OK;
-  HFR_CHECK_ARG(a->pose && a->g_verts && a->g_pose, "mano_backward: null pointer");
-  const int pose_dim = 3 + (m->NPC > 0 ? m->NPC : 3 * (m->NJ - 1));
+  const bool all_rot = a->rots && a->n_rot_in == m->NJ;
+  HFR_CHECK_ARG(a->g_verts && ((a->pose && a->g_pose) || all_rot), "mano_backward: null pointer");
+  HFR_CHECK_ARG(!a->rots || a->n_rot_in == 1 || a->n_rot_in == m->NJ, "mano_backward: n_rot_in must be 1 or NJ");
+  HFR_CHECK_ARG(!a->root_palm || (m->palm_verts[0] >= 0 && m->palm_verts[0] < m->V && m->palm_verts[1] >= 0 &&
+                                  m->palm_verts[1] < m->V), "mano_backward: root_palm needs palm_verts");
+  const int pose_dim = (a->pose_off > 0 ? a->pose_off : 3) + (m->NPC > 0 ? m->NPC : 3 * (m->NJ - 1));
   const int NK = m->NS + 9 * (m->NJ - 1);
   const size_t extra = (size_t)(12 * m->NJ + 3 * m->NJ + 9 * m->NJ + ((NK + 3) & ~3) + 3 * m->NJ + 8) * sizeof(float);
   const size_t smem = mano_smem_bytes(*m, true) + extra;

@@ -156,7 +156,7 @@ class MyNIMBLELayer(nn.Module):
         pose, shape = hand_params["pose_params"], hand_params["shape_params"]
         hm, topo = self.consts(pose.device)
         rot = pose[:, :3]
-        verts, joints25 = ops.ManoFunction.apply(hm, pose[:, :hm.pose_dim], shape, None)
+        verts, joints25 = ops.ManoFunction.apply(hm, pose[:, :hm.pose_dim], shape, None, None, 3, False)
         out = {"nimble_joints": joints25, "joints": joints25[:, self.mano21], "verts": verts, "faces": self.faces,
                "mano_verts": verts[:, self.mano_map], "rot": rot}
         tex_img = None

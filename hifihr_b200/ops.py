@@ -28,7 +28,8 @@ class HandModelConsts:
     (HfrHandModel).  Built from the arrays ManoLayer.__init__ reads (utils/my_mano.py:277-313)."""
 
     def __init__(self, *, v_template, shapedirs, posedirs, J_regressor, weights, parents, pca_comps=None,
-                 pose_mean=None, tip_verts=(), joint_order=None, center_joint=-1, max_influences=8, device="cuda"):
+                 pose_mean=None, tip_verts=(), joint_order=None, center_joint=-1, max_influences=8, palm_verts=(-1, -1),
+                 device="cuda"):
         v_template = np.asarray(v_template, np.float64)
         shapedirs = np.asarray(shapedirs, np.float64)
         posedirs = np.asarray(posedirs, np.float64)
@@ -76,6 +77,7 @@ class HandModelConsts:
         s.pose_mean = None if self.pose_mean is None else self.pose_mean.data_ptr()
         s.parents, s.skin_idx, s.skin_w = self.parents.data_ptr(), self.skin_idx.data_ptr(), self.skin_w.data_ptr()
         s.tip_verts, s.joint_order = self.tip_verts.data_ptr(), self.joint_order.data_ptr()
+        s.palm_verts = (C.c_int32 * 2)(int(palm_verts[0]), int(palm_verts[1]))
         self.struct = s
         self.device = dev
 
@@ -133,16 +135,21 @@ class TopologyConsts:
 # ------------------------------------------------------------------------------------------------
 # raw launches (no autograd) — also used by the fused step
 # ------------------------------------------------------------------------------------------------
-def mano_forward_raw(hm: HandModelConsts, pose, betas, trans, verts, joints):
-    a = L.HfrManoFwdArgs(pose.shape[0], L.ptr(pose, F32, "pose"), L.ptr(betas, F32, "betas"),
-                         L.ptr(trans, F32, "trans"), L.ptr(verts, F32), L.ptr(joints, F32))
+def mano_forward_raw(hm: HandModelConsts, pose, betas, trans, verts, joints, rots=None, pose_off=3, root_palm=False):
+    """rots (B,n,3,3) with n = 1 (matrix-driven root, rot6d mode) or NJ (rotmat mode, pose may be None)."""
+    n_rot = 0 if rots is None else rots.shape[1]
+    a = L.HfrManoFwdArgs(verts.shape[0], L.ptr(pose, F32, "pose"), L.ptr(betas, F32, "betas"),
+                         L.ptr(trans, F32, "trans"), L.ptr(verts, F32), L.ptr(joints, F32), L.ptr(rots, F32, "rots"),
+                         n_rot, pose_off, int(root_palm))
     L.call("hfr_mano_forward", hm.struct, a)
 
 
-def mano_backward_raw(hm, pose, betas, trans, g_verts, g_joints, g_pose, g_betas, g_trans):
-    a = L.HfrManoBwdArgs(pose.shape[0], L.ptr(pose, F32), L.ptr(betas, F32), L.ptr(trans, F32),
+def mano_backward_raw(hm, pose, betas, trans, g_verts, g_joints, g_pose, g_betas, g_trans, rots=None, pose_off=3,
+                      root_palm=False, g_rots=None):
+    n_rot = 0 if rots is None else rots.shape[1]
+    a = L.HfrManoBwdArgs(g_verts.shape[0], L.ptr(pose, F32), L.ptr(betas, F32), L.ptr(trans, F32),
                          L.ptr(g_verts, F32), L.ptr(g_joints, F32), L.ptr(g_pose, F32), L.ptr(g_betas, F32),
-                         L.ptr(g_trans, F32))
+                         L.ptr(g_trans, F32), L.ptr(rots, F32), n_rot, pose_off, int(root_palm), L.ptr(g_rots, F32))
     L.call("hfr_mano_backward", hm.struct, a)
 
 
@@ -218,30 +225,38 @@ def gauss_taps(device):
 # autograd bridges
 # ------------------------------------------------------------------------------------------------
 class ManoFunction(torch.autograd.Function):
+    """pose (B, pose_off + ncomps) or None (all joints matrix-driven), rots (B,1|NJ,3,3) or None."""
+
     @staticmethod
-    def forward(ctx, hm: HandModelConsts, pose, betas, trans):
-        pose = _cu(pose)
+    def forward(ctx, hm: HandModelConsts, pose, betas, trans, rots=None, pose_off=3, root_palm=False):
+        pose = None if pose is None else _cu(pose)
         betas = None if betas is None else _cu(betas)
         trans = None if trans is None else _cu(trans)
-        B = pose.shape[0]
-        verts = torch.empty(B, hm.V, 3, device=pose.device, dtype=F32)
-        joints = torch.empty(B, hm.n_out_joints, 3, device=pose.device, dtype=F32)
-        mano_forward_raw(hm, pose, betas, trans, verts, joints)
-        ctx.hm = hm
-        ctx.save_for_backward(pose, betas, trans)
+        rots = None if rots is None else _cu(rots)
+        ref = pose if pose is not None else rots
+        B = ref.shape[0]
+        verts = torch.empty(B, hm.V, 3, device=ref.device, dtype=F32)
+        joints = torch.empty(B, hm.n_out_joints, 3, device=ref.device, dtype=F32)
+        mano_forward_raw(hm, pose, betas, trans, verts, joints, rots, pose_off, root_palm)
+        ctx.hm, ctx.cfg = hm, (pose_off, bool(root_palm), B)
+        ctx.save_for_backward(pose, betas, trans, rots)
         return verts, joints
 
     @staticmethod
     def backward(ctx, g_verts, g_joints):
-        pose, betas, trans = ctx.saved_tensors
+        pose, betas, trans, rots = ctx.saved_tensors
         hm = ctx.hm
-        g_verts = pose.new_zeros(pose.shape[0], hm.V, 3) if g_verts is None else _cu(g_verts)
+        pose_off, root_palm, B = ctx.cfg
+        ref = pose if pose is not None else rots
+        g_verts = ref.new_zeros(B, hm.V, 3) if g_verts is None else _cu(g_verts)
         g_joints = None if g_joints is None else _cu(g_joints)
-        g_pose = torch.empty_like(pose)
+        g_pose = None if pose is None else torch.empty_like(pose)
         g_betas = None if betas is None else torch.empty_like(betas)
         g_trans = None if trans is None else torch.empty_like(trans)
-        mano_backward_raw(hm, pose, betas, trans, g_verts, g_joints, g_pose, g_betas, g_trans)
-        return None, g_pose, g_betas, g_trans
+        g_rots = None if rots is None else torch.empty_like(rots)
+        mano_backward_raw(hm, pose, betas, trans, g_verts, g_joints, g_pose, g_betas, g_trans, rots, pose_off, root_palm,
+                          g_rots)
+        return None, g_pose, g_betas, g_trans, g_rots, None, None
 
 
 class GeomFunction(torch.autograd.Function):

@@ -22,7 +22,7 @@ extern "C" {
 #define HFR_EINVAL 1    /* bad argument (shape, K out of range, null pointer)      */
 #define HFR_ECUDA 2     /* CUDA runtime error at launch                            */
 #define HFR_EUNSUPPORTED 3
-#define HFR_ABI_VERSION 1
+#define HFR_ABI_VERSION 2
 
 #define HFR_MAX_JOINTS 32
 #define HFR_MAX_K 16
@@ -55,11 +55,18 @@ typedef struct HfrHandModel {
   const float* skin_w;     /* (NW, V) weight per influence (0 padded)                     */
   const int32_t* tip_verts;/* (NT)                                                        */
   const int32_t* joint_order; /* (NJ+NT) output joint k = chain∪tips[joint_order[k]]     */
+  int32_t palm_verts[2];   /* root_palm mode (my_mano.py:459-461): the two vertices whose midpoint replaces
+                              chain joint 0 in the joint output (MANO: 95, 22)            */
 } HfrHandModel;
 
 /* Replaces ManoLayer.forward (utils/my_mano.py:315-483) / MyMANOLayer.forward (:39-54).
  * pose (B, 3+NPC) [or (B, 3*NJ) when NPC==0], betas (B,NS) or NULL (mean shape);
- * trans (B,3) or NULL (then centre on center_joint).  verts (B,V,3), joints (B,NJ+NT,3). */
+ * trans (B,3) or NULL (then centre on center_joint).  verts (B,V,3), joints (B,NJ+NT,3).
+ * Non-default rotation inputs (my_mano.py:355-373): the first `n_rot_in` chain joints take their
+ * rotation MATRIX from rots (B,n_rot_in,3,3) instead of Rodrigues — 1 = root_rot_mode 'rot6d' (the host
+ * turns the 6-D vector into a matrix), NJ = joint_rot_mode 'rotmat' (pose may then be NULL).  `pose_off`
+ * = number of leading pose columns that belong to the root (3 axis-angle, 6 rot6d); 0 means 3.
+ * root_palm != 0: output joint sourced from chain joint 0 becomes the palm midpoint (:459-461). */
 typedef struct HfrManoFwdArgs {
   int32_t B;
   const float* pose;
@@ -67,11 +74,14 @@ typedef struct HfrManoFwdArgs {
   const float* trans;
   float* verts;
   float* joints;
+  const float* rots;
+  int32_t n_rot_in, pose_off, root_palm;
 } HfrManoFwdArgs;
 int hfr_mano_forward(const HfrHandModel* m, const HfrManoFwdArgs* a, void* stream);
 
 /* Backward of the above (autograd of my_mano.py:315-483).  g_joints may be NULL.
- * Outputs g_pose (B,3+NPC), g_betas (B,NS) (may be NULL), g_trans (B,3) (may be NULL). */
+ * Outputs g_pose (B,pose_off+NPC) (columns of a matrix-driven root are zeroed; may be NULL when
+ * n_rot_in == NJ), g_betas (B,NS) (may be NULL), g_trans (B,3) (may be NULL). */
 typedef struct HfrManoBwdArgs {
   int32_t B;
   const float* pose;
@@ -82,6 +92,9 @@ typedef struct HfrManoBwdArgs {
   float* g_pose;
   float* g_betas;
   float* g_trans;
+  const float* rots;                /* as in the forward                                   */
+  int32_t n_rot_in, pose_off, root_palm;
+  float* g_rots;                    /* (B,n_rot_in,3,3) or NULL                            */
 } HfrManoBwdArgs;
 int hfr_mano_backward(const HfrHandModel* m, const HfrManoBwdArgs* a, void* stream);
 

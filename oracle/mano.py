@@ -40,9 +40,43 @@ def rodrigues(axisang: torch.Tensor) -> torch.Tensor:
     return R.view(-1, 3, 3)
 
 
+def _unit(v):
+    """utils/manopth/rot6d.py:54-60."""
+    return v / torch.sqrt((v * v).sum(1, keepdim=True)).clamp_min(1e-8)
+
+
+def ortho6d_to_matrix(p, robust=False):
+    """utils/manopth/rot6d.py:4-25 (Gram-Schmidt) and :27-51 (robust variant); columns are (x, y, z)."""
+    a, b = p[:, 0:3], p[:, 3:6]
+    if robust:
+        a, b = _unit(a), _unit(b)
+        mid, orth = _unit(a + b), _unit(a - b)
+        x, y = _unit(mid + orth), _unit(mid - orth)
+        z = _unit(torch.linalg.cross(x, y))
+    else:
+        x = _unit(a)
+        z = _unit(torch.linalg.cross(x, b))
+        y = torch.linalg.cross(z, x)
+    return torch.stack([x, y, z], 2)
+
+
+def project_rotations(M):
+    """utils/manopth/rotproj.py:4-23: U V^T of every 3x3 block, third column negated when det < 0."""
+    out = []
+    for m in M.reshape(-1, 3, 3):
+        U, _, V = torch.svd(m)
+        R = U @ V.t()
+        if torch.det(R) < 0:
+            R = torch.cat([R[:, :2], -R[:, 2:]], 1)
+        out.append(R)
+    return torch.stack(out).view(M.shape)
+
+
 class ManoOracle:
     def __init__(self, mano: dict, ncomps=48, flat_hand_mean=False, center_idx=9, use_pca=True,
-                 dtype=torch.float32):
+                 dtype=torch.float32, root_rot_mode="axisang", joint_rot_mode="axisang", robust_rot=False):
+        self.root_rot_mode, self.joint_rot_mode, self.robust_rot = root_rot_mode, joint_rot_mode, robust_rot
+        self.rot = 3 if root_rot_mode == "axisang" else 6
         t = lambda a: torch.tensor(np.asarray(a, dtype=np.float64)).to(dtype)  # noqa: E731
         self.dtype = dtype
         self.center_idx = center_idx
@@ -58,14 +92,25 @@ class ManoOracle:
         self.hands_mean = t(hm)[None]
         self.selected_comps = t(mano["hands_components"][:ncomps])
 
-    def __call__(self, pose, betas, trans=None):
+    def __call__(self, pose, betas, trans=None, root_palm=False, share_betas=False):
         B = pose.shape[0]
         dt = self.dtype
-        hand = pose[:, 3:3 + self.ncomps]
-        if self.use_pca:
-            hand = hand @ self.selected_comps
-        full = torch.cat([pose[:, :3], self.hands_mean + hand], 1)            # (B,48)
-        R = rodrigues(full.reshape(-1, 3)).view(B, 16, 3, 3)
+        if not self.use_pca and self.joint_rot_mode == "rotmat":             # my_mano.py:362-373
+            R = project_rotations(pose)
+        else:
+            hand = pose[:, self.rot:self.rot + self.ncomps]
+            if self.use_pca:
+                hand = hand @ self.selected_comps
+            hand = self.hands_mean + hand
+            if self.root_rot_mode == "axisang":                                # :349-354
+                R = rodrigues(torch.cat([pose[:, :3], hand], 1).reshape(-1, 3)).view(B, 16, 3, 3)
+            else:                                                              # :355-361
+                R = torch.cat([ortho6d_to_matrix(pose[:, :6], self.robust_rot)[:, None],
+                               rodrigues(hand.reshape(-1, 3)).view(B, 15, 3, 3)], 1)
+        if betas is None or betas.numel() == 1:                                # :376-381 mean shape
+            betas = torch.zeros(B, 10, dtype=dt)
+        elif share_betas:                                                      # :384-385
+            betas = betas.mean(0, keepdim=True).expand(B, 10)
         pose_map = (R[:, 1:] - torch.eye(3, dtype=dt)).reshape(B, 135)
         v_shaped = torch.einsum("vck,bk->bvc", self.shapedirs, betas) + self.v_template
         J = torch.einsum("jv,bvc->bjc", self.J_regressor, v_shaped)           # (B,16,3)
@@ -87,8 +132,11 @@ class ManoOracle:
         T = torch.einsum("bjrc,vj->bvrc", A, self.weights)                     # (B,778,4,4)
         vh = torch.cat([v_posed, torch.ones(B, v_posed.shape[1], 1, dtype=dt)], 2)
         verts = torch.einsum("bvrc,bvc->bvr", T, vh)[..., :3]
-        jtr = torch.cat([G[:, :, :3, 3], verts[:, TIP_VERTS_RIGHT]], 1)[:, JOINT_REORDER]
-        if trans is None:
+        chain = G[:, :, :3, 3]
+        if root_palm:                                                          # :459-461
+            chain = torch.cat([((verts[:, 95] + verts[:, 22]) / 2)[:, None], chain[:, 1:]], 1)
+        jtr = torch.cat([chain, verts[:, TIP_VERTS_RIGHT]], 1)[:, JOINT_REORDER]
+        if trans is None or bool(torch.norm(trans) == 0):                      # :471
             if self.center_idx is not None:
                 c = jtr[:, self.center_idx:self.center_idx + 1]
                 jtr = jtr - c

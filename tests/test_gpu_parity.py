@@ -53,6 +53,41 @@ def test_mano_matches_reference_golden(hf):
     assert j0[0, 9].abs().max() == 0
 
 
+def test_mano_modes_match_reference_golden(hf):
+    """rot6d / robust rot6d root, rotmat joints, axis-angle without PCA, root_palm, share_betas, th_trans and the
+    mean-shape default (my_mano.py:341-385, 459-461, 471-478) against golden vectors of the unmodified reference.
+    verts/joints 1e-6 m abs (rotmat: 2e-6, a batched device SVD replaces the reference's per-matrix CPU SVD);
+    gradients 1e-3 of the tensor's max magnitude."""
+    from oracle.gen_golden import MODE_CASES
+    z = np.load(os.path.join(GOLD, "mano_modes_reference.npz"))
+    for name, (ckw, _, fkw) in MODE_CASES.items():
+        kw = dict(ncomps=48, flat_hand_mean=False, center_idx=9)
+        kw.update(ckw)
+        layer = hf.ManoLayer(**kw)
+        pose = torch.tensor(z[f"{name}.pose"], device=DEV, requires_grad=True)
+        beta = torch.tensor(z[f"{name}.beta"], device=DEV, requires_grad=True)
+        fw = {}
+        if fkw.get("root_palm"):
+            fw["root_palm"] = torch.Tensor([1])
+        if fkw.get("share_betas"):
+            fw["share_betas"] = torch.Tensor([1])
+        trans = None
+        if fkw.get("trans"):
+            trans = torch.tensor(z[f"{name}.trans"], device=DEV, requires_grad=True)
+            fw["th_trans"] = trans
+        v, j = layer(pose, torch.zeros(1) if fkw.get("mean_shape") else beta, **fw)
+        tol = 2e-6 if name == "rotmat" else 1e-6
+        assert (v.detach().cpu() - torch.tensor(z[f"{name}.verts"])).abs().max() < tol, name
+        assert (j.detach().cpu() - torch.tensor(z[f"{name}.joints"])).abs().max() < tol, name
+        ((v * torch.tensor(z[f"{name}.g_verts"], device=DEV)).sum()
+         + (j * torch.tensor(z[f"{name}.g_joints"], device=DEV)).sum()).backward()
+        assert rel_err(pose.grad, torch.tensor(z[f"{name}.g_pose"])) < 1e-3, name
+        if f"{name}.g_beta" in z.files:
+            assert rel_err(beta.grad, torch.tensor(z[f"{name}.g_beta"])) < 1e-3, name
+        if trans is not None:
+            assert rel_err(trans.grad, torch.tensor(z[f"{name}.g_trans"])) < 1e-3, name
+
+
 def test_mano_vs_oracle_many_samples(hf, mano):
     orc = ManoOracle(mano)
     layer = hf.ManoLayer(center_idx=9, flat_hand_mean=False, ncomps=48)

@@ -30,6 +30,30 @@ def test_mano_oracle_matches_reference_golden(mano):
     assert (beta.grad - torch.tensor(z["g_beta"])).abs().max() < 2e-5 * np.abs(z["g_beta"]).max()
 
 
+def test_mano_oracle_modes_match_reference_golden(mano):
+    """Non-default modes of ManoLayer.forward (my_mano.py:341-385, 459-461, 471-478): golden vectors from the
+    unmodified reference (oracle/gen_golden.py::mano_mode_cases)."""
+    from oracle.gen_golden import MODE_CASES
+    z = np.load(os.path.join(GOLD, "mano_modes_reference.npz"))
+    for name, (ckw, _, fkw) in MODE_CASES.items():
+        kw = dict(ncomps=48, flat_hand_mean=False, center_idx=9)
+        kw.update(ckw)
+        orc = ManoOracle(mano, **kw)
+        pose = torch.tensor(z[f"{name}.pose"], requires_grad=True)
+        beta = torch.tensor(z[f"{name}.beta"], requires_grad=True)
+        trans = torch.tensor(z[f"{name}.trans"], requires_grad=True) if fkw.get("trans") else None
+        v, j = orc(pose, torch.zeros(1) if fkw.get("mean_shape") else beta, trans=trans,
+                   root_palm=bool(fkw.get("root_palm")), share_betas=bool(fkw.get("share_betas")))
+        assert (v.detach() - torch.tensor(z[f"{name}.verts"])).abs().max() < 2e-7, name
+        assert (j.detach() - torch.tensor(z[f"{name}.joints"])).abs().max() < 2e-7, name
+        ((v * torch.tensor(z[f"{name}.g_verts"])).sum() + (j * torch.tensor(z[f"{name}.g_joints"])).sum()).backward()
+        assert (pose.grad - torch.tensor(z[f"{name}.g_pose"])).abs().max() < 5e-5 * np.abs(z[f"{name}.g_pose"]).max(), name
+        if f"{name}.g_beta" in z.files:
+            assert (beta.grad - torch.tensor(z[f"{name}.g_beta"])).abs().max() < 5e-5 * np.abs(z[f"{name}.g_beta"]).max(), name
+        if trans is not None:
+            assert (trans.grad - torch.tensor(z[f"{name}.g_trans"])).abs().max() < 1e-4, name
+
+
 def test_generic_lbs_oracle_matches_mano_oracle(mano):
     """oracle/lbs.py (any skeleton; used for the NIMBLE-shaped layer) restricted to MANO's constants must be the
     pinned MANO oracle."""
@@ -147,7 +171,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.ENTRY_POINTS), declared ^ set(_lib.ENTRY_POINTS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.hfr_abi_version() == 1
+    assert lib.hfr_abi_version() == 2
 
 
 def test_ctypes_struct_sizes_match_header():
