@@ -155,6 +155,8 @@ def run_ours(args, cfg):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     B = cfg["B"] if cfg["B"] is not None else 4096 // world
     if args.batch:
@@ -178,8 +180,8 @@ def run_ours(args, cfg):
         pose, betas, focal, prpp, root, ldir, lcol, imgs, seg = tensors
         step.forward(pose, betas, focal, prpp, root, ldir, lcol, imgs, seg)
         hdist.all_reduce_loss_sums(step.sums)          # global means for the mean-RGB term (no-op at N=1)
-        step.backward(pose, betas, focal, prpp, root)
-        hdist.all_reduce_shared_grads(step.g_texture)  # gradient of the shared texture (no-op at N=1)
+        # gradient of the shared texture: all-reduced while the geometry / hand-layer backward run (no-op at N=1)
+        step.backward(pose, betas, focal, prpp, root, shared_grad_hook=hdist.all_reduce_shared_grads_async)
 
     def barrier():
         if world > 1:

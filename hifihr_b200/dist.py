@@ -36,6 +36,20 @@ def all_reduce_shared_grads(*grads: torch.Tensor, group=None):
             dist.all_reduce(g, group=group)
 
 
+def all_reduce_shared_grads_async(*grads: torch.Tensor, group=None):
+    """Start the all-reduce of the shared-parameter gradients and return the work handles (empty at world size 1).
+    FusedHandStep.backward calls this right after the shade/rasterize backward, so the NVLink transfer overlaps the
+    geometry and hand-layer backward kernels; `wait_all` makes the current stream wait for it."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        return [dist.all_reduce(g, group=group, async_op=True) for g in grads]
+    return []
+
+
+def wait_all(works):
+    for w in works:
+        w.wait()
+
+
 def loss_terms_from_sums(sums: torch.Tensor, n_local: int, n_global: int, H: int, W: int, group=None):
     """[texture, mrgb, ssim_tex, sil, iou] from all-reduced sums (IoU: local sum of per-sample IoUs, reduced)."""
     cnt = float(n_global * 3 * H * W)

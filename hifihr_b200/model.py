@@ -184,7 +184,9 @@ class FusedHandStep:
         L.call("hfr_loss_forward", self._loss_args)
         self._shade_args = s
 
-    def backward(self, pose, betas, focal, prp, root_xyz):
+    def backward(self, pose, betas, focal, prp, root_xyz, shared_grad_hook=None):
+        """shared_grad_hook(g_texture) -> work handles: called as soon as the gradient of the shared texture is
+        complete (after the shade/rasterize backward), waited on after the last kernel of the step is enqueued."""
         B, S = self.B, self.S
         a = L.HfrLossBwdArgs(self._loss_args, L.ptr(self.w), L.ptr(self.gauss), self.n_global * 3 * S * S,
                              self.n_global, L.ptr(self.g_image), None)
@@ -195,9 +197,12 @@ class FusedHandStep:
                                L.ptr(self.g_vn), L.ptr(self.g_texture), L.ptr(self.g_light_dir),
                                L.ptr(self.g_light_color), ops.raster_tile_box(self.ws, B * self.topo.F, B))
         L.call("hfr_shade_backward", sb)
+        works = shared_grad_hook(self.g_texture) if shared_grad_hook is not None else ()
         ops.geom_backward_raw(self.topo, self.verts, 9, root_xyz, focal, prp, None, None, self.g_view, self.g_ndc,
                               self.g_vn, self.g_verts)
         ops.mano_backward_raw(self.hm, pose, betas, None, self.g_verts, None, self.g_pose, self.g_betas, None)
+        for w in works:
+            w.wait()
 
     def step(self, pose, betas, focal, prp, root_xyz, light_dir, light_color, imgs, seg):
         self.forward(pose, betas, focal, prp, root_xyz, light_dir, light_color, imgs, seg)

@@ -505,3 +505,18 @@ def test_full_size_properties_c2(hf, mano):
         ref = raster_c.rasterize_naive(fv, [0], [1538], S, step.blur, K, threads=8)
         assert ((p2f[n].cpu() - n * 1538).where(p2f[n].cpu() >= 0, torch.tensor(-1)) == ref[0][0]).all()
         assert (z[n].cpu() == ref[1][0]).all() and (step.dists[n].cpu() == ref[3][0]).all()
+
+
+# ------------------------------------------------------------------------------------------ multi-GPU
+def test_two_gpu_sharded_step_matches_single_process(hf):
+    """NCCL, world size 2: batch slices + the two all-reduces reproduce the single-process step
+    (tools/multi_gpu_check.py; loss terms 2e-6 abs, gradients 1e-4 of the tensor's max)."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (the gloo twin of this test runs on CPU: tests/test_dist_gloo.py)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(29600 + os.getpid() % 300), os.path.join(root, "tools", "multi_gpu_check.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
