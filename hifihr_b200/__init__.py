@@ -13,7 +13,7 @@ All compute runs in hand-written CUDA kernels behind the C-ABI of include/hifihr
 (libhifihr_b200.so, loaded with ctypes).  There is no CPU / PyTorch fallback.
 """
 from ._lib import ENTRY_POINTS, LIB_PATH, HfrError  # noqa: F401
-from .losses import LossFunction  # noqa: F401
+from .losses import LossFunction, trans_proj_j2d  # noqa: F401
 from .mano import ManoLayer, MyMANOLayer, xyz_from_vertice  # noqa: F401
 from .model import FusedHandStep, HandRenderModel, get_ndc_fx_fy_cx_cy  # noqa: F401
 from .renderer import (BlendParams, DirectionalLights, Fragments, HardPhongShader, Materials,  # noqa: F401

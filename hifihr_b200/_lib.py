@@ -112,12 +112,26 @@ class HfrLossBwdArgs(C.Structure):
     _fields_ = [("f", HfrLossArgs), ("w", vp), ("gauss", vp), ("count_global", i64), ("n_global", i32), ("g_re_img", vp), ("g_re_sil", vp)]
 
 
+class HfrKeypointArgs(C.Structure):
+    _fields_ = [("B", i32), ("NJ", i32), ("V", i32), ("F", i32), ("l2", i32), ("NB", i32), ("scale_a", i32), ("scale_b", i32),
+                ("scale_len", f32), ("joints", vp), ("root_xyz", vp), ("Kmat", vp), ("verts", vp), ("faces", vp),
+                ("joints_gt", vp), ("j2d_gt", vp), ("verts_gt", vp), ("conf", vp), ("bone_parent", vp), ("bone_child", vp),
+                ("j2d", vp), ("sums", vp)]
+
+
+class HfrKeypointBwdArgs(C.Structure):
+    _fields_ = [("f", HfrKeypointArgs), ("w", vp), ("n_global", i32), ("g_j2d_in", vp), ("g_joints", vp), ("g_verts", vp)]
+
+
 LOSS_NSUMS = 8
+KP_NSUMS = 8
+KP_TERMS = ("joint_2d", "joint_3d", "vert_3d", "bone_direc", "bone_direc_3d", "edge_length", "mscale")
 ENTRY_POINTS = [
     "hfr_last_error", "hfr_abi_version", "hfr_device_ok", "hfr_mano_forward", "hfr_mano_backward",
     "hfr_geom_forward", "hfr_geom_backward", "hfr_raster_workspace_bytes", "hfr_raster_forward",
     "hfr_raster_backward", "hfr_raster_tile_box", "hfr_shade_forward", "hfr_shade_backward", "hfr_raster_shade_forward",
     "hfr_pool_forward", "hfr_pool_backward", "hfr_loss_forward", "hfr_loss_backward",
+    "hfr_keypoint_forward", "hfr_keypoint_backward",
 ]
 
 _lib = None

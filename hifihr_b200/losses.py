@@ -4,8 +4,10 @@
 Implemented terms: 'texture', 'mrgb', 'ssim_tex' (losses.py:355-378; computed whenever the
 outputs hold re_img and re_sil, as in the reference), 'sil' (:399-403) and 'iou' (:405-408).
 All five come out of ONE forward kernel pass (csrc/loss.cu) and one backward pass.
-Terms that do not depend on the render (keypoints, regularisers, VGG perceptual) are out of
-the hot path's scope and raise if requested.
+The keypoint / mesh terms next to the render path — 'joint_2d', 'joint_3d',
+'vert_3d', 'bone_direc', 'bone_direc_3d', 'edge_length' (losses.py:244-289) and 'mscale' (:293-299) — come out
+of one more kernel pair (csrc/keypoint.cu).  `trans_proj_j2d` is utils/traineval_util.py:338-354.
+Other terms (pose / shape priors, Laplacian, VGG perceptual, heat-maps) are out of scope and raise if requested.
 """
 from __future__ import annotations
 
@@ -14,6 +16,19 @@ import torch
 from . import ops
 
 _RENDER_TERMS = ("texture", "mrgb", "ssim_tex", "sil", "iou")
+_KEYPOINT_TERMS = ("joint_2d", "joint_3d", "vert_3d", "bone_direc", "bone_direc_3d", "edge_length", "mscale")
+_KP_LAMBDA = dict(joint_2d="lambda_j2d_gt", joint_3d="lambda_j3d", vert_3d="lambda_vert_3d", bone_direc="lambda_bone_direc",
+                  bone_direc_3d="lambda_bone_direc_3d", edge_length="lambda_edge_len", mscale="lambda_mscale")
+
+
+def trans_proj_j2d(outputs, Ks_this, scales=None, is_ortho=False, root_xyz=None, which_joints="joints"):
+    """utils/traineval_util.py:338-354 for the perspective / unscaled call the training loop makes
+    (train_hrnet.py:83): j2d = proj_func(outputs[which_joints] + root_xyz, Ks)."""
+    if scales is not None or is_ortho:
+        raise NotImplementedError("trans_proj_j2d: only the perspective, unscaled path (train_hrnet.py:83)")
+    j3d = outputs[which_joints]
+    _, j2d = ops.KeypointLossFunction.apply(j3d, None, root_xyz, Ks_this, None, None, None, None, None, 0)
+    return j2d
 
 
 class LossFunction:
@@ -24,9 +39,12 @@ class LossFunction:
 
     def __call__(self, examples, outputs, loss_used, dat_name, args) -> dict:
         loss_dic = {}
-        unknown = [k for k in loss_used if k not in _RENDER_TERMS]
+        unknown = [k for k in loss_used if k not in _RENDER_TERMS + _KEYPOINT_TERMS]
         if unknown:
             raise NotImplementedError(f"loss terms outside the render hot path: {unknown}")
+        kp = [k for k in loss_used if k in _KEYPOINT_TERMS]
+        if kp:
+            loss_dic.update(self._keypoint_terms(examples, outputs, kp, args))
         if "re_img" in outputs and "re_sil" in outputs:
             seg = examples["segms_gt"].float()
             terms = ops.RenderLossFunction.apply(outputs["re_img"], outputs["re_sil"], examples["imgs"], seg,
@@ -41,3 +59,33 @@ class LossFunction:
         elif "sil" in loss_used or "iou" in loss_used:
             raise AssertionError("silhouette loss needs rendered sil and gt sil")
         return loss_dic
+
+    @staticmethod
+    def _keypoint_terms(examples, outputs, used, args):
+        """One kernel pass for every requested keypoint / mesh term; same asserts as losses.py:245-286.  The 2-D
+        terms use the projection j2d = proj_func(joints + root_xyz, Ks) (what train_hrnet.py:83 stores in
+        outputs['j2d']) fused into the same kernel, so they need examples['Ks'] and examples['root_xyz']."""
+        need2d = "joint_2d" in used or "bone_direc" in used
+        need3d = "joint_3d" in used or "bone_direc_3d" in used
+        needv = "vert_3d" in used or "edge_length" in used
+        if need2d:
+            assert "j2d_gt" in examples and ("j2d" in outputs), "Using joint_2d in losses, but j2d_gt or j2d are not provided."
+        if need3d:
+            assert "joints" in outputs and "joints" in examples, "Using joint_3d in losses, but joints or joints_gt are not provided."
+        if needv:
+            assert "mano_verts" in outputs and "verts" in examples, "Using vert_3d in losses, but verts or verts_gt are not provided."
+        if "edge_length" in used:
+            assert "mano_faces" in outputs, "Using edge_length but verts or faces not outputted."
+        if "mscale" in used:
+            assert "joints" in outputs, "Using mscale but joints not outputted."
+        if need2d and not ("Ks" in examples and "root_xyz" in examples):
+            raise NotImplementedError("2-D keypoint terms need examples['Ks'] and examples['root_xyz'] (the projection is fused)")
+        l2 = {"L1": 0, "L2": 1}[getattr(args, "base_loss_fn", "L1")]
+        faces = outputs["mano_faces"][0] if needv else None
+        terms, _ = ops.KeypointLossFunction.apply(
+            outputs["joints"], outputs["mano_verts"] if needv else None,
+            examples["root_xyz"] if need2d else None, examples["Ks"] if need2d else None,
+            examples["joints"] if need3d else None, examples["j2d_gt"] if need2d else None,
+            examples["verts"] if needv else None, None, faces, l2)
+        idx = {k: i for i, k in enumerate(_KEYPOINT_TERMS)}
+        return {k: getattr(args, _KP_LAMBDA[k]) * terms[idx[k]] for k in used}

@@ -441,3 +441,72 @@ class RenderLossFunction(torch.autograd.Function):
         a = L.HfrLossBwdArgs(f, L.ptr(w, F32), L.ptr(gauss, F32), N * 3 * H * W, N, L.ptr(g_img, F32), L.ptr(g_sil, F32))
         L.call("hfr_loss_backward", a)
         return g_img, g_sil, None, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------
+# keypoints + mesh regularisers
+# ------------------------------------------------------------------------------------------------
+BONE_CHILD = list(range(1, 21))                                       # utils/losses_util.py:226-245: bone i ends at joint i+1
+BONE_PARENT = [0 if (c - 1) % 4 == 0 else c - 1 for c in BONE_CHILD]  # ... and starts at the wrist or the previous joint
+_BONES = {}
+
+
+def bone_tables(device):
+    key = str(device)
+    if key not in _BONES:
+        _BONES[key] = (torch.tensor(BONE_PARENT, dtype=I32, device=device), torch.tensor(BONE_CHILD, dtype=I32, device=device))
+    return _BONES[key]
+
+
+def keypoint_args(joints, root_xyz, Ks, verts, faces, joints_gt, j2d_gt, verts_gt, conf, l2, j2d, sums, mscale=True):
+    B, NJ = joints.shape[0], joints.shape[1]
+    bp, bc = bone_tables(joints.device)
+    nb = bp.shape[0] if NJ == 21 else 0          # the bone tables are the 21-joint FreiHAND skeleton's
+    V = verts.shape[1] if verts is not None else 0
+    F = faces.shape[0] if faces is not None else 0
+    return L.HfrKeypointArgs(B, NJ, V, F, int(l2), nb, 9 if (mscale and NJ > 10) else -1, 10, 0.0282,
+                             L.ptr(joints, F32, "joints"), L.ptr(root_xyz, F32, "root_xyz"), L.ptr(Ks, F32, "Ks"),
+                             L.ptr(verts, F32, "verts"), L.ptr(faces, I32, "faces"), L.ptr(joints_gt, F32, "joints_gt"),
+                             L.ptr(j2d_gt, F32, "j2d_gt"), L.ptr(verts_gt, F32, "verts_gt"), L.ptr(conf, F32, "conf"),
+                             L.ptr(bp, I32), L.ptr(bc, I32), L.ptr(j2d, F32), L.ptr(sums, F32))
+
+
+class KeypointLossFunction(torch.autograd.Function):
+    """(joints, verts) -> (terms (7,) [joint_2d, joint_3d, vert_3d, bone_direc, bone_direc_3d, edge_length, mscale]
+    unweighted, j2d (B,NJ,2)).  A term whose ground truth is None is 0; j2d is empty when Ks is None."""
+
+    @staticmethod
+    def forward(ctx, joints, verts, root_xyz, Ks, joints_gt, j2d_gt, verts_gt, conf, faces, l2):
+        c = lambda t: None if t is None else _cu(t)  # noqa: E731
+        joints, verts, joints_gt, j2d_gt, verts_gt = c(joints), c(verts), c(joints_gt), c(j2d_gt), c(verts_gt)
+        B, NJ = joints.shape[0], joints.shape[1]
+        dev = joints.device
+        root_xyz = None if root_xyz is None else _cu(root_xyz.reshape(B, 3))
+        Ks = None if Ks is None else _cu(Ks[:, :3, :3])
+        conf = None if conf is None else _cu(conf.reshape(B, NJ))
+        faces = None if faces is None else faces.to(I32).contiguous()
+        j2d = torch.empty(B, NJ, 2, dtype=F32, device=dev) if Ks is not None else None
+        sums = torch.zeros(L.KP_NSUMS, dtype=F32, device=dev)
+        a = keypoint_args(joints, root_xyz, Ks, verts, faces, joints_gt, j2d_gt, verts_gt, conf, l2, j2d, sums)
+        L.call("hfr_keypoint_forward", a)
+        V, F, NB = a.V, a.F, a.NB
+        cnt = torch.tensor([B * NJ * 2, B * NJ * 3, max(B * V * 3, 1), max(B * NB, 1), max(B * NB, 1), max(B * F * 3, 1), B],
+                           dtype=F32, device=dev)
+        ctx.l2 = int(l2)
+        ctx.save_for_backward(joints, verts, root_xyz, Ks, joints_gt, j2d_gt, verts_gt, conf, faces)
+        return sums[:7] / cnt, (j2d if j2d is not None else joints.new_zeros(0))
+
+    @staticmethod
+    def backward(ctx, g_terms, g_j2d):
+        joints, verts, root_xyz, Ks, joints_gt, j2d_gt, verts_gt, conf, faces = ctx.saved_tensors
+        B = joints.shape[0]
+        dev = joints.device
+        w = torch.zeros(L.KP_NSUMS, dtype=F32, device=dev)
+        w[:7] = g_terms
+        g_joints = torch.empty_like(joints)
+        g_verts = torch.empty_like(verts) if verts is not None else None
+        g2 = None if (g_j2d is None or g_j2d.numel() == 0 or Ks is None) else _cu(g_j2d)
+        f = keypoint_args(joints, root_xyz, Ks, verts, faces, joints_gt, j2d_gt, verts_gt, conf, ctx.l2, None, w)
+        a = L.HfrKeypointBwdArgs(f, L.ptr(w, F32), B, L.ptr(g2, F32), L.ptr(g_joints, F32), L.ptr(g_verts, F32))
+        L.call("hfr_keypoint_backward", a)
+        return g_joints, g_verts, None, None, None, None, None, None, None, None

@@ -323,6 +323,55 @@ typedef struct HfrLossBwdArgs {
 } HfrLossBwdArgs;
 int hfr_loss_backward(const HfrLossBwdArgs* a, void* stream);
 
+/* ------------------------------------------------------------------ keypoints + mesh regularisers
+ * SURVEY.md §8(f) rows 2-3.  j2d = proj_func(joints + root_xyz, K) (utils/traineval_util.py:338-354 as called at
+ * train_hrnet.py:83; utils/fh_utils.py:30-39) and the keypoint / mesh terms of LossFunction.__call__
+ * (losses.py:244-299): joint_2d, joint_3d, vert_3d (base_loss_fn = L1 mean or MSE), bone_direc, bone_direc_3d
+ * (utils/losses_util.py:217-282), edge_length (:284-301), mscale.  One launch forward, one backward.
+ *   forward : writes j2d (optional) and ADDS per-term partial sums to sums[HFR_KP_NSUMS] (caller zeroes; under
+ *             data parallelism the caller all-reduces them);  term = sums[k] / count_k with counts
+ *             n*NJ*2, n*NJ*3, n*V*3, n*NB, n*NB, n*3F, n  (n = global batch).
+ *   backward: w[k] = d(total)/d(term k) (DEVICE floats, lambda x upstream) -> g_joints (B,NJ,3) and g_verts (B,V,3),
+ *             both WRITTEN (not accumulated); feed them to hfr_geom_backward as g_joints / g_verts_rel. */
+#define HFR_KP_J2D 0
+#define HFR_KP_J3D 1
+#define HFR_KP_V3D 2
+#define HFR_KP_BONE2D 3
+#define HFR_KP_BONE3D 4
+#define HFR_KP_EDGE 5
+#define HFR_KP_MSCALE 6
+#define HFR_KP_NSUMS 8
+typedef struct HfrKeypointArgs {
+  int32_t B, NJ, V, F;
+  int32_t l2;                       /* base_loss_fn: 0 = nn.L1Loss, 1 = mse_loss (losses.py:239-242)        */
+  int32_t NB;                       /* bones                                                               */
+  int32_t scale_a, scale_b;         /* mscale reference bone (9, 10); scale_a < 0 disables the term         */
+  float scale_len;                  /* 0.0282                                                              */
+  const float* joints;              /* (B,NJ,3) root-relative joints (hfr_geom_forward output)             */
+  const float* root_xyz;            /* (B,3) or NULL                                                       */
+  const float* Kmat;                /* (B,3,3) intrinsics, or NULL (no projection, no 2-D terms)           */
+  const float* verts;               /* (B,V,3) root-relative verts, or NULL                                */
+  const int32_t* faces;             /* (F,3)                                                               */
+  const float* joints_gt;           /* (B,NJ,3) or NULL: joint_3d, bone_direc_3d off                       */
+  const float* j2d_gt;              /* (B,NJ,2) or NULL: joint_2d, bone_direc off                          */
+  const float* verts_gt;            /* (B,V,3)  or NULL: vert_3d, edge_length off                          */
+  const float* conf;                /* (B,NJ) joint confidences for the bone terms, or NULL (= ones)       */
+  const int32_t* bone_parent;       /* (NB)                                                                */
+  const int32_t* bone_child;        /* (NB)                                                                */
+  float* j2d;                       /* (B,NJ,2) output, or NULL                                            */
+  float* sums;                      /* (HFR_KP_NSUMS) accumulated                                          */
+} HfrKeypointArgs;
+int hfr_keypoint_forward(const HfrKeypointArgs* a, void* stream);
+typedef struct HfrKeypointBwdArgs {
+  HfrKeypointArgs f;
+  const float* w;                   /* DEVICE (HFR_KP_NSUMS) d(total)/d(term)                              */
+  int32_t n_global;                 /* global batch of the means                                           */
+  const float* g_j2d_in;            /* (B,NJ,2) extra upstream gradient on the j2d output, or NULL         */
+  float* g_joints;                  /* (B,NJ,3)                                                            */
+  float* g_verts;                   /* (B,V,3) or NULL                                                     */
+} HfrKeypointBwdArgs;
+int hfr_keypoint_backward(const HfrKeypointBwdArgs* a, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,6 +6,8 @@ Run in the build container (needs /root/reference for the MANO / SSIM goldens):
                        on seeded inputs, plus the SURVEY.md Appendix C known answers.
   mano_modes_reference.npz : the same layer in its non-default modes (rot6d / robust rot6d root, rotmat joints,
                        axis-angle without PCA, root_palm, share_betas, th_trans, mean shape), outputs + gradients.
+  keypoint_reference.npz : proj_func / trans_proj_j2d, bone_direction_loss, edge_length_loss, L1 / MSE keypoint and
+                       vertex terms, mscale — unmodified reference functions, terms + gradients.
   ssim_reference.npz : utils/pytorch_ssim.ssim on seeded images (unmodified module).
   raster_oracle.npz  : Fragments of the scalar C oracle on one small seeded MANO view (regression pin
                        of the restatement; PyTorch3D itself is unavailable -> parity unpinned).
@@ -73,6 +75,51 @@ def mano_mode_cases(B=3):
     return out
 
 
+def keypoint_cases(B=3):
+    """The unmodified reference functions (proj via trans_proj_j2d, bone_direction_loss, edge_length_loss, nn.L1Loss /
+    mse_loss, the mscale lines of losses.py:293-299) on seeded MANO-sized inputs; terms + autograd gradients of
+    sum_k (k+1) * term_k wrt joints and verts, for base_loss_fn L1 and L2."""
+    import torch.nn as nn
+    import torch.nn.functional as torch_f
+    lu, fh, tu = ref_mano.reference_keypoint_modules()
+    mano = load_mano()
+    faces = torch.tensor(np.asarray(mano["f"], np.int64))
+    g = torch.Generator().manual_seed(777)
+    out = {"faces": faces.numpy().astype(np.int32)}
+    vt = torch.tensor(np.asarray(mano["v_template"], np.float32))
+    for l2 in (0, 1):
+        base = torch_f.mse_loss if l2 else nn.L1Loss()
+        joints = (torch.randn(B, 21, 3, generator=g) * 0.04).requires_grad_(True)
+        joints_gt = torch.randn(B, 21, 3, generator=g) * 0.04
+        verts = (vt[None] + torch.randn(B, 778, 3, generator=g) * 0.003).requires_grad_(True)
+        verts_gt = vt[None] + torch.randn(B, 778, 3, generator=g) * 0.003
+        root = torch.stack([torch.rand(B, generator=g) * 0.06 - 0.03, torch.rand(B, generator=g) * 0.06 - 0.03,
+                            torch.rand(B, generator=g) * 0.2 + 0.55], 1).view(B, 1, 3)
+        K = torch.zeros(B, 3, 3)
+        K[:, 0, 0] = 440 + 80 * torch.rand(B, generator=g)
+        K[:, 1, 1] = 440 + 80 * torch.rand(B, generator=g)
+        K[:, 0, 2] = 112 + 8 * torch.rand(B, generator=g)
+        K[:, 1, 2] = 112 - 8 * torch.rand(B, generator=g)
+        K[:, 2, 2] = 1
+        j2d = tu.trans_proj_j2d({"joints": joints}, K, root_xyz=root)
+        j2d_gt = j2d.detach() + torch.randn(B, 21, 2, generator=g) * 4
+        con = torch.ones(B, 21, 1)
+        terms = [base(j2d_gt, j2d), base(joints, joints_gt), base(verts, verts_gt),
+                 lu.bone_direction_loss(j2d, j2d_gt, con), lu.bone_direction_loss(joints, joints_gt, con),
+                 lu.edge_length_loss(verts, verts_gt, faces[None].repeat(B, 1, 1)),
+                 nn.L1Loss()(torch.sqrt(torch.sum((joints[:, 9, :] - joints[:, 10, :]) ** 2, 1)),
+                             torch.ones(B) * 0.0282)]
+        total = sum((k + 1) * t for k, t in enumerate(terms))
+        total.backward()
+        pre = f"l{l2 + 1}."
+        out.update({pre + "joints": joints.detach().numpy(), pre + "joints_gt": joints_gt.numpy(),
+                    pre + "verts": verts.detach().numpy(), pre + "verts_gt": verts_gt.numpy(), pre + "root": root.numpy(),
+                    pre + "K": K.numpy(), pre + "j2d": j2d.detach().numpy(), pre + "j2d_gt": j2d_gt.numpy(),
+                    pre + "terms": np.array([float(t.detach()) for t in terms], np.float64),
+                    pre + "g_joints": joints.grad.numpy(), pre + "g_verts": verts.grad.numpy()})
+    return out
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     assert ref_mano.available(), "reference tree not found"
@@ -90,6 +137,7 @@ def main():
                         g_pose=pose.grad.numpy(), g_beta=beta.grad.numpy(), verts_zero=v0.detach().numpy(),
                         joints_zero=j0.detach().numpy())
     np.savez_compressed(os.path.join(OUT, "mano_modes_reference.npz"), **mano_mode_cases())
+    np.savez_compressed(os.path.join(OUT, "keypoint_reference.npz"), **keypoint_cases())
     ps = ref_mano.reference_ssim()
     a, b = torch.rand(2, 3, 40, 40, generator=g), torch.rand(2, 3, 40, 40, generator=g)
     np.savez_compressed(os.path.join(OUT, "ssim_reference.npz"), a=a.numpy(), b=b.numpy(),

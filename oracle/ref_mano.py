@@ -99,3 +99,30 @@ def reference_ssim():
     _install()
     import utils.pytorch_ssim as ps
     return ps
+
+
+class _StubModule(types.ModuleType):
+    """Stand-in for plotting / IO packages the reference imports at module level but never touches on this path."""
+
+    def __getattr__(self, k):
+        if k.startswith("__"):
+            raise AttributeError(k)
+        from unittest import mock
+        return mock.MagicMock()
+
+
+def reference_keypoint_modules():
+    """(utils.losses_util, utils.fh_utils, utils.traineval_util) of the reference, unmodified: bone_direction_loss /
+    edge_length_loss (losses_util.py:217-301), proj_func (fh_utils.py:30-39), trans_proj_j2d (traineval_util.py:338-354).
+    Absent third-party modules (pytorch3d.loss, skimage, matplotlib, ...) are stubbed as they are not on this path."""
+    _install()
+    import importlib
+    for _ in range(40):
+        try:
+            lu = importlib.import_module("utils.losses_util")
+            fh = importlib.import_module("utils.fh_utils")
+            tu = importlib.import_module("utils.traineval_util")
+            return lu, fh, tu
+        except ModuleNotFoundError as e:
+            sys.modules[e.name] = _StubModule(e.name)
+    raise RuntimeError("could not import the reference keypoint modules")

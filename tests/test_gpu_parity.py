@@ -507,6 +507,68 @@ def test_full_size_properties_c2(hf, mano):
         assert (z[n].cpu() == ref[1][0]).all() and (step.dists[n].cpu() == ref[3][0]).all()
 
 
+# ------------------------------------------------------------------------------------------ keypoints
+@pytest.mark.parametrize("pre", ["l1.", "l2."])
+def test_keypoint_losses_match_reference_golden(hf, pre):
+    """hfr_keypoint_forward/backward against golden vectors of the unmodified reference functions:
+    j2d 2e-4 px abs, terms 1e-5 rel, gradients 1e-4 of the tensor's max (L1 sign flips aside, none at these inputs)."""
+    from hifihr_b200 import ops
+    z = np.load(os.path.join(GOLD, "keypoint_reference.npz"))
+    t = lambda k: torch.tensor(z[pre + k], device=DEV)  # noqa: E731
+    j, v = t("joints").requires_grad_(True), t("verts").requires_grad_(True)
+    faces = torch.tensor(z["faces"], device=DEV)
+    terms, j2d = ops.KeypointLossFunction.apply(j, v, t("root"), t("K"), t("joints_gt"), t("j2d_gt"), t("verts_gt"), None,
+                                                faces, 1 if pre == "l2." else 0)
+    assert (j2d.detach().cpu() - torch.tensor(z[pre + "j2d"])).abs().max() < 2e-4
+    for k in range(7):
+        ref = z[pre + "terms"][k]
+        assert abs(float(terms[k]) - ref) < 1e-5 * max(1.0, abs(ref)), (k, float(terms[k]), ref)
+    w = torch.arange(1, 8, device=DEV, dtype=torch.float32)
+    (terms * w).sum().backward()
+    assert rel_err(j.grad, torch.tensor(z[pre + "g_joints"])) < 1e-4
+    assert rel_err(v.grad, torch.tensor(z[pre + "g_verts"])) < 1e-4
+
+
+def test_keypoint_terms_through_loss_function_and_model(hf, mano):
+    """LossFunction with the keypoint terms on HandRenderModel outputs (joints / mano_verts / mano_faces), gradients
+    flowing through hfr_geom_backward and hfr_mano_backward to pose and shape; oracle = MANO + keypoint restatements."""
+    from types import SimpleNamespace
+    from oracle import keypoints as KP
+    B = 5
+    inp = P.synthetic_inputs(B, S=8, seed=31)
+    g = torch.Generator().manual_seed(5)
+    gt_j, gt_v = torch.randn(B, 21, 3, generator=g) * 0.04, torch.randn(B, 778, 3, generator=g) * 0.04
+    gt_2d = torch.rand(B, 21, 2, generator=g) * 224
+    K33 = inp["Ks"][:, :, :3].contiguous()
+    args = SimpleNamespace(base_loss_fn="L1", lambda_j2d_gt=1e-3, lambda_j3d=10.0, lambda_vert_3d=10.0, lambda_bone_direc=0.5,
+                           lambda_bone_direc_3d=0.7, lambda_edge_len=3.0, lambda_mscale=2.0)
+    used = ["joint_2d", "joint_3d", "vert_3d", "bone_direc", "bone_direc_3d", "edge_length", "mscale"]
+    # ours
+    model = hf.HandRenderModel(ifRender=False, device=DEV)
+    pose, betas = inp["pose"].to(DEV).requires_grad_(True), inp["betas"].to(DEV).requires_grad_(True)
+    out = model({"pose_params": pose, "shape_params": betas})
+    ex = dict(joints=gt_j.to(DEV), verts=gt_v.to(DEV), j2d_gt=gt_2d.to(DEV), Ks=K33.to(DEV), root_xyz=inp["root_xyz"].to(DEV))
+    out["j2d"] = hf.trans_proj_j2d(out, ex["Ks"], root_xyz=ex["root_xyz"])
+    ld = hf.LossFunction()(ex, out, used, "FreiHand", args)
+    sum(ld.values()).backward()
+    # oracle
+    orc = ManoOracle(mano)
+    po, bo = inp["pose"].clone().requires_grad_(True), inp["betas"].clone().requires_grad_(True)
+    vo, _ = orc(po, bo)
+    jo = orc.xyz_from_vertice(vo)
+    root = jo[:, 9:10]
+    jo, vo = jo - root, vo - root
+    j2o = KP.project_joints(jo, K33, inp["root_xyz"])
+    assert (out["j2d"].detach().cpu() - j2o.detach()).abs().max() < 2e-3       # pixels
+    oo = KP.keypoint_losses(jo, j2o, vo, torch.tensor(np.asarray(mano["f"], np.int64)), gt_j, gt_2d, gt_v)
+    lam = dict(joint_2d=1e-3, joint_3d=10.0, vert_3d=10.0, bone_direc=0.5, bone_direc_3d=0.7, edge_length=3.0, mscale=2.0)
+    for k in used:
+        assert abs(float(ld[k]) - lam[k] * float(oo[k])) < 2e-5 * max(1.0, abs(lam[k] * float(oo[k]))), k
+    sum(lam[k] * oo[k] for k in used).backward()
+    assert rel_err(pose.grad, po.grad) < 1e-3
+    assert rel_err(betas.grad, bo.grad) < 1e-3
+
+
 # ------------------------------------------------------------------------------------------ multi-GPU
 def test_two_gpu_sharded_step_matches_single_process(hf):
     """NCCL, world size 2: batch slices + the two all-reduces reproduce the single-process step

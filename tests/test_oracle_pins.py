@@ -54,6 +54,46 @@ def test_mano_oracle_modes_match_reference_golden(mano):
             assert (trans.grad - torch.tensor(z[f"{name}.g_trans"])).abs().max() < 1e-4, name
 
 
+def test_keypoint_oracle_matches_reference_golden():
+    """oracle/keypoints.py against golden vectors of the unmodified reference functions (trans_proj_j2d / proj_func,
+    bone_direction_loss, edge_length_loss, L1 / MSE terms, mscale): terms 1e-6 rel, gradients 1e-5 of the max."""
+    from oracle import keypoints as KP
+    z = np.load(os.path.join(GOLD, "keypoint_reference.npz"))
+    for pre in ("l1.", "l2."):
+        t = lambda k: torch.tensor(z[pre + k])  # noqa: E731
+        j, v = t("joints").requires_grad_(True), t("verts").requires_grad_(True)
+        j2 = KP.project_joints(j, t("K"), t("root"))
+        assert (j2.detach() - t("j2d")).abs().max() < 1e-4          # pixels
+        o = KP.keypoint_losses(j, j2, v, torch.tensor(z["faces"]), t("joints_gt"), t("j2d_gt"), t("verts_gt"), l2=pre == "l2.")
+        terms = [o[k] for k in KP.TERMS]
+        for k, x in enumerate(terms):
+            assert abs(float(x) - z[pre + "terms"][k]) < 1e-6 * max(1.0, abs(z[pre + "terms"][k])), (pre, KP.TERMS[k])
+        sum((k + 1) * x for k, x in enumerate(terms)).backward()
+        assert (j.grad - t("g_joints")).abs().max() < 1e-5 * t("g_joints").abs().max()
+        assert (v.grad - t("g_verts")).abs().max() < 1e-5 * t("g_verts").abs().max()
+
+
+@pytest.mark.skipif(not ref_mano.available(), reason="reference tree not present (GPU box)")
+def test_keypoint_oracle_vs_live_reference():
+    from oracle import keypoints as KP
+    lu, fh, tu = ref_mano.reference_keypoint_modules()
+    g = torch.Generator().manual_seed(11)
+    B = 5
+    j, jg = torch.randn(B, 21, 3, generator=g) * 0.05, torch.randn(B, 21, 3, generator=g) * 0.05
+    root = torch.tensor([[0.01, -0.02, 0.6]]).repeat(B, 1).view(B, 1, 3)
+    K = torch.tensor([[480.0, 0.5, 112.0], [0.0, 470.0, 110.0], [0.0, 0.0, 1.0]]).repeat(B, 1, 1)
+    j2 = tu.trans_proj_j2d({"joints": j}, K, root_xyz=root)
+    assert (j2 - KP.project_joints(j, K, root)).abs().max() < 1e-4
+    assert (fh.proj_func(j + root, K) - KP.project_joints(j, K, root)).abs().max() < 1e-4
+    con = torch.rand(B, 21, 1, generator=g)
+    j2g = j2 + torch.randn(B, 21, 2, generator=g) * 3
+    assert abs(float(lu.bone_direction_loss(j2, j2g, con)) - float(KP.bone_direction(j2, j2g, con))) < 1e-7
+    assert abs(float(lu.bone_direction_loss(j, jg, con)) - float(KP.bone_direction(j, jg, con))) < 1e-6
+    faces = torch.randint(0, 50, (30, 3), generator=g)
+    v, vg = torch.randn(B, 50, 3, generator=g), torch.randn(B, 50, 3, generator=g)
+    assert abs(float(lu.edge_length_loss(v, vg, faces[None].repeat(B, 1, 1))) - float(KP.edge_length(v, vg, faces))) < 1e-6
+
+
 def test_generic_lbs_oracle_matches_mano_oracle(mano):
     """oracle/lbs.py (any skeleton; used for the NIMBLE-shaped layer) restricted to MANO's constants must be the
     pinned MANO oracle."""
@@ -181,7 +221,8 @@ def test_ctypes_struct_sizes_match_header():
     from hifihr_b200 import _lib
     names = ["HfrHandModel", "HfrManoFwdArgs", "HfrManoBwdArgs", "HfrTopology", "HfrGeomFwdArgs", "HfrGeomBwdArgs",
              "HfrRasterArgs", "HfrRasterBwdArgs", "HfrShadeParams", "HfrShadeFwdArgs", "HfrShadeBwdArgs",
-             "HfrRasterShadeArgs", "HfrPoolArgs", "HfrPoolBwdArgs", "HfrLossArgs", "HfrLossBwdArgs"]
+             "HfrRasterShadeArgs", "HfrPoolArgs", "HfrPoolBwdArgs", "HfrLossArgs", "HfrLossBwdArgs", "HfrKeypointArgs",
+             "HfrKeypointBwdArgs"]
     src = '#include <stdio.h>\n#include "hifihr_b200.h"\nint main(){' + "".join(
         f'printf("%zu\\n", sizeof({n}));' for n in names) + "return 0;}"
     with tempfile.TemporaryDirectory() as td:
