@@ -33,15 +33,19 @@ CONFIGS = {
     "c4": dict(B=None, S=224, K=4, soft=True, T=512, desc="C4 as C2 with global batch 4096 sharded over the GPUs"),
     "c5": dict(B=32, S=512, K=8, soft=True, T=512, desc="C5 soft raster 512^2 K=8, B=32/GPU (256 global at 8 GPUs)"),
     "r": dict(B=48, S=672, K=1, soft=False, T=512, desc="reference setting 672^2 K=1 hard Phong (no pooling stage), B=48"),
+    # the reference's own render config, fused (models_res_nimble.py:74-96, 208-220)
+    "rp": dict(B=48, S=224, K=1, soft=False, T=512, aa=3, binarize=True, sil_scale=255.0,
+               desc="R reference setting: 672^2 K=1 hard Phong + 3x3 SSAA pool + binarised alpha fused, losses at 224^2, B=48"),
 }
 LAMBDAS = dict(texture=1.0, mrgb=1.0, ssim_tex=1.0, sil=1.0, iou=0.0)
 
 
-def algorithmic_bytes_per_sample(S, K, V=778, T=512, B=64, n_params=58):
-    """Fragments written+read (56 B/pixel/K), image-side traffic (64 B/pixel), vertex streams,
-    parameters, shared texture read + grad write amortised over the per-GPU batch."""
+def algorithmic_bytes_per_sample(S, K, V=778, T=512, B=64, n_params=58, aa=1):
+    """Fragments written+read (56 B/pixel/K, at the RASTERISED resolution S*aa), image-side
+    traffic (64 B/pixel at the loss resolution S), vertex streams, parameters, shared texture read + grad write
+    amortised over the per-GPU batch."""
     P = S * S
-    return 56 * P * K + 64 * P + 48 * V + 8 * n_params + 24 * T * T / B
+    return 56 * P * aa * aa * K + 64 * P + 48 * V + 8 * n_params + 24 * T * T / B
 
 
 def peaks():
@@ -119,8 +123,8 @@ def run_reference(args, cfg):
         inp["betas"].requires_grad_(True)
         t = tex.clone().requires_grad_(True)
         out = P.render_path(mano, inp, t, image_size=S, K=K, blur_radius=blur, soft=cfg["soft"], c_select=True,
-                            threads=cores)
-        loss, _ = P.total_loss(out, inp, {k: v for k, v in LAMBDAS.items() if v}, 1.0)
+                            threads=cores, aa=cfg.get("aa", 1), binarize=cfg.get("binarize", False))
+        loss, _ = P.total_loss(out, inp, {k: v for k, v in LAMBDAS.items() if v}, cfg.get("sil_scale", 1.0))
         loss.backward()
         return float(loss.detach())
 
@@ -162,8 +166,10 @@ def run_ours(args, cfg):
     if args.batch:
         B = args.batch
     S, K = cfg["S"], cfg["K"]
+    aa = cfg.get("aa", 1)
     step = hf.FusedHandStep(B, image_size=S, faces_per_pixel=K, soft=cfg["soft"], texture_size=cfg["T"],
-                            lambdas=LAMBDAS, device=dev, n_global=B * world, sil_scale=1.0)
+                            lambdas=LAMBDAS, device=dev, n_global=B * world, sil_scale=cfg.get("sil_scale", 1.0),
+                            aa_factor=aa, binarize=cfg.get("binarize", False))
     inp = synthetic_inputs(B, S=S, seed=1234 + rank)
     fcl, prp = hf.get_ndc_fx_fy_cx_cy(inp["Ks"])
     host = [inp["pose"], inp["betas"], -fcl, prp, inp["root_xyz"], inp["light_dir"], inp["light_color"], inp["imgs"],
@@ -261,22 +267,14 @@ def run_ours(args, cfg):
         ev.append(timed("geom_fwd", lambda: ops.geom_forward_raw(step.topo, step.verts, 9, root, focal, prpp, step.joints,
                                                                  step.verts_rel, step.verts_view, step.verts_ndc,
                                                                  step.vnormals, step.face_verts)))
-        def rs():
-            r = ops.raster_args(step.face_verts, step.mesh_first, step.mesh_nf, S, S, K, step.blur, True, step.blur > 0,
-                                False, step.p2f, step.zbuf, step.bary, step.dists, step.ws)
-            L.call("hfr_raster_shade_forward", L.HfrRasterShadeArgs(r, step._shade_args))
-        ev.append(timed("raster_shade_fwd", rs))
+        ev.append(timed("raster_shade_fwd", lambda: step.launch_raster_shade(ldir, lcol, imgs)))
         step.sums.zero_()
         ev.append(timed("loss_fwd", lambda: L.call("hfr_loss_forward", step._loss_args)))
         lb = L.HfrLossBwdArgs(step._loss_args, L.ptr(step.w), L.ptr(step.gauss), step.n_global * 3 * S * S, step.n_global,
                               L.ptr(step.g_image), None)
         ev.append(timed("loss_bwd", lambda: L.call("hfr_loss_backward", lb)))
         step.acc.zero_()
-        sb = L.HfrShadeBwdArgs(step._shade_args, L.ptr(step.g_image), None, None, None, L.ptr(step.verts_ndc),
-                               L.ptr(step.g_ndc), float(step.blur), 1, int(step.blur > 0), L.ptr(step.g_view),
-                               L.ptr(step.g_vn), L.ptr(step.g_texture), L.ptr(step.g_light_dir), L.ptr(step.g_light_color),
-                               ops.raster_tile_box(step.ws, B * step.topo.F, B))
-        ev.append(timed("shade_raster_bwd", lambda: L.call("hfr_shade_backward", sb)))
+        ev.append(timed("shade_raster_bwd", lambda: step.launch_shade_backward()))
         ev.append(timed("geom_bwd", lambda: ops.geom_backward_raw(step.topo, step.verts, 9, root, focal, prpp, None, None,
                                                                   step.g_view, step.g_ndc, step.g_vn, step.g_verts)))
         ev.append(timed("mano_bwd", lambda: ops.mano_backward_raw(step.hm, pose, betas, None, step.g_verts, None,
@@ -298,8 +296,8 @@ def run_ours(args, cfg):
         top = max(kern_ms, key=kern_ms.get)
         P_ = S * S
         alg = {  # algorithmic bytes per launch of each big kernel
-            "raster_shade_fwd": B * (28 * K + 16) * P_,          # Fragments + RGBA written once
-            "shade_raster_bwd": B * (28 * K + 16) * P_,          # Fragments + image gradient read once
+            "raster_shade_fwd": B * (28 * K * aa * aa + 16) * P_,   # Fragments (rasterised res.) + RGBA written once
+            "shade_raster_bwd": B * (28 * K * aa * aa + 16) * P_,   # Fragments + image gradient read once
             "loss_fwd": B * (16 + 12 + 4 + 36) * P_,             # RGBA, target, mask read; 9 derivative maps written
             "loss_bwd": B * (16 + 12 + 4 + 36 + 16) * P_,        # the same read again + image gradient written
         }
@@ -313,16 +311,16 @@ def run_ours(args, cfg):
             tj = json.load(open(tpath))
             traffic = tj.get("dram_bytes_per_launch", {}).get(kname)
             traffic_src = tj.get("source")
-        step_bytes = algorithmic_bytes_per_sample(S, K, T=cfg["T"], B=B) * B
+        step_bytes = algorithmic_bytes_per_sample(S, K, T=cfg["T"], B=B, aa=aa) * B
         line = {
             "metric": "hand renders/sec (fwd+bwd)", "value": value, "unit": "samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak" if cfg["B"] is not None else "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": cfg["desc"], "batch_per_gpu": B, "global_batch": B * world, "image_size": S,
-                       "faces_per_pixel": K, "blur_radius": step.blur, "texture": cfg["T"],
+                       "ssaa": aa, "faces_per_pixel": K, "blur_radius": step.blur, "texture": cfg["T"],
                        "parallelism": f"dp{world} (batch shards by sample; NCCL all-reduce of loss sums + texture grad)",
-                       "l2": f"no flush: per-step working set ({(28 * K + 32) * P_ * B / 1e6:.0f} MB Fragments+images) exceeds the 126 MB L2"},
+                       "l2": f"no flush: per-step working set ({(28 * K * aa * aa + 32) * P_ * B / 1e6:.0f} MB Fragments+images) exceeds the 126 MB L2"},
             "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": step.launches_per_step * args.steps,
@@ -359,8 +357,9 @@ def cpu_baseline(cfg):
         inp["pose"].requires_grad_(True)
         t = tex.clone().requires_grad_(True)
         t0 = time.perf_counter()
-        out = P.render_path(mano, inp, t, image_size=S, K=K, blur_radius=blur, soft=cfg["soft"], c_select=True, threads=cores)
-        loss, _ = P.total_loss(out, inp, {k: v for k, v in LAMBDAS.items() if v}, 1.0)
+        out = P.render_path(mano, inp, t, image_size=S, K=K, blur_radius=blur, soft=cfg["soft"], c_select=True, threads=cores,
+                            aa=cfg.get("aa", 1), binarize=cfg.get("binarize", False))
+        loss, _ = P.total_loss(out, inp, {k: v for k, v in LAMBDAS.items() if v}, cfg.get("sil_scale", 1.0))
         loss.backward()
         dt = time.perf_counter() - t0
         if n > 0:

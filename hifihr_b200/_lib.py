@@ -85,11 +85,16 @@ class HfrShadeBwdArgs(C.Structure):
     _fields_ = [("f", HfrShadeFwdArgs), ("g_image", vp), ("g_zbuf", vp), ("g_bary", vp), ("g_dists", vp),
                 ("verts_ndc", vp), ("g_verts_ndc", vp), ("blur_radius", f32), ("perspective_correct", i32),
                 ("clip_barycentric", i32), ("g_verts_view", vp), ("g_vnormals", vp), ("g_texture", vp),
-                ("g_light_dir", vp), ("g_light_color", vp), ("tile_box", vp)]
+                ("g_light_dir", vp), ("g_light_color", vp), ("tile_box", vp), ("pool_aa", i32), ("pool_binarize", i32)]
 
 
 class HfrRasterShadeArgs(C.Structure):
     _fields_ = [("r", HfrRasterArgs), ("s", HfrShadeFwdArgs)]
+
+
+class HfrRasterShadePoolArgs(C.Structure):
+    _fields_ = [("r", HfrRasterArgs), ("s", HfrShadeFwdArgs), ("aa", i32), ("binarize", i32), ("images_in", vp),
+                ("pooled", vp), ("re_img", vp), ("re_sil", vp), ("mask_rgbs", vp)]
 
 
 class HfrPoolArgs(C.Structure):
@@ -130,7 +135,7 @@ ENTRY_POINTS = [
     "hfr_last_error", "hfr_abi_version", "hfr_device_ok", "hfr_mano_forward", "hfr_mano_backward",
     "hfr_geom_forward", "hfr_geom_backward", "hfr_raster_workspace_bytes", "hfr_raster_forward",
     "hfr_raster_backward", "hfr_raster_tile_box", "hfr_shade_forward", "hfr_shade_backward", "hfr_raster_shade_forward",
-    "hfr_pool_forward", "hfr_pool_backward", "hfr_loss_forward", "hfr_loss_backward",
+    "hfr_raster_shade_pool_forward", "hfr_pool_forward", "hfr_pool_backward", "hfr_loss_forward", "hfr_loss_backward",
     "hfr_keypoint_forward", "hfr_keypoint_backward",
 ]
 
@@ -154,7 +159,7 @@ def lib() -> C.CDLL:
         _lib.hfr_raster_workspace_bytes.argtypes = [C.c_int64]
         _lib.hfr_raster_tile_box.restype = C.c_void_p
         _lib.hfr_raster_tile_box.argtypes = [C.c_void_p, C.c_int64, C.c_int32]
-        if _lib.hfr_abi_version() != 2:
+        if _lib.hfr_abi_version() != 3:
             raise HfrError("libhifihr_b200.so ABI version mismatch")
     return _lib
 

@@ -35,34 +35,23 @@ __global__ void __launch_bounds__(256) shade_fwd_kernel(HfrShadeFwdArgs a) {
   *reinterpret_cast<float4*>(a.image + pix * 4) = make_float4(rgba[0], rgba[1], rgba[2], rgba[3]);
 }
 
-// Fused rasterize + shade forward: Fragments and the RGBA image leave the SM in the same pass.
-//
-// Epilogue: ONE runtime loop over the K winners of a pixel (a single copy of the exact fragment math,
-// the gathers, the texture fetch and the Phong code - the kernel stays inside the instruction cache).
-// The blends need no second pass: winners are sorted by depth, so the softmax reference depth
-// z_max belongs to slot 0 and weights accumulate on the fly.
-#ifndef HFR_RASTER_MINB
-#define HFR_RASTER_MINB 4
-#endif
+// Epilogue of the fused kernels: the K winners of one pixel -> Fragments (written here) and the blended RGBA
+// (returned).  ONE runtime loop over the winners (a single copy of the exact fragment math, the gathers, the
+// texture fetch and the Phong code - the kernel stays inside the instruction cache).  The blends need no second
+// pass: winners are sorted by depth, so the softmax reference depth z_max belongs to slot 0 and weights
+// accumulate on the fly.
 template <int KMAX>
-__global__ void __launch_bounds__(kRasterThreads, (KMAX <= 4 ? HFR_RASTER_MINB : 1)) raster_shade_fwd_kernel(HfrRasterArgs r, HfrShadeFwdArgs s,
-                                                                          const uint32_t* __restrict__ ranges,
-                                                                          const uint32_t* __restrict__ mesh_box) {
-  __shared__ RasterSmem sm;
-  PixelCtx c = make_pixel_ctx(r.H, r.W);
-  TopK<KMAX> top;
-  raster_tile<KMAX>(r, ranges, mesh_box, sm, c, top);
-  if (!c.pix_active) return;
+__device__ __forceinline__ void raster_shade_epilogue(const HfrRasterArgs& r, const HfrShadeFwdArgs& s, const PixelCtx& c,
+                                                      const TopK<KMAX>& top, size_t pix, float (&rgba)[4]) {
   const HfrShadeParams& P = s.p;
   const int K = r.K;
-  const size_t pix = ((size_t)c.n * r.H + c.yi) * r.W + c.xi;
   const bool ones = P.blend == HFR_BLEND_SIGMOID_ALPHA;
   int64_t id[KMAX];
   float z[KMAX], d[KMAX];
 #pragma unroll
   for (int k = 0; k < KMAX; ++k) { id[k] = -1; z[k] = -1.0f; d[k] = -1.0f; }
   float* __restrict__ ba = r.bary + pix * K * 3;
-  float rgba[4] = {ones ? 1.0f : P.background[0], ones ? 1.0f : P.background[1], ones ? 1.0f : P.background[2], 0.0f};
+  rgba[0] = ones ? 1.0f : P.background[0]; rgba[1] = ones ? 1.0f : P.background[1]; rgba[2] = ones ? 1.0f : P.background[2]; rgba[3] = 0.0f;
   if (top.f[0] < 0) {
     // empty pixel (winners are sorted, slot 0 empty = all empty): -1 fill, background colour, alpha 0
     if (K == KMAX && (KMAX % 4) == 0) {
@@ -155,7 +144,97 @@ __global__ void __launch_bounds__(kRasterThreads, (KMAX <= 4 ? HFR_RASTER_MINB :
         if (k < K) { p2f[k] = id[k]; zb[k] = z[k]; ds[k] = d[k]; }
     }
   }
+}
+
+// Fused rasterize + shade forward: Fragments and the RGBA image leave the SM in the same pass.
+#ifndef HFR_RASTER_MINB
+#define HFR_RASTER_MINB 4
+#endif
+template <int KMAX>
+__global__ void __launch_bounds__(kRasterThreads, (KMAX <= 4 ? HFR_RASTER_MINB : 1)) raster_shade_fwd_kernel(HfrRasterArgs r, HfrShadeFwdArgs s,
+                                                                          const uint32_t* __restrict__ ranges,
+                                                                          const uint32_t* __restrict__ mesh_box) {
+  __shared__ RasterSmem sm;
+  PixelCtx c = make_pixel_ctx(r.H, r.W);
+  TopK<KMAX> top;
+  raster_tile<KMAX>(r, ranges, mesh_box, sm, c, top);
+  if (!c.pix_active) return;
+  const size_t pix = ((size_t)c.n * r.H + c.yi) * r.W + c.xi;
+  float rgba[4];
+  raster_shade_epilogue<KMAX>(r, s, c, top, pix, rgba);
   *reinterpret_cast<float4*>(s.image + pix * 4) = make_float4(rgba[0], rgba[1], rgba[2], rgba[3]);
+}
+
+// Fused rasterize + shade + SSAA pool (the reference's render setting: 672^2, K=1, avg_pool2d(3,3), output split,
+// models_res_nimble.py:208-220).  One CTA owns a 16x16 tile of POOLED pixels = aa x aa rasterizer tiles, which it
+// walks one after the other with the same tile core; each tile's RGBA goes through 4 KB of shared memory into the
+// pooled accumulators (fixed summation order, so the result is deterministic), and only Fragments plus the
+// pooled outputs reach HBM - the (N, 672, 672, 4) image never exists.
+struct PoolOut {
+  int aa, binarize;
+  const float* images_in;
+  float* pooled; float* re_img; float* re_sil; float* mask_rgbs;
+};
+template <int KMAX>
+__global__ void __launch_bounds__(kRasterThreads, (KMAX <= 4 ? HFR_RASTER_MINB : 1)) raster_shade_pool_fwd_kernel(
+    HfrRasterArgs r, HfrShadeFwdArgs s, PoolOut po, const uint32_t* __restrict__ ranges, const uint32_t* __restrict__ mesh_box) {
+  __shared__ RasterSmem sm;
+  __shared__ float4 s_tile[kTileH * kTileW];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int aa = po.aa, n = blockIdx.z;
+  const int lx = (warp & 1) * 8 + (lane & 7), ly = (warp >> 1) * 4 + (lane >> 3);   // this thread's pixel inside a raster tile
+  const int px = tid & 15, py = tid >> 4;                                            // this thread's pooled pixel
+  const int gx0 = (blockIdx.x * kTileW + px) * aa, gy0 = (blockIdx.y * kTileH + py) * aa;   // its window's corner
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int sy = 0; sy < aa; ++sy) {
+    for (int sx = 0; sx < aa; ++sx) {
+      PixelCtx c;
+      c.n = n; c.tx = blockIdx.x * aa + sx; c.ty = blockIdx.y * aa + sy;
+      c.xi = c.tx * kTileW + lx; c.yi = c.ty * kTileH + ly;
+      c.pix_active = c.xi < r.W && c.yi < r.H;
+      c.warp_active = c.tx * kTileW + (warp & 1) * 8 < r.W && c.ty * kTileH + (warp >> 1) * 4 < r.H;
+      c.xf = 0.0f; c.yf = 0.0f;
+      TopK<KMAX> top;
+      raster_tile<KMAX>(r, ranges, mesh_box, sm, c, top);
+      float rgba[4] = {0.f, 0.f, 0.f, 0.f};
+      if (c.pix_active) {
+        const size_t pix = ((size_t)n * r.H + c.yi) * r.W + c.xi;
+        raster_shade_epilogue<KMAX>(r, s, c, top, pix, rgba);
+        if (s.image) *reinterpret_cast<float4*>(s.image + pix * 4) = make_float4(rgba[0], rgba[1], rgba[2], rgba[3]);
+      }
+      s_tile[ly * kTileW + lx] = make_float4(rgba[0], rgba[1], rgba[2], rgba[3]);
+      __syncthreads();
+      // the part of this thread's aa x aa window that lies in the tile just rendered, row-major
+      for (int dy = 0; dy < aa; ++dy) {
+        const int gy = gy0 + dy;
+        if ((gy >> 4) != c.ty) continue;
+        for (int dx = 0; dx < aa; ++dx) {
+          const int gx = gx0 + dx;
+          if ((gx >> 4) != c.tx) continue;
+          const float4 v = s_tile[(gy & 15) * kTileW + (gx & 15)];
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+      }
+      __syncthreads();   // s_tile and the tile core's shared state are reused by the next tile
+    }
+  }
+  const int Hp = r.H / aa, Wp = r.W / aa;
+  const int ox = blockIdx.x * kTileW + px, oy = blockIdx.y * kTileH + py;
+  if (ox >= Wp || oy >= Hp) return;
+  const float cnt = (float)(aa * aa);
+  const float c0 = acc.x / cnt, c1 = acc.y / cnt, c2 = acc.z / cnt, al = acc.w / cnt;
+  const float sil = (po.binarize && al > 0.0f) ? 255.0f : al;
+  const size_t hw = (size_t)Hp * Wp, p = (size_t)oy * Wp + ox;
+  *reinterpret_cast<float4*>(po.pooled + ((size_t)n * hw + p) * 4) = make_float4(c0, c1, c2, sil);
+  if (po.re_img) {
+    po.re_img[((size_t)n * 3 + 0) * hw + p] = c0; po.re_img[((size_t)n * 3 + 1) * hw + p] = c1; po.re_img[((size_t)n * 3 + 2) * hw + p] = c2;
+  }
+  if (po.re_sil) po.re_sil[(size_t)n * hw + p] = sil;
+  if (po.mask_rgbs) {
+    const float m = sil > 0.0f ? 1.0f : 0.0f;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) po.mask_rgbs[((size_t)n * 3 + ch) * hw + p] = __ldg(po.images_in + ((size_t)n * 3 + ch) * hw + p) * m;
+  }
 }
 
 int check_shade(const HfrShadeFwdArgs* a, const char* who) {
@@ -217,5 +296,32 @@ extern "C" int hfr_raster_shade_forward(const HfrRasterShadeArgs* a, void* strea
   HFR_DISPATCH_K(a->r.K, CALL);
 #undef CALL
   HFR_CHECK_LAUNCH("raster_shade_forward");
+  return HFR_OK;
+}
+
+extern "C" int hfr_raster_shade_pool_forward(const HfrRasterShadePoolArgs* a, void* stream) {
+  using namespace hfr;
+  HFR_CHECK_ARG(a, "raster_shade_pool_forward: null args");
+  if (int rc = check_raster(&a->r, "raster_shade_pool_forward")) return rc;
+  HfrShadeFwdArgs s = a->s;
+  s.pix_to_face = a->r.pix_to_face; s.zbuf = a->r.zbuf; s.bary = a->r.bary; s.dists = a->r.dists;
+  if (int rc = check_shade(&s, "raster_shade_pool_forward")) return rc;
+  HFR_CHECK_ARG(s.p.N == a->r.N && s.p.H == a->r.H && s.p.W == a->r.W && s.p.K == a->r.K,
+                "raster_shade_pool_forward: raster / shade dims differ");
+  HFR_CHECK_ARG(a->aa >= 1 && a->aa <= 16 && a->r.H % a->aa == 0 && a->r.W % a->aa == 0,
+                "raster_shade_pool_forward: image size must be a multiple of aa (1..16)");
+  HFR_CHECK_ARG(a->r.N == 0 || a->pooled, "raster_shade_pool_forward: null pooled image");
+  HFR_CHECK_ARG(!a->mask_rgbs || a->images_in, "raster_shade_pool_forward: mask_rgbs needs images_in");
+  if (a->r.N == 0) return HFR_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  uint32_t* ranges = reinterpret_cast<uint32_t*>(a->r.workspace);
+  if (int rc = launch_raster_setup(a->r, ranges, st)) return rc;
+  const int Hp = a->r.H / a->aa, Wp = a->r.W / a->aa;
+  dim3 grid((Wp + kTileW - 1) / kTileW, (Hp + kTileH - 1) / kTileH, a->r.N);
+  PoolOut po{a->aa, a->binarize, a->images_in, a->pooled, a->re_img, a->re_sil, a->mask_rgbs};
+#define CALL(KM) raster_shade_pool_fwd_kernel<KM><<<grid, kRasterThreads, 0, st>>>(a->r, s, po, ranges, raster_mesh_box(a->r))
+  HFR_DISPATCH_K(a->r.K, CALL);
+#undef CALL
+  HFR_CHECK_LAUNCH("raster_shade_pool_forward");
   return HFR_OK;
 }

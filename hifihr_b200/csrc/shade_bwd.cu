@@ -131,7 +131,15 @@ __global__ void __launch_bounds__(kBwdThreads, (KMAX <= 4 ? HFR_BWD_MINB : 1)) s
         for (int k = 0; k < KMAX; ++k)
           if (k < K) { z[k] = __ldg(f.zbuf + pix * K + k); d[k] = __ldg(f.dists + pix * K + k); }
       }
-      const float4 g4 = __ldg(reinterpret_cast<const float4*>(a.g_image + pix * 4));
+      float4 g4;
+      if (a.pool_aa > 1) {   // gradient of the pooled image: avg_pool2d backward folded into the load
+        const int aa = a.pool_aa, Wp = P.W / aa, Hp = P.H / aa;
+        g4 = __ldg(reinterpret_cast<const float4*>(a.g_image + (((size_t)n * Hp + yi / aa) * Wp + xi / aa) * 4));
+        const float inv = 1.0f / (float)(aa * aa);
+        g4.x *= inv; g4.y *= inv; g4.z *= inv; g4.w = a.pool_binarize ? 0.0f : g4.w * inv;
+      } else {
+        g4 = __ldg(reinterpret_cast<const float4*>(a.g_image + pix * 4));
+      }
       g_alpha = g4.w;
       if (P.blend == HFR_BLEND_HARD) {
         gnum[0] = g4.x; gnum[1] = g4.y; gnum[2] = g4.z;     // g_colour of slot 0, nothing else flows
@@ -374,6 +382,8 @@ extern "C" int hfr_shade_backward(const HfrShadeBwdArgs* a, void* stream) {
   HFR_CHECK_ARG(a->f.p.blend != HFR_BLEND_SOFTMAX || a->f.image, "shade_backward: the softmax blend needs the forward image");
   HFR_CHECK_ARG(!a->g_verts_ndc || (a->verts_ndc && a->f.faces && a->f.p.F > 0 && a->f.p.V > 0),
                 "shade_backward: fused raster backward needs verts_ndc and faces");
+  HFR_CHECK_ARG(a->pool_aa <= 1 || (a->pool_aa <= 16 && a->f.p.H % a->pool_aa == 0 && a->f.p.W % a->pool_aa == 0),
+                "shade_backward: image size must be a multiple of pool_aa (<= 16)");
   const HfrShadeParams& p = a->f.p;
   dim3 grid((p.W + kBwdTileW - 1) / kBwdTileW, (p.H + kBwdTileH - 1) / kBwdTileH, p.N);
   cudaStream_t st = (cudaStream_t)stream;

@@ -112,9 +112,17 @@ class FusedHandStep:
     """
 
     def __init__(self, B, image_size=224, faces_per_pixel=4, blur_radius=None, sigma=1e-4, gamma=1e-4, soft=True,
-                 texture_size=512, lambdas=None, device="cuda", mano_root=None, n_global=None, sil_scale=1.0):
+                 texture_size=512, lambdas=None, device="cuda", mano_root=None, n_global=None, sil_scale=1.0,
+                 aa_factor=1, binarize=False, want_nchw=False):
+        """aa_factor > 1 selects the SSAA-fused render (the reference's own setting is image_size=224,
+        aa_factor=3, faces_per_pixel=1, soft=False, binarize=True, sil_scale=255; models_res_nimble.py:74-96,
+        208-220): Fragments are rasterised at image_size*aa_factor, the pooled RGBA (B,S,S,4) is the only image
+        that exists, and the backward folds avg_pool2d' into the shading backward.  want_nchw also writes
+        re_img / re_sil / maskRGBs in the reference's NCHW layout."""
         dev = torch.device(device)
         self.B, self.S, self.K, self.dev = B, image_size, faces_per_pixel, dev
+        self.aa, self.binarize = int(aa_factor), bool(binarize)
+        self.Sr = image_size * self.aa          # rasterised resolution
         self.soft = soft
         self.blur = (np.log(1.0 / 1e-4 - 1.0) * sigma if soft else 0.0) if blur_radius is None else blur_radius
         self.layer = MyMANOLayer(True, dev, shape_ncomp=10, pose_ncomp=48, tex_ncomp=None, mano_root=mano_root)
@@ -132,14 +140,17 @@ class FusedHandStep:
         self.w = torch.tensor([lam["texture"], lam["mrgb"], lam["ssim_tex"], lam["sil"], lam["iou"]], device=dev)
         self.n_global = n_global or B
         self.sil_scale = sil_scale
-        V, Fm, S, K = self.hm.V, self.topo.F, self.S, self.K
+        V, Fm, S, K, Sr = self.hm.V, self.topo.F, self.S, self.K, self.Sr
         e = lambda *s, dt=F32: torch.empty(*s, dtype=dt, device=dev)  # noqa: E731
         self.verts, self.joints = e(B, V, 3), e(B, 21, 3)
         self.verts_rel, self.verts_view, self.verts_ndc, self.vnormals = e(B, V, 3), e(B, V, 3), e(B, V, 3), e(B, V, 3)
         self.face_verts = e(B * Fm, 3, 3)
-        self.p2f = e(B, S, S, K, dt=I64)
-        self.zbuf, self.bary, self.dists = e(B, S, S, K), e(B, S, S, K, 3), e(B, S, S, K)
-        self.image, self.g_image = e(B, S, S, 4), e(B, S, S, 4)
+        self.p2f = e(B, Sr, Sr, K, dt=I64)
+        self.zbuf, self.bary, self.dists = e(B, Sr, Sr, K), e(B, Sr, Sr, K, 3), e(B, Sr, Sr, K)
+        self.image, self.g_image = e(B, S, S, 4), e(B, S, S, 4)      # pooled RGBA when aa > 1
+        self.re_img = self.re_sil = self.mask_rgbs = None
+        if want_nchw:
+            self.re_img, self.re_sil, self.mask_rgbs = e(B, 3, S, S), e(B, 1, S, S), e(B, 3, S, S)
         self.dmaps = e(B, 9, S, S)
         self.tile_flags = torch.zeros(B, (S + 3) // 4, (S + 3) // 4, dtype=torch.uint8, device=dev)
         self.sums = e(L.LOSS_NSUMS + 2 * B)
@@ -160,29 +171,51 @@ class FusedHandStep:
         self.g_light_dir, self.g_light_color = take(3 * B, (B, 3)), take(3 * B, (B, 3))
         self.g_verts, self.g_pose, self.g_betas = e(B, V, 3), e(B, 48), e(B, 10)
         self.gauss = ops.gauss_taps(dev)
-        self.params = ops.shade_params(B, S, S, K, Fm, V, 2 if soft else 0, 1, sigma, gamma, (1.0, 1.0, 1.0),
+        self.params = ops.shade_params(B, Sr, Sr, K, Fm, V, 2 if soft else 0, 1, sigma, gamma, (1.0, 1.0, 1.0),
                                        (0.5, 0.5, 0.5), (0.2, 0.2, 0.2), (1.0, 1.0, 1.0), (0.8, 0.8, 0.8),
                                        (0.2, 0.2, 0.2), 30.0, tex_shape=self.texture.shape[:3], VT=self.verts_uvs.shape[0])
         self.launches_per_step = 11   # kernels of ours per step() (setup, mano, geom, raster+shade, loss | 5 bwd) + 1 memset
 
     # ---------------------------------------------------------------------------------------
     def forward(self, pose, betas, focal, prp, root_xyz, light_dir, light_color, imgs, seg):
-        B, S, K = self.B, self.S, self.K
+        B, S, K, Sr = self.B, self.S, self.K, self.Sr
         ops.mano_forward_raw(self.hm, pose, betas, None, self.verts, None)
         ops.geom_forward_raw(self.topo, self.verts, 9, root_xyz, focal, prp, self.joints, self.verts_rel,
                              self.verts_view, self.verts_ndc, self.vnormals, self.face_verts)
-        r = ops.raster_args(self.face_verts, self.mesh_first, self.mesh_nf, S, S, K, self.blur, True, self.blur > 0,
-                            False, self.p2f, self.zbuf, self.bary, self.dists, self.ws)
-        s = ops.shade_fwd_args(self.params, (self.p2f, self.zbuf, self.bary, self.dists), self.topo.faces,
-                               self.verts_view, self.vnormals, self.faces_uvs, self.verts_uvs, self.texture,
-                               light_dir, light_color, self.image)
-        L.call("hfr_raster_shade_forward", L.HfrRasterShadeArgs(r, s))
+        self.launch_raster_shade(light_dir, light_color, imgs)
         self.sums.zero_()
         self._loss_args = L.HfrLossArgs(B, S, S, self.sil_scale, 1, 1, 1, L.ptr(self.image), None, L.ptr(imgs, F32),
                                         L.ptr(seg, F32), L.ptr(self.sums), L.ptr(self.gauss), L.ptr(self.dmaps),
                                         L.ptr(self.tile_flags))
         L.call("hfr_loss_forward", self._loss_args)
+
+    def launch_raster_shade(self, light_dir, light_color, imgs=None):
+        """setup + rasterize + shade (+ SSAA pool and output split when aa_factor > 1) - two launches."""
+        K, Sr = self.K, self.Sr
+        r = ops.raster_args(self.face_verts, self.mesh_first, self.mesh_nf, Sr, Sr, K, self.blur, True, self.blur > 0,
+                            False, self.p2f, self.zbuf, self.bary, self.dists, self.ws)
+        s = ops.shade_fwd_args(self.params, (self.p2f, self.zbuf, self.bary, self.dists), self.topo.faces,
+                               self.verts_view, self.vnormals, self.faces_uvs, self.verts_uvs, self.texture,
+                               light_dir, light_color, self.image if self.aa == 1 else None)
+        if self.aa == 1:
+            L.call("hfr_raster_shade_forward", L.HfrRasterShadeArgs(r, s))
+        else:
+            nchw = self.re_img is not None
+            L.call("hfr_raster_shade_pool_forward",
+                   L.HfrRasterShadePoolArgs(r, s, self.aa, int(self.binarize), L.ptr(imgs, F32) if nchw else None,
+                                            L.ptr(self.image), L.ptr(self.re_img), L.ptr(self.re_sil),
+                                            L.ptr(self.mask_rgbs)))
         self._shade_args = s
+
+    def launch_shade_backward(self):
+        """shade' + blend' + rasterize' (+ avg_pool2d' when aa_factor > 1) in one launch; accumulates into self.acc."""
+        B = self.B
+        sb = L.HfrShadeBwdArgs(self._shade_args, L.ptr(self.g_image), None, None, None, L.ptr(self.verts_ndc),
+                               L.ptr(self.g_ndc), float(self.blur), 1, int(self.blur > 0), L.ptr(self.g_view),
+                               L.ptr(self.g_vn), L.ptr(self.g_texture), L.ptr(self.g_light_dir),
+                               L.ptr(self.g_light_color), ops.raster_tile_box(self.ws, B * self.topo.F, B),
+                               self.aa if self.aa > 1 else 0, int(self.binarize))
+        L.call("hfr_shade_backward", sb)
 
     def backward(self, pose, betas, focal, prp, root_xyz, shared_grad_hook=None):
         """shared_grad_hook(g_texture) -> work handles: called as soon as the gradient of the shared texture is
@@ -192,11 +225,7 @@ class FusedHandStep:
                              self.n_global, L.ptr(self.g_image), None)
         L.call("hfr_loss_backward", a)
         self.acc.zero_()
-        sb = L.HfrShadeBwdArgs(self._shade_args, L.ptr(self.g_image), None, None, None, L.ptr(self.verts_ndc),
-                               L.ptr(self.g_ndc), float(self.blur), 1, int(self.blur > 0), L.ptr(self.g_view),
-                               L.ptr(self.g_vn), L.ptr(self.g_texture), L.ptr(self.g_light_dir),
-                               L.ptr(self.g_light_color), ops.raster_tile_box(self.ws, B * self.topo.F, B))
-        L.call("hfr_shade_backward", sb)
+        self.launch_shade_backward()
         works = shared_grad_hook(self.g_texture) if shared_grad_hook is not None else ()
         ops.geom_backward_raw(self.topo, self.verts, 9, root_xyz, focal, prp, None, None, self.g_view, self.g_ndc,
                               self.g_vn, self.g_verts)

@@ -22,7 +22,7 @@ extern "C" {
 #define HFR_EINVAL 1    /* bad argument (shape, K out of range, null pointer)      */
 #define HFR_ECUDA 2     /* CUDA runtime error at launch                            */
 #define HFR_EUNSUPPORTED 3
-#define HFR_ABI_VERSION 2
+#define HFR_ABI_VERSION 3
 
 #define HFR_MAX_JOINTS 32
 #define HFR_MAX_K 16
@@ -246,6 +246,11 @@ typedef struct HfrShadeBwdArgs {
   /* optional: per-mesh tile box the rasterizer's setup pass left in its workspace (hfr_raster_tile_box);
    * tiles outside a mesh's footprint then leave without reading the Fragments.  NULL disables. */
   const uint32_t* tile_box;
+  /* SSAA-fused path (hfr_raster_shade_pool_forward): when pool_aa > 1, g_image is the gradient of the POOLED
+   * RGBA image, (N,H/pool_aa,W/pool_aa,4); every rasterised pixel takes g/pool_aa^2 of its pooled pixel
+   * (avg_pool2d backward, models_res_nimble.py:211) and, with pool_binarize, no gradient reaches alpha (the
+   * reference binarises re_sil in place, :219).  0 or 1 = g_image is full resolution. */
+  int32_t pool_aa, pool_binarize;
 } HfrShadeBwdArgs;
 int hfr_shade_backward(const HfrShadeBwdArgs* a, void* stream);
 /* Address of the (N,4) uint32 tile box {txmin, 255-txmax, tymin, 255-tymax} (16x16-pixel tiles) inside a
@@ -259,6 +264,24 @@ typedef struct HfrRasterShadeArgs {
   HfrShadeFwdArgs s;                /* its Fragments pointers are ignored (taken from r)   */
 } HfrRasterShadeArgs;
 int hfr_raster_shade_forward(const HfrRasterShadeArgs* a, void* stream);
+
+/* Fused rasterize + shade + SSAA pool + output split: the reference's own render setting
+ * (models_res_nimble.py:74-96 image_size=672, faces_per_pixel=1; :208-220 render, avg_pool2d(3,3),
+ * RGB/alpha split, in-place binarisation, maskRGBs) in ONE pass: Fragments are written at the
+ * rasterised resolution (r.H, r.W), the full-resolution RGBA image is never materialised
+ * (s.image may be NULL) and the pooled outputs leave the SM directly.
+ * r.H and r.W must be multiples of aa.  pooled is required; the NCHW outputs are optional. */
+typedef struct HfrRasterShadePoolArgs {
+  HfrRasterArgs r;
+  HfrShadeFwdArgs s;                /* Fragments pointers ignored (taken from r); image optional */
+  int32_t aa, binarize;
+  const float* images_in;           /* (N,3,H/aa,W/aa) network input for mask_rgbs, or NULL */
+  float* pooled;                    /* (N,H/aa,W/aa,4) RGBA, alpha binarised when `binarize` (loss kernels, nhwc=1) */
+  float* re_img;                    /* (N,3,H/aa,W/aa) or NULL                              */
+  float* re_sil;                    /* (N,1,H/aa,W/aa) or NULL                              */
+  float* mask_rgbs;                 /* (N,3,H/aa,W/aa) or NULL (needs images_in)            */
+} HfrRasterShadePoolArgs;
+int hfr_raster_shade_pool_forward(const HfrRasterShadePoolArgs* a, void* stream);
 
 /* ------------------------------------------------------------------ SSAA pooling + output split
  * models_res_nimble.py:210-220: NHWC->NCHW, avg_pool2d(aa,aa), split RGB / alpha,

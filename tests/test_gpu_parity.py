@@ -476,6 +476,78 @@ def test_fused_step_vs_oracle(hf, mano):
     assert (step.p2f == p2f0).all() and (step.zbuf == z0).all()
 
 
+@pytest.mark.parametrize("S,aa,B", [(32, 3, 3), (40, 2, 2)])
+def test_fused_ssaa_step_vs_oracle_and_modular(hf, mano, S, aa, B):
+    """SURVEY 8(f) row 1 - the reference's own render setting (672^2 -> 3x3 pool, K=1, hard Phong, binarised
+    alpha; models_res_nimble.py:74-96, 208-220) as ONE fused pass, at a small size: Fragments bit-exact vs the
+    C oracle at the rasterised resolution, pooled outputs vs the oracle pipeline AND vs the modular kernels
+    (raster+shade at full resolution, then hfr_pool_forward), losses and gradients vs oracle autograd."""
+    from hifihr_b200 import _lib as L
+    from hifihr_b200 import ops
+    K, Sr = 1, S * aa
+    inp = P.synthetic_inputs(B, S=S, seed=77)
+    lam = dict(texture=1.0, mrgb=0.5, ssim_tex=0.7, sil=0.3, iou=0.2)
+    step = hf.FusedHandStep(B, image_size=S, faces_per_pixel=K, soft=False, texture_size=64, lambdas=lam, device=DEV,
+                            aa_factor=aa, binarize=True, sil_scale=255.0, want_nchw=True)
+    tex = step.texture.detach().cpu().clone()
+    oi = {k: v.clone() for k, v in inp.items()}
+    for k in ("pose", "betas", "light_dir", "light_color"):
+        oi[k].requires_grad_(True)
+    tex_o = tex.clone().requires_grad_(True)
+    ro = P.render_path(mano, oi, tex_o, image_size=S, aa=aa, K=K, blur_radius=0.0, soft=False, binarize=True)
+    loss_o, terms_o = P.total_loss(ro, oi, lam, 255.0)
+    loss_o.backward()
+    fcl, prp = p3d.ndc_intrinsics(inp["Ks"])
+    d = lambda t: t.to(DEV).contiguous()  # noqa: E731
+    args = (d(inp["pose"]), d(inp["betas"]), d(-fcl), d(prp), d(inp["root_xyz"]), d(inp["light_dir"]),
+            d(inp["light_color"]), d(inp["imgs"]), d(inp["segms_gt"].float()))
+    step.step(*args)
+    torch.cuda.synchronize()
+    # Fragments at the rasterised resolution: bit-exact against the C oracle on the kernel's own face_verts
+    Fm = 1538
+    ref = raster_c.rasterize_naive(step.face_verts.cpu(), [i * Fm for i in range(B)], [Fm] * B, Sr, 0.0, K, threads=8)
+    assert step.p2f.shape == (B, Sr, Sr, K)
+    assert (step.p2f.cpu() == ref[0]).all() and (step.zbuf.cpu() == ref[1]).all()
+    assert (step.bary.cpu() == ref[2]).all() and (step.dists.cpu() == ref[3]).all()
+    # modular kernels on the same geometry: full-resolution image, then the pooling kernel
+    full = torch.empty(B, Sr, Sr, 4, device=DEV)
+    fr2 = [torch.empty_like(t) for t in (step.p2f, step.zbuf, step.bary, step.dists)]
+    r = ops.raster_args(step.face_verts, step.mesh_first, step.mesh_nf, Sr, Sr, K, 0.0, True, False, False, *fr2, step.ws)
+    sa = ops.shade_fwd_args(step.params, fr2, step.topo.faces, step.verts_view, step.vnormals, step.faces_uvs,
+                            step.verts_uvs, step.texture, args[5], args[6], full)
+    L.call("hfr_raster_shade_forward", L.HfrRasterShadeArgs(r, sa))
+    re_img, re_sil, mask = (torch.empty(B, 3, S, S, device=DEV), torch.empty(B, 1, S, S, device=DEV),
+                            torch.empty(B, 3, S, S, device=DEV))
+    L.call("hfr_pool_forward", L.HfrPoolArgs(B, S, S, aa, 1, L.ptr(full), L.ptr(args[7]), L.ptr(re_img), L.ptr(re_sil), L.ptr(mask)))
+    torch.cuda.synchronize()
+    assert (fr2[0] == step.p2f).all() and (fr2[1] == step.zbuf).all()
+    assert (step.re_img - re_img).abs().max() < 1e-6 and (step.re_sil == re_sil).all() and (step.mask_rgbs == mask).all()
+    assert (step.image[..., :3].permute(0, 3, 1, 2) == step.re_img).all() and (step.image[..., 3:4].permute(0, 3, 1, 2) == step.re_sil).all()
+    assert set(step.re_sil.unique().tolist()) <= {0.0, 255.0}
+    # against the oracle pipeline (a handful of edge pixels may flip: projected verts differ in the last bit)
+    diff_img = (step.re_img.cpu() - ro["re_img"]).abs().amax(1)
+    assert (diff_img > 1e-4).float().mean() < 2e-3
+    assert ((step.re_sil.cpu() != ro["re_sil"]).float().mean()) < 2e-3
+    terms = step.loss_terms().cpu()
+    for i, k in enumerate(("texture", "mrgb", "ssim_tex", "sil", "iou")):
+        assert abs(float(terms[i]) * lam[k] - float(terms_o[k])) < 5e-4 * max(1.0, abs(float(terms_o[k]))), k
+    assert rel_err(step.g_pose, oi["pose"].grad) < 2e-2
+    assert rel_err(step.g_betas, oi["betas"].grad) < 2e-2
+    assert rel_err(step.g_texture, tex_o.grad) < 2e-2
+    assert rel_err(step.g_light_color, oi["light_color"].grad) < 2e-2
+    assert rel_err(step.g_light_dir, oi["light_dir"].grad) < 2e-2
+
+
+def test_fused_ssaa_rejects_bad_sizes(hf):
+    from hifihr_b200 import _lib as L
+    a = L.HfrRasterShadePoolArgs()
+    a.r.N, a.r.H, a.r.W, a.r.K = 0, 50, 50, 1
+    a.s.p.N, a.s.p.H, a.s.p.W, a.s.p.K = 0, 50, 50, 1
+    a.aa = 3
+    with pytest.raises(ValueError):
+        L.call("hfr_raster_shade_pool_forward", a)
+
+
 def test_full_size_properties_c2(hf, mano):
     """BASELINE config 2 sizes (B=64, 224^2, K=4, soft): size-independent properties + a sampled bit-exact check."""
     B, S, K = 64, 224, 4

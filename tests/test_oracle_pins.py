@@ -211,7 +211,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.ENTRY_POINTS), declared ^ set(_lib.ENTRY_POINTS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.hfr_abi_version() == 2
+    assert lib.hfr_abi_version() == 3
 
 
 def test_ctypes_struct_sizes_match_header():
@@ -221,7 +221,7 @@ def test_ctypes_struct_sizes_match_header():
     from hifihr_b200 import _lib
     names = ["HfrHandModel", "HfrManoFwdArgs", "HfrManoBwdArgs", "HfrTopology", "HfrGeomFwdArgs", "HfrGeomBwdArgs",
              "HfrRasterArgs", "HfrRasterBwdArgs", "HfrShadeParams", "HfrShadeFwdArgs", "HfrShadeBwdArgs",
-             "HfrRasterShadeArgs", "HfrPoolArgs", "HfrPoolBwdArgs", "HfrLossArgs", "HfrLossBwdArgs", "HfrKeypointArgs",
+             "HfrRasterShadeArgs", "HfrRasterShadePoolArgs", "HfrPoolArgs", "HfrPoolBwdArgs", "HfrLossArgs", "HfrLossBwdArgs", "HfrKeypointArgs",
              "HfrKeypointBwdArgs"]
     src = '#include <stdio.h>\n#include "hifihr_b200.h"\nint main(){' + "".join(
         f'printf("%zu\\n", sizeof({n}));' for n in names) + "return 0;}"
