@@ -110,7 +110,7 @@ class HfrPoolBwdArgs(C.Structure):
 class HfrLossArgs(C.Structure):
     _fields_ = [("N", i32), ("H", i32), ("W", i32), ("sil_scale", f32), ("want_ssim", i32), ("want_grad", i32), ("nhwc", i32),
                 ("re_img", vp), ("re_sil", vp), ("imgs", vp), ("seg", vp), ("sums", vp), ("gauss", vp), ("dmaps", vp),
-                ("tile_flags", vp)]
+                ("tile_flags", vp), ("mask_mode", i32)]
 
 
 class HfrLossBwdArgs(C.Structure):
@@ -129,6 +129,7 @@ class HfrKeypointBwdArgs(C.Structure):
 
 
 LOSS_NSUMS = 8
+LOSS_L2 = 5
 KP_NSUMS = 8
 KP_TERMS = ("joint_2d", "joint_3d", "vert_3d", "bone_direc", "bone_direc_3d", "edge_length", "mscale")
 ENTRY_POINTS = [

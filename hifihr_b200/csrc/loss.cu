@@ -110,6 +110,10 @@ __device__ __forceinline__ float ssim_point(float m1, float m2, float e11, float
 
 constexpr size_t kLossFwdSmem = (size_t)(6 * kLH * kXP + 5 * kLH * kHP) * sizeof(float);
 
+// METRIC = the evaluation-time texture metrics (train_hrnet.py:149-161, compute_texture_metric.py:49-60): both
+// images are multiplied by the SAME mask (mask_mode 1: segms_gt, 2: re_sil > 0 as for HO3D) and the sum of squared
+// differences (-> L2 / PSNR) is accumulated next to L1 and SSIM.  The training variant compiles without it.
+template <bool METRIC>
 __global__ void __launch_bounds__(kLossThreads, 3) loss_fwd_kernel(HfrLossArgs a) {
   extern __shared__ __align__(16) float lsm[];
   float (*xs3)[kLH][kXP] = reinterpret_cast<float (*)[kLH][kXP]>(lsm);                       // [3]
@@ -125,7 +129,7 @@ __global__ void __launch_bounds__(kLossThreads, 3) loss_fwd_kernel(HfrLossArgs a
 #pragma unroll
     for (int t = 0; t < 11; ++t) g[t] = __ldg(a.gauss + t);
   }
-  float l1 = 0.f, sr = 0.f, st = 0.f, sl = 0.f, ss = 0.f, mul = 0.f, add = 0.f;
+  float l1 = 0.f, sr = 0.f, st = 0.f, sl = 0.f, ss = 0.f, mul = 0.f, add = 0.f, l2 = 0.f;
   bool nz_halo = false;   // any non-zero x / y sample in the tile's halo
   __shared__ unsigned char sub_nz[64];   // per 4x4 block of the interior: holds a non-zero sample
   if (tid < 64) sub_nz[tid] = 0;
@@ -170,16 +174,21 @@ __global__ void __launch_bounds__(kLossThreads, 3) loss_fwd_kernel(HfrLossArgs a
       const int hy = i / kLH, hx = i - hy * kLH;
       float vx[3] = {0.f, 0.f, 0.f}, vy[3] = {0.f, 0.f, 0.f};
       if (ok[u]) {
-        const float rgb[3] = {q[u].x, q[u].y, q[u].z}, sil = q[u].w, seg = sg[u], s = sil * inv_scale;
+        const float rgb[3] = {q[u].x, q[u].y, q[u].z}, sil = q[u].w, seg = sg[u];
+        const float mm = a.mask_mode == 2 ? (sil > 0.0f ? 1.0f : 0.0f) : seg;   // METRIC: one mask for both images
+        const float s = METRIC ? mm : sil * inv_scale, sy = METRIC ? mm : seg;
         const bool interior = hx >= kR && hx < kR + kLT && hy >= kR && hy < kR + kLT;
         bool nz_in = false;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           vx[c] = rgb[c] * s;
-          vy[c] = seg * im[u][c];
+          vy[c] = sy * im[u][c];
           const bool nzv = vx[c] != 0.0f || vy[c] != 0.0f;
           nz_halo |= nzv;
-          if (interior) { l1 += fabsf(vx[c] - vy[c]); sr += vx[c]; st += vy[c]; nz_in |= nzv; }
+          if (interior) {
+            l1 += fabsf(vx[c] - vy[c]); sr += vx[c]; st += vy[c]; nz_in |= nzv;
+            if (METRIC) { const float df = vx[c] - vy[c]; l2 += df * df; }
+          }
         }
         if (nz_in) sub_nz[((hy - kR) >> 2) * 8 + ((hx - kR) >> 2)] = 1;   // benign race: every writer stores 1
         if (interior) { sl += fabsf(sil - seg); mul += sil * seg; add += sil + seg; }
@@ -294,19 +303,20 @@ __global__ void __launch_bounds__(kLossThreads, 3) loss_fwd_kernel(HfrLossArgs a
     }
   }
   // ---- block reduction of the 7 partial sums: one atomic each per CTA -------------------------------
-  float vals[7] = {l1, sr, st, sl, ss, mul, add};
+  float vals[8] = {l1, sr, st, sl, ss, mul, add, l2};
+  constexpr int NV = METRIC ? 8 : 7;
 #pragma unroll
-  for (int i = 0; i < 7; ++i) vals[i] = warp_sum(vals[i]);
+  for (int i = 0; i < NV; ++i) vals[i] = warp_sum(vals[i]);
   if (lane == 0) {
 #pragma unroll
-    for (int i = 0; i < 7; ++i) red[warp][i] = vals[i];
+    for (int i = 0; i < NV; ++i) red[warp][i] = vals[i];
   }
   __syncthreads();
-  if (tid < 7) {
+  if (tid < NV) {
     float t = 0.f;
 #pragma unroll
     for (int w = 0; w < kLossThreads / 32; ++w) t += red[w][tid];
-    const int dst = tid < 5 ? tid : (tid == 5 ? HFR_LOSS_NSUMS + n : HFR_LOSS_NSUMS + a.N + n);
+    const int dst = tid < 5 ? tid : (tid == 5 ? HFR_LOSS_NSUMS + n : (tid == 6 ? HFR_LOSS_NSUMS + a.N + n : HFR_LOSS_L2));
     if (t != 0.0f) atomicAdd(a.sums + dst, t);
   }
 }
@@ -537,12 +547,16 @@ extern "C" int hfr_loss_forward(const HfrLossArgs* a, void* stream) {
   HFR_CHECK_ARG(a->re_img && (a->nhwc || a->re_sil) && a->imgs && a->seg && a->sums, "loss_forward: null pointer");
   HFR_CHECK_ARG(!a->want_ssim || a->gauss, "loss_forward: SSIM needs the Gaussian taps");
   dim3 grid((a->W + kLT - 1) / kLT, (a->H + kLT - 1) / kLT, a->N);
+  HFR_CHECK_ARG(a->mask_mode >= 0 && a->mask_mode <= 2, "loss_forward: mask_mode must be 0, 1 or 2");
+  HFR_CHECK_ARG(a->mask_mode == 0 || !(a->want_grad && a->dmaps), "loss_forward: the metric modes have no backward");
   static bool attr_set = false;   // benign race: the attribute is idempotent
   if (!attr_set) {
-    cudaFuncSetAttribute(loss_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLossFwdSmem);
+    cudaFuncSetAttribute(loss_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLossFwdSmem);
+    cudaFuncSetAttribute(loss_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLossFwdSmem);
     attr_set = true;
   }
-  loss_fwd_kernel<<<grid, kLossThreads, kLossFwdSmem, (cudaStream_t)stream>>>(*a);
+  if (a->mask_mode == 0) loss_fwd_kernel<false><<<grid, kLossThreads, kLossFwdSmem, (cudaStream_t)stream>>>(*a);
+  else loss_fwd_kernel<true><<<grid, kLossThreads, kLossFwdSmem, (cudaStream_t)stream>>>(*a);
   HFR_CHECK_LAUNCH("loss_forward");
   return HFR_OK;
 }

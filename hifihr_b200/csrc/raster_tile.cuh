@@ -28,6 +28,7 @@ constexpr int kTileW = 16, kTileH = 16, kRasterThreads = 256;
 constexpr int kListCap = 256;   // faces per staged batch
 constexpr int kRecFloats = 20;  // 80-byte record (9 vertex floats, dilated bbox, area, zmin, face id, pad): the 20-word
                                 // stride spreads the per-lane LDS.128 of the fine pass over all bank groups
+constexpr int kDepthBuckets = 32;   // one per lane: every warp scans the histogram in registers
 constexpr int kChunk = 32 * kRasterThreads;  // faces handled per coarse pass (one hit bit per face per thread)
 
 struct RasterSmem {
@@ -35,7 +36,10 @@ struct RasterSmem {
   uint32_t wmask[kRasterThreads / 32][kListCap / 32][32];   // per warp, per 32 list entries: one face mask per lane (pixel)
   float tabx[kTileW], taby[kTileH];                          // NDC sample positions of the tile's columns / rows
   int wsum[kRasterThreads / 32];
-  uint16_t order[kListCap];   // record indices sorted front to back (by the faces' nearest vertex)
+  uint16_t order[kListCap];   // record indices ordered front to back (depth buckets of the faces' nearest vertex)
+  float zred[2][kRasterThreads / 32];   // per-warp min / max of the batch's nearest-vertex depths
+  int hist[kDepthBuckets];              // faces per depth bucket
+  int bmin[kDepthBuckets];              // smallest nearest-vertex depth in the bucket (float bits; depths are > 0)
 };
 
 // 32x32 bit-matrix transpose across the warp: on return bit i of lane L = bit L of lane i's input
@@ -112,12 +116,12 @@ __device__ __forceinline__ float pix_to_ndc_pre(int i, float range, float offset
 //           single pass over the packed tile ranges; one block-wide scan of the hit counts then
 //           gives every thread its slot in the tile list.  A tile no face touches leaves after
 //           that scan.
-//   stage:  listed faces are gathered once per tile into 80-byte shared records and ranked front
-//           to back by their nearest vertex (rank sort in shared memory).
+//   stage:  listed faces are gathered once per tile into 80-byte shared records and ordered front
+//           to back by their nearest vertex (counting sort over depth buckets in shared memory).
 //   fine:   per 32 list entries lane i computes which of the warp's 8x4 pixels lie in face i's dilated
 //           bbox; the 32 masks are transposed (5 shuffles) into one face mask per pixel.  Each lane then
-//           walks its own faces front to back (per-lane LDS.128 of the record) and stops at the first face
-//           whose nearest vertex is not in front of its current K-th depth, so the exact coverage / depth /
+//           walks its own faces front to back (per-lane LDS.128 of the record), skips faces whose nearest
+//           vertex is not in front of its current K-th depth and stops once a whole depth bucket is, so the exact coverage / depth /
 //           distance math runs on densely populated warps.  The top-K is ordered by (z, packed face index),
 //           the CPU reference's order, ties included.
 template <int KMAX>
@@ -213,25 +217,56 @@ __device__ __forceinline__ void raster_tile(const HfrRasterArgs& a, const uint32
             dst[1] = make_float4(r[4], r[5], r[6], r[7]);
             dst[2] = make_float4(r[8], xmin, xmax, ymin);
             // zmin shrunk by 1e-5: the rounded pz of a convex combination can undershoot the smallest z by a few ulp
-            dst[3] = make_float4(ymax, area, hfr_min3(r[2], r[5], r[8]) * 0.99999f, __int_as_float(face));
+            // (slot 12 = the walk's exit depth, filled by the depth-bucket pass below)
+            dst[3] = make_float4(0.0f, area, hfr_min3(r[2], r[5], r[8]) * 0.99999f, __int_as_float(face));
+            sm.rec[(pos - lbase) * kRecFloats + 16] = ymax;
           }
           ++pos;
         }
       }
       __syncthreads();
-      // depth order: rank of every record by (shrunk zmin, list position); faces nearest to the camera are
-      // visited first, so a pixel's K-th depth drops quickly and most faces behind it fail the zmin test
-      if (tid < bcnt) {
-        int rank = tid;
-        if (zcull) {
-          const float zi = sm.rec[tid * kRecFloats + 14];
-          rank = 0;
-          for (int j = 0; j < bcnt; ++j) {
-            const float zj = sm.rec[j * kRecFloats + 14];
-            rank += (zj < zi || (zj == zi && j < tid)) ? 1 : 0;
-          }
+      // depth order: the records are bucketed by their (shrunk) nearest-vertex depth into kDepthBuckets equal
+      // slices of the batch's depth range (a counting sort: O(1) per face instead of a rank by pairwise compares).
+      // Faces nearest to the camera are visited first, so a pixel's K-th depth drops quickly and most faces behind
+      // it fail the zmin test.  Inside a bucket the order is arbitrary, therefore the walk may only STOP at a face
+      // when the smallest depth of that face's bucket (slot 12 of the record) is not in front of the K-th depth:
+      // later faces sit in the same or a farther bucket (the bucket index is monotone in the depth).
+      if (zcull) {
+        const float zi = tid < bcnt ? sm.rec[tid * kRecFloats + 14] : INFINITY;
+        float lo = zi, hi = tid < bcnt ? zi : -INFINITY;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+          hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
         }
-        sm.order[rank] = (uint16_t)tid;
+        if (lane == 0) { sm.zred[0][warp] = lo; sm.zred[1][warp] = hi; }
+        if (tid < kDepthBuckets) { sm.hist[tid] = 0; sm.bmin[tid] = 0x7f800000; }
+        __syncthreads();
+        float zlo = sm.zred[0][0], zhi = sm.zred[1][0];
+#pragma unroll
+        for (int w = 1; w < kRasterThreads / 32; ++w) { zlo = fminf(zlo, sm.zred[0][w]); zhi = fmaxf(zhi, sm.zred[1][w]); }
+        const float scale = zhi > zlo ? (float)kDepthBuckets / (zhi - zlo) : 0.0f;
+        int b = 0, pos = 0;
+        if (tid < bcnt) {
+          b = min(kDepthBuckets - 1, (int)((zi - zlo) * scale));
+          pos = atomicAdd(&sm.hist[b], 1);
+          atomicMin(&sm.bmin[b], __float_as_int(zi));
+        }
+        __syncthreads();
+        int incl = sm.hist[lane];   // every warp scans the 32 bucket counts in registers
+        const int own = incl;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += t;
+        }
+        const int base = __shfl_sync(0xffffffffu, incl - own, b);
+        if (tid < bcnt) {
+          sm.order[base + pos] = (uint16_t)tid;
+          sm.rec[tid * kRecFloats + 12] = __int_as_float(sm.bmin[b]);
+        }
+      } else if (tid < bcnt) {
+        sm.order[tid] = (uint16_t)tid;
       }
       __syncthreads();
       if (warp_active) {
@@ -243,7 +278,7 @@ __device__ __forceinline__ void raster_tile(const HfrRasterArgs& a, const uint32
           if (i < bcnt) {
             const float* rp = sm.rec + (int)sm.order[i] * kRecFloats;
             const float4 q2 = *reinterpret_cast<const float4*>(rp + 8);   // (z2, xmin, xmax, ymin)
-            const float ymax = rp[12];
+            const float ymax = rp[16];
             uint32_t xm = 0, ym = 0;
 #pragma unroll
             for (int e = 0; e < 8; ++e) { const float x = sm.tabx[lx0 + e]; xm |= (x < q2.y || x > q2.z) ? 0u : (1u << e); }
@@ -273,8 +308,11 @@ __device__ __forceinline__ void raster_tile(const HfrRasterArgs& a, const uint32
           }
           float4 q3 = make_float4(0.f, 0.f, 0.f, 0.f);
           if (ri >= 0) {
-            q3 = *reinterpret_cast<const float4*>(sm.rec + ri * kRecFloats + 12);   // (ymax, area, zmin, face)
-            if (zcull && !(q3.z < top.worst())) { ri = -1; done = true; }
+            q3 = *reinterpret_cast<const float4*>(sm.rec + ri * kRecFloats + 12);   // (bucket zmin, area, zmin, face)
+            if (zcull && !(q3.z < top.worst())) {   // this face cannot enter the top K ...
+              if (!(q3.x < top.worst())) done = true;   // ... and neither can any later one
+              ri = -1;
+            }
           }
           if (!__any_sync(0xffffffffu, ri >= 0)) {
             if (__all_sync(0xffffffffu, done)) break;

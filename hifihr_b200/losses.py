@@ -31,6 +31,28 @@ def trans_proj_j2d(outputs, Ks_this, scales=None, is_ortho=False, root_xyz=None,
     return j2d
 
 
+def texture_metrics(examples, outputs, dat_name="FreiHAND") -> dict:
+    """The evaluation-time texture metrics of train_hrnet.py:149-161 (and compute_texture_metric.py:49-60):
+    PSNR, SSIM, L1, L2 between the masked rendering and the masked input, one forward kernel pass
+    (csrc/loss.cu, metric mode).  Mask = segms_gt, or re_sil > 0 for dat_name == 'HO3D' (:150-155).
+    Returns 0-dim device tensors (the reference calls .item() on each; LPIPS needs a network and is not part
+    of this path)."""
+    from . import _lib as L
+    c = ops._cu
+    re_img, re_sil, imgs = c(outputs["re_img"].detach()), c(outputs["re_sil"].detach()), c(examples["imgs"])
+    N, _, H, W = re_img.shape
+    seg = c(examples["segms_gt"].float()) if "segms_gt" in examples else torch.zeros(N, H, W, device=re_img.device)
+    sums = torch.zeros(L.LOSS_NSUMS + 2 * N, dtype=torch.float32, device=re_img.device)
+    g = ops.gauss_taps(re_img.device)
+    a = L.HfrLossArgs(N, H, W, 1.0, 1, 0, 0, L.ptr(re_img, torch.float32), L.ptr(re_sil, torch.float32),
+                      L.ptr(imgs, torch.float32), L.ptr(seg, torch.float32), L.ptr(sums), L.ptr(g), None, None,
+                      2 if dat_name == "HO3D" else 1)
+    L.call("hfr_loss_forward", a)
+    cnt = float(N * 3 * H * W)
+    l2 = sums[L.LOSS_L2] / cnt
+    return {"psnr": -10 * torch.log10(l2), "ssim": sums[4] / cnt, "l1": sums[0] / cnt, "l2": l2}
+
+
 class LossFunction:
     def __init__(self, sil_scale: float = 255.0):
         # 255: reference mode (re_sil binarised to {0,255}, models_res_nimble.py:219; losses.py:359 divides by 255)

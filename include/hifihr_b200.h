@@ -318,6 +318,7 @@ int hfr_pool_backward(const HfrPoolBwdArgs* a, void* stream);
 #define HFR_LOSS_SUM_T 2     /* sum target                    */
 #define HFR_LOSS_SIL 3       /* sum |re_sil - seg|            */
 #define HFR_LOSS_SSIM 4      /* sum ssim_map                  */
+#define HFR_LOSS_L2 5        /* sum (rim - target)^2, metric modes only (mask_mode != 0) */
 #define HFR_LOSS_NSUMS 8     /* then per-sample: mul[N], add[N] for IoU */
 typedef struct HfrLossArgs {
   int32_t N, H, W;
@@ -332,6 +333,10 @@ typedef struct HfrLossArgs {
   uint8_t* tile_flags;              /* optional (N, ceil(H/4), ceil(W/4)): written by the forward (1 = that 4x4 pixel
                                        block holds a non-zero masked-image sample), read by the backward to skip the
                                        SSIM stencil where it contributes exactly nothing; NULL disables the skip */
+  int32_t mask_mode;                /* 0: training losses (rim = re_img * re_sil / sil_scale, target = imgs * seg).
+                                       Evaluation-time texture metrics (train_hrnet.py:149-161; forward only):
+                                       1: both images * seg; 2: both images * (re_sil > 0) (the HO3D branch);
+                                       sums[HFR_LOSS_L1], [HFR_LOSS_L2], [HFR_LOSS_SSIM] then give L1 / L2 / PSNR / SSIM */
 } HfrLossArgs;
 int hfr_loss_forward(const HfrLossArgs* a, void* stream);
 typedef struct HfrLossBwdArgs {

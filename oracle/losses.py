@@ -78,3 +78,16 @@ def render_losses(re_img, re_sil, imgs, segms_gt, lambdas: dict, sil_scale: floa
         if "ssim_tex_self" in lambdas:
             out["ssim_tex_self"] = lambdas["ssim_tex_self"] * (1 - ssim(re_img, masked_rgbs))
     return out
+
+
+def texture_metrics(re_img, re_sil, imgs, segms_gt, dat_name="FreiHAND"):
+    """train_hrnet.py:149-161: evaluation-time PSNR / SSIM / L1 / L2 between the masked rendering and the masked
+    input (mask = re_sil > 0 for HO3D, segms_gt otherwise).  LPIPS (a network) is outside this path."""
+    if dat_name == "HO3D":
+        m = (re_sil > 0).to(re_img.dtype).repeat(1, 3, 1, 1)
+        target, pred = imgs * m, re_img * m                     # :150-152
+    else:
+        seg = segms_gt.unsqueeze(1).to(re_img.dtype)
+        target, pred = seg * imgs, re_img * seg                 # :154-155
+    mse = ((pred - target) ** 2).mean()
+    return {"psnr": -10 * torch.log10(mse), "ssim": ssim(pred, target), "l1": (pred - target).abs().mean(), "l2": mse}

@@ -579,6 +579,28 @@ def test_full_size_properties_c2(hf, mano):
         assert (z[n].cpu() == ref[1][0]).all() and (step.dists[n].cpu() == ref[3][0]).all()
 
 
+@pytest.mark.parametrize("dat_name,key", [("FreiHAND", "freihand"), ("HO3D", "ho3d")])
+def test_texture_metrics_match_reference_golden(hf, dat_name, key):
+    """evaluation-time PSNR / SSIM / L1 / L2 (train_hrnet.py:149-161) from one forward kernel
+    pass, against values computed by the unmodified reference pieces; tolerance 1e-5 relative (fp32 sums)."""
+    z = np.load(os.path.join(GOLD, "texture_metrics_reference.npz"))
+    t = lambda k: torch.tensor(z[k]).to(DEV)  # noqa: E731
+    m = hf.texture_metrics({"imgs": t("imgs"), "segms_gt": t("segms_gt")}, {"re_img": t("re_img"), "re_sil": t("re_sil")},
+                           dat_name)
+    got = np.array([float(m[k]) for k in ("psnr", "ssim", "l1", "l2")])
+    assert np.abs(got - z[key]).max() < 1e-5 * np.maximum(1.0, np.abs(z[key])).max(), (got, z[key])
+    # and against the oracle on a second, ragged size (partial loss tiles)
+    g = torch.Generator().manual_seed(3)
+    N, H = 2, 50
+    imgs, re = torch.rand(N, 3, H, H, generator=g), torch.rand(N, 3, H, H, generator=g)
+    seg = (torch.rand(N, H, H, generator=g) > 0.6).float()
+    sil = (torch.rand(N, 1, H, H, generator=g) > 0.5).float() * 255
+    mo = olosses.texture_metrics(re, sil, imgs, seg, dat_name)
+    mg = hf.texture_metrics({"imgs": imgs.to(DEV), "segms_gt": seg.to(DEV)}, {"re_img": re.to(DEV), "re_sil": sil.to(DEV)}, dat_name)
+    for k in ("psnr", "ssim", "l1", "l2"):
+        assert abs(float(mg[k]) - float(mo[k])) < 1e-5 * max(1.0, abs(float(mo[k]))), k
+
+
 # ------------------------------------------------------------------------------------------ keypoints
 @pytest.mark.parametrize("pre", ["l1.", "l2."])
 def test_keypoint_losses_match_reference_golden(hf, pre):

@@ -149,6 +149,17 @@ def test_ssim_oracle_matches_reference_golden():
     assert abs(float(olosses.ssim(a, a)) - float(z["ssim_same"])) < 1e-6
 
 
+def test_texture_metrics_oracle_matches_reference_golden():
+    """PSNR / SSIM / L1 / L2 of train_hrnet.py:149-161, both mask branches; the golden values come
+    from the unmodified utils/pytorch_ssim and the reference's MSE / L1 bodies (oracle/gen_golden_metrics.py)."""
+    z = np.load(os.path.join(GOLD, "texture_metrics_reference.npz"))
+    t = lambda k: torch.tensor(z[k])  # noqa: E731
+    for name, key in (("FreiHAND", "freihand"), ("HO3D", "ho3d")):
+        m = olosses.texture_metrics(t("re_img"), t("re_sil"), t("imgs"), t("segms_gt"), name)
+        got = np.array([float(m[k]) for k in ("psnr", "ssim", "l1", "l2")])
+        assert np.abs(got - z[key]).max() < 1e-5 * np.maximum(1.0, np.abs(z[key])).max(), (name, got, z[key])
+
+
 def test_raster_two_restatements_agree_and_golden():
     z = np.load(os.path.join(GOLD, "raster_oracle.npz"))
     fv = torch.tensor(z["face_verts"])
