@@ -79,7 +79,8 @@ __global__ void __launch_bounds__(kRasterThreads) raster_fwd_kernel(HfrRasterArg
   __shared__ RasterSmem sm;
   PixelCtx c = make_pixel_ctx(a.H, a.W);
   TopK<KMAX> top;
-  raster_tile<KMAX>(a, ranges, mesh_box, sm, c, top);
+  uint32_t perm;
+  raster_tile<KMAX, false>(a, ranges, mesh_box, sm, c, top, nullptr, perm);
   if (c.pix_active) {
     int64_t id[KMAX];
     float z[KMAX], d[KMAX], b[KMAX * 3];

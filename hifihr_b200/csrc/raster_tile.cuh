@@ -73,6 +73,23 @@ struct TopK {
   }
   // replace the worst slot and bubble towards the front, ordered by (z, face index): faces may arrive in
   // any order (the tile list is depth-sorted), ties still resolve to the smaller packed face index
+  // as insert(), for the payload cache: `perm` holds one nibble per sorted position = the physical payload slot of
+  // that entry.  The new entry takes over the slot of the entry it evicts (returned), and the nibbles follow the
+  // bubble, so payloads are written once and never moved.
+  __device__ __forceinline__ int insert_slot(float pz, int face, uint32_t& perm) {
+    const int phys = (int)((perm >> (4 * (KMAX - 1))) & 0xfu);
+    z[KMAX - 1] = pz; f[KMAX - 1] = face;
+#pragma unroll
+    for (int i = KMAX - 1; i > 0; --i) {
+      if (z[i] < z[i - 1] || (z[i] == z[i - 1] && f[i] < f[i - 1])) {
+        const float tz = z[i]; z[i] = z[i - 1]; z[i - 1] = tz;
+        const int tf = f[i]; f[i] = f[i - 1]; f[i - 1] = tf;
+        const uint32_t x = ((perm >> (4 * i)) ^ (perm >> (4 * (i - 1)))) & 0xfu;
+        perm ^= (x << (4 * i)) | (x << (4 * (i - 1)));
+      }
+    }
+    return phys;
+  }
   __device__ __forceinline__ void insert(float pz, int face) {
     z[KMAX - 1] = pz; f[KMAX - 1] = face;
 #pragma unroll
@@ -124,9 +141,16 @@ __device__ __forceinline__ float pix_to_ndc_pre(int i, float range, float offset
 //           vertex is not in front of its current K-th depth and stops once a whole depth bucket is, so the exact coverage / depth /
 //           distance math runs on densely populated warps.  The top-K is ordered by (z, packed face index),
 //           the CPU reference's order, ties included.
-template <int KMAX>
+//
+// PAY: the fused kernels keep, per thread and per top-K slot, the (barycentrics, signed distance) of the entry in
+// shared memory (`pay`, [slot][thread] float4; `perm` maps sorted position -> slot), written when a candidate enters
+// the top K.  The epilogue then reads the winners' Fragments values instead of recomputing the exact math.
+constexpr uint32_t kPermIdentity = 0x76543210u;
+template <int KMAX, bool PAY>
 __device__ __forceinline__ void raster_tile(const HfrRasterArgs& a, const uint32_t* __restrict__ tile_ranges,
-                                            const uint32_t* __restrict__ mesh_box, RasterSmem& sm, PixelCtx& c, TopK<KMAX>& top) {
+                                            const uint32_t* __restrict__ mesh_box, RasterSmem& sm, PixelCtx& c, TopK<KMAX>& top,
+                                            float4* __restrict__ pay, uint32_t& perm) {
+  perm = kPermIdentity;
   const int n = c.n, tx = c.tx, ty = c.ty;
   const bool pix_active = c.pix_active, warp_active = c.warp_active;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -327,9 +351,15 @@ __device__ __forceinline__ void raster_tile(const HfrRasterArgs& a, const uint32
             bool inside;
             if (hfr_raster_bary(xf, yf, v, q3.y, pc, clip, &pz, bc, &inside)) {
               if (top.beats_worst(pz, face)) {
-                bool keep = inside;
-                if (!keep) keep = hfr_tri_dist2(xf, yf, v) < blur;
-                if (keep) top.insert(pz, face);
+                const float dd = (PAY || !inside) ? hfr_tri_dist2(xf, yf, v) : 0.0f;
+                if (inside || dd < blur) {
+                  if (PAY) {
+                    const int slot = top.insert_slot(pz, face, perm);
+                    pay[slot * kRasterThreads] = make_float4(bc[0], bc[1], bc[2], inside ? -dd : dd);
+                  } else {
+                    top.insert(pz, face);
+                  }
+                }
               }
             }
           }

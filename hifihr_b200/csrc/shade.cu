@@ -40,9 +40,12 @@ __global__ void __launch_bounds__(256) shade_fwd_kernel(HfrShadeFwdArgs a) {
 // texture fetch and the Phong code - the kernel stays inside the instruction cache).  The blends need no second
 // pass: winners are sorted by depth, so the softmax reference depth z_max belongs to slot 0 and weights
 // accumulate on the fly.
-template <int KMAX>
+// PAY: the winners' barycentrics / signed distances come from the payload cache the tile core filled
+// (raster_tile.cuh) instead of being recomputed from the face's vertices.
+template <int KMAX, bool PAY>
 __device__ __forceinline__ void raster_shade_epilogue(const HfrRasterArgs& r, const HfrShadeFwdArgs& s, const PixelCtx& c,
-                                                      const TopK<KMAX>& top, size_t pix, float (&rgba)[4]) {
+                                                      const TopK<KMAX>& top, size_t pix, const float4* __restrict__ pay,
+                                                      uint32_t perm, float (&rgba)[4]) {
   const HfrShadeParams& P = s.p;
   const int K = r.K;
   const bool ones = P.blend == HFR_BLEND_SIGMOID_ALPHA;
@@ -80,16 +83,24 @@ __device__ __forceinline__ void raster_shade_epilogue(const HfrRasterArgs& r, co
         ba[3 * k] = -1.0f; ba[3 * k + 1] = -1.0f; ba[3 * k + 2] = -1.0f;
         continue;
       }
-      float v[9];
-      const float* __restrict__ src = r.face_verts + (size_t)face * 9;
+      float pz, bc[3], sd;
+      if (PAY) {
+        const float4 q = pay[((perm >> (4 * k)) & 0xfu) * kRasterThreads];
+        bc[0] = q.x; bc[1] = q.y; bc[2] = q.z; sd = q.w;
+        pz = top.z[0];
 #pragma unroll
-      for (int e = 0; e < 9; ++e) v[e] = __ldg(src + e);
-      const float area = XADD(hfr_edge(v[6], v[7], v[0], v[1], v[3], v[4]), HFR_KEPS);
-      float pz, bc[3];
-      bool inside;
-      hfr_raster_bary(c.xf, c.yf, v, area, r.perspective_correct, r.clip_barycentric, &pz, bc, &inside);
-      const float dd = hfr_tri_dist2(c.xf, c.yf, v);
-      const float sd = inside ? -dd : dd;
+        for (int i = 1; i < KMAX; ++i) pz = (k == i) ? top.z[i] : pz;
+      } else {
+        float v[9];
+        const float* __restrict__ src = r.face_verts + (size_t)face * 9;
+#pragma unroll
+        for (int e = 0; e < 9; ++e) v[e] = __ldg(src + e);
+        const float area = XADD(hfr_edge(v[6], v[7], v[0], v[1], v[3], v[4]), HFR_KEPS);
+        bool inside;
+        hfr_raster_bary(c.xf, c.yf, v, area, r.perspective_correct, r.clip_barycentric, &pz, bc, &inside);
+        const float dd = hfr_tri_dist2(c.xf, c.yf, v);
+        sd = inside ? -dd : dd;
+      }
       ba[3 * k] = bc[0]; ba[3 * k + 1] = bc[1]; ba[3 * k + 2] = bc[2];
 #pragma unroll
       for (int i = 0; i < KMAX; ++i)
@@ -150,18 +161,24 @@ __device__ __forceinline__ void raster_shade_epilogue(const HfrRasterArgs& r, co
 #ifndef HFR_RASTER_MINB
 #define HFR_RASTER_MINB 4
 #endif
+#ifndef HFR_PAY_MAXK
+#define HFR_PAY_MAXK 4   // payload cache for K <= this (0 disables it: the epilogue recomputes the winners)
+#endif
 template <int KMAX>
 __global__ void __launch_bounds__(kRasterThreads, (KMAX <= 4 ? HFR_RASTER_MINB : 1)) raster_shade_fwd_kernel(HfrRasterArgs r, HfrShadeFwdArgs s,
                                                                           const uint32_t* __restrict__ ranges,
                                                                           const uint32_t* __restrict__ mesh_box) {
   __shared__ RasterSmem sm;
+  constexpr bool PAY = KMAX <= HFR_PAY_MAXK;   // 16 B x K x 256 threads of payload cache next to the 30 KB tile state
+  __shared__ float4 s_pay[PAY ? KMAX * kRasterThreads : 1];
   PixelCtx c = make_pixel_ctx(r.H, r.W);
   TopK<KMAX> top;
-  raster_tile<KMAX>(r, ranges, mesh_box, sm, c, top);
+  uint32_t perm;
+  raster_tile<KMAX, PAY>(r, ranges, mesh_box, sm, c, top, s_pay + threadIdx.x, perm);
   if (!c.pix_active) return;
   const size_t pix = ((size_t)c.n * r.H + c.yi) * r.W + c.xi;
   float rgba[4];
-  raster_shade_epilogue<KMAX>(r, s, c, top, pix, rgba);
+  raster_shade_epilogue<KMAX, PAY>(r, s, c, top, pix, s_pay + threadIdx.x, perm, rgba);
   *reinterpret_cast<float4*>(s.image + pix * 4) = make_float4(rgba[0], rgba[1], rgba[2], rgba[3]);
 }
 
@@ -180,6 +197,8 @@ __global__ void __launch_bounds__(kRasterThreads, (KMAX <= 4 ? HFR_RASTER_MINB :
     HfrRasterArgs r, HfrShadeFwdArgs s, PoolOut po, const uint32_t* __restrict__ ranges, const uint32_t* __restrict__ mesh_box) {
   __shared__ RasterSmem sm;
   __shared__ float4 s_tile[kTileH * kTileW];
+  constexpr bool PAY = KMAX <= (HFR_PAY_MAXK < 2 ? HFR_PAY_MAXK : 2);   // static shared memory stays under 48 KB
+  __shared__ float4 s_pay[PAY ? KMAX * kRasterThreads : 1];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int aa = po.aa, n = blockIdx.z;
   const int lx = (warp & 1) * 8 + (lane & 7), ly = (warp >> 1) * 4 + (lane >> 3);   // this thread's pixel inside a raster tile
@@ -195,11 +214,12 @@ __global__ void __launch_bounds__(kRasterThreads, (KMAX <= 4 ? HFR_RASTER_MINB :
       c.warp_active = c.tx * kTileW + (warp & 1) * 8 < r.W && c.ty * kTileH + (warp >> 1) * 4 < r.H;
       c.xf = 0.0f; c.yf = 0.0f;
       TopK<KMAX> top;
-      raster_tile<KMAX>(r, ranges, mesh_box, sm, c, top);
+      uint32_t perm;
+      raster_tile<KMAX, PAY>(r, ranges, mesh_box, sm, c, top, s_pay + tid, perm);
       float rgba[4] = {0.f, 0.f, 0.f, 0.f};
       if (c.pix_active) {
         const size_t pix = ((size_t)n * r.H + c.yi) * r.W + c.xi;
-        raster_shade_epilogue<KMAX>(r, s, c, top, pix, rgba);
+        raster_shade_epilogue<KMAX, PAY>(r, s, c, top, pix, s_pay + tid, perm, rgba);
         if (s.image) *reinterpret_cast<float4*>(s.image + pix * 4) = make_float4(rgba[0], rgba[1], rgba[2], rgba[3]);
       }
       s_tile[ly * kTileW + lx] = make_float4(rgba[0], rgba[1], rgba[2], rgba[3]);
