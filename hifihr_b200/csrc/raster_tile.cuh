@@ -77,15 +77,15 @@ struct TopK {
   // that entry.  The new entry takes over the slot of the entry it evicts (returned), and the nibbles follow the
   // bubble, so payloads are written once and never moved.
   __device__ __forceinline__ int insert_slot(float pz, int face, uint32_t& perm) {
-    const int phys = (int)((perm >> (4 * (KMAX - 1))) & 0xfu);
+    const int phys = (int)((perm >> ((4 * (KMAX - 1)) & 31)) & 0xfu);   // (payload slots exist for KMAX <= 8 only)
     z[KMAX - 1] = pz; f[KMAX - 1] = face;
 #pragma unroll
     for (int i = KMAX - 1; i > 0; --i) {
       if (z[i] < z[i - 1] || (z[i] == z[i - 1] && f[i] < f[i - 1])) {
         const float tz = z[i]; z[i] = z[i - 1]; z[i - 1] = tz;
         const int tf = f[i]; f[i] = f[i - 1]; f[i - 1] = tf;
-        const uint32_t x = ((perm >> (4 * i)) ^ (perm >> (4 * (i - 1)))) & 0xfu;
-        perm ^= (x << (4 * i)) | (x << (4 * (i - 1)));
+        const uint32_t x = ((perm >> ((4 * i) & 31)) ^ (perm >> ((4 * (i - 1)) & 31))) & 0xfu;
+        perm ^= (x << ((4 * i) & 31)) | (x << ((4 * (i - 1)) & 31));
       }
     }
     return phys;
@@ -424,6 +424,43 @@ __device__ __forceinline__ void store_fragments(const HfrRasterArgs& a, size_t p
       }
     }
   }
+}
+
+// Is tile (tx, ty) of mesh n outside the mesh's footprint (union of its faces' tile ranges)?  CTA-uniform.
+__device__ __forceinline__ bool tile_outside_mesh(const uint32_t* __restrict__ mesh_box, int n, int tx, int ty) {
+  if (!mesh_box) return false;
+  const uint4 bx = __ldg(reinterpret_cast<const uint4*>(mesh_box) + n);
+  return tx < (int)bx.x || tx > 255 - (int)bx.y || ty < (int)bx.z || ty > 255 - (int)bx.w;
+}
+
+// -1 fill of the four Fragments tensors over one whole tile that no face touches: the tile's 16 row segments are
+// contiguous runs (16 K x {8, 4, 4, 12} B), so the CTA streams them as 448 K 128-bit evict-first stores instead of
+// 6-13 narrow stores per pixel.  Returns false (nothing written) when the tile is clipped by the image border or the
+// rows are not 16-byte aligned; the per-pixel epilogue then does the fill.
+#ifndef HFR_FILL_PLAIN
+#define HFR_FILL_PLAIN 0
+#endif
+__device__ __forceinline__ bool fill_empty_tile(const HfrRasterArgs& a, int n, int tx, int ty) {
+  const int K = a.K, W = a.W, H = a.H;
+  if ((tx + 1) * kTileW > W || (ty + 1) * kTileH > H || ((W * K) & 3)) return false;
+  const int per_row = 28 * K;                         // 128-bit units per tile row: 8K ids, 4K z, 4K dists, 12K bary
+  const int row = threadIdx.x >> 4, t16 = threadIdx.x & 15;   // 16 threads stream one tile row
+  const size_t pix = ((size_t)n * H + (size_t)ty * kTileH + row) * W + (size_t)tx * kTileW;
+  float* const p0 = reinterpret_cast<float*>(a.pix_to_face + pix * K);
+  float* const p1 = a.zbuf + pix * K;
+  float* const p2 = a.dists + pix * K;
+  float* const p3 = a.bary + pix * K * 3;
+  const float m1 = -1.0f, mi = __int_as_float(-1);
+  for (int u = t16; u < per_row; u += 16) {
+    float* dst = u < 8 * K ? p0 + 4 * u : (u < 12 * K ? p1 + 4 * (u - 8 * K) : (u < 16 * K ? p2 + 4 * (u - 12 * K) : p3 + 4 * (u - 16 * K)));
+    const float v = u < 8 * K ? mi : m1;   // two int64 -1 per 128 bits of pix_to_face
+#if HFR_FILL_PLAIN
+    *reinterpret_cast<float4*>(dst) = make_float4(v, v, v, v);
+#else
+    st_cs_f4(dst, v, v, v, v);
+#endif
+  }
+  return true;
 }
 
 // host helpers defined in raster.cu
