@@ -42,6 +42,7 @@ struct ManoSmem {
   float* G;      // NJ*12
   float* A;      // NJ*12
   float* misc;   // kMisc scratch
+  int* depth;    // NJ: depth of every joint in the kinematic tree (root = 0)
   float* vp;     // C3 (posed rest verts)
   float* gv;     // C3 (backward only)
 };
@@ -57,6 +58,7 @@ __device__ __forceinline__ ManoSmem carve(float* s, const HfrHandModel& m, bool 
   o.G = s; s += 12 * NJ;
   o.A = s; s += 12 * NJ;
   o.misc = s; s += kMisc;
+  o.depth = reinterpret_cast<int*>(s); s += up4(NJ);
   o.vp = s; s += m.C3;
   o.gv = bwd ? s : nullptr;
   return o;
@@ -64,7 +66,7 @@ __device__ __forceinline__ ManoSmem carve(float* s, const HfrHandModel& m, bool 
 
 static size_t mano_smem_bytes(const HfrHandModel& m, bool bwd) {
   auto up4 = [](int x) { return (x + 3) & ~3; };
-  size_t f = up4(3 * m.NJ) + up4(9 * m.NJ) + up4(m.NS + 9 * (m.NJ - 1)) + up4(3 * m.NJ) + 24 * m.NJ + kMisc;
+  size_t f = up4(3 * m.NJ) + up4(9 * m.NJ) + up4(m.NS + 9 * (m.NJ - 1)) + up4(3 * m.NJ) + 24 * m.NJ + kMisc + up4(m.NJ);
   f += (size_t)m.C3 * (bwd ? 2 : 1);
   return f * sizeof(float);
 }
@@ -95,6 +97,12 @@ __device__ void mano_setup(const HfrHandModel& m, const ManoSmem& s, const float
     }
   }
   for (int i = tid; i < m.NS; i += kThreads) s.coef[i] = betas ? betas[i] : 0.0f;
+  if (tid >= kThreads - NJ) {   // (the last warp is idle here) depth of each joint in the kinematic tree
+    const int j = tid - (kThreads - NJ);
+    int d = 0;
+    for (int p = m.parents[j]; p >= 0; p = m.parents[p]) ++d;
+    s.depth[j] = d;
+  }
   __syncthreads();
   if (tid < NJ) {
     if (tid < n_rot) {
@@ -113,11 +121,15 @@ __device__ void mano_setup(const HfrHandModel& m, const ManoSmem& s, const float
     const int e = i % 9;
     s.coef[m.NS + i] = s.R[9 + i] - ((e == 0 || e == 4 || e == 8) ? 1.0f : 0.0f);
   }
-  if (tid < 32) {  // kinematic chain: 12 lanes cooperate on one 3x4 product per joint
-    const int r = tid >> 2, c = tid & 3;
-    for (int j = 0; j < NJ; ++j) {
-      const int p = m.parents[j];
-      if (tid < 12) {
+  // kinematic chain, one tree level at a time: 12 threads per joint (one per entry of its 3x4 transform), every
+  // joint of a level in parallel - 4 steps for a hand (wrist, 3 phalanges) instead of NJ dependent ones
+  {
+    const int j = tid / 12, e = tid - 12 * j, r = e >> 2, c = e & 3;
+    const int dj = j < NJ ? s.depth[j] : -1;
+    for (int d = 0; d < NJ; ++d) {
+      const bool mine = dj == d;
+      if (mine) {
+        const int p = m.parents[j];
         float val;
         const float* Rj = s.R + 9 * j;
         if (p < 0) {
@@ -132,12 +144,11 @@ __device__ void mano_setup(const HfrHandModel& m, const ManoSmem& s, const float
             val = P[r * 4 + 0] * t0 + P[r * 4 + 1] * t1 + P[r * 4 + 2] * t2 + P[r * 4 + 3];
           }
         }
-        s.G[12 * j + tid] = val;
+        s.G[12 * j + e] = val;
       }
-      __syncwarp();
+      if (!__syncthreads_or(mine)) break;   // no joint at this depth: the tree is done
     }
   }
-  __syncthreads();
   for (int i = tid; i < 3 * NJ; i += kThreads) {  // A_j = G_j with the rest joint removed
     const int j = i / 3, r = i % 3;
     const float* G = s.G + 12 * j;
@@ -382,10 +393,14 @@ __global__ void __launch_bounds__(kThreads) mano_bwd_kernel(HfrHandModel m, HfrM
     }
   }
   __syncthreads();
-  // ---- chain backward (serial over joints, leaves to root)
-  if (tid == 0) {
+  // ---- chain backward, one tree level at a time from the leaves to the root (thread per joint).  A joint's
+  //      contribution to its parent goes through a private slot and the parent sums its children in index
+  //      order, so the result does not depend on thread timing.
+  {
     float* gG = gA;  // converted in place: gG.R = gA.R - gA.t (x) J ; gG.t = gA.t (+ direct joint grads)
-    for (int j = 0; j < NJ; ++j) {
+    float* contrib = gfull + 3 * NJ;   // NJ x 15: d(parent transform) 12, d(local translation) 3
+    const int j = tid, dj = tid < NJ ? s.depth[tid] : -1;
+    if (j < NJ) {
       const float* G = s.G + 12 * j;
       const float* Jj = s.J + 3 * j;
       for (int r = 0; r < 3; ++r) {
@@ -397,18 +412,36 @@ __global__ void __launch_bounds__(kThreads) mano_bwd_kernel(HfrHandModel m, HfrM
         gG[12 * j + r * 4 + 3] = gt + gGt[3 * j + r];
       }
     }
-    for (int j = NJ - 1; j >= 0; --j) {
-      const int p = m.parents[j];
-      if (p >= 0) {
-        float tl[3] = {s.J[3 * j] - s.J[3 * p], s.J[3 * j + 1] - s.J[3 * p + 1], s.J[3 * j + 2] - s.J[3 * p + 2]};
-        float gtl[3];
-        hfr_rigid_compose_bwd(s.G + 12 * p, s.R + 9 * j, tl, gG + 12 * j, gG + 12 * p, gR + 9 * j, gtl);
-        for (int k = 0; k < 3; ++k) { gJ[3 * j + k] += gtl[k]; gJ[3 * p + k] -= gtl[k]; }
-      } else {
-        for (int r = 0; r < 3; ++r) {
-          for (int c = 0; c < 3; ++c) gR[9 * j + r * 3 + c] = gG[12 * j + r * 4 + c];
-          gJ[3 * j + r] += gG[12 * j + r * 4 + 3];
+    int maxd = 0;
+    for (int i = 0; i < NJ; ++i) maxd = max(maxd, s.depth[i]);
+    __syncthreads();
+    for (int d = maxd; d >= 1; --d) {
+      if (dj == d) {          // children of this level: differentiate G_j = G_p o [R_j | J_j - J_p]
+        const int p = m.parents[j];
+        const float tl[3] = {s.J[3 * j] - s.J[3 * p], s.J[3 * j + 1] - s.J[3 * p + 1], s.J[3 * j + 2] - s.J[3 * p + 2]};
+        float gP[12], gtl[3];
+#pragma unroll
+        for (int e = 0; e < 12; ++e) gP[e] = 0.0f;
+        hfr_rigid_compose_bwd(s.G + 12 * p, s.R + 9 * j, tl, gG + 12 * j, gP, gR + 9 * j, gtl);
+#pragma unroll
+        for (int e = 0; e < 12; ++e) contrib[15 * j + e] = gP[e];
+        for (int k = 0; k < 3; ++k) { contrib[15 * j + 12 + k] = gtl[k]; gJ[3 * j + k] += gtl[k]; }
+      }
+      __syncthreads();
+      if (dj == d - 1) {      // their parents gather, children in index order
+        for (int ch = 0; ch < NJ; ++ch) {
+          if (m.parents[ch] != j) continue;
+#pragma unroll
+          for (int e = 0; e < 12; ++e) gG[12 * j + e] += contrib[15 * ch + e];
+          for (int k = 0; k < 3; ++k) gJ[3 * j + k] -= contrib[15 * ch + 12 + k];
         }
+      }
+      __syncthreads();
+    }
+    if (dj == 0) {
+      for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) gR[9 * j + r * 3 + c] = gG[12 * j + r * 4 + c];
+        gJ[3 * j + r] += gG[12 * j + r * 4 + 3];
       }
     }
   }
@@ -490,7 +523,7 @@ extern "C" int hfr_mano_backward(const HfrHandModel* m, const HfrManoBwdArgs* a,
                                   m->palm_verts[1] < m->V), "mano_backward: root_palm needs palm_verts");
   const int pose_dim = (a->pose_off > 0 ? a->pose_off : 3) + (m->NPC > 0 ? m->NPC : 3 * (m->NJ - 1));
   const int NK = m->NS + 9 * (m->NJ - 1);
-  const size_t extra = (size_t)(12 * m->NJ + 3 * m->NJ + 9 * m->NJ + ((NK + 3) & ~3) + 3 * m->NJ + 8) * sizeof(float);
+  const size_t extra = (size_t)(12 * m->NJ + 3 * m->NJ + 9 * m->NJ + ((NK + 3) & ~3) + 3 * m->NJ + 15 * m->NJ + 8) * sizeof(float);
   const size_t smem = mano_smem_bytes(*m, true) + extra;
   HFR_CHECK_ARG(smem <= 227 * 1024, "mano_backward: model too large for shared memory (%zu B)", smem);
   if (smem > 48 * 1024) cudaFuncSetAttribute(mano_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
