@@ -169,7 +169,8 @@ def run_ours(args, cfg):
     aa = cfg.get("aa", 1)
     step = hf.FusedHandStep(B, image_size=S, faces_per_pixel=K, soft=cfg["soft"], texture_size=cfg["T"],
                             lambdas=LAMBDAS, device=dev, n_global=B * world, sil_scale=cfg.get("sil_scale", 1.0),
-                            aa_factor=aa, binarize=cfg.get("binarize", False))
+                            aa_factor=aa, binarize=cfg.get("binarize", False),
+                            face_records=bool(os.environ.get("HFR_FACE_RECORDS")))   # env: A/B tuning only
     inp = synthetic_inputs(B, S=S, seed=1234 + rank)
     fcl, prp = hf.get_ndc_fx_fy_cx_cy(inp["Ks"])
     host = [inp["pose"], inp["betas"], -fcl, prp, inp["root_xyz"], inp["light_dir"], inp["light_color"], inp["imgs"],

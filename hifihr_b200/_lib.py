@@ -78,7 +78,12 @@ class HfrShadeParams(C.Structure):
 class HfrShadeFwdArgs(C.Structure):
     _fields_ = [("p", HfrShadeParams), ("pix_to_face", vp), ("zbuf", vp), ("bary", vp), ("dists", vp),
                 ("faces", vp), ("verts_view", vp), ("vnormals", vp), ("faces_uvs", vp), ("verts_uvs", vp),
-                ("texture", vp), ("light_dir", vp), ("light_color", vp), ("image", vp)]
+                ("texture", vp), ("light_dir", vp), ("light_color", vp), ("image", vp), ("face_attr", vp)]
+
+
+class HfrFaceAttrArgs(C.Structure):
+    _fields_ = [("N", i32), ("F", i32), ("V", i32), ("VT", i32), ("faces", vp), ("verts_view", vp), ("vnormals", vp),
+                ("faces_uvs", vp), ("verts_uvs", vp), ("face_attr", vp)]
 
 
 class HfrShadeBwdArgs(C.Structure):
@@ -129,6 +134,7 @@ class HfrKeypointBwdArgs(C.Structure):
 
 
 LOSS_NSUMS = 8
+FACE_ATTR_FLOATS = 28
 LOSS_L2 = 5
 KP_NSUMS = 8
 KP_TERMS = ("joint_2d", "joint_3d", "vert_3d", "bone_direc", "bone_direc_3d", "edge_length", "mscale")
@@ -136,7 +142,7 @@ ENTRY_POINTS = [
     "hfr_last_error", "hfr_abi_version", "hfr_device_ok", "hfr_mano_forward", "hfr_mano_backward",
     "hfr_geom_forward", "hfr_geom_backward", "hfr_raster_workspace_bytes", "hfr_raster_forward",
     "hfr_raster_backward", "hfr_raster_tile_box", "hfr_shade_forward", "hfr_shade_backward", "hfr_raster_shade_forward",
-    "hfr_raster_shade_pool_forward", "hfr_pool_forward", "hfr_pool_backward", "hfr_loss_forward", "hfr_loss_backward",
+    "hfr_raster_shade_pool_forward", "hfr_face_attr_forward", "hfr_pool_forward", "hfr_pool_backward", "hfr_loss_forward", "hfr_loss_backward",
     "hfr_keypoint_forward", "hfr_keypoint_backward",
 ]
 

@@ -280,6 +280,34 @@ __global__ void __launch_bounds__(kRasterThreads, (KMAX <= 4 ? HFR_RASTER_MINB :
   }
 }
 
+// One thread per (mesh, face, 128-bit unit of the record): 7 coalesced 16-byte stores per face.
+__global__ void __launch_bounds__(256) face_attr_kernel(HfrFaceAttrArgs a) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)a.N * a.F * 7;
+  if (i >= total) return;
+  const int u = (int)(i % 7);
+  const size_t nf = i / 7;
+  const int f = (int)(nf % a.F), n = (int)(nf / a.F);
+  float v[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int w = 4 * u + e;          // word of the record
+    float x = 0.0f;
+    if (w < 18) {                     // positions then normals, corner-major xyz
+      const int q = w < 9 ? w : w - 9, corner = q / 3, c = q - 3 * corner;
+      const int vid = __ldg(a.faces + 3 * f + corner);
+      x = __ldg((w < 9 ? a.verts_view : a.vnormals) + ((size_t)n * a.V + vid) * 3 + c);
+    } else if (w < 24) {
+      const int q = w - 18, corner = q >> 1;
+      x = __ldg(a.verts_uvs + 2 * __ldg(a.faces_uvs + 3 * f + corner) + (q & 1));
+    } else if (w < 27) {
+      x = __int_as_float(__ldg(a.faces + 3 * f + (w - 24)));
+    }
+    v[e] = x;
+  }
+  *reinterpret_cast<float4*>(a.face_attr + nf * HFR_FACE_ATTR_FLOATS + 4 * u) = make_float4(v[0], v[1], v[2], v[3]);
+}
+
 int check_shade(const HfrShadeFwdArgs* a, const char* who) {
   HFR_CHECK_ARG(a, "%s: null args", who);
   const HfrShadeParams& p = a->p;
@@ -366,5 +394,17 @@ extern "C" int hfr_raster_shade_pool_forward(const HfrRasterShadePoolArgs* a, vo
   HFR_DISPATCH_K(a->r.K, CALL);
 #undef CALL
   HFR_CHECK_LAUNCH("raster_shade_pool_forward");
+  return HFR_OK;
+}
+
+extern "C" int hfr_face_attr_forward(const HfrFaceAttrArgs* a, void* stream) {
+  using namespace hfr;
+  HFR_CHECK_ARG(a && a->N >= 0 && a->F > 0 && a->V > 0 && a->VT > 0, "face_attr_forward: bad dims");
+  if (a->N == 0) return HFR_OK;
+  HFR_CHECK_ARG(a->faces && a->verts_view && a->vnormals && a->faces_uvs && a->verts_uvs && a->face_attr,
+                "face_attr_forward: null pointer");
+  const size_t total = (size_t)a->N * a->F * 7;
+  face_attr_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*a);
+  HFR_CHECK_LAUNCH("face_attr_forward");
   return HFR_OK;
 }

@@ -43,11 +43,17 @@ __device__ __forceinline__ int selk_i(const int (&a)[KMAX], int k) {
 #ifndef HFR_BWD_WARP_LIGHT
 #define HFR_BWD_WARP_LIGHT 0
 #endif
+// Resident CTAs per SM (register cap = 65536 / (threads x CTAs)).  Measured on B200 (C2, K=4): 8 CTAs x 64 registers
+// 377 us, 4 x 128 registers 368 us, 3 x 168 411 us - the per-slot loop is latency-bound and wants both warps and
+// registers.  K=1 at 672^2 (Fragments streaming dominates) prefers the 8-CTA setting: 406 vs 459 us.
 #ifndef HFR_BWD_MINB
-#define HFR_BWD_MINB (1024 / HFR_BWD_THREADS)
+#define HFR_BWD_MINB 4
+#endif
+#ifndef HFR_BWD_MINB_K1
+#define HFR_BWD_MINB_K1 8
 #endif
 template <int KMAX>
-__global__ void __launch_bounds__(kBwdThreads, (KMAX <= 4 ? HFR_BWD_MINB : 1)) shade_bwd_kernel(HfrShadeBwdArgs a) {
+__global__ void __launch_bounds__(kBwdThreads, (KMAX == 1 ? HFR_BWD_MINB_K1 : (KMAX <= 4 ? HFR_BWD_MINB : 1))) shade_bwd_kernel(HfrShadeBwdArgs a) {
   __shared__ float s_light[kBwdThreads / 32][6];
   // per-warp staging of the 27 per-fragment components, pitch 33: lane L writes column L (bank j+L),
   // lane j later sums row j over the lanes of one face group (bank j+m) - both conflict-free

@@ -14,6 +14,24 @@ struct FragGeom {        // per-fragment gathered attributes
 
 HFR_HD void gather_frag(const HfrShadeFwdArgs& a, int n, int fl, FragGeom& g) {
   const int V = a.p.V;
+#if defined(__CUDA_ARCH__)
+  if (a.face_attr) {   // one contiguous 112-byte record per (mesh, face): 7 independent 128-bit loads
+    const float4* __restrict__ r4 = reinterpret_cast<const float4*>(a.face_attr + ((size_t)n * a.p.F + fl) * HFR_FACE_ATTR_FLOATS);
+    float w[28];
+#pragma unroll
+    for (int u = 0; u < 7; ++u) {
+      const float4 q = __ldg(r4 + u);
+      w[4 * u] = q.x; w[4 * u + 1] = q.y; w[4 * u + 2] = q.z; w[4 * u + 3] = q.w;
+    }
+#pragma unroll
+    for (int e = 0; e < 9; ++e) { g.X[e] = w[e]; g.Nv[e] = w[9 + e]; }
+#pragma unroll
+    for (int e = 0; e < 6; ++e) g.uv[e] = w[18 + e];
+#pragma unroll
+    for (int e = 0; e < 3; ++e) g.vid[e] = __float_as_int(w[24 + e]);
+    return;
+  }
+#endif
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     const int vid = HFR_LDG(a.faces + 3 * fl + i);

@@ -113,12 +113,14 @@ class FusedHandStep:
 
     def __init__(self, B, image_size=224, faces_per_pixel=4, blur_radius=None, sigma=1e-4, gamma=1e-4, soft=True,
                  texture_size=512, lambdas=None, device="cuda", mano_root=None, n_global=None, sil_scale=1.0,
-                 aa_factor=1, binarize=False, want_nchw=False):
+                 aa_factor=1, binarize=False, want_nchw=False, face_records=False):
         """aa_factor > 1 selects the SSAA-fused render (the reference's own setting is image_size=224,
         aa_factor=3, faces_per_pixel=1, soft=False, binarize=True, sil_scale=255; models_res_nimble.py:74-96,
         208-220): Fragments are rasterised at image_size*aa_factor, the pooled RGBA (B,S,S,4) is the only image
         that exists, and the backward folds avg_pool2d' into the shading backward.  want_nchw also writes
-        re_img / re_sil / maskRGBs in the reference's NCHW layout."""
+        re_img / re_sil / maskRGBs in the reference's NCHW layout.  face_records packs one contiguous attribute
+        record per (sample, face) each step (one more launch) so the shaders skip two dependent gathers; measured
+        neutral on B200 at C2 (backward 370 -> 363 us, forward + 9 us for the packing launch), hence off by default."""
         dev = torch.device(device)
         self.B, self.S, self.K, self.dev = B, image_size, faces_per_pixel, dev
         self.aa, self.binarize = int(aa_factor), bool(binarize)
@@ -145,6 +147,7 @@ class FusedHandStep:
         self.verts, self.joints = e(B, V, 3), e(B, 21, 3)
         self.verts_rel, self.verts_view, self.verts_ndc, self.vnormals = e(B, V, 3), e(B, V, 3), e(B, V, 3), e(B, V, 3)
         self.face_verts = e(B * Fm, 3, 3)
+        self.face_attr = e(B, Fm, L.FACE_ATTR_FLOATS) if face_records else None
         self.p2f = e(B, Sr, Sr, K, dt=I64)
         self.zbuf, self.bary, self.dists = e(B, Sr, Sr, K), e(B, Sr, Sr, K, 3), e(B, Sr, Sr, K)
         self.image, self.g_image = e(B, S, S, 4), e(B, S, S, 4)      # pooled RGBA when aa > 1
@@ -174,7 +177,9 @@ class FusedHandStep:
         self.params = ops.shade_params(B, Sr, Sr, K, Fm, V, 2 if soft else 0, 1, sigma, gamma, (1.0, 1.0, 1.0),
                                        (0.5, 0.5, 0.5), (0.2, 0.2, 0.2), (1.0, 1.0, 1.0), (0.8, 0.8, 0.8),
                                        (0.2, 0.2, 0.2), 30.0, tex_shape=self.texture.shape[:3], VT=self.verts_uvs.shape[0])
-        self.launches_per_step = 11   # kernels of ours per step() (setup, mano, geom, raster+shade, loss | 5 bwd) + 1 memset
+        # kernels of OURS per step(): mano, geom, [face records], raster setup, raster+shade(+pool), loss | loss', shade'+raster',
+        # geom', mano'  (the two torch memsets of the accumulators are not counted)
+        self.launches_per_step = 9 + (1 if face_records else 0)
 
     # ---------------------------------------------------------------------------------------
     def forward(self, pose, betas, focal, prp, root_xyz, light_dir, light_color, imgs, seg):
@@ -192,11 +197,14 @@ class FusedHandStep:
     def launch_raster_shade(self, light_dir, light_color, imgs=None):
         """setup + rasterize + shade (+ SSAA pool and output split when aa_factor > 1) - two launches."""
         K, Sr = self.K, self.Sr
+        if self.face_attr is not None:
+            ops.face_attr_forward(self.topo.faces, self.verts_view, self.vnormals, self.faces_uvs, self.verts_uvs,
+                                  self.face_attr)
         r = ops.raster_args(self.face_verts, self.mesh_first, self.mesh_nf, Sr, Sr, K, self.blur, True, self.blur > 0,
                             False, self.p2f, self.zbuf, self.bary, self.dists, self.ws)
         s = ops.shade_fwd_args(self.params, (self.p2f, self.zbuf, self.bary, self.dists), self.topo.faces,
                                self.verts_view, self.vnormals, self.faces_uvs, self.verts_uvs, self.texture,
-                               light_dir, light_color, self.image if self.aa == 1 else None)
+                               light_dir, light_color, self.image if self.aa == 1 else None, self.face_attr)
         if self.aa == 1:
             L.call("hfr_raster_shade_forward", L.HfrRasterShadeArgs(r, s))
         else:

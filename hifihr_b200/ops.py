@@ -201,12 +201,21 @@ def shade_params(N, H, W, K, F, V, blend, shade, sigma, gamma, background, light
     return p
 
 
-def shade_fwd_args(p, frags, faces, verts_view, vnormals, faces_uvs, verts_uvs, texture, light_dir, light_color, image):
+def shade_fwd_args(p, frags, faces, verts_view, vnormals, faces_uvs, verts_uvs, texture, light_dir, light_color, image,
+                   face_attr=None):
     p2f, zbuf, bary, dists = frags
     return L.HfrShadeFwdArgs(p, L.ptr(p2f, I64), L.ptr(zbuf, F32), L.ptr(bary, F32), L.ptr(dists, F32),
                              L.ptr(faces, I32), L.ptr(verts_view, F32), L.ptr(vnormals, F32), L.ptr(faces_uvs, I32),
                              L.ptr(verts_uvs, F32), L.ptr(texture, F32), L.ptr(light_dir, F32), L.ptr(light_color, F32),
-                             L.ptr(image, F32))
+                             L.ptr(image, F32), L.ptr(face_attr, F32))
+
+
+def face_attr_forward(faces, verts_view, vnormals, faces_uvs, verts_uvs, out):
+    """Pack the per-(mesh, face) attribute records the shaders read (hfr_face_attr_forward)."""
+    N, V = verts_view.shape[0], verts_view.shape[1]
+    a = L.HfrFaceAttrArgs(N, faces.shape[0], V, verts_uvs.shape[0], L.ptr(faces, I32), L.ptr(verts_view, F32),
+                          L.ptr(vnormals, F32), L.ptr(faces_uvs, I32), L.ptr(verts_uvs, F32), L.ptr(out, F32))
+    L.call("hfr_face_attr_forward", a)
 
 
 _GAUSS = {}

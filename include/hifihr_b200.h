@@ -225,8 +225,27 @@ typedef struct HfrShadeFwdArgs {
   const float* light_dir;           /* (N,3)                                               */
   const float* light_color;         /* (N,3) diffuse colour                                */
   float* image;                     /* (N,H,W,4)                                           */
+  /* optional: per-(mesh, face) attribute records written by hfr_face_attr_forward, (N,F,HFR_FACE_ATTR_FLOATS).
+   * When set, the shaders read one contiguous record per fragment instead of chasing
+   * faces -> verts_view / vnormals and faces_uvs -> verts_uvs (two dependent gathers).  NULL = gather path. */
+  const float* face_attr;
 } HfrShadeFwdArgs;
 int hfr_shade_forward(const HfrShadeFwdArgs* a, void* stream);
+
+/* Per-face attribute records for the shaders (what interpolate_face_attributes / TexturesUV.sample_textures
+ * gather per fragment upstream): for every mesh n and face f, 28 floats =
+ *   view-space corner positions (9), corner vertex normals (9), corner uvs (6), corner vertex ids (3, int bits), pad. */
+#define HFR_FACE_ATTR_FLOATS 28
+typedef struct HfrFaceAttrArgs {
+  int32_t N, F, V, VT;
+  const int32_t* faces;             /* (F,3)                                               */
+  const float* verts_view;          /* (N,V,3)                                             */
+  const float* vnormals;            /* (N,V,3)                                             */
+  const int32_t* faces_uvs;         /* (F,3)                                               */
+  const float* verts_uvs;           /* (VT,2)                                              */
+  float* face_attr;                 /* (N,F,28)                                            */
+} HfrFaceAttrArgs;
+int hfr_face_attr_forward(const HfrFaceAttrArgs* a, void* stream);
 
 typedef struct HfrShadeBwdArgs {
   HfrShadeFwdArgs f;                /* forward inputs; f.image = the forward OUTPUT (read by the softmax blend) */

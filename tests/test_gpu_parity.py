@@ -548,6 +548,32 @@ def test_fused_ssaa_rejects_bad_sizes(hf):
         L.call("hfr_raster_shade_pool_forward", a)
 
 
+def test_face_records_match_gather_path(hf):
+    """The per-(sample, face) attribute records (hfr_face_attr_forward) are a pure re-layout: the fused step with
+    and without them renders the same image bit for bit and produces the same gradients up to atomic order."""
+    B, S, K = 2, 64, 4
+    inp = P.synthetic_inputs(B, S=S, seed=21)
+    fcl, prp = p3d.ndc_intrinsics(inp["Ks"])
+    d = lambda t: t.to(DEV).contiguous()  # noqa: E731
+    args = (d(inp["pose"]), d(inp["betas"]), d(-fcl), d(prp), d(inp["root_xyz"]), d(inp["light_dir"]),
+            d(inp["light_color"]), d(inp["imgs"]), d(inp["segms_gt"].float()))
+    steps = [hf.FusedHandStep(B, image_size=S, faces_per_pixel=K, soft=True, texture_size=64, device=DEV, face_records=fr)
+             for fr in (True, False)]
+    for st in steps:
+        st.step(*args)
+    torch.cuda.synchronize()
+    a, b = steps
+    rec = a.face_attr.cpu()
+    faces = a.topo.faces.cpu().long()
+    assert torch.equal(rec[..., 0:9].reshape(B, -1, 3, 3), a.verts_view.cpu()[:, faces])
+    assert torch.equal(rec[..., 9:18].reshape(B, -1, 3, 3), a.vnormals.cpu()[:, faces])
+    assert torch.equal(rec[..., 18:24].reshape(B, -1, 3, 2), a.verts_uvs.cpu()[a.faces_uvs.cpu().long()][None].expand(B, -1, -1, -1))
+    assert torch.equal(rec[..., 24:27].contiguous().view(torch.int32).long(), faces[None].expand(B, -1, -1))
+    assert torch.equal(a.image, b.image) and torch.equal(a.p2f, b.p2f)
+    for k in ("g_pose", "g_betas", "g_texture", "g_light_dir", "g_light_color"):
+        assert rel_err(getattr(a, k), getattr(b, k)) < 1e-4, k
+
+
 def test_full_size_properties_c2(hf, mano):
     """BASELINE config 2 sizes (B=64, 224^2, K=4, soft): size-independent properties + a sampled bit-exact check."""
     B, S, K = 64, 224, 4

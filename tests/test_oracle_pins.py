@@ -232,7 +232,7 @@ def test_ctypes_struct_sizes_match_header():
     from hifihr_b200 import _lib
     names = ["HfrHandModel", "HfrManoFwdArgs", "HfrManoBwdArgs", "HfrTopology", "HfrGeomFwdArgs", "HfrGeomBwdArgs",
              "HfrRasterArgs", "HfrRasterBwdArgs", "HfrShadeParams", "HfrShadeFwdArgs", "HfrShadeBwdArgs",
-             "HfrRasterShadeArgs", "HfrRasterShadePoolArgs", "HfrPoolArgs", "HfrPoolBwdArgs", "HfrLossArgs", "HfrLossBwdArgs", "HfrKeypointArgs",
+             "HfrRasterShadeArgs", "HfrRasterShadePoolArgs", "HfrFaceAttrArgs", "HfrPoolArgs", "HfrPoolBwdArgs", "HfrLossArgs", "HfrLossBwdArgs", "HfrKeypointArgs",
              "HfrKeypointBwdArgs"]
     src = '#include <stdio.h>\n#include "hifihr_b200.h"\nint main(){' + "".join(
         f'printf("%zu\\n", sizeof({n}));' for n in names) + "return 0;}"
