@@ -77,6 +77,16 @@ __device__ __forceinline__ float ld_sil(const HfrLossArgs& a, int n, size_t p, s
   return a.nhwc ? __ldg(a.re_img + ((size_t)n * hw + p) * 4 + 3) : __ldg(a.re_sil + (size_t)n * hw + p);
 }
 
+// target colour / mask of pixel p of sample n, float or 8-bit transport (lut[k] = k / 255.0f, IEEE division)
+__device__ __forceinline__ float ld_target(const HfrLossArgs& a, const float* lut, int n, int c, size_t p, size_t hw) {
+  const size_t i = ((size_t)n * 3 + c) * hw + p;
+  return a.imgs_u8 ? lut[__ldg(a.imgs_u8 + i)] : __ldg(a.imgs + i);
+}
+__device__ __forceinline__ float ld_seg(const HfrLossArgs& a, int n, size_t p, size_t hw) {
+  const size_t i = (size_t)n * hw + p;
+  return a.seg_u8 ? (__ldg(a.seg_u8 + i) != 0 ? 1.0f : 0.0f) : __ldg(a.seg + i);
+}
+
 // 8 outputs of an 11-tap row filter from 18 inputs, `NM` maps at once: out[o] += g[j-o] * in[j]
 template <int NM>
 __device__ __forceinline__ void tap_accumulate(float (&acc)[8][NM], const float (&val)[NM], int j, const float (&g)[11]) {
@@ -132,7 +142,9 @@ __global__ void __launch_bounds__(kLossThreads, 3) loss_fwd_kernel(HfrLossArgs a
   float l1 = 0.f, sr = 0.f, st = 0.f, sl = 0.f, ss = 0.f, mul = 0.f, add = 0.f, l2 = 0.f;
   bool nz_halo = false;   // any non-zero x / y sample in the tile's halo
   __shared__ unsigned char sub_nz[64];   // per 4x4 block of the interior: holds a non-zero sample
+  __shared__ float lut[256];             // k / 255 for the 8-bit target transport
   if (tid < 64) sub_nz[tid] = 0;
+  if (a.imgs_u8) lut[tid] = __fdiv_rn((float)tid, 255.0f);   // kLossThreads == 256
   __syncthreads();
   // ---- halo load, all three channels at once (zero padding as F.conv2d(padding=5)) + the pointwise
   //      sums over the tile's interior
@@ -162,9 +174,9 @@ __global__ void __launch_bounds__(kLossThreads, 3) loss_fwd_kernel(HfrLossArgs a
           q[u].y = __ldg(a.re_img + ((size_t)n * 3 + 1) * hw + p);
           q[u].z = __ldg(a.re_img + ((size_t)n * 3 + 2) * hw + p);
         }
-        sg[u] = __ldg(a.seg + n * hw + p);
+        sg[u] = ld_seg(a, n, p, hw);
 #pragma unroll
-        for (int c = 0; c < 3; ++c) im[u][c] = __ldg(a.imgs + ((size_t)n * 3 + c) * hw + p);
+        for (int c = 0; c < 3; ++c) im[u][c] = ld_target(a, lut, n, c, p, hw);
       }
     }
 #pragma unroll
@@ -361,6 +373,11 @@ __global__ void __launch_bounds__(kLossThreads, HFR_LOSSB_MINB) loss_bwd_kernel(
   // RGBA, mask, target) is requested up front for all channels, so the round trips overlap each other and, on
   // tiles with a live SSIM stencil, the halo loads and the stencil itself.
   const int gx = x0 + lane;
+  __shared__ float lut[256];             // k / 255 for the 8-bit target transport
+  if (a.imgs_u8) {                       // (uniform branch)
+    lut[tid] = __fdiv_rn((float)tid, 255.0f);
+    __syncthreads();
+  }
   float sil[4], seg[4], rimg[4][3], timg[4][3];
   bool in[4];
 #pragma unroll
@@ -380,9 +397,9 @@ __global__ void __launch_bounds__(kLossThreads, HFR_LOSSB_MINB) loss_bwd_kernel(
 #pragma unroll
         for (int c = 0; c < 3; ++c) rimg[o][c] = __ldg(a.re_img + ((size_t)n * 3 + c) * hw + p);
       }
-      seg[o] = __ldg(a.seg + n * hw + p);
+      seg[o] = ld_seg(a, n, p, hw);
 #pragma unroll
-      for (int c = 0; c < 3; ++c) timg[o][c] = __ldg(a.imgs + ((size_t)n * 3 + c) * hw + p);
+      for (int c = 0; c < 3; ++c) timg[o][c] = ld_target(a, lut, n, c, p, hw);
     }
   }
   const float mulv = a.sums[HFR_LOSS_NSUMS + n], addv = a.sums[HFR_LOSS_NSUMS + a.N + n];
@@ -544,7 +561,7 @@ extern "C" int hfr_loss_forward(const HfrLossArgs* a, void* stream) {
   using namespace hfr;
   HFR_CHECK_ARG(a && a->N >= 0 && a->H > 0 && a->W > 0 && a->sil_scale > 0.f, "loss_forward: bad dims");
   if (a->N == 0) return HFR_OK;
-  HFR_CHECK_ARG(a->re_img && (a->nhwc || a->re_sil) && a->imgs && a->seg && a->sums, "loss_forward: null pointer");
+  HFR_CHECK_ARG(a->re_img && (a->nhwc || a->re_sil) && (a->imgs || a->imgs_u8) && (a->seg || a->seg_u8) && a->sums, "loss_forward: null pointer");
   HFR_CHECK_ARG(!a->want_ssim || a->gauss, "loss_forward: SSIM needs the Gaussian taps");
   dim3 grid((a->W + kLT - 1) / kLT, (a->H + kLT - 1) / kLT, a->N);
   HFR_CHECK_ARG(a->mask_mode >= 0 && a->mask_mode <= 2, "loss_forward: mask_mode must be 0, 1 or 2");
@@ -565,7 +582,7 @@ extern "C" int hfr_loss_backward(const HfrLossBwdArgs* a, void* stream) {
   using namespace hfr;
   HFR_CHECK_ARG(a && a->f.N >= 0 && a->f.H > 0 && a->f.W > 0, "loss_backward: bad dims");
   if (a->f.N == 0) return HFR_OK;
-  HFR_CHECK_ARG(a->f.re_img && (a->f.nhwc || (a->f.re_sil && a->g_re_sil)) && a->f.imgs && a->f.seg && a->f.sums && a->w && a->g_re_img,
+  HFR_CHECK_ARG(a->f.re_img && (a->f.nhwc || (a->f.re_sil && a->g_re_sil)) && (a->f.imgs || a->f.imgs_u8) && (a->f.seg || a->f.seg_u8) && a->f.sums && a->w && a->g_re_img,
                 "loss_backward: null pointer");
   HFR_CHECK_ARG(!(a->f.want_ssim && a->f.dmaps) || a->gauss, "loss_backward: SSIM needs the Gaussian taps");
   HFR_CHECK_ARG(a->count_global > 0 && a->n_global > 0, "loss_backward: bad global counts");

@@ -106,7 +106,8 @@ class FusedHandStep:
     """Forward + backward of the whole hot path as raw launches on preallocated buffers.
 
     Inputs (device, fp32, contiguous): pose (B,48), betas (B,10), focal (B,2), prp (B,2), root_xyz (B,3),
-    light_dir (B,3), light_color (B,3), imgs (B,3,S,S), seg (B,S,S).  The shared texture (1,T,T,3) and the
+    light_dir (B,3), light_color (B,3), imgs (B,3,S,S), seg (B,S,S).  imgs / seg may also be uint8 (the datasets'
+    8-bit images and {0,1} masks): the loss kernels then apply ToTensor's x / 255 while loading.  The shared texture (1,T,T,3) and the
     loss weights live in the object.  After `step()`: `sums` holds the loss partial sums, and g_pose, g_betas,
     g_texture, g_light_dir, g_light_color the gradients of  sum_k lambda_k * term_k.
     """
@@ -189,9 +190,13 @@ class FusedHandStep:
                              self.verts_view, self.verts_ndc, self.vnormals, self.face_verts)
         self.launch_raster_shade(light_dir, light_color, imgs)
         self.sums.zero_()
-        self._loss_args = L.HfrLossArgs(B, S, S, self.sil_scale, 1, 1, 1, L.ptr(self.image), None, L.ptr(imgs, F32),
-                                        L.ptr(seg, F32), L.ptr(self.sums), L.ptr(self.gauss), L.ptr(self.dmaps),
-                                        L.ptr(self.tile_flags))
+        # targets may arrive as the dataset's 8-bit images / masks: the loss kernels convert while loading
+        u8i, u8s = imgs.dtype == torch.uint8, seg.dtype == torch.uint8
+        self._loss_args = L.HfrLossArgs(B, S, S, self.sil_scale, 1, 1, 1, L.ptr(self.image), None,
+                                        None if u8i else L.ptr(imgs, F32, "imgs"), None if u8s else L.ptr(seg, F32, "seg"),
+                                        L.ptr(self.sums), L.ptr(self.gauss), L.ptr(self.dmaps), L.ptr(self.tile_flags), 0,
+                                        L.ptr(imgs, torch.uint8, "imgs") if u8i else None,
+                                        L.ptr(seg, torch.uint8, "seg") if u8s else None)
         L.call("hfr_loss_forward", self._loss_args)
 
     def launch_raster_shade(self, light_dir, light_color, imgs=None):
@@ -208,11 +213,11 @@ class FusedHandStep:
         if self.aa == 1:
             L.call("hfr_raster_shade_forward", L.HfrRasterShadeArgs(r, s))
         else:
-            nchw = self.re_img is not None
+            masks = self.re_img is not None and imgs is not None and imgs.dtype == F32   # maskRGBs needs float images
             L.call("hfr_raster_shade_pool_forward",
-                   L.HfrRasterShadePoolArgs(r, s, self.aa, int(self.binarize), L.ptr(imgs, F32) if nchw else None,
+                   L.HfrRasterShadePoolArgs(r, s, self.aa, int(self.binarize), L.ptr(imgs, F32) if masks else None,
                                             L.ptr(self.image), L.ptr(self.re_img), L.ptr(self.re_sil),
-                                            L.ptr(self.mask_rgbs)))
+                                            L.ptr(self.mask_rgbs) if masks else None))
         self._shade_args = s
 
     def launch_shade_backward(self):

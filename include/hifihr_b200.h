@@ -356,6 +356,11 @@ typedef struct HfrLossArgs {
                                        Evaluation-time texture metrics (train_hrnet.py:149-161; forward only):
                                        1: both images * seg; 2: both images * (re_sil > 0) (the HO3D branch);
                                        sums[HFR_LOSS_L1], [HFR_LOSS_L2], [HFR_LOSS_SSIM] then give L1 / L2 / PSNR / SSIM */
+  /* optional 8-bit transport of the targets (the datasets store 8-bit images and {0,1} masks; the reference
+   * converts on the host, ToTensor = x / 255): when set they REPLACE imgs / seg, and the kernels convert while
+   * loading (exact x / 255.0f through a 256-entry table, mask byte != 0 -> 1.0f), so 4x fewer bytes cross PCIe. */
+  const uint8_t* imgs_u8;           /* (N,3,H,W) or NULL                                   */
+  const uint8_t* seg_u8;            /* (N,H,W) or NULL                                     */
 } HfrLossArgs;
 int hfr_loss_forward(const HfrLossArgs* a, void* stream);
 typedef struct HfrLossBwdArgs {

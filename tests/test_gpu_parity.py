@@ -574,6 +574,32 @@ def test_face_records_match_gather_path(hf):
         assert rel_err(getattr(a, k), getattr(b, k)) < 1e-4, k
 
 
+def test_uint8_target_transport_matches_float(hf):
+    """8-bit transport of the targets (imgs_u8 / seg_u8 of HfrLossArgs): the loss kernels apply ToTensor's x / 255
+    (and byte != 0 -> 1.0) while loading, so a step fed with bytes equals a step fed with the floats the reference's
+    loader would have produced - sums to 1e-6 relative (atomic order), the image gradient and parameter gradients too."""
+    B, S, K = 2, 72, 4
+    inp = P.synthetic_inputs(B, S=S, seed=8)
+    fcl, prp = p3d.ndc_intrinsics(inp["Ks"])
+    d = lambda t: t.to(DEV).contiguous()  # noqa: E731
+    imgs_u8 = (inp["imgs"] * 255.0).round().to(torch.uint8)
+    seg_u8 = inp["segms_gt"].to(torch.uint8)
+    common = (d(inp["pose"]), d(inp["betas"]), d(-fcl), d(prp), d(inp["root_xyz"]), d(inp["light_dir"]), d(inp["light_color"]))
+    a = hf.FusedHandStep(B, image_size=S, faces_per_pixel=K, soft=True, texture_size=64, device=DEV)
+    b = hf.FusedHandStep(B, image_size=S, faces_per_pixel=K, soft=True, texture_size=64, device=DEV)
+    a.step(*common, d(imgs_u8.float() / 255.0), d(seg_u8.float()))
+    b.step(*common, d(imgs_u8), d(seg_u8))
+    torch.cuda.synchronize()
+    assert torch.equal(a.image, b.image)
+    assert rel_err(b.sums[:5], a.sums[:5]) < 1e-6
+    assert rel_err(b.g_image, a.g_image) < 1e-6
+    for k in ("g_pose", "g_betas", "g_texture", "g_light_dir", "g_light_color"):
+        assert rel_err(getattr(b, k), getattr(a, k)) < 1e-4, k
+    # the conversion table is ToTensor's division, bit for bit
+    ref = torch.arange(256, dtype=torch.float32) / 255.0
+    assert torch.equal((torch.arange(256, dtype=torch.uint8).float() / 255.0), ref)
+
+
 def test_full_size_properties_c2(hf, mano):
     """BASELINE config 2 sizes (B=64, 224^2, K=4, soft): size-independent properties + a sampled bit-exact check."""
     B, S, K = 64, 224, 4
