@@ -159,8 +159,11 @@ def run_ours(args, cfg):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # rank 0 prints ONE JSON line on stdout: NCCL's own output (the version banner it prints at VERSION / WARN /
+        # INFO) goes to a per-process file instead
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+            os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/hifihr_b200_nccl.%h.%p.log")
         dist.init_process_group("nccl", device_id=dev)
     B = cfg["B"] if cfg["B"] is not None else 4096 // world
     if args.batch:

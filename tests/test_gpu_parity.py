@@ -600,6 +600,27 @@ def test_uint8_target_transport_matches_float(hf):
     assert torch.equal((torch.arange(256, dtype=torch.uint8).float() / 255.0), ref)
 
 
+@pytest.mark.parametrize("K,soft", [(2, True), (3, True), (8, True), (3, False)])
+def test_fused_fragments_bit_exact_other_k(hf, K, soft):
+    """The fused rasterize+shade kernel at the K values the dispatch maps to other template sizes (K=2 -> 2, K=3 -> 4
+    with a spare slot, K=8 -> 8 without the payload cache): all four Fragments tensors bit-exact vs the C oracle."""
+    B, S = 2, 56
+    inp = P.synthetic_inputs(B, S=S, seed=40 + K)
+    fcl, prp = p3d.ndc_intrinsics(inp["Ks"])
+    d = lambda t: t.to(DEV).contiguous()  # noqa: E731
+    step = hf.FusedHandStep(B, image_size=S, faces_per_pixel=K, soft=soft, texture_size=32, device=DEV)
+    step.step(d(inp["pose"]), d(inp["betas"]), d(-fcl), d(prp), d(inp["root_xyz"]), d(inp["light_dir"]),
+              d(inp["light_color"]), d(inp["imgs"]), d(inp["segms_gt"].float()))
+    torch.cuda.synchronize()
+    Fm = 1538
+    ref = raster_c.rasterize_naive(step.face_verts.cpu(), [i * Fm for i in range(B)], [Fm] * B, S, step.blur, K, threads=8)
+    assert (step.p2f.cpu() == ref[0]).all() and (step.zbuf.cpu() == ref[1]).all()
+    assert (step.bary.cpu() == ref[2]).all() and (step.dists.cpu() == ref[3]).all()
+    assert (step.p2f >= 0).any() and torch.isfinite(step.image).all()
+    for t in (step.g_pose, step.g_betas, step.g_texture):
+        assert torch.isfinite(t).all() and t.abs().sum() > 0
+
+
 def test_full_size_properties_c2(hf, mano):
     """BASELINE config 2 sizes (B=64, 224^2, K=4, soft): size-independent properties + a sampled bit-exact check."""
     B, S, K = 64, 224, 4
