@@ -5,7 +5,7 @@ Public surface mirrors the reference's names for this path:
   Meshes                                      (pytorch3d.structures, the subset used)
   RasterizationSettings, MeshRasterizer, Fragments, MeshRenderer, HardPhongShader,
   SoftPhongShader, SoftSilhouetteShader, Materials, DirectionalLights, PerspectiveCameras,
-  BlendParams, TexturesUV                     (pytorch3d.renderer, the subset used)
+  BlendParams, TexturesUV, TexturesUVPCA      (pytorch3d.renderer, the subset used; PCA = NIMBLE texture model)
   LossFunction                                (losses.py, render-dependent terms)
   texture_metrics                             (train_hrnet.py:149-161 PSNR / SSIM / L1 / L2)
   HandRenderModel, FusedHandStep              (models_res_nimble.py:133-223 without the CNNs)
@@ -19,7 +19,7 @@ from .mano import ManoLayer, MyMANOLayer, xyz_from_vertice  # noqa: F401
 from .model import FusedHandStep, HandRenderModel, get_ndc_fx_fy_cx_cy  # noqa: F401
 from .renderer import (BlendParams, DirectionalLights, Fragments, HardPhongShader, Materials,  # noqa: F401
                        MeshRasterizer, MeshRenderer, PerspectiveCameras, PointLights, RasterizationSettings,
-                       SoftPhongShader, SoftSilhouetteShader, TexturesUV, rasterize_meshes)
+                       SoftPhongShader, SoftSilhouetteShader, TexturesUV, TexturesUVPCA, rasterize_meshes)
 from .structures import Meshes  # noqa: F401
 
 __version__ = "0.1.0"

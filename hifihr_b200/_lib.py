@@ -72,13 +72,13 @@ class HfrShadeParams(C.Structure):
                 ("shade", i32), ("sigma", f32), ("gamma", f32), ("znear", f32), ("zfar", f32),
                 ("background", f32 * 3), ("light_ambient", f32 * 3), ("light_specular", f32 * 3),
                 ("mat_ambient", f32 * 3), ("mat_diffuse", f32 * 3), ("mat_specular", f32 * 3),
-                ("shininess", f32), ("tex_n", i32), ("tex_h", i32), ("tex_w", i32), ("VT", i32)]
+                ("shininess", f32), ("tex_n", i32), ("tex_h", i32), ("tex_w", i32), ("VT", i32), ("tex_pca", i32)]
 
 
 class HfrShadeFwdArgs(C.Structure):
     _fields_ = [("p", HfrShadeParams), ("pix_to_face", vp), ("zbuf", vp), ("bary", vp), ("dists", vp),
                 ("faces", vp), ("verts_view", vp), ("vnormals", vp), ("faces_uvs", vp), ("verts_uvs", vp),
-                ("texture", vp), ("light_dir", vp), ("light_color", vp), ("image", vp), ("face_attr", vp)]
+                ("texture", vp), ("light_dir", vp), ("light_color", vp), ("image", vp), ("face_attr", vp), ("tex_basis", vp), ("tex_params", vp)]
 
 
 class HfrFaceAttrArgs(C.Structure):
@@ -90,7 +90,7 @@ class HfrShadeBwdArgs(C.Structure):
     _fields_ = [("f", HfrShadeFwdArgs), ("g_image", vp), ("g_zbuf", vp), ("g_bary", vp), ("g_dists", vp),
                 ("verts_ndc", vp), ("g_verts_ndc", vp), ("blur_radius", f32), ("perspective_correct", i32),
                 ("clip_barycentric", i32), ("g_verts_view", vp), ("g_vnormals", vp), ("g_texture", vp),
-                ("g_light_dir", vp), ("g_light_color", vp), ("tile_box", vp), ("pool_aa", i32), ("pool_binarize", i32)]
+                ("g_light_dir", vp), ("g_light_color", vp), ("tile_box", vp), ("pool_aa", i32), ("pool_binarize", i32), ("g_tex_params", vp)]
 
 
 class HfrRasterShadeArgs(C.Structure):

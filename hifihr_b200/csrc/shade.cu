@@ -11,7 +11,7 @@
 
 namespace hfr {
 
-template <int KMAX>
+template <int KMAX, bool PCA>
 __global__ void __launch_bounds__(256) shade_fwd_kernel(HfrShadeFwdArgs a) {
   const int n = blockIdx.y, K = a.p.K;
   const int HW = a.p.H * a.p.W;
@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(256) shade_fwd_kernel(HfrShadeFwdArgs a) {
     }
   }
   float rgba[4];
-  shade_pixel<KMAX>(a, n, id, z, d, b, rgba);
+  shade_pixel<KMAX, PCA>(a, n, id, z, d, b, rgba);
   *reinterpret_cast<float4*>(a.image + pix * 4) = make_float4(rgba[0], rgba[1], rgba[2], rgba[3]);
 }
 
@@ -321,6 +321,9 @@ int check_shade(const HfrShadeFwdArgs* a, const char* who) {
                       a->light_dir && a->light_color && p.F > 0 && p.V > 0 && p.tex_h > 0 && p.tex_w > 0 &&
                       (p.tex_n == 1 || p.tex_n == p.N),
                   "%s: phong/uv shading needs mesh, uv, texture and light pointers", who);
+  HFR_CHECK_ARG(p.tex_pca >= 0 && p.tex_pca <= HFR_MAX_TEX_PCA, "%s: tex_pca must be in [0,%d]", who, HFR_MAX_TEX_PCA);
+  if (p.shade == HFR_SHADE_PHONG_UV && p.tex_pca > 0)
+    HFR_CHECK_ARG(p.tex_n == 1 && a->tex_basis && a->tex_params, "%s: a PCA texture needs the mean map (tex_n = 1), basis and coefficients", who);
   return HFR_OK;
 }
 
@@ -341,7 +344,11 @@ extern "C" int hfr_shade_forward(const HfrShadeFwdArgs* a, void* stream) {
   HFR_CHECK_ARG(a->p.N == 0 || a->image, "shade_forward: null image");
   if (a->p.N == 0) return HFR_OK;
   dim3 grid((a->p.H * a->p.W + 255) / 256, a->p.N);
-#define CALL(KM) shade_fwd_kernel<KM><<<grid, 256, 0, (cudaStream_t)stream>>>(*a)
+#define CALL(KM)                                                                          \
+  do {                                                                                    \
+    if (a->p.tex_pca > 0) shade_fwd_kernel<KM, true><<<grid, 256, 0, (cudaStream_t)stream>>>(*a);   \
+    else shade_fwd_kernel<KM, false><<<grid, 256, 0, (cudaStream_t)stream>>>(*a);         \
+  } while (0)
   HFR_DISPATCH_K(a->p.K, CALL);
 #undef CALL
   HFR_CHECK_LAUNCH("shade_forward");
@@ -358,6 +365,7 @@ extern "C" int hfr_raster_shade_forward(const HfrRasterShadeArgs* a, void* strea
   HFR_CHECK_ARG(s.p.N == a->r.N && s.p.H == a->r.H && s.p.W == a->r.W && s.p.K == a->r.K,
                 "raster_shade_forward: raster / shade dims differ");
   HFR_CHECK_ARG(a->r.N == 0 || s.image, "raster_shade_forward: null image");
+  HFR_CHECK_ARG(s.p.tex_pca == 0, "raster_shade_forward: PCA textures are shaded by hfr_shade_forward (rasterize with hfr_raster_forward)");
   if (a->r.N == 0) return HFR_OK;
   cudaStream_t st = (cudaStream_t)stream;
   uint32_t* ranges = reinterpret_cast<uint32_t*>(a->r.workspace);
@@ -382,6 +390,7 @@ extern "C" int hfr_raster_shade_pool_forward(const HfrRasterShadePoolArgs* a, vo
   HFR_CHECK_ARG(a->aa >= 1 && a->aa <= 16 && a->r.H % a->aa == 0 && a->r.W % a->aa == 0,
                 "raster_shade_pool_forward: image size must be a multiple of aa (1..16)");
   HFR_CHECK_ARG(a->r.N == 0 || a->pooled, "raster_shade_pool_forward: null pooled image");
+  HFR_CHECK_ARG(s.p.tex_pca == 0, "raster_shade_pool_forward: PCA textures are shaded by hfr_shade_forward");
   HFR_CHECK_ARG(!a->mask_rgbs || a->images_in, "raster_shade_pool_forward: mask_rgbs needs images_in");
   if (a->r.N == 0) return HFR_OK;
   cudaStream_t st = (cudaStream_t)stream;

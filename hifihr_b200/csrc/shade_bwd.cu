@@ -40,6 +40,10 @@ __device__ __forceinline__ int selk_i(const int (&a)[KMAX], int k) {
   return r;
 }
 
+__device__ __forceinline__ float gtp_of(const HfrShadeFwdArgs& f, int n, const HfrTexTap& tap, const float* gtex, int c) {
+  return hfr_tex_param_grad(tex_source<true>(f, n), &tap, gtex, c);
+}
+
 #ifndef HFR_BWD_WARP_LIGHT
 #define HFR_BWD_WARP_LIGHT 0
 #endif
@@ -52,7 +56,7 @@ __device__ __forceinline__ int selk_i(const int (&a)[KMAX], int k) {
 #ifndef HFR_BWD_MINB_K1
 #define HFR_BWD_MINB_K1 8
 #endif
-template <int KMAX>
+template <int KMAX, bool PCA>
 __global__ void __launch_bounds__(kBwdThreads, (KMAX == 1 ? HFR_BWD_MINB_K1 : (KMAX <= 4 ? HFR_BWD_MINB : 1))) shade_bwd_kernel(HfrShadeBwdArgs a) {
   __shared__ float s_light[kBwdThreads / 32][6];
   // per-warp staging of the 27 per-fragment components, pitch 33: lane L writes column L (bank j+L),
@@ -230,6 +234,10 @@ __global__ void __launch_bounds__(kBwdThreads, (KMAX == 1 ? HFR_BWD_MINB_K1 : (K
 #pragma unroll
       for (int i = 0; i < 27; ++i) v27[i] = 0.f;
       int vid[3] = {0, 0, 0};
+      HfrTexTap tap_k;                       // kept for the texture-coefficient gradient after the fragment block
+      float gtex_k[3] = {0.f, 0.f, 0.f};
+      tap_k.idx[0] = tap_k.idx[1] = tap_k.idx[2] = tap_k.idx[3] = -1;
+      tap_k.w[0] = tap_k.w[1] = tap_k.w[2] = tap_k.w[3] = 0.f;
       if (vk) {
         const float* __restrict__ bp = f.bary + (pix * K + k) * 3;
         const float bc[3] = {__ldg(bp), __ldg(bp + 1), __ldg(bp + 2)};
@@ -242,7 +250,7 @@ __global__ void __launch_bounds__(kBwdThreads, (KMAX == 1 ? HFR_BWD_MINB_K1 : (K
         if (k < kshade) {
           gather_frag(f, n, face, g);
           vid[0] = g.vid[0]; vid[1] = g.vid[1]; vid[2] = g.vid[2];
-          shade_fragment(f, n, g, bc, dhat, lcol, col, &tap, &ctx, texel);
+          shade_fragment<PCA>(f, n, g, bc, dhat, lcol, col, &tap, &ctx, texel);
         }
         if (P.blend == HFR_BLEND_SOFTMAX) {
           const float wk = pk * ek;
@@ -258,7 +266,13 @@ __global__ void __launch_bounds__(kBwdThreads, (KMAX == 1 ? HFR_BWD_MINB_K1 : (K
           float gP[3], gNn[3], gtex[3];
           hfr_phong_bwd(P, dhat, lcol, texel, &ctx, gcol, gP, gNn, gtex, acc_dhat, acc_lcol);
           float gu = 0.f, gv = 0.f;
-          hfr_tex_uv_grad(f.texture + tbase, &tap, gtex, &gu, &gv);
+          const HfrTexSrc tsrc = tex_source<PCA>(f, n);
+          hfr_tex_uv_grad(tsrc, &tap, gtex, &gu, &gv);
+          if (PCA && a.g_tex_params) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { tap_k.idx[q] = tap.idx[q]; tap_k.w[q] = tap.w[q]; }
+            gtex_k[0] = gtex[0]; gtex_k[1] = gtex[1]; gtex_k[2] = gtex[2];
+          }
           if (a.g_texture) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -293,6 +307,13 @@ __global__ void __launch_bounds__(kBwdThreads, (KMAX == 1 ? HFR_BWD_MINB_K1 : (K
           hfr_raster_eval_bwd(xf, yf, vv, a.perspective_correct, a.clip_barycentric, g_bc, gz, gd, gvv);
 #pragma unroll
           for (int i = 0; i < 3; ++i) { v27[9 * i] = gvv[3 * i]; v27[9 * i + 1] = gvv[3 * i + 1]; v27[9 * i + 2] = gvv[3 * i + 2]; }
+        }
+      }
+      if (PCA && a.g_tex_params && k < kshade) {
+        // d(loss)/d(texture coefficients): warp-reduce each component over the lanes of this slot, one RED per warp
+        for (int c = 0; c < P.tex_pca; ++c) {
+          const float t = warp_sum(vk ? gtp_of(f, n, tap_k, gtex_k, c) : 0.0f);
+          if (lane == 0 && t != 0.0f) atomicAdd(a.g_tex_params + (size_t)n * P.tex_pca + c, t);
         }
       }
       if (!(a.g_verts_ndc || (k < kshade && (a.g_verts_view || a.g_vnormals)))) continue;
@@ -388,6 +409,7 @@ extern "C" int hfr_shade_backward(const HfrShadeBwdArgs* a, void* stream) {
   HFR_CHECK_ARG(a->f.p.blend != HFR_BLEND_SOFTMAX || a->f.image, "shade_backward: the softmax blend needs the forward image");
   HFR_CHECK_ARG(!a->g_verts_ndc || (a->verts_ndc && a->f.faces && a->f.p.F > 0 && a->f.p.V > 0),
                 "shade_backward: fused raster backward needs verts_ndc and faces");
+  HFR_CHECK_ARG(!a->g_tex_params || a->f.p.tex_pca > 0, "shade_backward: g_tex_params needs a PCA texture (tex_pca > 0)");
   HFR_CHECK_ARG(a->pool_aa <= 1 || (a->pool_aa <= 16 && a->f.p.H % a->pool_aa == 0 && a->f.p.W % a->pool_aa == 0),
                 "shade_backward: image size must be a multiple of pool_aa (<= 16)");
   const HfrShadeParams& p = a->f.p;
@@ -396,8 +418,13 @@ extern "C" int hfr_shade_backward(const HfrShadeBwdArgs* a, void* stream) {
 #define HFR_LAUNCH_BWD(KM)                                                                              \
   do {                                                                                                  \
     const size_t sm = (size_t)(KM) * 4 * kBwdThreads * sizeof(float);                                   \
-    cudaFuncSetAttribute(shade_bwd_kernel<KM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);   \
-    shade_bwd_kernel<KM><<<grid, kBwdThreads, sm, st>>>(*a);                                            \
+    if (p.tex_pca > 0) {                                                                                \
+      cudaFuncSetAttribute(shade_bwd_kernel<KM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);   \
+      shade_bwd_kernel<KM, true><<<grid, kBwdThreads, sm, st>>>(*a);                                    \
+    } else {                                                                                            \
+      cudaFuncSetAttribute(shade_bwd_kernel<KM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);  \
+      shade_bwd_kernel<KM, false><<<grid, kBwdThreads, sm, st>>>(*a);                                   \
+    }                                                                                                   \
   } while (0)
   if (p.K == 1) HFR_LAUNCH_BWD(1);
   else if (p.K == 2) HFR_LAUNCH_BWD(2);

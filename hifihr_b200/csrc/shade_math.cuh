@@ -41,19 +41,47 @@ HFR_HD void hfr_tex_tap(int Ht, int Wt, float u, float v, HfrTexTap* t) {
   t->idx[3] = (xin1 && yin1) ? (Ht - 2 - yi) * Wt + xi + 1 : -1;
 }
 
-HFR_HD void hfr_tex_fetch(const float* tex, const HfrTexTap* t, float* out) {
+// Where texel values come from: a plain map, or a PCA texture model evaluated on the fly,
+//   texel(idx) = mean[idx] + sum_k params[k] * basis[k][idx]
+// (NIMBLE-style per-sample texture, SURVEY.md 8(f) row 4: the per-sample 1024^2 map is never materialised).
+struct HfrTexSrc {
+  const float* tex;      // plain map of this sample, or the PCA mean map
+  const float* basis;    // (npc, Ht, Wt, 3) or NULL
+  const float* params;   // this sample's npc coefficients or NULL
+  int npc;               // 0 = plain map
+  size_t map_floats;     // Ht * Wt * 3
+};
+
+HFR_HD HfrTexSrc hfr_tex_plain(const float* tex) {
+  HfrTexSrc s; s.tex = tex; s.basis = nullptr; s.params = nullptr; s.npc = 0; s.map_floats = 0;
+  return s;
+}
+
+HFR_HD void hfr_texel(const HfrTexSrc& src, int idx, float* v) {
+  const float* m = src.tex + (size_t)idx * 3;
+  v[0] = m[0]; v[1] = m[1]; v[2] = m[2];
+  for (int k = 0; k < src.npc; ++k) {
+    const float pk = src.params[k];
+    const float* b = src.basis + (size_t)k * src.map_floats + (size_t)idx * 3;
+    v[0] += pk * b[0]; v[1] += pk * b[1]; v[2] += pk * b[2];
+  }
+}
+
+HFR_HD void hfr_tex_fetch(const HfrTexSrc& src, const HfrTexTap* t, float* out) {
   out[0] = out[1] = out[2] = 0.0f;
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     if (t->idx[q] >= 0) {
-      const float* s = tex + (size_t)t->idx[q] * 3;
+      float s[3];
+      hfr_texel(src, t->idx[q], s);
       out[0] += s[0] * t->w[q]; out[1] += s[1] * t->w[q]; out[2] += s[2] * t->w[q];
     }
   }
 }
+HFR_HD void hfr_tex_fetch(const float* tex, const HfrTexTap* t, float* out) { hfr_tex_fetch(hfr_tex_plain(tex), t, out); }
 
 // d(texel)/d(u,v) contracted with g[3]
-HFR_HD void hfr_tex_uv_grad(const float* tex, const HfrTexTap* t, const float* g, float* gu, float* gv) {
+HFR_HD void hfr_tex_uv_grad(const HfrTexSrc& src, const HfrTexTap* t, const float* g, float* gu, float* gv) {
   float gix = 0.0f, giy = 0.0f;
   const float ax = t->x0 + 1.0f - t->ix, bx = t->ix - t->x0, ay = t->y0 + 1.0f - t->iy, by = t->iy - t->y0;
   const float dwx[4] = {-ay, ay, -by, by};   // d w / d ix
@@ -61,13 +89,30 @@ HFR_HD void hfr_tex_uv_grad(const float* tex, const HfrTexTap* t, const float* g
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     if (t->idx[q] >= 0) {
-      const float* s = tex + (size_t)t->idx[q] * 3;
+      float s[3];
+      hfr_texel(src, t->idx[q], s);
       const float dot = s[0] * g[0] + s[1] * g[1] + s[2] * g[2];
       gix += dot * dwx[q]; giy += dot * dwy[q];
     }
   }
   *gu = gix * t->mx;
   *gv = giy * t->my;
+}
+HFR_HD void hfr_tex_uv_grad(const float* tex, const HfrTexTap* t, const float* g, float* gu, float* gv) {
+  hfr_tex_uv_grad(hfr_tex_plain(tex), t, g, gu, gv);
+}
+
+// d(texel)/d(params[k]) contracted with g[3]: sum_q w_q * (g . basis[k][idx_q])
+HFR_HD float hfr_tex_param_grad(const HfrTexSrc& src, const HfrTexTap* t, const float* g, int k) {
+  float acc = 0.0f;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if (t->idx[q] >= 0) {
+      const float* b = src.basis + (size_t)k * src.map_floats + (size_t)t->idx[q] * 3;
+      acc += t->w[q] * (b[0] * g[0] + b[1] * g[1] + b[2] * g[2]);
+    }
+  }
+  return acc;
 }
 
 // ---------------------------------------------------------------------------------- lighting

@@ -55,7 +55,24 @@ HFR_HD void light_dir_hat(const HfrShadeFwdArgs& a, int n, float* dhat, float* l
   hfr_normalize_eps(d, dhat, len);
 }
 
+// texel source of sample n: its own / the shared map, or the PCA texture model with the sample's coefficients
+// (PCA is a template parameter so the plain-map kernels carry none of the model's state: with it as a runtime
+// branch the fused forward lost 6 % and the backward 28 % to extra live registers)
+template <bool PCA>
+HFR_HD HfrTexSrc tex_source(const HfrShadeFwdArgs& a, int n) {
+  const size_t map_floats = (size_t)a.p.tex_h * a.p.tex_w * 3;
+  HfrTexSrc s = hfr_tex_plain(a.texture + (a.p.tex_n == 1 ? 0 : (size_t)n * map_floats));
+  if (PCA) {
+    s.map_floats = map_floats;
+    s.npc = a.p.tex_pca;
+    s.basis = a.tex_basis;
+    s.params = a.tex_params + (size_t)n * a.p.tex_pca;
+  }
+  return s;
+}
+
 // colour of one fragment (Phong x UV texel).  `tap` and `ctx` are kept for the backward.
+template <bool PCA = false>
 HFR_HD void shade_fragment(const HfrShadeFwdArgs& a, int n, const FragGeom& g, const float* bc,
                                                const float* dhat, const float* lcol, float* color, HfrTexTap* tap,
                                                HfrPhongCtx* ctx, float* texel) {
@@ -65,13 +82,12 @@ HFR_HD void shade_fragment(const HfrShadeFwdArgs& a, int n, const FragGeom& g, c
   const float u = bc[0] * g.uv[0] + bc[1] * g.uv[2] + bc[2] * g.uv[4];
   const float v = bc[0] * g.uv[1] + bc[1] * g.uv[3] + bc[2] * g.uv[5];
   hfr_tex_tap(a.p.tex_h, a.p.tex_w, u, v, tap);
-  const float* tex = a.texture + (a.p.tex_n == 1 ? 0 : (size_t)n * a.p.tex_h * a.p.tex_w * 3);
-  hfr_tex_fetch(tex, tap, texel);
+  hfr_tex_fetch(tex_source<PCA>(a, n), tap, texel);
   hfr_phong_fwd(a.p, P, Nn, dhat, lcol, texel, color, ctx);
 }
 
 // Full forward for one pixel given its K fragments.
-template <int KMAX>
+template <int KMAX, bool PCA = false>
 HFR_HD void shade_pixel(const HfrShadeFwdArgs& a, int n, const int64_t* id, const float* z,
                                             const float* d, const float* b, float* rgba) {
   const int K = a.p.K;
@@ -105,7 +121,7 @@ HFR_HD void shade_pixel(const HfrShadeFwdArgs& a, int n, const int64_t* id, cons
       FragGeom g;
       gather_frag(a, n, (int)(id[k] - (int64_t)n * a.p.F), g);
       HfrTexTap tap; HfrPhongCtx ctx; float texel[3];
-      shade_fragment(a, n, g, b + 3 * k, dhat, lcol, colors + 3 * k, &tap, &ctx, texel);
+      shade_fragment<PCA>(a, n, g, b + 3 * k, dhat, lcol, colors + 3 * k, &tap, &ctx, texel);
     }
   }
   hfr_blend_fwd<KMAX>(a.p, K, valid, z, d, colors, rgba);

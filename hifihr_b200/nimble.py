@@ -22,7 +22,7 @@ import torch
 from torch import nn
 
 from . import ops
-from .renderer import TexturesUV
+from .renderer import TexturesUV, TexturesUVPCA
 from .structures import Meshes
 
 SEED = 20231
@@ -124,10 +124,11 @@ def build_nimble_like(tex_size=1024, n_shape=20, n_pose_pca=30, n_tex=10, seed=S
 
 
 class MyNIMBLELayer(nn.Module):
-    def __init__(self, ifRender, device, shape_ncomp=20, pose_ncomp=30, tex_ncomp=10, tex_size=1024):
+    def __init__(self, ifRender, device, shape_ncomp=20, pose_ncomp=30, tex_ncomp=10, tex_size=1024, fused_texture=False):
         super().__init__()
         self.device = torch.device(device)
         self.ifRender = ifRender
+        self.fused_texture = fused_texture   # True: skin_meshes carry a TexturesUVPCA, no per-sample maps are built
         d = build_nimble_like(tex_size, shape_ncomp, pose_ncomp, tex_ncomp)
         self._d = d
         self.V, self.F = d["v_template"].shape[0], d["faces"].shape[0]
@@ -160,14 +161,18 @@ class MyNIMBLELayer(nn.Module):
         out = {"nimble_joints": joints25, "joints": joints25[:, self.mano21], "verts": verts, "faces": self.faces,
                "mano_verts": verts[:, self.mano_map], "rot": rot}
         tex_img = None
+        meshes = Meshes(verts, self.faces, topology=topo)
         if self.ifRender and hand_params.get("texture_params") is not None:
             tp = hand_params["texture_params"]                                    # (B, 10)
             T = self.tex_mean.shape[0]
-            # per-sample diffuse map = mean + params @ basis (plain library GEMM; see DESIGN.md §8 for the fused plan)
-            tex_img = (self.tex_mean.reshape(1, -1) + tp @ self.tex_basis.reshape(tp.shape[1], -1)).view(-1, T, T, 3)
-        meshes = Meshes(verts, self.faces, topology=topo)
-        if tex_img is not None:
-            meshes.textures = TexturesUV(tex_img, self.faces, self.verts_uvs)
+            if self.fused_texture:
+                # the shader kernels evaluate mean + params @ basis at the taps of every fragment: the (B,T,T,3) maps
+                # never exist; 'textures' is then None - ask for maps_padded() to export them
+                meshes.textures = TexturesUVPCA(self.tex_mean, self.tex_basis, tp, self.faces, self.verts_uvs)
+            else:
+                # per-sample diffuse map = mean + params @ basis (plain library GEMM), as the reference's layer returns it
+                tex_img = (self.tex_mean.reshape(1, -1) + tp @ self.tex_basis.reshape(tp.shape[1], -1)).view(-1, T, T, 3)
+                meshes.textures = TexturesUV(tex_img, self.faces, self.verts_uvs)
         out["skin_meshes"] = meshes
         out["textures"] = tex_img
         return out

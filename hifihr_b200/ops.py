@@ -189,7 +189,8 @@ def raster_tile_box(ws, Ftot, N):
 
 
 def shade_params(N, H, W, K, F, V, blend, shade, sigma, gamma, background, light_ambient, light_specular,
-                 mat_ambient, mat_diffuse, mat_specular, shininess, tex_shape=(1, 1, 1), VT=0, znear=1.0, zfar=100.0):
+                 mat_ambient, mat_diffuse, mat_specular, shininess, tex_shape=(1, 1, 1), VT=0, znear=1.0, zfar=100.0,
+                 tex_pca=0):
     p = L.HfrShadeParams()
     p.N, p.H, p.W, p.K, p.F, p.V, p.blend, p.shade = N, H, W, K, F, V, blend, shade
     p.sigma, p.gamma, p.znear, p.zfar = float(sigma), float(gamma), float(znear), float(zfar)
@@ -198,16 +199,17 @@ def shade_params(N, H, W, K, F, V, blend, shade, sigma, gamma, background, light
     p.mat_ambient, p.mat_diffuse, p.mat_specular = L.f3(mat_ambient), L.f3(mat_diffuse), L.f3(mat_specular)
     p.shininess = float(shininess)
     p.tex_n, p.tex_h, p.tex_w, p.VT = int(tex_shape[0]), int(tex_shape[1]), int(tex_shape[2]), int(VT)
+    p.tex_pca = int(tex_pca)
     return p
 
 
 def shade_fwd_args(p, frags, faces, verts_view, vnormals, faces_uvs, verts_uvs, texture, light_dir, light_color, image,
-                   face_attr=None):
+                   face_attr=None, tex_basis=None, tex_params=None):
     p2f, zbuf, bary, dists = frags
     return L.HfrShadeFwdArgs(p, L.ptr(p2f, I64), L.ptr(zbuf, F32), L.ptr(bary, F32), L.ptr(dists, F32),
                              L.ptr(faces, I32), L.ptr(verts_view, F32), L.ptr(vnormals, F32), L.ptr(faces_uvs, I32),
                              L.ptr(verts_uvs, F32), L.ptr(texture, F32), L.ptr(light_dir, F32), L.ptr(light_color, F32),
-                             L.ptr(image, F32), L.ptr(face_attr, F32))
+                             L.ptr(image, F32), L.ptr(face_attr, F32), L.ptr(tex_basis, F32), L.ptr(tex_params, F32))
 
 
 def face_attr_forward(faces, verts_view, vnormals, faces_uvs, verts_uvs, out):
@@ -342,37 +344,41 @@ class ShadeFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, params, p2f, zbuf, bary, dists, faces, verts_view, vnormals, faces_uvs, verts_uvs, texture,
-                light_dir, light_color):
+                light_dir, light_color, tex_basis=None, tex_params=None):
         N, H, W, K = p2f.shape
         cu = lambda t: None if t is None else _cu(t)  # noqa: E731
         zbuf, bary, dists = cu(zbuf), cu(bary), cu(dists)
         verts_view, vnormals, texture = cu(verts_view), cu(vnormals), cu(texture)
         light_dir, light_color, verts_uvs = cu(light_dir), cu(light_color), cu(verts_uvs)
+        tex_basis, tex_params = cu(tex_basis), cu(tex_params)
         image = torch.empty(N, H, W, 4, dtype=F32, device=p2f.device)
         a = shade_fwd_args(params, (p2f, zbuf, bary, dists), faces, verts_view, vnormals, faces_uvs, verts_uvs,
-                           texture, light_dir, light_color, image)
+                           texture, light_dir, light_color, image, None, tex_basis, tex_params)
         L.call("hfr_shade_forward", a)
         ctx.params = params
+        ctx.pca = tex_basis is not None
         ctx.save_for_backward(p2f, zbuf, bary, dists, faces, verts_view, vnormals, faces_uvs, verts_uvs, texture,
-                              light_dir, light_color, image)
+                              light_dir, light_color, image, *([tex_basis, tex_params] if tex_basis is not None else []))
         return image
 
     @staticmethod
     def backward(ctx, g_image):
         (p2f, zbuf, bary, dists, faces, verts_view, vnormals, faces_uvs, verts_uvs, texture, light_dir,
-         light_color, image) = ctx.saved_tensors
+         light_color, image) = ctx.saved_tensors[:13]
+        tex_basis, tex_params = ctx.saved_tensors[13:] if ctx.pca else (None, None)
         p = ctx.params
         g_image = _cu(g_image)
         f = shade_fwd_args(p, (p2f, zbuf, bary, dists), faces, verts_view, vnormals, faces_uvs, verts_uvs, texture,
-                           light_dir, light_color, image)
+                           light_dir, light_color, image, None, tex_basis, tex_params)
+        g_tp = torch.zeros_like(tex_params) if ctx.pca else None
         g_zbuf, g_bary, g_dists = torch.empty_like(zbuf), torch.empty_like(bary), torch.empty_like(dists)
         z = lambda t: None if t is None else torch.zeros_like(t)  # noqa: E731
         g_vv, g_vn, g_tex, g_ld, g_lc = z(verts_view), z(vnormals), z(texture), z(light_dir), z(light_color)
         a = L.HfrShadeBwdArgs(f, L.ptr(g_image, F32), L.ptr(g_zbuf, F32), L.ptr(g_bary, F32), L.ptr(g_dists, F32),
                               None, None, 0.0, 1, 0, L.ptr(g_vv, F32), L.ptr(g_vn, F32), L.ptr(g_tex, F32),
-                              L.ptr(g_ld, F32), L.ptr(g_lc, F32))
+                              L.ptr(g_ld, F32), L.ptr(g_lc, F32), None, 0, 0, L.ptr(g_tp, F32))
         L.call("hfr_shade_backward", a)
-        return None, None, g_zbuf, g_bary, g_dists, None, g_vv, g_vn, None, None, g_tex, g_ld, g_lc
+        return None, None, g_zbuf, g_bary, g_dists, None, g_vv, g_vn, None, None, g_tex, g_ld, g_lc, None, g_tp
 
 
 class PoolFunction(torch.autograd.Function):

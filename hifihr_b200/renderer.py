@@ -150,6 +150,25 @@ class TexturesUV:
         raise NotImplementedError("texel sampling is fused into the shader kernels (hfr_shade_forward)")
 
 
+class TexturesUVPCA(TexturesUV):
+    """UV texture given as a PCA model: per-sample map = mean + params @ basis (the NIMBLE texture model, SURVEY.md
+    §8f row 4).  The shader kernels evaluate the model at the four bilinear taps of every fragment, so the
+    (N, T, T, 3) per-sample maps are never materialised; gradients flow to `params` (and to `mean`).
+    mean (1,T,T,3) or (T,T,3); basis (n_comp,T,T,3); params (N,n_comp)."""
+
+    def __init__(self, mean, basis, params, faces_uvs, verts_uvs):
+        mean = mean if mean.dim() == 4 else mean[None]
+        super().__init__(mean, faces_uvs, verts_uvs)
+        if basis.shape[1:] != mean.shape[1:] or params.shape[1] != basis.shape[0]:
+            raise ValueError("TexturesUVPCA: basis must be (n_comp,T,T,3) matching the mean map, params (N,n_comp)")
+        self._basis, self._params = basis, params
+
+    def maps_padded(self):
+        """The materialised per-sample maps (library GEMM) - for visualisation / export only."""
+        n = self._params.shape[1]
+        return (self._maps.reshape(1, -1) + self._params @ self._basis.reshape(n, -1)).view(-1, *self._maps.shape[1:])
+
+
 # ------------------------------------------------------------------------------------------------
 class MeshRasterizer(nn.Module):
     def __init__(self, cameras=None, raster_settings=None):
@@ -238,17 +257,20 @@ class _ShaderBase(nn.Module):
             tex = meshes.textures
             if tex is None:
                 raise ValueError("Meshes does not have textures")
-            maps = tex.maps_padded()
+            pca = isinstance(tex, TexturesUVPCA)
+            maps = tex._maps if pca else tex.maps_padded()
             params = ops.shade_params(N, H, W, K, topo.F, topo.V, self.blend, 1, bp.sigma, bp.gamma,
                                       bp.background_color, _c3(lights.ambient_color), _c3(lights.specular_color),
                                       _c3(materials.ambient_color), _c3(materials.diffuse_color),
                                       _c3(materials.specular_color), materials.shininess,
-                                      tex_shape=maps.shape[:3], VT=tex._verts_uvs.shape[0])
+                                      tex_shape=maps.shape[:3], VT=tex._verts_uvs.shape[0],
+                                      tex_pca=tex._basis.shape[0] if pca else 0)
             ldir = _rows(lights.direction, N, dev, "lights.direction")
             lcol = _rows(lights.diffuse_color, N, dev, "lights.diffuse_color")
             return ops.ShadeFunction.apply(params, p2f, fragments.zbuf, fragments.bary_coords, fragments.dists,
                                            topo.faces, meshes.verts_padded(), meshes.verts_normals_padded(),
-                                           tex._faces_uvs.to(dev), tex._verts_uvs.to(dev), maps, ldir, lcol)
+                                           tex._faces_uvs.to(dev), tex._verts_uvs.to(dev), maps, ldir, lcol,
+                                           tex._basis if pca else None, tex._params if pca else None)
         params = ops.shade_params(N, H, W, K, topo.F, topo.V, self.blend, 0, bp.sigma, bp.gamma, bp.background_color,
                                   (0, 0, 0), (0, 0, 0), (0, 0, 0), (0, 0, 0), (0, 0, 0), 1.0)
         return ops.ShadeFunction.apply(params, p2f, fragments.zbuf, fragments.bary_coords, fragments.dists,

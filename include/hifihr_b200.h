@@ -211,7 +211,11 @@ typedef struct HfrShadeParams {
   float shininess;
   int32_t tex_n, tex_h, tex_w;      /* texture maps (tex_n = 1 shared, or N)               */
   int32_t VT;                       /* number of uv vertices                               */
+  int32_t tex_pca;                  /* > 0: `texture` is the MEAN map (tex_n = 1) of a PCA texture model with this many
+                                       components, evaluated per fragment: texel = mean + sum_k params[n][k] * basis[k]
+                                       (NIMBLE-style per-sample texture without materialising the per-sample maps) */
 } HfrShadeParams;
+#define HFR_MAX_TEX_PCA 64
 
 typedef struct HfrShadeFwdArgs {
   HfrShadeParams p;
@@ -229,6 +233,8 @@ typedef struct HfrShadeFwdArgs {
    * When set, the shaders read one contiguous record per fragment instead of chasing
    * faces -> verts_view / vnormals and faces_uvs -> verts_uvs (two dependent gathers).  NULL = gather path. */
   const float* face_attr;
+  const float* tex_basis;           /* (tex_pca,tex_h,tex_w,3) when p.tex_pca > 0          */
+  const float* tex_params;          /* (N,tex_pca)             when p.tex_pca > 0          */
 } HfrShadeFwdArgs;
 int hfr_shade_forward(const HfrShadeFwdArgs* a, void* stream);
 
@@ -270,6 +276,7 @@ typedef struct HfrShadeBwdArgs {
    * (avg_pool2d backward, models_res_nimble.py:211) and, with pool_binarize, no gradient reaches alpha (the
    * reference binarises re_sil in place, :219).  0 or 1 = g_image is full resolution. */
   int32_t pool_aa, pool_binarize;
+  float* g_tex_params;              /* (N,tex_pca) accumulated (caller zeroes), PCA textures only; may be NULL */
 } HfrShadeBwdArgs;
 int hfr_shade_backward(const HfrShadeBwdArgs* a, void* stream);
 /* Address of the (N,4) uint32 tile box {txmin, 255-txmax, tymin, 255-tymax} (16x16-pixel tiles) inside a

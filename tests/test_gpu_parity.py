@@ -184,6 +184,68 @@ def test_nimble_layer_contract_and_lbs_parity(hf):
     assert leaves[2].grad is not None and leaves[2].grad.abs().max() > 0
 
 
+@pytest.mark.parametrize("K,soft", [(1, False), (3, True)])
+def test_pca_texture_sampled_in_the_shader(hf, K, soft):
+    """SURVEY 8(f) row 4, second half: the NIMBLE-style texture model (mean + params @ basis) evaluated at the
+    bilinear taps inside the shader kernels (TexturesUVPCA) against the same render with the per-sample maps
+    materialised first (TexturesUV) and against oracle autograd for d/d(texture params): images 2e-5 abs,
+    gradients 1e-3 of the tensor's max."""
+    from hifihr_b200.nimble import MyNIMBLELayer
+    B, T, S = 3, 32, 48
+    g = torch.Generator().manual_seed(91)
+    pose = torch.cat([torch.randn(B, 3, generator=g) * 0.4, torch.randn(B, 30, generator=g) * 0.5], 1).to(DEV)
+    shape = (torch.randn(B, 20, generator=g) * 0.5).to(DEV)
+    texp = torch.randn(B, 10, generator=g)
+    inp = P.synthetic_inputs(B, S=S, seed=6)
+    root = torch.tensor([[0.0, 0.0, 0.45]]).repeat(B, 1).to(DEV)
+    fcl, prp = p3d.ndc_intrinsics(inp["Ks"])
+    cams = hf.PerspectiveCameras(focal_length=-fcl.to(DEV), principal_point=prp.to(DEV), device=DEV)
+    lights = hf.DirectionalLights(diffuse_color=inp["light_color"].to(DEV), direction=inp["light_dir"].to(DEV), device=DEV)
+    blur = 9.21e-4 if soft else 0.0
+    rs = hf.RasterizationSettings(image_size=S, blur_radius=blur, faces_per_pixel=K)
+    mats = hf.Materials(diffuse_color=((0.8, 0.8, 0.8),), specular_color=((0.2, 0.2, 0.2),), shininess=30, device=DEV)
+    shader = (hf.SoftPhongShader if soft else hf.HardPhongShader)(materials=mats, device=DEV)
+    renderer = hf.MeshRenderer(rasterizer=hf.MeshRasterizer(raster_settings=rs), shader=shader)
+    gimg = torch.randn(B, S, S, 4, generator=g).to(DEV)
+    imgs, grads = [], []
+    for fused in (True, False):
+        layer = MyNIMBLELayer(True, DEV, shape_ncomp=20, pose_ncomp=30, tex_ncomp=10, tex_size=T, fused_texture=fused).to(DEV)
+        tp = texp.clone().to(DEV).requires_grad_(True)
+        out = layer({"pose_params": pose, "shape_params": shape, "texture_params": tp}, handle_collision=False)
+        assert (out["textures"] is None) == fused
+        assert isinstance(out["skin_meshes"].textures, hf.TexturesUVPCA) == fused
+        meshes = out["skin_meshes"]
+        meshes.offset_verts_(root[:, None].repeat(1, layer.V, 1).view(B * layer.V, 3))
+        img = renderer(meshes, cameras=cams, lights=lights)
+        (img * gimg).sum().backward()
+        imgs.append(img.detach())
+        grads.append(tp.grad.clone())
+        if fused:   # the export path materialises the same maps the unfused layer returns
+            maps = meshes.textures.maps_padded()
+            d = layer._d
+            ref_maps = d["tex_mean"][None] + torch.einsum("bk,khwc->bhwc", texp, d["tex_basis"])
+            assert (maps.detach().cpu() - ref_maps).abs().max() < 1e-5
+    assert (imgs[0] - imgs[1]).abs().max() < 2e-5
+    assert (imgs[0][..., 3] > 0).float().mean() > 0.02
+    assert rel_err(grads[0], grads[1]) < 1e-3 and grads[0].abs().max() > 0
+    # oracle autograd for d(image)/d(texture params) on the kernel's own Fragments
+    d = layer._d
+    with torch.no_grad():
+        fr_dev = renderer.rasterizer(meshes, cameras=cams)
+    fr = p3d.Fragments(fr_dev.pix_to_face.cpu(), fr_dev.zbuf.cpu(), fr_dev.bary_coords.cpu(), fr_dev.dists.cpu()) \
+        if hasattr(p3d, "Fragments") else fr_dev
+    tpo = texp.clone().requires_grad_(True)
+    tex_o = d["tex_mean"][None] + torch.einsum("bk,khwc->bhwc", tpo, d["tex_basis"])
+    faces = torch.tensor(d["faces"])
+    texels = p3d.sample_textures_uv(fr, tex_o, faces, torch.tensor(d["verts_uvs"]))
+    view = meshes.verts_padded().detach().cpu()
+    colors = p3d.phong_shading(fr, view, faces, texels, inp["light_dir"], inp["light_color"])
+    img_o = p3d.softmax_rgb_blend(colors, fr, 1e-4, 1e-4) if soft else p3d.hard_rgb_blend(colors, fr)
+    (img_o * gimg.cpu()).sum().backward()
+    assert (imgs[0].cpu() - img_o.detach()).abs().max() < 2e-5
+    assert rel_err(grads[0], tpo.grad) < 1e-3
+
+
 # ------------------------------------------------------------------------------------------ geometry
 def test_geometry_forward_backward(hf, mano):
     from hifihr_b200 import ops
