@@ -9,9 +9,9 @@
 //           a warp owns an 8x4 pixel block, so every Fragments row segment a warp writes is
 //           contiguous (8 pixels * K * {8,4,12,4} B) and sector-aligned.
 //   coarse: every thread looks at one face's packed tile range (4 B, coalesced, from the setup
-//           kernel) per step; hits are compacted IN FACE ORDER with a ballot/popc prefix, so the
-//           tile list is sorted by face index and z-ties resolve to the smaller index with a
-//           strict `<` (the CPU reference's (z, face) ordering).
+//           kernel) per step; hits are compacted with a popc prefix into the tile list (any order:
+//           the list is depth-sorted afterwards and the top-K resolves z-ties by the packed face
+//           index explicitly - the CPU reference's (z, face) ordering).
 //   stage:  the listed faces' 9 floats are gathered once per tile into 64-byte shared records
 //           together with the dilated bbox and the barycentric denominator.
 //   fine:   per 32 list entries, lane i builds the 32-bit mask of the warp's 8x4 pixels that lie in
@@ -37,6 +37,7 @@ struct RasterSmem {
   float tabx[kTileW], taby[kTileH];                          // NDC sample positions of the tile's columns / rows
   int wsum[kRasterThreads / 32];
   uint16_t order[kListCap];   // record indices ordered front to back (depth buckets of the faces' nearest vertex)
+  int fidx[kListCap];         // face index (within the mesh) of every list entry of the batch being staged
   float zred[2][kRasterThreads / 32];   // per-warp min / max of the batch's nearest-vertex depths
   int hist[kDepthBuckets];              // faces per depth bucket
   int bmin[kDepthBuckets];              // smallest nearest-vertex depth in the bucket (float bits; depths are > 0)
@@ -129,9 +130,9 @@ __device__ __forceinline__ float pix_to_ndc_pre(int i, float range, float offset
 // Coarse + stage + fine for one tile.  On return `top` holds, per thread (= pixel), the KMAX
 // nearest valid faces as packed face ids (sorted by (z, id)).
 //
-//   coarse: thread t owns a CONTIGUOUS chunk of faces and keeps one hit bit per face from a
+//   coarse: thread t tests faces t, t + 256, ... (coalesced loads) and keeps one hit bit per face from a
 //           single pass over the packed tile ranges; one block-wide scan of the hit counts then
-//           gives every thread its slot in the tile list.  A tile no face touches leaves after
+//           gives every thread its slots in the tile list.  A tile no face touches leaves after
 //           that scan.
 //   stage:  listed faces are gathered once per tile into 80-byte shared records and ordered front
 //           to back by their nearest vertex (counting sort over depth buckets in shared memory).
@@ -186,14 +187,22 @@ __device__ __forceinline__ void raster_tile(const HfrRasterArgs& a, const uint32
   for (int cbase = 0; cbase < nf; cbase += kChunk) {
     const int cn = min(nf - cbase, kChunk);
     const int per = (cn + kRasterThreads - 1) / kRasterThreads;   // <= 32
-    const int first = cbase + tid * per;
+    // thread t looks at faces cbase + j * 256 + t: every load of the warp is one coalesced 128-byte line and the
+    // iterations are independent (4 in flight).  Hit bit j <-> that face; the order of the tile list is irrelevant
+    // (it is depth-sorted below and z-ties are resolved by the packed face index explicitly).
     uint32_t hits = 0;
-    for (int j = 0; j < per; ++j) {
-      const int fi = first + j;
-      if (fi < cbase + cn) {
-        const uint32_t w = __ldg(tile_ranges + f0 + fi);
+    for (int j0 = 0; j0 < per; j0 += 4) {
+      uint32_t w4[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int fi = (j0 + u) * kRasterThreads + tid;
+        w4[u] = (j0 + u < per && fi < cn) ? __ldg(tile_ranges + f0 + cbase + fi) : kEmptyRange;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t w = w4[u];
         const int txmin = w & 255, txmax = (w >> 8) & 255, tymin = (w >> 16) & 255, tymax = w >> 24;
-        if (tx >= txmin && tx <= txmax && ty >= tymin && ty <= tymax) hits |= 1u << j;
+        if (tx >= txmin && tx <= txmax && ty >= tymin && ty <= tymax) hits |= 1u << (j0 + u);
       }
     }
     // block-wide exclusive scan of the per-thread hit counts
@@ -220,33 +229,37 @@ __device__ __forceinline__ void raster_tile(const HfrRasterArgs& a, const uint32
     for (int lbase = 0; lbase < total; lbase += kListCap) {
       const int bcnt = min(total - lbase, kListCap);
       if (lbase > 0) __syncthreads();   // previous batch consumed
-      // stage: every thread writes the records of its own hits that fall into this batch
+      // stage, balanced: the hit face ids of this batch go to a shared index list first (a thread may own many
+      // hits, a coherent mesh puts up to 32 consecutive faces of one thread into the same tile), then thread p
+      // gathers and precomputes record p - one record per thread, 9 independent loads each
       {
         uint32_t m = hits;
         int pos = my0;
         while (m) {
           const int j = __ffs(m) - 1;
           m &= m - 1;
-          if (pos >= lbase && pos < lbase + bcnt) {
-            const int face = (int)(f0 + first + j);
-            const float* __restrict__ v = a.face_verts + (size_t)face * 9;
-            float r[9];
-#pragma unroll
-            for (int e = 0; e < 9; ++e) r[e] = __ldg(v + e);
-            float4* dst = reinterpret_cast<float4*>(sm.rec + (pos - lbase) * kRecFloats);
-            const float xmin = XSUB(hfr_min3(r[0], r[3], r[6]), rblur), xmax = XADD(hfr_max3(r[0], r[3], r[6]), rblur);
-            const float ymin = XSUB(hfr_min3(r[1], r[4], r[7]), rblur), ymax = XADD(hfr_max3(r[1], r[4], r[7]), rblur);
-            const float area = XADD(hfr_edge(r[6], r[7], r[0], r[1], r[3], r[4]), HFR_KEPS);
-            dst[0] = make_float4(r[0], r[1], r[2], r[3]);
-            dst[1] = make_float4(r[4], r[5], r[6], r[7]);
-            dst[2] = make_float4(r[8], xmin, xmax, ymin);
-            // zmin shrunk by 1e-5: the rounded pz of a convex combination can undershoot the smallest z by a few ulp
-            // (slot 12 = the walk's exit depth, filled by the depth-bucket pass below)
-            dst[3] = make_float4(0.0f, area, hfr_min3(r[2], r[5], r[8]) * 0.99999f, __int_as_float(face));
-            sm.rec[(pos - lbase) * kRecFloats + 16] = ymax;
-          }
+          if (pos >= lbase && pos < lbase + bcnt) sm.fidx[pos - lbase] = cbase + j * kRasterThreads + tid;
           ++pos;
         }
+      }
+      __syncthreads();
+      if (tid < bcnt) {
+        const int face = (int)(f0 + sm.fidx[tid]);
+        const float* __restrict__ v = a.face_verts + (size_t)face * 9;
+        float r[9];
+#pragma unroll
+        for (int e = 0; e < 9; ++e) r[e] = __ldg(v + e);
+        float4* dst = reinterpret_cast<float4*>(sm.rec + tid * kRecFloats);
+        const float xmin = XSUB(hfr_min3(r[0], r[3], r[6]), rblur), xmax = XADD(hfr_max3(r[0], r[3], r[6]), rblur);
+        const float ymin = XSUB(hfr_min3(r[1], r[4], r[7]), rblur), ymax = XADD(hfr_max3(r[1], r[4], r[7]), rblur);
+        const float area = XADD(hfr_edge(r[6], r[7], r[0], r[1], r[3], r[4]), HFR_KEPS);
+        dst[0] = make_float4(r[0], r[1], r[2], r[3]);
+        dst[1] = make_float4(r[4], r[5], r[6], r[7]);
+        dst[2] = make_float4(r[8], xmin, xmax, ymin);
+        // zmin shrunk by 1e-5: the rounded pz of a convex combination can undershoot the smallest z by a few ulp
+        // (slot 12 = the walk's exit depth, filled by the depth-bucket pass below)
+        dst[3] = make_float4(0.0f, area, hfr_min3(r[2], r[5], r[8]) * 0.99999f, __int_as_float(face));
+        sm.rec[tid * kRecFloats + 16] = ymax;
       }
       __syncthreads();
       // depth order: the records are bucketed by their (shrunk) nearest-vertex depth into kDepthBuckets equal
