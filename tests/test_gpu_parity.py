@@ -538,7 +538,7 @@ def test_fused_step_vs_oracle(hf, mano):
     assert (step.p2f == p2f0).all() and (step.zbuf == z0).all()
 
 
-@pytest.mark.parametrize("S,aa,B", [(32, 3, 3), (40, 2, 2)])
+@pytest.mark.parametrize("S,aa,B", [(32, 3, 3), (40, 2, 2), (25, 2, 2)])   # 25*2 = 50: border-clipped tiles, unaligned rows
 def test_fused_ssaa_step_vs_oracle_and_modular(hf, mano, S, aa, B):
     """SURVEY 8(f) row 1 - the reference's own render setting (672^2 -> 3x3 pool, K=1, hard Phong, binarised
     alpha; models_res_nimble.py:74-96, 208-220) as ONE fused pass, at a small size: Fragments bit-exact vs the
