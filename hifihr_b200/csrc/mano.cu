@@ -28,6 +28,16 @@ extern "C" int hfr_device_ok(void) {
   return p.major == 10 ? 1 : 0;
 }
 
+#ifdef HFR_MANO_TIMING   // tuning builds only (tools/mano_phases.py): clock64 of block 0 at the phase boundaries
+__device__ long long g_mano_t[32];
+#define MT(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_mano_t[i] = clock64(); } while (0)
+extern "C" int hfr_debug_mano_times(long long* out, int n) {
+  return cudaMemcpyFromSymbol(out, g_mano_t, sizeof(long long) * (n < 32 ? n : 32)) == cudaSuccess ? 0 : 1;
+}
+#else
+#define MT(i) do { } while (0)
+#endif
+
 namespace {
 
 constexpr int kThreads = 1024;   // one CTA per sample: enough threads to cover every vertex / basis column and to keep
@@ -43,6 +53,8 @@ struct ManoSmem {
   float* A;      // NJ*12
   float* misc;   // kMisc scratch
   int* depth;    // NJ: depth of every joint in the kinematic tree (root = 0)
+  int* parent;   // NJ: parent joint (-1 = root), a shared-memory copy: the chain loops would otherwise pay a
+                 //     global-load round trip per tree level
   float* vp;     // C3 (posed rest verts)
   float* gv;     // C3 (backward only)
 };
@@ -59,6 +71,7 @@ __device__ __forceinline__ ManoSmem carve(float* s, const HfrHandModel& m, bool 
   o.A = s; s += 12 * NJ;
   o.misc = s; s += kMisc;
   o.depth = reinterpret_cast<int*>(s); s += up4(NJ);
+  o.parent = reinterpret_cast<int*>(s); s += up4(NJ);
   o.vp = s; s += m.C3;
   o.gv = bwd ? s : nullptr;
   return o;
@@ -66,7 +79,7 @@ __device__ __forceinline__ ManoSmem carve(float* s, const HfrHandModel& m, bool 
 
 static size_t mano_smem_bytes(const HfrHandModel& m, bool bwd) {
   auto up4 = [](int x) { return (x + 3) & ~3; };
-  size_t f = up4(3 * m.NJ) + up4(9 * m.NJ) + up4(m.NS + 9 * (m.NJ - 1)) + up4(3 * m.NJ) + 24 * m.NJ + kMisc + up4(m.NJ);
+  size_t f = up4(3 * m.NJ) + up4(9 * m.NJ) + up4(m.NS + 9 * (m.NJ - 1)) + up4(3 * m.NJ) + 24 * m.NJ + kMisc + 2 * up4(m.NJ);
   f += (size_t)m.C3 * (bwd ? 2 : 1);
   return f * sizeof(float);
 }
@@ -100,8 +113,10 @@ __device__ void mano_setup(const HfrHandModel& m, const ManoSmem& s, const float
   if (tid >= kThreads - NJ) {   // (the last warp is idle here) depth of each joint in the kinematic tree
     const int j = tid - (kThreads - NJ);
     int d = 0;
-    for (int p = m.parents[j]; p >= 0; p = m.parents[p]) ++d;
+    const int pj = m.parents[j];
+    for (int p = pj; p >= 0; p = m.parents[p]) ++d;
     s.depth[j] = d;
+    s.parent[j] = pj;
   }
   __syncthreads();
   if (tid < NJ) {
@@ -129,7 +144,7 @@ __device__ void mano_setup(const HfrHandModel& m, const ManoSmem& s, const float
     for (int d = 0; d < NJ; ++d) {
       const bool mine = dj == d;
       if (mine) {
-        const int p = m.parents[j];
+        const int p = s.parent[j];
         float val;
         const float* Rj = s.R + 9 * j;
         if (p < 0) {
@@ -181,15 +196,23 @@ __device__ void mano_blend(const HfrHandModel& m, const ManoSmem& s) {
   __syncthreads();
 }
 
+// (all weights, then all joint indices, are requested before the first one is used: two global round trips per
+//  vertex instead of 2 NW dependent ones)
 __device__ __forceinline__ void skin_matrix(const HfrHandModel& m, const float* A, int v, float* T) {
 #pragma unroll
   for (int e = 0; e < 12; ++e) T[e] = 0.0f;
-  for (int i = 0; i < m.NW; ++i) {
-    const float w = m.skin_w[i * m.V + v];
-    if (w != 0.0f) {
-      const float* Aj = A + 12 * m.skin_idx[i * m.V + v];
+  float w[8];
+  int ji[8];
 #pragma unroll
-      for (int e = 0; e < 12; ++e) T[e] += w * Aj[e];
+  for (int i = 0; i < 8; ++i) w[i] = i < m.NW ? __ldg(m.skin_w + i * m.V + v) : 0.0f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) ji[i] = w[i] != 0.0f ? __ldg(m.skin_idx + i * m.V + v) : 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (w[i] != 0.0f) {
+      const float* Aj = A + 12 * ji[i];
+#pragma unroll
+      for (int e = 0; e < 12; ++e) T[e] += w[i] * Aj[e];
     }
   }
 }
@@ -257,9 +280,12 @@ __global__ void __launch_bounds__(kThreads) mano_bwd_kernel(HfrHandModel m, HfrM
   const int NK = m.NS + 9 * (NJ - 1), NPOSE = 3 * (NJ - 1);
   const float* pose = a.pose ? a.pose + (size_t)b * pose_dim : nullptr;
   const int poff = a.pose_off > 0 ? a.pose_off : 3, n_rot = a.rots ? a.n_rot_in : 0;
+  MT(0);
   mano_setup(m, s, pose, a.betas ? a.betas + (size_t)b * m.NS : nullptr,
              a.rots ? a.rots + (size_t)b * a.n_rot_in * 9 : nullptr, n_rot, poff);
+  MT(1);
   mano_blend(m, s);
+  MT(2);
   // backward-only shared arrays live in the tail of the dynamic allocation (after gv)
   float* gA = s.gv + m.C3;        // NJ*12, later reused as gG
   float* gJ = gA + 12 * NJ;       // NJ*3
@@ -294,6 +320,7 @@ __global__ void __launch_bounds__(kThreads) mano_bwd_kernel(HfrHandModel m, HfrM
     red[3 * nwarps + tid] = t;
   }
   __syncthreads();
+  MT(3);
   // gGt: translation-column grads that bypass A (chain joint outputs, centre)
   float* gGt = gfull;  // the gfull region (3*NJ floats) is free until the Rodrigues backward
   for (int i = tid; i < 3 * NJ; i += kThreads) gGt[i] = 0.0f;
@@ -321,6 +348,7 @@ __global__ void __launch_bounds__(kThreads) mano_bwd_kernel(HfrHandModel m, HfrM
     }
   }
   __syncthreads();
+  MT(4);
   // ---- gA[j] = sum_v w_vj * g_v (x) [vp;1]: a thread per vertex keeps its <= NW influences in
   //      registers; per joint the 12 components are summed inside the warp (joints no lane touches are
   //      skipped) and one lane adds them to the shared accumulator
@@ -364,6 +392,7 @@ __global__ void __launch_bounds__(kThreads) mano_bwd_kernel(HfrHandModel m, HfrM
     }
   }
   __syncthreads();
+  MT(5);
   // ---- g_vp = T_rot^T g_v, in place
   for (int v = tid; v < V; v += kThreads) {
     float T[12];
@@ -374,6 +403,7 @@ __global__ void __launch_bounds__(kThreads) mano_bwd_kernel(HfrHandModel m, HfrM
     s.gv[3 * v + 2] = T[2] * g0 + T[6] * g1 + T[10] * g2;
   }
   __syncthreads();
+  MT(6);
   // ---- transposed blend contraction: g_coef[k] = <dirs_k, g_vp>  (warp per coefficient row)
   {
     const int C4 = m.C3 >> 2;
@@ -393,6 +423,7 @@ __global__ void __launch_bounds__(kThreads) mano_bwd_kernel(HfrHandModel m, HfrM
     }
   }
   __syncthreads();
+  MT(7);
   // ---- chain backward, one tree level at a time from the leaves to the root (thread per joint).  A joint's
   //      contribution to its parent goes through a private slot and the parent sums its children in index
   //      order, so the result does not depend on thread timing.
@@ -417,7 +448,7 @@ __global__ void __launch_bounds__(kThreads) mano_bwd_kernel(HfrHandModel m, HfrM
     __syncthreads();
     for (int d = maxd; d >= 1; --d) {
       if (dj == d) {          // children of this level: differentiate G_j = G_p o [R_j | J_j - J_p]
-        const int p = m.parents[j];
+        const int p = s.parent[j];
         const float tl[3] = {s.J[3 * j] - s.J[3 * p], s.J[3 * j + 1] - s.J[3 * p + 1], s.J[3 * j + 2] - s.J[3 * p + 2]};
         float gP[12], gtl[3];
 #pragma unroll
@@ -430,7 +461,7 @@ __global__ void __launch_bounds__(kThreads) mano_bwd_kernel(HfrHandModel m, HfrM
       __syncthreads();
       if (dj == d - 1) {      // their parents gather, children in index order
         for (int ch = 0; ch < NJ; ++ch) {
-          if (m.parents[ch] != j) continue;
+          if (s.parent[ch] != j) continue;
 #pragma unroll
           for (int e = 0; e < 12; ++e) gG[12 * j + e] += contrib[15 * ch + e];
           for (int k = 0; k < 3; ++k) gJ[3 * j + k] -= contrib[15 * ch + 12 + k];
@@ -446,6 +477,7 @@ __global__ void __launch_bounds__(kThreads) mano_bwd_kernel(HfrHandModel m, HfrM
     }
   }
   __syncthreads();
+  MT(8);
   // ---- Rodrigues backward (thread per joint) and shape grads
   if (tid < NJ) {
     float g[9];
@@ -467,6 +499,7 @@ __global__ void __launch_bounds__(kThreads) mano_bwd_kernel(HfrHandModel m, HfrM
     }
   }
   __syncthreads();
+  MT(9);
   if (!a.g_pose || n_rot >= NJ) return;
   float* gp = a.g_pose + (size_t)b * pose_dim;
   if (tid < poff) gp[tid] = (n_rot == 0 && tid < 3) ? gfull[tid] : 0.0f;   // a matrix-driven root gets its gradient via g_rots
@@ -479,6 +512,7 @@ __global__ void __launch_bounds__(kThreads) mano_bwd_kernel(HfrHandModel m, HfrM
   } else {
     for (int o = tid; o < NPOSE; o += kThreads) gp[poff + o] = gfull[3 + o];
   }
+  MT(10);
 }
 
 static int check_model(const HfrHandModel* m) {
