@@ -100,5 +100,17 @@ void emul_tex(const float* tex, int Ht, int Wt, int M, const float* uv, const fl
     for (int q = 0; q < 4; ++q) if (t.idx[q] >= 0) for (int c = 0; c < 3; ++c) gtex[(size_t)t.idx[q]*3+c] += t.w[q]*g[3*i+c];
   }
 }
+// PCA texture model (mean + sum_k params[k] * basis[k]) sampled at the taps: fetch, uv grad, d/d(params)
+void emul_tex_pca(const float* mean, const float* basis, const float* params, int npc, int Ht, int Wt, int M, const float* uv,
+                  const float* g, float* out, float* guv, float* gparams) {
+  HfrTexSrc src;
+  src.tex = mean; src.basis = basis; src.params = params; src.npc = npc; src.map_floats = (size_t)Ht * Wt * 3;
+  for (int i = 0; i < M; ++i) {
+    HfrTexTap t; hfr_tex_tap(Ht, Wt, uv[2*i], uv[2*i+1], &t);
+    hfr_tex_fetch(src, &t, out + 3*i);
+    hfr_tex_uv_grad(src, &t, g + 3*i, guv + 2*i, guv + 2*i + 1);
+    for (int k = 0; k < npc; ++k) gparams[k] += hfr_tex_param_grad(src, &t, g + 3*i, k);
+  }
+}
 }
 #endif

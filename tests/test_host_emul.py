@@ -189,3 +189,26 @@ def test_phong_and_texture_backward_match_autograd():
     assert np.abs(o - f(smp)).max() < 1e-5
     assert np.abs(guv - uv.grad.numpy()).max() < 1e-3 * max(1, uv.grad.abs().max().item())
     assert np.abs(gtex - tex.grad[0].numpy()).max() < 1e-4 * max(1, tex.grad.abs().max().item())
+
+
+def test_pca_texture_math_matches_autograd():
+    """the texture PCA model evaluated at the bilinear taps (shade_math.cuh hfr_texel /
+    hfr_tex_fetch / hfr_tex_uv_grad / hfr_tex_param_grad) against grid_sample on the composed map, fp64 autograd."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(23)
+    M, Ht, Wt, npc = 150, 10, 14, 5
+    mean = torch.rand(Ht, Wt, 3, generator=g, dtype=torch.float64)
+    basis = torch.randn(npc, Ht, Wt, 3, generator=g, dtype=torch.float64) * 0.1
+    params = torch.randn(npc, generator=g, dtype=torch.float64).requires_grad_(True)
+    uv = (torch.rand(M, 2, generator=g, dtype=torch.float64) * 1.2 - 0.1).requires_grad_(True)
+    tex = (mean + torch.einsum("k,khwc->hwc", params, basis))[None]
+    tm = torch.flip(tex.permute(0, 3, 1, 2), [2])
+    smp = F.grid_sample(tm, (uv * 2 - 1).view(1, M, 1, 2), mode="bilinear", align_corners=True, padding_mode="border")[0, :, :, 0].T
+    gs = torch.randn(M, 3, generator=g, dtype=torch.float64)
+    (smp * gs).sum().backward()
+    f = lambda t: np.ascontiguousarray(t.detach().float().numpy())  # noqa: E731
+    o, guv, gp = np.zeros((M, 3), np.float32), np.zeros((M, 2), np.float32), np.zeros(npc, np.float32)
+    lib.emul_tex_pca(ptr(f(mean)), ptr(f(basis)), ptr(f(params)), npc, Ht, Wt, M, ptr(f(uv)), ptr(f(gs)), ptr(o), ptr(guv), ptr(gp))
+    assert np.abs(o - f(smp)).max() < 1e-5
+    assert np.abs(guv - uv.grad.numpy()).max() < 1e-3 * max(1, uv.grad.abs().max().item())
+    assert np.abs(gp - params.grad.numpy()).max() < 1e-4 * max(1, params.grad.abs().max().item())
