@@ -157,7 +157,13 @@ class FusedHandStep:
             self.re_img, self.re_sil, self.mask_rgbs = e(B, 3, S, S), e(B, 1, S, S), e(B, 3, S, S)
         self.dmaps = e(B, 9, S, S)
         self.tile_flags = torch.zeros(B, (S + 3) // 4, (S + 3) // 4, dtype=torch.uint8, device=dev)
-        self.sums = e(L.LOSS_NSUMS + 2 * B)
+        # step outputs (loss partial sums, per-sample pose / shape gradients) live in ONE flat buffer so a single
+        # device->host copy returns them, and in two alternating sets (flip_outputs) so that copy can overlap the
+        # next step on another stream
+        self._n_sums = L.LOSS_NSUMS + 2 * B
+        self._outs = [torch.zeros(self._n_sums + 58 * B, dtype=F32, device=dev) for _ in range(2)]
+        self._out_set = 0
+        self._bind_outputs()
         self.ws = ops.raster_workspace(B * Fm, dev)
         self.mesh_first = (torch.arange(B, device=dev, dtype=I64) * Fm).contiguous()
         self.mesh_nf = torch.full((B,), Fm, device=dev, dtype=I64)
@@ -173,7 +179,7 @@ class FusedHandStep:
         self.g_ndc, self.g_view, self.g_vn = take(B * V * 3, (B, V, 3)), take(B * V * 3, (B, V, 3)), take(B * V * 3, (B, V, 3))
         self.g_texture = take(self.texture.numel(), self.texture.shape)
         self.g_light_dir, self.g_light_color = take(3 * B, (B, 3)), take(3 * B, (B, 3))
-        self.g_verts, self.g_pose, self.g_betas = e(B, V, 3), e(B, 48), e(B, 10)
+        self.g_verts = e(B, V, 3)
         self.gauss = ops.gauss_taps(dev)
         self.params = ops.shade_params(B, Sr, Sr, K, Fm, V, 2 if soft else 0, 1, sigma, gamma, (1.0, 1.0, 1.0),
                                        (0.5, 0.5, 0.5), (0.2, 0.2, 0.2), (1.0, 1.0, 1.0), (0.8, 0.8, 0.8),
@@ -181,6 +187,18 @@ class FusedHandStep:
         # kernels of OURS per step(): mano, geom, [face records], raster setup, raster+shade(+pool), loss | loss', shade'+raster',
         # geom', mano'  (the two torch memsets of the accumulators are not counted)
         self.launches_per_step = 9 + (1 if face_records else 0)
+
+    def _bind_outputs(self):
+        o, B, ns = self._outs[self._out_set], self.B, self._n_sums
+        self.out = o
+        self.sums = o[:ns]
+        self.g_pose = o[ns:ns + 48 * B].view(B, 48)
+        self.g_betas = o[ns + 48 * B:].view(B, 10)
+
+    def flip_outputs(self):
+        """Switch to the other output set: the next step() writes there, the set just produced stays intact."""
+        self._out_set ^= 1
+        self._bind_outputs()
 
     # ---------------------------------------------------------------------------------------
     def forward(self, pose, betas, focal, prp, root_xyz, light_dir, light_color, imgs, seg):
