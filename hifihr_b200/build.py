@@ -17,7 +17,7 @@ LIB = os.path.join(HERE, "libhifihr_b200.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
-    "-O3", "-lineinfo", "-std=c++17",
+    "-O3", "-lineinfo", "-std=c++17", "--threads", "0",
     "--shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off",
     "-Xptxas", "-v",
     "-I", os.path.join(ROOT, "include"), "-I", CSRC,
