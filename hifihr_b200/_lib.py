@@ -39,7 +39,7 @@ class HfrManoBwdArgs(C.Structure):
 class HfrTopology(C.Structure):
     _fields_ = [("V", i32), ("F", i32), ("faces", vp), ("vf_ptr", vp), ("vf_idx", vp),
                 ("NJR", i32), ("NOUT", i32), ("jr_ptr", vp), ("jr_col", vp), ("jr_val", vp),
-                ("vj_ptr", vp), ("vj_row", vp), ("vj_val", vp), ("out_src", vp)]
+                ("vj_ptr", vp), ("vj_row", vp), ("vj_val", vp), ("out_src", vp), ("vf_nbr", vp)]
 
 
 class HfrGeomFwdArgs(C.Structure):

@@ -20,12 +20,26 @@ __device__ __forceinline__ void cross3(const float* u, const float* w, float* o)
   o[2] = u[0] * w[1] - u[1] * w[0];
 }
 
+// corners (a = v, b, c in winding order) of incidence entry e of vertex v: one 8-byte load when the topology carries
+// the neighbour table, else the vf_idx -> faces chain (two dependent round trips)
+__device__ __forceinline__ void incident_face(const HfrTopology& t, int e, int v, int& ia, int& ib, int& ic) {
+  if (t.vf_nbr) {
+    const int2 q = __ldg(reinterpret_cast<const int2*>(t.vf_nbr) + e);
+    ia = v; ib = q.x; ic = q.y;
+  } else {
+    const int code = t.vf_idx[e], f = code >> 2, c = code & 3;
+    ia = t.faces[3 * f + c]; ib = t.faces[3 * f + (c + 1) % 3]; ic = t.faces[3 * f + (c + 2) % 3];
+  }
+}
+
 // raw (un-normalised) vertex normal: sum over incident (face, corner) of the corner cross product
 __device__ __forceinline__ void raw_normal(const HfrTopology& t, const float* sv, int v, float* n) {
   n[0] = n[1] = n[2] = 0.0f;
-  for (int e = t.vf_ptr[v]; e < t.vf_ptr[v + 1]; ++e) {
-    const int code = t.vf_idx[e], f = code >> 2, c = code & 3;
-    const int ia = t.faces[3 * f + c], ib = t.faces[3 * f + (c + 1) % 3], ic = t.faces[3 * f + (c + 2) % 3];
+  const int e0 = __ldg(t.vf_ptr + v), e1 = __ldg(t.vf_ptr + v + 1);
+#pragma unroll 2
+  for (int e = e0; e < e1; ++e) {
+    int ia, ib, ic;
+    incident_face(t, e, v, ia, ib, ic);
     float u[3], w[3], x[3];
     for (int k = 0; k < 3; ++k) { u[k] = sv[3 * ib + k] - sv[3 * ia + k]; w[k] = sv[3 * ic + k] - sv[3 * ia + k]; }
     cross3(u, w, x);
@@ -173,9 +187,11 @@ __global__ void __launch_bounds__(kThreads) geom_bwd_kernel(HfrTopology t, HfrGe
       g[2] += gz - (gx * fx * X + gy * fy * Y) / (Z * Z);
     }
     if (a.g_vnormals) {
-      for (int e = t.vf_ptr[v]; e < t.vf_ptr[v + 1]; ++e) {
-        const int code = t.vf_idx[e], f = code >> 2, c = code & 3;
-        const int ia = t.faces[3 * f + c], ib = t.faces[3 * f + (c + 1) % 3], ic = t.faces[3 * f + (c + 2) % 3];
+      const int e0 = __ldg(t.vf_ptr + v), e1 = __ldg(t.vf_ptr + v + 1);
+#pragma unroll 2
+      for (int e = e0; e < e1; ++e) {
+        int ia, ib, ic;
+        incident_face(t, e, v, ia, ib, ic);
         // corner terms: N_a += (b-a)x(c-a);  N_b += (c-b)x(a-b);  N_c += (a-c)x(b-c)
         float u[3], w[3], x[3];
         const float *ga = s_gN + 3 * ia, *gb = s_gN + 3 * ib, *gc = s_gN + 3 * ic;

@@ -95,15 +95,18 @@ class TopologyConsts:
         vf_ptr = np.zeros(V + 1, np.int64)
         vf_ptr[1:] = np.cumsum([len(x) for x in inc])
         vf_idx = np.asarray([e for x in inc for e in x] or [0], np.int64)
+        vf_nbr = np.stack([faces[vf_idx >> 2, ((vf_idx & 3) + 1) % 3], faces[vf_idx >> 2, ((vf_idx & 3) + 2) % 3]], 1) \
+            if F > 0 else np.zeros((1, 2), np.int64)
         dev = torch.device(device)
         t = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a)).to(dt).to(dev).contiguous()  # noqa: E731
         self.V, self.F = int(V), int(F)
         self.faces = t(faces, I32)
         self.faces_long = t(faces, I64)
-        self.vf_ptr, self.vf_idx = t(vf_ptr, I32), t(vf_idx, I32)
+        self.vf_ptr, self.vf_idx, self.vf_nbr = t(vf_ptr, I32), t(vf_idx, I32), t(vf_nbr, I32)
         s = L.HfrTopology()
         s.V, s.F = self.V, self.F
         s.faces, s.vf_ptr, s.vf_idx = self.faces.data_ptr(), self.vf_ptr.data_ptr(), self.vf_idx.data_ptr()
+        s.vf_nbr = self.vf_nbr.data_ptr()
         self.NJR = self.NOUT = 0
         if J_regressor is not None:
             J = np.asarray(J_regressor, np.float64)

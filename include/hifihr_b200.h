@@ -119,6 +119,9 @@ typedef struct HfrTopology {
   const int32_t* vj_row;      /* (nnz) joint ids                                         */
   const float* vj_val;        /* (nnz)                                                   */
   const int32_t* out_src;     /* (NOUT) >=0: regressed joint id; <0: -(vertex id)-1      */
+  const int32_t* vf_nbr;      /* optional (3F,2): for incidence entry e of vertex a, the other two corners (b, c) of
+                                 that face in winding order - saves the vf_idx -> faces round trip in the normal
+                                 gathers; NULL = derive them from vf_idx / faces                                  */
 } HfrTopology;
 
 typedef struct HfrGeomFwdArgs {
