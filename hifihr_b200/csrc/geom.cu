@@ -228,17 +228,17 @@ __global__ void __launch_bounds__(kThreads) geom_bwd_kernel(HfrTopology t, HfrGe
   if (lane == 0) { s_red[warp * 3] = sx; s_red[warp * 3 + 1] = sy; s_red[warp * 3 + 2] = sz; }
   for (int i = tid; i < 3 * t.NJR; i += kThreads) s_gj[i] = 0.0f;
   __syncthreads();
-  if (tid == 0) {
-    float groot[3] = {0.f, 0.f, 0.f};
-    for (int w = 0; w < kThreads / 32; ++w) { groot[0] -= s_red[w * 3]; groot[1] -= s_red[w * 3 + 1]; groot[2] -= s_red[w * 3 + 2]; }
-    for (int k = 0; k < t.NOUT; ++k) {
-      const int src = t.out_src[k];
-      for (int c = 0; c < 3; ++c) {
-        float g = gj_in ? gj_in[3 * k + c] : 0.0f;
-        if (k == a.root_out) g += groot[c];
-        if (src >= 0) s_gj[3 * src + c] += g; else s_g[3 * (-(src + 1)) + c] += g;
-      }
+  // one thread per (output joint, axis) - the serial version paid NOUT dependent global round trips for out_src;
+  // shared-memory atomics because two outputs may name the same source
+  for (int i = tid; i < t.NOUT * 3; i += kThreads) {
+    const int k = i / 3, c = i - 3 * k, src = __ldg(t.out_src + k);
+    float g = gj_in ? gj_in[i] : 0.0f;
+    if (k == a.root_out) {
+      float groot = 0.f;
+      for (int w = 0; w < kThreads / 32; ++w) groot -= s_red[w * 3 + c];
+      g += groot;
     }
+    if (src >= 0) atomicAdd(&s_gj[3 * src + c], g); else atomicAdd(&s_g[3 * (-(src + 1)) + c], g);
   }
   __syncthreads();
   for (int v = tid; v < V; v += kThreads) {
