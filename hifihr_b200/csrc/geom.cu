@@ -60,9 +60,11 @@ __device__ void geom_stage(const HfrTopology& t, int B, int b, int root_out, con
   if (root_out >= 0) {
     for (int j = warp; j < t.NJR; j += kThreads / 32) {
       float ax = 0.f, ay = 0.f, az = 0.f;
-      for (int e = t.jr_ptr[j] + lane; e < t.jr_ptr[j + 1]; e += 32) {
-        const int v = t.jr_col[e];
-        const float w = t.jr_val[e];
+      const int e1 = __ldg(t.jr_ptr + j + 1);
+#pragma unroll 4
+      for (int e = __ldg(t.jr_ptr + j) + lane; e < e1; e += 32) {   // independent (col, val) loads, 4 rounds in flight
+        const int v = __ldg(t.jr_col + e);
+        const float w = __ldg(t.jr_val + e);
         ax += w * s_v[3 * v]; ay += w * s_v[3 * v + 1]; az += w * s_v[3 * v + 2];
       }
       ax = warp_sum(ax); ay = warp_sum(ay); az = warp_sum(az);
@@ -243,9 +245,11 @@ __global__ void __launch_bounds__(kThreads) geom_bwd_kernel(HfrTopology t, HfrGe
   __syncthreads();
   for (int v = tid; v < V; v += kThreads) {
     float g0 = s_g[3 * v], g1 = s_g[3 * v + 1], g2 = s_g[3 * v + 2];
-    for (int e = t.vj_ptr[v]; e < t.vj_ptr[v + 1]; ++e) {
-      const int j = t.vj_row[e];
-      const float w = t.vj_val[e];
+    const int e1 = __ldg(t.vj_ptr + v + 1);
+#pragma unroll 4
+    for (int e = __ldg(t.vj_ptr + v); e < e1; ++e) {
+      const int j = __ldg(t.vj_row + e);
+      const float w = __ldg(t.vj_val + e);
       g0 += w * s_gj[3 * j]; g1 += w * s_gj[3 * j + 1]; g2 += w * s_gj[3 * j + 2];
     }
     a.g_verts[base + 3 * v] = g0; a.g_verts[base + 3 * v + 1] = g1; a.g_verts[base + 3 * v + 2] = g2;
