@@ -22,7 +22,8 @@ class HfrHandModel(C.Structure):
                 ("center_joint", i32), ("C3", i32),
                 ("dirs", vp), ("v_template", vp), ("J_template", vp), ("J_shapedirs", vp),
                 ("pca_comps", vp), ("pose_mean", vp), ("parents", vp), ("skin_idx", vp), ("skin_w", vp),
-                ("tip_verts", vp), ("joint_order", vp), ("palm_verts", i32 * 2)]
+                ("tip_verts", vp), ("joint_order", vp), ("palm_verts", i32 * 2),
+                ("jv_ptr", vp), ("jv_vert", vp), ("jv_w", vp)]
 
 
 class HfrManoFwdArgs(C.Structure):

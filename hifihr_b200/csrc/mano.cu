@@ -352,6 +352,28 @@ __global__ void __launch_bounds__(kThreads) mano_bwd_kernel(HfrHandModel m, HfrM
   // ---- gA[j] = sum_v w_vj * g_v (x) [vp;1]: a thread per vertex keeps its <= NW influences in
   //      registers; per joint the 12 components are summed inside the warp (joints no lane touches are
   //      skipped) and one lane adds them to the shared accumulator
+  if (m.jv_ptr) {
+    // joint-major: thread = (joint, entry of its 3x4 block, quarter of the joint's weight list); the four quarters are
+    // neighbouring lanes and meet in two shuffles - no atomics, no per-joint warp reductions
+    const int total = NJ * 48;
+    for (int base = warp * 32; base < total; base += kThreads) {
+      const int idx = base + lane;
+      float acc = 0.0f;
+      if (idx < total) {
+        const int q = idx & 3, e = (idx >> 2) % 12, j = idx / 48, r = e >> 2, c = e & 3;
+        const int p1 = __ldg(m.jv_ptr + j + 1);
+#pragma unroll 4
+        for (int p = __ldg(m.jv_ptr + j) + q; p < p1; p += 4) {
+          const int v = __ldg(m.jv_vert + p);
+          const float w = __ldg(m.jv_w + p);
+          acc += w * s.gv[3 * v + r] * (c < 3 ? s.vp[3 * v + c] : 1.0f);
+        }
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      if (idx < total && (idx & 3) == 0) gA[12 * (idx / 48) + (idx >> 2) % 12] = acc;
+    }
+  } else
   for (int v0 = warp * 32; v0 < V; v0 += kThreads) {
     const int v = v0 + lane;
     int ji[8];

@@ -65,6 +65,15 @@ class HandModelConsts:
         self.parents = t(np.asarray(parents, np.int64), I32)
         self.skin_idx = t(skin_idx, I32)
         self.skin_w = t(skin_w)
+        # joint-major view of the same non-zero weights (CSR over joints) for the backward's gA reduction
+        jv_ptr, jv_vert, jv_w = [0], [], []
+        for j in range(NJ):
+            for i in range(nw):
+                sel = np.nonzero((skin_idx[i] == j) & (skin_w[i] != 0))[0]
+                jv_vert += sel.tolist()
+                jv_w += skin_w[i, sel].tolist()
+            jv_ptr.append(len(jv_vert))
+        self.jv_ptr, self.jv_vert, self.jv_w = t(jv_ptr, I32), t(jv_vert or [0], I32), t(np.asarray(jv_w or [0.0], np.float32))
         self.tip_verts = t(np.asarray(list(tip_verts) or [0], np.int64), I32)
         self.joint_order = t(np.asarray(joint_order, np.int64), I32)
         self.pose_dim = 3 + (self.NPC if self.NPC > 0 else 3 * (NJ - 1))
@@ -78,6 +87,7 @@ class HandModelConsts:
         s.parents, s.skin_idx, s.skin_w = self.parents.data_ptr(), self.skin_idx.data_ptr(), self.skin_w.data_ptr()
         s.tip_verts, s.joint_order = self.tip_verts.data_ptr(), self.joint_order.data_ptr()
         s.palm_verts = (C.c_int32 * 2)(int(palm_verts[0]), int(palm_verts[1]))
+        s.jv_ptr, s.jv_vert, s.jv_w = self.jv_ptr.data_ptr(), self.jv_vert.data_ptr(), self.jv_w.data_ptr()
         self.struct = s
         self.device = dev
 

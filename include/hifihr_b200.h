@@ -57,6 +57,11 @@ typedef struct HfrHandModel {
   const int32_t* joint_order; /* (NJ+NT) output joint k = chain∪tips[joint_order[k]]     */
   int32_t palm_verts[2];   /* root_palm mode (my_mano.py:459-461): the two vertices whose midpoint replaces
                               chain joint 0 in the joint output (MANO: 95, 22)            */
+  /* optional joint-major view of the skinning weights (CSR over joints) for the backward's
+   * d/d(joint transform) reduction; NULL = reduce vertex-major with warp sums */
+  const int32_t* jv_ptr;   /* (NJ+1)                                                       */
+  const int32_t* jv_vert;  /* (nnz) vertex of each non-zero weight                         */
+  const float* jv_w;       /* (nnz)                                                        */
 } HfrHandModel;
 
 /* Replaces ManoLayer.forward (utils/my_mano.py:315-483) / MyMANOLayer.forward (:39-54).
