@@ -464,6 +464,14 @@ __device__ __forceinline__ bool fill_empty_tile(const HfrRasterArgs& a, int n, i
   float* const p2 = a.dists + pix * K;
   float* const p3 = a.bary + pix * K * 3;
   const float m1 = -1.0f, mi = __int_as_float(-1);
+  if (K == 1) {
+    // 28 units per row, fixed roles: lanes 0-7 the ids, 8-11 z, 12-15 dists, then lanes 0-11 the barycentrics
+    float* const d1 = t16 < 8 ? p0 + 4 * t16 : (t16 < 12 ? p1 + 4 * (t16 - 8) : p2 + 4 * (t16 - 12));
+    const float v1 = t16 < 8 ? mi : m1;
+    st_cs_f4(d1, v1, v1, v1, v1);
+    if (t16 < 12) st_cs_f4(p3 + 4 * t16, m1, m1, m1, m1);
+    return true;
+  }
   for (int u = t16; u < per_row; u += 16) {
     float* dst = u < 8 * K ? p0 + 4 * u : (u < 12 * K ? p1 + 4 * (u - 8 * K) : (u < 16 * K ? p2 + 4 * (u - 12 * K) : p3 + 4 * (u - 16 * K)));
     const float v = u < 8 * K ? mi : m1;   // two int64 -1 per 128 bits of pix_to_face
