@@ -236,8 +236,8 @@ __global__ void __launch_bounds__(kRasterThreads, (KMAX <= 4 ? HFR_RASTER_MINB :
       if (HFR_FAST_FILL_POOL && tile_outside_mesh(mesh_box, n, c.tx, c.ty) && fill_empty_tile(r, n, c.tx, c.ty)) {
         // no face touches this tile: rows of -1 Fragments, and the window's share of it is plain background
         if (s.image) *reinterpret_cast<float4*>(s.image + (((size_t)n * r.H + c.yi) * r.W + c.xi) * 4) = make_float4(bg0, bg1, bg2, 0.0f);
-        for (int y = ya; y < yb; ++y)
-          for (int x = xa; x < xb; ++x) { acc.x += bg0; acc.y += bg1; acc.z += bg2; }
+        const float cntw = (float)(max(xb - xa, 0) * max(yb - ya, 0));   // window pixels in this tile, all background
+        acc.x += cntw * bg0; acc.y += cntw * bg1; acc.z += cntw * bg2;
         continue;
       }
       c.warp_active = tx0 + (warp & 1) * 8 < r.W && ty0 + (warp >> 1) * 4 < r.H;
