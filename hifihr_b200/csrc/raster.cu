@@ -78,8 +78,8 @@ __global__ void __launch_bounds__(kRasterThreads) raster_fwd_kernel(HfrRasterArg
                                                                     const uint32_t* __restrict__ mesh_box) {
   __shared__ RasterSmem sm;
   PixelCtx c = make_pixel_ctx(a.H, a.W);
-  // K = 1: a tile no face touches streams its -1 Fragments as whole rows (measured win at 672^2, see shade.cu)
-  if (KMAX == 1 && tile_outside_mesh(mesh_box, c.n, c.tx, c.ty) && fill_empty_tile(a, c.n, c.tx, c.ty)) return;
+  // K = 1 / 4: a tile no face touches streams its -1 Fragments as whole rows (fixed-role fills, see shade.cu)
+  if ((a.K == 1 || a.K == 4) && tile_outside_mesh(mesh_box, c.n, c.tx, c.ty) && fill_empty_tile(a, c.n, c.tx, c.ty)) return;
   TopK<KMAX> top;
   uint32_t perm;
   raster_tile<KMAX, false>(a, ranges, mesh_box, sm, c, top, nullptr, perm);

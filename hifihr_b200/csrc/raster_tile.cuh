@@ -472,6 +472,17 @@ __device__ __forceinline__ bool fill_empty_tile(const HfrRasterArgs& a, int n, i
     if (t16 < 12) st_cs_f4(p3 + 4 * t16, m1, m1, m1, m1);
     return true;
   }
+  if (K == 4) {
+    // 112 units per row and every group of 16 lanes stays inside one tensor: 2 x ids, z, dists, 3 x barycentrics
+    st_cs_f4(p0 + 4 * t16, mi, mi, mi, mi);
+    st_cs_f4(p0 + 4 * (t16 + 16), mi, mi, mi, mi);
+    st_cs_f4(p1 + 4 * t16, m1, m1, m1, m1);
+    st_cs_f4(p2 + 4 * t16, m1, m1, m1, m1);
+    st_cs_f4(p3 + 4 * t16, m1, m1, m1, m1);
+    st_cs_f4(p3 + 4 * (t16 + 16), m1, m1, m1, m1);
+    st_cs_f4(p3 + 4 * (t16 + 32), m1, m1, m1, m1);
+    return true;
+  }
   for (int u = t16; u < per_row; u += 16) {
     float* dst = u < 8 * K ? p0 + 4 * u : (u < 12 * K ? p1 + 4 * (u - 8 * K) : (u < 16 * K ? p2 + 4 * (u - 12 * K) : p3 + 4 * (u - 16 * K)));
     const float v = u < 8 * K ? mi : m1;   // two int64 -1 per 128 bits of pix_to_face

@@ -163,13 +163,14 @@ __device__ __forceinline__ void raster_shade_epilogue(const HfrRasterArgs& r, co
 #endif
 // Tiles outside the mesh can stream their -1 Fragments as whole rows (fill_empty_tile).  Measured on B200: with
 // the generic unit loop (any K) neutral to slightly slower in the one-tile-per-CTA kernel (473 -> 480 us at 672^2
-// K=1) - off; with the fixed-role K=1 path a clear win there (472 -> 426 us) and inside the SSAA-fused kernel, where
-// it also skips the tile's shared-memory round trip and two barriers (663 -> 524 us) - on.
+// K=1) - off; with the fixed-role K=1 / K=4 paths (HFR_FAST_FILL_K1) a win there (K=1 672^2: 472 -> 426 us, C2 K=4:
+// 332 -> 320 us) and inside the SSAA-fused kernel, where it also skips the tile's shared-memory round trip and two
+// barriers (663 -> 524 us) - on.
 #ifndef HFR_FAST_FILL
 #define HFR_FAST_FILL 0
 #endif
 #ifndef HFR_FAST_FILL_K1
-#define HFR_FAST_FILL_K1 1   // K = 1: fixed-role row fill, measured 472 -> 433 us at 672^2 B=48
+#define HFR_FAST_FILL_K1 1   // K = 1 and K = 4: fixed-role row fills
 #endif
 #ifndef HFR_FAST_FILL_POOL
 #define HFR_FAST_FILL_POOL 1
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(kRasterThreads, (KMAX <= 4 ? HFR_RASTER_MINB :
   constexpr bool PAY = KMAX <= HFR_PAY_MAXK;   // 16 B x K x 256 threads of payload cache next to the 30 KB tile state
   __shared__ float4 s_pay[PAY ? KMAX * kRasterThreads : 1];
   PixelCtx c = make_pixel_ctx(r.H, r.W);
-  if ((HFR_FAST_FILL || (HFR_FAST_FILL_K1 && r.K == 1)) && tile_outside_mesh(mesh_box, c.n, c.tx, c.ty) && fill_empty_tile(r, c.n, c.tx, c.ty)) {
+  if ((HFR_FAST_FILL || (HFR_FAST_FILL_K1 && (r.K == 1 || r.K == 4))) && tile_outside_mesh(mesh_box, c.n, c.tx, c.ty) && fill_empty_tile(r, c.n, c.tx, c.ty)) {
     // no face touches this tile: Fragments are streamed out as whole rows, the pixel is the background
     const bool ones = s.p.blend == HFR_BLEND_SIGMOID_ALPHA;
     const size_t pix = ((size_t)c.n * r.H + c.yi) * r.W + c.xi;
