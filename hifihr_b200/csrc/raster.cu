@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(kRasterThreads) raster_fwd_kernel(HfrRasterArg
   __shared__ RasterSmem sm;
   PixelCtx c = make_pixel_ctx(a.H, a.W);
   // K = 1 / 4: a tile no face touches streams its -1 Fragments as whole rows (fixed-role fills, see shade.cu)
-  if ((a.K == 1 || a.K == 4) && tile_outside_mesh(mesh_box, c.n, c.tx, c.ty) && fill_empty_tile(a, c.n, c.tx, c.ty)) return;
+  if ((a.K == 1 || (a.K & 3) == 0) && tile_outside_mesh(mesh_box, c.n, c.tx, c.ty) && fill_empty_tile(a, c.n, c.tx, c.ty)) return;
   TopK<KMAX> top;
   uint32_t perm;
   raster_tile<KMAX, false>(a, ranges, mesh_box, sm, c, top, nullptr, perm);

@@ -472,15 +472,15 @@ __device__ __forceinline__ bool fill_empty_tile(const HfrRasterArgs& a, int n, i
     if (t16 < 12) st_cs_f4(p3 + 4 * t16, m1, m1, m1, m1);
     return true;
   }
-  if (K == 4) {
-    // 112 units per row and every group of 16 lanes stays inside one tensor: 2 x ids, z, dists, 3 x barycentrics
-    st_cs_f4(p0 + 4 * t16, mi, mi, mi, mi);
-    st_cs_f4(p0 + 4 * (t16 + 16), mi, mi, mi, mi);
-    st_cs_f4(p1 + 4 * t16, m1, m1, m1, m1);
-    st_cs_f4(p2 + 4 * t16, m1, m1, m1, m1);
-    st_cs_f4(p3 + 4 * t16, m1, m1, m1, m1);
-    st_cs_f4(p3 + 4 * (t16 + 16), m1, m1, m1, m1);
-    st_cs_f4(p3 + 4 * (t16 + 32), m1, m1, m1, m1);
+  if ((K & 3) == 0) {
+    // K = 4, 8, 16: every group of 16 lanes stays inside one tensor (K/2 rounds of ids, K/4 of z, K/4 of dists,
+    // 3K/4 of barycentrics per row) - no per-unit address selection
+    for (int i = 0; i < K / 2; ++i) st_cs_f4(p0 + 4 * (t16 + 16 * i), mi, mi, mi, mi);
+    for (int i = 0; i < K / 4; ++i) {
+      st_cs_f4(p1 + 4 * (t16 + 16 * i), m1, m1, m1, m1);
+      st_cs_f4(p2 + 4 * (t16 + 16 * i), m1, m1, m1, m1);
+    }
+    for (int i = 0; i < 3 * K / 4; ++i) st_cs_f4(p3 + 4 * (t16 + 16 * i), m1, m1, m1, m1);
     return true;
   }
   for (int u = t16; u < per_row; u += 16) {

@@ -170,7 +170,7 @@ __device__ __forceinline__ void raster_shade_epilogue(const HfrRasterArgs& r, co
 #define HFR_FAST_FILL 0
 #endif
 #ifndef HFR_FAST_FILL_K1
-#define HFR_FAST_FILL_K1 1   // K = 1 and K = 4: fixed-role row fills
+#define HFR_FAST_FILL_K1 1   // K = 1 and K = 4, 8, 16: fixed-role row fills
 #endif
 #ifndef HFR_FAST_FILL_POOL
 #define HFR_FAST_FILL_POOL 1
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(kRasterThreads, (KMAX <= 4 ? HFR_RASTER_MINB :
   constexpr bool PAY = KMAX <= HFR_PAY_MAXK;   // 16 B x K x 256 threads of payload cache next to the 30 KB tile state
   __shared__ float4 s_pay[PAY ? KMAX * kRasterThreads : 1];
   PixelCtx c = make_pixel_ctx(r.H, r.W);
-  if ((HFR_FAST_FILL || (HFR_FAST_FILL_K1 && (r.K == 1 || r.K == 4))) && tile_outside_mesh(mesh_box, c.n, c.tx, c.ty) && fill_empty_tile(r, c.n, c.tx, c.ty)) {
+  if ((HFR_FAST_FILL || (HFR_FAST_FILL_K1 && (r.K == 1 || (r.K & 3) == 0))) && tile_outside_mesh(mesh_box, c.n, c.tx, c.ty) && fill_empty_tile(r, c.n, c.tx, c.ty)) {
     // no face touches this tile: Fragments are streamed out as whole rows, the pixel is the background
     const bool ones = s.p.blend == HFR_BLEND_SIGMOID_ALPHA;
     const size_t pix = ((size_t)c.n * r.H + c.yi) * r.W + c.xi;
