@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import threading
 
 import torch
 
@@ -73,7 +74,7 @@ class HfrShadeParams(C.Structure):
                 ("shade", i32), ("sigma", f32), ("gamma", f32), ("znear", f32), ("zfar", f32),
                 ("background", f32 * 3), ("light_ambient", f32 * 3), ("light_specular", f32 * 3),
                 ("mat_ambient", f32 * 3), ("mat_diffuse", f32 * 3), ("mat_specular", f32 * 3),
-                ("shininess", f32), ("tex_n", i32), ("tex_h", i32), ("tex_w", i32), ("VT", i32), ("tex_pca", i32)]
+                ("shininess", f32), ("tex_n", i32), ("tex_h", i32), ("tex_w", i32), ("VT", i32), ("tex_pca", i32), ("light_point", i32)]
 
 
 class HfrShadeFwdArgs(C.Structure):
@@ -120,25 +121,28 @@ class HfrLossArgs(C.Structure):
 
 
 class HfrLossBwdArgs(C.Structure):
-    _fields_ = [("f", HfrLossArgs), ("w", vp), ("gauss", vp), ("count_global", i64), ("n_global", i32), ("g_re_img", vp), ("g_re_sil", vp)]
+    _fields_ = [("f", HfrLossArgs), ("w", vp), ("gauss", vp), ("count_global", i64), ("n_global", i32), ("g_re_img", vp), ("g_re_sil", vp),
+                ("tex_con", vp), ("self_norm", vp)]
 
 
 class HfrKeypointArgs(C.Structure):
     _fields_ = [("B", i32), ("NJ", i32), ("V", i32), ("F", i32), ("l2", i32), ("NB", i32), ("scale_a", i32), ("scale_b", i32),
                 ("scale_len", f32), ("joints", vp), ("root_xyz", vp), ("Kmat", vp), ("verts", vp), ("faces", vp),
                 ("joints_gt", vp), ("j2d_gt", vp), ("verts_gt", vp), ("conf", vp), ("bone_parent", vp), ("bone_child", vp),
-                ("j2d", vp), ("sums", vp)]
+                ("j2d", vp), ("sums", vp), ("nbr_ptr", vp), ("nbr_idx", vp)]
 
 
 class HfrKeypointBwdArgs(C.Structure):
     _fields_ = [("f", HfrKeypointArgs), ("w", vp), ("n_global", i32), ("g_j2d_in", vp), ("g_joints", vp), ("g_verts", vp)]
 
 
+ABI_VERSION = 4
 LOSS_NSUMS = 8
 FACE_ATTR_FLOATS = 28
 LOSS_L2 = 5
+LOSS_SSIM = 4
 KP_NSUMS = 8
-KP_TERMS = ("joint_2d", "joint_3d", "vert_3d", "bone_direc", "bone_direc_3d", "edge_length", "mscale")
+KP_TERMS = ("joint_2d", "joint_3d", "vert_3d", "bone_direc", "bone_direc_3d", "edge_length", "mscale", "triangle")
 ENTRY_POINTS = [
     "hfr_last_error", "hfr_abi_version", "hfr_device_ok", "hfr_mano_forward", "hfr_mano_backward",
     "hfr_geom_forward", "hfr_geom_backward", "hfr_raster_workspace_bytes", "hfr_raster_forward",
@@ -167,17 +171,45 @@ def lib() -> C.CDLL:
         _lib.hfr_raster_workspace_bytes.argtypes = [C.c_int64]
         _lib.hfr_raster_tile_box.restype = C.c_void_p
         _lib.hfr_raster_tile_box.argtypes = [C.c_void_p, C.c_int64, C.c_int32]
-        if _lib.hfr_abi_version() != 3:
+        if _lib.hfr_abi_version() != ABI_VERSION:
             raise HfrError("libhifihr_b200.so ABI version mismatch")
     return _lib
 
 
-def call(name: str, *structs):
-    """Invoke an entry point on the current torch CUDA stream; map error codes to exceptions
-    (HFR_EINVAL -> ValueError as PyTorch3D does for bad settings, others -> RuntimeError)."""
+_tls = threading.local()
+
+
+def _pending_devices():
+    if not hasattr(_tls, "devs"):
+        _tls.devs = set()
+    return _tls.devs
+
+
+def call(name: str, *structs, device=None):
+    """Invoke an entry point on the current torch CUDA stream OF THE DEVICE THAT OWNS THE TENSORS (the reference's
+    nn.DataParallel calls forward from one thread per device, train_hrnet.py:560; the launchers themselves never call
+    cudaSetDevice).  The device is `device` when given, else the one every tensor unpacked by ptr() since the last
+    call lives on (mixing devices raises), else the current device.  Error codes map to exceptions: HFR_EINVAL ->
+    ValueError as PyTorch3D raises for bad settings, others -> RuntimeError."""
     L = lib()
-    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-    rc = getattr(L, name)(*[C.byref(s) for s in structs], stream)
+    devs = _pending_devices()
+    if device is not None:
+        dev = torch.device(device).index
+        dev = torch.cuda.current_device() if dev is None else dev
+    elif len(devs) > 1:
+        found = sorted(devs)
+        devs.clear()
+        raise HfrError(f"{name}: tensors live on different CUDA devices {found}")
+    else:
+        dev = next(iter(devs)) if devs else torch.cuda.current_device()
+    devs.clear()
+    if dev == torch.cuda.current_device():
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        rc = getattr(L, name)(*[C.byref(s) for s in structs], stream)
+    else:
+        with torch.cuda.device(dev):
+            stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            rc = getattr(L, name)(*[C.byref(s) for s in structs], stream)
     if rc != 0:
         msg = L.hfr_last_error().decode()
         if rc == 1:
@@ -195,6 +227,7 @@ def ptr(t: torch.Tensor | None, dtype=None, name="tensor"):
         raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
     if not t.is_contiguous():
         raise ValueError(f"{name} must be contiguous")
+    _pending_devices().add(t.device.index)
     return t.data_ptr()
 
 

@@ -7,6 +7,8 @@
 //   bone_direc(_3d) = mean conf * |unit(bone) - unit(bone_gt)|^2 losses.py:268-282, utils/losses_util.py:217-282
 //   edge_length = mean | |edge| - |edge_gt| | over 3 edges/face  losses.py:285-289, utils/losses_util.py:284-301
 //   mscale     = mean | |j_a - j_b| - 0.0282 |                   losses.py:293-299
+//   triangle   = uniform Laplacian smoothing, mean_n mean_v |mean_{j in N(v)} x_j - x_v|   losses.py:422-429,
+//                utils/losses_util.py:340-364 (pytorch3d mesh_laplacian_smoothing(method="uniform"))
 //
 // The reference runs ~60 tiny ATen kernels for these (two bmm against constant 0/+-1 matrices, boolean-mask gathers,
 // six fancy-index gathers over the faces).  Here: one CTA per sample, joints / gradients staged in shared memory,
@@ -54,6 +56,19 @@ __device__ __forceinline__ BoneTerm bone_term(const float* jc, const float* jp, 
     for (int c = 0; c < D; ++c) o.gv[c] = gu[c] * s - k * v[c];
   }
   return o;
+}
+
+// row v of the uniform Laplacian applied to the vertices: mean of the neighbours minus the vertex (the diagonal is -1
+// for every vertex, an isolated vertex keeps -x_v as upstream does)
+__device__ __forceinline__ void lap_row(const HfrKeypointArgs& a, const float* __restrict__ pv, int v, float* L) {
+  const int p0 = __ldg(a.nbr_ptr + v), p1 = __ldg(a.nbr_ptr + v + 1);
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+  for (int p = p0; p < p1; ++p) {
+    const int j = __ldg(a.nbr_idx + p);
+    s0 += __ldg(pv + 3 * j); s1 += __ldg(pv + 3 * j + 1); s2 += __ldg(pv + 3 * j + 2);
+  }
+  const float id = p1 > p0 ? 1.0f / (float)(p1 - p0) : 0.0f;
+  L[0] = s0 * id - __ldg(pv + 3 * v); L[1] = s1 * id - __ldg(pv + 3 * v + 1); L[2] = s2 * id - __ldg(pv + 3 * v + 2);
 }
 
 __device__ __forceinline__ float base_val(float d, int l2) { return l2 ? d * d : fabsf(d); }
@@ -134,6 +149,14 @@ __global__ void __launch_bounds__(kThreads) keypoint_fwd_kernel(HfrKeypointArgs 
     float d2 = 0.f;
     for (int c = 0; c < 3; ++c) { const float x = s_j[3 * a.scale_a + c] - s_j[3 * a.scale_b + c]; d2 += x * x; }
     acc[HFR_KP_MSCALE] += fabsf(sqrtf(d2) - a.scale_len);
+  }
+  if (a.verts && a.nbr_ptr) {
+    const float* pv = a.verts + (size_t)b * a.V * 3;
+    for (int v = tid; v < a.V; v += kThreads) {
+      float L[3];
+      lap_row(a, pv, v, L);
+      acc[HFR_KP_LAP] += sqrtf(L[0] * L[0] + L[1] * L[1] + L[2] * L[2]);
+    }
   }
 #pragma unroll
   for (int i = 0; i < HFR_KP_NSUMS; ++i) {
@@ -242,6 +265,33 @@ __global__ void __launch_bounds__(kThreads) keypoint_bwd_kernel(HfrKeypointBwdAr
     }
   }
   __syncthreads();
+  const float wl = q.w[HFR_KP_LAP] / (ng * a.V);
+  if (a.verts && a.nbr_ptr && wl != 0.f) {
+    // d|L_v| / dx: u_v = L_v / |L_v| reaches x_v with -1 and every neighbour j with 1 / deg(v).  The unit vectors go
+    // to a second shared array first, then every vertex GATHERS over its (symmetric) neighbourhood - no atomics.
+    float* s_u = s_gv + a.V * 3;
+    const float* xv = a.verts + (size_t)b * a.V * 3;
+    for (int v = tid; v < a.V; v += kThreads) {
+      float L[3];
+      lap_row(a, xv, v, L);
+      const float nrm = sqrtf(L[0] * L[0] + L[1] * L[1] + L[2] * L[2]);
+      const float deg = (float)(__ldg(a.nbr_ptr + v + 1) - __ldg(a.nbr_ptr + v));
+      const float k = nrm > 0.f ? wl / nrm : 0.f;
+      s_gv[3 * v] -= k * L[0]; s_gv[3 * v + 1] -= k * L[1]; s_gv[3 * v + 2] -= k * L[2];
+      const float kd = deg > 0.f ? k / deg : 0.f;
+      s_u[3 * v] = kd * L[0]; s_u[3 * v + 1] = kd * L[1]; s_u[3 * v + 2] = kd * L[2];
+    }
+    __syncthreads();
+    for (int i = tid; i < a.V; i += kThreads) {
+      float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+      for (int p = __ldg(a.nbr_ptr + i); p < __ldg(a.nbr_ptr + i + 1); ++p) {
+        const int v = __ldg(a.nbr_idx + p);
+        g0 += s_u[3 * v]; g1 += s_u[3 * v + 1]; g2 += s_u[3 * v + 2];
+      }
+      s_gv[3 * i] += g0; s_gv[3 * i + 1] += g1; s_gv[3 * i + 2] += g2;
+    }
+    __syncthreads();
+  }
   for (int i = tid; i < a.V * 3; i += kThreads) q.g_verts[(size_t)b * a.V * 3 + i] = s_gv[i];
 }
 
@@ -251,6 +301,7 @@ int check_kp(const HfrKeypointArgs* a, const char* who) {
   HFR_CHECK_ARG(a->joints && a->NJ > 0 && a->NJ <= kMaxJ, "%s: joints missing or NJ out of range (<= %d)", who, kMaxJ);
   HFR_CHECK_ARG(a->NB == 0 || (a->bone_parent && a->bone_child), "%s: bone tables missing", who);
   HFR_CHECK_ARG(!(a->verts && a->verts_gt) || (a->faces && a->F > 0 && a->V > 0), "%s: verts need faces", who);
+  HFR_CHECK_ARG(!a->nbr_ptr || (a->nbr_idx && a->verts && a->V > 0), "%s: the Laplacian term needs verts and the neighbour lists", who);
   HFR_CHECK_ARG(a->scale_a < a->NJ && a->scale_b < a->NJ && (a->scale_a < 0 || a->scale_b >= 0), "%s: bad mscale joints", who);
   return HFR_OK;
 }
@@ -270,7 +321,7 @@ extern "C" int hfr_keypoint_backward(const HfrKeypointBwdArgs* q, void* stream) 
   if (int rc = check_kp(&q->f, "keypoint_backward")) return rc;
   if (q->f.B == 0) return HFR_OK;
   HFR_CHECK_ARG(q->w && q->g_joints && q->n_global > 0, "keypoint_backward: w / g_joints / n_global missing");
-  const size_t smem = q->g_verts ? (size_t)q->f.V * 3 * sizeof(float) : 0;
+  const size_t smem = q->g_verts ? (size_t)q->f.V * 3 * sizeof(float) * (q->f.nbr_ptr ? 2 : 1) : 0;
   HFR_CHECK_ARG(smem <= 200 * 1024, "keypoint_backward: mesh too large for shared memory");
   if (smem > 40 * 1024) cudaFuncSetAttribute(keypoint_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   keypoint_bwd_kernel<<<q->f.B, kThreads, smem, (cudaStream_t)stream>>>(*q);

@@ -123,8 +123,12 @@ constexpr size_t kLossFwdSmem = (size_t)(6 * kLH * kXP + 5 * kLH * kHP) * sizeof
 // METRIC = the evaluation-time texture metrics (train_hrnet.py:149-161, compute_texture_metric.py:49-60): both
 // images are multiplied by the SAME mask (mask_mode 1: segms_gt, 2: re_sil > 0 as for HO3D) and the sum of squared
 // differences (-> L2 / PSNR) is accumulated next to L1 and SSIM.  The training variant compiles without it.
-template <bool METRIC>
+// MODE 2 = the self-supervised photometric terms (losses.py:317-340): x = re_img as rendered (NOT multiplied by the
+// silhouette), y = maskRGBs given as `imgs` (models_res_nimble.py:220), and the L1 / mean-RGB sums are kept PER SAMPLE
+// (sums[NSUMS + n], [NSUMS + N + n], [NSUMS + 2N + n]) because the reference weights them by texture_con[n]^2.
+template <int MODE>
 __global__ void __launch_bounds__(kLossThreads, 3) loss_fwd_kernel(HfrLossArgs a) {
+  constexpr bool METRIC = MODE == 1, SELF = MODE == 2;
   extern __shared__ __align__(16) float lsm[];
   float (*xs3)[kLH][kXP] = reinterpret_cast<float (*)[kLH][kXP]>(lsm);                       // [3]
   float (*ys3)[kLH][kXP] = reinterpret_cast<float (*)[kLH][kXP]>(lsm + 3 * kLH * kXP);         // [3]
@@ -169,12 +173,12 @@ __global__ void __launch_bounds__(kLossThreads, 3) loss_fwd_kernel(HfrLossArgs a
         if (a.nhwc) {
           q[u] = __ldg(reinterpret_cast<const float4*>(a.re_img + ((size_t)n * hw + p) * 4));
         } else {
-          q[u].w = __ldg(a.re_sil + (size_t)n * hw + p);
+          q[u].w = SELF ? 1.0f : __ldg(a.re_sil + (size_t)n * hw + p);
           q[u].x = __ldg(a.re_img + ((size_t)n * 3 + 0) * hw + p);
           q[u].y = __ldg(a.re_img + ((size_t)n * 3 + 1) * hw + p);
           q[u].z = __ldg(a.re_img + ((size_t)n * 3 + 2) * hw + p);
         }
-        sg[u] = ld_seg(a, n, p, hw);
+        sg[u] = SELF ? 1.0f : ld_seg(a, n, p, hw);
 #pragma unroll
         for (int c = 0; c < 3; ++c) im[u][c] = ld_target(a, lut, n, c, p, hw);
       }
@@ -188,7 +192,7 @@ __global__ void __launch_bounds__(kLossThreads, 3) loss_fwd_kernel(HfrLossArgs a
       if (ok[u]) {
         const float rgb[3] = {q[u].x, q[u].y, q[u].z}, sil = q[u].w, seg = sg[u];
         const float mm = a.mask_mode == 2 ? (sil > 0.0f ? 1.0f : 0.0f) : seg;   // METRIC: one mask for both images
-        const float s = METRIC ? mm : sil * inv_scale, sy = METRIC ? mm : seg;
+        const float s = SELF ? 1.0f : (METRIC ? mm : sil * inv_scale), sy = SELF ? 1.0f : (METRIC ? mm : seg);
         const bool interior = hx >= kR && hx < kR + kLT && hy >= kR && hy < kR + kLT;
         bool nz_in = false;
 #pragma unroll
@@ -203,7 +207,7 @@ __global__ void __launch_bounds__(kLossThreads, 3) loss_fwd_kernel(HfrLossArgs a
           }
         }
         if (nz_in) sub_nz[((hy - kR) >> 2) * 8 + ((hx - kR) >> 2)] = 1;   // benign race: every writer stores 1
-        if (interior) { sl += fabsf(sil - seg); mul += sil * seg; add += sil + seg; }
+        if (interior && !SELF) { sl += fabsf(sil - seg); mul += sil * seg; add += sil + seg; }
       }
 #pragma unroll
       for (int c = 0; c < 3; ++c) { xs3[c][hy][hx] = vx[c]; ys3[c][hy][hx] = vy[c]; }
@@ -328,8 +332,9 @@ __global__ void __launch_bounds__(kLossThreads, 3) loss_fwd_kernel(HfrLossArgs a
     float t = 0.f;
 #pragma unroll
     for (int w = 0; w < kLossThreads / 32; ++w) t += red[w][tid];
-    const int dst = tid < 5 ? tid : (tid == 5 ? HFR_LOSS_NSUMS + n : (tid == 6 ? HFR_LOSS_NSUMS + a.N + n : HFR_LOSS_L2));
-    if (t != 0.0f) atomicAdd(a.sums + dst, t);
+    int dst = tid < 5 ? tid : (tid == 5 ? HFR_LOSS_NSUMS + n : (tid == 6 ? HFR_LOSS_NSUMS + a.N + n : HFR_LOSS_L2));
+    if (SELF) dst = tid == 0 ? HFR_LOSS_NSUMS + n : (tid == 1 ? HFR_LOSS_NSUMS + a.N + n : (tid == 2 ? HFR_LOSS_NSUMS + 2 * a.N + n : (tid == 4 ? HFR_LOSS_SSIM : -1)));
+    if (t != 0.0f && dst >= 0) atomicAdd(a.sums + dst, t);
   }
 }
 
@@ -339,6 +344,8 @@ __global__ void __launch_bounds__(kLossThreads, 3) loss_fwd_kernel(HfrLossArgs a
 #ifndef HFR_LOSSB_MINB
 #define HFR_LOSSB_MINB 3
 #endif
+// SELF = backward of the self-supervised terms (losses.py:317-340; forward MODE 2): gradients reach re_img only.
+template <bool SELF>
 __global__ void __launch_bounds__(kLossThreads, HFR_LOSSB_MINB) loss_bwd_kernel(HfrLossBwdArgs b) {
   const HfrLossArgs& a = b.f;
   __shared__ __align__(16) float sd[3][kLH][kXP];
@@ -367,8 +374,17 @@ __global__ void __launch_bounds__(kLossThreads, HFR_LOSSB_MINB) loss_bwd_kernel(
   const float w_tex = __ldg(b.w), w_mrgb = __ldg(b.w + 1), w_ssim = __ldg(b.w + 2), w_sil = __ldg(b.w + 3), w_iou = __ldg(b.w + 4);
   const float cnt = (float)b.count_global, icnt = 1.0f / cnt;
   const float mR = a.sums[HFR_LOSS_SUM_R] * icnt, mT = a.sums[HFR_LOSS_SUM_T] * icnt;
-  const float k_mrgb = w_mrgb * 2.0f * (mT - mR) * (-icnt);
-  const float inv_scale = 1.0f / a.sil_scale;
+  float k_mrgb = w_mrgb * 2.0f * (mT - mR) * (-icnt);
+  float k_l1 = w_tex * icnt;
+  if (SELF) {
+    // texture_self = sum_n c_n^2 sum|x - y| / (3HW sum_n c_n^2); mrgb_self = sum_n c_n^2 |mean_n x - mean_n y| / sum_n c_n^2
+    const float per = 1.0f / (3.0f * (float)hw);
+    const float c = __ldg(b.tex_con + n), c2 = c * c / __ldg(b.self_norm);
+    const float dm = (a.sums[HFR_LOSS_NSUMS + a.N + n] - a.sums[HFR_LOSS_NSUMS + 2 * a.N + n]) * per;
+    k_l1 = w_tex * c2 * per;
+    k_mrgb = w_mrgb * c2 * per * (dm > 0.f ? 1.f : (dm < 0.f ? -1.f : 0.f));
+  }
+  const float inv_scale = SELF ? 1.0f : 1.0f / a.sil_scale;
   // this thread's 4 pixels: column x0+lane, rows y0 + warp*4 + o.  Everything the pointwise part needs (rendered
   // RGBA, mask, target) is requested up front for all channels, so the round trips overlap each other and, on
   // tiles with a live SSIM stencil, the halo loads and the stencil itself.
@@ -393,11 +409,12 @@ __global__ void __launch_bounds__(kLossThreads, HFR_LOSSB_MINB) loss_bwd_kernel(
         const float4 q = __ldg(reinterpret_cast<const float4*>(a.re_img + ((size_t)n * hw + p) * 4));
         rimg[o][0] = q.x; rimg[o][1] = q.y; rimg[o][2] = q.z; sil[o] = q.w;
       } else {
-        sil[o] = __ldg(a.re_sil + (size_t)n * hw + p);
+        if (!SELF) sil[o] = __ldg(a.re_sil + (size_t)n * hw + p);
 #pragma unroll
         for (int c = 0; c < 3; ++c) rimg[o][c] = __ldg(a.re_img + ((size_t)n * 3 + c) * hw + p);
       }
-      seg[o] = ld_seg(a, n, p, hw);
+      seg[o] = SELF ? 1.0f : ld_seg(a, n, p, hw);
+      if (SELF) sil[o] = 1.0f;
 #pragma unroll
       for (int c = 0; c < 3; ++c) timg[o][c] = ld_target(a, lut, n, c, p, hw);
     }
@@ -408,7 +425,7 @@ __global__ void __launch_bounds__(kLossThreads, HFR_LOSSB_MINB) loss_bwd_kernel(
 #pragma unroll
   for (int o = 0; o < 4; ++o) {
     gsil[o] = 0.f;
-    if (in[o]) {
+    if (in[o] && !SELF) {
       const float d = sil[o] - seg[o];
       gsil[o] = w_sil * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) / ((float)b.n_global * (float)hw);
       gsil[o] += w_iou * (-1.0f / (float)b.n_global) * (seg[o] * den - mulv * (1.0f - seg[o])) / (den * den);
@@ -512,10 +529,10 @@ __global__ void __launch_bounds__(kLossThreads, HFR_LOSSB_MINB) loss_bwd_kernel(
       const float xv = rim * so, yv = seg[o] * tim;
       const float gS = r[o][0] + 2.0f * xv * r[o][1] + yv * r[o][2];
       const float d = xv - yv;
-      const float grim = w_tex * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) * icnt + k_mrgb + w_ssim * (-icnt) * gS;
+      const float grim = k_l1 * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) + k_mrgb + w_ssim * (-icnt) * gS;
       const float gc = in[o] ? grim * so : 0.f;
       if (c == 0) grgb[o][0] = gc; else if (c == 1) grgb[o][1] = gc; else grgb[o][2] = gc;
-      if (in[o]) gsil[o] += grim * rim * inv_scale;
+      if (in[o] && !SELF) gsil[o] += grim * rim * inv_scale;
     }
   }
 #pragma unroll
@@ -527,7 +544,7 @@ __global__ void __launch_bounds__(kLossThreads, HFR_LOSSB_MINB) loss_bwd_kernel(
       } else {
 #pragma unroll
         for (int c = 0; c < 3; ++c) b.g_re_img[((size_t)n * 3 + c) * hw + p] = grgb[o][c];
-        b.g_re_sil[n * hw + p] = gsil[o];
+        if (!SELF) b.g_re_sil[n * hw + p] = gsil[o];
       }
     }
   }
@@ -561,19 +578,21 @@ extern "C" int hfr_loss_forward(const HfrLossArgs* a, void* stream) {
   using namespace hfr;
   HFR_CHECK_ARG(a && a->N >= 0 && a->H > 0 && a->W > 0 && a->sil_scale > 0.f, "loss_forward: bad dims");
   if (a->N == 0) return HFR_OK;
-  HFR_CHECK_ARG(a->re_img && (a->nhwc || a->re_sil) && (a->imgs || a->imgs_u8) && (a->seg || a->seg_u8) && a->sums, "loss_forward: null pointer");
+  HFR_CHECK_ARG(a->re_img && (a->nhwc || a->re_sil || a->mask_mode == 3) && (a->imgs || a->imgs_u8) && (a->seg || a->seg_u8 || a->mask_mode == 3) && a->sums, "loss_forward: null pointer");
   HFR_CHECK_ARG(!a->want_ssim || a->gauss, "loss_forward: SSIM needs the Gaussian taps");
   dim3 grid((a->W + kLT - 1) / kLT, (a->H + kLT - 1) / kLT, a->N);
-  HFR_CHECK_ARG(a->mask_mode >= 0 && a->mask_mode <= 2, "loss_forward: mask_mode must be 0, 1 or 2");
-  HFR_CHECK_ARG(a->mask_mode == 0 || !(a->want_grad && a->dmaps), "loss_forward: the metric modes have no backward");
+  HFR_CHECK_ARG(a->mask_mode >= 0 && a->mask_mode <= 3, "loss_forward: mask_mode must be 0..3");
+  HFR_CHECK_ARG(a->mask_mode == 0 || a->mask_mode == 3 || !(a->want_grad && a->dmaps), "loss_forward: the metric modes have no backward");
   static bool attr_set = false;   // benign race: the attribute is idempotent
   if (!attr_set) {
-    cudaFuncSetAttribute(loss_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLossFwdSmem);
-    cudaFuncSetAttribute(loss_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLossFwdSmem);
+    cudaFuncSetAttribute(loss_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLossFwdSmem);
+    cudaFuncSetAttribute(loss_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLossFwdSmem);
+    cudaFuncSetAttribute(loss_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLossFwdSmem);
     attr_set = true;
   }
-  if (a->mask_mode == 0) loss_fwd_kernel<false><<<grid, kLossThreads, kLossFwdSmem, (cudaStream_t)stream>>>(*a);
-  else loss_fwd_kernel<true><<<grid, kLossThreads, kLossFwdSmem, (cudaStream_t)stream>>>(*a);
+  if (a->mask_mode == 0) loss_fwd_kernel<0><<<grid, kLossThreads, kLossFwdSmem, (cudaStream_t)stream>>>(*a);
+  else if (a->mask_mode == 3) loss_fwd_kernel<2><<<grid, kLossThreads, kLossFwdSmem, (cudaStream_t)stream>>>(*a);
+  else loss_fwd_kernel<1><<<grid, kLossThreads, kLossFwdSmem, (cudaStream_t)stream>>>(*a);
   HFR_CHECK_LAUNCH("loss_forward");
   return HFR_OK;
 }
@@ -582,12 +601,17 @@ extern "C" int hfr_loss_backward(const HfrLossBwdArgs* a, void* stream) {
   using namespace hfr;
   HFR_CHECK_ARG(a && a->f.N >= 0 && a->f.H > 0 && a->f.W > 0, "loss_backward: bad dims");
   if (a->f.N == 0) return HFR_OK;
-  HFR_CHECK_ARG(a->f.re_img && (a->f.nhwc || (a->f.re_sil && a->g_re_sil)) && (a->f.imgs || a->f.imgs_u8) && (a->f.seg || a->f.seg_u8) && a->f.sums && a->w && a->g_re_img,
+  const bool self = a->f.mask_mode == 3;
+  HFR_CHECK_ARG(a->f.mask_mode == 0 || self, "loss_backward: mask_mode must be 0 (training terms) or 3 (self-supervised terms)");
+  HFR_CHECK_ARG(a->f.re_img && (a->f.nhwc || self || (a->f.re_sil && a->g_re_sil)) && (a->f.imgs || a->f.imgs_u8) && (self || a->f.seg || a->f.seg_u8) && a->f.sums && a->w && a->g_re_img,
                 "loss_backward: null pointer");
+  HFR_CHECK_ARG(!self || (a->tex_con && a->self_norm && !a->f.nhwc), "loss_backward: the self-supervised terms need tex_con, self_norm and NCHW images");
+  HFR_CHECK_ARG(!(a->f.want_ssim && !a->f.dmaps), "loss_backward: want_ssim is set but the forward wrote no derivative maps (dmaps)");
   HFR_CHECK_ARG(!(a->f.want_ssim && a->f.dmaps) || a->gauss, "loss_backward: SSIM needs the Gaussian taps");
   HFR_CHECK_ARG(a->count_global > 0 && a->n_global > 0, "loss_backward: bad global counts");
   dim3 grid((a->f.W + kLT - 1) / kLT, (a->f.H + kLT - 1) / kLT, a->f.N);
-  loss_bwd_kernel<<<grid, kLossThreads, 0, (cudaStream_t)stream>>>(*a);
+  if (self) loss_bwd_kernel<true><<<grid, kLossThreads, 0, (cudaStream_t)stream>>>(*a);
+  else loss_bwd_kernel<false><<<grid, kLossThreads, 0, (cudaStream_t)stream>>>(*a);
   HFR_CHECK_LAUNCH("loss_backward");
   return HFR_OK;
 }

@@ -264,7 +264,15 @@ __global__ void __launch_bounds__(kBwdThreads, (KMAX == 1 ? HFR_BWD_MINB_K1 : (K
         }
         if (k < kshade) {
           float gP[3], gNn[3], gtex[3];
-          hfr_phong_bwd(P, dhat, lcol, texel, &ctx, gcol, gP, gNn, gtex, acc_dhat, acc_lcol);
+          if (P.light_point) {   // the direction depends on the fragment's position: location - P
+            float gdh[3] = {0.f, 0.f, 0.f}, gd[3];
+            hfr_phong_bwd(P, ctx.lhat, lcol, texel, &ctx, gcol, gP, gNn, gtex, gdh, acc_lcol);
+            hfr_normalize_eps_bwd(ctx.lhat, ctx.llen, gdh, gd);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { acc_dhat[c] += gd[c]; gP[c] -= gd[c]; }
+          } else {
+            hfr_phong_bwd(P, dhat, lcol, texel, &ctx, gcol, gP, gNn, gtex, acc_dhat, acc_lcol);
+          }
           float gu = 0.f, gv = 0.f;
           const HfrTexSrc tsrc = tex_source<PCA>(f, n);
           hfr_tex_uv_grad(tsrc, &tap, gtex, &gu, &gv);
@@ -365,8 +373,8 @@ __global__ void __launch_bounds__(kBwdThreads, (KMAX == 1 ? HFR_BWD_MINB_K1 : (K
     // one set of atomics per warp, no CTA barrier: warps of a partially covered tile finish independently
     if (lane == 0 && warp_any) {
       const float t[6] = {acc_dhat[0], acc_dhat[1], acc_dhat[2], acc_lcol[0], acc_lcol[1], acc_lcol[2]};
-      float gd[3];
-      hfr_normalize_eps_bwd(dhat, dlen, t, gd);   // linear in t, so per-warp application sums to the same gradient
+      float gd[3] = {t[0], t[1], t[2]};
+      if (!P.light_point) hfr_normalize_eps_bwd(dhat, dlen, t, gd);   // linear in t, so per-warp application sums to the same gradient
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         if (a.g_light_dir && gd[c] != 0.f) atomicAdd(a.g_light_dir + 3 * n + c, gd[c]);
@@ -384,8 +392,8 @@ __global__ void __launch_bounds__(kBwdThreads, (KMAX == 1 ? HFR_BWD_MINB_K1 : (K
       for (int w = 0; w < kBwdThreads / 32; ++w)
 #pragma unroll
         for (int c = 0; c < 6; ++c) t[c] += s_light[w][c];
-      float gd[3];
-      hfr_normalize_eps_bwd(dhat, dlen, t, gd);
+      float gd[3] = {t[0], t[1], t[2]};
+      if (!P.light_point) hfr_normalize_eps_bwd(dhat, dlen, t, gd);   // PointLights: t already is d/d(location)
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         if (a.g_light_dir && gd[c] != 0.f) atomicAdd(a.g_light_dir + 3 * n + c, gd[c]);

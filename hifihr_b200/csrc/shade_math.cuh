@@ -135,6 +135,7 @@ HFR_HD void hfr_normalize_eps_bwd(const float* o, float len, const float* g, flo
 
 struct HfrPhongCtx {   // forward intermediates kept for the backward
   float nh[3], nlen, view[3], vlen, refl[3], cosang, vr, alpha, spec;
+  float lhat[3], llen;   // unit light direction of THIS fragment (PointLights: normalize(location - P)) and |location - P|
 };
 
 // P: interpolated view-space position, Nn: interpolated (un-normalised) normal, dhat: unit light

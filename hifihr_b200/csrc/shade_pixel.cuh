@@ -50,8 +50,11 @@ HFR_HD void interp3(const float* bc, const float* A, float* o) {
   for (int c = 0; c < 3; ++c) o[c] = bc[0] * A[c] + bc[1] * A[3 + c] + bc[2] * A[6 + c];
 }
 
+// DirectionalLights: the sample's unit light direction.  PointLights (models_res_nimble.py:191-198, taken when
+// ifLight=False): the raw light LOCATION - the direction is per fragment, location - P (shade_fragment).
 HFR_HD void light_dir_hat(const HfrShadeFwdArgs& a, int n, float* dhat, float* len) {
   const float d[3] = {a.light_dir[3 * n], a.light_dir[3 * n + 1], a.light_dir[3 * n + 2]};
+  if (a.p.light_point) { dhat[0] = d[0]; dhat[1] = d[1]; dhat[2] = d[2]; *len = 1.0f; return; }
   hfr_normalize_eps(d, dhat, len);
 }
 
@@ -83,7 +86,13 @@ HFR_HD void shade_fragment(const HfrShadeFwdArgs& a, int n, const FragGeom& g, c
   const float v = bc[0] * g.uv[1] + bc[1] * g.uv[3] + bc[2] * g.uv[5];
   hfr_tex_tap(a.p.tex_h, a.p.tex_w, u, v, tap);
   hfr_tex_fetch(tex_source<PCA>(a, n), tap, texel);
-  hfr_phong_fwd(a.p, P, Nn, dhat, lcol, texel, color, ctx);
+  if (a.p.light_point) {   // PointLights.diffuse / .specular: direction = location - points, normalised per fragment
+    const float d[3] = {dhat[0] - P[0], dhat[1] - P[1], dhat[2] - P[2]};
+    hfr_normalize_eps(d, ctx->lhat, &ctx->llen);
+  } else {
+    ctx->lhat[0] = dhat[0]; ctx->lhat[1] = dhat[1]; ctx->lhat[2] = dhat[2]; ctx->llen = 0.0f;
+  }
+  hfr_phong_fwd(a.p, P, Nn, ctx->lhat, lcol, texel, color, ctx);
 }
 
 // Full forward for one pixel given its K fragments.

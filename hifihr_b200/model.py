@@ -18,7 +18,7 @@ from . import _lib as L
 from . import ops
 from .mano import MyMANOLayer, xyz_from_vertice
 from .renderer import (BlendParams, DirectionalLights, HardPhongShader, Materials, MeshRasterizer, MeshRenderer,
-                       PerspectiveCameras, RasterizationSettings, SoftPhongShader, TexturesUV)
+                       PerspectiveCameras, PointLights, RasterizationSettings, SoftPhongShader, TexturesUV)
 
 F32, I32, I64 = torch.float32, torch.int32, torch.int64
 
@@ -44,8 +44,9 @@ class HandRenderModel(nn.Module):
 
     def __init__(self, ifRender=True, device="cuda", hand_model="mano", root_id=9, image_size=224, aa_factor=3,
                  blur_radius=0.0, faces_per_pixel=1, soft=False, binarize=True, texture_size=512, mano_root=None,
-                 blend_params=None):
+                 blend_params=None, ifLight=True):
         super().__init__()
+        self.ifLight = ifLight      # models_res_nimble.py:187-198: False renders with a default PointLights
         if hand_model != "mano":
             raise NotImplementedError("use hifihr_b200.nimble.MyNIMBLELayer for the NIMBLE-shaped stand-in")
         self.root_id = root_id
@@ -85,8 +86,11 @@ class HandRenderModel(nn.Module):
         if self.ifRender:
             fcl, prp = get_ndc_fx_fy_cx_cy(Ks)
             cameras = PerspectiveCameras(focal_length=-fcl, principal_point=prp, device=dev)
-            lighting = DirectionalLights(diffuse_color=light_params["colors"], direction=light_params["directions"],
-                                         device=dev)
+            if self.ifLight:
+                lighting = DirectionalLights(diffuse_color=light_params["colors"], direction=light_params["directions"],
+                                             device=dev)
+            else:
+                lighting = PointLights(device=dev)
             meshes = outputs["skin_meshes"]
             pred_root = (verts - verts_rel)[:, :1]            # = joints[:, root_id] before the shift
             verts_num = verts.shape[1]                        # = meshes._num_verts_per_mesh[0], without a host sync

@@ -113,6 +113,14 @@ class TopologyConsts:
         self.faces = t(faces, I32)
         self.faces_long = t(faces, I64)
         self.vf_ptr, self.vf_idx, self.vf_nbr = t(vf_ptr, I32), t(vf_idx, I32), t(vf_nbr, I32)
+        # vertex neighbourhoods over the unique edges (uniform Laplacian, pytorch3d Meshes.laplacian_packed)
+        e = np.concatenate([faces[:, [0, 1]], faces[:, [1, 2]], faces[:, [2, 0]]], 0) if F > 0 else np.zeros((0, 2), np.int64)
+        e = np.unique(np.sort(e, 1), axis=0)
+        both = np.concatenate([e, e[:, ::-1]], 0)
+        both = both[np.lexsort((both[:, 1], both[:, 0]))]
+        nbr_ptr = np.zeros(V + 1, np.int64)
+        np.add.at(nbr_ptr, both[:, 0] + 1, 1)
+        self.nbr_ptr, self.nbr_idx = t(np.cumsum(nbr_ptr), I32), t(both[:, 1] if len(both) else np.zeros(1, np.int64), I32)
         s = L.HfrTopology()
         s.V, s.F = self.V, self.F
         s.faces, s.vf_ptr, s.vf_idx = self.faces.data_ptr(), self.vf_ptr.data_ptr(), self.vf_idx.data_ptr()
@@ -203,7 +211,7 @@ def raster_tile_box(ws, Ftot, N):
 
 def shade_params(N, H, W, K, F, V, blend, shade, sigma, gamma, background, light_ambient, light_specular,
                  mat_ambient, mat_diffuse, mat_specular, shininess, tex_shape=(1, 1, 1), VT=0, znear=1.0, zfar=100.0,
-                 tex_pca=0):
+                 tex_pca=0, light_point=0):
     p = L.HfrShadeParams()
     p.N, p.H, p.W, p.K, p.F, p.V, p.blend, p.shade = N, H, W, K, F, V, blend, shade
     p.sigma, p.gamma, p.znear, p.zfar = float(sigma), float(gamma), float(znear), float(zfar)
@@ -213,6 +221,7 @@ def shade_params(N, H, W, K, F, V, blend, shade, sigma, gamma, background, light
     p.shininess = float(shininess)
     p.tex_n, p.tex_h, p.tex_w, p.VT = int(tex_shape[0]), int(tex_shape[1]), int(tex_shape[2]), int(VT)
     p.tex_pca = int(tex_pca)
+    p.light_point = int(light_point)
     return p
 
 
@@ -311,8 +320,9 @@ class GeomFunction(torch.autograd.Function):
         verts, root_xyz, focal, prp = ctx.saved_tensors
         fix = lambda g, ok=True: None if (g is None or not ok or g.numel() == 0) else _cu(g)  # noqa: E731
         g_verts = torch.empty_like(verts)
-        geom_backward_raw(ctx.topo, verts, ctx.root_out, root_xyz, focal, prp, fix(g_joints, ctx.root_out >= 0),
-                          fix(g_rel), fix(g_view), fix(g_ndc, focal is not None), fix(g_vn), g_verts)
+        gs = (fix(g_joints, ctx.root_out >= 0), fix(g_rel), fix(g_view), fix(g_ndc, focal is not None), fix(g_vn))
+        geom_backward_raw(ctx.topo, verts, ctx.root_out, root_xyz, focal, prp, *gs, g_verts)
+        del gs                                                   # (kept alive until the launch was enqueued)
         return None, g_verts, None, None, None, None, None
 
 
@@ -345,10 +355,11 @@ class RasterizeFunction(torch.autograd.Function):
         H, W, K, blur, pc, clip = ctx.cfg
         g_fv = torch.zeros_like(face_verts)
         fix = lambda g: None if g is None else _cu(g)  # noqa: E731
+        gz, gb, gd = fix(g_zbuf), fix(g_bary), fix(g_dists)      # kept alive until the launch is enqueued
         a = L.HfrRasterBwdArgs(p2f.shape[0], H, W, K, face_verts.shape[0], L.ptr(face_verts, F32), L.ptr(p2f, I64),
-                               L.ptr(fix(g_zbuf), F32), L.ptr(fix(g_bary), F32), L.ptr(fix(g_dists), F32), blur, pc, clip,
-                               L.ptr(g_fv, F32))
+                               L.ptr(gz, F32), L.ptr(gb, F32), L.ptr(gd, F32), blur, pc, clip, L.ptr(g_fv, F32))
         L.call("hfr_raster_backward", a)
+        del gz, gb, gd
         return g_fv, None, None, None, None, None, None, None, None
 
 
@@ -422,8 +433,10 @@ class PoolFunction(torch.autograd.Function):
         ref = g_img if g_img is not None else g_sil
         g_image = torch.empty(N, H * aa, W * aa, 4, dtype=F32, device=ref.device)
         fix = lambda g: None if g is None else _cu(g)  # noqa: E731
-        a = L.HfrPoolBwdArgs(N, H, W, aa, binarize, L.ptr(fix(g_img), F32), L.ptr(fix(g_sil), F32), L.ptr(g_image, F32))
+        gi, gs = fix(g_img), fix(g_sil)                          # kept alive until the launch is enqueued
+        a = L.HfrPoolBwdArgs(N, H, W, aa, binarize, L.ptr(gi, F32), L.ptr(gs, F32), L.ptr(g_image, F32))
         L.call("hfr_pool_backward", a)
+        del gi, gs
         return g_image, None, None, None
 
 
@@ -433,11 +446,13 @@ class RenderLossFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, re_img, re_sil, imgs, seg, sil_scale, want_ssim):
+        # grad mode is off inside Function.forward and _cu() may copy (non-contiguous / non-fp32 input), so whether a
+        # gradient will be asked for is read from autograd's own bookkeeping, not from the (possibly copied) tensors
+        need_grad = bool(ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
         re_img, re_sil, imgs, seg = _cu(re_img), _cu(re_sil), _cu(imgs), _cu(seg)
         N, _, H, W = re_img.shape
         dev = re_img.device
         sums = torch.zeros(L.LOSS_NSUMS + 2 * N, dtype=F32, device=dev)
-        need_grad = re_img.requires_grad or re_sil.requires_grad
         dmaps = torch.empty(N, 9, H, W, dtype=F32, device=dev) if (want_ssim and need_grad) else None
         gauss = gauss_taps(dev)
         flags = torch.zeros(N, (H + 3) // 4, (W + 3) // 4, dtype=torch.uint8, device=dev)
@@ -461,6 +476,9 @@ class RenderLossFunction(torch.autograd.Function):
         re_img, re_sil, imgs, seg, sums, dmaps, flags = ctx.saved_tensors
         N, H, W, sil_scale, want_ssim = ctx.cfg
         dmaps = dmaps if dmaps.numel() else None
+        if want_ssim and dmaps is None:
+            raise L.HfrError("RenderLossFunction.backward: the forward kept no SSIM derivative maps (it saw no input that "
+                             "required grad); the ssim_tex gradient would be dropped")
         gauss = gauss_taps(re_img.device)
         f = L.HfrLossArgs(N, H, W, sil_scale, want_ssim, 1, 0, L.ptr(re_img, F32), L.ptr(re_sil, F32), L.ptr(imgs, F32),
                           L.ptr(seg, F32), L.ptr(sums, F32), L.ptr(gauss, F32), L.ptr(dmaps, F32), L.ptr(flags))
@@ -469,6 +487,52 @@ class RenderLossFunction(torch.autograd.Function):
         a = L.HfrLossBwdArgs(f, L.ptr(w, F32), L.ptr(gauss, F32), N * 3 * H * W, N, L.ptr(g_img, F32), L.ptr(g_sil, F32))
         L.call("hfr_loss_backward", a)
         return g_img, g_sil, None, None, None, None
+
+
+class SelfRenderLossFunction(torch.autograd.Function):
+    """The self-supervised photometric terms of losses.py:317-340 (unweighted) from one pass: returns (3,)
+    [texture_self, mrgb_self, ssim_tex_self] for re_img (N,3,H,W) against maskRGBs (N,3,H,W) with the per-sample
+    confidences texture_con (N,).  Gradients reach re_img only (maskRGBs is images * (re_sil > 0), models_res_nimble.py:220)."""
+
+    @staticmethod
+    def forward(ctx, re_img, mask_rgbs, texture_con):
+        need_grad = bool(ctx.needs_input_grad[0])
+        re_img, mask_rgbs, con = _cu(re_img), _cu(mask_rgbs), _cu(texture_con.reshape(-1))
+        N, _, H, W = re_img.shape
+        dev = re_img.device
+        sums = torch.zeros(L.LOSS_NSUMS + 3 * N, dtype=F32, device=dev)
+        dmaps = torch.empty(N, 9, H, W, dtype=F32, device=dev) if need_grad else None
+        gauss = gauss_taps(dev)
+        a = L.HfrLossArgs(N, H, W, 1.0, 1, int(need_grad), 0, L.ptr(re_img, F32), None, L.ptr(mask_rgbs, F32), None,
+                          L.ptr(sums, F32), L.ptr(gauss, F32), L.ptr(dmaps, F32), None, 3)
+        L.call("hfr_loss_forward", a)
+        per = float(3 * H * W)
+        c2 = con * con
+        norm = c2.sum().reshape(1)
+        ns = L.LOSS_NSUMS
+        tex = (sums[ns:ns + N] * c2).sum() / (per * norm[0])
+        mrgb = ((sums[ns + N:ns + 2 * N] / per - sums[ns + 2 * N:ns + 3 * N] / per).abs() * c2).sum() / norm[0]
+        ssim = 1 - sums[L.LOSS_SSIM] / (N * per)
+        ctx.cfg = (N, H, W)
+        ctx.save_for_backward(re_img, mask_rgbs, con, norm, sums, dmaps if dmaps is not None else sums.new_zeros(0))
+        return torch.stack([tex, mrgb, ssim])
+
+    @staticmethod
+    def backward(ctx, g):
+        re_img, mask_rgbs, con, norm, sums, dmaps = ctx.saved_tensors
+        N, H, W = ctx.cfg
+        if not dmaps.numel():
+            raise L.HfrError("SelfRenderLossFunction.backward: the forward kept no SSIM derivative maps")
+        gauss = gauss_taps(re_img.device)
+        f = L.HfrLossArgs(N, H, W, 1.0, 1, 1, 0, L.ptr(re_img, F32), None, L.ptr(mask_rgbs, F32), None, L.ptr(sums, F32),
+                          L.ptr(gauss, F32), L.ptr(dmaps, F32), None, 3)
+        g_img = torch.empty_like(re_img)
+        w = torch.zeros(5, dtype=F32, device=re_img.device)
+        w[:3] = g
+        a = L.HfrLossBwdArgs(f, L.ptr(w, F32), L.ptr(gauss, F32), N * 3 * H * W, N, L.ptr(g_img, F32), None,
+                             L.ptr(con, F32), L.ptr(norm, F32))
+        L.call("hfr_loss_backward", a)
+        return g_img, None, None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -486,7 +550,8 @@ def bone_tables(device):
     return _BONES[key]
 
 
-def keypoint_args(joints, root_xyz, Ks, verts, faces, joints_gt, j2d_gt, verts_gt, conf, l2, j2d, sums, mscale=True):
+def keypoint_args(joints, root_xyz, Ks, verts, faces, joints_gt, j2d_gt, verts_gt, conf, l2, j2d, sums, mscale=True,
+                  nbr=None):
     B, NJ = joints.shape[0], joints.shape[1]
     bp, bc = bone_tables(joints.device)
     nb = bp.shape[0] if NJ == 21 else 0          # the bone tables are the 21-joint FreiHAND skeleton's
@@ -496,15 +561,17 @@ def keypoint_args(joints, root_xyz, Ks, verts, faces, joints_gt, j2d_gt, verts_g
                              L.ptr(joints, F32, "joints"), L.ptr(root_xyz, F32, "root_xyz"), L.ptr(Ks, F32, "Ks"),
                              L.ptr(verts, F32, "verts"), L.ptr(faces, I32, "faces"), L.ptr(joints_gt, F32, "joints_gt"),
                              L.ptr(j2d_gt, F32, "j2d_gt"), L.ptr(verts_gt, F32, "verts_gt"), L.ptr(conf, F32, "conf"),
-                             L.ptr(bp, I32), L.ptr(bc, I32), L.ptr(j2d, F32), L.ptr(sums, F32))
+                             L.ptr(bp, I32), L.ptr(bc, I32), L.ptr(j2d, F32), L.ptr(sums, F32),
+                             L.ptr(nbr[0], I32) if nbr is not None else None, L.ptr(nbr[1], I32) if nbr is not None else None)
 
 
 class KeypointLossFunction(torch.autograd.Function):
-    """(joints, verts) -> (terms (7,) [joint_2d, joint_3d, vert_3d, bone_direc, bone_direc_3d, edge_length, mscale]
-    unweighted, j2d (B,NJ,2)).  A term whose ground truth is None is 0; j2d is empty when Ks is None."""
+    """(joints, verts) -> (terms (8,) [joint_2d, joint_3d, vert_3d, bone_direc, bone_direc_3d, edge_length, mscale,
+    triangle] unweighted, j2d (B,NJ,2)).  A term whose ground truth is None is 0; j2d is empty when Ks is None;
+    `nbr` = (nbr_ptr, nbr_idx) of TopologyConsts switches the uniform Laplacian term on."""
 
     @staticmethod
-    def forward(ctx, joints, verts, root_xyz, Ks, joints_gt, j2d_gt, verts_gt, conf, faces, l2):
+    def forward(ctx, joints, verts, root_xyz, Ks, joints_gt, j2d_gt, verts_gt, conf, faces, l2, nbr=None):
         c = lambda t: None if t is None else _cu(t)  # noqa: E731
         joints, verts, joints_gt, j2d_gt, verts_gt = c(joints), c(verts), c(joints_gt), c(j2d_gt), c(verts_gt)
         B, NJ = joints.shape[0], joints.shape[1]
@@ -515,14 +582,15 @@ class KeypointLossFunction(torch.autograd.Function):
         faces = None if faces is None else faces.to(I32).contiguous()
         j2d = torch.empty(B, NJ, 2, dtype=F32, device=dev) if Ks is not None else None
         sums = torch.zeros(L.KP_NSUMS, dtype=F32, device=dev)
-        a = keypoint_args(joints, root_xyz, Ks, verts, faces, joints_gt, j2d_gt, verts_gt, conf, l2, j2d, sums)
+        a = keypoint_args(joints, root_xyz, Ks, verts, faces, joints_gt, j2d_gt, verts_gt, conf, l2, j2d, sums, nbr=nbr)
         L.call("hfr_keypoint_forward", a)
         V, F, NB = a.V, a.F, a.NB
-        cnt = torch.tensor([B * NJ * 2, B * NJ * 3, max(B * V * 3, 1), max(B * NB, 1), max(B * NB, 1), max(B * F * 3, 1), B],
-                           dtype=F32, device=dev)
+        cnt = torch.tensor([B * NJ * 2, B * NJ * 3, max(B * V * 3, 1), max(B * NB, 1), max(B * NB, 1), max(B * F * 3, 1), B,
+                            max(B * V, 1)], dtype=F32, device=dev)
         ctx.l2 = int(l2)
+        ctx.nbr = nbr
         ctx.save_for_backward(joints, verts, root_xyz, Ks, joints_gt, j2d_gt, verts_gt, conf, faces)
-        return sums[:7] / cnt, (j2d if j2d is not None else joints.new_zeros(0))
+        return sums[:8] / cnt, (j2d if j2d is not None else joints.new_zeros(0))
 
     @staticmethod
     def backward(ctx, g_terms, g_j2d):
@@ -530,11 +598,11 @@ class KeypointLossFunction(torch.autograd.Function):
         B = joints.shape[0]
         dev = joints.device
         w = torch.zeros(L.KP_NSUMS, dtype=F32, device=dev)
-        w[:7] = g_terms
+        w[:8] = g_terms
         g_joints = torch.empty_like(joints)
         g_verts = torch.empty_like(verts) if verts is not None else None
         g2 = None if (g_j2d is None or g_j2d.numel() == 0 or Ks is None) else _cu(g_j2d)
-        f = keypoint_args(joints, root_xyz, Ks, verts, faces, joints_gt, j2d_gt, verts_gt, conf, ctx.l2, None, w)
+        f = keypoint_args(joints, root_xyz, Ks, verts, faces, joints_gt, j2d_gt, verts_gt, conf, ctx.l2, None, w, nbr=ctx.nbr)
         a = L.HfrKeypointBwdArgs(f, L.ptr(w, F32), B, L.ptr(g2, F32), L.ptr(g_joints, F32), L.ptr(g_verts, F32))
         L.call("hfr_keypoint_backward", a)
-        return g_joints, g_verts, None, None, None, None, None, None, None, None
+        return g_joints, g_verts, None, None, None, None, None, None, None, None, None

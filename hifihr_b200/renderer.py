@@ -108,11 +108,15 @@ class DirectionalLights:
 
 
 class PointLights:
+    """pytorch3d.renderer.lighting.PointLights as constructed at models_res_nimble.py:191-198 (ifLight=False):
+    the light direction of a shaded point is location - point (diffuse / specular of renderer/lighting.py)."""
+
     def __init__(self, ambient_color=((0.5, 0.5, 0.5),), diffuse_color=((0.3, 0.3, 0.3),),
                  specular_color=((0.2, 0.2, 0.2),), location=((0, 1, 0),), device="cpu"):
         self.device = torch.device(device)
-        self.ambient_color, self.diffuse_color = ambient_color, diffuse_color
-        self.specular_color, self.location = specular_color, location
+        t = lambda x: x if isinstance(x, torch.Tensor) else torch.tensor(x, dtype=F32, device=self.device)  # noqa: E731
+        self.ambient_color, self.diffuse_color = t(ambient_color), t(diffuse_color)
+        self.specular_color, self.location = t(specular_color), t(location)
 
 
 class Materials:
@@ -252,8 +256,7 @@ class _ShaderBase(nn.Module):
         dev = p2f.device
         topo = meshes.topology
         if self.shade == 1:
-            if isinstance(lights, PointLights):
-                raise NotImplementedError("PointLights: the reference renders with DirectionalLights (ifLight=True)")
+            point = isinstance(lights, PointLights)
             tex = meshes.textures
             if tex is None:
                 raise ValueError("Meshes does not have textures")
@@ -264,8 +267,8 @@ class _ShaderBase(nn.Module):
                                       _c3(materials.ambient_color), _c3(materials.diffuse_color),
                                       _c3(materials.specular_color), materials.shininess,
                                       tex_shape=maps.shape[:3], VT=tex._verts_uvs.shape[0],
-                                      tex_pca=tex._basis.shape[0] if pca else 0)
-            ldir = _rows(lights.direction, N, dev, "lights.direction")
+                                      tex_pca=tex._basis.shape[0] if pca else 0, light_point=int(point))
+            ldir = _rows(lights.location, N, dev, "lights.location") if point else _rows(lights.direction, N, dev, "lights.direction")
             lcol = _rows(lights.diffuse_color, N, dev, "lights.diffuse_color")
             return ops.ShadeFunction.apply(params, p2f, fragments.zbuf, fragments.bary_coords, fragments.dists,
                                            topo.faces, meshes.verts_padded(), meshes.verts_normals_padded(),

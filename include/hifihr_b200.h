@@ -22,7 +22,7 @@ extern "C" {
 #define HFR_EINVAL 1    /* bad argument (shape, K out of range, null pointer)      */
 #define HFR_ECUDA 2     /* CUDA runtime error at launch                            */
 #define HFR_EUNSUPPORTED 3
-#define HFR_ABI_VERSION 3
+#define HFR_ABI_VERSION 4
 
 #define HFR_MAX_JOINTS 32
 #define HFR_MAX_K 16
@@ -222,6 +222,10 @@ typedef struct HfrShadeParams {
   int32_t tex_pca;                  /* > 0: `texture` is the MEAN map (tex_n = 1) of a PCA texture model with this many
                                        components, evaluated per fragment: texel = mean + sum_k params[n][k] * basis[k]
                                        (NIMBLE-style per-sample texture without materialising the per-sample maps) */
+  int32_t light_point;              /* 0: DirectionalLights, light_dir = direction (N,3).  1: PointLights (the branch of
+                                       models_res_nimble.py:191-198 taken when ifLight=False): light_dir = LOCATION (N,3),
+                                       the light direction of a fragment is location - position; g_light_dir then receives
+                                       d/d(location) */
 } HfrShadeParams;
 #define HFR_MAX_TEX_PCA 64
 
@@ -370,7 +374,13 @@ typedef struct HfrLossArgs {
   int32_t mask_mode;                /* 0: training losses (rim = re_img * re_sil / sil_scale, target = imgs * seg).
                                        Evaluation-time texture metrics (train_hrnet.py:149-161; forward only):
                                        1: both images * seg; 2: both images * (re_sil > 0) (the HO3D branch);
-                                       sums[HFR_LOSS_L1], [HFR_LOSS_L2], [HFR_LOSS_SSIM] then give L1 / L2 / PSNR / SSIM */
+                                       sums[HFR_LOSS_L1], [HFR_LOSS_L2], [HFR_LOSS_SSIM] then give L1 / L2 / PSNR / SSIM
+                                       3: the self-supervised photometric terms texture_self / mrgb_self / ssim_tex_self
+                                       (losses.py:317-340): x = re_img as rendered (no silhouette factor), y = `imgs`, which
+                                       the caller points at maskRGBs (models_res_nimble.py:220); re_sil / seg are unused
+                                       (NCHW only).  sums needs HFR_LOSS_NSUMS + 3N floats: [HFR_LOSS_SSIM] the SSIM sum and,
+                                       per sample n, [NSUMS + n] = sum|x - y|, [NSUMS + N + n] = sum x, [NSUMS + 2N + n] = sum y
+                                       (the reference weights them by texture_con[n]^2).  Has a backward. */
   /* optional 8-bit transport of the targets (the datasets store 8-bit images and {0,1} masks; the reference
    * converts on the host, ToTensor = x / 255): when set they REPLACE imgs / seg, and the kernels convert while
    * loading (exact x / 255.0f through a 256-entry table, mask byte != 0 -> 1.0f), so 4x fewer bytes cross PCIe. */
@@ -387,6 +397,9 @@ typedef struct HfrLossBwdArgs {
   int64_t count_global;             /* N_global*3*H*W for the means (multi-GPU aware)      */
   int32_t n_global;                 /* global batch for the IoU mean                       */
   float* g_re_img; float* g_re_sil; /* (N,3,H,W), (N,1,H,W)                                */
+  /* mask_mode 3 only: w[0..2] = d(total)/d(texture_self, mrgb_self, ssim_tex_self); g_re_sil is not written */
+  const float* tex_con;             /* (N) examples['texture_con'] (losses.py:325)         */
+  const float* self_norm;           /* DEVICE pointer to 1 float: sum_n tex_con[n]^2 over the GLOBAL batch */
 } HfrLossBwdArgs;
 int hfr_loss_backward(const HfrLossBwdArgs* a, void* stream);
 
@@ -397,7 +410,7 @@ int hfr_loss_backward(const HfrLossBwdArgs* a, void* stream);
  * (utils/losses_util.py:217-282), edge_length (:284-301), mscale.  One launch forward, one backward.
  *   forward : writes j2d (optional) and ADDS per-term partial sums to sums[HFR_KP_NSUMS] (caller zeroes; under
  *             data parallelism the caller all-reduces them);  term = sums[k] / count_k with counts
- *             n*NJ*2, n*NJ*3, n*V*3, n*NB, n*NB, n*3F, n  (n = global batch).
+ *             n*NJ*2, n*NJ*3, n*V*3, n*NB, n*NB, n*3F, n, n*V  (n = global batch).
  *   backward: w[k] = d(total)/d(term k) (DEVICE floats, lambda x upstream) -> g_joints (B,NJ,3) and g_verts (B,V,3),
  *             both WRITTEN (not accumulated); feed them to hfr_geom_backward as g_joints / g_verts_rel. */
 #define HFR_KP_J2D 0
@@ -407,6 +420,7 @@ int hfr_loss_backward(const HfrLossBwdArgs* a, void* stream);
 #define HFR_KP_BONE3D 4
 #define HFR_KP_EDGE 5
 #define HFR_KP_MSCALE 6
+#define HFR_KP_LAP 7      /* 'triangle': uniform Laplacian smoothing (losses.py:422-429, utils/losses_util.py:340-364); count n*V */
 #define HFR_KP_NSUMS 8
 typedef struct HfrKeypointArgs {
   int32_t B, NJ, V, F;
@@ -427,6 +441,9 @@ typedef struct HfrKeypointArgs {
   const int32_t* bone_child;        /* (NB)                                                                */
   float* j2d;                       /* (B,NJ,2) output, or NULL                                            */
   float* sums;                      /* (HFR_KP_NSUMS) accumulated                                          */
+  /* uniform Laplacian term: CSR of each vertex's neighbours over the mesh's unique edges; NULL disables it */
+  const int32_t* nbr_ptr;           /* (V+1)                                                               */
+  const int32_t* nbr_idx;           /* (2E)                                                                */
 } HfrKeypointArgs;
 int hfr_keypoint_forward(const HfrKeypointArgs* a, void* stream);
 typedef struct HfrKeypointBwdArgs {

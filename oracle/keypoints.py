@@ -74,3 +74,22 @@ def keypoint_losses(joints, j2d, verts, faces, joints_gt=None, j2d_gt=None, vert
         out["edge_length"] = edge_length(verts, verts_gt, faces)
     out["mscale"] = mscale(joints)
     return out
+
+
+def laplacian_uniform(verts, faces):
+    """'triangle' term: losses.py:422-429 -> utils/losses_util.py:340-364 -> pytorch3d.loss.mesh_laplacian_smoothing
+    (method="uniform") on Meshes(verts=(B,V,3), faces=(F,3) shared).  Upstream (PARITY UNPINNED - PyTorch3D is not in
+    the container; restated from loss/mesh_laplacian_smoothing.py and ops/laplacian_matrices.py):
+        L[i, j] = 1 / deg(i) for every edge (i, j) of the mesh (unique, undirected), L[i, i] = -1,
+        loss = sum_n (1 / V_n) sum_v | (L x)_v |_2  /  N."""
+    f = faces.long()
+    V = verts.shape[1]
+    e = torch.cat([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]], 0)
+    e = torch.unique(torch.sort(e, 1)[0], dim=0)
+    A = torch.zeros(V, V, dtype=verts.dtype)
+    A[e[:, 0], e[:, 1]] = 1
+    A[e[:, 1], e[:, 0]] = 1
+    deg = A.sum(1)
+    Lm = A * torch.where(deg > 0, 1.0 / deg, deg)[:, None] - torch.eye(V, dtype=verts.dtype)
+    lx = torch.einsum("ij,bjc->bic", Lm, verts)
+    return (lx.norm(dim=2) / V).sum() / verts.shape[0]

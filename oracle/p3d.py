@@ -241,9 +241,12 @@ def vertex_normals(verts: torch.Tensor, faces: torch.Tensor):
 def phong_shading(fragments: Fragments, verts_view, faces, texels, light_dir, light_diffuse,
                   light_ambient=(0.5, 0.5, 0.5), light_specular=(0.2, 0.2, 0.2),
                   mat_ambient=(1.0, 1.0, 1.0), mat_diffuse=(0.8, 0.8, 0.8),
-                  mat_specular=(0.2, 0.2, 0.2), shininess: float = 30.0, cam_center=None):
+                  mat_specular=(0.2, 0.2, 0.2), shininess: float = 30.0, cam_center=None, point_light=False):
     """phong_shading + _apply_lighting + DirectionalLights.diffuse/specular.
-    verts_view (N,V,3); faces (F,3); texels (N,H,W,K,3); light_dir/diffuse (N,3)."""
+    verts_view (N,V,3); faces (F,3); texels (N,H,W,K,3); light_dir/diffuse (N,3).
+    point_light=True restates PointLights.diffuse/specular (renderer/lighting.py; the branch of
+    models_res_nimble.py:191-198): light_dir is then the light LOCATION and the direction of every
+    shaded point is location - point."""
     N, V, _ = verts_view.shape
     dt = verts_view.dtype
     Fm = faces.shape[0]
@@ -254,6 +257,8 @@ def phong_shading(fragments: Fragments, verts_view, faces, texels, light_dir, li
     pts = interpolate_face_attributes(fragments.pix_to_face, fragments.bary_coords, fverts)
     nrm = interpolate_face_attributes(fragments.pix_to_face, fragments.bary_coords, fnorm)
     d = light_dir.view(N, 1, 1, 1, 3)
+    if point_light:
+        d = d - pts
     col = light_diffuse.view(N, 1, 1, 1, 3)
     n_hat = F.normalize(nrm, p=2, dim=-1, eps=1e-6)
     d_hat = F.normalize(d, p=2, dim=-1, eps=1e-6)

@@ -60,8 +60,10 @@ def synthetic_texture(T=512, seed=20231):
 
 def render_path(mano, inp, texture, *, image_size=224, aa=1, K=1, blur_radius=0.0, soft=False, sigma=1e-4,
                 gamma=1e-4, binarize=False, root_id=9, dtype=torch.float32, mano_oracle=None, c_select=False,
-                threads=1):
-    """Returns dict with verts, joints, verts_view, verts_ndc, fragments, image (N,H,W,4), re_img, re_sil."""
+                threads=1, pix_to_face=None, point_light=False):
+    """Returns dict with verts, joints, verts_view, verts_ndc, fragments, image (N,H,W,4), re_img, re_sil.
+    pix_to_face: use this face selection instead of searching (three-way precision tests give the fp32 and the fp64
+    evaluation the SAME fragments, so only arithmetic differs)."""
     orc = mano_oracle or ManoOracle(mano, dtype=dtype)
     verts, jtr = orc(inp["pose"], inp["betas"])
     joints = orc.xyz_from_vertice(verts)
@@ -77,14 +79,14 @@ def render_path(mano, inp, texture, *, image_size=224, aa=1, K=1, blur_radius=0.
     fv = ndc[:, faces].reshape(-1, 3, 3)
     first = [i * Fm for i in range(B)]
     nf = [Fm] * B
-    sel = None
-    if c_select:   # CPU baseline: the scalar C rasterizer does the O(P*F) search, torch differentiates the winners
+    sel = pix_to_face
+    if c_select and sel is None:   # CPU baseline: the scalar C rasterizer does the O(P*F) search, torch differentiates the winners
         from . import raster_c
         sel = raster_c.rasterize_naive(fv, first, nf, S, blur_radius, K, perspective_correct=True, threads=threads)[0]
     fr = p3d.rasterize_meshes(fv, first, nf, S, blur_radius, K, perspective_correct=True, pix_to_face=sel)
     uvs, fuv = mano_uvs(mano)
     texels = p3d.sample_textures_uv(fr, texture.to(dtype), fuv, uvs.to(dtype))
-    colors = p3d.phong_shading(fr, view, faces, texels, inp["light_dir"], inp["light_color"])
+    colors = p3d.phong_shading(fr, view, faces, texels, inp["light_dir"], inp["light_color"], point_light=point_light)
     if soft:
         image = p3d.softmax_rgb_blend(colors, fr, sigma, gamma)
     else:

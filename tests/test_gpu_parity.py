@@ -753,7 +753,7 @@ def test_keypoint_losses_match_reference_golden(hf, pre):
         ref = z[pre + "terms"][k]
         assert abs(float(terms[k]) - ref) < 1e-5 * max(1.0, abs(ref)), (k, float(terms[k]), ref)
     w = torch.arange(1, 8, device=DEV, dtype=torch.float32)
-    (terms * w).sum().backward()
+    (terms[:7] * w).sum().backward()          # (term 7 is the Laplacian, off here: no neighbour lists given)
     assert rel_err(j.grad, torch.tensor(z[pre + "g_joints"])) < 1e-4
     assert rel_err(v.grad, torch.tensor(z[pre + "g_verts"])) < 1e-4
 
