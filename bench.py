@@ -294,8 +294,7 @@ def run_ours(args, cfg):
         ev.append(timed("loss_bwd", lambda: L.call("hfr_loss_backward", lb)))
         step.acc.zero_()
         ev.append(timed("shade_raster_bwd", lambda: step.launch_shade_backward()))
-        ev.append(timed("geom_bwd", lambda: ops.geom_backward_raw(step.topo, step.verts, 9, root, focal, prpp, None, None,
-                                                                  step.g_view, step.g_ndc, step.g_vn, step.g_verts)))
+        ev.append(timed("geom_bwd", lambda: step.launch_geom_backward(focal, prpp, root)))
         ev.append(timed("mano_bwd", lambda: ops.mano_backward_raw(step.hm, pose, betas, None, step.g_verts, None,
                                                                   step.g_pose, step.g_betas, None)))
         torch.cuda.synchronize()

@@ -53,7 +53,7 @@ class HfrGeomFwdArgs(C.Structure):
 class HfrGeomBwdArgs(C.Structure):
     _fields_ = [("B", i32), ("root_out", i32), ("verts", vp), ("root_xyz", vp), ("focal", vp), ("prp", vp),
                 ("g_joints", vp), ("g_verts_rel", vp), ("g_verts_view", vp), ("g_verts_ndc", vp),
-                ("g_vnormals", vp), ("g_verts", vp)]
+                ("g_vnormals", vp), ("g_verts", vp), ("face_rec", vp), ("raster_ws", vp), ("status", vp)]
 
 
 class HfrRasterArgs(C.Structure):
@@ -93,6 +93,18 @@ class HfrShadeBwdArgs(C.Structure):
                 ("verts_ndc", vp), ("g_verts_ndc", vp), ("blur_radius", f32), ("perspective_correct", i32),
                 ("clip_barycentric", i32), ("g_verts_view", vp), ("g_vnormals", vp), ("g_texture", vp),
                 ("g_light_dir", vp), ("g_light_color", vp), ("tile_box", vp), ("pool_aa", i32), ("pool_binarize", i32), ("g_tex_params", vp)]
+
+
+class HfrShadeBwdTiledArgs(C.Structure):
+    _fields_ = [("f", HfrShadeFwdArgs), ("g_image", vp), ("verts_ndc", vp), ("focal", vp), ("blur_radius", f32),
+                ("perspective_correct", i32), ("clip_barycentric", i32), ("raster_ws", vp), ("face_rec", vp),
+                ("rec_cap", i64), ("light_acc", vp), ("tex_acc", vp), ("g_texture", vp), ("fx_scale", vp), ("status", vp),
+                ("pool_aa", i32), ("pool_binarize", i32)]
+
+
+class HfrGradFinishArgs(C.Structure):
+    _fields_ = [("tex_acc", vp), ("g_texture", vp), ("n_tex", i64), ("light_acc", vp), ("g_light_dir", vp),
+                ("g_light_color", vp), ("N", i32), ("fx_scale", vp)]
 
 
 class HfrRasterShadeArgs(C.Structure):
@@ -139,6 +151,7 @@ class HfrKeypointBwdArgs(C.Structure):
 ABI_VERSION = 4
 LOSS_NSUMS = 8
 FACE_ATTR_FLOATS = 28
+FACE_REC_FLOATS = 18
 LOSS_L2 = 5
 LOSS_SSIM = 4
 KP_NSUMS = 8
@@ -148,7 +161,7 @@ ENTRY_POINTS = [
     "hfr_geom_forward", "hfr_geom_backward", "hfr_raster_workspace_bytes", "hfr_raster_forward",
     "hfr_raster_backward", "hfr_raster_tile_box", "hfr_shade_forward", "hfr_shade_backward", "hfr_raster_shade_forward",
     "hfr_raster_shade_pool_forward", "hfr_face_attr_forward", "hfr_pool_forward", "hfr_pool_backward", "hfr_loss_forward", "hfr_loss_backward",
-    "hfr_keypoint_forward", "hfr_keypoint_backward",
+    "hfr_keypoint_forward", "hfr_keypoint_backward", "hfr_shade_backward_tiled", "hfr_grad_finish",
 ]
 
 _lib = None

@@ -10,6 +10,7 @@
 // reference (index_add for normals, J_regressor^T in the backward) are turned into gathers
 // over precomputed CSR incidence lists, so there are no atomics and results are deterministic.
 #include "common.cuh"
+#include "raster_tile.cuh"
 
 namespace {
 constexpr int kThreads = 1024;   // one CTA per sample; every per-vertex loop runs in a single round (latency-bound gathers)
@@ -44,6 +45,29 @@ __device__ __forceinline__ void raw_normal(const HfrTopology& t, const float* sv
     for (int k = 0; k < 3; ++k) { u[k] = sv[3 * ib + k] - sv[3 * ia + k]; w[k] = sv[3 * ic + k] - sv[3 * ia + k]; }
     cross3(u, w, x);
     n[0] += x[0]; n[1] += x[1]; n[2] += x[2];
+  }
+}
+
+// d/d(view position) (out[0..2]) and d/d(vertex normal) (out[3..5]) of vertex v of sample b, gathered from the
+// (face, tile) records of hfr_shade_backward_tiled in a FIXED order: incident (face, corner) entries in CSR order,
+// the tiles of a face's range row by row.  No atomics anywhere between the fragments and this sum.
+__device__ __forceinline__ void gather_face_rec(const HfrTopology& t, const float* __restrict__ rec, const uint32_t* __restrict__ ws,
+                                                const hfr::WsLayout& L, int b, int v, float* out) {
+#pragma unroll
+  for (int i = 0; i < 6; ++i) out[i] = 0.0f;
+  const int e0 = __ldg(t.vf_ptr + v), e1 = __ldg(t.vf_ptr + v + 1);
+  for (int e = e0; e < e1; ++e) {
+    const int code = __ldg(t.vf_idx + e), f = code >> 2, c = code & 3;
+    const int64_t fp = (int64_t)b * t.F + f;
+    const uint32_t r = __ldg(ws + fp);
+    if (r == hfr::kEmptyRange) continue;
+    const int nx = (int)((r >> 8) & 255) - (int)(r & 255) + 1, ny = (int)(r >> 24) - (int)((r >> 16) & 255) + 1;
+    const size_t base = (size_t)__ldg(ws + L.blk + (fp >> 8)) + __ldg(ws + L.loc + fp);
+    const float2* __restrict__ q = reinterpret_cast<const float2*>(rec + base * HFR_FACE_REC_FLOATS + 6 * c);
+    for (int j = 0; j < nx * ny; ++j) {       // records are 72 B apart: 9 float2 per record
+      const float2 a0 = __ldg(q + 9 * j), a1 = __ldg(q + 9 * j + 1), a2 = __ldg(q + 9 * j + 2);
+      out[0] += a0.x; out[1] += a0.y; out[2] += a1.x; out[3] += a1.y; out[4] += a2.x; out[5] += a2.y;
+    }
   }
 }
 
@@ -154,15 +178,25 @@ __global__ void __launch_bounds__(kThreads) geom_bwd_kernel(HfrTopology t, HfrGe
   float* s_gj = s_red + 3 * (kThreads / 32) + 4;              // NJR*3 grads wrt regressed joints
   geom_stage(t, a.B, b, a.root_out, a.verts, a.root_xyz, s_v, s_view, s_j, s_pos, s_root);
   const size_t base = (size_t)b * V * 3;
+  const bool from_rec = a.face_rec != nullptr;
+  const uint32_t* __restrict__ ws = reinterpret_cast<const uint32_t*>(a.raster_ws);
+  const hfr::WsLayout L = hfr::ws_layout((int64_t)a.B * t.F);
+  const bool rec_bad = from_rec && a.status && __ldg(a.status) != 0u;   // record store overflowed: fail loudly (NaN)
   // 1. raw-normal grads
   for (int v = tid; v < V; v += kThreads) {
     float g[3] = {0.f, 0.f, 0.f};
-    if (a.g_vnormals) {
+    float r6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (from_rec) {
+      gather_face_rec(t, a.face_rec, ws, L, b, v, r6);
+      // s_v is dead after geom_stage: park d/d(view) there for step 2
+      s_g[3 * v] = r6[0]; s_g[3 * v + 1] = r6[1]; s_g[3 * v + 2] = r6[2];
+    }
+    if (a.g_vnormals || from_rec) {
       float n[3];
       raw_normal(t, s_view, v, n);
       const float len = sqrtf(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
-      const float gx = a.g_vnormals[base + 3 * v], gy = a.g_vnormals[base + 3 * v + 1],
-                  gz = a.g_vnormals[base + 3 * v + 2];
+      const float gx = from_rec ? r6[3] : a.g_vnormals[base + 3 * v], gy = from_rec ? r6[4] : a.g_vnormals[base + 3 * v + 1],
+                  gz = from_rec ? r6[5] : a.g_vnormals[base + 3 * v + 2];
       if (len >= 1e-6f) {
         const float hx = n[0] / len, hy = n[1] / len, hz = n[2] / len;
         const float d = hx * gx + hy * gy + hz * gz;
@@ -179,7 +213,9 @@ __global__ void __launch_bounds__(kThreads) geom_bwd_kernel(HfrTopology t, HfrGe
   const float fx = a.g_verts_ndc ? a.focal[2 * b] : 0.f, fy = a.g_verts_ndc ? a.focal[2 * b + 1] : 0.f;
   for (int v = tid; v < V; v += kThreads) {
     float g[3] = {0.f, 0.f, 0.f};
-    if (a.g_verts_view) { g[0] = a.g_verts_view[base + 3 * v]; g[1] = a.g_verts_view[base + 3 * v + 1]; g[2] = a.g_verts_view[base + 3 * v + 2]; }
+    if (from_rec) { g[0] = s_g[3 * v]; g[1] = s_g[3 * v + 1]; g[2] = s_g[3 * v + 2]; }
+    if (rec_bad) g[0] = __int_as_float(0x7fc00000);
+    if (a.g_verts_view) { g[0] += a.g_verts_view[base + 3 * v]; g[1] += a.g_verts_view[base + 3 * v + 1]; g[2] += a.g_verts_view[base + 3 * v + 2]; }
     if (a.g_verts_ndc) {
       const float X = s_view[3 * v], Y = s_view[3 * v + 1], Z = s_view[3 * v + 2];
       const float gx = a.g_verts_ndc[base + 3 * v], gy = a.g_verts_ndc[base + 3 * v + 1], gz = a.g_verts_ndc[base + 3 * v + 2];
@@ -188,7 +224,7 @@ __global__ void __launch_bounds__(kThreads) geom_bwd_kernel(HfrTopology t, HfrGe
       g[1] += gy * fy / Z;
       g[2] += gz - (gx * fx * X + gy * fy * Y) / (Z * Z);
     }
-    if (a.g_vnormals) {
+    if (a.g_vnormals || from_rec) {
       const int e0 = __ldg(t.vf_ptr + v), e1 = __ldg(t.vf_ptr + v + 1);
 #pragma unroll 2
       for (int e = e0; e < e1; ++e) {
@@ -287,6 +323,8 @@ extern "C" int hfr_geom_backward(const HfrTopology* t, const HfrGeomBwdArgs* a, 
   HFR_CHECK_ARG(a->verts && a->g_verts, "geom_backward: null pointer");
   if (int rc = check_topo(t, a->root_out >= 0)) return rc;
   HFR_CHECK_ARG(!a->g_verts_ndc || (a->focal && a->prp), "geom_backward: g_verts_ndc needs focal/prp");
+  HFR_CHECK_ARG(!a->face_rec || (a->raster_ws && !a->g_verts_ndc && !a->g_vnormals),
+                "geom_backward: face records need the rasterizer workspace and replace g_verts_ndc / g_vnormals");
   if (a->B == 0) return HFR_OK;
   const size_t smem = (size_t)(9 * t->V + 6 * (t->NJR > 0 ? t->NJR : 1) + 3 * (t->NOUT > 0 ? t->NOUT : 1) + 16 + 3 * (kThreads / 32)) * sizeof(float);
   HFR_CHECK_ARG(smem <= 227 * 1024, "geom_backward: mesh too large for shared memory");

@@ -13,7 +13,9 @@ namespace hfr {
 // union of those ranges per mesh (4 min-reduced words per mesh, the two upper bounds stored as 255 - x,
 // initialised to 0xff by a memset), so that tiles outside a mesh's footprint skip the coarse scan.
 __global__ void __launch_bounds__(256) raster_setup_kernel(HfrRasterArgs a, uint32_t* __restrict__ ranges,
-                                                           uint32_t* __restrict__ mesh_box) {
+                                                           uint32_t* __restrict__ mesh_box, uint32_t* __restrict__ rec_loc,
+                                                           uint32_t* __restrict__ blk_tot) {
+  __shared__ uint32_t s_wsum[8];
   const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = f < a.Ftot;
   uint32_t out = kEmptyRange;
@@ -44,6 +46,23 @@ __global__ void __launch_bounds__(256) raster_setup_kernel(HfrRasterArgs a, uint
     }
     ranges[f] = out;
   }
+  {   // exclusive prefix of the range areas inside this 256-face block (record slots of the atomics-free backward)
+    const uint32_t area = (live && out != kEmptyRange) ? (uint32_t)((tx1 - tx0 + 1) * (ty1 - ty0 + 1)) : 0u;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = area;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_wsum[warp] = incl;
+    __syncthreads();
+    uint32_t before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { const uint32_t c = s_wsum[w]; before += (w < warp) ? c : 0u; total += c; }
+    if (live) rec_loc[f] = before + incl - area;
+    if (threadIdx.x == 0) blk_tot[blockIdx.x] = total;
+  }
   if (mesh_box == nullptr) return;
   // mesh of this face: last n with mesh_first[n] <= f (meshes are packed in order)
   int n = -1;
@@ -71,6 +90,35 @@ __global__ void __launch_bounds__(256) raster_setup_kernel(HfrRasterArgs a, uint
     atomicMin(mesh_box + 4 * n, (unsigned)tx0); atomicMin(mesh_box + 4 * n + 1, (unsigned)(255 - tx1));
     atomicMin(mesh_box + 4 * n + 2, (unsigned)ty0); atomicMin(mesh_box + 4 * n + 3, (unsigned)(255 - ty1));
   }
+}
+
+// exclusive scan of the per-block record totals, in place (one CTA; nblk + 1 entries, the last one receives the total)
+__global__ void __launch_bounds__(1024) raster_scan_kernel(uint32_t* __restrict__ blk, int nblk) {
+  __shared__ uint32_t s_w[32];
+  __shared__ uint32_t s_carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nblk; base += 1024) {
+    const int i = base + tid;
+    const uint32_t v = i < nblk ? blk[i] : 0u;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    uint32_t before = 0, total = 0;
+    for (int w = 0; w < 32; ++w) { const uint32_t c = s_w[w]; before += (w < warp) ? c : 0u; total += c; }
+    const uint32_t carry = s_carry;
+    if (i < nblk) blk[i] = carry + before + incl - v;
+    __syncthreads();
+    if (tid == 0) s_carry = carry + total;
+    __syncthreads();
+  }
+  if (tid == 0) blk[nblk] = s_carry;
 }
 
 template <int KMAX>
@@ -130,18 +178,22 @@ int check_raster(const HfrRasterArgs* a, const char* who) {
   return HFR_OK;
 }
 
-// workspace layout: [Ftot + 64 words: packed tile range per face][4 words per mesh: tile box], the box only
-// when N <= Ftot (hfr_raster_workspace_bytes sizes the buffer for that)
+// workspace layout: ws_layout() in raster_tile.cuh; the tile box only when N <= Ftot (hfr_raster_workspace_bytes sizes
+// the buffer for that)
 const uint32_t* raster_mesh_box(const HfrRasterArgs& a) {
-  return (a.N <= a.Ftot) ? reinterpret_cast<const uint32_t*>(a.workspace) + ((a.Ftot + 64 + 3) & ~(int64_t)3) : nullptr;   // 16-byte aligned
+  return (a.N <= a.Ftot) ? reinterpret_cast<const uint32_t*>(a.workspace) + ws_layout(a.Ftot).box : nullptr;   // 16-byte aligned
 }
 
 int launch_raster_setup(const HfrRasterArgs& a, uint32_t* ranges, cudaStream_t s) {
   if (a.Ftot > 0) {
     uint32_t* box = const_cast<uint32_t*>(raster_mesh_box(a));
     if (box) cudaMemsetAsync(box, 0xff, (size_t)a.N * 4 * sizeof(uint32_t), s);
-    raster_setup_kernel<<<(unsigned)((a.Ftot + 255) / 256), 256, 0, s>>>(a, ranges, box);
+    const WsLayout L = ws_layout(a.Ftot);
+    uint32_t* ws = reinterpret_cast<uint32_t*>(a.workspace);
+    raster_setup_kernel<<<(unsigned)L.nblk, 256, 0, s>>>(a, ranges, box, ws + L.loc, ws + L.blk);
     HFR_CHECK_LAUNCH("raster_setup");
+    raster_scan_kernel<<<1, 1024, 0, s>>>(ws + L.blk, (int)L.nblk);
+    HFR_CHECK_LAUNCH("raster_scan");
   }
   return HFR_OK;
 }
@@ -154,11 +206,11 @@ static void launch_fwd(const HfrRasterArgs& a, const uint32_t* ranges, cudaStrea
 
 }  // namespace hfr
 
-extern "C" int64_t hfr_raster_workspace_bytes(int64_t Ftot) { return (5 * Ftot + 80) * 4; }
+extern "C" int64_t hfr_raster_workspace_bytes(int64_t Ftot) { return hfr::ws_layout(Ftot < 1 ? 1 : Ftot).words * 4 + 64; }
 
 extern "C" const uint32_t* hfr_raster_tile_box(const void* workspace, int64_t Ftot, int32_t N) {
   if (!workspace || N <= 0 || N > Ftot) return nullptr;
-  return reinterpret_cast<const uint32_t*>(workspace) + ((Ftot + 64 + 3) & ~(int64_t)3);
+  return reinterpret_cast<const uint32_t*>(workspace) + hfr::ws_layout(Ftot).box;
 }
 
 extern "C" int hfr_raster_forward(const HfrRasterArgs* a, void* stream) {

@@ -495,6 +495,31 @@ __device__ __forceinline__ bool fill_empty_tile(const HfrRasterArgs& a, int n, i
   return true;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Rasterizer workspace layout (32-bit words), filled by the setup pass (raster.cu) for Ftot packed faces / N meshes:
+//   [0, Ftot + 64)                     packed tile range per face (pack_tile_range)
+//   [box, box + 4 N)                   per-mesh tile box {txmin, 255 - txmax, tymin, 255 - tymax}   (only when N <= Ftot)
+//   [loc, loc + Ftot)                  per face: exclusive prefix of the tile-range AREAS inside its 256-face block
+//   [blk, blk + nblk + 1)              per 256-face block: exclusive prefix of the block totals; [blk + nblk] = total
+// (face, tile) record index of the atomics-free backward = blk[f >> 8] + loc[f] + (ty - tymin) * (txmax - txmin + 1)
+// + (tx - txmin): every (face, tile-in-its-range) pair owns one slot, so gradients are scattered without atomics and
+// gathered per vertex in a fixed order (shade_bwd_tiled.cu, geom.cu).
+struct WsLayout { int64_t box, loc, blk, nblk, words; };
+__host__ __device__ __forceinline__ WsLayout ws_layout(int64_t Ftot) {
+  WsLayout w;
+  w.box = (Ftot + 64 + 3) & ~(int64_t)3;
+  w.loc = w.box + 4 * Ftot;
+  w.nblk = (Ftot + 255) >> 8;
+  w.blk = w.loc + Ftot;
+  w.words = w.blk + w.nblk + 4;
+  return w;
+}
+__device__ __forceinline__ uint32_t face_rec_index(const uint32_t* __restrict__ ws, const WsLayout& L, int64_t fp, int tx, int ty) {
+  const uint32_t r = __ldg(ws + fp);
+  const int txmin = r & 255, txmax = (r >> 8) & 255, tymin = (r >> 16) & 255;
+  return __ldg(ws + L.blk + (fp >> 8)) + __ldg(ws + L.loc + fp) + (uint32_t)((ty - tymin) * (txmax - txmin + 1) + (tx - txmin));
+}
+
 // host helpers defined in raster.cu
 int launch_raster_setup(const HfrRasterArgs& a, uint32_t* ranges, cudaStream_t s);
 const uint32_t* raster_mesh_box(const HfrRasterArgs& a);

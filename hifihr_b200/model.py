@@ -118,14 +118,20 @@ class FusedHandStep:
 
     def __init__(self, B, image_size=224, faces_per_pixel=4, blur_radius=None, sigma=1e-4, gamma=1e-4, soft=True,
                  texture_size=512, lambdas=None, device="cuda", mano_root=None, n_global=None, sil_scale=1.0,
-                 aa_factor=1, binarize=False, want_nchw=False, face_records=False):
+                 aa_factor=1, binarize=False, want_nchw=False, face_records=False, tiled_backward=True,
+                 deterministic=True, rec_per_face=12):
         """aa_factor > 1 selects the SSAA-fused render (the reference's own setting is image_size=224,
         aa_factor=3, faces_per_pixel=1, soft=False, binarize=True, sil_scale=255; models_res_nimble.py:74-96,
         208-220): Fragments are rasterised at image_size*aa_factor, the pooled RGBA (B,S,S,4) is the only image
         that exists, and the backward folds avg_pool2d' into the shading backward.  want_nchw also writes
         re_img / re_sil / maskRGBs in the reference's NCHW layout.  face_records packs one contiguous attribute
         record per (sample, face) each step (one more launch) so the shaders skip two dependent gathers; measured
-        neutral on B200 at C2 (backward 370 -> 363 us, forward + 9 us for the packing launch), hence off by default."""
+        neutral on B200 at C2 (backward 370 -> 363 us, forward + 9 us for the packing launch), hence off by default.
+        tiled_backward selects the atomics-free backward (hfr_shade_backward_tiled: per-tile face sort, one record per
+        (face, tile), fixed-order gather in the geometry backward); with deterministic=True the texture gradient goes
+        through 64-bit fixed-point accumulators as the light gradients always do, so a step is bit-reproducible.
+        rec_per_face sizes the record store (records = rec_per_face * B * F; a face needs one per 16x16 tile its
+        dilated bounding box touches; overflow raises through the status word / NaN gradients)."""
         dev = torch.device(device)
         self.B, self.S, self.K, self.dev = B, image_size, faces_per_pixel, dev
         self.aa, self.binarize = int(aa_factor), bool(binarize)
@@ -184,13 +190,23 @@ class FusedHandStep:
         self.g_texture = take(self.texture.numel(), self.texture.shape)
         self.g_light_dir, self.g_light_color = take(3 * B, (B, 3)), take(3 * B, (B, 3))
         self.g_verts = e(B, V, 3)
+        self.tiled, self.deterministic = bool(tiled_backward), bool(deterministic)
+        if self.tiled:
+            self.rec_cap = int(rec_per_face) * B * Fm + 4096
+            self.face_rec = e(self.rec_cap, L.FACE_REC_FLOATS)
+            self.light_acc = torch.zeros(B, 6, dtype=I64, device=dev)
+            self.tex_acc = torch.zeros(self.texture.shape, dtype=I64, device=dev) if self.deterministic else None
+            self.status = torch.zeros(1, dtype=torch.int32, device=dev)
+            self.fx_scale = torch.ones(1, dtype=F32, device=dev)
+            self._focal = None
         self.gauss = ops.gauss_taps(dev)
         self.params = ops.shade_params(B, Sr, Sr, K, Fm, V, 2 if soft else 0, 1, sigma, gamma, (1.0, 1.0, 1.0),
                                        (0.5, 0.5, 0.5), (0.2, 0.2, 0.2), (1.0, 1.0, 1.0), (0.8, 0.8, 0.8),
                                        (0.2, 0.2, 0.2), 30.0, tex_shape=self.texture.shape[:3], VT=self.verts_uvs.shape[0])
         # kernels of OURS per step(): mano, geom, [face records], raster setup, raster+shade(+pool), loss | loss', shade'+raster',
         # geom', mano'  (the two torch memsets of the accumulators are not counted)
-        self.launches_per_step = 9 + (1 if face_records else 0)
+        # tiled backward: + raster scan, record clear, gradient finish (the fixed-point scale is two small torch reductions)
+        self.launches_per_step = 9 + (1 if face_records else 0) + (4 if self.tiled else 0)
 
     def _bind_outputs(self):
         o, B, ns = self._outs[self._out_set], self.B, self._n_sums
@@ -207,6 +223,9 @@ class FusedHandStep:
     # ---------------------------------------------------------------------------------------
     def forward(self, pose, betas, focal, prp, root_xyz, light_dir, light_color, imgs, seg):
         B, S, K, Sr = self.B, self.S, self.K, self.Sr
+        # the cached argument structs hold raw pointers: keep the inputs alive until the backward has been enqueued
+        self._inputs = (pose, betas, focal, prp, root_xyz, light_dir, light_color, imgs, seg)
+        self._focal = focal
         ops.mano_forward_raw(self.hm, pose, betas, None, self.verts, None)
         ops.geom_forward_raw(self.topo, self.verts, 9, root_xyz, focal, prp, self.joints, self.verts_rel,
                              self.verts_view, self.verts_ndc, self.vnormals, self.face_verts)
@@ -245,12 +264,33 @@ class FusedHandStep:
     def launch_shade_backward(self):
         """shade' + blend' + rasterize' (+ avg_pool2d' when aa_factor > 1) in one launch; accumulates into self.acc."""
         B = self.B
+        if self.tiled:
+            # fixed-point multiplier of the 64-bit accumulators: 2^36 over the power of two above max |g_image|
+            gmax = self.g_image.abs().amax().clamp_min(1e-30)
+            torch.exp2(36.0 - torch.ceil(torch.log2(gmax)), out=self.fx_scale[0])
+            t = L.HfrShadeBwdTiledArgs(self._shade_args, L.ptr(self.g_image), L.ptr(self.verts_ndc), L.ptr(self._focal, F32, "focal"),
+                                       float(self.blur), 1, int(self.blur > 0), L.ptr(self.ws), L.ptr(self.face_rec), self.rec_cap,
+                                       L.ptr(self.light_acc), L.ptr(self.tex_acc), None if self.deterministic else L.ptr(self.g_texture),
+                                       L.ptr(self.fx_scale), L.ptr(self.status), self.aa if self.aa > 1 else 0, int(self.binarize))
+            L.call("hfr_shade_backward_tiled", t)
+            L.call("hfr_grad_finish", L.HfrGradFinishArgs(L.ptr(self.tex_acc), L.ptr(self.g_texture) if self.deterministic else None,
+                                                          self.texture.numel() if self.deterministic else 0, L.ptr(self.light_acc),
+                                                          L.ptr(self.g_light_dir), L.ptr(self.g_light_color), B, L.ptr(self.fx_scale)))
+            return
         sb = L.HfrShadeBwdArgs(self._shade_args, L.ptr(self.g_image), None, None, None, L.ptr(self.verts_ndc),
                                L.ptr(self.g_ndc), float(self.blur), 1, int(self.blur > 0), L.ptr(self.g_view),
                                L.ptr(self.g_vn), L.ptr(self.g_texture), L.ptr(self.g_light_dir),
                                L.ptr(self.g_light_color), ops.raster_tile_box(self.ws, B * self.topo.F, B),
                                self.aa if self.aa > 1 else 0, int(self.binarize))
         L.call("hfr_shade_backward", sb)
+
+    def launch_geom_backward(self, focal, prp, root_xyz):
+        if self.tiled:   # gathers d/d(view), d/d(normal) from the (face, tile) records in a fixed order
+            ops.geom_backward_raw(self.topo, self.verts, 9, root_xyz, focal, prp, None, None, None, None, None, self.g_verts,
+                                  face_rec=self.face_rec, raster_ws=self.ws, status=self.status)
+        else:
+            ops.geom_backward_raw(self.topo, self.verts, 9, root_xyz, focal, prp, None, None, self.g_view, self.g_ndc,
+                                  self.g_vn, self.g_verts)
 
     def backward(self, pose, betas, focal, prp, root_xyz, shared_grad_hook=None):
         """shared_grad_hook(g_texture) -> work handles: called as soon as the gradient of the shared texture is
@@ -259,11 +299,13 @@ class FusedHandStep:
         a = L.HfrLossBwdArgs(self._loss_args, L.ptr(self.w), L.ptr(self.gauss), self.n_global * 3 * S * S,
                              self.n_global, L.ptr(self.g_image), None)
         L.call("hfr_loss_backward", a)
-        self.acc.zero_()
+        if not self.tiled:
+            self.acc.zero_()
+        elif not self.deterministic:
+            self.g_texture.zero_()
         self.launch_shade_backward()
         works = shared_grad_hook(self.g_texture) if shared_grad_hook is not None else ()
-        ops.geom_backward_raw(self.topo, self.verts, 9, root_xyz, focal, prp, None, None, self.g_view, self.g_ndc,
-                              self.g_vn, self.g_verts)
+        self.launch_geom_backward(focal, prp, root_xyz)
         ops.mano_backward_raw(self.hm, pose, betas, None, self.g_verts, None, self.g_pose, self.g_betas, None)
         for w in works:
             w.wait()
@@ -271,6 +313,11 @@ class FusedHandStep:
     def step(self, pose, betas, focal, prp, root_xyz, light_dir, light_color, imgs, seg):
         self.forward(pose, betas, focal, prp, root_xyz, light_dir, light_color, imgs, seg)
         self.backward(pose, betas, focal, prp, root_xyz)
+
+    def check_status(self):
+        """Host check of the record-store status word (a device->host sync): raises if the store was too small."""
+        if self.tiled and int(self.status.item()) != 0:
+            raise L.HfrError("FusedHandStep: the (face, tile) record store overflowed; raise rec_per_face")
 
     def loss_terms(self, sums=None):
         """[texture, mrgb, ssim_tex, sil, iou] (unweighted) from the partial sums (device tensor ops)."""

@@ -182,10 +182,12 @@ def geom_forward_raw(topo, verts, root_out, root_xyz, focal, prp, joints, verts_
     L.call("hfr_geom_forward", topo.struct, a)
 
 
-def geom_backward_raw(topo, verts, root_out, root_xyz, focal, prp, g_joints, g_rel, g_view, g_ndc, g_vn, g_verts):
+def geom_backward_raw(topo, verts, root_out, root_xyz, focal, prp, g_joints, g_rel, g_view, g_ndc, g_vn, g_verts,
+                      face_rec=None, raster_ws=None, status=None):
     a = L.HfrGeomBwdArgs(verts.shape[0], root_out, L.ptr(verts, F32), L.ptr(root_xyz, F32), L.ptr(focal, F32),
                          L.ptr(prp, F32), L.ptr(g_joints, F32), L.ptr(g_rel, F32), L.ptr(g_view, F32),
-                         L.ptr(g_ndc, F32), L.ptr(g_vn, F32), L.ptr(g_verts, F32))
+                         L.ptr(g_ndc, F32), L.ptr(g_vn, F32), L.ptr(g_verts, F32), L.ptr(face_rec, F32),
+                         L.ptr(raster_ws), L.ptr(status))
     L.call("hfr_geom_backward", topo.struct, a)
 
 

@@ -158,6 +158,12 @@ typedef struct HfrGeomBwdArgs {
   const float* g_verts_ndc;
   const float* g_vnormals;
   float* g_verts;             /* (B,V,3)                                                 */
+  /* optional: gather d/d(view) and d/d(vertex normal) from the (face, tile) records of hfr_shade_backward_tiled instead
+   * of reading g_verts_view / g_vnormals / g_verts_ndc (which must then be NULL).  Fixed summation order: incident
+   * faces in CSR order, tiles of a face's range row by row. */
+  const float* face_rec;
+  const void* raster_ws;      /* the rasterizer workspace (tile ranges + record offsets), Ftot = B * F, mesh n = faces [n F, (n+1) F) */
+  const uint32_t* status;     /* record-store status word of the backward; non-zero -> g_verts = NaN */
 } HfrGeomBwdArgs;
 int hfr_geom_backward(const HfrTopology* t, const HfrGeomBwdArgs* a, void* stream);
 
@@ -295,6 +301,49 @@ int hfr_shade_backward(const HfrShadeBwdArgs* a, void* stream);
  * rasterizer workspace that hfr_raster_forward / hfr_raster_shade_forward filled for N meshes and Ftot packed
  * faces; NULL when the workspace holds none (N > Ftot). */
 const uint32_t* hfr_raster_tile_box(const void* workspace, int64_t Ftot, int32_t N);
+
+/* Atomics-free, deterministic fused backward (shade' + blend' + rasterize' + d(ndc)/d(view)) - the replacement of
+ * upstream rasterize_meshes_backward / interp_face_attrs_backward's 9 + 18 atomics per covered pixel, reached by
+ * loss.backward() at train_hrnet.py:112.  One CTA owns a 16x16 tile: its fragments are counting-sorted by face in
+ * shared memory (integer bookkeeping only), each face's 18 gradient components (3 corners x {view position, vertex
+ * normal}) are summed SEQUENTIALLY in pixel order by one warp and stored as ONE record per (face, tile) at the slot the
+ * rasterizer's setup pass reserved (hfr_raster_workspace layout); hfr_geom_backward then gathers per vertex over the
+ * static vertex->face incidence lists in a fixed order.  Quantities summed over ALL fragments of a sample or batch
+ * (light gradients, the shared texture's gradient) go through 64-bit FIXED-POINT accumulators: integer addition is
+ * associative, so the result does not depend on the order the hardware serialises them in; hfr_grad_finish converts
+ * them to fp32 and clears them.  The whole backward is therefore bit-reproducible run to run.
+ * Needs the rasterizer workspace exactly as hfr_raster_(shade_)forward left it for the same N / Ftot, with
+ * mesh_first[n] = n * F (uniform packing, what MeshRasterizer builds for a batch of one topology). */
+#define HFR_FACE_REC_FLOATS 18      /* corner-major: {d/d(view xyz), d/d(vertex normal xyz)} x 3 corners */
+typedef struct HfrShadeBwdTiledArgs {
+  HfrShadeFwdArgs f;                /* forward inputs; f.image = the forward OUTPUT (softmax blend)             */
+  const float* g_image;             /* (N,H,W,4), or the pooled gradient (N,H/aa,W/aa,4) when pool_aa > 1          */
+  const float* verts_ndc;           /* (N,V,3)                                                                     */
+  const float* focal;               /* (N,2) NDC focal as given to the camera: d(ndc)/d(view) is folded in here    */
+  float blur_radius; int32_t perspective_correct, clip_barycentric;
+  const void* raster_ws;            /* rasterizer workspace filled by the forward                                  */
+  float* face_rec;                  /* (rec_cap, HFR_FACE_REC_FLOATS) record store; cleared here up to the used size */
+  int64_t rec_cap;                  /* records that fit; when the batch needs more: status bit 0, gradients = NaN  */
+  int64_t* light_acc;               /* (N,6) fixed point d/d(light_dir | location), d/d(light_color); caller zeroes ONCE,
+                                       hfr_grad_finish re-clears                                                    */
+  int64_t* tex_acc;                 /* (tex_n,tex_h,tex_w,3) fixed-point gradient of the texture, same protocol; NULL:
+                                       plain fp32 atomics into g_texture (faster, not run-to-run reproducible)      */
+  float* g_texture;                 /* used when tex_acc == NULL (accumulated, caller zeroes); may be NULL           */
+  const float* fx_scale;            /* DEVICE pointer to the fixed-point multiplier (a power of two; pick 2^36 / the power
+                                       of two above max |g_image| so accumulators neither overflow nor lose bits)   */
+  uint32_t* status;                 /* DEVICE word, OR-ed: bit 0 = record store too small                            */
+  int32_t pool_aa, pool_binarize;   /* as in HfrShadeBwdArgs                                                         */
+} HfrShadeBwdTiledArgs;
+int hfr_shade_backward_tiled(const HfrShadeBwdTiledArgs* a, void* stream);
+
+/* Fixed-point accumulators -> fp32 gradients (and clears the accumulators for the next step):
+ *   g_texture[i] = tex_acc[i] / scale (n_tex values), g_light_dir / g_light_color (N,3) from light_acc (N,6). */
+typedef struct HfrGradFinishArgs {
+  int64_t* tex_acc; float* g_texture; int64_t n_tex;
+  int64_t* light_acc; float* g_light_dir; float* g_light_color; int32_t N;
+  const float* fx_scale;
+} HfrGradFinishArgs;
+int hfr_grad_finish(const HfrGradFinishArgs* a, void* stream);
 
 /* Fused rasterize + shade forward: writes Fragments AND the image in one pass. */
 typedef struct HfrRasterShadeArgs {

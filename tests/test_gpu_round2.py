@@ -380,3 +380,71 @@ def test_three_way_precision(hf, mano, B, S, K, T):
         # a barycentric clamp) show up in either one, so the comparison is on the L2 norm with an absolute floor
         assert g2 < 3.0 * o2 + 2e-3, (k, g2, o2)
         assert gm < TOL_KINK, (k, gm)
+
+
+# ------------------------------------------------------------------------------------------ determinism
+@pytest.mark.parametrize("S,K,soft,aa", [(96, 4, True, 1), (32, 1, False, 3)])
+def test_backward_is_bit_reproducible(hf, S, K, soft, aa):
+    """The atomics-free backward: two steps on the same inputs give bit-identical gradients (pose, shape, texture,
+    lights) - vertex gradients never meet an atomic, the batch-wide sums go through 64-bit fixed-point accumulators -
+    and a second FusedHandStep object reproduces them too."""
+    B = 3
+    inp = P.synthetic_inputs(B, S=S, seed=23)
+    fcl, prp = p3d.ndc_intrinsics(inp["Ks"])
+    d = lambda t: t.to(DEV).contiguous()  # noqa: E731
+    args = (d(inp["pose"]), d(inp["betas"]), d(-fcl), d(prp), d(inp["root_xyz"]), d(inp["light_dir"]),
+            d(inp["light_color"]), d(inp["imgs"]), d(inp["segms_gt"].float()))
+    kw = dict(image_size=S, faces_per_pixel=K, soft=soft, texture_size=64, device=DEV, aa_factor=aa, binarize=aa > 1,
+              sil_scale=255.0 if aa > 1 else 1.0)
+    runs = []
+    for obj in range(2):
+        step = hf.FusedHandStep(B, **kw)
+        for rep in range(3):
+            step.step(*args)
+            torch.cuda.synchronize()
+            step.check_status()
+            runs.append({k: getattr(step, k).clone() for k in ("g_pose", "g_betas", "g_texture", "g_light_dir", "g_light_color", "g_verts")})
+    for r in runs[1:]:
+        for k, v in r.items():
+            assert torch.equal(v, runs[0][k]), k
+    assert runs[0]["g_pose"].abs().max() > 0 and runs[0]["g_texture"].abs().max() > 0
+
+
+@pytest.mark.parametrize("S,K,soft,aa,blur", [(64, 4, True, 1, None), (40, 1, False, 2, None), (56, 2, True, 1, None), (48, 8, True, 1, None)])
+def test_tiled_backward_matches_atomic_backward(hf, S, K, soft, aa, blur):
+    """hfr_shade_backward_tiled + record gather against the round-1 atomic backward on identical forward state:
+    every gradient to 1e-4 of its max (summation order differs), fixed-point texture / light accumulators included."""
+    B = 2
+    inp = P.synthetic_inputs(B, S=S, seed=31 + K)
+    fcl, prp = p3d.ndc_intrinsics(inp["Ks"])
+    d = lambda t: t.to(DEV).contiguous()  # noqa: E731
+    args = (d(inp["pose"]), d(inp["betas"]), d(-fcl), d(prp), d(inp["root_xyz"]), d(inp["light_dir"]),
+            d(inp["light_color"]), d(inp["imgs"]), d(inp["segms_gt"].float()))
+    kw = dict(image_size=S, faces_per_pixel=K, soft=soft, texture_size=64, device=DEV, aa_factor=aa, binarize=aa > 1,
+              sil_scale=255.0 if aa > 1 else 1.0)
+    a = hf.FusedHandStep(B, tiled_backward=True, **kw)
+    b = hf.FusedHandStep(B, tiled_backward=False, **kw)
+    c = hf.FusedHandStep(B, tiled_backward=True, deterministic=False, **kw)
+    for st in (a, b, c):
+        st.step(*args)
+    torch.cuda.synchronize()
+    a.check_status()
+    for k in ("g_verts", "g_pose", "g_betas", "g_texture", "g_light_dir", "g_light_color"):
+        assert rel_err(getattr(a, k), getattr(b, k)) < 1e-4, k
+        assert rel_err(getattr(c, k), getattr(b, k)) < 1e-4, k
+
+
+def test_record_store_overflow_fails_loudly(hf):
+    B, S = 2, 64
+    inp = P.synthetic_inputs(B, S=S, seed=3)
+    fcl, prp = p3d.ndc_intrinsics(inp["Ks"])
+    d = lambda t: t.to(DEV).contiguous()  # noqa: E731
+    args = (d(inp["pose"]), d(inp["betas"]), d(-fcl), d(prp), d(inp["root_xyz"]), d(inp["light_dir"]),
+            d(inp["light_color"]), d(inp["imgs"]), d(inp["segms_gt"].float()))
+    step = hf.FusedHandStep(B, image_size=S, faces_per_pixel=4, soft=True, texture_size=32, device=DEV, rec_per_face=0)
+    step.rec_cap = 16       # far too small
+    step.step(*args)
+    torch.cuda.synchronize()
+    with pytest.raises(hf._lib.HfrError):
+        step.check_status()
+    assert torch.isnan(step.g_pose).any()
