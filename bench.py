@@ -192,9 +192,10 @@ def run_ours(args, cfg):
     def one_step(tensors):
         pose, betas, focal, prpp, root, ldir, lcol, imgs, seg = tensors
         step.forward(pose, betas, focal, prpp, root, ldir, lcol, imgs, seg)
-        hdist.all_reduce_loss_sums(step.sums)          # global means for the mean-RGB term (no-op at N=1)
-        # gradient of the shared texture: all-reduced while the geometry / hand-layer backward run (no-op at N=1)
-        step.backward(pose, betas, focal, prpp, root, shared_grad_hook=hdist.all_reduce_shared_grads_async)
+        # loss partial sums (global means of the mean-RGB term): all-reduced while the loss backward kernel runs;
+        # gradient of the shared texture: all-reduced while the geometry / hand-layer backward run (both no-ops at N=1)
+        step.backward(pose, betas, focal, prpp, root, shared_grad_hook=hdist.all_reduce_shared_grads_async,
+                      sums_hook=hdist.all_reduce_loss_sums_async)
 
     def barrier():
         if world > 1:
@@ -287,12 +288,12 @@ def run_ours(args, cfg):
                                                                  step.verts_rel, step.verts_view, step.verts_ndc,
                                                                  step.vnormals, step.face_verts)))
         ev.append(timed("raster_shade_fwd", lambda: step.launch_raster_shade(ldir, lcol, imgs)))
-        step.sums.zero_()
+        if not step.deterministic:
+            step.sums.zero_()
         ev.append(timed("loss_fwd", lambda: L.call("hfr_loss_forward", step._loss_args)))
-        lb = L.HfrLossBwdArgs(step._loss_args, L.ptr(step.w), L.ptr(step.gauss), step.n_global * 3 * S * S, step.n_global,
-                              L.ptr(step.g_image), None)
-        ev.append(timed("loss_bwd", lambda: L.call("hfr_loss_backward", lb)))
-        step.acc.zero_()
+        ev.append(timed("loss_bwd", lambda: step.launch_loss_backward()))
+        if not step.tiled:
+            step.acc.zero_()
         ev.append(timed("shade_raster_bwd", lambda: step.launch_shade_backward()))
         ev.append(timed("geom_bwd", lambda: step.launch_geom_backward(focal, prpp, root)))
         ev.append(timed("mano_bwd", lambda: ops.mano_backward_raw(step.hm, pose, betas, None, step.g_verts, None,

@@ -99,12 +99,13 @@ class HfrShadeBwdTiledArgs(C.Structure):
     _fields_ = [("f", HfrShadeFwdArgs), ("g_image", vp), ("verts_ndc", vp), ("focal", vp), ("blur_radius", f32),
                 ("perspective_correct", i32), ("clip_barycentric", i32), ("raster_ws", vp), ("face_rec", vp),
                 ("rec_cap", i64), ("light_acc", vp), ("tex_acc", vp), ("g_texture", vp), ("fx_scale", vp), ("status", vp),
-                ("pool_aa", i32), ("pool_binarize", i32)]
+                ("pool_aa", i32), ("pool_binarize", i32), ("gmax_bits", vp), ("fix_sums", vp), ("fix_w", vp),
+                ("fix_image", vp), ("fix_inv_scale", f32), ("fix_count", i64)]
 
 
 class HfrGradFinishArgs(C.Structure):
     _fields_ = [("tex_acc", vp), ("g_texture", vp), ("n_tex", i64), ("light_acc", vp), ("g_light_dir", vp),
-                ("g_light_color", vp), ("N", i32), ("fx_scale", vp)]
+                ("g_light_color", vp), ("N", i32), ("fx_scale", vp), ("gmax_bits", vp)]
 
 
 class HfrRasterShadeArgs(C.Structure):
@@ -129,12 +130,12 @@ class HfrPoolBwdArgs(C.Structure):
 class HfrLossArgs(C.Structure):
     _fields_ = [("N", i32), ("H", i32), ("W", i32), ("sil_scale", f32), ("want_ssim", i32), ("want_grad", i32), ("nhwc", i32),
                 ("re_img", vp), ("re_sil", vp), ("imgs", vp), ("seg", vp), ("sums", vp), ("gauss", vp), ("dmaps", vp),
-                ("tile_flags", vp), ("mask_mode", i32), ("imgs_u8", vp), ("seg_u8", vp)]
+                ("tile_flags", vp), ("mask_mode", i32), ("imgs_u8", vp), ("seg_u8", vp), ("partials", vp), ("ticket", vp)]
 
 
 class HfrLossBwdArgs(C.Structure):
     _fields_ = [("f", HfrLossArgs), ("w", vp), ("gauss", vp), ("count_global", i64), ("n_global", i32), ("g_re_img", vp), ("g_re_sil", vp),
-                ("tex_con", vp), ("self_norm", vp)]
+                ("tex_con", vp), ("self_norm", vp), ("tile_box", vp), ("box_aa", i32), ("skip_mrgb", i32), ("gmax_bits", vp)]
 
 
 class HfrKeypointArgs(C.Structure):
@@ -162,6 +163,7 @@ ENTRY_POINTS = [
     "hfr_raster_backward", "hfr_raster_tile_box", "hfr_shade_forward", "hfr_shade_backward", "hfr_raster_shade_forward",
     "hfr_raster_shade_pool_forward", "hfr_face_attr_forward", "hfr_pool_forward", "hfr_pool_backward", "hfr_loss_forward", "hfr_loss_backward",
     "hfr_keypoint_forward", "hfr_keypoint_backward", "hfr_shade_backward_tiled", "hfr_grad_finish",
+    "hfr_loss_partials_floats",
 ]
 
 _lib = None
@@ -184,6 +186,8 @@ def lib() -> C.CDLL:
         _lib.hfr_raster_workspace_bytes.argtypes = [C.c_int64]
         _lib.hfr_raster_tile_box.restype = C.c_void_p
         _lib.hfr_raster_tile_box.argtypes = [C.c_void_p, C.c_int64, C.c_int32]
+        _lib.hfr_loss_partials_floats.restype = C.c_int64
+        _lib.hfr_loss_partials_floats.argtypes = [C.c_int32, C.c_int32, C.c_int32]
         if _lib.hfr_abi_version() != ABI_VERSION:
             raise HfrError("libhifihr_b200.so ABI version mismatch")
     return _lib

@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(kLossThreads, 3) loss_fwd_kernel(HfrLossArgs a
       }
     }
   }
-  // ---- block reduction of the 7 partial sums: one atomic each per CTA -------------------------------
+  // ---- block reduction of the partial sums -------------------------------------------------------------------
   float vals[8] = {l1, sr, st, sl, ss, mul, add, l2};
   constexpr int NV = METRIC ? 8 : 7;
 #pragma unroll
@@ -328,13 +328,67 @@ __global__ void __launch_bounds__(kLossThreads, 3) loss_fwd_kernel(HfrLossArgs a
     for (int i = 0; i < NV; ++i) red[warp][i] = vals[i];
   }
   __syncthreads();
-  if (tid < NV) {
-    float t = 0.f;
+  float t = 0.f;
+  if (tid < 8) {
 #pragma unroll
-    for (int w = 0; w < kLossThreads / 32; ++w) t += red[w][tid];
-    int dst = tid < 5 ? tid : (tid == 5 ? HFR_LOSS_NSUMS + n : (tid == 6 ? HFR_LOSS_NSUMS + a.N + n : HFR_LOSS_L2));
-    if (SELF) dst = tid == 0 ? HFR_LOSS_NSUMS + n : (tid == 1 ? HFR_LOSS_NSUMS + a.N + n : (tid == 2 ? HFR_LOSS_NSUMS + 2 * a.N + n : (tid == 4 ? HFR_LOSS_SSIM : -1)));
-    if (t != 0.0f && dst >= 0) atomicAdd(a.sums + dst, t);
+    for (int w = 0; w < kLossThreads / 32; ++w) t += tid < NV ? red[w][tid] : 0.f;
+  }
+  // where component `comp` of sample `n` goes (-1: unused), and whether it is a per-sample sum
+  auto dst_of = [&](int comp, int nn) -> int {
+    if (SELF) return comp == 0 ? HFR_LOSS_NSUMS + nn : (comp == 1 ? HFR_LOSS_NSUMS + a.N + nn : (comp == 2 ? HFR_LOSS_NSUMS + 2 * a.N + nn : (comp == 4 ? HFR_LOSS_SSIM : -1)));
+    return comp < 5 ? comp : (comp == 5 ? HFR_LOSS_NSUMS + nn : (comp == 6 ? HFR_LOSS_NSUMS + a.N + nn : (METRIC ? HFR_LOSS_L2 : -1)));
+  };
+  auto per_sample = [&](int comp) -> bool { return SELF ? comp < 3 : (comp == 5 || comp == 6); };
+  if (!a.partials) {      // one fp32 atomic per CTA and component: fast, order-dependent in the last bits
+    if (tid < NV) {
+      const int dst = dst_of(tid, n);
+      if (t != 0.0f && dst >= 0) atomicAdd(a.sums + dst, t);
+    }
+    return;
+  }
+  // deterministic variant: every CTA leaves its 8 partial sums in a workspace row, the LAST CTA to arrive (ticket)
+  // adds all rows in a fixed order and WRITES sums (no atomics on floating point, no zeroing needed by the caller)
+  __shared__ int s_last;
+  float (*s_tot)[8] = reinterpret_cast<float (*)[8]>(lsm);      // the stencil's shared arrays are dead by now
+  const int ctas_per_sample = gridDim.x * gridDim.y, n_cta = ctas_per_sample * gridDim.z;
+  const int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  if (tid < 8) a.partials[(size_t)cta * 8 + tid] = t;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = atomicAdd(a.ticket, 1u) == (unsigned)(n_cta - 1);
+  __syncthreads();             // (also: every thread is done with the stencil arrays that s_tot aliases)
+  if (!s_last) return;
+  __threadfence();
+  {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int r = tid; r < n_cta; r += kLossThreads) {
+      const float4 q0 = __ldcg(reinterpret_cast<const float4*>(a.partials + (size_t)r * 8));
+      const float4 q1 = __ldcg(reinterpret_cast<const float4*>(a.partials + (size_t)r * 8 + 4));
+      acc[0] += q0.x; acc[1] += q0.y; acc[2] += q0.z; acc[3] += q0.w; acc[4] += q1.x; acc[5] += q1.y; acc[6] += q1.z; acc[7] += q1.w;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s_tot[tid][i] = acc[i];
+    __syncthreads();
+    for (int o = kLossThreads / 2; o > 0; o >>= 1) {
+      if (tid < o) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s_tot[tid][i] += s_tot[tid + o][i];
+      }
+      __syncthreads();
+    }
+    if (tid < 8 && !per_sample(tid)) {
+      const int dst = dst_of(tid, 0);
+      if (dst >= 0) a.sums[dst] = s_tot[0][tid];
+    }
+    // per-sample sums: the CTAs of a sample are consecutive rows
+    for (int i = tid; i < a.N * 8; i += kLossThreads) {
+      const int nn = i >> 3, comp = i & 7;
+      if (!per_sample(comp)) continue;
+      float sacc = 0.f;
+      for (int r = 0; r < ctas_per_sample; ++r) sacc += __ldcg(a.partials + ((size_t)nn * ctas_per_sample + r) * 8 + comp);
+      a.sums[dst_of(comp, nn)] = sacc;
+    }
+    if (tid == 0) *a.ticket = 0u;     // ready for the next launch
   }
 }
 
@@ -353,6 +407,14 @@ __global__ void __launch_bounds__(kLossThreads, HFR_LOSSB_MINB) loss_bwd_kernel(
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = blockIdx.z, x0 = blockIdx.x * kLT, y0 = blockIdx.y * kLT;
   const size_t hw = (size_t)a.H * a.W;
+  if (b.tile_box) {
+    // Only pixels that hold a fragment pass their gradient on: a 32x32 tile whose rasterizer tiles (16x16 at the
+    // rasterised resolution, box_aa x finer than the loss resolution) all lie outside the mesh's tile box is skipped.
+    const uint4 bx = __ldg(reinterpret_cast<const uint4*>(b.tile_box) + n);
+    const int aa = b.box_aa > 1 ? b.box_aa : 1;
+    const int tx0 = (x0 * aa) >> 4, tx1 = ((x0 + kLT) * aa - 1) >> 4, ty0 = (y0 * aa) >> 4, ty1 = ((y0 + kLT) * aa - 1) >> 4;
+    if (tx1 < (int)bx.x || tx0 > 255 - (int)bx.y || ty1 < (int)bx.z || ty0 > 255 - (int)bx.w) return;
+  }
   bool ssim = a.want_ssim && a.dmaps;
   if (ssim && a.tile_flags) {
     // d(SSIM)/dx at a pixel is r0 + 2 x r1 + y r2 with r = Gauss * dmaps: when x and y vanish within 12 pixels
@@ -373,8 +435,11 @@ __global__ void __launch_bounds__(kLossThreads, HFR_LOSSB_MINB) loss_bwd_kernel(
   }
   const float w_tex = __ldg(b.w), w_mrgb = __ldg(b.w + 1), w_ssim = __ldg(b.w + 2), w_sil = __ldg(b.w + 3), w_iou = __ldg(b.w + 4);
   const float cnt = (float)b.count_global, icnt = 1.0f / cnt;
-  const float mR = a.sums[HFR_LOSS_SUM_R] * icnt, mT = a.sums[HFR_LOSS_SUM_T] * icnt;
-  float k_mrgb = w_mrgb * 2.0f * (mT - mR) * (-icnt);
+  // (the global sums may be in flight in an all-reduce when skip_mrgb is set: they are not touched then)
+  const float mR = b.skip_mrgb ? 0.f : a.sums[HFR_LOSS_SUM_R] * icnt, mT = b.skip_mrgb ? 0.f : a.sums[HFR_LOSS_SUM_T] * icnt;
+  // skip_mrgb: the mean-RGB term's gradient is a per-step scalar times (alpha, rgb); the fused backward adds it from
+  // the (all-reduced) sums, so that this kernel does not have to wait for them
+  float k_mrgb = b.skip_mrgb ? 0.0f : w_mrgb * 2.0f * (mT - mR) * (-icnt);
   float k_l1 = w_tex * icnt;
   if (SELF) {
     // texture_self = sum_n c_n^2 sum|x - y| / (3HW sum_n c_n^2); mrgb_self = sum_n c_n^2 |mean_n x - mean_n y| / sum_n c_n^2
@@ -535,6 +600,15 @@ __global__ void __launch_bounds__(kLossThreads, HFR_LOSSB_MINB) loss_bwd_kernel(
       if (in[o] && !SELF) gsil[o] += grim * rim * inv_scale;
     }
   }
+  if (b.gmax_bits) {   // max |gradient| of this launch (positive floats order like their bit patterns): order-independent
+    float m = 0.f;
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+      if (in[o]) m = fmaxf(fmaxf(fmaxf(m, fabsf(grgb[o][0])), fmaxf(fabsf(grgb[o][1]), fabsf(grgb[o][2]))), fabsf(gsil[o]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0 && m > 0.f) atomicMax(b.gmax_bits, __float_as_uint(m));
+  }
 #pragma unroll
   for (int o = 0; o < 4; ++o) {
     if (in[o]) {
@@ -574,6 +648,11 @@ extern "C" int hfr_pool_backward(const HfrPoolBwdArgs* a, void* stream) {
   return HFR_OK;
 }
 
+extern "C" int64_t hfr_loss_partials_floats(int32_t N, int32_t H, int32_t W) {
+  using namespace hfr;
+  return (int64_t)N * ((W + kLT - 1) / kLT) * ((H + kLT - 1) / kLT) * 8;
+}
+
 extern "C" int hfr_loss_forward(const HfrLossArgs* a, void* stream) {
   using namespace hfr;
   HFR_CHECK_ARG(a && a->N >= 0 && a->H > 0 && a->W > 0 && a->sil_scale > 0.f, "loss_forward: bad dims");
@@ -582,6 +661,8 @@ extern "C" int hfr_loss_forward(const HfrLossArgs* a, void* stream) {
   HFR_CHECK_ARG(!a->want_ssim || a->gauss, "loss_forward: SSIM needs the Gaussian taps");
   dim3 grid((a->W + kLT - 1) / kLT, (a->H + kLT - 1) / kLT, a->N);
   HFR_CHECK_ARG(a->mask_mode >= 0 && a->mask_mode <= 3, "loss_forward: mask_mode must be 0..3");
+  HFR_CHECK_ARG(!a->partials || (a->ticket && (reinterpret_cast<uintptr_t>(a->partials) & 15) == 0),
+                "loss_forward: the deterministic reduction needs a 16-byte aligned partials workspace and a ticket word");
   HFR_CHECK_ARG(a->mask_mode == 0 || a->mask_mode == 3 || !(a->want_grad && a->dmaps), "loss_forward: the metric modes have no backward");
   static bool attr_set = false;   // benign race: the attribute is idempotent
   if (!attr_set) {

@@ -97,6 +97,23 @@ HFR_HD bool hfr_raster_eval(float px, float py, const float* v, float blur_radiu
 }
 
 // ------------------------------------------------------------------------------------ backward
+// Plain-arithmetic variants for the backward (FMA contraction allowed, no IEEE division): gradients need fp32
+// accuracy, not the forward's bit pattern.
+HFR_HD float hfr_edge_f(float px, float py, float ax, float ay, float bx, float by) {
+  return (px - ax) * (by - ay) - (py - ay) * (bx - ax);
+}
+HFR_HD float hfr_seg_dist2_f(float px, float py, float ax, float ay, float bx, float by) {
+  const float bax = bx - ax, bay = by - ay;
+  const float l2 = bax * bax + bay * bay;
+  if (l2 <= HFR_KEPS) {
+    const float ex = px - bx, ey = py - by;
+    return ex * ex + ey * ey;
+  }
+  const float t = hfr_clamp01(HFR_FDIV(bax * (px - ax) + bay * (py - ay), l2));
+  const float dx = ax + t * bax - px, dy = ay + t * bay - py;
+  return dx * dx + dy * dy;
+}
+
 // d(seg_dist2)/d(a,b) accumulated into ga[2], gb[2] with upstream g.
 HFR_HD void hfr_seg_dist2_bwd(float px, float py, float ax, float ay, float bx, float by, float g, float* ga,
                               float* gb) {
@@ -130,9 +147,9 @@ HFR_HD void hfr_seg_dist2_bwd(float px, float py, float ax, float ay, float bx, 
 HFR_HD void hfr_raster_eval_bwd(float px, float py, const float* v, int pc, int clip, const float* g_bc, float g_pz,
                                 float g_sd, float* gv) {
   const float x0 = v[0], y0 = v[1], z0 = v[2], x1 = v[3], y1 = v[4], z1 = v[5], x2 = v[6], y2 = v[7], z2 = v[8];
-  const float area = hfr_edge(x2, y2, x0, y0, x1, y1) + HFR_KEPS;
-  const float E0 = hfr_edge(px, py, x1, y1, x2, y2), E1 = hfr_edge(px, py, x2, y2, x0, y0),
-              E2 = hfr_edge(px, py, x0, y0, x1, y1);
+  const float area = hfr_edge_f(x2, y2, x0, y0, x1, y1) + HFR_KEPS;
+  const float E0 = hfr_edge_f(px, py, x1, y1, x2, y2), E1 = hfr_edge_f(px, py, x2, y2, x0, y0),
+              E2 = hfr_edge_f(px, py, x0, y0, x1, y1);
   const float ia = HFR_RCP(area);
   const float w0 = E0 * ia, w1 = E1 * ia, w2 = E2 * ia;
   float b0 = w0, b1 = w1, b2 = w2, t0 = 0.f, t1 = 0.f, t2 = 0.f, tsum = 0.f, den = 1.f;
@@ -188,8 +205,8 @@ HFR_HD void hfr_raster_eval_bwd(float px, float py, const float* v, int pc, int 
   gx2 += garea * (y1 - y0); gy2 += garea * -(x1 - x0);
   // signed distance: first-match priority e01, e02, e12
   if (g_sd != 0.0f) {
-    const float e01 = hfr_seg_dist2(px, py, x0, y0, x1, y1), e02 = hfr_seg_dist2(px, py, x0, y0, x2, y2),
-                e12 = hfr_seg_dist2(px, py, x1, y1, x2, y2);
+    const float e01 = hfr_seg_dist2_f(px, py, x0, y0, x1, y1), e02 = hfr_seg_dist2_f(px, py, x0, y0, x2, y2),
+                e12 = hfr_seg_dist2_f(px, py, x1, y1, x2, y2);
     const float g = inside ? -g_sd : g_sd;
     float ga[2] = {0.f, 0.f}, gb[2] = {0.f, 0.f};
     if (e01 <= e02 && e01 <= e12) {

@@ -27,34 +27,30 @@ namespace hfr {
 
 constexpr int kBT = 256;         // threads = pixels of one 16x16 tile; thread t <-> pixel (warp = 8x4 block, as the forward)
 constexpr int kBW = kBT / 32;
-constexpr int kCap = 256;        // distinct faces per pass (a tile with more is processed in several passes)
+constexpr int kCap = 128;        // distinct faces per pass (a tile with more is processed in several passes)
 constexpr int kNC = 24;          // components summed per face: 18 vertex + 3 light direction / location + 3 light colour
+constexpr int kFR = 36;          // words per staged face record (144 B: LDS.128 rows of different faces spread over the banks)
 constexpr uint16_t kNoFrag = 0xffffu;
-
-template <int KMAX>
-struct TCfg {
-  static constexpr int HT = KMAX <= 1 ? 512 : (KMAX <= 2 ? 1024 : (KMAX <= 4 ? 2048 : (KMAX <= 8 ? 4096 : 8192)));   // >= 2 x 256 K
-};
+constexpr int kMaxFacesTiled = 65535;   // local face ids and slots are 16-bit
 
 template <int KMAX>
 struct TSmem {
-  int keys[TCfg<KMAX>::HT];               // hash set of the faces (local id) present in the tile, -1 = empty
-  uint16_t slotmap[TCfg<KMAX>::HT];       // table entry -> dense slot
+  __align__(16) float facerec[kCap][kFR]; // per face of the pass: view xyz x3, normals x3, uv x3, ndc xy x3, record slot
+  float stage[kBW][kNC][33];              // per warp: the chunk's components, transposed for the per-face chains
+  float part[KMAX * 8][2][kNC];           // per chunk: partial sums of a face that continues from / into a neighbour chunk
+  float pix[7][kBT];                      // per pixel: gnum[3], gden, g_alpha, gzmax, kmax (int bits)
+  float frag[KMAX][3][kBT];               // per fragment: sigmoid prob, softmax exponent, prod_{j != k} (1 - p_j)
   uint32_t masks[kCap][8];                // per slot of the pass: which of the 256 pixels hold that face
   int offs[kCap + 1];                     // exclusive prefix of the slots' fragment counts
   uint16_t sorted[KMAX * kBT];            // fragments (pixel | k << 8) grouped by slot, pixel order inside a slot
-  uint16_t fragh[KMAX][kBT];              // table entry of every fragment (kNoFrag: carries no gradient)
-  float pix[8][kBT];                      // per pixel: gnum[3], gden, g_alpha, gzmax, kmax (int bits), spare
-  float frag[KMAX][3][kBT];               // per fragment: sigmoid prob, softmax exponent, prod_{j != k} (1 - p_j)
-  float stage[kBW][kNC][33];              // per warp: the chunk's components, transposed for the per-face chains
+  uint16_t fragslot[KMAX][kBT];           // canonical slot of every fragment (kNoFrag: carries no gradient)
+  uint16_t slotface[KMAX * kBT];          // slot -> face id within the mesh
+  uint8_t cflag[KMAX * 8];                // per chunk: bit 0 head partial present, bit 1 tail partial, bit 2 whole chunk is one open run
   float tabx[kTileW], taby[kTileH];       // NDC sample positions of the tile's columns / rows
   int wsum[kBW];
-  int wstart[kBW + 1];
   unsigned long long light[6];            // fixed-point light sums of the tile
-  int misc[4];
+  int next_chunk;
 };
-
-__device__ __forceinline__ uint32_t hash_face(int f) { return (uint32_t)f * 2654435761u; }
 
 // block-wide exclusive scan of one int per thread (kBT threads); returns the exclusive prefix, *total = sum
 __device__ __forceinline__ int block_excl_scan(int v, int* wsum, int* total) {
@@ -75,12 +71,36 @@ __device__ __forceinline__ int block_excl_scan(int v, int* wsum, int* total) {
   return before + incl - v;
 }
 
+// a finished face: 18 floats into its (face, tile) record, the 6 light components into the tile's fixed-point sums
+__device__ __forceinline__ void flush_face(const HfrShadeBwdTiledArgs& a, unsigned long long* light, long long rec, int lane,
+                                           float tot, float fxs) {
+  if (lane < HFR_FACE_REC_FLOATS) {
+    if (rec < a.rec_cap) a.face_rec[rec * HFR_FACE_REC_FLOATS + lane] = tot;
+    else if (lane == 0) atomicOr(a.status, 1u);
+  } else if (lane < kNC && tot != 0.0f) {
+    atomicAdd(&light[lane - HFR_FACE_REC_FLOATS], (unsigned long long)__float2ll_rn(tot * fxs));
+  }
+}
+
+// fixed-point multiplier from the largest gradient magnitude: 2^34 over the power of two above it
+__device__ __forceinline__ float fx_from_gmax(float g) {
+  if (!(g > 1e-37f) || !(g < 1e37f)) g = 1.0f;
+  const unsigned bits = __float_as_uint(g);
+  int e = (int)((bits >> 23) & 255u) - 127 + ((bits & 0x7fffffu) ? 1 : 0);
+  e = max(-90, min(90, 34 - e));
+  return __uint_as_float((unsigned)(127 + e) << 23);
+}
+
+#ifndef HFR_TILED_MINB
+#define HFR_TILED_MINB 2
+#endif
 template <int KMAX>
-__global__ void __launch_bounds__(kBT, (KMAX <= 1 ? 4 : (KMAX <= 4 ? 3 : (KMAX <= 8 ? 2 : 1))))
-shade_bwd_tiled_kernel(HfrShadeBwdTiledArgs a, WsLayout L) {
+__global__ void __launch_bounds__(kBT, (KMAX <= 4 ? HFR_TILED_MINB : 1))
+shade_bwd_tiled_kernel(HfrShadeBwdTiledArgs a, WsLayout L, int FW) {
   extern __shared__ __align__(16) unsigned char smraw[];
   TSmem<KMAX>& sm = *reinterpret_cast<TSmem<KMAX>*>(smraw);
-  constexpr int HT = TCfg<KMAX>::HT;
+  uint32_t* bitmap = reinterpret_cast<uint32_t*>(smraw + ((sizeof(TSmem<KMAX>) + 15) & ~(size_t)15));   // FW words: faces present in the tile
+  uint32_t* wprefix = bitmap + FW;                                                                     // FW words: set bits before each word
   const HfrShadeFwdArgs& f = a.f;
   const HfrShadeParams& P = f.p;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -97,7 +117,12 @@ shade_bwd_tiled_kernel(HfrShadeBwdTiledArgs a, WsLayout L) {
   const int kshade = phong ? (P.blend == HFR_BLEND_SOFTMAX ? K : 1) : 0;
   const size_t pix = ((size_t)n * P.H + yi) * P.W + xi;
 
-  for (int i = tid; i < HT; i += kBT) sm.keys[i] = -1;
+  float k_mrgb = 0.0f;
+  if (a.fix_sums) {
+    const float icnt = 1.0f / (float)a.fix_count;
+    k_mrgb = __ldg(a.fix_w + 1) * 2.0f * (__ldg(a.fix_sums + HFR_LOSS_SUM_T) - __ldg(a.fix_sums + HFR_LOSS_SUM_R)) * icnt * (-icnt);
+  }
+  for (int i = tid; i < FW; i += kBT) bitmap[i] = 0u;
   if (tid < kTileW) sm.tabx[tid] = hfr_pix_to_ndc(P.W - 1 - (tx * kTileW + tid), P.W, P.H);
   else if (tid < kTileW + kTileH) sm.taby[tid - kTileW] = hfr_pix_to_ndc(P.H - 1 - (ty * kTileH + tid - kTileW), P.H, P.W);
   if (tid < 6) sm.light[tid] = 0ull;
@@ -156,6 +181,16 @@ shade_bwd_tiled_kernel(HfrShadeBwdTiledArgs a, WsLayout L) {
       } else {
         g4 = __ldg(reinterpret_cast<const float4*>(a.g_image + pix * 4));
       }
+      if (a.fix_sums) {
+        // mean-RGB term (losses.py:369): d/d(rim) = k_mrgb for every pixel and channel with rim = rgb * alpha / scale,
+        // k_mrgb from the (all-reduced) sums - added here so that the loss backward never waits for the collective
+        const float4 im = __ldg(reinterpret_cast<const float4*>(a.fix_image + (a.pool_aa > 1
+            ? (((size_t)n * (P.H / a.pool_aa) + yi / a.pool_aa) * (P.W / a.pool_aa) + xi / a.pool_aa) : pix) * 4));
+        const float sc = a.pool_aa > 1 ? 1.0f / (float)(a.pool_aa * a.pool_aa) : 1.0f;
+        const float so = im.w * a.fix_inv_scale;
+        g4.x += k_mrgb * so * sc; g4.y += k_mrgb * so * sc; g4.z += k_mrgb * so * sc;
+        if (!(a.pool_aa > 1 && a.pool_binarize)) g4.w += k_mrgb * (im.x + im.y + im.z) * a.fix_inv_scale * sc;
+      }
       g_alpha = g4.w;
       if (P.blend == HFR_BLEND_HARD) {
         gnum[0] = g4.x; gnum[1] = g4.y; gnum[2] = g4.z;
@@ -213,34 +248,37 @@ shade_bwd_tiled_kernel(HfrShadeBwdTiledArgs a, WsLayout L) {
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) {
       sm.frag[k][0][tid] = prob[k]; sm.frag[k][1][tid] = wexp[k]; sm.frag[k][2][tid] = others[k];
-      uint16_t hh = kNoFrag;
-      if (((vmask >> k) & 1u) && (P.blend != HFR_BLEND_HARD || k == 0)) {   // hidden slots of a hard blend carry no gradient
-        uint32_t h = hash_face(fl[k]) & (HT - 1);
-        while (true) {
-          const int old = atomicCAS(&sm.keys[h], -1, fl[k]);
-          if (old == -1 || old == fl[k]) break;
-          h = (h + 1) & (HT - 1);
-        }
-        hh = (uint16_t)h;
-      }
-      sm.fragh[k][tid] = hh;
+      // hidden slots of a hard blend carry no gradient
+      if (!(((vmask >> k) & 1u) && (P.blend != HFR_BLEND_HARD || k == 0))) fl[k] = -1;
+      if (fl[k] >= 0) atomicOr(&bitmap[fl[k] >> 5], 1u << (fl[k] & 31));
     }
   }
   __syncthreads();
-  // dense slot numbers for the occupied table entries (their order is irrelevant: a face's sum is a sequential
-  // chain over ITS fragments in pixel order, wherever the face sits in the sorted list)
+  // canonical slot of a face = its rank among the faces present (bitmap order = face-id order): whatever order the
+  // atomics ran in, the sorted fragment list below comes out the same - so do the 32-fragment chunks
   int D = 0;
   {
-    constexpr int PER = HT / kBT;
+    const int per = (FW + kBT - 1) / kBT, w0 = tid * per, w1 = min(w0 + per, FW);
     int cnt = 0;
-#pragma unroll
-    for (int j = 0; j < PER; ++j) cnt += sm.keys[tid * PER + j] >= 0 ? 1 : 0;
+    for (int w = w0; w < w1; ++w) cnt += __popc(bitmap[w]);
     int q = block_excl_scan(cnt, sm.wsum, &D);
-#pragma unroll
-    for (int j = 0; j < PER; ++j)
-      if (sm.keys[tid * PER + j] >= 0) sm.slotmap[tid * PER + j] = (uint16_t)(q++);
+    for (int w = w0; w < w1; ++w) {
+      wprefix[w] = (uint32_t)q;
+      uint32_t bits = bitmap[w];
+      while (bits) {
+        const int bpos = __ffs(bits) - 1;
+        bits &= bits - 1;
+        sm.slotface[q++] = (uint16_t)(w * 32 + bpos);
+      }
+    }
   }
   __syncthreads();
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    uint16_t sl = kNoFrag;
+    if (fl[k] >= 0) sl = (uint16_t)(wprefix[fl[k] >> 5] + __popc(bitmap[fl[k] >> 5] & ((1u << (fl[k] & 31)) - 1u)));
+    sm.fragslot[k][tid] = sl;
+  }
 
   // per-sample light constants
   float dhat[3] = {0.f, 0.f, 0.f}, dlen = 1.f, lcol[3] = {0.f, 0.f, 0.f};
@@ -248,7 +286,13 @@ shade_bwd_tiled_kernel(HfrShadeBwdTiledArgs a, WsLayout L) {
     light_dir_hat(f, n, dhat, &dlen);
     lcol[0] = __ldg(f.light_color + 3 * n); lcol[1] = __ldg(f.light_color + 3 * n + 1); lcol[2] = __ldg(f.light_color + 3 * n + 2);
   }
-  const float fxs = __ldg(a.fx_scale);
+  float fxs;
+  if (a.gmax_bits) {       // every CTA derives the same multiplier; the first thread of each leaves it for hfr_grad_finish
+    fxs = fx_from_gmax(__uint_as_float(__ldg(a.gmax_bits)) + 4.0f * fabsf(k_mrgb));
+    if (tid == 0) *a.fx_scale = fxs;
+  } else {
+    fxs = *a.fx_scale;
+  }
   const float fcx = __ldg(a.focal + 2 * n), fcy = __ldg(a.focal + 2 * n + 1);
   const size_t tbase = (P.tex_n == 1 ? 0 : (size_t)n * P.tex_h * P.tex_w * 3);
   const float zr = P.zfar - P.znear;
@@ -257,14 +301,34 @@ shade_bwd_tiled_kernel(HfrShadeBwdTiledArgs a, WsLayout L) {
     const int Dp = min(kCap, D - p0);
     // ============================================================== 2. counting sort of the fragments by face
     for (int i = tid; i < Dp * 8; i += kBT) (&sm.masks[0][0])[i] = 0u;
+    if (tid == 0) sm.next_chunk = 0;
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) {
-      const uint16_t hh = sm.fragh[k][tid];
-      if (hh != kNoFrag) {
-        const int s = (int)sm.slotmap[hh] - p0;
-        if ((unsigned)s < (unsigned)Dp) atomicOr(&sm.masks[s][warp], 1u << lane);
+      const int s = (int)sm.fragslot[k][tid] - p0;
+      if ((unsigned)s < (unsigned)Dp) atomicOr(&sm.masks[s][warp], 1u << lane);
+    }
+    // stage the pass's faces: corner attributes and the record slot, one face per thread
+    if (tid < Dp) {
+      const int face = sm.slotface[p0 + tid];
+      float* r = sm.facerec[tid];
+      int vid[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) vid[c] = __ldg(f.faces + 3 * face + c);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float* __restrict__ x = f.verts_view + ((size_t)n * V + vid[c]) * 3;
+        const float* __restrict__ q = a.verts_ndc + ((size_t)n * V + vid[c]) * 3;
+        r[3 * c] = __ldg(x); r[3 * c + 1] = __ldg(x + 1); r[3 * c + 2] = __ldg(x + 2);
+        r[24 + 2 * c] = __ldg(q); r[25 + 2 * c] = __ldg(q + 1);
+        if (phong) {
+          const float* __restrict__ nn = f.vnormals + ((size_t)n * V + vid[c]) * 3;
+          const int t = __ldg(f.faces_uvs + 3 * face + c);
+          r[9 + 3 * c] = __ldg(nn); r[10 + 3 * c] = __ldg(nn + 1); r[11 + 3 * c] = __ldg(nn + 2);
+          r[18 + 2 * c] = __ldg(f.verts_uvs + 2 * t); r[19 + 2 * c] = __ldg(f.verts_uvs + 2 * t + 1);
+        }
       }
+      r[30] = __uint_as_float(face_rec_index(ws, L, (int64_t)n * P.F + face, tx, ty));
     }
     __syncthreads();
     int nfr = 0;
@@ -281,51 +345,37 @@ shade_bwd_tiled_kernel(HfrShadeBwdTiledArgs a, WsLayout L) {
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) {
-      const uint16_t hh = sm.fragh[k][tid];
-      if (hh != kNoFrag) {
-        const int s = (int)sm.slotmap[hh] - p0;
-        if ((unsigned)s < (unsigned)Dp) {
-          int rank = __popc(sm.masks[s][warp] & ((1u << lane) - 1u));
-          for (int w = 0; w < warp; ++w) rank += __popc(sm.masks[s][w]);
-          sm.sorted[sm.offs[s] + rank] = (uint16_t)(tid | (k << 8));
-        }
+      const int s = (int)sm.fragslot[k][tid] - p0;
+      if ((unsigned)s < (unsigned)Dp) {
+        int rank = __popc(sm.masks[s][warp] & ((1u << lane) - 1u));
+        for (int w = 0; w < warp; ++w) rank += __popc(sm.masks[s][w]);
+        sm.sorted[sm.offs[s] + rank] = (uint16_t)(tid | (k << 8));
       }
     }
-    // a warp owns WHOLE faces: those whose first fragment falls into its eighth of the sorted list
-    if (tid <= kBW) {
-      int st = nfr;
-      if (tid < kBW) {
-        const int target = (int)(((long long)tid * nfr) / kBW);
-        int lo = 0, hi = Dp;                 // first slot with offs >= target (offs is strictly increasing)
-        while (lo < hi) {
-          const int mid = (lo + hi) >> 1;
-          if (sm.offs[mid] >= target) hi = mid; else lo = mid + 1;
-        }
-        st = sm.offs[lo];
-      }
-      sm.wstart[tid] = st;
-    }
+    const int nch = (nfr + 31) >> 5;
+    if (tid < nch) sm.cflag[tid] = 0;
     __syncthreads();
 
-    // ============================================================== 3. differentiate, per-face sequential sums
-    const int beg = sm.wstart[warp], end = sm.wstart[warp + 1];
-    float tot = 0.0f;                 // lane c < kNC: running sum of component c of the open face
-    long long open_rec = -1;          // record slot of the open face (warp-uniform)
-    int prev_slot = -1;
-    for (int base = beg; base < end; base += 32) {
-      const int i = base + lane;
-      const bool valid = i < end;
+    // ============================================================== 3. differentiate 32 sorted fragments at a time
+    // Chunks are canonical (the sorted list is), so any warp may take any chunk: they are handed out dynamically.
+    // Inside a chunk lane c adds component c of each face's fragments one after the other; a face that lies wholly
+    // inside the chunk is finished there, a face cut by a chunk boundary leaves partial sums that the fix-up below
+    // joins in chunk order.
+    while (true) {
+      int c = 0;
+      if (lane == 0) c = atomicAdd(&sm.next_chunk, 1);
+      c = __shfl_sync(0xffffffffu, c, 0);
+      if (c >= nch) break;
+      const int i = c * 32 + lane;
+      const bool valid = i < nfr;
       int slot = -2;
-      long long rec = -1;
       float v[kNC];
 #pragma unroll
-      for (int c = 0; c < kNC; ++c) v[c] = 0.0f;
+      for (int q = 0; q < kNC; ++q) v[q] = 0.0f;
       if (valid) {
         const int e = sm.sorted[i], p = e & 255, k = e >> 8;
-        const uint16_t hh = sm.fragh[k][p];
-        slot = sm.slotmap[hh];
-        const int face = sm.keys[hh];
-        rec = (long long)face_rec_index(ws, L, (int64_t)n * P.F + face, tx, ty);
+        slot = (int)sm.fragslot[k][p] - p0;
+        const float4* __restrict__ r4 = reinterpret_cast<const float4*>(sm.facerec[slot]);
         const int pw = p >> 5, pl = p & 31;
         const int lx = (pw & 1) * 8 + (pl & 7), ly = (pw >> 1) * 4 + (pl >> 3);
         const size_t fpix = ((size_t)n * P.H + (ty * kTileH + ly)) * P.W + (tx * kTileW + lx);
@@ -339,18 +389,19 @@ shade_bwd_tiled_kernel(HfrShadeBwdTiledArgs a, WsLayout L) {
         float gprob = sm.pix[4][p] * sm.frag[k][2][p], gz = 0.f;
         float g_bc[3] = {0.f, 0.f, 0.f}, col[3] = {1.0f, 1.0f, 1.0f}, gcol[3];
         FragGeom g;
+        {
+          const float4 q0 = r4[0], q1 = r4[1];
+          g.X[0] = q0.x; g.X[1] = q0.y; g.X[2] = q0.z; g.X[3] = q0.w; g.X[4] = q1.x; g.X[5] = q1.y; g.X[6] = q1.z; g.X[7] = q1.w;
+          g.X[8] = sm.facerec[slot][8];
+        }
         HfrTexTap tap; HfrPhongCtx ctx; float texel[3];
         const bool shaded = k < kshade;
         if (shaded) {
-          gather_frag(f, n, face, g);
+          const float4 q2 = r4[2], q3 = r4[3], q4 = r4[4], q5 = r4[5];
+          g.Nv[0] = q2.y; g.Nv[1] = q2.z; g.Nv[2] = q2.w; g.Nv[3] = q3.x; g.Nv[4] = q3.y; g.Nv[5] = q3.z; g.Nv[6] = q3.w;
+          g.Nv[7] = q4.x; g.Nv[8] = q4.y;
+          g.uv[0] = q4.z; g.uv[1] = q4.w; g.uv[2] = q5.x; g.uv[3] = q5.y; g.uv[4] = q5.z; g.uv[5] = q5.w;
           shade_fragment<false>(f, n, g, bc, dhat, lcol, col, &tap, &ctx, texel);
-        } else {
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            g.vid[c] = __ldg(f.faces + 3 * face + c);
-            const float* __restrict__ x = f.verts_view + ((size_t)n * V + g.vid[c]) * 3;
-            g.X[3 * c] = __ldg(x); g.X[3 * c + 1] = __ldg(x + 1); g.X[3 * c + 2] = __ldg(x + 2);
-          }
         }
         if (P.blend == HFR_BLEND_SOFTMAX) {
           const float wk = pk * ek;
@@ -400,17 +451,17 @@ shade_bwd_tiled_kernel(HfrShadeBwdTiledArgs a, WsLayout L) {
                        gNn[0] * g.Nv[3 * c3] + gNn[1] * g.Nv[3 * c3 + 1] + gNn[2] * g.Nv[3 * c3 + 2] +
                        gu * g.uv[2 * c3] + gv * g.uv[2 * c3 + 1];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) { v[6 * c3 + c] = bc[c3] * gP[c]; v[6 * c3 + 3 + c] = bc[c3] * gNn[c]; }
+            for (int q = 0; q < 3; ++q) { v[6 * c3 + q] = bc[c3] * gP[q]; v[6 * c3 + 3 + q] = bc[c3] * gNn[q]; }
           }
         }
         const float gd = P.blend == HFR_BLEND_HARD ? 0.f : HFR_FDIV(-gprob * pk * (1.0f - pk), P.sigma);
-        // rasterizer backward on the face's NDC vertices, then d(ndc)/d(view) per corner:
+        // rasterizer backward on the face's NDC vertices (z_ndc = view z), then d(ndc)/d(view) per corner:
         //   x = fx X / Z + px,  y = fy Y / Z + py,  z = Z
         float vv[9], gvv[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int c3 = 0; c3 < 3; ++c3) {
-          const float* __restrict__ src = a.verts_ndc + ((size_t)n * V + g.vid[c3]) * 3;
-          vv[3 * c3] = __ldg(src); vv[3 * c3 + 1] = __ldg(src + 1); vv[3 * c3 + 2] = __ldg(src + 2);
+        {
+          const float4 q6 = r4[6];
+          const float2 q7 = *reinterpret_cast<const float2*>(sm.facerec[slot] + 28);
+          vv[0] = q6.x; vv[1] = q6.y; vv[2] = g.X[2]; vv[3] = q6.z; vv[4] = q6.w; vv[5] = g.X[5]; vv[6] = q7.x; vv[7] = q7.y; vv[8] = g.X[8];
         }
         hfr_raster_eval_bwd(xf, yf, vv, a.perspective_correct, a.clip_barycentric, g_bc, gz, gd, gvv);
 #pragma unroll
@@ -422,46 +473,60 @@ shade_bwd_tiled_kernel(HfrShadeBwdTiledArgs a, WsLayout L) {
           v[6 * c3 + 2] += gvv[3 * c3 + 2] - (ax * X + ay * Y) * iz;
         }
       }
-      // stage the components, then lane c walks the chunk's members of each face in order
+      // stage the components, then lane q walks the chunk's members of each face in order
 #pragma unroll
-      for (int c = 0; c < kNC; ++c) sm.stage[warp][c][lane] = v[c];
+      for (int q = 0; q < kNC; ++q) sm.stage[warp][q][lane] = v[q];
       __syncwarp();
+      const int cnt = min(32, nfr - c * 32);
+      // does the first face continue from the previous chunk / the last one into the next?
+      int prev_slot = -1, next_slot = -1;
+      if (c > 0) { const int e = sm.sorted[c * 32 - 1]; prev_slot = (int)sm.fragslot[e >> 8][e & 255] - p0; }
+      if (c * 32 + 32 < nfr) { const int e = sm.sorted[c * 32 + 32]; next_slot = (int)sm.fragslot[e >> 8][e & 255] - p0; }
       const int up = __shfl_up_sync(0xffffffffu, slot, 1);
-      const bool starts = valid && (lane == 0 ? slot != prev_slot : slot != up);
+      const bool starts = valid && (lane == 0 || slot != up);
       const unsigned sb = __ballot_sync(0xffffffffu, starts);
-      const int cnt = __popc(__ballot_sync(0xffffffffu, valid));
+      const int first_slot = __shfl_sync(0xffffffffu, slot, 0), last_slot = __shfl_sync(0xffffffffu, slot, cnt - 1);
+      const bool head_cont = first_slot == prev_slot, tail_cont = last_slot == next_slot;
       int m = 0;
+      unsigned flags = 0;
       while (m < cnt) {
-        if ((sb >> m) & 1u) {      // a new face starts at member m: write out the open one
-          if (open_rec >= 0) {
-            if (lane < HFR_FACE_REC_FLOATS) {
-              if (open_rec < a.rec_cap) a.face_rec[open_rec * HFR_FACE_REC_FLOATS + lane] = tot;
-              else if (lane == 0) atomicOr(a.status, 1u);
-            } else if (lane < kNC && tot != 0.0f) {
-              atomicAdd(&sm.light[lane - HFR_FACE_REC_FLOATS], (unsigned long long)__float2ll_rn(tot * fxs));
-            }
-          }
-          tot = 0.0f;
-          open_rec = __shfl_sync(0xffffffffu, rec, m);
-        }
         const unsigned nxt = sb & ~((2u << m) - 1u);
         const int m1 = nxt ? __ffs(nxt) - 1 : cnt;
+        float tot = 0.0f;
         if (lane < kNC)
           for (int j = m; j < m1; ++j) tot += sm.stage[warp][lane][j];
+        const bool is_head = (m == 0) && head_cont, is_tail = (m1 == cnt) && tail_cont;
+        if (is_head) {                         // (a run that is head AND tail fills the whole chunk: flag bit 2)
+          if (lane < kNC) sm.part[c][0][lane] = tot;
+          flags |= 1u | (is_tail ? 4u : 0u);
+        } else if (is_tail) {
+          if (lane < kNC) sm.part[c][1][lane] = tot;
+          flags |= 2u;
+        } else {
+          const int sl = __shfl_sync(0xffffffffu, slot, m);
+          flush_face(a, sm.light, (long long)__float_as_uint(sm.facerec[sl][30]), lane, tot, fxs);
+        }
         m = m1;
       }
-      prev_slot = __shfl_sync(0xffffffffu, slot, cnt - 1);
+      if (lane == 0) sm.cflag[c] = (uint8_t)flags;
       __syncwarp();
     }
-    if (open_rec >= 0) {
-      if (lane < HFR_FACE_REC_FLOATS) {
-        if (open_rec < a.rec_cap) a.face_rec[open_rec * HFR_FACE_REC_FLOATS + lane] = tot;
-        else if (lane == 0) atomicOr(a.status, 1u);
-      } else if (lane < kNC && tot != 0.0f) {
-        atomicAdd(&sm.light[lane - HFR_FACE_REC_FLOATS], (unsigned long long)__float2ll_rn(tot * fxs));
+    __syncthreads();
+    // fix-up: a face cut by chunk boundaries = tail partial of its first chunk + the whole-chunk partials in between +
+    // head partial of its last chunk, added in chunk order (canonical, so the rounding is too)
+    for (int t = tid; t < nch * 32; t += kBT) {
+      const int c = t >> 5, q = t & 31;
+      if (q < kNC && (sm.cflag[c] & 2u)) {
+        float tot = sm.part[c][1][q];
+        int cc = c + 1;
+        while (sm.cflag[cc] & 4u) { tot += sm.part[cc][0][q]; ++cc; }
+        tot += sm.part[cc][0][q];
+        const int e = sm.sorted[min(c * 32 + 31, nfr - 1)];
+        const int sl = (int)sm.fragslot[e >> 8][e & 255] - p0;
+        flush_face(a, sm.light, (long long)__float_as_uint(sm.facerec[sl][30]), q, tot, fxs);
       }
     }
-    __syncthreads();     // the next pass reuses masks / sorted
+    __syncthreads();     // the next pass reuses masks / sorted / facerec
   }
   if (tid < 6 && a.light_acc && sm.light[tid] != 0ull)
     atomicAdd(reinterpret_cast<unsigned long long*>(a.light_acc) + (size_t)n * 6 + tid, sm.light[tid]);
@@ -477,7 +542,8 @@ __global__ void __launch_bounds__(256) face_rec_zero_kernel(float* __restrict__ 
 }
 
 __global__ void __launch_bounds__(256) grad_finish_kernel(HfrGradFinishArgs a) {
-  const float inv = 1.0f / __ldg(a.fx_scale);     // a power of two: exact
+  const float inv = 1.0f / *a.fx_scale;     // a power of two: exact
+  if (a.gmax_bits && blockIdx.x == 0 && threadIdx.x == 0) *a.gmax_bits = 0u;
   const int64_t nl = a.light_acc ? (int64_t)a.N * 6 : 0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n_tex + nl; i += (int64_t)gridDim.x * blockDim.x) {
     if (i < a.n_tex) {
@@ -512,10 +578,13 @@ extern "C" int hfr_shade_backward_tiled(const HfrShadeBwdTiledArgs* a, void* str
   HFR_CHECK_ARG(p.blend != HFR_BLEND_SOFTMAX || a->f.image, "shade_backward_tiled: the softmax blend needs the forward image");
   HFR_CHECK_ARG(p.tex_pca == 0, "shade_backward_tiled: PCA textures are differentiated by hfr_shade_backward");
   HFR_CHECK_ARG(p.shade != HFR_SHADE_PHONG_UV || a->light_acc, "shade_backward_tiled: Phong shading needs light_acc");
+  HFR_CHECK_ARG(!a->fix_sums || (a->fix_w && a->fix_image && a->fix_count > 0 && a->fix_inv_scale > 0.f),
+                "shade_backward_tiled: the mean-RGB fix-up needs sums, weights, the loss image and its element count");
   HFR_CHECK_ARG(a->pool_aa <= 1 || (a->pool_aa <= 16 && p.H % a->pool_aa == 0 && p.W % a->pool_aa == 0),
                 "shade_backward_tiled: image size must be a multiple of pool_aa (<= 16)");
   HFR_CHECK_ARG((p.W + kTileW - 1) / kTileW <= 255 && (p.H + kTileH - 1) / kTileH <= 255, "shade_backward_tiled: image too large");
   HFR_CHECK_ARG((reinterpret_cast<uintptr_t>(a->face_rec) & 15) == 0, "shade_backward_tiled: face_rec must be 16-byte aligned");
+  HFR_CHECK_ARG(p.F <= kMaxFacesTiled, "shade_backward_tiled: at most %d faces per mesh", kMaxFacesTiled);
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t Ftot = (int64_t)p.N * p.F;
   const WsLayout L = ws_layout(Ftot);
@@ -527,11 +596,13 @@ extern "C" int hfr_shade_backward_tiled(const HfrShadeBwdTiledArgs* a, void* str
     HFR_CHECK_LAUNCH("face_rec_zero");
   }
   dim3 grid((p.W + kTileW - 1) / kTileW, (p.H + kTileH - 1) / kTileH, p.N);
+  const int FW = (p.F + 31) / 32;
 #define HFR_LAUNCH_T(KM)                                                                                         \
   do {                                                                                                           \
-    const size_t smem = sizeof(TSmem<KM>);                                                                       \
+    const size_t smem = ((sizeof(TSmem<KM>) + 15) & ~(size_t)15) + (size_t)FW * 8;                               \
+    HFR_CHECK_ARG(smem <= 227 * 1024, "shade_backward_tiled: mesh too large for shared memory (%zu B)", smem);   \
     cudaFuncSetAttribute(shade_bwd_tiled_kernel<KM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
-    shade_bwd_tiled_kernel<KM><<<grid, kBT, smem, st>>>(*a, L);                                                  \
+    shade_bwd_tiled_kernel<KM><<<grid, kBT, smem, st>>>(*a, L, FW);                                              \
   } while (0)
   if (p.K == 1) HFR_LAUNCH_T(1);
   else if (p.K == 2) HFR_LAUNCH_T(2);

@@ -30,6 +30,14 @@ def all_reduce_loss_sums(sums: torch.Tensor, group=None):
     return sums
 
 
+def all_reduce_loss_sums_async(sums: torch.Tensor, group=None):
+    """As all_reduce_loss_sums, but only STARTS the collective and returns the work handles (empty at world size 1):
+    FusedHandStep.backward waits for them after it has enqueued the loss backward, which does not need the sums."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        return [dist.all_reduce(sums[:LOSS_NSUMS], group=group, async_op=True)]
+    return []
+
+
 def all_reduce_shared_grads(*grads: torch.Tensor, group=None):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         for g in grads:

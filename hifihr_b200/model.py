@@ -161,7 +161,8 @@ class FusedHandStep:
         self.face_attr = e(B, Fm, L.FACE_ATTR_FLOATS) if face_records else None
         self.p2f = e(B, Sr, Sr, K, dt=I64)
         self.zbuf, self.bary, self.dists = e(B, Sr, Sr, K), e(B, Sr, Sr, K, 3), e(B, Sr, Sr, K)
-        self.image, self.g_image = e(B, S, S, 4), e(B, S, S, 4)      # pooled RGBA when aa > 1
+        # pooled RGBA when aa > 1.  g_image starts as zeros: the loss backward only writes the tiles that can hold fragments
+        self.image, self.g_image = e(B, S, S, 4), torch.zeros(B, S, S, 4, dtype=F32, device=dev)
         self.re_img = self.re_sil = self.mask_rgbs = None
         if want_nchw:
             self.re_img, self.re_sil, self.mask_rgbs = e(B, 3, S, S), e(B, 1, S, S), e(B, 3, S, S)
@@ -198,7 +199,11 @@ class FusedHandStep:
             self.tex_acc = torch.zeros(self.texture.shape, dtype=I64, device=dev) if self.deterministic else None
             self.status = torch.zeros(1, dtype=torch.int32, device=dev)
             self.fx_scale = torch.ones(1, dtype=F32, device=dev)
+            self.gmax_bits = torch.zeros(1, dtype=torch.int32, device=dev)
             self._focal = None
+        # deterministic loss sums: per-CTA partials + a ticket word (the last CTA adds them in a fixed order)
+        self.loss_partials = e(int(L.lib().hfr_loss_partials_floats(B, S, S)) + 8) if self.deterministic else None
+        self.loss_ticket = torch.zeros(1, dtype=torch.int32, device=dev) if self.deterministic else None
         self.gauss = ops.gauss_taps(dev)
         self.params = ops.shade_params(B, Sr, Sr, K, Fm, V, 2 if soft else 0, 1, sigma, gamma, (1.0, 1.0, 1.0),
                                        (0.5, 0.5, 0.5), (0.2, 0.2, 0.2), (1.0, 1.0, 1.0), (0.8, 0.8, 0.8),
@@ -207,6 +212,8 @@ class FusedHandStep:
         # geom', mano'  (the two torch memsets of the accumulators are not counted)
         # tiled backward: + raster scan, record clear, gradient finish (the fixed-point scale is two small torch reductions)
         self.launches_per_step = 9 + (1 if face_records else 0) + (4 if self.tiled else 0)
+        if self.tiled and not self.deterministic:
+            self.g_light_dir.zero_()
 
     def _bind_outputs(self):
         o, B, ns = self._outs[self._out_set], self.B, self._n_sums
@@ -230,14 +237,16 @@ class FusedHandStep:
         ops.geom_forward_raw(self.topo, self.verts, 9, root_xyz, focal, prp, self.joints, self.verts_rel,
                              self.verts_view, self.verts_ndc, self.vnormals, self.face_verts)
         self.launch_raster_shade(light_dir, light_color, imgs)
-        self.sums.zero_()
+        if not self.deterministic:
+            self.sums.zero_()
         # targets may arrive as the dataset's 8-bit images / masks: the loss kernels convert while loading
         u8i, u8s = imgs.dtype == torch.uint8, seg.dtype == torch.uint8
         self._loss_args = L.HfrLossArgs(B, S, S, self.sil_scale, 1, 1, 1, L.ptr(self.image), None,
                                         None if u8i else L.ptr(imgs, F32, "imgs"), None if u8s else L.ptr(seg, F32, "seg"),
                                         L.ptr(self.sums), L.ptr(self.gauss), L.ptr(self.dmaps), L.ptr(self.tile_flags), 0,
                                         L.ptr(imgs, torch.uint8, "imgs") if u8i else None,
-                                        L.ptr(seg, torch.uint8, "seg") if u8s else None)
+                                        L.ptr(seg, torch.uint8, "seg") if u8s else None,
+                                        L.ptr(self.loss_partials), L.ptr(self.loss_ticket))
         L.call("hfr_loss_forward", self._loss_args)
 
     def launch_raster_shade(self, light_dir, light_color, imgs=None):
@@ -265,17 +274,19 @@ class FusedHandStep:
         """shade' + blend' + rasterize' (+ avg_pool2d' when aa_factor > 1) in one launch; accumulates into self.acc."""
         B = self.B
         if self.tiled:
-            # fixed-point multiplier of the 64-bit accumulators: 2^36 over the power of two above max |g_image|
-            gmax = self.g_image.abs().amax().clamp_min(1e-30)
-            torch.exp2(36.0 - torch.ceil(torch.log2(gmax)), out=self.fx_scale[0])
+            # the fixed-point multiplier of the 64-bit accumulators is derived on the device from max |g_image| (gmax_bits,
+            # left by the loss backward); the mean-RGB term's gradient is added here from the (all-reduced) sums
             t = L.HfrShadeBwdTiledArgs(self._shade_args, L.ptr(self.g_image), L.ptr(self.verts_ndc), L.ptr(self._focal, F32, "focal"),
                                        float(self.blur), 1, int(self.blur > 0), L.ptr(self.ws), L.ptr(self.face_rec), self.rec_cap,
                                        L.ptr(self.light_acc), L.ptr(self.tex_acc), None if self.deterministic else L.ptr(self.g_texture),
-                                       L.ptr(self.fx_scale), L.ptr(self.status), self.aa if self.aa > 1 else 0, int(self.binarize))
+                                       L.ptr(self.fx_scale), L.ptr(self.status), self.aa if self.aa > 1 else 0, int(self.binarize),
+                                       L.ptr(self.gmax_bits), L.ptr(self.sums), L.ptr(self.w), L.ptr(self.image),
+                                       1.0 / float(self.sil_scale), self.n_global * 3 * self.S * self.S)
             L.call("hfr_shade_backward_tiled", t)
             L.call("hfr_grad_finish", L.HfrGradFinishArgs(L.ptr(self.tex_acc), L.ptr(self.g_texture) if self.deterministic else None,
                                                           self.texture.numel() if self.deterministic else 0, L.ptr(self.light_acc),
-                                                          L.ptr(self.g_light_dir), L.ptr(self.g_light_color), B, L.ptr(self.fx_scale)))
+                                                          L.ptr(self.g_light_dir), L.ptr(self.g_light_color), B, L.ptr(self.fx_scale),
+                                                          L.ptr(self.gmax_bits)))
             return
         sb = L.HfrShadeBwdArgs(self._shade_args, L.ptr(self.g_image), None, None, None, L.ptr(self.verts_ndc),
                                L.ptr(self.g_ndc), float(self.blur), 1, int(self.blur > 0), L.ptr(self.g_view),
@@ -292,13 +303,31 @@ class FusedHandStep:
             ops.geom_backward_raw(self.topo, self.verts, 9, root_xyz, focal, prp, None, None, self.g_view, self.g_ndc,
                                   self.g_vn, self.g_verts)
 
-    def backward(self, pose, betas, focal, prp, root_xyz, shared_grad_hook=None):
-        """shared_grad_hook(g_texture) -> work handles: called as soon as the gradient of the shared texture is
-        complete (after the shade/rasterize backward), waited on after the last kernel of the step is enqueued."""
-        B, S = self.B, self.S
+    def launch_loss_backward(self):
+        S = self.S
         a = L.HfrLossBwdArgs(self._loss_args, L.ptr(self.w), L.ptr(self.gauss), self.n_global * 3 * S * S,
-                             self.n_global, L.ptr(self.g_image), None)
+                             self.n_global, L.ptr(self.g_image), None, None, None,
+                             ops.raster_tile_box(self.ws, self.B * self.topo.F, self.B) if self.tiled else None,
+                             self.aa, 1 if self.tiled else 0, L.ptr(self.gmax_bits) if self.tiled else None)
         L.call("hfr_loss_backward", a)
+
+    def backward(self, pose, betas, focal, prp, root_xyz, shared_grad_hook=None, sums_hook=None):
+        """sums_hook(sums) -> work handles (or None): all-reduce of the loss partial sums under data parallelism.  With
+        the tiled backward the loss backward does not depend on it (the only global quantity, the mean-RGB scale, is
+        applied by the shading backward), so the collective overlaps the loss backward kernel instead of sitting in
+        front of it.
+        shared_grad_hook(g_texture) -> work handles: called as soon as the gradient of the shared texture is complete
+        (after the shade/rasterize backward), waited on after the last kernel of the step is enqueued."""
+        # the collective is STARTED before the loss backward is enqueued (it only waits for the loss forward) and the
+        # main stream waits for it after: with the tiled backward the two overlap
+        pending = (sums_hook(self.sums) or ()) if sums_hook is not None else ()
+        if not self.tiled:
+            for w in pending:
+                w.wait()
+            pending = ()
+        self.launch_loss_backward()
+        for w in pending:
+            w.wait()
         if not self.tiled:
             self.acc.zero_()
         elif not self.deterministic:

@@ -329,10 +329,18 @@ typedef struct HfrShadeBwdTiledArgs {
   int64_t* tex_acc;                 /* (tex_n,tex_h,tex_w,3) fixed-point gradient of the texture, same protocol; NULL:
                                        plain fp32 atomics into g_texture (faster, not run-to-run reproducible)      */
   float* g_texture;                 /* used when tex_acc == NULL (accumulated, caller zeroes); may be NULL           */
-  const float* fx_scale;            /* DEVICE pointer to the fixed-point multiplier (a power of two; pick 2^36 / the power
-                                       of two above max |g_image| so accumulators neither overflow nor lose bits)   */
+  float* fx_scale;                  /* DEVICE float: the fixed-point multiplier (a power of two).  READ when gmax_bits is NULL
+                                       (pick 2^34 / the power of two above max |g_image|); WRITTEN when gmax_bits is set */
   uint32_t* status;                 /* DEVICE word, OR-ed: bit 0 = record store too small                            */
   int32_t pool_aa, pool_binarize;   /* as in HfrShadeBwdArgs                                                         */
+  const uint32_t* gmax_bits;        /* optional: bit pattern of max |g_image| as hfr_loss_backward leaves it; the multiplier
+                                       is derived from it on the device (no host round trip, no extra reduction pass)   */
+  /* optional mean-RGB fix-up (pairs with HfrLossBwdArgs.skip_mrgb): g_image lacks the gradient of the mean-RGB term
+   * (losses.py:369), which needs the GLOBAL sums; it is added here per pixel from fix_sums[HFR_LOSS_SUM_R / _T]
+   * (all-reduced), fix_w[1] = d(total)/d(mrgb), the image the loss saw (fix_image, (N,H,W,4) or pooled) and
+   * fix_inv_scale = 1 / sil_scale, fix_count = N_global * 3 * H * W of the loss resolution */
+  const float* fix_sums; const float* fix_w; const float* fix_image;
+  float fix_inv_scale; int64_t fix_count;
 } HfrShadeBwdTiledArgs;
 int hfr_shade_backward_tiled(const HfrShadeBwdTiledArgs* a, void* stream);
 
@@ -342,6 +350,7 @@ typedef struct HfrGradFinishArgs {
   int64_t* tex_acc; float* g_texture; int64_t n_tex;
   int64_t* light_acc; float* g_light_dir; float* g_light_color; int32_t N;
   const float* fx_scale;
+  uint32_t* gmax_bits;              /* optional: reset to 0 for the next step                                         */
 } HfrGradFinishArgs;
 int hfr_grad_finish(const HfrGradFinishArgs* a, void* stream);
 
@@ -435,7 +444,14 @@ typedef struct HfrLossArgs {
    * loading (exact x / 255.0f through a 256-entry table, mask byte != 0 -> 1.0f), so 4x fewer bytes cross PCIe. */
   const uint8_t* imgs_u8;           /* (N,3,H,W) or NULL                                   */
   const uint8_t* seg_u8;            /* (N,H,W) or NULL                                     */
+  /* optional deterministic reduction: every CTA leaves its 8 partial sums in `partials` (hfr_loss_partials_floats(N,H,W)
+   * floats, 16-byte aligned), the last CTA to arrive adds them in a fixed order and WRITES sums (the caller need not
+   * zero them).  `ticket` = one DEVICE word, zero before the first launch (the kernel resets it).  NULL: one fp32
+   * atomic per CTA and component (the sums then differ in the last bits from run to run). */
+  float* partials;
+  uint32_t* ticket;
 } HfrLossArgs;
+int64_t hfr_loss_partials_floats(int32_t N, int32_t H, int32_t W);
 int hfr_loss_forward(const HfrLossArgs* a, void* stream);
 typedef struct HfrLossBwdArgs {
   HfrLossArgs f;
@@ -449,6 +465,13 @@ typedef struct HfrLossBwdArgs {
   /* mask_mode 3 only: w[0..2] = d(total)/d(texture_self, mrgb_self, ssim_tex_self); g_re_sil is not written */
   const float* tex_con;             /* (N) examples['texture_con'] (losses.py:325)         */
   const float* self_norm;           /* DEVICE pointer to 1 float: sum_n tex_con[n]^2 over the GLOBAL batch */
+  /* fused step only (all optional) */
+  const uint32_t* tile_box;         /* per-mesh tile box of the rasterizer (hfr_raster_tile_box): tiles whose pixels hold no
+                                       fragment are not written (their gradient is never read by the fused backward)  */
+  int32_t box_aa;                   /* rasterised resolution / loss resolution (SSAA factor), 0 or 1 = same           */
+  int32_t skip_mrgb;                /* 1: leave the mean-RGB term out; hfr_shade_backward_tiled adds it from the sums  */
+  uint32_t* gmax_bits;              /* DEVICE word, atomicMax of the bit pattern of max |gradient written| (caller zeroes
+                                       or lets hfr_grad_finish reset it): scales the fixed-point accumulators           */
 } HfrLossBwdArgs;
 int hfr_loss_backward(const HfrLossBwdArgs* a, void* stream);
 
