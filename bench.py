@@ -283,7 +283,7 @@ def run_ours(args, cfg):
     from hifihr_b200 import ops
     for _ in range(reps):
         ev = []
-        ev.append(timed("mano_fwd", lambda: ops.mano_forward_raw(step.hm, pose, betas, None, step.verts, None)))
+        ev.append(timed("mano_fwd", lambda: ops.mano_forward_raw(step.hm, pose, betas, None, step.verts, None, workspace=step.mano_ws)))
         ev.append(timed("geom_fwd", lambda: ops.geom_forward_raw(step.topo, step.verts, 9, root, focal, prpp, step.joints,
                                                                  step.verts_rel, step.verts_view, step.verts_ndc,
                                                                  step.vnormals, step.face_verts)))
@@ -297,7 +297,8 @@ def run_ours(args, cfg):
         ev.append(timed("shade_raster_bwd", lambda: step.launch_shade_backward()))
         ev.append(timed("geom_bwd", lambda: step.launch_geom_backward(focal, prpp, root)))
         ev.append(timed("mano_bwd", lambda: ops.mano_backward_raw(step.hm, pose, betas, None, step.g_verts, None,
-                                                                  step.g_pose, step.g_betas, None)))
+                                                                  step.g_pose, step.g_betas, None, workspace=step.mano_ws,
+                                                                  reuse_forward=True)))
         torch.cuda.synchronize()
         for n, a, b in ev:
             acc[n] += a.elapsed_time(b)

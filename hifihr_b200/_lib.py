@@ -24,18 +24,19 @@ class HfrHandModel(C.Structure):
                 ("dirs", vp), ("v_template", vp), ("J_template", vp), ("J_shapedirs", vp),
                 ("pca_comps", vp), ("pose_mean", vp), ("parents", vp), ("skin_idx", vp), ("skin_w", vp),
                 ("tip_verts", vp), ("joint_order", vp), ("palm_verts", i32 * 2),
-                ("jv_ptr", vp), ("jv_vert", vp), ("jv_w", vp)]
+                ("jv_ptr", vp), ("jv_vert", vp), ("jv_w", vp), ("basis_packed", vp)]
 
 
 class HfrManoFwdArgs(C.Structure):
     _fields_ = [("B", i32), ("pose", vp), ("betas", vp), ("trans", vp), ("verts", vp), ("joints", vp),
-                ("rots", vp), ("n_rot_in", i32), ("pose_off", i32), ("root_palm", i32)]
+                ("rots", vp), ("n_rot_in", i32), ("pose_off", i32), ("root_palm", i32), ("workspace", vp)]
 
 
 class HfrManoBwdArgs(C.Structure):
     _fields_ = [("B", i32), ("pose", vp), ("betas", vp), ("trans", vp), ("g_verts", vp), ("g_joints", vp),
                 ("g_pose", vp), ("g_betas", vp), ("g_trans", vp),
-                ("rots", vp), ("n_rot_in", i32), ("pose_off", i32), ("root_palm", i32), ("g_rots", vp)]
+                ("rots", vp), ("n_rot_in", i32), ("pose_off", i32), ("root_palm", i32), ("g_rots", vp),
+                ("workspace", vp), ("reuse_forward", i32)]
 
 
 class HfrTopology(C.Structure):
@@ -149,7 +150,7 @@ class HfrKeypointBwdArgs(C.Structure):
     _fields_ = [("f", HfrKeypointArgs), ("w", vp), ("n_global", i32), ("g_j2d_in", vp), ("g_joints", vp), ("g_verts", vp)]
 
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 LOSS_NSUMS = 8
 FACE_ATTR_FLOATS = 28
 FACE_REC_FLOATS = 18
@@ -163,7 +164,8 @@ ENTRY_POINTS = [
     "hfr_raster_backward", "hfr_raster_tile_box", "hfr_shade_forward", "hfr_shade_backward", "hfr_raster_shade_forward",
     "hfr_raster_shade_pool_forward", "hfr_face_attr_forward", "hfr_pool_forward", "hfr_pool_backward", "hfr_loss_forward", "hfr_loss_backward",
     "hfr_keypoint_forward", "hfr_keypoint_backward", "hfr_shade_backward_tiled", "hfr_grad_finish",
-    "hfr_loss_partials_floats",
+    "hfr_loss_partials_floats", "hfr_mano_packed_basis_bytes", "hfr_mano_pack_basis", "hfr_mano_workspace_bytes",
+    "hfr_mano_batched_status",
 ]
 
 _lib = None
@@ -188,6 +190,10 @@ def lib() -> C.CDLL:
         _lib.hfr_raster_tile_box.argtypes = [C.c_void_p, C.c_int64, C.c_int32]
         _lib.hfr_loss_partials_floats.restype = C.c_int64
         _lib.hfr_loss_partials_floats.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+        _lib.hfr_mano_packed_basis_bytes.restype = C.c_int64
+        _lib.hfr_mano_packed_basis_bytes.argtypes = [C.c_void_p]
+        _lib.hfr_mano_workspace_bytes.restype = C.c_int64
+        _lib.hfr_mano_workspace_bytes.argtypes = [C.c_void_p, C.c_int32]
         if _lib.hfr_abi_version() != ABI_VERSION:
             raise HfrError("libhifihr_b200.so ABI version mismatch")
     return _lib
@@ -220,13 +226,14 @@ def call(name: str, *structs, device=None):
     else:
         dev = next(iter(devs)) if devs else torch.cuda.current_device()
     devs.clear()
+    cargs = [C.byref(s) if isinstance(s, C.Structure) else s for s in structs]   # structs by address, scalars / pointers by value
     if dev == torch.cuda.current_device():
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        rc = getattr(L, name)(*[C.byref(s) for s in structs], stream)
+        rc = getattr(L, name)(*cargs, stream)
     else:
         with torch.cuda.device(dev):
             stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-            rc = getattr(L, name)(*[C.byref(s) for s in structs], stream)
+            rc = getattr(L, name)(*cargs, stream)
     if rc != 0:
         msg = L.hfr_last_error().decode()
         if rc == 1:

@@ -10,6 +10,7 @@
 
 #include "common.cuh"
 #include "mano_math.cuh"
+#include "mano_batched.cuh"
 
 static thread_local char g_err[512] = "";
 void hfr_set_error(const char* fmt, ...) {
@@ -568,6 +569,7 @@ extern "C" int hfr_mano_forward(const HfrHandModel* m, const HfrManoFwdArgs* a, 
   HFR_CHECK_ARG(!a->root_palm || (m->palm_verts[0] >= 0 && m->palm_verts[0] < m->V && m->palm_verts[1] >= 0 &&
                                   m->palm_verts[1] < m->V), "mano_forward: root_palm needs palm_verts");
   const int pose_dim = (a->pose_off > 0 ? a->pose_off : 3) + (m->NPC > 0 ? m->NPC : 3 * (m->NJ - 1));
+  if (hfr::mano_batched_ok(m, a->B, a->workspace)) return hfr::mano_batched_forward(m, a, pose_dim, (cudaStream_t)stream);
   const size_t smem = mano_smem_bytes(*m, false);
   HFR_CHECK_ARG(smem <= 227 * 1024, "mano_forward: model too large for shared memory (%zu B)", smem);
   if (smem > 48 * 1024) cudaFuncSetAttribute(mano_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -586,6 +588,7 @@ extern "C" int hfr_mano_backward(const HfrHandModel* m, const HfrManoBwdArgs* a,
   HFR_CHECK_ARG(!a->root_palm || (m->palm_verts[0] >= 0 && m->palm_verts[0] < m->V && m->palm_verts[1] >= 0 &&
                                   m->palm_verts[1] < m->V), "mano_backward: root_palm needs palm_verts");
   const int pose_dim = (a->pose_off > 0 ? a->pose_off : 3) + (m->NPC > 0 ? m->NPC : 3 * (m->NJ - 1));
+  if (hfr::mano_batched_ok(m, a->B, a->workspace)) return hfr::mano_batched_backward(m, a, pose_dim, (cudaStream_t)stream);
   const int NK = m->NS + 9 * (m->NJ - 1);
   const size_t extra = (size_t)(12 * m->NJ + 3 * m->NJ + 9 * m->NJ + ((NK + 3) & ~3) + 3 * m->NJ + 15 * m->NJ + 8) * sizeof(float);
   const size_t smem = mano_smem_bytes(*m, true) + extra;

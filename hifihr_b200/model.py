@@ -119,7 +119,7 @@ class FusedHandStep:
     def __init__(self, B, image_size=224, faces_per_pixel=4, blur_radius=None, sigma=1e-4, gamma=1e-4, soft=True,
                  texture_size=512, lambdas=None, device="cuda", mano_root=None, n_global=None, sil_scale=1.0,
                  aa_factor=1, binarize=False, want_nchw=False, face_records=False, tiled_backward=True,
-                 deterministic=True, rec_per_face=12):
+                 deterministic=True, rec_per_face=12, batched_hand=True):
         """aa_factor > 1 selects the SSAA-fused render (the reference's own setting is image_size=224,
         aa_factor=3, faces_per_pixel=1, soft=False, binarize=True, sil_scale=255; models_res_nimble.py:74-96,
         208-220): Fragments are rasterised at image_size*aa_factor, the pooled RGBA (B,S,S,4) is the only image
@@ -191,6 +191,7 @@ class FusedHandStep:
         self.g_texture = take(self.texture.numel(), self.texture.shape)
         self.g_light_dir, self.g_light_color = take(3 * B, (B, 3)), take(3 * B, (B, 3))
         self.g_verts = e(B, V, 3)
+        self.mano_ws = self.hm.workspace(B) if batched_hand else None   # batched tensor-core hand layer (None: per-sample kernels)
         self.tiled, self.deterministic = bool(tiled_backward), bool(deterministic)
         if self.tiled:
             self.rec_cap = int(rec_per_face) * B * Fm + 4096
@@ -211,7 +212,7 @@ class FusedHandStep:
         # kernels of OURS per step(): mano, geom, [face records], raster setup, raster+shade(+pool), loss | loss', shade'+raster',
         # geom', mano'  (the two torch memsets of the accumulators are not counted)
         # tiled backward: + raster scan, record clear, gradient finish (the fixed-point scale is two small torch reductions)
-        self.launches_per_step = 9 + (1 if face_records else 0) + (4 if self.tiled else 0)
+        self.launches_per_step = 9 + (1 if face_records else 0) + (4 if self.tiled else 0) + (4 if self.mano_ws is not None else 0)
         if self.tiled and not self.deterministic:
             self.g_light_dir.zero_()
 
@@ -233,7 +234,7 @@ class FusedHandStep:
         # the cached argument structs hold raw pointers: keep the inputs alive until the backward has been enqueued
         self._inputs = (pose, betas, focal, prp, root_xyz, light_dir, light_color, imgs, seg)
         self._focal = focal
-        ops.mano_forward_raw(self.hm, pose, betas, None, self.verts, None)
+        ops.mano_forward_raw(self.hm, pose, betas, None, self.verts, None, workspace=self.mano_ws)
         ops.geom_forward_raw(self.topo, self.verts, 9, root_xyz, focal, prp, self.joints, self.verts_rel,
                              self.verts_view, self.verts_ndc, self.vnormals, self.face_verts)
         self.launch_raster_shade(light_dir, light_color, imgs)
@@ -335,7 +336,8 @@ class FusedHandStep:
         self.launch_shade_backward()
         works = shared_grad_hook(self.g_texture) if shared_grad_hook is not None else ()
         self.launch_geom_backward(focal, prp, root_xyz)
-        ops.mano_backward_raw(self.hm, pose, betas, None, self.g_verts, None, self.g_pose, self.g_betas, None)
+        ops.mano_backward_raw(self.hm, pose, betas, None, self.g_verts, None, self.g_pose, self.g_betas, None,
+                              workspace=self.mano_ws, reuse_forward=True)
         for w in works:
             w.wait()
 

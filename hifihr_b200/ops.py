@@ -90,6 +90,23 @@ class HandModelConsts:
         s.jv_ptr, s.jv_vert, s.jv_w = self.jv_ptr.data_ptr(), self.jv_vert.data_ptr(), self.jv_w.data_ptr()
         self.struct = s
         self.device = dev
+        # batched tensor-core path: the basis split into tf32 hi / lo parts, pre-tiled in the MMA operand layout (once)
+        self.basis_packed = None
+        self.batched_min = 8          # below this batch the per-sample kernels are used (no workspace is passed)
+        if dev.type == "cuda":
+            nbytes = int(L.lib().hfr_mano_packed_basis_bytes(C.byref(s)))
+            if nbytes > 0:
+                self.basis_packed = torch.empty(nbytes // 4, dtype=F32, device=dev)
+                L._pending_devices().add(dev.index if dev.index is not None else torch.cuda.current_device())
+                L.call("hfr_mano_pack_basis", s, C.c_void_p(self.basis_packed.data_ptr()))
+                s.basis_packed = self.basis_packed.data_ptr()
+
+    def workspace(self, B):
+        """Scratch of the batched path for B samples (None = use the per-sample kernels)."""
+        if self.basis_packed is None or B < self.batched_min:
+            return None
+        n = int(L.lib().hfr_mano_workspace_bytes(C.byref(self.struct), int(B)))
+        return torch.empty((n + 3) // 4, dtype=F32, device=self.device)
 
 
 class TopologyConsts:
@@ -156,21 +173,24 @@ class TopologyConsts:
 # ------------------------------------------------------------------------------------------------
 # raw launches (no autograd) — also used by the fused step
 # ------------------------------------------------------------------------------------------------
-def mano_forward_raw(hm: HandModelConsts, pose, betas, trans, verts, joints, rots=None, pose_off=3, root_palm=False):
-    """rots (B,n,3,3) with n = 1 (matrix-driven root, rot6d mode) or NJ (rotmat mode, pose may be None)."""
+def mano_forward_raw(hm: HandModelConsts, pose, betas, trans, verts, joints, rots=None, pose_off=3, root_palm=False,
+                     workspace=None):
+    """rots (B,n,3,3) with n = 1 (matrix-driven root, rot6d mode) or NJ (rotmat mode, pose may be None).
+    workspace (hm.workspace(B)) selects the batched tensor-core path."""
     n_rot = 0 if rots is None else rots.shape[1]
     a = L.HfrManoFwdArgs(verts.shape[0], L.ptr(pose, F32, "pose"), L.ptr(betas, F32, "betas"),
                          L.ptr(trans, F32, "trans"), L.ptr(verts, F32), L.ptr(joints, F32), L.ptr(rots, F32, "rots"),
-                         n_rot, pose_off, int(root_palm))
+                         n_rot, pose_off, int(root_palm), L.ptr(workspace, F32))
     L.call("hfr_mano_forward", hm.struct, a)
 
 
 def mano_backward_raw(hm, pose, betas, trans, g_verts, g_joints, g_pose, g_betas, g_trans, rots=None, pose_off=3,
-                      root_palm=False, g_rots=None):
+                      root_palm=False, g_rots=None, workspace=None, reuse_forward=False):
     n_rot = 0 if rots is None else rots.shape[1]
     a = L.HfrManoBwdArgs(g_verts.shape[0], L.ptr(pose, F32), L.ptr(betas, F32), L.ptr(trans, F32),
                          L.ptr(g_verts, F32), L.ptr(g_joints, F32), L.ptr(g_pose, F32), L.ptr(g_betas, F32),
-                         L.ptr(g_trans, F32), L.ptr(rots, F32), n_rot, pose_off, int(root_palm), L.ptr(g_rots, F32))
+                         L.ptr(g_trans, F32), L.ptr(rots, F32), n_rot, pose_off, int(root_palm), L.ptr(g_rots, F32),
+                         L.ptr(workspace, F32), int(bool(reuse_forward) and workspace is not None))
     L.call("hfr_mano_backward", hm.struct, a)
 
 
@@ -272,8 +292,9 @@ class ManoFunction(torch.autograd.Function):
         B = ref.shape[0]
         verts = torch.empty(B, hm.V, 3, device=ref.device, dtype=F32)
         joints = torch.empty(B, hm.n_out_joints, 3, device=ref.device, dtype=F32)
-        mano_forward_raw(hm, pose, betas, trans, verts, joints, rots, pose_off, root_palm)
-        ctx.hm, ctx.cfg = hm, (pose_off, bool(root_palm), B)
+        ws = hm.workspace(B)      # kept for the backward: pose state and posed rest vertices are not recomputed
+        mano_forward_raw(hm, pose, betas, trans, verts, joints, rots, pose_off, root_palm, workspace=ws)
+        ctx.hm, ctx.cfg, ctx.ws = hm, (pose_off, bool(root_palm), B), ws
         ctx.save_for_backward(pose, betas, trans, rots)
         return verts, joints
 
@@ -290,7 +311,7 @@ class ManoFunction(torch.autograd.Function):
         g_trans = None if trans is None else torch.empty_like(trans)
         g_rots = None if rots is None else torch.empty_like(rots)
         mano_backward_raw(hm, pose, betas, trans, g_verts, g_joints, g_pose, g_betas, g_trans, rots, pose_off, root_palm,
-                          g_rots)
+                          g_rots, workspace=ctx.ws, reuse_forward=True)
         return None, g_pose, g_betas, g_trans, g_rots, None, None
 
 

@@ -22,7 +22,7 @@ extern "C" {
 #define HFR_EINVAL 1    /* bad argument (shape, K out of range, null pointer)      */
 #define HFR_ECUDA 2     /* CUDA runtime error at launch                            */
 #define HFR_EUNSUPPORTED 3
-#define HFR_ABI_VERSION 4
+#define HFR_ABI_VERSION 5
 
 #define HFR_MAX_JOINTS 32
 #define HFR_MAX_K 16
@@ -62,7 +62,19 @@ typedef struct HfrHandModel {
   const int32_t* jv_ptr;   /* (NJ+1)                                                       */
   const int32_t* jv_vert;  /* (nnz) vertex of each non-zero weight                         */
   const float* jv_w;       /* (nnz)                                                        */
+  /* optional: the blend basis pre-split into tf32 hi / lo parts and pre-tiled in the tensor-core operand layout
+   * (hfr_mano_packed_basis_bytes / hfr_mano_pack_basis, built once).  With it, and a workspace in the call, the
+   * layer runs as ONE batched blend contraction on the tensor cores (tcgen05) instead of one basis stream per
+   * sample; NULL = per-sample kernels */
+  const void* basis_packed;
 } HfrHandModel;
+/* Batched path (utils/my_mano.py:386-393 as one [B x NK].[NK x 3V] product per batch, and its transpose in the
+ * backward): size of the packed basis, the one-time packing launch, and the per-call workspace size for B samples. */
+int64_t hfr_mano_packed_basis_bytes(const HfrHandModel* m);
+int hfr_mano_pack_basis(const HfrHandModel* m, void* packed, void* stream);
+int64_t hfr_mano_workspace_bytes(const HfrHandModel* m, int32_t B);
+/* 0 when no barrier wait of the batched kernels has ever timed out on the current device (diagnostic) */
+int hfr_mano_batched_status(void);
 
 /* Replaces ManoLayer.forward (utils/my_mano.py:315-483) / MyMANOLayer.forward (:39-54).
  * pose (B, 3+NPC) [or (B, 3*NJ) when NPC==0], betas (B,NS) or NULL (mean shape);
@@ -81,6 +93,8 @@ typedef struct HfrManoFwdArgs {
   float* joints;
   const float* rots;
   int32_t n_rot_in, pose_off, root_palm;
+  void* workspace;         /* hfr_mano_workspace_bytes(m, B) bytes, or NULL (per-sample kernels).  Selects the batched
+                              tensor-core path when the model carries basis_packed */
 } HfrManoFwdArgs;
 int hfr_mano_forward(const HfrHandModel* m, const HfrManoFwdArgs* a, void* stream);
 
@@ -100,6 +114,9 @@ typedef struct HfrManoBwdArgs {
   const float* rots;                /* as in the forward                                   */
   int32_t n_rot_in, pose_off, root_palm;
   float* g_rots;                    /* (B,n_rot_in,3,3) or NULL                            */
+  void* workspace;                  /* as in the forward; NULL = per-sample kernel           */
+  int32_t reuse_forward;            /* 1: `workspace` still holds what hfr_mano_forward left for the SAME inputs (pose
+                                       state and posed rest vertices are not recomputed); 0: recompute them          */
 } HfrManoBwdArgs;
 int hfr_mano_backward(const HfrHandModel* m, const HfrManoBwdArgs* a, void* stream);
 
@@ -312,7 +329,7 @@ const uint32_t* hfr_raster_tile_box(const void* workspace, int64_t Ftot, int32_t
  * (light gradients, the shared texture's gradient) go through 64-bit FIXED-POINT accumulators: integer addition is
  * associative, so the result does not depend on the order the hardware serialises them in; hfr_grad_finish converts
  * them to fp32 and clears them.  The whole backward is therefore bit-reproducible run to run.
- * Needs the rasterizer workspace exactly as hfr_raster_(shade_)forward left it for the same N / Ftot, with
+ * Needs the rasterizer workspace exactly as hfr_raster_forward or hfr_raster_shade_forward left it for the same N / Ftot, with
  * mesh_first[n] = n * F (uniform packing, what MeshRasterizer builds for a batch of one topology). */
 #define HFR_FACE_REC_FLOATS 18      /* corner-major: {d/d(view xyz), d/d(vertex normal xyz)} x 3 corners */
 typedef struct HfrShadeBwdTiledArgs {

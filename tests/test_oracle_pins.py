@@ -222,7 +222,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.ENTRY_POINTS), declared ^ set(_lib.ENTRY_POINTS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.hfr_abi_version() == 4
+    assert lib.hfr_abi_version() == _lib.ABI_VERSION == 5
 
 
 def test_ctypes_struct_sizes_match_header():

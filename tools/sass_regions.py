@@ -1,14 +1,14 @@
 #!/usr/bin/env python
 """Aggregate tools/sass_hotspots.py output (all lines) by file and line ranges.
-usage: python tools/sass_regions.py <ncu-rep> <kernel-regex> <cubin> file:lo-hi[:label] ..."""
+usage: python tools/sass_regions.py <ncu-rep> <kernel-regex> <cubin> <mangled-substring> file:lo-hi[:label] ..."""
 import subprocess, sys, re, collections
-rep, kre, cubin = sys.argv[1:4]
+rep, kre, cubin, mangled = sys.argv[1:5]
 regions = []
-for r in sys.argv[4:]:
+for r in sys.argv[5:]:
     parts = r.split(":")
     lo, hi = parts[1].split("-")
     regions.append((parts[0], int(lo), int(hi), parts[2] if len(parts) > 2 else r))
-out = subprocess.run([sys.executable, "tools/sass_hotspots.py", rep, kre, cubin, "100000"], capture_output=True, text=True).stdout
+out = subprocess.run([sys.executable, "tools/sass_hotspots.py", rep, kre, cubin, mangled, "100000"], capture_output=True, text=True).stdout
 agg = collections.Counter(); samp = collections.Counter(); byfile = collections.Counter()
 for ln in out.splitlines():
     m = re.match(r"\s*([\d.]+)% inst\s+([\d.]+)% samp thr/inst\s+[\d.]+\s+(\S+?):(\d+):", ln)
