@@ -173,7 +173,8 @@ def run_ours(args, cfg):
     step = hf.FusedHandStep(B, image_size=S, faces_per_pixel=K, soft=cfg["soft"], texture_size=cfg["T"],
                             lambdas=LAMBDAS, device=dev, n_global=B * world, sil_scale=cfg.get("sil_scale", 1.0),
                             aa_factor=aa, binarize=cfg.get("binarize", False),
-                            face_records=bool(os.environ.get("HFR_FACE_RECORDS")))   # env: A/B tuning only
+                            face_records=bool(os.environ.get("HFR_FACE_RECORDS")),     # env: A/B tuning only
+                            tile_queue=os.environ.get("HFR_TILE_QUEUE", "1") != "0")
     inp = synthetic_inputs(B, S=S, seed=1234 + rank)
     fcl, prp = hf.get_ndc_fx_fy_cx_cy(inp["Ks"])
     # Target images are 8-bit in the datasets the reference trains on (its loader applies ToTensor = x / 255 on the

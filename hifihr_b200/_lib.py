@@ -61,7 +61,7 @@ class HfrRasterArgs(C.Structure):
     _fields_ = [("N", i32), ("H", i32), ("W", i32), ("K", i32), ("Ftot", i64), ("face_verts", vp),
                 ("mesh_first", vp), ("mesh_nfaces", vp), ("blur_radius", f32),
                 ("perspective_correct", i32), ("clip_barycentric", i32), ("cull_backfaces", i32),
-                ("pix_to_face", vp), ("zbuf", vp), ("bary", vp), ("dists", vp), ("workspace", vp)]
+                ("pix_to_face", vp), ("zbuf", vp), ("bary", vp), ("dists", vp), ("workspace", vp), ("tile_queue", vp)]
 
 
 class HfrRasterBwdArgs(C.Structure):
@@ -165,7 +165,7 @@ ENTRY_POINTS = [
     "hfr_raster_shade_pool_forward", "hfr_face_attr_forward", "hfr_pool_forward", "hfr_pool_backward", "hfr_loss_forward", "hfr_loss_backward",
     "hfr_keypoint_forward", "hfr_keypoint_backward", "hfr_shade_backward_tiled", "hfr_grad_finish",
     "hfr_loss_partials_floats", "hfr_mano_packed_basis_bytes", "hfr_mano_pack_basis", "hfr_mano_workspace_bytes",
-    "hfr_mano_batched_status",
+    "hfr_mano_batched_status", "hfr_raster_queue_bytes",
 ]
 
 _lib = None
@@ -190,6 +190,8 @@ def lib() -> C.CDLL:
         _lib.hfr_raster_tile_box.argtypes = [C.c_void_p, C.c_int64, C.c_int32]
         _lib.hfr_loss_partials_floats.restype = C.c_int64
         _lib.hfr_loss_partials_floats.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+        _lib.hfr_raster_queue_bytes.restype = C.c_int64
+        _lib.hfr_raster_queue_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32]
         _lib.hfr_mano_packed_basis_bytes.restype = C.c_int64
         _lib.hfr_mano_packed_basis_bytes.argtypes = [C.c_void_p]
         _lib.hfr_mano_workspace_bytes.restype = C.c_int64

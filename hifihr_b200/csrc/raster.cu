@@ -14,7 +14,7 @@ namespace hfr {
 // initialised to 0xff by a memset), so that tiles outside a mesh's footprint skip the coarse scan.
 __global__ void __launch_bounds__(256) raster_setup_kernel(HfrRasterArgs a, uint32_t* __restrict__ ranges,
                                                            uint32_t* __restrict__ mesh_box, uint32_t* __restrict__ rec_loc,
-                                                           uint32_t* __restrict__ blk_tot) {
+                                                           uint32_t* __restrict__ blk_tot, uint32_t* __restrict__ tile_cnt) {
   __shared__ uint32_t s_wsum[8];
   const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = f < a.Ftot;
@@ -89,6 +89,89 @@ __global__ void __launch_bounds__(256) raster_setup_kernel(HfrRasterArgs a, uint
   } else if (n >= 0) {
     atomicMin(mesh_box + 4 * n, (unsigned)tx0); atomicMin(mesh_box + 4 * n + 1, (unsigned)(255 - tx1));
     atomicMin(mesh_box + 4 * n + 2, (unsigned)ty0); atomicMin(mesh_box + 4 * n + 3, (unsigned)(255 - ty1));
+  }
+  // tile queue: how many faces' ranges cover each tile (the cost proxy the tiles are ordered by; integer atomics)
+  if (tile_cnt && n >= 0) {
+    const int TX = (a.W + kTileW - 1) / kTileW, TY = (a.H + kTileH - 1) / kTileH;
+    uint32_t* c = tile_cnt + (size_t)n * TX * TY;
+    for (int ty = ty0; ty <= ty1; ++ty)
+      for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(c + ty * TX + tx, 1u);
+  }
+}
+
+// Tile queue layout (32-bit words), T = N * TX * TY tiles:
+//   [0] nc = tiles with at least one face, [1] ng = groups of empty tiles, [2, 2 + 8) = tiles per cost class
+//   [16, 16 + T)            face count per tile (n-major, row-major), zeroed with the header every launch
+//   [16 + T, 16 + 9 T)      8 class lists of tile ids (class c = floor(log2(face count)), capped at 7), capacity T each
+//   [16 + 9 T, 16 + 10 T)   groups of up to kFillRun (8) horizontally adjacent empty tiles: first tile id | (len - 1) << 28
+// Orders inside a list depend on atomic timing; no result depends on the order tiles are processed in.
+__device__ __forceinline__ int cost_class(uint32_t cnt) { return min(kCostClasses - 1, 31 - __clz(cnt)); }   // cnt > 0
+__global__ void __launch_bounds__(256) raster_order_kernel(uint32_t* __restrict__ q, int N, int TX, int TY, int max_run) {
+  // one thread per tile row.  Pass 1 counts the row's entries per list, the block reserves its share of every list with
+  // ONE global atomic per list, pass 2 writes the entries.
+  __shared__ uint32_t s_cnt[kCostClasses + 1], s_base[kCostClasses + 1];
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = r < N * TY;
+  const int T = N * TX * TY;
+  const uint32_t* cnt = q + kQueueHdr + (size_t)(live ? r : 0) * TX;
+  uint32_t* lists = q + kQueueHdr + T;
+  uint32_t* groups = q + kQueueHdr + (size_t)(1 + kCostClasses) * T;
+  if (threadIdx.x <= kCostClasses) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  uint32_t mine[kCostClasses + 1];
+#pragma unroll
+  for (int k = 0; k <= kCostClasses; ++k) mine[k] = 0;
+  if (live) {
+    int run = 0;
+    for (int tx = 0; tx <= TX; ++tx) {
+      const uint32_t c = tx < TX ? cnt[tx] : 1u;
+      if (c == 0) {
+        if (++run == max_run) { ++mine[kCostClasses]; run = 0; }
+      } else {
+        if (run > 0) { ++mine[kCostClasses]; run = 0; }
+        if (tx < TX) {
+          const int k = cost_class(c);
+#pragma unroll
+          for (int j = 0; j < kCostClasses; ++j) mine[j] += (j == k) ? 1u : 0u;
+        }
+      }
+    }
+  }
+  uint32_t off[kCostClasses + 1];
+#pragma unroll
+  for (int k = 0; k <= kCostClasses; ++k) off[k] = mine[k] ? atomicAdd(&s_cnt[k], mine[k]) : 0u;
+  __syncthreads();
+  if (threadIdx.x <= kCostClasses) {
+    const int k = threadIdx.x;
+    const uint32_t c = s_cnt[k];
+    s_base[k] = c ? atomicAdd(k == kCostClasses ? q + 1 : q + 2 + k, c) : 0u;
+    if (k < kCostClasses && c) atomicAdd(q, c);
+  }
+  __syncthreads();
+  if (!live) return;
+  int run0 = -1;
+  for (int tx = 0; tx <= TX; ++tx) {
+    const uint32_t c = tx < TX ? cnt[tx] : 1u;
+    if (c == 0) {
+      if (run0 < 0) run0 = tx;
+      if (tx - run0 + 1 == max_run) {
+        groups[s_base[kCostClasses] + off[kCostClasses]++] = (uint32_t)(r * TX + run0) | ((uint32_t)(max_run - 1) << 28);
+        run0 = -1;
+      }
+    } else {
+      if (run0 >= 0) {
+        groups[s_base[kCostClasses] + off[kCostClasses]++] = (uint32_t)(r * TX + run0) | ((uint32_t)(tx - run0 - 1) << 28);
+        run0 = -1;
+      }
+      if (tx < TX) {
+        const int k = cost_class(c);
+        uint32_t pos = 0;
+#pragma unroll
+        for (int j = 0; j < kCostClasses; ++j)
+          if (j == k) pos = s_base[j] + off[j]++;
+        lists[(size_t)k * T + pos] = (uint32_t)(r * TX + tx);
+      }
+    }
   }
 }
 
@@ -184,16 +267,25 @@ const uint32_t* raster_mesh_box(const HfrRasterArgs& a) {
   return (a.N <= a.Ftot) ? reinterpret_cast<const uint32_t*>(a.workspace) + ws_layout(a.Ftot).box : nullptr;   // 16-byte aligned
 }
 
-int launch_raster_setup(const HfrRasterArgs& a, uint32_t* ranges, cudaStream_t s) {
+int launch_raster_setup(const HfrRasterArgs& a, uint32_t* ranges, cudaStream_t s, bool use_queue) {
   if (a.Ftot > 0) {
     uint32_t* box = const_cast<uint32_t*>(raster_mesh_box(a));
     if (box) cudaMemsetAsync(box, 0xff, (size_t)a.N * 4 * sizeof(uint32_t), s);
     const WsLayout L = ws_layout(a.Ftot);
     uint32_t* ws = reinterpret_cast<uint32_t*>(a.workspace);
-    raster_setup_kernel<<<(unsigned)L.nblk, 256, 0, s>>>(a, ranges, box, ws + L.loc, ws + L.blk);
+    uint32_t* queue = (box && use_queue) ? reinterpret_cast<uint32_t*>(a.tile_queue) : nullptr;
+    const int TX = (a.W + kTileW - 1) / kTileW, TY = (a.H + kTileH - 1) / kTileH, T = a.N * TX * TY;
+    if (queue) cudaMemsetAsync(queue, 0, (size_t)(kQueueHdr + T) * sizeof(uint32_t), s);
+    raster_setup_kernel<<<(unsigned)L.nblk, 256, 0, s>>>(a, ranges, box, ws + L.loc, ws + L.blk, queue ? queue + kQueueHdr : nullptr);
     HFR_CHECK_LAUNCH("raster_setup");
     raster_scan_kernel<<<1, 1024, 0, s>>>(ws + L.blk, (int)L.nblk);
     HFR_CHECK_LAUNCH("raster_scan");
+    if (queue) {
+      // empty tiles per fill group: bounded by the 16 K-word pattern buffer of the bulk-copy fill ((80 K + 64) words per tile)
+      const int max_run = a.K <= 4 ? kFillRun : (a.K <= 8 ? kFillRun / 2 : kFillRun / 4);
+      raster_order_kernel<<<(a.N * TY + 255) / 256, 256, 0, s>>>(queue, a.N, TX, TY, max_run);
+      HFR_CHECK_LAUNCH("raster_order");
+    }
   }
   return HFR_OK;
 }
@@ -205,6 +297,12 @@ static void launch_fwd(const HfrRasterArgs& a, const uint32_t* ranges, cudaStrea
 }
 
 }  // namespace hfr
+
+extern "C" int64_t hfr_raster_queue_bytes(int32_t N, int32_t H, int32_t W) {
+  if (N < 1 || H < 1 || W < 1) return 64;
+  const int64_t T = (int64_t)N * ((W + hfr::kTileW - 1) / hfr::kTileW) * ((H + hfr::kTileH - 1) / hfr::kTileH);
+  return (hfr::kQueueHdr + (2 + hfr::kCostClasses) * T) * 4 + 64;
+}
 
 extern "C" int64_t hfr_raster_workspace_bytes(int64_t Ftot) { return hfr::ws_layout(Ftot < 1 ? 1 : Ftot).words * 4 + 64; }
 

@@ -30,6 +30,9 @@ constexpr int kRecFloats = 20;  // 80-byte record (9 vertex floats, dilated bbox
                                 // stride spreads the per-lane LDS.128 of the fine pass over all bank groups
 constexpr int kDepthBuckets = 32;   // one per lane: every warp scans the histogram in registers
 constexpr int kChunk = 32 * kRasterThreads;  // faces handled per coarse pass (one hit bit per face per thread)
+constexpr int kCostClasses = 8;     // tile queue (raster.cu): cost classes, header words, empty tiles per fill group
+constexpr int kQueueHdr = 16;
+constexpr int kFillRun = 8;
 
 struct RasterSmem {
   __align__(16) float rec[kListCap * kRecFloats];
@@ -114,6 +117,20 @@ __device__ __forceinline__ PixelCtx make_pixel_ctx(int H, int W) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   c.n = blockIdx.z; c.tx = blockIdx.x; c.ty = blockIdx.y;
   const int wx0 = c.tx * kTileW + (warp & 1) * 8, wy0 = c.ty * kTileH + (warp >> 1) * 4;
+  c.xi = wx0 + (lane & 7);
+  c.yi = wy0 + (lane >> 3);
+  c.pix_active = c.xi < W && c.yi < H;
+  c.warp_active = wx0 < W && wy0 < H;
+  c.xf = 0.0f; c.yf = 0.0f;
+  return c;
+}
+
+// the same for an explicit tile (tile-queue order: the CTA index no longer names the tile)
+__device__ __forceinline__ PixelCtx make_pixel_ctx_at(int n, int tx, int ty, int H, int W) {
+  PixelCtx c;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  c.n = n; c.tx = tx; c.ty = ty;
+  const int wx0 = tx * kTileW + (warp & 1) * 8, wy0 = ty * kTileH + (warp >> 1) * 4;
   c.xi = wx0 + (lane & 7);
   c.yi = wy0 + (lane >> 3);
   c.pix_active = c.xi < W && c.yi < H;
@@ -495,6 +512,49 @@ __device__ __forceinline__ bool fill_empty_tile(const HfrRasterArgs& a, int n, i
   return true;
 }
 
+// The same fill with the TMA engine: the tile's 16 row segments of the four Fragments tensors and of the RGBA image are
+// bulk copies (cp.async.bulk shared -> global) out of constant patterns in shared memory - 80 copy instructions per
+// tile instead of 256 threads x 14 vector stores, issued with an evict-first L2 policy (the data is read once, by the
+// backward).  A group of `len` horizontally adjacent empty tiles is one set of copies (len x longer rows).  `pat` needs
+// ((2 + 3) * 16 K + 64) * len words.  Returns false when the run is clipped by the image border or rows are unaligned.
+__device__ __forceinline__ bool fill_empty_tile_bulk(const HfrRasterArgs& a, float* __restrict__ image, const float* bg, int n,
+                                                     int tx, int ty, int len, uint32_t* pat) {
+  const int K = a.K, W = a.W, H = a.H;
+  if ((tx + len) * kTileW > W || (ty + 1) * kTileH > H || ((W * K) & 3)) return false;
+  const int tid = threadIdx.x;
+  const int nid = 32 * K * len, nfl = 48 * K * len;   // words: ids row (16 px * K * 2 per tile), float row (16 px * K * 3)
+  uint32_t* pid = pat;
+  float* pfl = reinterpret_cast<float*>(pat + nid);
+  float* pim = pfl + nfl;
+  for (int i = tid; i < nid + nfl + 64 * len; i += kRasterThreads) {
+    if (i < nid) pid[i] = 0xffffffffu;
+    else if (i < nid + nfl) pfl[i - nid] = -1.0f;
+    else { const int e = (i - nid - nfl) & 3; pim[i - nid - nfl] = e < 3 ? bg[e] : 0.0f; }
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the bulk-copy engine
+  __syncthreads();
+  if (tid < 5 * kTileH) {
+    const int row = tid / 5, which = tid - 5 * row;
+    const size_t pix = ((size_t)n * H + (size_t)ty * kTileH + row) * W + (size_t)tx * kTileW;
+    void* dst;
+    const void* src;
+    uint32_t bytes;
+    if (which == 0) { dst = a.pix_to_face + pix * K; src = pid; bytes = 128u * K * len; }
+    else if (which == 1) { dst = a.zbuf + pix * K; src = pfl; bytes = 64u * K * len; }
+    else if (which == 2) { dst = a.dists + pix * K; src = pfl; bytes = 64u * K * len; }
+    else if (which == 3) { dst = a.bary + pix * K * 3; src = pfl; bytes = 192u * K * len; }
+    else { dst = image + pix * 4; src = pim; bytes = 256u * len; }
+    uint64_t policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst),
+                 "r"((uint32_t)__cvta_generic_to_shared(src)), "r"(bytes), "l"(policy)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the patterns must outlive the reads
+  }
+  return true;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Rasterizer workspace layout (32-bit words), filled by the setup pass (raster.cu) for Ftot packed faces / N meshes:
 //   [0, Ftot + 64)                     packed tile range per face (pack_tile_range)
@@ -521,7 +581,7 @@ __device__ __forceinline__ uint32_t face_rec_index(const uint32_t* __restrict__ 
 }
 
 // host helpers defined in raster.cu
-int launch_raster_setup(const HfrRasterArgs& a, uint32_t* ranges, cudaStream_t s);
+int launch_raster_setup(const HfrRasterArgs& a, uint32_t* ranges, cudaStream_t s, bool use_queue = false);
 const uint32_t* raster_mesh_box(const HfrRasterArgs& a);
 int check_raster(const HfrRasterArgs* a, const char* who);
 

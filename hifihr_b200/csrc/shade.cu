@@ -178,20 +178,70 @@ __device__ __forceinline__ void raster_shade_epilogue(const HfrRasterArgs& r, co
 #ifndef HFR_PAY_MAXK
 #define HFR_PAY_MAXK 4   // payload cache for K <= this (0 disables it: the epilogue recomputes the winners)
 #endif
+#ifndef HFR_FILL_TMA
+#define HFR_FILL_TMA 1   // tile-queue path: empty tiles are filled by bulk shared->global copies (0: vector stores)
+#endif
 template <int KMAX>
 __global__ void __launch_bounds__(kRasterThreads, (KMAX <= 4 ? HFR_RASTER_MINB : 1)) raster_shade_fwd_kernel(HfrRasterArgs r, HfrShadeFwdArgs s,
                                                                           const uint32_t* __restrict__ ranges,
-                                                                          const uint32_t* __restrict__ mesh_box) {
+                                                                          const uint32_t* __restrict__ mesh_box,
+                                                                          const uint32_t* __restrict__ queue) {
   __shared__ RasterSmem sm;
   constexpr bool PAY = KMAX <= HFR_PAY_MAXK;   // 16 B x K x 256 threads of payload cache next to the 30 KB tile state
   __shared__ float4 s_pay[PAY ? KMAX * kRasterThreads : 1];
-  PixelCtx c = make_pixel_ctx(r.H, r.W);
-  if ((HFR_FAST_FILL || (HFR_FAST_FILL_K1 && (r.K == 1 || (r.K & 3) == 0))) && tile_outside_mesh(mesh_box, c.n, c.tx, c.ty) && fill_empty_tile(r, c.n, c.tx, c.ty)) {
-    // no face touches this tile: Fragments are streamed out as whole rows, the pixel is the background
+  PixelCtx c;
+  bool empty_tile;
+  int run = 1;
+  if (queue) {
+    // cost-ordered queue (raster.cu): block i takes the next non-empty tile (heaviest class first) or the next group of
+    // empty tiles, the two kinds spread evenly so that the ALU-bound tiles and the HBM-bound fills share the SMs for the
+    // whole launch
+    const uint32_t nc = __ldg(queue), ng = __ldg(queue + 1), i = blockIdx.x, tot = nc + ng;
+    if (i >= tot) return;
+    const uint32_t ci = (uint32_t)(((uint64_t)i * nc) / tot), ci1 = (uint32_t)(((uint64_t)(i + 1) * nc) / tot);
+    empty_tile = ci1 == ci;
+    const int TX = (r.W + kTileW - 1) / kTileW, TY = (r.H + kTileH - 1) / kTileH;
+    const uint32_t T = (uint32_t)(r.N * TX * TY);
+    uint32_t t;
+    if (empty_tile) {
+      const uint32_t g = __ldg(queue + kQueueHdr + (size_t)(1 + kCostClasses) * T + (i - ci));
+      t = g & 0x0fffffffu;
+      run = (int)(g >> 28) + 1;
+    } else {
+      uint32_t left = ci;
+      int k = kCostClasses - 1;
+      for (; k > 0; --k) {
+        const uint32_t ck = __ldg(queue + 2 + k);
+        if (left < ck) break;
+        left -= ck;
+      }
+      t = __ldg(queue + kQueueHdr + T + (size_t)k * T + left);
+    }
+    const int n = (int)(t / (uint32_t)(TX * TY)), rem = (int)(t - (uint32_t)n * (uint32_t)(TX * TY));
+    c = make_pixel_ctx_at(n, rem % TX, rem / TX, r.H, r.W);
+  } else {
+    c = make_pixel_ctx(r.H, r.W);
+    empty_tile = (HFR_FAST_FILL || (HFR_FAST_FILL_K1 && (r.K == 1 || (r.K & 3) == 0))) && tile_outside_mesh(mesh_box, c.n, c.tx, c.ty);
+  }
+  if (empty_tile) {
+    // no face touches these tiles: Fragments are streamed out as whole rows, the pixels are the background
     const bool ones = s.p.blend == HFR_BLEND_SIGMOID_ALPHA;
-    const size_t pix = ((size_t)c.n * r.H + c.yi) * r.W + c.xi;
-    *reinterpret_cast<float4*>(s.image + pix * 4) = make_float4(ones ? 1.0f : s.p.background[0], ones ? 1.0f : s.p.background[1],
-                                                                ones ? 1.0f : s.p.background[2], 0.0f);
+    const float bg[3] = {ones ? 1.0f : s.p.background[0], ones ? 1.0f : s.p.background[1], ones ? 1.0f : s.p.background[2]};
+    if (HFR_FILL_TMA && queue && fill_empty_tile_bulk(r, s.image, bg, c.n, c.tx, c.ty, run, reinterpret_cast<uint32_t*>(sm.rec))) return;
+    for (int u = 0; u < run; ++u) {
+      PixelCtx cu = u == 0 ? c : make_pixel_ctx_at(c.n, c.tx + u, c.ty, r.H, r.W);
+      if ((r.K == 1 || (r.K & 3) == 0) && fill_empty_tile(r, cu.n, cu.tx, cu.ty)) {
+        const size_t pix = ((size_t)cu.n * r.H + cu.yi) * r.W + cu.xi;
+        *reinterpret_cast<float4*>(s.image + pix * 4) = make_float4(bg[0], bg[1], bg[2], 0.0f);
+      } else if (cu.pix_active) {   // clipped / unaligned tile: per-pixel fill
+        const size_t pix = ((size_t)cu.n * r.H + cu.yi) * r.W + cu.xi;
+        TopK<KMAX> none;
+        none.init();
+        float rgba[4];
+        raster_shade_epilogue<KMAX, false>(r, s, cu, none, pix, nullptr, kPermIdentity, rgba);
+        *reinterpret_cast<float4*>(s.image + pix * 4) = make_float4(rgba[0], rgba[1], rgba[2], rgba[3]);
+      }
+    }
     return;
   }
   TopK<KMAX> top;
@@ -374,9 +424,13 @@ extern "C" int hfr_raster_shade_forward(const HfrRasterShadeArgs* a, void* strea
   if (a->r.N == 0) return HFR_OK;
   cudaStream_t st = (cudaStream_t)stream;
   uint32_t* ranges = reinterpret_cast<uint32_t*>(a->r.workspace);
-  if (int rc = launch_raster_setup(a->r, ranges, st)) return rc;
+  const uint32_t* box = raster_mesh_box(a->r);
+  const bool use_queue = a->r.tile_queue != nullptr && box != nullptr;
+  if (int rc = launch_raster_setup(a->r, ranges, st, use_queue)) return rc;
   dim3 grid((a->r.W + kTileW - 1) / kTileW, (a->r.H + kTileH - 1) / kTileH, a->r.N);
-#define CALL(KM) raster_shade_fwd_kernel<KM><<<grid, kRasterThreads, 0, st>>>(a->r, s, ranges, raster_mesh_box(a->r))
+  const uint32_t* queue = use_queue ? reinterpret_cast<const uint32_t*>(a->r.tile_queue) : nullptr;
+  if (use_queue) grid = dim3(grid.x * grid.y * grid.z, 1, 1);
+#define CALL(KM) raster_shade_fwd_kernel<KM><<<grid, kRasterThreads, 0, st>>>(a->r, s, ranges, box, queue)
   HFR_DISPATCH_K(a->r.K, CALL);
 #undef CALL
   HFR_CHECK_LAUNCH("raster_shade_forward");

@@ -119,7 +119,7 @@ class FusedHandStep:
     def __init__(self, B, image_size=224, faces_per_pixel=4, blur_radius=None, sigma=1e-4, gamma=1e-4, soft=True,
                  texture_size=512, lambdas=None, device="cuda", mano_root=None, n_global=None, sil_scale=1.0,
                  aa_factor=1, binarize=False, want_nchw=False, face_records=False, tiled_backward=True,
-                 deterministic=True, rec_per_face=12, batched_hand=True):
+                 deterministic=True, rec_per_face=12, batched_hand=True, tile_queue=True):
         """aa_factor > 1 selects the SSAA-fused render (the reference's own setting is image_size=224,
         aa_factor=3, faces_per_pixel=1, soft=False, binarize=True, sil_scale=255; models_res_nimble.py:74-96,
         208-220): Fragments are rasterised at image_size*aa_factor, the pooled RGBA (B,S,S,4) is the only image
@@ -176,6 +176,7 @@ class FusedHandStep:
         self._out_set = 0
         self._bind_outputs()
         self.ws = ops.raster_workspace(B * Fm, dev)
+        self.tile_queue = ops.raster_tile_queue(B, Sr, Sr, dev) if (tile_queue and self.aa == 1) else None
         self.mesh_first = (torch.arange(B, device=dev, dtype=I64) * Fm).contiguous()
         self.mesh_nf = torch.full((B,), Fm, device=dev, dtype=I64)
         # every accumulated gradient lives in one flat buffer so a single memset clears them
@@ -257,7 +258,7 @@ class FusedHandStep:
             ops.face_attr_forward(self.topo.faces, self.verts_view, self.vnormals, self.faces_uvs, self.verts_uvs,
                                   self.face_attr)
         r = ops.raster_args(self.face_verts, self.mesh_first, self.mesh_nf, Sr, Sr, K, self.blur, True, self.blur > 0,
-                            False, self.p2f, self.zbuf, self.bary, self.dists, self.ws)
+                            False, self.p2f, self.zbuf, self.bary, self.dists, self.ws, self.tile_queue)
         s = ops.shade_fwd_args(self.params, (self.p2f, self.zbuf, self.bary, self.dists), self.topo.faces,
                                self.verts_view, self.vnormals, self.faces_uvs, self.verts_uvs, self.texture,
                                light_dir, light_color, self.image if self.aa == 1 else None, self.face_attr)

@@ -212,13 +212,18 @@ def geom_backward_raw(topo, verts, root_out, root_xyz, focal, prp, g_joints, g_r
 
 
 def raster_args(face_verts, mesh_first, mesh_nf, H, W, K, blur_radius, perspective_correct, clip_bary, cull,
-                pix_to_face, zbuf, bary, dists, workspace):
+                pix_to_face, zbuf, bary, dists, workspace, tile_queue=None):
     N = mesh_first.shape[0]
     return L.HfrRasterArgs(N, H, W, K, face_verts.shape[0], L.ptr(face_verts, F32, "face_verts"),
                            L.ptr(mesh_first, I64, "mesh_to_face_first_idx"), L.ptr(mesh_nf, I64, "num_faces_per_mesh"),
                            float(blur_radius), int(perspective_correct), int(clip_bary), int(cull),
                            L.ptr(pix_to_face, I64), L.ptr(zbuf, F32), L.ptr(bary, F32), L.ptr(dists, F32),
-                           L.ptr(workspace))
+                           L.ptr(workspace), L.ptr(tile_queue))
+
+
+def raster_tile_queue(N, H, W, device):
+    """Workspace of the cost-ordered tile queue of the fused rasterize+shade kernel."""
+    return torch.empty(int(L.lib().hfr_raster_queue_bytes(int(N), int(H), int(W))), dtype=torch.uint8, device=device)
 
 
 def raster_workspace(Ftot, device):

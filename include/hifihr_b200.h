@@ -202,8 +202,15 @@ typedef struct HfrRasterArgs {
   float* bary;                      /* (N,H,W,K,3)                                        */
   float* dists;                     /* (N,H,W,K)                                          */
   void* workspace;
+  /* optional cost-ordered tile queue (hfr_raster_queue_bytes(N, H, W) bytes): the setup pass counts the faces whose tile
+   * range covers each 16x16 tile and lists the tiles heaviest first; the fused kernel then runs them in that order with
+   * the tiles no face touches (pure -1 fills, streamed with bulk shared->global copies) spread evenly in between, so
+   * the ALU-bound and the HBM-bound work overlap and no heavy tile is left for the tail.  NULL = row-major tile order.
+   * Used by hfr_raster_shade_forward. */
+  void* tile_queue;
 } HfrRasterArgs;
 int64_t hfr_raster_workspace_bytes(int64_t Ftot);
+int64_t hfr_raster_queue_bytes(int32_t N, int32_t H, int32_t W);
 int hfr_raster_forward(const HfrRasterArgs* a, void* stream);
 
 typedef struct HfrRasterBwdArgs {
