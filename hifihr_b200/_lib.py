@@ -101,7 +101,7 @@ class HfrShadeBwdTiledArgs(C.Structure):
                 ("perspective_correct", i32), ("clip_barycentric", i32), ("raster_ws", vp), ("face_rec", vp),
                 ("rec_cap", i64), ("light_acc", vp), ("tex_acc", vp), ("g_texture", vp), ("fx_scale", vp), ("status", vp),
                 ("pool_aa", i32), ("pool_binarize", i32), ("gmax_bits", vp), ("fix_sums", vp), ("fix_w", vp),
-                ("fix_image", vp), ("fix_inv_scale", f32), ("fix_count", i64)]
+                ("fix_image", vp), ("fix_inv_scale", f32), ("fix_count", i64), ("tile_queue", vp)]
 
 
 class HfrGradFinishArgs(C.Structure):

@@ -27,7 +27,10 @@ namespace hfr {
 
 constexpr int kBT = 256;         // threads = pixels of one 16x16 tile; thread t <-> pixel (warp = 8x4 block, as the forward)
 constexpr int kBW = kBT / 32;
-constexpr int kCap = 128;        // distinct faces per pass (a tile with more is processed in several passes)
+#ifndef HFR_TILED_CAP
+#define HFR_TILED_CAP 128
+#endif
+constexpr int kCap = HFR_TILED_CAP;   // distinct faces per pass (a tile with more is processed in several passes)
 constexpr int kNC = 24;          // components summed per face: 18 vertex + 3 light direction / location + 3 light colour
 constexpr int kFR = 36;          // words per staged face record (144 B: LDS.128 rows of different faces spread over the banks)
 constexpr uint16_t kNoFrag = 0xffffu;
@@ -104,9 +107,29 @@ shade_bwd_tiled_kernel(HfrShadeBwdTiledArgs a, WsLayout L, int FW) {
   const HfrShadeFwdArgs& f = a.f;
   const HfrShadeParams& P = f.p;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int n = blockIdx.z, tx = blockIdx.x, ty = blockIdx.y, K = P.K, V = P.V;
+  const int K = P.K, V = P.V;
   const uint32_t* __restrict__ ws = reinterpret_cast<const uint32_t*>(a.raster_ws);
-  {   // tile outside this mesh's footprint: no fragment, no record
+  int n, tx, ty;
+  if (a.tile_queue) {
+    // the forward's tile queue: block i takes the i-th tile that holds faces, heaviest cost class first
+    const uint32_t* __restrict__ q = reinterpret_cast<const uint32_t*>(a.tile_queue);
+    uint32_t left = blockIdx.x;
+    if (left >= __ldg(q)) return;
+    const int TX = (P.W + kTileW - 1) / kTileW, TY = (P.H + kTileH - 1) / kTileH;
+    const uint32_t T = (uint32_t)(P.N * TX * TY);
+    int k = kCostClasses - 1;
+    for (; k > 0; --k) {
+      const uint32_t ck = __ldg(q + 2 + k);
+      if (left < ck) break;
+      left -= ck;
+    }
+    const uint32_t t = __ldg(q + kQueueHdr + T + (size_t)k * T + left);
+    n = (int)(t / (uint32_t)(TX * TY));
+    const int rem = (int)(t - (uint32_t)n * (uint32_t)(TX * TY));
+    tx = rem % TX; ty = rem / TX;
+  } else {
+    n = blockIdx.z; tx = blockIdx.x; ty = blockIdx.y;
+    // tile outside this mesh's footprint: no fragment, no record
     const uint4 bx = __ldg(reinterpret_cast<const uint4*>(ws + L.box) + n);
     if (tx < (int)bx.x || tx > 255 - (int)bx.y || ty < (int)bx.z || ty > 255 - (int)bx.w) return;
   }
@@ -596,6 +619,7 @@ extern "C" int hfr_shade_backward_tiled(const HfrShadeBwdTiledArgs* a, void* str
     HFR_CHECK_LAUNCH("face_rec_zero");
   }
   dim3 grid((p.W + kTileW - 1) / kTileW, (p.H + kTileH - 1) / kTileH, p.N);
+  if (a->tile_queue) grid = dim3(grid.x * grid.y * grid.z, 1, 1);
   const int FW = (p.F + 31) / 32;
 #define HFR_LAUNCH_T(KM)                                                                                         \
   do {                                                                                                           \

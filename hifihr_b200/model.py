@@ -283,7 +283,7 @@ class FusedHandStep:
                                        L.ptr(self.light_acc), L.ptr(self.tex_acc), None if self.deterministic else L.ptr(self.g_texture),
                                        L.ptr(self.fx_scale), L.ptr(self.status), self.aa if self.aa > 1 else 0, int(self.binarize),
                                        L.ptr(self.gmax_bits), L.ptr(self.sums), L.ptr(self.w), L.ptr(self.image),
-                                       1.0 / float(self.sil_scale), self.n_global * 3 * self.S * self.S)
+                                       1.0 / float(self.sil_scale), self.n_global * 3 * self.S * self.S, L.ptr(self.tile_queue))
             L.call("hfr_shade_backward_tiled", t)
             L.call("hfr_grad_finish", L.HfrGradFinishArgs(L.ptr(self.tex_acc), L.ptr(self.g_texture) if self.deterministic else None,
                                                           self.texture.numel() if self.deterministic else 0, L.ptr(self.light_acc),

@@ -365,6 +365,9 @@ typedef struct HfrShadeBwdTiledArgs {
    * fix_inv_scale = 1 / sil_scale, fix_count = N_global * 3 * H * W of the loss resolution */
   const float* fix_sums; const float* fix_w; const float* fix_image;
   float fix_inv_scale; int64_t fix_count;
+  /* optional: the tile queue the forward filled (HfrRasterArgs.tile_queue, same N / H / W): only tiles that hold faces are
+   * visited, heaviest class first.  NULL = every tile of the grid, row-major */
+  const void* tile_queue;
 } HfrShadeBwdTiledArgs;
 int hfr_shade_backward_tiled(const HfrShadeBwdTiledArgs* a, void* stream);
 
