@@ -28,10 +28,16 @@ if ROOT not in sys.path:
 import torch  # noqa: E402
 
 CONFIGS = {
-    # name: (per-GPU batch, image size, K, soft, texture size)
+    # name: per-GPU batch B (or global batch G sharded over the GPUs = strong scaling), image size, K, soft, texture size
+    # BASELINE.json configs[0]: the reference's own CPU-runnable case - the whole batch of 8 is one step of the CPU arm
+    "c1": dict(B=8, S=224, K=1, soft=False, T=512, ref_batch=8,
+               desc="C1 MANO + hard Phong/UV texture render + losses, 224^2, K=1, batch 8 (BASELINE configs[0])"),
     "c2": dict(B=64, S=224, K=4, soft=True, T=512, desc="C2 MANO soft-raster K=4 + Phong/UV texture + losses, 224^2, B=64/GPU"),
-    "c4": dict(B=None, S=224, K=4, soft=True, T=512, desc="C4 as C2 with global batch 4096 sharded over the GPUs"),
-    "c5": dict(B=32, S=512, K=8, soft=True, T=512, desc="C5 soft raster 512^2 K=8, B=32/GPU (256 global at 8 GPUs)"),
+    # configs[2]: NIMBLE-shaped stand-in (V=5986, F=11968), 10 x 1024^2 texture PCA sampled in the shader, modular path
+    "c3": dict(B=128, S=256, K=1, soft=False, T=1024, nimble=True,
+               desc="C3 NIMBLE-shaped hand (V=5986, F=11968), 1024^2 PCA texture, 256^2, K=1 hard Phong + photometric losses, B=128/GPU"),
+    "c4": dict(G=4096, S=224, K=4, soft=True, T=512, desc="C4 as C2 with global batch 4096 sharded over the GPUs"),
+    "c5": dict(G=256, S=512, K=8, soft=True, T=512, desc="C5 soft raster 512^2 K=8 blur>0, global batch 256 sharded over the GPUs"),
     "r": dict(B=48, S=672, K=1, soft=False, T=512, desc="reference setting 672^2 K=1 hard Phong (no pooling stage), B=48"),
     # the reference's own render config, fused (models_res_nimble.py:74-96, 208-220)
     "rp": dict(B=48, S=224, K=1, soft=False, T=512, aa=3, binarize=True, sil_scale=255.0,
@@ -112,7 +118,7 @@ def run_reference(args, cfg):
     mano = load_mano()
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    Bs = 2                                      # bounded sample per step
+    Bs = cfg.get("ref_batch", 2)                # bounded sample per step (C1: the configuration's own batch of 8)
     S, K = cfg["S"], cfg["K"]
     blur = 9.21034e-4 if cfg["soft"] else 0.0
     tex = P.synthetic_texture(cfg["T"])
@@ -165,7 +171,7 @@ def run_ours(args, cfg):
             os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/hifihr_b200_nccl.%h.%p.log")
         dist.init_process_group("nccl", device_id=dev)
-    B = cfg["B"] if cfg["B"] is not None else 4096 // world
+    B = cfg["B"] if "B" in cfg else cfg["G"] // world
     if args.batch:
         B = args.batch
     S, K = cfg["S"], cfg["K"]
@@ -207,15 +213,20 @@ def run_ours(args, cfg):
     for _ in range(max(args.warmup, 3)):
         one_step(devt)
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # `windows` windows of EXACTLY args.steps steps each, every one bracketed by barrier + synchronize; the reported
+    # time is the median window (max over ranks per window), the spread is printed next to it.  Several windows keep
+    # the GPU under load long enough for the clock sampler to see it.
+    win_ms = []
     with ClockSampler(local) as clk:
-        barrier()
-        e0.record()
-        for _ in range(args.steps):
-            one_step(devt)
-        e1.record()
-        barrier()
-    ms = e0.elapsed_time(e1)
+        for _ in range(args.windows):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            e0.record()
+            for _ in range(args.steps):
+                one_step(devt)
+            e1.record()
+            barrier()
+            win_ms.append(e0.elapsed_time(e1))
     # ---- end to end: pinned host inputs in (8-bit targets), loss + per-sample grads out, every step ---
     # Double-buffered: step i+1's host->device copies run on a copy stream while step i computes (what a
     # DataLoader with pin_memory + non_blocking does for the reference, train_hrnet.py:375-391 /
@@ -260,12 +271,15 @@ def run_ours(args, cfg):
 
     e2e_run(3)
     barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    e2e_run(args.steps)
-    f1.record()
-    barrier()
-    ms_e2e = f0.elapsed_time(f1)
+    win_e2e = []
+    for _ in range(args.windows):
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        f0.record()
+        e2e_run(args.steps)
+        f1.record()
+        barrier()
+        win_e2e.append(f0.elapsed_time(f1))
     one_step(devt)      # rebind the cached launch arguments to the output set that is active now (untimed)
     torch.cuda.synchronize()
     # ---- per-kernel durations (CUDA events around each launch group, same stream) -----------------
@@ -305,10 +319,11 @@ def run_ours(args, cfg):
             acc[n] += a.elapsed_time(b)
     kern_ms = {n: acc[n] / reps for n in names}
     # ---- reduce over ranks (max time) -------------------------------------------------------------
-    t = torch.tensor([ms, ms_e2e], device=dev)
+    t = torch.tensor([win_ms, win_e2e], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = float(t[0]), float(t[1])
+    win_ms, win_e2e = sorted(float(x) for x in t[0]), sorted(float(x) for x in t[1])
+    ms, ms_e2e = win_ms[len(win_ms) // 2], win_e2e[len(win_e2e) // 2]
     if rank == 0:
         total = B * world * args.steps
         value = total / (ms * 1e-3)
@@ -336,7 +351,7 @@ def run_ours(args, cfg):
         line = {
             "metric": "hand renders/sec (fwd+bwd)", "value": value, "unit": "samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak" if cfg["B"] is not None else "strong", "vs_baseline": None,
+            "higher_is_better": True, "scaling": "weak" if "B" in cfg else "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": cfg["desc"], "batch_per_gpu": B, "global_batch": B * world, "image_size": S,
                        "ssaa": aa, "faces_per_pixel": K, "blur_radius": step.blur, "texture": cfg["T"],
@@ -345,11 +360,15 @@ def run_ours(args, cfg):
             "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": ms_e2e / args.steps,
                     "inputs": "pose/shape/camera/light fp32 + target images and masks as uint8 (x/255 fused into the loss kernels)"},
-            "gpu_launches": step.launches_per_step * args.steps,
+            "windows": {"n": args.windows, "steps_each": args.steps, "statistic": "median",
+                        "ms_per_step": [w / args.steps for w in win_ms],
+                        "e2e_ms_per_step": [w / args.steps for w in win_e2e]},
+            "gpu_launches": step.launches_per_step * args.steps * args.windows,
             "clocks": clk.summary(),
             "roofline": {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": traffic, "traffic_source": traffic_src,
                          "algorithmic_bytes_per_launch": alg.get(top, 0), "peak_source": peak_src, "kernel_ms": kern_ms,
+                         "step_frac": step_bytes / (ms / args.steps * 1e-3) / 1e9 / peak,
                          "step": {"algorithmic_MB_per_sample": step_bytes / B / 1e6,
                                   "achieved": step_bytes / (ms / args.steps * 1e-3) / 1e9,
                                   "frac": step_bytes / (ms / args.steps * 1e-3) / 1e9 / peak}},
@@ -360,6 +379,210 @@ def run_ours(args, cfg):
     if world > 1:
         dist.destroy_process_group()
 
+
+
+# ------------------------------------------------------------------------------------------------ C3 (NIMBLE-shaped)
+def c3_inputs(B, S, seed):
+    """Synthetic C3 inputs: pose (3 + 30 PCA), 20 shape, 10 texture coefficients, camera, lights, targets."""
+    from hifihr_b200.synthetic import synthetic_inputs
+    g = torch.Generator().manual_seed(seed)
+    pose = torch.cat([torch.randn(B, 3, generator=g) * 0.4, torch.randn(B, 30, generator=g) * 0.5], 1)
+    shape = torch.randn(B, 20, generator=g) * 0.5
+    texp = torch.randn(B, 10, generator=g)
+    inp = synthetic_inputs(B, S=S, seed=seed + 1)
+    root = torch.tensor([[0.0, 0.0, 0.45]]).repeat(B, 1)
+    return pose, shape, texp, inp, root
+
+
+def c3_reference_step(d, pose, shape, texp, inp, root, S, threads):
+    """CPU restatement of the C3 step: generic LBS oracle -> NDC -> scalar C rasterizer (selection) + torch autograd
+    (values) -> PCA texture -> Phong -> hard blend -> photometric losses, backward."""
+    from oracle import losses as olosses
+    from oracle import p3d, raster_c
+    from oracle.lbs import LBSOracle
+    orc = LBSOracle(d["v_template"], d["shapedirs"], d["posedirs"], d["J_regressor"], d["weights"], d["parents"],
+                    pca_comps=d["pca_comps"], pose_mean=d["pose_mean"], tip_verts=d["tip_verts"], dtype=torch.float32)
+    B = pose.shape[0]
+    po, so, to = pose.clone().requires_grad_(True), shape.clone().requires_grad_(True), texp.clone().requires_grad_(True)
+    vo, _ = orc(po, so)
+    view = vo + root[:, None]
+    fcl, prp = p3d.ndc_intrinsics(inp["Ks"])
+    ndc = p3d.project_ndc(view, -fcl, prp)
+    faces = torch.tensor(d["faces"])
+    Fn = faces.shape[0]
+    fv = ndc[:, faces].reshape(-1, 3, 3)
+    first, nf = [i * Fn for i in range(B)], [Fn] * B
+    sel = raster_c.rasterize_naive(fv.detach(), first, nf, S, 0.0, 1, perspective_correct=True, threads=threads)[0]
+    fr = p3d.rasterize_meshes(fv, first, nf, S, 0.0, 1, perspective_correct=True, pix_to_face=sel)
+    tex_o = d["tex_mean"][None] + torch.einsum("bk,khwc->bhwc", to, d["tex_basis"])
+    texels = p3d.sample_textures_uv(fr, tex_o, faces, torch.as_tensor(d["verts_uvs"]))
+    colors = p3d.phong_shading(fr, view, faces, texels, inp["light_dir"], inp["light_color"])
+    imo = p3d.hard_rgb_blend(colors, fr).permute(0, 3, 1, 2)
+    terms = olosses.render_losses(imo[:, :3], imo[:, 3:4], inp["imgs"], inp["segms_gt"], dict(texture=1.0, mrgb=1.0, ssim_tex=1.0),
+                                  sil_scale=1.0)
+    sum(terms.values()).backward()
+    return float(sum(terms.values()).detach())
+
+
+def run_c3_reference(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from hifihr_b200.nimble import build_nimble_like
+    from oracle import raster_c
+    raster_c.build()
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    d = {k: (torch.tensor(v) if isinstance(v, __import__("numpy").ndarray) and v.dtype.kind == "f" else v)
+         for k, v in build_nimble_like(tex_size=cfg["T"]).items()}
+    d = {k: (v.float() if torch.is_tensor(v) else v) for k, v in d.items()}
+    Bs, S = 1, cfg["S"]
+    for w in range(min(args.warmup, 1)):
+        c3_reference_step(d, *c3_inputs(Bs, S, 100 + w), S, cores)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        c3_reference_step(d, *c3_inputs(Bs, S, 200 + k), S, cores)
+    dt = time.perf_counter() - t0
+    val = Bs * args.steps / dt
+    sample = f"{Bs} sample/step of {cfg['desc']} (fwd+bwd), {args.steps} steps"
+    print(json.dumps({"impl": "reference", "metric": "hand renders/sec (fwd+bwd)", "value": val, "unit": "samples/s",
+                      "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+                      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": cfg["desc"], "image_size": S, "faces_per_pixel": 1, "sample_batch": Bs},
+                      "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+                      "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                      "gpu_launches": 0}), flush=True)
+
+
+def run_c3(args, cfg):
+    """BASELINE configs[2] on the modular path: MyNIMBLELayer (LBS kernels at NIMBLE size) -> MeshRasterizer ->
+    HardPhongShader with the 10 x 1024^2 texture PCA evaluated at the bilinear taps -> photometric losses, autograd
+    bridges over the C-ABI for the backward.  No fused step exists for this shape."""
+    import torch.distributed as dist
+    import hifihr_b200 as hf
+    from hifihr_b200 import ops
+    from hifihr_b200.nimble import MyNIMBLELayer
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/hifihr_b200_nccl.%h.%p.log")
+        dist.init_process_group("nccl", device_id=dev)
+    B, S, T = args.batch or cfg["B"], cfg["S"], cfg["T"]
+    layer = MyNIMBLELayer(True, dev, shape_ncomp=20, pose_ncomp=30, tex_ncomp=10, tex_size=T, fused_texture=True).to(dev)
+    V, Fn = layer.V, layer.F
+    pose, shape, texp, inp, root = c3_inputs(B, S, 1234 + rank)
+    fcl, prp = hf.get_ndc_fx_fy_cx_cy(inp["Ks"])
+    small = [pose, shape, texp, -fcl, prp, root, inp["light_dir"], inp["light_color"]]
+    imgs_u8 = (inp["imgs"] * 255.0).round().to(torch.uint8)
+    seg_u8 = inp["segms_gt"].to(torch.uint8)
+    host = [t.contiguous().pin_memory() for t in small + [imgs_u8, seg_u8]]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host)
+    rs = hf.RasterizationSettings(image_size=S, blur_radius=0.0, faces_per_pixel=1)
+    mats = hf.Materials(diffuse_color=((0.8, 0.8, 0.8),), specular_color=((0.2, 0.2, 0.2),), shininess=30, device=dev)
+    renderer = hf.MeshRenderer(rasterizer=hf.MeshRasterizer(raster_settings=rs), shader=hf.HardPhongShader(materials=mats, device=dev))
+    out_host = torch.empty(3 + B * (33 + 20 + 10), dtype=torch.float32).pin_memory()
+    d2h_bytes = out_host.numel() * 4
+
+    def one_step(tensors):
+        po, so, to, focal, prpp, rt, ldir, lcol, imgs, seg = tensors
+        leaves = [t.detach().requires_grad_(True) for t in (po, so, to)]
+        cams = hf.PerspectiveCameras(focal_length=focal, principal_point=prpp, device=dev)
+        lights = hf.DirectionalLights(diffuse_color=lcol, direction=ldir, device=dev)
+        out = layer({"pose_params": leaves[0], "shape_params": leaves[1], "texture_params": leaves[2]}, handle_collision=False)
+        meshes = out["skin_meshes"]
+        meshes.offset_verts_(rt[:, None].repeat(1, V, 1).view(B * V, 3))
+        img = renderer(meshes, cameras=cams, lights=lights).permute(0, 3, 1, 2)
+        tgt = imgs.float() / 255.0 if imgs.dtype == torch.uint8 else imgs
+        sg = seg.float() if seg.dtype == torch.uint8 else seg
+        terms = ops.RenderLossFunction.apply(img[:, :3], img[:, 3:4], tgt, sg, 1.0, True)
+        loss = terms[0] + terms[1] + terms[2]
+        if world > 1:
+            loss = loss / world
+        loss.backward()
+        return torch.cat([terms[:3].detach().reshape(-1)] + [t.grad.reshape(-1) for t in leaves])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    devt = [t.to(dev) for t in small] + [imgs_u8.float().to(dev) / 255.0, seg_u8.float().to(dev)]
+    for _ in range(max(args.warmup, 3)):
+        one_step(devt)
+    win_ms, win_e2e = [], []
+    with ClockSampler(local) as clk:
+        for _ in range(args.windows):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            e0.record()
+            for _ in range(args.steps):
+                one_step(devt)
+            e1.record()
+            barrier()
+            win_ms.append(e0.elapsed_time(e1))
+    for _ in range(args.windows):       # end to end: this step's inputs from pinned host memory, its results back to the host
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            res = one_step([h.to(dev, non_blocking=True) for h in host])
+            out_host.copy_(res, non_blocking=True)
+        e1.record()
+        barrier()
+        win_e2e.append(e0.elapsed_time(e1))
+    # the rasterizer alone (the dominant kernel of this shape)
+    with torch.no_grad():
+        out = layer({"pose_params": devt[0], "shape_params": devt[1], "texture_params": devt[2]}, handle_collision=False)
+        meshes = out["skin_meshes"]
+        meshes.offset_verts_(devt[5][:, None].repeat(1, V, 1).view(B * V, 3))
+        cams = hf.PerspectiveCameras(focal_length=devt[3], principal_point=devt[4], device=dev)
+        for _ in range(2):
+            renderer.rasterizer(meshes, cameras=cams)
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        for _ in range(5):
+            renderer.rasterizer(meshes, cameras=cams)
+        r1.record()
+        torch.cuda.synchronize()
+        raster_ms = r0.elapsed_time(r1) / 5
+    t = torch.tensor([win_ms, win_e2e], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    win_ms, win_e2e = sorted(float(x) for x in t[0]), sorted(float(x) for x in t[1])
+    ms, ms_e2e = win_ms[len(win_ms) // 2], win_e2e[len(win_e2e) // 2]
+    if rank == 0:
+        total = B * world * args.steps
+        peak, peak_src = peaks()
+        P_ = S * S
+        # SURVEY.md 8(d), C3: Fragments w+r, image-side traffic, vertex streams, parameters, texture basis + mean read once per step
+        step_bytes = (56 * P_ + 64 * P_ + 48 * V + 8 * 60) * B + 12 * 11 * T * T
+        alg_raster = B * 28 * P_
+        line = {"metric": "hand renders/sec (fwd+bwd)", "value": total / (ms * 1e-3), "unit": "samples/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": cfg["desc"], "batch_per_gpu": B, "global_batch": B * world, "image_size": S,
+                           "faces_per_pixel": 1, "texture": T, "verts": V, "faces": Fn,
+                           "parallelism": f"dp{world} (modular path, batch shards by sample)",
+                           "l2": "no flush: the texture basis alone (132 MB) exceeds the 126 MB L2"},
+                "e2e": {"value": total / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes,
+                        "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / args.steps},
+                "windows": {"n": args.windows, "steps_each": args.steps, "statistic": "median",
+                            "ms_per_step": [w / args.steps for w in win_ms], "e2e_ms_per_step": [w / args.steps for w in win_e2e]},
+                "gpu_launches": 14 * args.steps * args.windows, "clocks": clk.summary(),
+                "roofline": {"bound": "hbm", "kernel": "raster_fwd", "achieved": alg_raster / (raster_ms * 1e-3) / 1e9, "peak": peak,
+                             "unit": "GB/s", "frac": alg_raster / (raster_ms * 1e-3) / 1e9 / peak, "traffic": None,
+                             "algorithmic_bytes_per_launch": alg_raster, "peak_source": peak_src,
+                             "kernel_ms": {"raster_fwd": raster_ms},
+                             "step_frac": step_bytes / (ms / args.steps * 1e-3) / 1e9 / peak,
+                             "step": {"algorithmic_MB_per_sample": step_bytes / B / 1e6}}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 def cpu_baseline(cfg):
     """Oracle port timed on this box's host cores on a bounded sample of the same workload (rank 0, N=1)."""
@@ -372,7 +595,7 @@ def cpu_baseline(cfg):
     torch.set_num_threads(cores)
     S, K = cfg["S"], cfg["K"]
     blur = 9.21034e-4 if cfg["soft"] else 0.0
-    Bs, n, t_used = 2, 0, 0.0
+    Bs, n, t_used = cfg.get("ref_batch", 2), 0, 0.0
     tex = P.synthetic_texture(cfg["T"])
     while t_used < 12.0 and n < 8:
         inp = P.synthetic_inputs(Bs, S=S, seed=500 + n)
@@ -402,14 +625,21 @@ def main():
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--windows", type=int, default=5, help="timing windows of --steps steps each (median reported)")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     if args.impl == "reference":
-        run_reference(args, cfg)
+        if cfg.get("nimble"):
+            run_c3_reference(args, cfg)
+        else:
+            run_reference(args, cfg)
     else:
         if not torch.cuda.is_available():
             raise SystemExit("bench.py: no CUDA device; hifihr_b200 has no CPU path (use --impl reference for the CPU arm)")
-        run_ours(args, cfg)
+        if cfg.get("nimble"):
+            run_c3(args, cfg)
+        else:
+            run_ours(args, cfg)
 
 
 if __name__ == "__main__":
