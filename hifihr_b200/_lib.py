@@ -54,7 +54,7 @@ class HfrGeomFwdArgs(C.Structure):
 class HfrGeomBwdArgs(C.Structure):
     _fields_ = [("B", i32), ("root_out", i32), ("verts", vp), ("root_xyz", vp), ("focal", vp), ("prp", vp),
                 ("g_joints", vp), ("g_verts_rel", vp), ("g_verts_view", vp), ("g_verts_ndc", vp),
-                ("g_vnormals", vp), ("g_verts", vp), ("face_rec", vp), ("raster_ws", vp), ("status", vp)]
+                ("g_vnormals", vp), ("g_verts", vp), ("face_rec", vp), ("raster_ws", vp), ("status", vp), ("rec_partial", vp)]
 
 
 class HfrRasterArgs(C.Structure):
@@ -165,7 +165,7 @@ ENTRY_POINTS = [
     "hfr_raster_shade_pool_forward", "hfr_face_attr_forward", "hfr_pool_forward", "hfr_pool_backward", "hfr_loss_forward", "hfr_loss_backward",
     "hfr_keypoint_forward", "hfr_keypoint_backward", "hfr_shade_backward_tiled", "hfr_grad_finish",
     "hfr_loss_partials_floats", "hfr_mano_packed_basis_bytes", "hfr_mano_pack_basis", "hfr_mano_workspace_bytes",
-    "hfr_mano_batched_status", "hfr_raster_queue_bytes",
+    "hfr_mano_batched_status", "hfr_raster_queue_bytes", "hfr_geom_rec_partial_floats",
 ]
 
 _lib = None
@@ -190,6 +190,8 @@ def lib() -> C.CDLL:
         _lib.hfr_raster_tile_box.argtypes = [C.c_void_p, C.c_int64, C.c_int32]
         _lib.hfr_loss_partials_floats.restype = C.c_int64
         _lib.hfr_loss_partials_floats.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+        _lib.hfr_geom_rec_partial_floats.restype = C.c_int64
+        _lib.hfr_geom_rec_partial_floats.argtypes = [C.c_void_p, C.c_int32]
         _lib.hfr_raster_queue_bytes.restype = C.c_int64
         _lib.hfr_raster_queue_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32]
         _lib.hfr_mano_packed_basis_bytes.restype = C.c_int64

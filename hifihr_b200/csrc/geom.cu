@@ -71,6 +71,30 @@ __device__ __forceinline__ void gather_face_rec(const HfrTopology& t, const floa
   }
 }
 
+// The same sum for ONE incidence entry (one thread per (sample, entry), chip-wide): out[idx][6]
+__global__ void __launch_bounds__(256) rec_gather_kernel(HfrTopology t, const float* __restrict__ rec, const uint32_t* __restrict__ ws,
+                                                         hfr::WsLayout L, int B, float* __restrict__ out) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int E = 3 * t.F;
+  if (idx >= (int64_t)B * E) return;
+  const int b = (int)(idx / E), e = (int)(idx - (int64_t)b * E);
+  const int code = __ldg(t.vf_idx + e), f = code >> 2, c = code & 3;
+  const int64_t fp = (int64_t)b * t.F + f;
+  const uint32_t r = __ldg(ws + fp);
+  float o[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (r != hfr::kEmptyRange) {
+    const int nx = (int)((r >> 8) & 255) - (int)(r & 255) + 1, ny = (int)(r >> 24) - (int)((r >> 16) & 255) + 1;
+    const size_t base = (size_t)__ldg(ws + L.blk + (fp >> 8)) + __ldg(ws + L.loc + fp);
+    const float2* __restrict__ q = reinterpret_cast<const float2*>(rec + base * HFR_FACE_REC_FLOATS + 6 * c);
+    for (int j = 0; j < nx * ny; ++j) {
+      const float2 a0 = __ldg(q + 9 * j), a1 = __ldg(q + 9 * j + 1), a2 = __ldg(q + 9 * j + 2);
+      o[0] += a0.x; o[1] += a0.y; o[2] += a1.x; o[3] += a1.y; o[4] += a2.x; o[5] += a2.y;
+    }
+  }
+  float2* dst = reinterpret_cast<float2*>(out + idx * 6);
+  dst[0] = make_float2(o[0], o[1]); dst[1] = make_float2(o[2], o[3]); dst[2] = make_float2(o[4], o[5]);
+}
+
 // Shared by fwd/bwd: stage verts, regress joints, find root; leaves view-space verts in s_view.
 // s_pos (NOUT*3) holds un-shifted output joints, s_root[3] the predicted root.
 __device__ void geom_stage(const HfrTopology& t, int B, int b, int root_out, const float* __restrict__ verts,
@@ -186,7 +210,16 @@ __global__ void __launch_bounds__(kThreads) geom_bwd_kernel(HfrTopology t, HfrGe
   for (int v = tid; v < V; v += kThreads) {
     float g[3] = {0.f, 0.f, 0.f};
     float r6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (from_rec) {
+    if (from_rec && a.rec_partial) {
+      // the entries were summed chip-wide (rec_gather_kernel); add this vertex's entries in CSR order
+      const int e0 = __ldg(t.vf_ptr + v), e1 = __ldg(t.vf_ptr + v + 1);
+      const float2* __restrict__ q = reinterpret_cast<const float2*>(a.rec_partial + ((size_t)b * 3 * t.F) * 6);
+      for (int e = e0; e < e1; ++e) {
+        const float2 a0 = __ldg(q + 3 * e), a1 = __ldg(q + 3 * e + 1), a2 = __ldg(q + 3 * e + 2);
+        r6[0] += a0.x; r6[1] += a0.y; r6[2] += a1.x; r6[3] += a1.y; r6[4] += a2.x; r6[5] += a2.y;
+      }
+      s_g[3 * v] = r6[0]; s_g[3 * v + 1] = r6[1]; s_g[3 * v + 2] = r6[2];
+    } else if (from_rec) {
       gather_face_rec(t, a.face_rec, ws, L, b, v, r6);
       // s_v is dead after geom_stage: park d/d(view) there for step 2
       s_g[3 * v] = r6[0]; s_g[3 * v + 1] = r6[1]; s_g[3 * v + 2] = r6[2];
@@ -302,6 +335,10 @@ static int check_topo(const HfrTopology* t, int need_joints) {
 }
 }  // namespace
 
+extern "C" int64_t hfr_geom_rec_partial_floats(const HfrTopology* t, int32_t B) {
+  return (t && B > 0) ? (int64_t)B * 3 * t->F * 6 : 0;
+}
+
 extern "C" int hfr_geom_forward(const HfrTopology* t, const HfrGeomFwdArgs* a, void* stream) {
   HFR_CHECK_ARG(a && a->B >= 0, "geom_forward: null argument");
   if (a->B == 0) return HFR_OK;
@@ -329,6 +366,12 @@ extern "C" int hfr_geom_backward(const HfrTopology* t, const HfrGeomBwdArgs* a, 
   const size_t smem = (size_t)(9 * t->V + 6 * (t->NJR > 0 ? t->NJR : 1) + 3 * (t->NOUT > 0 ? t->NOUT : 1) + 16 + 3 * (kThreads / 32)) * sizeof(float);
   HFR_CHECK_ARG(smem <= 227 * 1024, "geom_backward: mesh too large for shared memory");
   if (smem > 48 * 1024) cudaFuncSetAttribute(geom_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (a->face_rec && a->rec_partial) {
+    const int64_t total = (int64_t)a->B * 3 * t->F;
+    rec_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        *t, a->face_rec, reinterpret_cast<const uint32_t*>(a->raster_ws), hfr::ws_layout((int64_t)a->B * t->F), a->B, a->rec_partial);
+    HFR_CHECK_LAUNCH("geom_backward (record gather)");
+  }
   geom_bwd_kernel<<<a->B, kThreads, smem, (cudaStream_t)stream>>>(*t, *a);
   HFR_CHECK_LAUNCH("geom_backward");
   return HFR_OK;

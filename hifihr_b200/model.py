@@ -10,6 +10,8 @@ FusedHandStep     — the same computation as ONE forward+backward sequence of r
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import numpy as np
 import torch
 from torch import nn
@@ -197,6 +199,7 @@ class FusedHandStep:
         if self.tiled:
             self.rec_cap = int(rec_per_face) * B * Fm + 4096
             self.face_rec = e(self.rec_cap, L.FACE_REC_FLOATS)
+            self.rec_partial = e(int(L.lib().hfr_geom_rec_partial_floats(C.byref(self.topo.struct), B)))
             self.light_acc = torch.zeros(B, 6, dtype=I64, device=dev)
             self.tex_acc = torch.zeros(self.texture.shape, dtype=I64, device=dev) if self.deterministic else None
             self.status = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -213,7 +216,8 @@ class FusedHandStep:
         # kernels of OURS per step(): mano, geom, [face records], raster setup, raster+shade(+pool), loss | loss', shade'+raster',
         # geom', mano'  (the two torch memsets of the accumulators are not counted)
         # tiled backward: + raster scan, record clear, gradient finish (the fixed-point scale is two small torch reductions)
-        self.launches_per_step = 9 + (1 if face_records else 0) + (4 if self.tiled else 0) + (4 if self.mano_ws is not None else 0)
+        self.launches_per_step = (9 + (1 if face_records else 0) + (5 if self.tiled else 0) + (4 if self.mano_ws is not None else 0)
+                                  + (1 if self.tile_queue is not None else 0))
         if self.tiled and not self.deterministic:
             self.g_light_dir.zero_()
 
@@ -300,7 +304,7 @@ class FusedHandStep:
     def launch_geom_backward(self, focal, prp, root_xyz):
         if self.tiled:   # gathers d/d(view), d/d(normal) from the (face, tile) records in a fixed order
             ops.geom_backward_raw(self.topo, self.verts, 9, root_xyz, focal, prp, None, None, None, None, None, self.g_verts,
-                                  face_rec=self.face_rec, raster_ws=self.ws, status=self.status)
+                                  face_rec=self.face_rec, raster_ws=self.ws, status=self.status, rec_partial=self.rec_partial)
         else:
             ops.geom_backward_raw(self.topo, self.verts, 9, root_xyz, focal, prp, None, None, self.g_view, self.g_ndc,
                                   self.g_vn, self.g_verts)

@@ -203,11 +203,11 @@ def geom_forward_raw(topo, verts, root_out, root_xyz, focal, prp, joints, verts_
 
 
 def geom_backward_raw(topo, verts, root_out, root_xyz, focal, prp, g_joints, g_rel, g_view, g_ndc, g_vn, g_verts,
-                      face_rec=None, raster_ws=None, status=None):
+                      face_rec=None, raster_ws=None, status=None, rec_partial=None):
     a = L.HfrGeomBwdArgs(verts.shape[0], root_out, L.ptr(verts, F32), L.ptr(root_xyz, F32), L.ptr(focal, F32),
                          L.ptr(prp, F32), L.ptr(g_joints, F32), L.ptr(g_rel, F32), L.ptr(g_view, F32),
                          L.ptr(g_ndc, F32), L.ptr(g_vn, F32), L.ptr(g_verts, F32), L.ptr(face_rec, F32),
-                         L.ptr(raster_ws), L.ptr(status))
+                         L.ptr(raster_ws), L.ptr(status), L.ptr(rec_partial, F32))
     L.call("hfr_geom_backward", topo.struct, a)
 
 

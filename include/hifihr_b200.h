@@ -181,7 +181,12 @@ typedef struct HfrGeomBwdArgs {
   const float* face_rec;
   const void* raster_ws;      /* the rasterizer workspace (tile ranges + record offsets), Ftot = B * F, mesh n = faces [n F, (n+1) F) */
   const uint32_t* status;     /* record-store status word of the backward; non-zero -> g_verts = NaN */
+  /* optional scratch of hfr_geom_rec_partial_floats(t, B) floats: the records are first summed per (sample, incidence entry)
+   * by a chip-wide launch (one thread per entry: the dependent range -> slot -> record loads of all entries overlap), the
+   * per-sample kernel then adds a vertex's entries in CSR order (a fixed order: reproducible run to run) */
+  float* rec_partial;
 } HfrGeomBwdArgs;
+int64_t hfr_geom_rec_partial_floats(const HfrTopology* t, int32_t B);
 int hfr_geom_backward(const HfrTopology* t, const HfrGeomBwdArgs* a, void* stream);
 
 /* ------------------------------------------------------------------ rasterizer
