@@ -131,7 +131,8 @@ class HfrPoolBwdArgs(C.Structure):
 class HfrLossArgs(C.Structure):
     _fields_ = [("N", i32), ("H", i32), ("W", i32), ("sil_scale", f32), ("want_ssim", i32), ("want_grad", i32), ("nhwc", i32),
                 ("re_img", vp), ("re_sil", vp), ("imgs", vp), ("seg", vp), ("sums", vp), ("gauss", vp), ("dmaps", vp),
-                ("tile_flags", vp), ("mask_mode", i32), ("imgs_u8", vp), ("seg_u8", vp), ("partials", vp), ("ticket", vp)]
+                ("tile_flags", vp), ("mask_mode", i32), ("imgs_u8", vp), ("seg_u8", vp), ("partials", vp), ("ticket", vp),
+                ("dmaps_box", vp), ("dmaps_box_aa", i32)]
 
 
 class HfrLossBwdArgs(C.Structure):

@@ -120,6 +120,90 @@ __device__ __forceinline__ float ssim_point(float m1, float m2, float e11, float
 
 constexpr size_t kLossFwdSmem = (size_t)(6 * kLH * kXP + 5 * kLH * kHP) * sizeof(float);
 
+// One colour channel of the SSIM stencil over the CTA's 32x32 tile (halo arrays in shared memory): separable 11-tap
+// Gaussian of the moment maps, SSIM value summed over this thread's 4 pixels, derivative maps written when `want_d`.
+// XZERO: x vanishes on the whole halo, so mu_x = E[x^2] = E[xy] = +0 exactly and only (y, y^2) are filtered.
+template <bool XZERO>
+__device__ __forceinline__ float ssim_channel(const HfrLossArgs& a, float (*xs)[kXP], float (*ys)[kXP], float (*hb)[kLH][kHP],
+                                              const float (&g)[11], int n, int c, int x0, int y0, size_t hw, bool want_d) {
+  constexpr int NM = XZERO ? 2 : 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // ---- horizontal pass: (halo row, strip of 8 outputs) per thread ------------------------------
+  if (tid < kHTasks) {
+    const int row = tid >> 2, strip = tid & 3;
+    float acc[8][NM];
+#pragma unroll
+    for (int o = 0; o < 8; ++o)
+#pragma unroll
+      for (int m = 0; m < NM; ++m) acc[o][m] = 0.f;
+    const float4* xr = reinterpret_cast<const float4*>(&xs[row][strip * 8]);
+    const float4* yr = reinterpret_cast<const float4*>(&ys[row][strip * 8]);
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+      const float4 yv = yr[q];
+      float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (!XZERO) xv = xr[q];
+      const float xa[4] = {xv.x, xv.y, xv.z, xv.w}, ya[4] = {yv.x, yv.y, yv.z, yv.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = 4 * q + e;
+        if (j < 18) {
+          float val[NM];
+          if (XZERO) { val[0] = ya[e]; val[1] = ya[e] * ya[e]; }
+          else { val[0] = xa[e]; val[1] = ya[e]; val[2] = xa[e] * xa[e]; val[NM - 2] = ya[e] * ya[e]; val[NM - 1] = xa[e] * ya[e]; }
+          tap_accumulate<NM>(acc, val, j, g);
+        }
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < NM; ++m) {
+      float4* dst = reinterpret_cast<float4*>(&hb[m][row][strip * 8]);
+      dst[0] = make_float4(acc[0][m], acc[1][m], acc[2][m], acc[3][m]);
+      dst[1] = make_float4(acc[4][m], acc[5][m], acc[6][m], acc[7][m]);
+    }
+  }
+  __syncthreads();
+  // ---- vertical pass: (column, strip of 4 rows) per thread, then the SSIM map --------------------
+  const int x = lane, rs = warp;       // 8 warps x 4 rows = 32 rows
+  float acc[4][NM];
+#pragma unroll
+  for (int o = 0; o < 4; ++o)
+#pragma unroll
+    for (int m = 0; m < NM; ++m) acc[o][m] = 0.f;
+#pragma unroll
+  for (int j = 0; j < 14; ++j) {
+    float val[NM];
+#pragma unroll
+    for (int m = 0; m < NM; ++m) val[m] = hb[m][rs * 4 + j][x];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      const int t = j - o;
+      if (t >= 0 && t < 11) {
+#pragma unroll
+        for (int m = 0; m < NM; ++m) acc[o][m] = fmaf(g[t], val[m], acc[o][m]);
+      }
+    }
+  }
+  const int gx = x0 + x;
+  float ss = 0.f;
+#pragma unroll
+  for (int o = 0; o < 4; ++o) {
+    const int gy = y0 + rs * 4 + o;
+    if (gx < a.W && gy < a.H) {
+      float dm1, de11, de12;
+      if (XZERO) ss += ssim_point(0.f, acc[o][0], 0.f, acc[o][NM - 1], 0.f, &dm1, &de11, &de12);
+      else ss += ssim_point(acc[o][0], acc[o][1], acc[o][2], acc[o][NM - 2], acc[o][NM - 1], &dm1, &de11, &de12);
+      if (want_d) {
+        const size_t p = (size_t)gy * a.W + gx;
+        a.dmaps[((size_t)n * 9 + c * 3 + 0) * hw + p] = dm1;
+        a.dmaps[((size_t)n * 9 + c * 3 + 1) * hw + p] = de11;
+        a.dmaps[((size_t)n * 9 + c * 3 + 2) * hw + p] = de12;
+      }
+    }
+  }
+  return ss;
+}
+
 // METRIC = the evaluation-time texture metrics (train_hrnet.py:149-161, compute_texture_metric.py:49-60): both
 // images are multiplied by the SAME mask (mask_mode 1: segms_gt, 2: re_sil > 0 as for HO3D) and the sum of squared
 // differences (-> L2 / PSNR) is accumulated next to L1 and SSIM.  The training variant compiles without it.
@@ -144,7 +228,18 @@ __global__ void __launch_bounds__(kLossThreads, 3) loss_fwd_kernel(HfrLossArgs a
     for (int t = 0; t < 11; ++t) g[t] = __ldg(a.gauss + t);
   }
   float l1 = 0.f, sr = 0.f, st = 0.f, sl = 0.f, ss = 0.f, mul = 0.f, add = 0.f, l2 = 0.f;
+  // derivative maps: only where the box-limited backward will read them (within 5 px of the 32x32 tiles touching the mesh box)
+  bool want_d = a.dmaps != nullptr;
+  if (want_d && a.dmaps_box) {
+    const uint4 bx = __ldg(reinterpret_cast<const uint4*>(a.dmaps_box) + n);
+    const int aa = a.dmaps_box_aa > 1 ? a.dmaps_box_aa : 1;
+    const int bx0 = ((int)bx.x * 16) / aa, bx1 = ((256 - (int)bx.y) * 16 + aa - 1) / aa;   // pixel range [bx0, bx1) of the box
+    const int by0 = ((int)bx.z * 16) / aa, by1 = ((256 - (int)bx.w) * 16 + aa - 1) / aa;
+    constexpr int kM = kLT + kR + 2;   // a touching tile reaches 31 px beyond the box, its stencil 5 more
+    want_d = x0 + kLT > bx0 - kM && x0 < bx1 + kM && y0 + kLT > by0 - kM && y0 < by1 + kM && bx0 < bx1 && by0 < by1;
+  }
   bool nz_halo = false;   // any non-zero x / y sample in the tile's halo
+  bool nz_x = false;      // any non-zero x sample in the halo
   __shared__ unsigned char sub_nz[64];   // per 4x4 block of the interior: holds a non-zero sample
   __shared__ float lut[256];             // k / 255 for the 8-bit target transport
   if (tid < 64) sub_nz[tid] = 0;
@@ -201,6 +296,7 @@ __global__ void __launch_bounds__(kLossThreads, 3) loss_fwd_kernel(HfrLossArgs a
           vy[c] = sy * im[u][c];
           const bool nzv = vx[c] != 0.0f || vy[c] != 0.0f;
           nz_halo |= nzv;
+          nz_x |= vx[c] != 0.0f;
           if (interior) {
             l1 += fabsf(vx[c] - vy[c]); sr += vx[c]; st += vy[c]; nz_in |= nzv;
             if (METRIC) { const float df = vx[c] - vy[c]; l2 += df * df; }
@@ -234,7 +330,7 @@ __global__ void __launch_bounds__(kLossThreads, 3) loss_fwd_kernel(HfrLossArgs a
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           ss += S;
-          if (a.dmaps) {
+          if (want_d) {
             a.dmaps[((size_t)n * 9 + c * 3 + 0) * hw + p] = dm1;
             a.dmaps[((size_t)n * 9 + c * 3 + 1) * hw + p] = de11;
             a.dmaps[((size_t)n * 9 + c * 3 + 2) * hw + p] = de12;
@@ -243,79 +339,14 @@ __global__ void __launch_bounds__(kLossThreads, 3) loss_fwd_kernel(HfrLossArgs a
       }
     }
   }
-  for (int c = 0; c < 3; ++c) {
-    float (*xs)[kXP] = xs3[c];
-    float (*ys)[kXP] = ys3[c];
-    if (!a.want_ssim || !any_halo) continue;
-    if (c > 0) __syncthreads();
-    // ---- horizontal pass: (halo row, strip of 8 outputs) per thread ------------------------------
-    if (tid < kHTasks) {
-      const int row = tid >> 2, strip = tid & 3;
-      float acc[8][5];
-#pragma unroll
-      for (int o = 0; o < 8; ++o)
-#pragma unroll
-        for (int m = 0; m < 5; ++m) acc[o][m] = 0.f;
-      const float4* xr = reinterpret_cast<const float4*>(&xs[row][strip * 8]);
-      const float4* yr = reinterpret_cast<const float4*>(&ys[row][strip * 8]);
-#pragma unroll
-      for (int q = 0; q < 5; ++q) {
-        const float4 xv = xr[q], yv = yr[q];
-        const float xa[4] = {xv.x, xv.y, xv.z, xv.w}, ya[4] = {yv.x, yv.y, yv.z, yv.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int j = 4 * q + e;
-          if (j < 18) {
-            const float val[5] = {xa[e], ya[e], xa[e] * xa[e], ya[e] * ya[e], xa[e] * ya[e]};
-            tap_accumulate<5>(acc, val, j, g);
-          }
-        }
-      }
-#pragma unroll
-      for (int m = 0; m < 5; ++m) {
-        float4* dst = reinterpret_cast<float4*>(&hb[m][row][strip * 8]);
-        dst[0] = make_float4(acc[0][m], acc[1][m], acc[2][m], acc[3][m]);
-        dst[1] = make_float4(acc[4][m], acc[5][m], acc[6][m], acc[7][m]);
-      }
-    }
-    __syncthreads();
-    // ---- vertical pass: (column, strip of 4 rows) per thread, then the SSIM map --------------------
-    {
-      const int x = lane, rs = warp;       // 8 warps x 4 rows = 32 rows
-      float acc[4][5];
-#pragma unroll
-      for (int o = 0; o < 4; ++o)
-#pragma unroll
-        for (int m = 0; m < 5; ++m) acc[o][m] = 0.f;
-#pragma unroll
-      for (int j = 0; j < 14; ++j) {
-        float val[5];
-#pragma unroll
-        for (int m = 0; m < 5; ++m) val[m] = hb[m][rs * 4 + j][x];
-#pragma unroll
-        for (int o = 0; o < 4; ++o) {
-          const int t = j - o;
-          if (t >= 0 && t < 11) {
-#pragma unroll
-            for (int m = 0; m < 5; ++m) acc[o][m] = fmaf(g[t], val[m], acc[o][m]);
-          }
-        }
-      }
-      const int gx = x0 + x;
-#pragma unroll
-      for (int o = 0; o < 4; ++o) {
-        const int gy = y0 + rs * 4 + o;
-        if (gx < a.W && gy < a.H) {
-          float dm1, de11, de12;
-          ss += ssim_point(acc[o][0], acc[o][1], acc[o][2], acc[o][3], acc[o][4], &dm1, &de11, &de12);
-          if (a.dmaps) {
-            const size_t p = (size_t)gy * a.W + gx;
-            a.dmaps[((size_t)n * 9 + c * 3 + 0) * hw + p] = dm1;
-            a.dmaps[((size_t)n * 9 + c * 3 + 1) * hw + p] = de11;
-            a.dmaps[((size_t)n * 9 + c * 3 + 2) * hw + p] = de12;
-          }
-        }
-      }
+  if (a.want_ssim && any_halo) {
+    // the rendered image vanishes on the whole halo (a tile of the target mask away from the hand): its three moments
+    // are exactly +0 and only the two target moments go through the stencil
+    const bool xzero = !__syncthreads_or(nz_x);
+    for (int c = 0; c < 3; ++c) {
+      if (c > 0) __syncthreads();
+      ss += xzero ? ssim_channel<true>(a, xs3[c], ys3[c], hb, g, n, c, x0, y0, hw, want_d)
+                  : ssim_channel<false>(a, xs3[c], ys3[c], hb, g, n, c, x0, y0, hw, want_d);
     }
   }
   // ---- block reduction of the partial sums -------------------------------------------------------------------

@@ -252,7 +252,8 @@ class FusedHandStep:
                                         L.ptr(self.sums), L.ptr(self.gauss), L.ptr(self.dmaps), L.ptr(self.tile_flags), 0,
                                         L.ptr(imgs, torch.uint8, "imgs") if u8i else None,
                                         L.ptr(seg, torch.uint8, "seg") if u8s else None,
-                                        L.ptr(self.loss_partials), L.ptr(self.loss_ticket))
+                                        L.ptr(self.loss_partials), L.ptr(self.loss_ticket),
+                                        ops.raster_tile_box(self.ws, B * self.topo.F, B) if self.tiled else None, self.aa)
         L.call("hfr_loss_forward", self._loss_args)
 
     def launch_raster_shade(self, light_dir, light_color, imgs=None):

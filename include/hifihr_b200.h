@@ -482,6 +482,11 @@ typedef struct HfrLossArgs {
    * atomic per CTA and component (the sums then differ in the last bits from run to run). */
   float* partials;
   uint32_t* ticket;
+  /* optional (fused step): the rasterizer's per-mesh tile box (hfr_raster_tile_box) and the ratio rasterised / loss
+   * resolution.  The backward that is limited to that box (HfrLossBwdArgs.tile_box) reads the derivative maps only
+   * within 5 pixels of the 32x32 tiles touching it, so the forward writes `dmaps` only there.  NULL = everywhere. */
+  const uint32_t* dmaps_box;
+  int32_t dmaps_box_aa;
 } HfrLossArgs;
 int64_t hfr_loss_partials_floats(int32_t N, int32_t H, int32_t W);
 int hfr_loss_forward(const HfrLossArgs* a, void* stream);
