@@ -161,6 +161,10 @@ __device__ __forceinline__ void raster_shade_epilogue(const HfrRasterArgs& r, co
 #ifndef HFR_RASTER_MINB
 #define HFR_RASTER_MINB 4
 #endif
+#ifndef HFR_RASTER_MINB8
+#define HFR_RASTER_MINB8 4   // K = 8: measured on B200 at C5 (512^2, B=32): 1 CTA/SM (148 registers) 1943 us, 2: 1142, 3: 957, 4: 937
+#endif
+#define HFR_RASTER_MINB_FOR(KMAX) ((KMAX) <= 4 ? HFR_RASTER_MINB : ((KMAX) <= 8 ? HFR_RASTER_MINB8 : 2))
 // Tiles outside the mesh can stream their -1 Fragments as whole rows (fill_empty_tile).  Measured on B200: with
 // the generic unit loop (any K) neutral to slightly slower in the one-tile-per-CTA kernel (473 -> 480 us at 672^2
 // K=1) - off; with the fixed-role K=1 / K=4 paths (HFR_FAST_FILL_K1) a win there (K=1 672^2: 472 -> 426 us, C2 K=4:
@@ -182,7 +186,7 @@ __device__ __forceinline__ void raster_shade_epilogue(const HfrRasterArgs& r, co
 #define HFR_FILL_TMA 1   // tile-queue path: empty tiles are filled by bulk shared->global copies (0: vector stores)
 #endif
 template <int KMAX>
-__global__ void __launch_bounds__(kRasterThreads, (KMAX <= 4 ? HFR_RASTER_MINB : 1)) raster_shade_fwd_kernel(HfrRasterArgs r, HfrShadeFwdArgs s,
+__global__ void __launch_bounds__(kRasterThreads, HFR_RASTER_MINB_FOR(KMAX)) raster_shade_fwd_kernel(HfrRasterArgs r, HfrShadeFwdArgs s,
                                                                           const uint32_t* __restrict__ ranges,
                                                                           const uint32_t* __restrict__ mesh_box,
                                                                           const uint32_t* __restrict__ queue) {
@@ -265,7 +269,7 @@ struct PoolOut {
   float* pooled; float* re_img; float* re_sil; float* mask_rgbs;
 };
 template <int KMAX>
-__global__ void __launch_bounds__(kRasterThreads, (KMAX <= 4 ? HFR_RASTER_MINB : 1)) raster_shade_pool_fwd_kernel(
+__global__ void __launch_bounds__(kRasterThreads, HFR_RASTER_MINB_FOR(KMAX)) raster_shade_pool_fwd_kernel(
     HfrRasterArgs r, HfrShadeFwdArgs s, PoolOut po, const uint32_t* __restrict__ ranges, const uint32_t* __restrict__ mesh_box) {
   __shared__ RasterSmem sm;
   __shared__ float4 s_tile[kTileH * kTileW];

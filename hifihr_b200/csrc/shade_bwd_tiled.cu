@@ -43,7 +43,6 @@ struct TSmem {
   float part[KMAX * 8][2][kNC];           // per chunk: partial sums of a face that continues from / into a neighbour chunk
   float pix[7][kBT];                      // per pixel: gnum[3], gden, g_alpha, gzmax, kmax (int bits)
   float frag[KMAX][3][kBT];               // per fragment: sigmoid prob, softmax exponent, prod_{j != k} (1 - p_j)
-  float bary[KMAX * 3][kBT];              // per fragment: barycentrics, loaded with the pixel's other Fragments (coalesced)
   uint32_t masks[kCap][8];                // per slot of the pass: which of the 256 pixels hold that face
   int offs[kCap + 1];                     // exclusive prefix of the slots' fragment counts
   uint16_t sorted[KMAX * kBT];            // fragments (pixel | k << 8) grouped by slot, pixel order inside a slot
@@ -98,8 +97,11 @@ __device__ __forceinline__ float fx_from_gmax(float g) {
 #ifndef HFR_TILED_MINB
 #define HFR_TILED_MINB 2
 #endif
+#ifndef HFR_TILED_MINB8
+#define HFR_TILED_MINB8 2   // K = 8: 2 CTAs / SM (128 registers, 102 KB shared memory each): C5 backward 1538 -> 1110 us (B=32)
+#endif
 template <int KMAX>
-__global__ void __launch_bounds__(kBT, (KMAX <= 4 ? HFR_TILED_MINB : 1))
+__global__ void __launch_bounds__(kBT, (KMAX <= 4 ? HFR_TILED_MINB : (KMAX <= 8 ? HFR_TILED_MINB8 : 1)))
 shade_bwd_tiled_kernel(HfrShadeBwdTiledArgs a, WsLayout L, int FW) {
   extern __shared__ __align__(16) unsigned char smraw[];
   TSmem<KMAX>& sm = *reinterpret_cast<TSmem<KMAX>*>(smraw);
@@ -195,21 +197,6 @@ shade_bwd_tiled_kernel(HfrShadeBwdTiledArgs a, WsLayout L, int FW) {
 #pragma unroll
         for (int k = 0; k < KMAX; ++k)
           if (k < K) { z[k] = __ldg(f.zbuf + pix * K + k); d[k] = __ldg(f.dists + pix * K + k); }
-      }
-      {   // the pixel's barycentrics: 3 K contiguous floats, requested here with the rest of its Fragments so that the
-          // per-fragment pass below never waits on a scattered DRAM load
-        const float* __restrict__ bp = f.bary + pix * K * 3;
-        if (K == KMAX && (KMAX % 4) == 0) {
-#pragma unroll
-          for (int e = 0; e < KMAX * 3; e += 4) {
-            const float4 q = __ldg(reinterpret_cast<const float4*>(bp + e));
-            sm.bary[e][tid] = q.x; sm.bary[e + 1][tid] = q.y; sm.bary[e + 2][tid] = q.z; sm.bary[e + 3][tid] = q.w;
-          }
-        } else {
-#pragma unroll
-          for (int e = 0; e < KMAX * 3; ++e)
-            if (e < K * 3) sm.bary[e][tid] = __ldg(bp + e);
-        }
       }
       float4 g4;
       if (a.pool_aa > 1) {   // gradient of the pooled image: avg_pool2d backward folded into the load
@@ -417,8 +404,10 @@ shade_bwd_tiled_kernel(HfrShadeBwdTiledArgs a, WsLayout L, int FW) {
         const float4* __restrict__ r4 = reinterpret_cast<const float4*>(sm.facerec[slot]);
         const int pw = p >> 5, pl = p & 31;
         const int lx = (pw & 1) * 8 + (pl & 7), ly = (pw >> 1) * 4 + (pl >> 3);
+        const size_t fpix = ((size_t)n * P.H + (ty * kTileH + ly)) * P.W + (tx * kTileW + lx);
         const float xf = sm.tabx[lx], yf = sm.taby[ly];
-        const float bc[3] = {sm.bary[3 * k][p], sm.bary[3 * k + 1][p], sm.bary[3 * k + 2][p]};
+        const float* __restrict__ bp = f.bary + (fpix * K + k) * 3;
+        const float bc[3] = {__ldg(bp), __ldg(bp + 1), __ldg(bp + 2)};
         const float pk = sm.frag[k][0][p], ek = sm.frag[k][1][p];
         const float gnum[3] = {sm.pix[0][p], sm.pix[1][p], sm.pix[2][p]};
         const float gden = sm.pix[3][p], gzmax = sm.pix[5][p];
