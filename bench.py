@@ -40,7 +40,7 @@ CONFIGS = {
     "c5": dict(G=256, S=512, K=8, soft=True, T=512, desc="C5 soft raster 512^2 K=8 blur>0, global batch 256 sharded over the GPUs"),
     "r": dict(B=48, S=672, K=1, soft=False, T=512, desc="reference setting 672^2 K=1 hard Phong (no pooling stage), B=48"),
     # the reference's own render config, fused (models_res_nimble.py:74-96, 208-220)
-    "rp": dict(B=48, S=224, K=1, soft=False, T=512, aa=3, binarize=True, sil_scale=255.0,
+    "rp": dict(B=48, S=224, K=1, soft=False, T=512, aa=3, binarize=True, sil_scale=255.0, tiled=False,
                desc="R reference setting: 672^2 K=1 hard Phong + 3x3 SSAA pool + binarised alpha fused, losses at 224^2, B=48"),
 }
 LAMBDAS = dict(texture=1.0, mrgb=1.0, ssim_tex=1.0, sil=1.0, iou=0.0)
@@ -180,7 +180,11 @@ def run_ours(args, cfg):
                             lambdas=LAMBDAS, device=dev, n_global=B * world, sil_scale=cfg.get("sil_scale", 1.0),
                             aa_factor=aa, binarize=cfg.get("binarize", False),
                             face_records=bool(os.environ.get("HFR_FACE_RECORDS")),     # env: A/B tuning only
-                            tile_queue=os.environ.get("HFR_TILE_QUEUE", "1") != "0")
+                            tile_queue=os.environ.get("HFR_TILE_QUEUE", "1") != "0",
+                            # K=1 hard rasterization at 672^2 has ~1 fragment per covered pixel: the per-tile sort of the
+                            # atomics-free backward costs more than it saves there (605 vs 417 us) - that config keeps the
+                            # scatter backward (not bit-reproducible); everything else uses the deterministic tiled backward
+                            tiled_backward=cfg.get("tiled", True))
     inp = synthetic_inputs(B, S=S, seed=1234 + rank)
     fcl, prp = hf.get_ndc_fx_fy_cx_cy(inp["Ks"])
     # Target images are 8-bit in the datasets the reference trains on (its loader applies ToTensor = x / 255 on the
@@ -352,7 +356,7 @@ def run_ours(args, cfg):
         # DRAM bytes of one launch of that kernel from the committed `ncu --set full` capture (same workload only)
         traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        kname = {"raster_shade_fwd": "raster_shade_fwd_kernel", "shade_raster_bwd": "shade_bwd_kernel",
+        kname = {"raster_shade_fwd": "raster_shade_fwd_kernel", "shade_raster_bwd": "shade_bwd_tiled_kernel" if step.tiled else "shade_bwd_kernel",
                  "loss_fwd": "loss_fwd_kernel", "loss_bwd": "loss_bwd_kernel"}.get(top)
         if args.config == "c2" and B == 64 and kname and os.path.isfile(tpath):
             tj = json.load(open(tpath))
