@@ -224,9 +224,30 @@ def run_ours(args, cfg):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # The step is replayed from a CUDA graph (one driver call per step instead of ~17 launches through python/ctypes:
+    # 650 us of host time per eager step would bound the 900 us step as soon as several ranks share the host's cores).
+    # HFR_GRAPH=0 times the eager launches instead; a failed capture falls back to them and says so in `config`.
+    use_graph = os.environ.get("HFR_GRAPH", "1") != "0"
+    graph_note = "eager launches"
+
+    def make_graph(tensors):
+        return step.capture(*tensors, shared_grad_hook=hdist.all_reduce_shared_grads_async,
+                            sums_hook=hdist.all_reduce_loss_sums_async)
+
+    dev_graph = None
+    if use_graph:
+        try:
+            dev_graph = make_graph(devt)
+            graph_note = "CUDA graph replay (one graph launch per step)"
+        except Exception as e:   # noqa: BLE001
+            graph_note = f"eager launches (graph capture failed: {type(e).__name__})"
+            dev_graph = None
+            torch.cuda.synchronize()
+    run_dev = (lambda t: dev_graph.replay()) if dev_graph is not None else one_step
+
     # ---- device-resident timing ----------------------------------------------------------------
     for _ in range(max(args.warmup, 3)):
-        one_step(devt)
+        run_dev(devt)
     barrier()
     # `windows` windows of EXACTLY args.steps steps each, every one bracketed by barrier + synchronize; the reported
     # time is the median window (max over ranks per window), the spread is printed next to it.  Several windows keep
@@ -238,7 +259,7 @@ def run_ours(args, cfg):
             barrier()
             e0.record()
             for _ in range(args.steps):
-                one_step(devt)
+                run_dev(devt)
             e1.record()
             barrier()
             win_ms.append(e0.elapsed_time(e1))
@@ -261,6 +282,19 @@ def run_ours(args, cfg):
             raw[slot].copy_(host, non_blocking=True)
             ready[slot].record(copy_stream)
 
+    e2e_graphs = {}
+    if dev_graph is not None:
+        try:
+            for r in raw:
+                r.copy_(host)
+            for slot in (0, 1):          # every (input slot, output set) combination the loop can meet
+                for _ in (0, 1):
+                    e2e_graphs[(slot, step._out_set)] = make_graph(bufs[slot])
+                    step.flip_outputs()
+        except Exception:   # noqa: BLE001
+            e2e_graphs = {}
+            torch.cuda.synchronize()
+
     def e2e_run(nsteps):
         # The step's results (loss sums + per-sample gradients, one flat buffer) go back on a third stream while the
         # next step computes into the other output set; a set is only rewritten after its copy has finished.
@@ -274,7 +308,11 @@ def run_ours(args, cfg):
             main_stream.wait_event(ready[cur])
             oset = step._out_set
             main_stream.wait_event(d2h_done[oset])      # this output set was copied out (two steps ago)
-            one_step(bufs[cur])
+            g = e2e_graphs.get((cur, oset))
+            if g is not None:
+                g.replay()
+            else:
+                one_step(bufs[cur])
             consumed[cur].record(main_stream)
             done = torch.cuda.Event()
             done.record(main_stream)
@@ -371,6 +409,7 @@ def run_ours(args, cfg):
             "config": {"workload": cfg["desc"], "batch_per_gpu": B, "global_batch": B * world, "image_size": S,
                        "ssaa": aa, "faces_per_pixel": K, "blur_radius": step.blur, "texture": cfg["T"],
                        "parallelism": f"dp{world} (batch shards by sample; NCCL all-reduce of loss sums + texture grad)",
+                       "launch": graph_note,
                        "l2": f"no flush: per-step working set ({(28 * K * aa * aa + 32) * P_ * B / 1e6:.0f} MB Fragments+images) exceeds the 126 MB L2"},
             "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": ms_e2e / args.steps,
