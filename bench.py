@@ -431,7 +431,15 @@ def run_ours(args, cfg):
             line["cpu_baseline"] = cpu_baseline(cfg)
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # graphs that captured NCCL collectives must be gone before the communicator is; tearing the process group down
+        # with them alive was seen to hang, so the ranks meet at a barrier and leave without the destructor
+        dev_graph = None
+        e2e_graphs.clear()
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 
