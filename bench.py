@@ -264,17 +264,20 @@ def run_ours(args, cfg):
             barrier()
             win_ms.append(e0.elapsed_time(e1))
     # ---- end to end: pinned host inputs in (8-bit targets), loss + per-sample grads out, every step ---
-    # Double-buffered: step i+1's host->device copies run on a copy stream while step i computes (what a
-    # DataLoader with pin_memory + non_blocking does for the reference, train_hrnet.py:375-391 /
-    # utils/traineval_util.py:26-96).  Every step's inputs cross PCIe inside the timed region.
+    # Double-buffered (NB = 2): step i+1's inputs cross PCIe on a copy stream while step i computes (what a DataLoader
+    # with pin_memory + non_blocking does for the reference, train_hrnet.py:375-391 / utils/traineval_util.py:26-96).
+    # Every step's inputs cross PCIe inside the timed region.  A third buffer (two steps of prefetch) was measured at
+    # N = 8 and made the end-to-end step SLOWER (1.10 -> 1.28 ms): more host->device traffic in flight, not less slack,
+    # is what costs there.
+    NB = 2
     copy_stream = torch.cuda.Stream(device=dev)
     d2h_stream = torch.cuda.Stream(device=dev)
     main_stream = torch.cuda.current_stream(dev)
     d2h_done = [torch.cuda.Event() for _ in range(2)]
-    raw = [torch.empty(total_b, dtype=torch.uint8, device=dev) for _ in range(2)]
+    raw = [torch.empty(total_b, dtype=torch.uint8, device=dev) for _ in range(NB)]
     bufs = [field_views(r) for r in raw]
-    ready = [torch.cuda.Event() for _ in range(2)]
-    consumed = [torch.cuda.Event() for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(NB)]
+    consumed = [torch.cuda.Event() for _ in range(NB)]
 
     def enqueue_copy(slot):
         with torch.cuda.stream(copy_stream):
@@ -287,7 +290,7 @@ def run_ours(args, cfg):
         try:
             for r in raw:
                 r.copy_(host)
-            for slot in (0, 1):          # every (input slot, output set) combination the loop can meet
+            for slot in range(NB):       # every (input slot, output set) combination the loop can meet
                 for _ in (0, 1):
                     e2e_graphs[(slot, step._out_set)] = make_graph(bufs[slot])
                     step.flip_outputs()
@@ -300,11 +303,12 @@ def run_ours(args, cfg):
         # next step computes into the other output set; a set is only rewritten after its copy has finished.
         for ev in consumed + d2h_done:
             ev.record(main_stream)
-        enqueue_copy(0)
+        for j in range(min(NB - 1, nsteps)):
+            enqueue_copy(j)
         for i in range(nsteps):
-            cur = i & 1
-            if i + 1 < nsteps:
-                enqueue_copy(cur ^ 1)
+            cur = i % NB
+            if i + NB - 1 < nsteps:
+                enqueue_copy((i + NB - 1) % NB)
             main_stream.wait_event(ready[cur])
             oset = step._out_set
             main_stream.wait_event(d2h_done[oset])      # this output set was copied out (two steps ago)
