@@ -204,8 +204,11 @@ __global__ void __launch_bounds__(1024) raster_scan_kernel(uint32_t* __restrict_
   if (tid == 0) blk[nblk] = s_carry;
 }
 
+#ifndef HFR_RASTERONLY_MINB
+#define HFR_RASTERONLY_MINB 5   // C3 standalone rasterizer (B=128, 256^2, 11968 faces): 3 CTAs/SM 2.83 ms, 4: 2.47, 5: 2.34
+#endif
 template <int KMAX>
-__global__ void __launch_bounds__(kRasterThreads) raster_fwd_kernel(HfrRasterArgs a, const uint32_t* __restrict__ ranges,
+__global__ void __launch_bounds__(kRasterThreads, (KMAX <= 8 ? HFR_RASTERONLY_MINB : 2)) raster_fwd_kernel(HfrRasterArgs a, const uint32_t* __restrict__ ranges,
                                                                     const uint32_t* __restrict__ mesh_box) {
   __shared__ RasterSmem sm;
   PixelCtx c = make_pixel_ctx(a.H, a.W);
