@@ -180,7 +180,10 @@ __device__ __forceinline__ void raster_shade_epilogue(const HfrRasterArgs& r, co
 #define HFR_FAST_FILL_POOL 1
 #endif
 #ifndef HFR_PAY_MAXK
-#define HFR_PAY_MAXK 4   // payload cache for K <= this (0 disables it: the epilogue recomputes the winners)
+#define HFR_PAY_MAXK 4   // payload cache for K <= this (0 disables it: the epilogue recomputes the winners); the slot
+                          // permutation is one nibble per sorted position of a 32-bit word, so 8 is the limit.  K = 8 with
+                          // the cache (32 KB more shared memory, 3 instead of 4 CTAs / SM) measured SLOWER: C5 B=32 forward
+                          // 937 -> 1073 us
 #endif
 #ifndef HFR_FILL_TMA
 #define HFR_FILL_TMA 1   // tile-queue path: empty tiles are filled by bulk shared->global copies (0: vector stores)
@@ -192,7 +195,7 @@ __global__ void __launch_bounds__(kRasterThreads, HFR_RASTER_MINB_FOR(KMAX)) ras
                                                                           const uint32_t* __restrict__ queue) {
   __shared__ RasterSmem sm;
   constexpr bool PAY = KMAX <= HFR_PAY_MAXK;   // 16 B x K x 256 threads of payload cache next to the 30 KB tile state
-  __shared__ float4 s_pay[PAY ? KMAX * kRasterThreads : 1];
+  extern __shared__ __align__(16) float4 s_pay[];   // dynamic (K = 8: 32 KB, beyond the static limit): PAY ? KMAX * 256 : 0 entries
   PixelCtx c;
   bool empty_tile;
   int run = 1;
@@ -434,7 +437,13 @@ extern "C" int hfr_raster_shade_forward(const HfrRasterShadeArgs* a, void* strea
   dim3 grid((a->r.W + kTileW - 1) / kTileW, (a->r.H + kTileH - 1) / kTileH, a->r.N);
   const uint32_t* queue = use_queue ? reinterpret_cast<const uint32_t*>(a->r.tile_queue) : nullptr;
   if (use_queue) grid = dim3(grid.x * grid.y * grid.z, 1, 1);
-#define CALL(KM) raster_shade_fwd_kernel<KM><<<grid, kRasterThreads, 0, st>>>(a->r, s, ranges, box, queue)
+#define CALL(KM)                                                                                              \
+  do {                                                                                                        \
+    const size_t pay = (KM) <= HFR_PAY_MAXK ? (size_t)(KM) * kRasterThreads * sizeof(float4) : 0;             \
+    if (pay + sizeof(RasterSmem) > 48 * 1024)                                                                 \
+      cudaFuncSetAttribute(raster_shade_fwd_kernel<KM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pay); \
+    raster_shade_fwd_kernel<KM><<<grid, kRasterThreads, pay, st>>>(a->r, s, ranges, box, queue);             \
+  } while (0)
   HFR_DISPATCH_K(a->r.K, CALL);
 #undef CALL
   HFR_CHECK_LAUNCH("raster_shade_forward");
