@@ -450,3 +450,83 @@ def test_record_store_overflow_fails_loudly(hf):
     with pytest.raises(hf._lib.HfrError):
         step.check_status()
     assert torch.isnan(step.g_pose).any()
+
+
+# ------------------------------------------------------------------------------------------ tile queue / graphs
+def _step_args(inp):
+    fcl, prp = p3d.ndc_intrinsics(inp["Ks"])
+    d = lambda t: t.to(DEV).contiguous()  # noqa: E731
+    return (d(inp["pose"]), d(inp["betas"]), d(-fcl), d(prp), d(inp["root_xyz"]), d(inp["light_dir"]),
+            d(inp["light_color"]), d(inp["imgs"]), d(inp["segms_gt"].float()))
+
+
+@pytest.mark.parametrize("S,K,soft", [(224, 4, True), (56, 8, True), (72, 16, True), (48, 1, False), (40, 3, True)])
+def test_tile_queue_order_changes_nothing(hf, S, K, soft):
+    """The cost-ordered tile queue (heaviest tiles first, runs of empty tiles streamed by cp.async.bulk) only changes the
+    ORDER tiles are processed in and how empty tiles are written: all four Fragments tensors, the image, the loss sums
+    and every gradient are bit-identical to the row-major launch with vector-store fills - at sizes with clipped
+    border tiles (56, 72, 40), K that takes the bulk path (1, 4, 8, 16) and K that cannot (3)."""
+    B = 3
+    inp = P.synthetic_inputs(B, S=S, seed=40 + K)
+    args = _step_args(inp)
+    outs = []
+    for q in (True, False):
+        st = hf.FusedHandStep(B, image_size=S, faces_per_pixel=K, soft=soft, texture_size=64, device=DEV, tile_queue=q)
+        assert (st.tile_queue is not None) == q
+        st.step(*args)
+        torch.cuda.synchronize()
+        st.check_status()
+        outs.append({k: getattr(st, k).clone() for k in ("p2f", "zbuf", "bary", "dists", "image", "sums", "g_pose", "g_betas",
+                                                          "g_texture", "g_light_dir", "g_light_color")})
+    for k, v in outs[0].items():
+        assert torch.equal(v, outs[1][k]), k
+    assert (outs[0]["p2f"] >= 0).any() and (outs[0]["p2f"] < 0).any()
+
+
+def test_graph_replay_matches_eager_step(hf):
+    """FusedHandStep.capture(): the whole forward + backward as one CUDA graph gives the bits of the eager launches,
+    replay after replay (inputs may be overwritten in place between replays)."""
+    B, S = 4, 96
+    inp = P.synthetic_inputs(B, S=S, seed=9)
+    args = _step_args(inp)
+    st = hf.FusedHandStep(B, image_size=S, faces_per_pixel=4, soft=True, texture_size=64, device=DEV)
+    st.step(*args)
+    torch.cuda.synchronize()
+    keys = ("p2f", "image", "sums", "g_pose", "g_betas", "g_texture", "g_light_dir", "g_light_color")
+    want = {k: getattr(st, k).clone() for k in keys}
+    g = st.capture(*args)
+    for _ in range(3):
+        for k in ("g_pose", "g_texture", "image"):
+            getattr(st, k).fill_(7.0)
+        g.replay()
+        torch.cuda.synchronize()
+        for k in keys:
+            assert torch.equal(getattr(st, k), want[k]), k
+    # new inputs through the same static tensors
+    inp2 = P.synthetic_inputs(B, S=S, seed=10)
+    for dst, src in zip(args, _step_args(inp2)):
+        dst.copy_(src)
+    g.replay()
+    torch.cuda.synchronize()
+    got = {k: getattr(st, k).clone() for k in keys}
+    st2 = hf.FusedHandStep(B, image_size=S, faces_per_pixel=4, soft=True, texture_size=64, device=DEV)
+    st2.step(*args)
+    torch.cuda.synchronize()
+    for k in keys:
+        assert torch.equal(got[k], getattr(st2, k)), k
+
+
+def test_geometry_backward_record_gather_paths_agree(hf):
+    """hfr_geom_backward with the chip-wide per-entry gather (rec_partial) against the in-kernel gather: the same records,
+    a different (fixed) association of the per-vertex sum -> 1e-6 of the tensor max; each is bit-reproducible."""
+    B, S = 3, 80
+    inp = P.synthetic_inputs(B, S=S, seed=14)
+    args = _step_args(inp)
+    a = hf.FusedHandStep(B, image_size=S, faces_per_pixel=4, soft=True, texture_size=64, device=DEV)
+    b = hf.FusedHandStep(B, image_size=S, faces_per_pixel=4, soft=True, texture_size=64, device=DEV)
+    b.rec_partial = None
+    a.step(*args)
+    b.step(*args)
+    torch.cuda.synchronize()
+    assert rel_err(a.g_verts, b.g_verts) < 1e-6 and rel_err(a.g_pose, b.g_pose) < 1e-5
+    assert a.g_verts.abs().max() > 0

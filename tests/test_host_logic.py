@@ -41,3 +41,27 @@ def test_call_rejects_mixed_devices_bookkeeping():
     with pytest.raises(L.HfrError):
         L.ptr(torch.zeros(3), torch.float32, "x")
     assert L.ptr(None) is None
+
+
+def test_workspace_size_queries_are_host_only_and_consistent():
+    """The size queries of the round-2 entry points are plain host arithmetic (no GPU): tile queue, hand-layer
+    workspace / packed basis, record partials.  Sizes follow the layouts documented in include/hifihr_b200.h."""
+    import ctypes as C
+    from hifihr_b200 import _lib as L
+    lib = L.lib()
+    # tile queue: 16 header words + (1 count + 8 class lists + 1 group list) words per 16x16 tile
+    T = 64 * 14 * 14
+    assert lib.hfr_raster_queue_bytes(64, 224, 224) == (16 + 10 * T) * 4 + 64
+    assert lib.hfr_raster_queue_bytes(1, 17, 33) == (16 + 10 * (2 * 3)) * 4 + 64      # ragged sizes round tiles up
+    # MANO-shaped model: V=778, NJ=16, NS=10 -> NK=145, KP=152, NKP16=160, C3=2336 -> C3P=2368, 73 forward tiles, 37 chunks
+    m = L.HfrHandModel()
+    m.V, m.NJ, m.NS, m.NPC, m.NW, m.NT, m.center_joint, m.C3 = 778, 16, 10, 45, 4, 5, 9, 2336
+    fwd, bwd = 73 * 2 * 32 * 152, 37 * 2 * 160 * 64
+    assert lib.hfr_mano_packed_basis_bytes(C.byref(m)) == (fwd + bwd + 32) * 4
+    w64, w4096 = lib.hfr_mano_workspace_bytes(C.byref(m), 64), lib.hfr_mano_workspace_bytes(C.byref(m), 4096)
+    assert 0 < w64 < w4096 and w64 % 4 == 0
+    # one 128-sample tile of operands at B=64, 32 at B=4096; split-K shrinks as the batch grows (enough CTAs already)
+    assert w4096 < 64 * w64
+    t = L.HfrTopology()
+    t.V, t.F = 778, 1538
+    assert lib.hfr_geom_rec_partial_floats(C.byref(t), 64) == 64 * 3 * 1538 * 6
