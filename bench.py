@@ -62,6 +62,28 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+_wc_keepalive = []
+
+
+def pinned_buffer(nbytes, write_combined=False):
+    """Pinned host staging buffer.  write_combined: cudaHostAllocWriteCombined (the device reads it over PCIe without
+    snooping the CPU caches; the host only ever writes it sequentially) - falls back to torch's pinned allocator."""
+    if write_combined:
+        try:
+            import ctypes as C
+            rt = C.CDLL("libcudart.so.12")
+            ptr = C.c_void_p()
+            if rt.cudaHostAlloc(C.byref(ptr), C.c_size_t(nbytes), C.c_uint(0x04)) == 0 and ptr.value:
+                arr = (C.c_ubyte * nbytes).from_address(ptr.value)
+                _wc_keepalive.append(arr)
+                t = torch.frombuffer(arr, dtype=torch.uint8)
+                if t.is_pinned():
+                    return t
+        except Exception:   # noqa: BLE001
+            pass
+    return torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
 
@@ -200,7 +222,7 @@ def run_ours(args, cfg):
     for t in fields:
         offs.append(total_b)
         total_b += (t.numel() * t.element_size() + 255) // 256 * 256
-    host = torch.empty(total_b, dtype=torch.uint8).pin_memory()
+    host = pinned_buffer(total_b, write_combined=os.environ.get("HFR_E2E_WC", "0") == "1")
     for t, o in zip(fields, offs):
         host[o:o + t.numel() * t.element_size()] = t.view(-1).view(torch.uint8)
     devt = [t.to(dev, non_blocking=True) for t in small + [imgs_u8.float() / 255.0, seg_u8.float()]]
@@ -282,7 +304,8 @@ def run_ours(args, cfg):
     def enqueue_copy(slot):
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed[slot])      # the step that last read this slot has finished
-            raw[slot].copy_(host, non_blocking=True)
+            if os.environ.get("HFR_E2E_NOCOPY") != "1":     # diagnostic only: the e2e number needs the copy
+                raw[slot].copy_(host, non_blocking=True)
             ready[slot].record(copy_stream)
 
     e2e_graphs = {}
@@ -322,7 +345,8 @@ def run_ours(args, cfg):
             done.record(main_stream)
             with torch.cuda.stream(d2h_stream):
                 d2h_stream.wait_event(done)
-                out_host[oset].copy_(step.out, non_blocking=True)
+                if os.environ.get("HFR_E2E_NOD2H") != "1":  # diagnostic only
+                    out_host[oset].copy_(step.out, non_blocking=True)
                 d2h_done[oset].record(d2h_stream)
             step.flip_outputs()
 
