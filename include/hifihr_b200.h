@@ -94,7 +94,8 @@ typedef struct HfrManoFwdArgs {
   const float* rots;
   int32_t n_rot_in, pose_off, root_palm;
   void* workspace;         /* hfr_mano_workspace_bytes(m, B) bytes, or NULL (per-sample kernels).  Selects the batched
-                              tensor-core path when the model carries basis_packed */
+                              tensor-core path when the model carries basis_packed.  Scratch of ONE call at a time:
+                              calls that may run concurrently (different streams) need their own */
 } HfrManoFwdArgs;
 int hfr_mano_forward(const HfrHandModel* m, const HfrManoFwdArgs* a, void* stream);
 
