@@ -210,8 +210,11 @@ __device__ __forceinline__ float ssim_channel(const HfrLossArgs& a, float (*xs)[
 // MODE 2 = the self-supervised photometric terms (losses.py:317-340): x = re_img as rendered (NOT multiplied by the
 // silhouette), y = maskRGBs given as `imgs` (models_res_nimble.py:220), and the L1 / mean-RGB sums are kept PER SAMPLE
 // (sums[NSUMS + n], [NSUMS + N + n], [NSUMS + 2N + n]) because the reference weights them by texture_con[n]^2.
+#ifndef HFR_LOSSF_MINB
+#define HFR_LOSSF_MINB 3
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(kLossThreads, 3) loss_fwd_kernel(HfrLossArgs a) {
+__global__ void __launch_bounds__(kLossThreads, HFR_LOSSF_MINB) loss_fwd_kernel(HfrLossArgs a) {
   constexpr bool METRIC = MODE == 1, SELF = MODE == 2;
   extern __shared__ __align__(16) float lsm[];
   float (*xs3)[kLH][kXP] = reinterpret_cast<float (*)[kLH][kXP]>(lsm);                       // [3]

@@ -215,8 +215,9 @@ class FusedHandStep:
                                        (0.2, 0.2, 0.2), 30.0, tex_shape=self.texture.shape[:3], VT=self.verts_uvs.shape[0])
         # kernels of OURS per step(): mano, geom, [face records], raster setup, raster+shade(+pool), loss | loss', shade'+raster',
         # geom', mano'  (the two torch memsets of the accumulators are not counted)
-        # tiled backward: + raster scan, record clear, gradient finish (the fixed-point scale is two small torch reductions)
-        self.launches_per_step = (9 + (1 if face_records else 0) + (5 if self.tiled else 0) + (4 if self.mano_ws is not None else 0)
+        # tiled backward: + raster scan, record clear, gradient finish, record gather; batched hand layer: 3 + 3 launches
+        # instead of 1 + 1; tile queue: + the ordering pass  (C2 default: 18 kernels per step, as the ncu launch list shows)
+        self.launches_per_step = (9 + (1 if face_records else 0) + (4 if self.tiled else 0) + (4 if self.mano_ws is not None else 0)
                                   + (1 if self.tile_queue is not None else 0))
         if self.tiled and not self.deterministic:
             self.g_light_dir.zero_()
