@@ -586,10 +586,12 @@ def run_c3(args, cfg):
         out = layer({"pose_params": leaves[0], "shape_params": leaves[1], "texture_params": leaves[2]}, handle_collision=False)
         meshes = out["skin_meshes"]
         meshes.offset_verts_(rt[:, None].repeat(1, V, 1).view(B * V, 3))
-        img = renderer(meshes, cameras=cams, lights=lights).permute(0, 3, 1, 2)
+        img = renderer(meshes, cameras=cams, lights=lights)
+        # the output split of models_res_nimble.py:210-220 (permute + slices; no pooling at this render size) as one kernel
+        re_img, re_sil, _ = ops.PoolFunction.apply(img, 1, False, None)
         tgt = imgs.float() / 255.0 if imgs.dtype == torch.uint8 else imgs
         sg = seg.float() if seg.dtype == torch.uint8 else seg
-        terms = ops.RenderLossFunction.apply(img[:, :3], img[:, 3:4], tgt, sg, 1.0, True)
+        terms = ops.RenderLossFunction.apply(re_img, re_sil, tgt, sg, 1.0, True)
         loss = terms[0] + terms[1] + terms[2]
         if world > 1:
             loss = loss / world

@@ -57,6 +57,10 @@ class HfrGeomBwdArgs(C.Structure):
                 ("g_vnormals", vp), ("g_verts", vp), ("face_rec", vp), ("raster_ws", vp), ("status", vp), ("rec_partial", vp)]
 
 
+class HfrFaceVertsArgs(C.Structure):
+    _fields_ = [("B", i32), ("verts", vp), ("face_verts", vp), ("g_face_verts", vp), ("g_verts", vp)]
+
+
 class HfrRasterArgs(C.Structure):
     _fields_ = [("N", i32), ("H", i32), ("W", i32), ("K", i32), ("Ftot", i64), ("face_verts", vp),
                 ("mesh_first", vp), ("mesh_nfaces", vp), ("blur_radius", f32),
@@ -75,7 +79,8 @@ class HfrShadeParams(C.Structure):
                 ("shade", i32), ("sigma", f32), ("gamma", f32), ("znear", f32), ("zfar", f32),
                 ("background", f32 * 3), ("light_ambient", f32 * 3), ("light_specular", f32 * 3),
                 ("mat_ambient", f32 * 3), ("mat_diffuse", f32 * 3), ("mat_specular", f32 * 3),
-                ("shininess", f32), ("tex_n", i32), ("tex_h", i32), ("tex_w", i32), ("VT", i32), ("tex_pca", i32), ("light_point", i32)]
+                ("shininess", f32), ("tex_n", i32), ("tex_h", i32), ("tex_w", i32), ("VT", i32), ("tex_pca", i32), ("light_point", i32),
+                ("tex_basis_stride", i32)]
 
 
 class HfrShadeFwdArgs(C.Structure):
@@ -167,6 +172,7 @@ ENTRY_POINTS = [
     "hfr_keypoint_forward", "hfr_keypoint_backward", "hfr_shade_backward_tiled", "hfr_grad_finish",
     "hfr_loss_partials_floats", "hfr_mano_packed_basis_bytes", "hfr_mano_pack_basis", "hfr_mano_workspace_bytes",
     "hfr_mano_batched_status", "hfr_raster_queue_bytes", "hfr_geom_rec_partial_floats",
+    "hfr_face_verts_forward", "hfr_face_verts_backward",
 ]
 
 _lib = None

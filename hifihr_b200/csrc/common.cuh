@@ -17,6 +17,7 @@
 #define HFR_HD __host__ __device__ __forceinline__
 #else
 #define HFR_HD static inline
+struct alignas(16) float4 { float x, y, z, w; };   // host build of the math headers (tests/host_emul)
 #endif
 
 #if defined(__CUDA_ARCH__)

@@ -325,6 +325,39 @@ __global__ void __launch_bounds__(kThreads) geom_bwd_kernel(HfrTopology t, HfrGe
   }
 }
 
+// face_verts[b][f][c][:] = verts[b][faces[f][c]][:], one thread per (sample, face corner), chip-wide
+__global__ void __launch_bounds__(256) face_verts_fwd_kernel(HfrTopology t, int B, const float* __restrict__ verts,
+                                                             float* __restrict__ out) {
+  const int64_t total = (int64_t)B * t.F * 3;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int b = (int)(i / (3 * t.F)), e = (int)(i - (int64_t)b * 3 * t.F);
+    const float* __restrict__ src = verts + ((size_t)b * t.V + __ldg(t.faces + e)) * 3;
+    const float x = __ldg(src), y = __ldg(src + 1), z = __ldg(src + 2);
+    float* dst = out + (size_t)i * 3;
+    dst[0] = x; dst[1] = y; dst[2] = z;
+  }
+}
+
+// its adjoint: one thread per (sample, vertex) adds the vertex's incident (face, corner) entries in CSR order
+__global__ void __launch_bounds__(256) face_verts_bwd_kernel(HfrTopology t, int B, const float* __restrict__ g_fv,
+                                                             float* __restrict__ g_verts) {
+  const int64_t total = (int64_t)B * t.V;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int b = (int)(i / t.V), v = (int)(i - (int64_t)b * t.V);
+    const int e0 = __ldg(t.vf_ptr + v), e1 = __ldg(t.vf_ptr + v + 1);
+    const float* __restrict__ g = g_fv + (size_t)b * t.F * 9;
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+#pragma unroll 4
+    for (int e = e0; e < e1; ++e) {
+      const int fc = __ldg(t.vf_idx + e);                      // face * 4 + corner
+      const float* __restrict__ q = g + (size_t)(fc >> 2) * 9 + (fc & 3) * 3;
+      sx += __ldg(q); sy += __ldg(q + 1); sz += __ldg(q + 2);
+    }
+    float* dst = g_verts + (size_t)i * 3;
+    dst[0] = sx; dst[1] = sy; dst[2] = sz;
+  }
+}
+
 static int check_topo(const HfrTopology* t, int need_joints) {
   HFR_CHECK_ARG(t && t->V > 0 && t->F > 0 && t->faces && t->vf_ptr && t->vf_idx, "topology: null/empty");
   if (need_joints)
@@ -374,5 +407,29 @@ extern "C" int hfr_geom_backward(const HfrTopology* t, const HfrGeomBwdArgs* a, 
   }
   geom_bwd_kernel<<<a->B, kThreads, smem, (cudaStream_t)stream>>>(*t, *a);
   HFR_CHECK_LAUNCH("geom_backward");
+  return HFR_OK;
+}
+
+extern "C" int hfr_face_verts_forward(const HfrTopology* t, const HfrFaceVertsArgs* a, void* stream) {
+  HFR_CHECK_ARG(a && a->B >= 0, "face_verts_forward: null argument");
+  if (a->B == 0) return HFR_OK;
+  if (int rc = check_topo(t, 0)) return rc;
+  HFR_CHECK_ARG(a->verts && a->face_verts, "face_verts_forward: null pointer");
+  const int64_t total = (int64_t)a->B * t->F * 3;
+  const unsigned blocks = (unsigned)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  face_verts_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(*t, a->B, a->verts, a->face_verts);
+  HFR_CHECK_LAUNCH("face_verts_forward");
+  return HFR_OK;
+}
+
+extern "C" int hfr_face_verts_backward(const HfrTopology* t, const HfrFaceVertsArgs* a, void* stream) {
+  HFR_CHECK_ARG(a && a->B >= 0, "face_verts_backward: null argument");
+  if (a->B == 0) return HFR_OK;
+  if (int rc = check_topo(t, 0)) return rc;
+  HFR_CHECK_ARG(a->g_face_verts && a->g_verts, "face_verts_backward: null pointer");
+  const int64_t total = (int64_t)a->B * t->V;
+  const unsigned blocks = (unsigned)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  face_verts_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(*t, a->B, a->g_face_verts, a->g_verts);
+  HFR_CHECK_LAUNCH("face_verts_backward");
   return HFR_OK;
 }

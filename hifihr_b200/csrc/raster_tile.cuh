@@ -179,6 +179,7 @@ __device__ __forceinline__ void raster_tile(const HfrRasterArgs& a, const uint32
   // pz is a convex combination of the vertex depths unless an outside pixel keeps unclipped
   // barycentrics (blur > 0 without clipping): only then the zmin early-out is not exact
   const bool zcull = clip || !(blur > 0.0f);
+  const bool hard = KMAX == 1 && !(blur > 0.0f);   // see the walk below (compile-time false for K > 1: those kernels are unchanged)
   top.init();
   if (mesh_box) {   // tile outside the mesh's footprint (union of its faces' tile ranges): nothing to do
     const uint4 bx = __ldg(reinterpret_cast<const uint4*>(mesh_box) + n);
@@ -348,46 +349,101 @@ __device__ __forceinline__ void raster_tile(const HfrRasterArgs& a, const uint32
         int ch = 0;
         uint32_t Wc = sm.wmask[warp][0][lane];
         bool done = false;
-        while (true) {
-          int ri = -1;
-          if (!done) {
-            while (Wc == 0 && ++ch < nch) Wc = sm.wmask[warp][ch][lane];
-            if (Wc == 0) {
-              done = true;
-            } else {
+        if (hard) {
+          // K = 1, blur_radius == 0 (HardPhong settings): only a pixel INSIDE the face can win, and a pixel is outside as
+          // soon as one edge function is zero or disagrees in sign with the face area (the barycentric quotient, and
+          // its perspective-corrected form with z > 0, is then <= 0 - exact for IEEE division, underflow included).
+          // Every lane therefore skips through its candidates with that sign test (21 flops) until one survives; the
+          // exact coverage / depth math then runs once per SURVIVOR on lanes that all carry one, and the
+          // point-triangle distance is only evaluated where it is an output.
+          while (true) {
+            int ri = -1;
+            float4 q3 = make_float4(0.f, 0.f, 0.f, 0.f);
+            while (!done) {
+              while (Wc == 0 && ++ch < nch) Wc = sm.wmask[warp][ch][lane];
+              if (Wc == 0) { done = true; break; }
               const int j = __ffs(Wc) - 1;
               Wc &= Wc - 1;
-              ri = sm.order[ch * 32 + j];
+              const int r = sm.order[ch * 32 + j];
+              q3 = *reinterpret_cast<const float4*>(sm.rec + r * kRecFloats + 12);   // (bucket zmin, area, zmin, face)
+              if (zcull && !(q3.z < top.worst())) {
+                if (!(q3.x < top.worst())) done = true;
+                continue;
+              }
+              const float4* r4 = reinterpret_cast<const float4*>(sm.rec + r * kRecFloats);
+              const float4 q0 = r4[0], q1 = r4[1];   // x0 y0 z0 x1 | y1 z1 x2 y2
+              const float e0 = hfr_edge(xf, yf, q0.w, q1.x, q1.z, q1.w), e1 = hfr_edge(xf, yf, q1.z, q1.w, q0.x, q0.y),
+                          e2 = hfr_edge(xf, yf, q0.x, q0.y, q0.w, q1.x);
+              const float ar = q3.y;
+              const bool pos = ar > 0.0f;
+              const bool out = (ar > 0.0f || ar < 0.0f) &&
+                               (!(e0 > 0.0f || e0 < 0.0f) || !(e1 > 0.0f || e1 < 0.0f) || !(e2 > 0.0f || e2 < 0.0f) ||
+                                (e0 > 0.0f) != pos || (e1 > 0.0f) != pos || (e2 > 0.0f) != pos);
+              if (out) continue;
+              ri = r;
+              break;
+            }
+            if (!__any_sync(0xffffffffu, ri >= 0)) break;   // every lane left the search finished
+            if (ri >= 0) {
+              const float4* r4 = reinterpret_cast<const float4*>(sm.rec + ri * kRecFloats);
+              const float4 q0 = r4[0], q1 = r4[1];
+              const float v[9] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, sm.rec[ri * kRecFloats + 8]};
+              const int face = __float_as_int(q3.w);
+              float pz, bc[3];
+              bool inside;
+              if (hfr_raster_bary(xf, yf, v, q3.y, pc, clip, &pz, bc, &inside) && inside && top.beats_worst(pz, face)) {
+                if (PAY) {
+                  const float dd = hfr_tri_dist2(xf, yf, v);
+                  const int slot = top.insert_slot(pz, face, perm);
+                  pay[slot * kRasterThreads] = make_float4(bc[0], bc[1], bc[2], -dd);
+                } else {
+                  top.insert(pz, face);
+                }
+              }
             }
           }
-          float4 q3 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ri >= 0) {
-            q3 = *reinterpret_cast<const float4*>(sm.rec + ri * kRecFloats + 12);   // (bucket zmin, area, zmin, face)
-            if (zcull && !(q3.z < top.worst())) {   // this face cannot enter the top K ...
-              if (!(q3.x < top.worst())) done = true;   // ... and neither can any later one
-              ri = -1;
+        } else {
+          while (true) {
+            int ri = -1;
+            if (!done) {
+              while (Wc == 0 && ++ch < nch) Wc = sm.wmask[warp][ch][lane];
+              if (Wc == 0) {
+                done = true;
+              } else {
+                const int j = __ffs(Wc) - 1;
+                Wc &= Wc - 1;
+                ri = sm.order[ch * 32 + j];
+              }
             }
-          }
-          if (!__any_sync(0xffffffffu, ri >= 0)) {
-            if (__all_sync(0xffffffffu, done)) break;
-            continue;
-          }
-          if (ri >= 0) {
-            const float4* r4 = reinterpret_cast<const float4*>(sm.rec + ri * kRecFloats);
-            const float4 q0 = r4[0], q1 = r4[1];
-            const float v[9] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, sm.rec[ri * kRecFloats + 8]};
-            const int face = __float_as_int(q3.w);
-            float pz, bc[3];
-            bool inside;
-            if (hfr_raster_bary(xf, yf, v, q3.y, pc, clip, &pz, bc, &inside)) {
-              if (top.beats_worst(pz, face)) {
-                const float dd = (PAY || !inside) ? hfr_tri_dist2(xf, yf, v) : 0.0f;
-                if (inside || dd < blur) {
-                  if (PAY) {
-                    const int slot = top.insert_slot(pz, face, perm);
-                    pay[slot * kRasterThreads] = make_float4(bc[0], bc[1], bc[2], inside ? -dd : dd);
-                  } else {
-                    top.insert(pz, face);
+            float4 q3 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ri >= 0) {
+              q3 = *reinterpret_cast<const float4*>(sm.rec + ri * kRecFloats + 12);   // (bucket zmin, area, zmin, face)
+              if (zcull && !(q3.z < top.worst())) {   // this face cannot enter the top K ...
+                if (!(q3.x < top.worst())) done = true;   // ... and neither can any later one
+                ri = -1;
+              }
+            }
+            if (!__any_sync(0xffffffffu, ri >= 0)) {
+              if (__all_sync(0xffffffffu, done)) break;
+              continue;
+            }
+            if (ri >= 0) {
+              const float4* r4 = reinterpret_cast<const float4*>(sm.rec + ri * kRecFloats);
+              const float4 q0 = r4[0], q1 = r4[1];
+              const float v[9] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, sm.rec[ri * kRecFloats + 8]};
+              const int face = __float_as_int(q3.w);
+              float pz, bc[3];
+              bool inside;
+              if (hfr_raster_bary(xf, yf, v, q3.y, pc, clip, &pz, bc, &inside)) {
+                if (top.beats_worst(pz, face)) {
+                  const float dd = (PAY || !inside) ? hfr_tri_dist2(xf, yf, v) : 0.0f;
+                  if (inside || dd < blur) {
+                    if (PAY) {
+                      const int slot = top.insert_slot(pz, face, perm);
+                      pay[slot * kRasterThreads] = make_float4(bc[0], bc[1], bc[2], inside ? -dd : dd);
+                    } else {
+                      top.insert(pz, face);
+                    }
                   }
                 }
               }

@@ -384,6 +384,9 @@ int check_shade(const HfrShadeFwdArgs* a, const char* who) {
                       (p.tex_n == 1 || p.tex_n == p.N),
                   "%s: phong/uv shading needs mesh, uv, texture and light pointers", who);
   HFR_CHECK_ARG(p.tex_pca >= 0 && p.tex_pca <= HFR_MAX_TEX_PCA, "%s: tex_pca must be in [0,%d]", who, HFR_MAX_TEX_PCA);
+  HFR_CHECK_ARG(p.tex_basis_stride == 0 || (p.tex_pca > 0 && p.tex_basis_stride == 12 * ((p.tex_pca + 3) / 4) &&
+                                            (reinterpret_cast<uintptr_t>(a->tex_basis) & 15) == 0),
+                "%s: a texel-major basis has stride 12 * ceil(tex_pca / 4) floats and a 16-byte aligned base", who);
   if (p.shade == HFR_SHADE_PHONG_UV && p.tex_pca > 0)
     HFR_CHECK_ARG(p.tex_n == 1 && a->tex_basis && a->tex_params, "%s: a PCA texture needs the mean map (tex_n = 1), basis and coefficients", who);
   return HFR_OK;

@@ -40,10 +40,6 @@ __device__ __forceinline__ int selk_i(const int (&a)[KMAX], int k) {
   return r;
 }
 
-__device__ __forceinline__ float gtp_of(const HfrShadeFwdArgs& f, int n, const HfrTexTap& tap, const float* gtex, int c) {
-  return hfr_tex_param_grad(tex_source<true>(f, n), &tap, gtex, c);
-}
-
 #ifndef HFR_BWD_WARP_LIGHT
 #define HFR_BWD_WARP_LIGHT 0
 #endif
@@ -319,9 +315,15 @@ __global__ void __launch_bounds__(kBwdThreads, (KMAX == 1 ? HFR_BWD_MINB_K1 : (K
       }
       if (PCA && a.g_tex_params && k < kshade) {
         // d(loss)/d(texture coefficients): warp-reduce each component over the lanes of this slot, one RED per warp
-        for (int c = 0; c < P.tex_pca; ++c) {
-          const float t = warp_sum(vk ? gtp_of(f, n, tap_k, gtex_k, c) : 0.0f);
-          if (lane == 0 && t != 0.0f) atomicAdd(a.g_tex_params + (size_t)n * P.tex_pca + c, t);
+        const HfrTexSrc tsrc = tex_source<true>(f, n);
+        for (int c0 = 0; c0 < P.tex_pca; c0 += 4) {
+          float t4[4] = {0.f, 0.f, 0.f, 0.f};
+          if (vk) hfr_tex_param_grad4(tsrc, &tap_k, gtex_k, c0, t4);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float t = warp_sum(t4[i]);
+            if (lane == 0 && c0 + i < P.tex_pca && t != 0.0f) atomicAdd(a.g_tex_params + (size_t)n * P.tex_pca + c0 + i, t);
+          }
         }
       }
       if (!(a.g_verts_ndc || (k < kshade && (a.g_verts_view || a.g_vnormals)))) continue;

@@ -46,20 +46,43 @@ HFR_HD void hfr_tex_tap(int Ht, int Wt, float u, float v, HfrTexTap* t) {
 // (NIMBLE-style per-sample texture, SURVEY.md 8(f) row 4: the per-sample 1024^2 map is never materialised).
 struct HfrTexSrc {
   const float* tex;      // plain map of this sample, or the PCA mean map
-  const float* basis;    // (npc, Ht, Wt, 3) or NULL
+  const float* basis;    // (npc, Ht, Wt, 3), or texel-major (Ht * Wt, stride) when stride > 0, or NULL
   const float* params;   // this sample's npc coefficients or NULL
   int npc;               // 0 = plain map
+  int stride;            // > 0: floats per texel record of the texel-major basis (12 * ceil(npc / 4))
   size_t map_floats;     // Ht * Wt * 3
 };
 
 HFR_HD HfrTexSrc hfr_tex_plain(const float* tex) {
-  HfrTexSrc s; s.tex = tex; s.basis = nullptr; s.params = nullptr; s.npc = 0; s.map_floats = 0;
+  HfrTexSrc s; s.tex = tex; s.basis = nullptr; s.params = nullptr; s.npc = 0; s.stride = 0; s.map_floats = 0;
   return s;
+}
+
+HFR_HD float4 hfr_ld4(const float4* p) {
+#ifdef __CUDA_ARCH__
+  return __ldg(p);
+#else
+  return *p;
+#endif
 }
 
 HFR_HD void hfr_texel(const HfrTexSrc& src, int idx, float* v) {
   const float* m = src.tex + (size_t)idx * 3;
   v[0] = m[0]; v[1] = m[1]; v[2] = m[2];
+  if (src.stride > 0) {
+    // texel-major record: 4 components (12 floats, three 16-byte loads) per round, same summation order as below
+    const float4* b = reinterpret_cast<const float4*>(src.basis + (size_t)idx * src.stride);
+    for (int k0 = 0; k0 < src.npc; k0 += 4, b += 3) {
+      const float4 r0 = hfr_ld4(b), r1 = hfr_ld4(b + 1), r2 = hfr_ld4(b + 2);
+      const float p0 = src.params[k0], p1 = k0 + 1 < src.npc ? src.params[k0 + 1] : 0.0f,
+                  p2 = k0 + 2 < src.npc ? src.params[k0 + 2] : 0.0f, p3 = k0 + 3 < src.npc ? src.params[k0 + 3] : 0.0f;
+      v[0] += p0 * r0.x; v[1] += p0 * r0.y; v[2] += p0 * r0.z;
+      v[0] += p1 * r0.w; v[1] += p1 * r1.x; v[2] += p1 * r1.y;
+      v[0] += p2 * r1.z; v[1] += p2 * r1.w; v[2] += p2 * r2.x;
+      v[0] += p3 * r2.y; v[1] += p3 * r2.z; v[2] += p3 * r2.w;
+    }
+    return;
+  }
   for (int k = 0; k < src.npc; ++k) {
     const float pk = src.params[k];
     const float* b = src.basis + (size_t)k * src.map_floats + (size_t)idx * 3;
@@ -108,11 +131,35 @@ HFR_HD float hfr_tex_param_grad(const HfrTexSrc& src, const HfrTexTap* t, const 
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     if (t->idx[q] >= 0) {
-      const float* b = src.basis + (size_t)k * src.map_floats + (size_t)t->idx[q] * 3;
+      const float* b = src.stride > 0 ? src.basis + (size_t)t->idx[q] * src.stride + 3 * k
+                                      : src.basis + (size_t)k * src.map_floats + (size_t)t->idx[q] * 3;
       acc += t->w[q] * (b[0] * g[0] + b[1] * g[1] + b[2] * g[2]);
     }
   }
   return acc;
+}
+
+// the same for components k0 .. k0 + 3 at once (k0 % 4 == 0): with the texel-major basis every tap is three 16-byte
+// loads, all twelve of a round independent
+HFR_HD void hfr_tex_param_grad4(const HfrTexSrc& src, const HfrTexTap* t, const float* g, int k0, float* out) {
+  out[0] = out[1] = out[2] = out[3] = 0.0f;
+  if (src.stride > 0) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (t->idx[q] >= 0) {
+        const float4* b = reinterpret_cast<const float4*>(src.basis + (size_t)t->idx[q] * src.stride + 3 * k0);
+        const float4 r0 = hfr_ld4(b), r1 = hfr_ld4(b + 1), r2 = hfr_ld4(b + 2);
+        const float w = t->w[q];
+        out[0] += w * (r0.x * g[0] + r0.y * g[1] + r0.z * g[2]);
+        out[1] += w * (r0.w * g[0] + r1.x * g[1] + r1.y * g[2]);
+        out[2] += w * (r1.z * g[0] + r1.w * g[1] + r2.x * g[2]);
+        out[3] += w * (r2.y * g[0] + r2.z * g[1] + r2.w * g[2]);
+      }
+    }
+    return;
+  }
+  for (int i = 0; i < 4; ++i)
+    if (k0 + i < src.npc) out[i] = hfr_tex_param_grad(src, t, g, k0 + i);
 }
 
 // ---------------------------------------------------------------------------------- lighting

@@ -68,6 +68,7 @@ HFR_HD HfrTexSrc tex_source(const HfrShadeFwdArgs& a, int n) {
   if (PCA) {
     s.map_floats = map_floats;
     s.npc = a.p.tex_pca;
+    s.stride = a.p.tex_basis_stride;
     s.basis = a.tex_basis;
     s.params = a.tex_params + (size_t)n * a.p.tex_pca;
   }

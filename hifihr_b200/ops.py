@@ -238,7 +238,7 @@ def raster_tile_box(ws, Ftot, N):
 
 def shade_params(N, H, W, K, F, V, blend, shade, sigma, gamma, background, light_ambient, light_specular,
                  mat_ambient, mat_diffuse, mat_specular, shininess, tex_shape=(1, 1, 1), VT=0, znear=1.0, zfar=100.0,
-                 tex_pca=0, light_point=0):
+                 tex_pca=0, light_point=0, tex_basis_stride=0):
     p = L.HfrShadeParams()
     p.N, p.H, p.W, p.K, p.F, p.V, p.blend, p.shade = N, H, W, K, F, V, blend, shade
     p.sigma, p.gamma, p.znear, p.zfar = float(sigma), float(gamma), float(znear), float(zfar)
@@ -249,7 +249,27 @@ def shade_params(N, H, W, K, F, V, blend, shade, sigma, gamma, background, light
     p.tex_n, p.tex_h, p.tex_w, p.VT = int(tex_shape[0]), int(tex_shape[1]), int(tex_shape[2]), int(VT)
     p.tex_pca = int(tex_pca)
     p.light_point = int(light_point)
+    p.tex_basis_stride = int(tex_basis_stride)
     return p
+
+
+def pack_tex_basis(basis):
+    """Texel-major copy of a (n_comp,T,T,3) texture PCA basis: (T*T, 12*ceil(n_comp/4)) floats, component k / channel c
+    of a texel at 3k + c, zero padded (HfrShadeParams.tex_basis_stride).  Built once per basis tensor (cached on the
+    tensor, keyed by its version counter): a layout change of a constant, like the packed hand-layer basis."""
+    b = basis.detach()
+    cached = getattr(basis, "_hfr_texel_major", None)
+    if cached is not None and cached[0] == (b._version, b.data_ptr()):
+        return cached[1]
+    n = b.shape[0]
+    stride = 12 * ((n + 3) // 4)
+    packed = torch.zeros(b.shape[1] * b.shape[2], stride, dtype=F32, device=b.device)
+    packed[:, :3 * n] = b.to(F32).permute(1, 2, 0, 3).reshape(-1, 3 * n)
+    try:
+        basis._hfr_texel_major = ((b._version, b.data_ptr()), packed)
+    except AttributeError:
+        pass
+    return packed
 
 
 def shade_fwd_args(p, frags, faces, verts_view, vnormals, faces_uvs, verts_uvs, texture, light_dir, light_color, image,
@@ -354,6 +374,27 @@ class GeomFunction(torch.autograd.Function):
         return None, g_verts, None, None, None, None, None
 
 
+class FaceVertsFunction(torch.autograd.Function):
+    """(N,V,3) vertices -> packed (N*F,3,3) face vertices (`verts_packed()[faces_packed()]` of MeshRasterizer.forward);
+    the backward is a fixed-order CSR gather instead of ATen's sort-based index_put."""
+
+    @staticmethod
+    def forward(ctx, topo: TopologyConsts, verts):
+        verts = _cu(verts)
+        N = verts.shape[0]
+        fv = torch.empty(N * topo.F, 3, 3, dtype=F32, device=verts.device)
+        L.call("hfr_face_verts_forward", topo.struct, L.HfrFaceVertsArgs(N, L.ptr(verts, F32), L.ptr(fv, F32), None, None))
+        ctx.topo, ctx.N = topo, N
+        return fv
+
+    @staticmethod
+    def backward(ctx, g_fv):
+        g_fv = _cu(g_fv)
+        g_verts = torch.empty(ctx.N, ctx.topo.V, 3, dtype=F32, device=g_fv.device)
+        L.call("hfr_face_verts_backward", ctx.topo.struct, L.HfrFaceVertsArgs(ctx.N, None, None, L.ptr(g_fv, F32), L.ptr(g_verts, F32)))
+        return None, g_verts
+
+
 class RasterizeFunction(torch.autograd.Function):
     """Same contract as pytorch3d._C.rasterize_meshes / rasterize_meshes_backward."""
 
@@ -422,10 +463,14 @@ class ShadeFunction(torch.autograd.Function):
         g_image = _cu(g_image)
         f = shade_fwd_args(p, (p2f, zbuf, bary, dists), faces, verts_view, vnormals, faces_uvs, verts_uvs, texture,
                            light_dir, light_color, image, None, tex_basis, tex_params)
-        g_tp = torch.zeros_like(tex_params) if ctx.pca else None
-        g_zbuf, g_bary, g_dists = torch.empty_like(zbuf), torch.empty_like(bary), torch.empty_like(dists)
-        z = lambda t: None if t is None else torch.zeros_like(t)  # noqa: E731
-        g_vv, g_vn, g_tex, g_ld, g_lc = z(verts_view), z(vnormals), z(texture), z(light_dir), z(light_color)
+        # only the gradients autograd asks for are computed: every NULL output drops its reductions from the kernel (a
+        # frozen texture / mean map alone is 12 scattered atomics per shaded fragment)
+        need = ctx.needs_input_grad
+        g_tp = torch.zeros_like(tex_params) if (ctx.pca and need[14]) else None
+        e = lambda t, i: torch.empty_like(t) if need[i] else None  # noqa: E731
+        g_zbuf, g_bary, g_dists = e(zbuf, 2), e(bary, 3), e(dists, 4)
+        z = lambda t, i: None if (t is None or not need[i]) else torch.zeros_like(t)  # noqa: E731
+        g_vv, g_vn, g_tex, g_ld, g_lc = z(verts_view, 6), z(vnormals, 7), z(texture, 10), z(light_dir, 11), z(light_color, 12)
         a = L.HfrShadeBwdArgs(f, L.ptr(g_image, F32), L.ptr(g_zbuf, F32), L.ptr(g_bary, F32), L.ptr(g_dists, F32),
                               None, None, 0.0, 1, 0, L.ptr(g_vv, F32), L.ptr(g_vn, F32), L.ptr(g_tex, F32),
                               L.ptr(g_ld, F32), L.ptr(g_lc, F32), None, 0, 0, L.ptr(g_tp, F32))

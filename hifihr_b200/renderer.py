@@ -210,7 +210,7 @@ class MeshRasterizer(nn.Module):
         cameras = kwargs.get("cameras", self.cameras)
         pc = rs.perspective_correct if rs.perspective_correct is not None else cameras.is_perspective()
         clip = rs.clip_barycentric_coords if rs.clip_barycentric_coords is not None else rs.blur_radius > 0.0
-        face_verts = verts_ndc.reshape(N * V, 3)[meshes_world.faces_packed()]
+        face_verts = ops.FaceVertsFunction.apply(meshes_world.topology, verts_ndc)   # verts_packed()[faces_packed()]
         p2f, zbuf, bary, dists = ops.RasterizeFunction.apply(
             face_verts, meshes_world.mesh_to_faces_packed_first_idx(), meshes_world.num_faces_per_mesh(), (H, W),
             rs.blur_radius, K, pc, clip, rs.cull_backfaces)
@@ -224,7 +224,7 @@ def rasterize_meshes(meshes_or_face_verts, image_size=256, blur_radius=0.0, face
     """Functional form (pytorch3d.renderer.mesh.rasterize_meshes): a Meshes already in NDC, or packed face_verts."""
     if isinstance(meshes_or_face_verts, Meshes):
         m = meshes_or_face_verts
-        fv = m.verts_packed()[m.faces_packed()]
+        fv = ops.FaceVertsFunction.apply(m.topology, m.verts_padded())
         first, nf = m.mesh_to_faces_packed_first_idx(), m.num_faces_per_mesh()
     else:
         fv, first, nf = meshes_or_face_verts, mesh_to_face_first_idx, num_faces_per_mesh
@@ -262,18 +262,20 @@ class _ShaderBase(nn.Module):
                 raise ValueError("Meshes does not have textures")
             pca = isinstance(tex, TexturesUVPCA)
             maps = tex._maps if pca else tex.maps_padded()
+            basis = ops.pack_tex_basis(tex._basis) if pca else None     # texel-major copy, built once per basis
             params = ops.shade_params(N, H, W, K, topo.F, topo.V, self.blend, 1, bp.sigma, bp.gamma,
                                       bp.background_color, _c3(lights.ambient_color), _c3(lights.specular_color),
                                       _c3(materials.ambient_color), _c3(materials.diffuse_color),
                                       _c3(materials.specular_color), materials.shininess,
                                       tex_shape=maps.shape[:3], VT=tex._verts_uvs.shape[0],
-                                      tex_pca=tex._basis.shape[0] if pca else 0, light_point=int(point))
+                                      tex_pca=tex._basis.shape[0] if pca else 0, light_point=int(point),
+                                      tex_basis_stride=basis.shape[1] if pca else 0)
             ldir = _rows(lights.location, N, dev, "lights.location") if point else _rows(lights.direction, N, dev, "lights.direction")
             lcol = _rows(lights.diffuse_color, N, dev, "lights.diffuse_color")
             return ops.ShadeFunction.apply(params, p2f, fragments.zbuf, fragments.bary_coords, fragments.dists,
                                            topo.faces, meshes.verts_padded(), meshes.verts_normals_padded(),
                                            tex._faces_uvs.to(dev), tex._verts_uvs.to(dev), maps, ldir, lcol,
-                                           tex._basis if pca else None, tex._params if pca else None)
+                                           basis, tex._params if pca else None)
         params = ops.shade_params(N, H, W, K, topo.F, topo.V, self.blend, 0, bp.sigma, bp.gamma, bp.background_color,
                                   (0, 0, 0), (0, 0, 0), (0, 0, 0), (0, 0, 0), (0, 0, 0), 1.0)
         return ops.ShadeFunction.apply(params, p2f, fragments.zbuf, fragments.bary_coords, fragments.dists,

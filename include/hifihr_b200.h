@@ -190,6 +190,20 @@ typedef struct HfrGeomBwdArgs {
 int64_t hfr_geom_rec_partial_floats(const HfrTopology* t, int32_t B);
 int hfr_geom_backward(const HfrTopology* t, const HfrGeomBwdArgs* a, void* stream);
 
+/* Packed per-face vertices for the rasterizer: face_verts[b][f][c][:] = verts[b][faces[f][c]][:].
+ * Replaces `verts_packed()[faces_packed()]` of pytorch3d MeshRasterizer.forward (reached from
+ * models_res_nimble.py:208) and ATen's sort-based index backward behind it.  The backward adds a vertex's
+ * incident (face, corner) entries in CSR order: no atomics, reproducible run to run. */
+typedef struct HfrFaceVertsArgs {
+  int32_t B;
+  const float* verts;         /* forward: (B,V,3), e.g. verts_ndc                        */
+  float* face_verts;          /* forward: (B,F,3,3)                                      */
+  const float* g_face_verts;  /* backward: (B,F,3,3)                                     */
+  float* g_verts;             /* backward: (B,V,3), overwritten                          */
+} HfrFaceVertsArgs;
+int hfr_face_verts_forward(const HfrTopology* t, const HfrFaceVertsArgs* a, void* stream);
+int hfr_face_verts_backward(const HfrTopology* t, const HfrFaceVertsArgs* a, void* stream);
+
 /* ------------------------------------------------------------------ rasterizer
  * Replaces pytorch3d._C.rasterize_meshes / rasterize_meshes_backward as reached from
  * MeshRasterizer.forward (models_res_nimble.py:208).  Packed face_verts (Ftot,3,3) in
@@ -262,6 +276,11 @@ typedef struct HfrShadeParams {
                                        models_res_nimble.py:191-198 taken when ifLight=False): light_dir = LOCATION (N,3),
                                        the light direction of a fragment is location - position; g_light_dir then receives
                                        d/d(location) */
+  int32_t tex_basis_stride;         /* layout of tex_basis.  0: component-major (tex_pca,tex_h,tex_w,3).  > 0: TEXEL-major
+                                       (tex_h*tex_w, stride) floats, component k / channel c of a texel at 3k + c, zero
+                                       padded; stride = 12 * ceil(tex_pca / 4) (16-byte aligned records): the tex_pca
+                                       values a bilinear tap needs are one contiguous record instead of tex_pca reads
+                                       tex_h*tex_w*12 bytes apart */
 } HfrShadeParams;
 #define HFR_MAX_TEX_PCA 64
 
@@ -281,7 +300,7 @@ typedef struct HfrShadeFwdArgs {
    * When set, the shaders read one contiguous record per fragment instead of chasing
    * faces -> verts_view / vnormals and faces_uvs -> verts_uvs (two dependent gathers).  NULL = gather path. */
   const float* face_attr;
-  const float* tex_basis;           /* (tex_pca,tex_h,tex_w,3) when p.tex_pca > 0          */
+  const float* tex_basis;           /* when p.tex_pca > 0; layout: p.tex_basis_stride      */
   const float* tex_params;          /* (N,tex_pca)             when p.tex_pca > 0          */
 } HfrShadeFwdArgs;
 int hfr_shade_forward(const HfrShadeFwdArgs* a, void* stream);

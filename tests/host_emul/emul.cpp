@@ -102,14 +102,19 @@ void emul_tex(const float* tex, int Ht, int Wt, int M, const float* uv, const fl
 }
 // PCA texture model (mean + sum_k params[k] * basis[k]) sampled at the taps: fetch, uv grad, d/d(params)
 void emul_tex_pca(const float* mean, const float* basis, const float* params, int npc, int Ht, int Wt, int M, const float* uv,
-                  const float* g, float* out, float* guv, float* gparams) {
+                  const float* g, float* out, float* guv, float* gparams, int stride) {
   HfrTexSrc src;
   src.tex = mean; src.basis = basis; src.params = params; src.npc = npc; src.map_floats = (size_t)Ht * Wt * 3;
+  src.stride = stride;   // 0: (npc,Ht,Wt,3); > 0: texel-major records of `stride` floats
   for (int i = 0; i < M; ++i) {
     HfrTexTap t; hfr_tex_tap(Ht, Wt, uv[2*i], uv[2*i+1], &t);
     hfr_tex_fetch(src, &t, out + 3*i);
     hfr_tex_uv_grad(src, &t, g + 3*i, guv + 2*i, guv + 2*i + 1);
-    for (int k = 0; k < npc; ++k) gparams[k] += hfr_tex_param_grad(src, &t, g + 3*i, k);
+    for (int k0 = 0; k0 < npc; k0 += 4) {
+      float t4[4];
+      hfr_tex_param_grad4(src, &t, g + 3*i, k0, t4);
+      for (int j = 0; j < 4 && k0 + j < npc; ++j) gparams[k0 + j] += t4[j];
+    }
   }
 }
 }

@@ -207,8 +207,20 @@ def test_pca_texture_math_matches_autograd():
     gs = torch.randn(M, 3, generator=g, dtype=torch.float64)
     (smp * gs).sum().backward()
     f = lambda t: np.ascontiguousarray(t.detach().float().numpy())  # noqa: E731
-    o, guv, gp = np.zeros((M, 3), np.float32), np.zeros((M, 2), np.float32), np.zeros(npc, np.float32)
-    lib.emul_tex_pca(ptr(f(mean)), ptr(f(basis)), ptr(f(params)), npc, Ht, Wt, M, ptr(f(uv)), ptr(f(gs)), ptr(o), ptr(guv), ptr(gp))
-    assert np.abs(o - f(smp)).max() < 1e-5
-    assert np.abs(guv - uv.grad.numpy()).max() < 1e-3 * max(1, uv.grad.abs().max().item())
-    assert np.abs(gp - params.grad.numpy()).max() < 1e-4 * max(1, params.grad.abs().max().item())
+    res = []
+    for texel_major in (False, True):   # (npc,Ht,Wt,3), and the texel-major records of HfrShadeParams.tex_basis_stride
+        stride = 12 * ((npc + 3) // 4) if texel_major else 0
+        bs = f(basis)
+        if texel_major:
+            bs = np.zeros((Ht * Wt, stride), np.float32)
+            bs[:, :3 * npc] = f(basis.permute(1, 2, 0, 3).reshape(Ht * Wt, 3 * npc))
+            assert bs.ctypes.data % 16 == 0
+        o, guv, gp = np.zeros((M, 3), np.float32), np.zeros((M, 2), np.float32), np.zeros(npc, np.float32)
+        lib.emul_tex_pca(ptr(f(mean)), ptr(bs), ptr(f(params)), npc, Ht, Wt, M, ptr(f(uv)), ptr(f(gs)), ptr(o), ptr(guv), ptr(gp),
+                         stride)
+        assert np.abs(o - f(smp)).max() < 1e-5
+        assert np.abs(guv - uv.grad.numpy()).max() < 1e-3 * max(1, uv.grad.abs().max().item())
+        assert np.abs(gp - params.grad.numpy()).max() < 1e-4 * max(1, params.grad.abs().max().item())
+        res.append((o, guv, gp))
+    # the two layouts run the same sums in the same order
+    assert all(np.array_equal(a, b) for a, b in zip(*res))

@@ -230,7 +230,7 @@ def test_ctypes_struct_sizes_match_header():
     import subprocess
     import tempfile
     from hifihr_b200 import _lib
-    names = ["HfrHandModel", "HfrManoFwdArgs", "HfrManoBwdArgs", "HfrTopology", "HfrGeomFwdArgs", "HfrGeomBwdArgs",
+    names = ["HfrHandModel", "HfrManoFwdArgs", "HfrManoBwdArgs", "HfrTopology", "HfrGeomFwdArgs", "HfrGeomBwdArgs", "HfrFaceVertsArgs",
              "HfrRasterArgs", "HfrRasterBwdArgs", "HfrShadeParams", "HfrShadeFwdArgs", "HfrShadeBwdArgs",
              "HfrRasterShadeArgs", "HfrRasterShadePoolArgs", "HfrFaceAttrArgs", "HfrPoolArgs", "HfrPoolBwdArgs", "HfrLossArgs", "HfrLossBwdArgs", "HfrKeypointArgs",
              "HfrKeypointBwdArgs"]
