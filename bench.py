@@ -36,6 +36,9 @@ CONFIGS = {
     # configs[2]: NIMBLE-shaped stand-in (V=5986, F=11968), 10 x 1024^2 texture PCA sampled in the shader, modular path
     "c3": dict(B=128, S=256, K=1, soft=False, T=1024, nimble=True,
                desc="C3 NIMBLE-shaped hand (V=5986, F=11968), 1024^2 PCA texture, 256^2, K=1 hard Phong + photometric losses, B=128/GPU"),
+    # the same workload through the modular drop-in API (MyNIMBLELayer -> MeshRenderer -> losses under autograd)
+    "c3m": dict(B=128, S=256, K=1, soft=False, T=1024, nimble=True, modular=True,
+                desc="C3 (modular autograd path) NIMBLE-shaped hand (V=5986, F=11968), 1024^2 PCA texture, 256^2, K=1 hard Phong + photometric losses, B=128/GPU"),
     "c4": dict(G=4096, S=224, K=4, soft=True, T=512, desc="C4 as C2 with global batch 4096 sharded over the GPUs"),
     "c5": dict(G=256, S=512, K=8, soft=True, T=512, desc="C5 soft raster 512^2 K=8 blur>0, global batch 256 sharded over the GPUs"),
     "r": dict(B=48, S=672, K=1, soft=False, T=512, desc="reference setting 672^2 K=1 hard Phong (no pooling stage), B=48"),
@@ -545,9 +548,181 @@ def run_c3_reference(args, cfg):
 
 
 def run_c3(args, cfg):
+    """BASELINE configs[2] as raw launches (hifihr_b200.FusedNimbleStep): per-sample LBS kernels at NIMBLE size -> geometry
+    (root shift, camera, normals, packed face vertices) -> rasterizer -> Phong shader evaluating the 10 x 1024^2 texture
+    PCA at the bilinear taps -> photometric losses -> their backward (loss', shade' + rasterize' fused, geometry', LBS'),
+    replayed from a CUDA graph.  Gradients: pose (B,33), shape (B,20), texture coefficients (B,10), lights."""
+    import torch.distributed as dist
+    import hifihr_b200 as hf
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/hifihr_b200_nccl.%h.%p.log")
+        dist.init_process_group("nccl", device_id=dev)
+    B, S, T = args.batch or cfg["B"], cfg["S"], cfg["T"]
+    step = hf.FusedNimbleStep(B, image_size=S, texture_size=T, device=dev, n_global=B * world)
+    V, Fn = step.hm.V, step.topo.F
+    pose, shape, texp, inp, root = c3_inputs(B, S, 1234 + rank)
+    fcl, prp = hf.get_ndc_fx_fy_cx_cy(inp["Ks"])
+    small = [pose, shape, -fcl, prp, root, inp["light_dir"], inp["light_color"]]
+    imgs_u8 = (inp["imgs"] * 255.0).round().to(torch.uint8)
+    seg_u8 = inp["segms_gt"].to(torch.uint8)
+    host = [t.contiguous().pin_memory() for t in small + [imgs_u8, seg_u8, texp]]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host)
+    out_host = torch.empty(step.out.shape, dtype=torch.float32).pin_memory()    # sums + g_pose + g_shape + g_tex_params
+    d2h_bytes = out_host.numel() * 4
+
+    from hifihr_b200 import dist as hdist
+
+    def one_step(t):
+        step.forward(*t[:9], tex_params=t[9])
+        # the mean-RGB term is a difference of GLOBAL means: its sums are all-reduced before the loss backward (no-op at N=1)
+        step.backward(*t[:5], sums_hook=hdist.all_reduce_loss_sums_async)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # device-resident arm: float targets (what ToTensor produces); end-to-end arm: the 8-bit targets cross PCIe and the
+    # loss kernels convert while loading (as in run_ours)
+    devt = [t.to(dev) for t in small] + [imgs_u8.float().to(dev) / 255.0, seg_u8.float().to(dev), texp.to(dev)]
+    e2e_in = [torch.empty_like(h, device=dev) for h in host]
+    use_graph = os.environ.get("HFR_GRAPH", "1") != "0"
+    graph_note, g_dev, g_e2e = "eager launches", None, None
+    if use_graph:
+        try:
+            g_dev = step.capture(*devt[:9], tex_params=devt[9], sums_hook=hdist.all_reduce_loss_sums_async)
+            g_e2e = step.capture(*e2e_in[:9], tex_params=e2e_in[9], sums_hook=hdist.all_reduce_loss_sums_async)
+            graph_note = "CUDA graph replay (one graph launch per step)"
+        except Exception as e:   # noqa: BLE001
+            graph_note = f"eager launches (graph capture failed: {type(e).__name__})"
+            g_dev = g_e2e = None
+            torch.cuda.synchronize()
+    run_dev = (lambda: g_dev.replay()) if g_dev is not None else (lambda: one_step(devt))
+    run_e2e = (lambda: g_e2e.replay()) if g_e2e is not None else (lambda: one_step(e2e_in))
+    for _ in range(max(args.warmup, 3)):
+        run_dev()
+    barrier()
+    win_ms, win_e2e = [], []
+    with ClockSampler(local) as clk:
+        for _ in range(args.windows):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            e0.record()
+            for _ in range(args.steps):
+                run_dev()
+            e1.record()
+            barrier()
+            win_ms.append(e0.elapsed_time(e1))
+    for _ in range(args.windows):       # end to end: this step's inputs from pinned host memory, its results back to the host
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            for d, h in zip(e2e_in, host):
+                d.copy_(h, non_blocking=True)
+            run_e2e()
+            out_host.copy_(step.out, non_blocking=True)
+        e1.record()
+        barrier()
+        win_e2e.append(e0.elapsed_time(e1))
+    # per-kernel times of one eager step (CUDA events around each stage)
+    names = ["lbs_fwd", "geom_fwd", "raster_fwd", "shade_fwd", "loss_fwd", "loss_bwd", "shade_raster_bwd", "geom_bwd", "lbs_bwd"]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
+    from hifihr_b200 import _lib as L
+    from hifihr_b200 import ops
+    kernel_ms = {k: 0.0 for k in names}
+    reps = 5
+    po, sh, fo, pp, rt, ld, lc, im, sg, tp = devt
+    for _ in range(reps):
+        step._tex_params, step._focal = tp, fo
+        step._inputs = tuple(devt)
+        ev[0].record()
+        ops.mano_forward_raw(step.hm, po, sh, None, step.verts, None, workspace=step.mano_ws)
+        ev[1].record()
+        ops.geom_forward_raw(step.topo, step.verts, step.root_out, rt, fo, pp, step.joints, step.verts_rel, step.verts_view,
+                             step.verts_ndc, step.vnormals, step.face_verts)
+        ev[2].record()
+        r = ops.raster_args(step.face_verts, step.mesh_first, step.mesh_nf, S, S, 1, 0.0, True, False, False, step.p2f, step.zbuf,
+                            step.bary, step.dists, step.ws, None)
+        L.call("hfr_raster_forward", r)
+        ev[3].record()
+        step.launch_raster_shade(ld, lc, im)          # rasterizer again + shader: the shader's share is the difference
+        ev[4].record()
+        step.forward(po, sh, fo, pp, rt, ld, lc, im, sg, tp)   # whole forward (keeps the loss arguments current)
+        ev[5].record()
+        step.launch_loss_backward()
+        ev[6].record()
+        step.acc.zero_()
+        step.g_tex_params.zero_()
+        step.launch_shade_backward()
+        ev[7].record()
+        step.launch_geom_backward(fo, pp, rt)
+        ev[8].record()
+        ops.mano_backward_raw(step.hm, po, sh, None, step.g_verts, None, step.g_pose, step.g_betas, None, workspace=step.mano_ws,
+                              reuse_forward=True)
+        ev[9].record()
+        torch.cuda.synchronize()
+        t = [ev[i].elapsed_time(ev[i + 1]) for i in range(9)]
+        kernel_ms["lbs_fwd"] += t[0] / reps
+        kernel_ms["geom_fwd"] += t[1] / reps
+        kernel_ms["raster_fwd"] += t[2] / reps
+        kernel_ms["shade_fwd"] += max(t[3] - t[2], 0.0) / reps
+        kernel_ms["loss_fwd"] += max(t[4] - t[0] - t[1] - t[3], 0.0) / reps
+        kernel_ms["loss_bwd"] += t[5] / reps
+        kernel_ms["shade_raster_bwd"] += t[6] / reps
+        kernel_ms["geom_bwd"] += t[7] / reps
+        kernel_ms["lbs_bwd"] += t[8] / reps
+    t = torch.tensor([win_ms, win_e2e], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    win_ms, win_e2e = sorted(float(x) for x in t[0]), sorted(float(x) for x in t[1])
+    ms, ms_e2e = win_ms[len(win_ms) // 2], win_e2e[len(win_e2e) // 2]
+    if rank == 0:
+        total = B * world * args.steps
+        peak, peak_src = peaks()
+        P_ = S * S
+        # SURVEY.md 8(d), C3: Fragments w+r, image-side traffic, vertex streams, parameters, texture basis + mean read once per step
+        step_bytes = (56 * P_ + 64 * P_ + 48 * V + 8 * 60) * B + 12 * 11 * T * T
+        alg_raster = B * 28 * P_
+        raster_ms = kernel_ms["raster_fwd"]
+        line = {"metric": "hand renders/sec (fwd+bwd)", "value": total / (ms * 1e-3), "unit": "samples/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": cfg["desc"], "batch_per_gpu": B, "global_batch": B * world, "image_size": S,
+                           "faces_per_pixel": 1, "texture": T, "verts": V, "faces": Fn, "launch": graph_note,
+                           "parallelism": f"dp{world} (FusedNimbleStep, batch shards by sample; no shared-parameter gradient: "
+                                          "the texture model is frozen)",
+                           "l2": "no flush: the texture basis alone (151 MB texel-major) exceeds the 126 MB L2"},
+                "e2e": {"value": total / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes,
+                        "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / args.steps,
+                        "inputs": "pose/shape/texture coefficients/camera/light fp32 + target images and masks as uint8, pinned"},
+                "windows": {"n": args.windows, "steps_each": args.steps, "statistic": "median",
+                            "ms_per_step": [w / args.steps for w in win_ms], "e2e_ms_per_step": [w / args.steps for w in win_e2e]},
+                "gpu_launches": step.launches_per_step * args.steps * args.windows, "clocks": clk.summary(),
+                "roofline": {"bound": "hbm", "kernel": "raster_fwd", "achieved": alg_raster / (raster_ms * 1e-3) / 1e9, "peak": peak,
+                             "unit": "GB/s", "frac": alg_raster / (raster_ms * 1e-3) / 1e9 / peak, "traffic": None,
+                             "algorithmic_bytes_per_launch": alg_raster, "peak_source": peak_src,
+                             "kernel_ms": kernel_ms,
+                             "step_frac": step_bytes / (ms / args.steps * 1e-3) / 1e9 / peak,
+                             "step": {"algorithmic_MB_per_sample": step_bytes / B / 1e6}}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        # graphs must go before the process group (see run_ours)
+        del g_dev, g_e2e
+        dist.destroy_process_group()
+
+
+def run_c3_modular(args, cfg):
     """BASELINE configs[2] on the modular path: MyNIMBLELayer (LBS kernels at NIMBLE size) -> MeshRasterizer ->
     HardPhongShader with the 10 x 1024^2 texture PCA evaluated at the bilinear taps -> photometric losses, autograd
-    bridges over the C-ABI for the backward.  No fused step exists for this shape."""
+    bridges over the C-ABI for the backward (`--config c3m`; `--config c3` runs the fused step, run_c3)."""
     import torch.distributed as dist
     import hifihr_b200 as hf
     from hifihr_b200 import ops
@@ -729,7 +904,7 @@ def main():
         if not torch.cuda.is_available():
             raise SystemExit("bench.py: no CUDA device; hifihr_b200 has no CPU path (use --impl reference for the CPU arm)")
         if cfg.get("nimble"):
-            run_c3(args, cfg)
+            (run_c3_modular if cfg.get("modular") else run_c3)(args, cfg)
         else:
             run_ours(args, cfg)
 

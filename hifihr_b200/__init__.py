@@ -8,7 +8,7 @@ Public surface mirrors the reference's names for this path:
   BlendParams, TexturesUV, TexturesUVPCA      (pytorch3d.renderer, the subset used; PCA = NIMBLE texture model)
   LossFunction                                (losses.py, render-dependent terms)
   texture_metrics                             (train_hrnet.py:149-161 PSNR / SSIM / L1 / L2)
-  HandRenderModel, FusedHandStep              (models_res_nimble.py:133-223 without the CNNs)
+  HandRenderModel, FusedHandStep, FusedNimbleStep   (models_res_nimble.py:133-223 without the CNNs)
 
 All compute runs in hand-written CUDA kernels behind the C-ABI of include/hifihr_b200.h
 (libhifihr_b200.so, loaded with ctypes).  There is no CPU / PyTorch fallback.
@@ -16,7 +16,7 @@ All compute runs in hand-written CUDA kernels behind the C-ABI of include/hifihr
 from ._lib import ENTRY_POINTS, LIB_PATH, HfrError  # noqa: F401
 from .losses import LossFunction, texture_metrics, trans_proj_j2d  # noqa: F401
 from .mano import ManoLayer, MyMANOLayer, xyz_from_vertice  # noqa: F401
-from .model import FusedHandStep, HandRenderModel, get_ndc_fx_fy_cx_cy  # noqa: F401
+from .model import FusedHandStep, FusedNimbleStep, HandRenderModel, get_ndc_fx_fy_cx_cy  # noqa: F401
 from .renderer import (BlendParams, DirectionalLights, Fragments, HardPhongShader, Materials,  # noqa: F401
                        MeshRasterizer, MeshRenderer, PerspectiveCameras, PointLights, RasterizationSettings,
                        SoftPhongShader, SoftSilhouetteShader, TexturesUV, TexturesUVPCA, rasterize_meshes)

@@ -140,15 +140,7 @@ class FusedHandStep:
         self.Sr = image_size * self.aa          # rasterised resolution
         self.soft = soft
         self.blur = (np.log(1.0 / 1e-4 - 1.0) * sigma if soft else 0.0) if blur_radius is None else blur_radius
-        self.layer = MyMANOLayer(True, dev, shape_ncomp=10, pose_ncomp=48, tex_ncomp=None, mano_root=mano_root)
-        self.hm = self.layer.mano_layer.consts(dev)
-        self.topo = self.layer.topology(dev)
-        d = self.layer.mano_layer._mano
-        uv, fuv = mano_synthetic_uvs(d["v_template"], d["f"])
-        self.verts_uvs = torch.tensor(uv, device=dev)
-        self.faces_uvs = torch.tensor(fuv, device=dev, dtype=I32)
-        g = torch.Generator().manual_seed(20231)
-        self.texture = torch.rand(1, texture_size, texture_size, 3, generator=g).to(dev)
+        self._build_model(dev, mano_root, texture_size)
         lam = dict(texture=1.0, mrgb=1.0, ssim_tex=1.0, sil=1.0, iou=0.0)
         lam.update(lambdas or {})
         self.lambdas = lam
@@ -157,7 +149,7 @@ class FusedHandStep:
         self.sil_scale = sil_scale
         V, Fm, S, K, Sr = self.hm.V, self.topo.F, self.S, self.K, self.Sr
         e = lambda *s, dt=F32: torch.empty(*s, dtype=dt, device=dev)  # noqa: E731
-        self.verts, self.joints = e(B, V, 3), e(B, 21, 3)
+        self.verts, self.joints = e(B, V, 3), e(B, max(self.topo.NOUT, 1), 3)
         self.verts_rel, self.verts_view, self.verts_ndc, self.vnormals = e(B, V, 3), e(B, V, 3), e(B, V, 3), e(B, V, 3)
         self.face_verts = e(B * Fm, 3, 3)
         self.face_attr = e(B, Fm, L.FACE_ATTR_FLOATS) if face_records else None
@@ -174,7 +166,9 @@ class FusedHandStep:
         # device->host copy returns them, and in two alternating sets (flip_outputs) so that copy can overlap the
         # next step on another stream
         self._n_sums = L.LOSS_NSUMS + 2 * B
-        self._outs = [torch.zeros(self._n_sums + 58 * B, dtype=F32, device=dev) for _ in range(2)]
+        self._n_pose, self._n_shape = self.hm.pose_dim, self.hm.NS          # 48 + 10 for MANO
+        self._outs = [torch.zeros(self._n_sums + (self._n_pose + self._n_shape + self.n_tex) * B, dtype=F32, device=dev)
+                      for _ in range(2)]
         self._out_set = 0
         self._bind_outputs()
         self.ws = ops.raster_workspace(B * Fm, dev)
@@ -182,7 +176,8 @@ class FusedHandStep:
         self.mesh_first = (torch.arange(B, device=dev, dtype=I64) * Fm).contiguous()
         self.mesh_nf = torch.full((B,), Fm, device=dev, dtype=I64)
         # every accumulated gradient lives in one flat buffer so a single memset clears them
-        n_acc = 3 * B * V * 3 + self.texture.numel() + 6 * B
+        n_tex_acc = self.texture.numel() if self.texture_grad else 0
+        n_acc = 3 * B * V * 3 + n_tex_acc + 6 * B
         self.acc = torch.zeros(n_acc, dtype=F32, device=dev)
         o = 0
         def take(n, shape):
@@ -191,7 +186,7 @@ class FusedHandStep:
             o += n
             return t
         self.g_ndc, self.g_view, self.g_vn = take(B * V * 3, (B, V, 3)), take(B * V * 3, (B, V, 3)), take(B * V * 3, (B, V, 3))
-        self.g_texture = take(self.texture.numel(), self.texture.shape)
+        self.g_texture = take(n_tex_acc, self.texture.shape) if self.texture_grad else None
         self.g_light_dir, self.g_light_color = take(3 * B, (B, 3)), take(3 * B, (B, 3))
         self.g_verts = e(B, V, 3)
         self.mano_ws = self.hm.workspace(B) if batched_hand else None   # batched tensor-core hand layer (None: per-sample kernels)
@@ -212,22 +207,41 @@ class FusedHandStep:
         self.gauss = ops.gauss_taps(dev)
         self.params = ops.shade_params(B, Sr, Sr, K, Fm, V, 2 if soft else 0, 1, sigma, gamma, (1.0, 1.0, 1.0),
                                        (0.5, 0.5, 0.5), (0.2, 0.2, 0.2), (1.0, 1.0, 1.0), (0.8, 0.8, 0.8),
-                                       (0.2, 0.2, 0.2), 30.0, tex_shape=self.texture.shape[:3], VT=self.verts_uvs.shape[0])
+                                       (0.2, 0.2, 0.2), 30.0, tex_shape=self.texture.shape[:3], VT=self.verts_uvs.shape[0],
+                                       tex_pca=self.n_tex, tex_basis_stride=self.tex_basis.shape[1] if self.n_tex else 0)
         # kernels of OURS per step(): mano, geom, [face records], raster setup, raster+shade(+pool), loss | loss', shade'+raster',
         # geom', mano'  (the two torch memsets of the accumulators are not counted)
         # tiled backward: + raster scan, record clear, gradient finish, record gather; batched hand layer: 3 + 3 launches
         # instead of 1 + 1; tile queue: + the ordering pass  (C2 default: 18 kernels per step, as the ncu launch list shows)
         self.launches_per_step = (9 + (1 if face_records else 0) + (4 if self.tiled else 0) + (4 if self.mano_ws is not None else 0)
-                                  + (1 if self.tile_queue is not None else 0))
+                                  + (1 if self.tile_queue is not None else 0) + (1 if self.n_tex else 0))
         if self.tiled and not self.deterministic:
             self.g_light_dir.zero_()
+
+    def _build_model(self, dev, mano_root, texture_size):
+        """The hand model behind the step: MANO (utils/my_mano.py), its synthetic UV layout and one shared (1,T,T,3) map.
+        Subclasses swap the model (FusedNimbleStep); root_out is the output joint the mesh is centred on (-1: none)."""
+        self.layer = MyMANOLayer(True, dev, shape_ncomp=10, pose_ncomp=48, tex_ncomp=None, mano_root=mano_root)
+        self.hm = self.layer.mano_layer.consts(dev)
+        self.topo = self.layer.topology(dev)
+        d = self.layer.mano_layer._mano
+        uv, fuv = mano_synthetic_uvs(d["v_template"], d["f"])
+        self.verts_uvs = torch.tensor(uv, device=dev)
+        self.faces_uvs = torch.tensor(fuv, device=dev, dtype=I32)
+        g = torch.Generator().manual_seed(20231)
+        self.texture = torch.rand(1, texture_size, texture_size, 3, generator=g).to(dev)
+        self.root_out = 9
+        self.tex_basis, self.n_tex = None, 0       # texture PCA model (texel-major basis, components): FusedNimbleStep
+        self.texture_grad = True                   # False: the map is frozen (no gradient buffer, no reductions)
 
     def _bind_outputs(self):
         o, B, ns = self._outs[self._out_set], self.B, self._n_sums
         self.out = o
         self.sums = o[:ns]
-        self.g_pose = o[ns:ns + 48 * B].view(B, 48)
-        self.g_betas = o[ns + 48 * B:].view(B, 10)
+        npz, nsh = self._n_pose, self._n_shape
+        self.g_pose = o[ns:ns + npz * B].view(B, npz)
+        self.g_betas = o[ns + npz * B:ns + (npz + nsh) * B].view(B, nsh)
+        self.g_tex_params = o[ns + (npz + nsh) * B:].view(B, self.n_tex) if self.n_tex else None
 
     def flip_outputs(self):
         """Switch to the other output set: the next step() writes there, the set just produced stays intact."""
@@ -235,13 +249,16 @@ class FusedHandStep:
         self._bind_outputs()
 
     # ---------------------------------------------------------------------------------------
-    def forward(self, pose, betas, focal, prp, root_xyz, light_dir, light_color, imgs, seg):
+    def forward(self, pose, betas, focal, prp, root_xyz, light_dir, light_color, imgs, seg, tex_params=None):
         B, S, K, Sr = self.B, self.S, self.K, self.Sr
+        if (tex_params is not None) != bool(self.n_tex):
+            raise ValueError("tex_params: texture PCA coefficients are given exactly when the step has a texture model")
+        self._tex_params = tex_params
         # the cached argument structs hold raw pointers: keep the inputs alive until the backward has been enqueued
-        self._inputs = (pose, betas, focal, prp, root_xyz, light_dir, light_color, imgs, seg)
+        self._inputs = (pose, betas, focal, prp, root_xyz, light_dir, light_color, imgs, seg, tex_params)
         self._focal = focal
         ops.mano_forward_raw(self.hm, pose, betas, None, self.verts, None, workspace=self.mano_ws)
-        ops.geom_forward_raw(self.topo, self.verts, 9, root_xyz, focal, prp, self.joints, self.verts_rel,
+        ops.geom_forward_raw(self.topo, self.verts, self.root_out, root_xyz, focal, prp, self.joints, self.verts_rel,
                              self.verts_view, self.verts_ndc, self.vnormals, self.face_verts)
         self.launch_raster_shade(light_dir, light_color, imgs)
         if not self.deterministic:
@@ -267,8 +284,14 @@ class FusedHandStep:
                             False, self.p2f, self.zbuf, self.bary, self.dists, self.ws, self.tile_queue)
         s = ops.shade_fwd_args(self.params, (self.p2f, self.zbuf, self.bary, self.dists), self.topo.faces,
                                self.verts_view, self.vnormals, self.faces_uvs, self.verts_uvs, self.texture,
-                               light_dir, light_color, self.image if self.aa == 1 else None, self.face_attr)
-        if self.aa == 1:
+                               light_dir, light_color, self.image if self.aa == 1 else None, self.face_attr,
+                               self.tex_basis, self._tex_params if self.n_tex else None)
+        if self.n_tex:
+            # texture PCA model: the texel evaluation is a template parameter of the standalone shader only (DESIGN.md
+            # 8), so rasterize and shade are two launches here
+            L.call("hfr_raster_forward", r)
+            L.call("hfr_shade_forward", s)
+        elif self.aa == 1:
             L.call("hfr_raster_shade_forward", L.HfrRasterShadeArgs(r, s))
         else:
             masks = self.re_img is not None and imgs is not None and imgs.dtype == F32   # maskRGBs needs float images
@@ -300,15 +323,15 @@ class FusedHandStep:
                                L.ptr(self.g_ndc), float(self.blur), 1, int(self.blur > 0), L.ptr(self.g_view),
                                L.ptr(self.g_vn), L.ptr(self.g_texture), L.ptr(self.g_light_dir),
                                L.ptr(self.g_light_color), ops.raster_tile_box(self.ws, B * self.topo.F, B),
-                               self.aa if self.aa > 1 else 0, int(self.binarize))
+                               self.aa if self.aa > 1 else 0, int(self.binarize), L.ptr(self.g_tex_params))
         L.call("hfr_shade_backward", sb)
 
     def launch_geom_backward(self, focal, prp, root_xyz):
         if self.tiled:   # gathers d/d(view), d/d(normal) from the (face, tile) records in a fixed order
-            ops.geom_backward_raw(self.topo, self.verts, 9, root_xyz, focal, prp, None, None, None, None, None, self.g_verts,
+            ops.geom_backward_raw(self.topo, self.verts, self.root_out, root_xyz, focal, prp, None, None, None, None, None, self.g_verts,
                                   face_rec=self.face_rec, raster_ws=self.ws, status=self.status, rec_partial=self.rec_partial)
         else:
-            ops.geom_backward_raw(self.topo, self.verts, 9, root_xyz, focal, prp, None, None, self.g_view, self.g_ndc,
+            ops.geom_backward_raw(self.topo, self.verts, self.root_out, root_xyz, focal, prp, None, None, self.g_view, self.g_ndc,
                                   self.g_vn, self.g_verts)
 
     def launch_loss_backward(self):
@@ -338,22 +361,24 @@ class FusedHandStep:
             w.wait()
         if not self.tiled:
             self.acc.zero_()
+            if self.n_tex:
+                self.g_tex_params.zero_()
         elif not self.deterministic:
             self.g_texture.zero_()
         self.launch_shade_backward()
-        works = shared_grad_hook(self.g_texture) if shared_grad_hook is not None else ()
+        works = shared_grad_hook(self.g_texture) if (shared_grad_hook is not None and self.g_texture is not None) else ()
         self.launch_geom_backward(focal, prp, root_xyz)
         ops.mano_backward_raw(self.hm, pose, betas, None, self.g_verts, None, self.g_pose, self.g_betas, None,
                               workspace=self.mano_ws, reuse_forward=True)
         for w in works:
             w.wait()
 
-    def step(self, pose, betas, focal, prp, root_xyz, light_dir, light_color, imgs, seg):
-        self.forward(pose, betas, focal, prp, root_xyz, light_dir, light_color, imgs, seg)
+    def step(self, pose, betas, focal, prp, root_xyz, light_dir, light_color, imgs, seg, tex_params=None):
+        self.forward(pose, betas, focal, prp, root_xyz, light_dir, light_color, imgs, seg, tex_params)
         self.backward(pose, betas, focal, prp, root_xyz)
 
     def capture(self, pose, betas, focal, prp, root_xyz, light_dir, light_color, imgs, seg, shared_grad_hook=None,
-                sums_hook=None):
+                sums_hook=None, tex_params=None):
         """Capture one forward + backward on these (static) input tensors and the CURRENT output set into a CUDA graph;
         `graph.replay()` then enqueues the whole step with one driver call.  The eager step costs ~650 us of host time
         (python + ctypes + 17 launches) against ~900 us of device time at C2 - with several ranks sharing the host's
@@ -363,13 +388,13 @@ class FusedHandStep:
         side.wait_stream(cur)
         with torch.cuda.stream(side):      # warm-up off the capturing stream (lazy initialisations, allocator)
             for _ in range(2):
-                self.forward(pose, betas, focal, prp, root_xyz, light_dir, light_color, imgs, seg)
+                self.forward(pose, betas, focal, prp, root_xyz, light_dir, light_color, imgs, seg, tex_params)
                 self.backward(pose, betas, focal, prp, root_xyz, shared_grad_hook=shared_grad_hook, sums_hook=sums_hook)
         cur.wait_stream(side)
         torch.cuda.synchronize(self.dev)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            self.forward(pose, betas, focal, prp, root_xyz, light_dir, light_color, imgs, seg)
+            self.forward(pose, betas, focal, prp, root_xyz, light_dir, light_color, imgs, seg, tex_params)
             self.backward(pose, betas, focal, prp, root_xyz, shared_grad_hook=shared_grad_hook, sums_hook=sums_hook)
         return g
 
@@ -386,3 +411,41 @@ class FusedHandStep:
         mul, add = s[L.LOSS_NSUMS:L.LOSS_NSUMS + B], s[L.LOSS_NSUMS + B:]
         return torch.stack([s[0] / cnt, (s[2] / cnt - s[1] / cnt) ** 2, 1 - s[4] / cnt,
                             s[3] / float(self.n_global * S * S), 1 - (mul / (add - mul)).sum() / self.n_global])
+
+
+class FusedNimbleStep(FusedHandStep):
+    """The same raw-launch step for the NIMBLE-shaped hand (BASELINE configs[2]: V = 5986, F = 11968, 20 shape + 30 pose PCA
+    + 10 texture coefficients, 1024^2 texture PCA, K = 1 hard Phong; models_res_nimble.py:133-142 is the layer's
+    contract).  Differences from the MANO step: the LBS layer runs the per-sample kernels at NIMBLE size; no joint
+    regression / root centring (the reference adds root_xyz only, :203-205 -> geometry with root_out = -1); the texture is
+    mean + params @ basis evaluated at the bilinear taps from the texel-major basis (the (B,T,T,3) maps never exist),
+    which is a template parameter of the standalone shader - so rasterize and shade are two launches; the backward is
+    hfr_shade_backward with the rasterizer backward fused in (no Fragments gradients, no per-face gradient tensor) and
+    d/d(texture coefficients) as a step output (g_tex_params); the mean map is frozen.
+    `step(pose (B,33), shape (B,20), focal, prp, root_xyz, light_dir, light_color, imgs, seg, tex_params=(B,10))`."""
+
+    def __init__(self, B, image_size=256, texture_size=1024, shape_ncomp=20, pose_ncomp=30, tex_ncomp=10, lambdas=None,
+                 device="cuda", n_global=None, sil_scale=1.0):
+        self._nimble_cfg = (shape_ncomp, pose_ncomp, tex_ncomp)
+        lam = dict(texture=1.0, mrgb=1.0, ssim_tex=1.0, sil=0.0, iou=0.0)
+        lam.update(lambdas or {})
+        super().__init__(B, image_size=image_size, faces_per_pixel=1, blur_radius=0.0, soft=False, texture_size=texture_size,
+                         lambdas=lam, device=device, n_global=n_global, sil_scale=sil_scale, tiled_backward=False,
+                         deterministic=True, batched_hand=True, tile_queue=False)
+        # LBS, geometry, raster setup + scan + fine pass, shader, loss | loss', shade' + rasterize', geometry', LBS'
+        self.launches_per_step = 11 + (4 if self.mano_ws is not None else 0)
+
+    def _build_model(self, dev, mano_root, texture_size):
+        from .nimble import MyNIMBLELayer
+        ns, npz, nt = self._nimble_cfg
+        self.layer = MyNIMBLELayer(True, dev, shape_ncomp=ns, pose_ncomp=npz, tex_ncomp=nt, tex_size=texture_size,
+                                   fused_texture=True).to(dev)
+        self.hm, self.topo = self.layer.consts(dev)
+        self.verts_uvs = self.layer.verts_uvs.to(dev).to(F32).contiguous()
+        self.faces_uvs = self.topo.faces                       # the stand-in shares the vertex indexing with its UVs
+        self.texture = self.layer.tex_mean.to(dev).to(F32)[None].contiguous()      # (1,T,T,3) mean map
+        self.tex_basis = ops.pack_tex_basis(self.layer.tex_basis)                    # texel-major, built once
+        self.n_tex = int(self.layer.tex_basis.shape[0])
+        self.root_out = -1
+        self.texture_grad = False
+

@@ -198,3 +198,67 @@ def test_shade_backward_only_computes_requested_gradients(hf, mano):
         assert (model.texture.grad is None) == frozen and (lcol.grad is None) == frozen
     err = float((grads[0] - grads[1]).abs().max() / grads[0].abs().max())
     assert err < 1e-4, err
+
+
+def test_fused_nimble_step_matches_modular_path(hf):
+    """FusedNimbleStep (raw launches, rasterizer backward fused into the shading backward, texel-major texture PCA) against
+    the modular autograd path on the same inputs - which test_c3_shaped_losses_and_gradients pins to the oracle: identical
+    pix_to_face, loss terms to 1e-5, every gradient to 1e-4 (summation order of the atomics); a CUDA-graph replay of the
+    step reproduces the eager one."""
+    from hifihr_b200 import ops
+    B, T, S = 3, 256, 128
+    step = hf.FusedNimbleStep(B, image_size=S, texture_size=T, device=DEV)
+    layer = step.layer
+    V = layer.V
+    g = torch.Generator().manual_seed(21)
+    pose = torch.cat([torch.randn(B, 3, generator=g) * 0.4, torch.randn(B, 30, generator=g) * 0.5], 1).to(DEV)
+    shape = (torch.randn(B, 20, generator=g) * 0.5).to(DEV)
+    texp = torch.randn(B, 10, generator=g).to(DEV)
+    inp = P.synthetic_inputs(B, S=S, seed=6)
+    root = torch.tensor([[0.0, 0.0, 0.45]]).repeat(B, 1).to(DEV)
+    fcl, prp = hf.get_ndc_fx_fy_cx_cy(inp["Ks"])
+    focal, prp = (-fcl).to(DEV).contiguous(), prp.to(DEV).contiguous()
+    ldir, lcol = inp["light_dir"].to(DEV), inp["light_color"].to(DEV)
+    imgs, seg = inp["imgs"].to(DEV), inp["segms_gt"].float().to(DEV)
+    # ---- modular path ---------------------------------------------------------------------------
+    leaves = [t.clone().requires_grad_(True) for t in (pose, shape, texp)]
+    lc = lcol.clone().requires_grad_(True)
+    out = layer({"pose_params": leaves[0], "shape_params": leaves[1], "texture_params": leaves[2]}, handle_collision=False)
+    cams = hf.PerspectiveCameras(focal_length=focal, principal_point=prp, device=DEV)
+    lights = hf.DirectionalLights(diffuse_color=lc, direction=ldir, device=DEV)
+    rs = hf.RasterizationSettings(image_size=S, blur_radius=0.0, faces_per_pixel=1)
+    mats = hf.Materials(diffuse_color=((0.8, 0.8, 0.8),), specular_color=((0.2, 0.2, 0.2),), shininess=30, device=DEV)
+    meshes = out["skin_meshes"]
+    meshes.offset_verts_(root[:, None].repeat(1, V, 1).view(B * V, 3))
+    frags = hf.MeshRasterizer(raster_settings=rs)(meshes, cameras=cams)
+    img = hf.HardPhongShader(materials=mats, device=DEV)(frags, meshes, cameras=cams, lights=lights)
+    re_img, re_sil, _ = ops.PoolFunction.apply(img, 1, False, None)
+    t = ops.RenderLossFunction.apply(re_img, re_sil, imgs, seg, 1.0, True)
+    (t[0] + t[1] + t[2]).backward()
+    assert (frags.pix_to_face >= 0).float().mean() > 0.02
+    # ---- fused step -----------------------------------------------------------------------------
+    args = (pose, shape, focal, prp, root, ldir, lcol, imgs, seg)
+    step.step(*args, tex_params=texp)
+    torch.cuda.synchronize()
+    assert torch.equal(step.p2f, frags.pix_to_face) and torch.equal(step.zbuf, frags.zbuf)
+    assert float((step.image - img.detach()).abs().max()) < 1e-6
+    terms = step.loss_terms()
+    for i in range(3):
+        assert abs(float(terms[i]) - float(t[i])) < 1e-5 * max(1.0, abs(float(t[i]))), i
+    got = {"pose": step.g_pose.clone(), "shape": step.g_betas.clone(), "tex": step.g_tex_params.clone(),
+           "lcol": step.g_light_color.clone()}
+    for name, a, b in (("pose", got["pose"], leaves[0].grad), ("shape", got["shape"], leaves[1].grad),
+                       ("tex", got["tex"], leaves[2].grad), ("lcol", got["lcol"], lc.grad)):
+        err = float((a - b).abs().max() / b.abs().max())
+        print("fused nimble", name, err)
+        assert err < 1e-4, (name, err)
+    with pytest.raises(ValueError):
+        step.step(*args)                       # the texture coefficients are a required input of this step
+    # ---- graph replay == eager ------------------------------------------------------------------
+    graph = step.capture(*args, tex_params=texp)
+    step.g_pose.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    for name, a in (("pose", step.g_pose), ("shape", step.g_betas), ("tex", step.g_tex_params)):
+        err = float((a - got[name]).abs().max() / got[name].abs().max())
+        assert err < 1e-5, (name, err)
