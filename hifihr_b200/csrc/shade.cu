@@ -16,6 +16,12 @@ __global__ void __launch_bounds__(256) shade_fwd_kernel(HfrShadeFwdArgs a) {
   const int n = blockIdx.y, K = a.p.K;
   const int HW = a.p.H * a.p.W;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  // texture PCA: this sample's coefficients, staged once per CTA and zero padded to a multiple of 4
+  __shared__ float s_tp[PCA ? HFR_MAX_TEX_PCA : 1];
+  if (PCA) {
+    if (threadIdx.x < HFR_MAX_TEX_PCA) s_tp[threadIdx.x] = (int)threadIdx.x < a.p.tex_pca ? a.tex_params[(size_t)n * a.p.tex_pca + threadIdx.x] : 0.0f;
+    __syncthreads();
+  }
   if (p >= HW) return;
   const size_t pix = (size_t)n * HW + p;
   int64_t id[KMAX];
@@ -31,7 +37,7 @@ __global__ void __launch_bounds__(256) shade_fwd_kernel(HfrShadeFwdArgs a) {
     }
   }
   float rgba[4];
-  shade_pixel<KMAX, PCA>(a, n, id, z, d, b, rgba);
+  shade_pixel<KMAX, PCA>(a, n, id, z, d, b, rgba, PCA ? s_tp : nullptr);
   *reinterpret_cast<float4*>(a.image + pix * 4) = make_float4(rgba[0], rgba[1], rgba[2], rgba[3]);
 }
 

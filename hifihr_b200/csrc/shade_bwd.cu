@@ -52,8 +52,11 @@ __device__ __forceinline__ int selk_i(const int (&a)[KMAX], int k) {
 #ifndef HFR_BWD_MINB_K1
 #define HFR_BWD_MINB_K1 8
 #endif
+#ifndef HFR_BWD_MINB_K1_PCA
+#define HFR_BWD_MINB_K1_PCA HFR_BWD_MINB_K1   // texture PCA, K = 1 (C3): resident CTAs per SM of that instantiation
+#endif
 template <int KMAX, bool PCA>
-__global__ void __launch_bounds__(kBwdThreads, (KMAX == 1 ? HFR_BWD_MINB_K1 : (KMAX <= 4 ? HFR_BWD_MINB : 1))) shade_bwd_kernel(HfrShadeBwdArgs a) {
+__global__ void __launch_bounds__(kBwdThreads, (KMAX == 1 ? (PCA ? HFR_BWD_MINB_K1_PCA : HFR_BWD_MINB_K1) : (KMAX <= 4 ? HFR_BWD_MINB : 1))) shade_bwd_kernel(HfrShadeBwdArgs a) {
   __shared__ float s_light[kBwdThreads / 32][6];
   // per-warp staging of the 27 per-fragment components, pitch 33: lane L writes column L (bank j+L),
   // lane j later sums row j over the lanes of one face group (bank j+m) - both conflict-free
@@ -78,6 +81,12 @@ __global__ void __launch_bounds__(kBwdThreads, (KMAX == 1 ? HFR_BWD_MINB_K1 : (K
     const uint4 bx = __ldg(reinterpret_cast<const uint4*>(a.tile_box) + n);
     const int tx = blockIdx.x, ty = (blockIdx.y * kBwdTileH) >> 4;
     if (tx < (int)bx.x || tx > 255 - (int)bx.y || ty < (int)bx.z || ty > 255 - (int)bx.w) return;
+  }
+  // texture PCA: this sample's coefficients, staged once per CTA and zero padded to a multiple of 4
+  __shared__ float s_tp[PCA ? HFR_MAX_TEX_PCA : 1];
+  if (PCA) {
+    if (tid < HFR_MAX_TEX_PCA) s_tp[tid] = tid < P.tex_pca ? f.tex_params[(size_t)n * P.tex_pca + tid] : 0.0f;
+    __syncthreads();
   }
 
   // ---- fragments of this pixel -----------------------------------------------------------
@@ -243,10 +252,11 @@ __global__ void __launch_bounds__(kBwdThreads, (KMAX == 1 ? HFR_BWD_MINB_K1 : (K
         float col[3] = {1.0f, 1.0f, 1.0f}, gcol[3];
         FragGeom g;
         HfrTexTap tap; HfrPhongCtx ctx; float texel[3];
+        float duv[6];   // PCA: uv-derivative sums of the texel fetch (one visit of the taps)
         if (k < kshade) {
           gather_frag(f, n, face, g);
           vid[0] = g.vid[0]; vid[1] = g.vid[1]; vid[2] = g.vid[2];
-          shade_fragment<PCA>(f, n, g, bc, dhat, lcol, col, &tap, &ctx, texel);
+          shade_fragment<PCA>(f, n, g, bc, dhat, lcol, col, &tap, &ctx, texel, PCA ? s_tp : nullptr, PCA ? duv : nullptr);
         }
         if (P.blend == HFR_BLEND_SOFTMAX) {
           const float wk = pk * ek;
@@ -270,8 +280,8 @@ __global__ void __launch_bounds__(kBwdThreads, (KMAX == 1 ? HFR_BWD_MINB_K1 : (K
             hfr_phong_bwd(P, dhat, lcol, texel, &ctx, gcol, gP, gNn, gtex, acc_dhat, acc_lcol);
           }
           float gu = 0.f, gv = 0.f;
-          const HfrTexSrc tsrc = tex_source<PCA>(f, n);
-          hfr_tex_uv_grad(tsrc, &tap, gtex, &gu, &gv);
+          if (PCA) hfr_tex_uv_grad_d(&tap, duv, duv + 3, gtex, &gu, &gv);
+          else hfr_tex_uv_grad(tex_source<PCA>(f, n), &tap, gtex, &gu, &gv);
           if (PCA && a.g_tex_params) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) { tap_k.idx[q] = tap.idx[q]; tap_k.w[q] = tap.w[q]; }
@@ -315,7 +325,7 @@ __global__ void __launch_bounds__(kBwdThreads, (KMAX == 1 ? HFR_BWD_MINB_K1 : (K
       }
       if (PCA && a.g_tex_params && k < kshade) {
         // d(loss)/d(texture coefficients): warp-reduce each component over the lanes of this slot, one RED per warp
-        const HfrTexSrc tsrc = tex_source<true>(f, n);
+        const HfrTexSrc tsrc = tex_source<true>(f, n, s_tp);
         for (int c0 = 0; c0 < P.tex_pca; c0 += 4) {
           float t4[4] = {0.f, 0.f, 0.f, 0.f};
           if (vk) hfr_tex_param_grad4(tsrc, &tap_k, gtex_k, c0, t4);

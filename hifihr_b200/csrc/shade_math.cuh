@@ -50,11 +50,12 @@ struct HfrTexSrc {
   const float* params;   // this sample's npc coefficients or NULL
   int npc;               // 0 = plain map
   int stride;            // > 0: floats per texel record of the texel-major basis (12 * ceil(npc / 4))
+  int padded;            // != 0: params holds 4 * ceil(npc / 4) readable entries, zero beyond npc (the kernels' shared copy)
   size_t map_floats;     // Ht * Wt * 3
 };
 
 HFR_HD HfrTexSrc hfr_tex_plain(const float* tex) {
-  HfrTexSrc s; s.tex = tex; s.basis = nullptr; s.params = nullptr; s.npc = 0; s.stride = 0; s.map_floats = 0;
+  HfrTexSrc s; s.tex = tex; s.basis = nullptr; s.params = nullptr; s.npc = 0; s.stride = 0; s.padded = 0; s.map_floats = 0;
   return s;
 }
 
@@ -74,8 +75,9 @@ HFR_HD void hfr_texel(const HfrTexSrc& src, int idx, float* v) {
     const float4* b = reinterpret_cast<const float4*>(src.basis + (size_t)idx * src.stride);
     for (int k0 = 0; k0 < src.npc; k0 += 4, b += 3) {
       const float4 r0 = hfr_ld4(b), r1 = hfr_ld4(b + 1), r2 = hfr_ld4(b + 2);
-      const float p0 = src.params[k0], p1 = k0 + 1 < src.npc ? src.params[k0 + 1] : 0.0f,
-                  p2 = k0 + 2 < src.npc ? src.params[k0 + 2] : 0.0f, p3 = k0 + 3 < src.npc ? src.params[k0 + 3] : 0.0f;
+      const bool pad = src.padded != 0;
+      const float p0 = src.params[k0], p1 = (pad || k0 + 1 < src.npc) ? src.params[k0 + 1] : 0.0f,
+                  p2 = (pad || k0 + 2 < src.npc) ? src.params[k0 + 2] : 0.0f, p3 = (pad || k0 + 3 < src.npc) ? src.params[k0 + 3] : 0.0f;
       v[0] += p0 * r0.x; v[1] += p0 * r0.y; v[2] += p0 * r0.z;
       v[0] += p1 * r0.w; v[1] += p1 * r1.x; v[2] += p1 * r1.y;
       v[0] += p2 * r1.z; v[1] += p2 * r1.w; v[2] += p2 * r2.x;
@@ -102,6 +104,32 @@ HFR_HD void hfr_tex_fetch(const HfrTexSrc& src, const HfrTexTap* t, float* out) 
   }
 }
 HFR_HD void hfr_tex_fetch(const float* tex, const HfrTexTap* t, float* out) { hfr_tex_fetch(hfr_tex_plain(tex), t, out); }
+
+// The fetch together with the two weight-derivative sums the uv gradient needs,
+//   dax[c] = sum_q (d w_q / d ix) * texel_q[c],   day[c] = sum_q (d w_q / d iy) * texel_q[c],
+// so the backward visits the taps ONCE (with a PCA texture a second visit is another 4 x npc basis reads):
+// d(texel . g)/d(u, v) = ((dax . g) * mx, (day . g) * my)  -  hfr_tex_uv_grad_d below.
+HFR_HD void hfr_tex_fetch_d(const HfrTexSrc& src, const HfrTexTap* t, float* out, float* dax, float* day) {
+  out[0] = out[1] = out[2] = 0.0f;
+  dax[0] = dax[1] = dax[2] = 0.0f;
+  day[0] = day[1] = day[2] = 0.0f;
+  const float ax = t->x0 + 1.0f - t->ix, bx = t->ix - t->x0, ay = t->y0 + 1.0f - t->iy, by = t->iy - t->y0;
+  const float dwx[4] = {-ay, ay, -by, by};   // d w / d ix
+  const float dwy[4] = {-ax, -bx, ax, bx};   // d w / d iy
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if (t->idx[q] >= 0) {
+      float s[3];
+      hfr_texel(src, t->idx[q], s);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { out[c] += s[c] * t->w[q]; dax[c] += s[c] * dwx[q]; day[c] += s[c] * dwy[q]; }
+    }
+  }
+}
+HFR_HD void hfr_tex_uv_grad_d(const HfrTexTap* t, const float* dax, const float* day, const float* g, float* gu, float* gv) {
+  *gu = (dax[0] * g[0] + dax[1] * g[1] + dax[2] * g[2]) * t->mx;
+  *gv = (day[0] * g[0] + day[1] * g[1] + day[2] * g[2]) * t->my;
+}
 
 // d(texel)/d(u,v) contracted with g[3]
 HFR_HD void hfr_tex_uv_grad(const HfrTexSrc& src, const HfrTexTap* t, const float* g, float* gu, float* gv) {

@@ -61,8 +61,9 @@ HFR_HD void light_dir_hat(const HfrShadeFwdArgs& a, int n, float* dhat, float* l
 // texel source of sample n: its own / the shared map, or the PCA texture model with the sample's coefficients
 // (PCA is a template parameter so the plain-map kernels carry none of the model's state: with it as a runtime
 // branch the fused forward lost 6 % and the backward 28 % to extra live registers)
+// `sparams`: the sample's coefficients staged by the kernel (shared memory, zero padded to a multiple of 4), or NULL
 template <bool PCA>
-HFR_HD HfrTexSrc tex_source(const HfrShadeFwdArgs& a, int n) {
+HFR_HD HfrTexSrc tex_source(const HfrShadeFwdArgs& a, int n, const float* sparams = nullptr) {
   const size_t map_floats = (size_t)a.p.tex_h * a.p.tex_w * 3;
   HfrTexSrc s = hfr_tex_plain(a.texture + (a.p.tex_n == 1 ? 0 : (size_t)n * map_floats));
   if (PCA) {
@@ -70,7 +71,8 @@ HFR_HD HfrTexSrc tex_source(const HfrShadeFwdArgs& a, int n) {
     s.npc = a.p.tex_pca;
     s.stride = a.p.tex_basis_stride;
     s.basis = a.tex_basis;
-    s.params = a.tex_params + (size_t)n * a.p.tex_pca;
+    s.params = sparams ? sparams : a.tex_params + (size_t)n * a.p.tex_pca;
+    s.padded = sparams ? 1 : 0;
   }
   return s;
 }
@@ -79,14 +81,16 @@ HFR_HD HfrTexSrc tex_source(const HfrShadeFwdArgs& a, int n) {
 template <bool PCA = false>
 HFR_HD void shade_fragment(const HfrShadeFwdArgs& a, int n, const FragGeom& g, const float* bc,
                                                const float* dhat, const float* lcol, float* color, HfrTexTap* tap,
-                                               HfrPhongCtx* ctx, float* texel) {
+                                               HfrPhongCtx* ctx, float* texel, const float* sparams = nullptr,
+                                               float* duv = nullptr) {
   float P[3], Nn[3];
   interp3(bc, g.X, P);
   interp3(bc, g.Nv, Nn);
   const float u = bc[0] * g.uv[0] + bc[1] * g.uv[2] + bc[2] * g.uv[4];
   const float v = bc[0] * g.uv[1] + bc[1] * g.uv[3] + bc[2] * g.uv[5];
   hfr_tex_tap(a.p.tex_h, a.p.tex_w, u, v, tap);
-  hfr_tex_fetch(tex_source<PCA>(a, n), tap, texel);
+  if (PCA && duv) hfr_tex_fetch_d(tex_source<PCA>(a, n, sparams), tap, texel, duv, duv + 3);   // backward: uv-derivative sums too
+  else hfr_tex_fetch(tex_source<PCA>(a, n, sparams), tap, texel);
   if (a.p.light_point) {   // PointLights.diffuse / .specular: direction = location - points, normalised per fragment
     const float d[3] = {dhat[0] - P[0], dhat[1] - P[1], dhat[2] - P[2]};
     hfr_normalize_eps(d, ctx->lhat, &ctx->llen);
@@ -99,7 +103,7 @@ HFR_HD void shade_fragment(const HfrShadeFwdArgs& a, int n, const FragGeom& g, c
 // Full forward for one pixel given its K fragments.
 template <int KMAX, bool PCA = false>
 HFR_HD void shade_pixel(const HfrShadeFwdArgs& a, int n, const int64_t* id, const float* z,
-                                            const float* d, const float* b, float* rgba) {
+                                            const float* d, const float* b, float* rgba, const float* sparams = nullptr) {
   const int K = a.p.K;
   {   // empty pixel: the blends reduce to the background (alpha 0); silhouette colour stays 1
     bool any = false;
@@ -131,7 +135,7 @@ HFR_HD void shade_pixel(const HfrShadeFwdArgs& a, int n, const int64_t* id, cons
       FragGeom g;
       gather_frag(a, n, (int)(id[k] - (int64_t)n * a.p.F), g);
       HfrTexTap tap; HfrPhongCtx ctx; float texel[3];
-      shade_fragment<PCA>(a, n, g, b + 3 * k, dhat, lcol, colors + 3 * k, &tap, &ctx, texel);
+      shade_fragment<PCA>(a, n, g, b + 3 * k, dhat, lcol, colors + 3 * k, &tap, &ctx, texel, sparams);
     }
   }
   hfr_blend_fwd<KMAX>(a.p, K, valid, z, d, colors, rgba);

@@ -105,11 +105,19 @@ void emul_tex_pca(const float* mean, const float* basis, const float* params, in
                   const float* g, float* out, float* guv, float* gparams, int stride) {
   HfrTexSrc src;
   src.tex = mean; src.basis = basis; src.params = params; src.npc = npc; src.map_floats = (size_t)Ht * Wt * 3;
-  src.stride = stride;   // 0: (npc,Ht,Wt,3); > 0: texel-major records of `stride` floats
+  src.stride = stride < 0 ? -stride : stride;   // 0: (npc,Ht,Wt,3); > 0: texel-major records of `stride` floats; < 0: the same
+  src.padded = 0;                               // through hfr_tex_fetch_d
   for (int i = 0; i < M; ++i) {
     HfrTexTap t; hfr_tex_tap(Ht, Wt, uv[2*i], uv[2*i+1], &t);
-    hfr_tex_fetch(src, &t, out + 3*i);
-    hfr_tex_uv_grad(src, &t, g + 3*i, guv + 2*i, guv + 2*i + 1);
+    if (stride < 0) {   // the backward's single visit of the taps: texel + uv-derivative sums
+      float dax[3], day[3];
+      src.stride = -stride;
+      hfr_tex_fetch_d(src, &t, out + 3*i, dax, day);
+      hfr_tex_uv_grad_d(&t, dax, day, g + 3*i, guv + 2*i, guv + 2*i + 1);
+    } else {
+      hfr_tex_fetch(src, &t, out + 3*i);
+      hfr_tex_uv_grad(src, &t, g + 3*i, guv + 2*i, guv + 2*i + 1);
+    }
     for (int k0 = 0; k0 < npc; k0 += 4) {
       float t4[4];
       hfr_tex_param_grad4(src, &t, g + 3*i, k0, t4);

@@ -224,3 +224,8 @@ def test_pca_texture_math_matches_autograd():
         res.append((o, guv, gp))
     # the two layouts run the same sums in the same order
     assert all(np.array_equal(a, b) for a, b in zip(*res))
+    # the backward's single visit of the taps (hfr_tex_fetch_d + hfr_tex_uv_grad_d): same texel bits, uv gradient re-associated
+    o, guv, gp = np.zeros((M, 3), np.float32), np.zeros((M, 2), np.float32), np.zeros(npc, np.float32)
+    lib.emul_tex_pca(ptr(f(mean)), ptr(bs), ptr(f(params)), npc, Ht, Wt, M, ptr(f(uv)), ptr(f(gs)), ptr(o), ptr(guv), ptr(gp), -stride)
+    assert np.array_equal(o, res[1][0]) and np.array_equal(gp, res[1][2])
+    assert np.abs(guv - uv.grad.numpy()).max() < 1e-3 * max(1, uv.grad.abs().max().item())
