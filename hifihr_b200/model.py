@@ -271,7 +271,7 @@ class FusedHandStep:
                                         L.ptr(imgs, torch.uint8, "imgs") if u8i else None,
                                         L.ptr(seg, torch.uint8, "seg") if u8s else None,
                                         L.ptr(self.loss_partials), L.ptr(self.loss_ticket),
-                                        ops.raster_tile_box(self.ws, B * self.topo.F, B) if self.tiled else None, self.aa)
+                                        ops.raster_tile_box(self.ws, B * self.topo.F, B), self.aa)
         L.call("hfr_loss_forward", self._loss_args)
 
     def launch_raster_shade(self, light_dir, light_color, imgs=None):
@@ -338,7 +338,8 @@ class FusedHandStep:
         S = self.S
         a = L.HfrLossBwdArgs(self._loss_args, L.ptr(self.w), L.ptr(self.gauss), self.n_global * 3 * S * S,
                              self.n_global, L.ptr(self.g_image), None, None, None,
-                             ops.raster_tile_box(self.ws, self.B * self.topo.F, self.B) if self.tiled else None,
+                             # both shading backwards skip the tiles outside the mesh's tile box, so the loss backward does too
+                             ops.raster_tile_box(self.ws, self.B * self.topo.F, self.B),
                              self.aa, 1 if self.tiled else 0, L.ptr(self.gmax_bits) if self.tiled else None)
         L.call("hfr_loss_backward", a)
 
