@@ -4,9 +4,21 @@ usage: python tools/ncu_summary.py <tag> [note]"""
 import csv, os, subprocess, sys, collections
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1]
-note = sys.argv[2] if len(sys.argv) > 2 else ""
-rep = os.path.join(ROOT, "gpurun_out", f"{tag}_prof.ncu-rep")
-lau = os.path.join(ROOT, "gpurun_out", f"{tag}_launches.csv")
+note = sys.argv[2] if len(sys.argv) > 2 and not sys.argv[2].startswith("--") else ""
+# optional: --reps a.ncu-rep b.ncu-rep (instead of gpurun_out/<tag>_prof.ncu-rep; later files win per kernel name),
+#           --launches file.csv, --keep-traffic (do not rewrite profiles/traffic.json: the captures are not the C2 step)
+opt = {"--reps": [], "--launches": []}
+cur = None
+for a in sys.argv[2:]:
+    if a in opt:
+        cur = a
+    elif a == "--keep-traffic":
+        opt[a] = True
+        cur = None
+    elif cur:
+        opt[cur].append(a)
+reps = opt["--reps"] or [os.path.join(ROOT, "gpurun_out", f"{tag}_prof.ncu-rep")]
+lau = opt["--launches"][0] if opt["--launches"] else os.path.join(ROOT, "gpurun_out", f"{tag}_launches.csv")
 out = os.path.join(ROOT, "profiles", f"{tag}_summary.md")
 WANT = [("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "dram rd"), ("dram__bytes_write.sum", "dram wr"),
         ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram %"),
@@ -19,16 +31,20 @@ WANT = [("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "dram rd"),
         ("launch__registers_per_thread", "regs"), ("launch__grid_size", "grid"), ("launch__block_size", "block"),
         ("lts__t_bytes.sum", "L2 bytes")]
 lines = [f"# ncu summary `{tag}`", "", note, ""]
-if os.path.isfile(rep):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(raw.splitlines()))
-    hdr, units = rows[0], rows[1]
-    idx = {h: i for i, h in enumerate(hdr)}
+reps = [r for r in reps if os.path.isfile(r)]
+if reps:
     seen = set()
     traffic = {}
     lines += ["## `ncu --set full --clock-control none` (one launch per kernel; cold-cache, serialised)", "",
+              "captures: " + ", ".join(f"`{os.path.relpath(r, ROOT)}`" for r in reps), "",
               "| kernel | " + " | ".join(n for _, n in WANT) + " |", "|---|" + "---|" * len(WANT)]
-    for r in rows[2:]:
+    allrows = []
+    for rep in reversed(reps):
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(raw.splitlines()))
+        hdr, units = rows[0], rows[1]
+        allrows += [(r, {h: i for i, h in enumerate(hdr)}, units) for r in rows[2:]]
+    for r, idx, units in allrows:
         k = r[idx["Kernel Name"]]
         if k in seen:
             continue
@@ -54,8 +70,9 @@ if os.path.isfile(rep):
         lines.append(f"| `{short}` | " + " | ".join(cells) + " |")
     lines.append("")
     import json
-    json.dump({"tag": tag, "source": f"profiles/{tag}_summary.md (ncu --set full, one launch, C2 B=64)",
-               "dram_bytes_per_launch": traffic}, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
+    if not opt.get("--keep-traffic"):
+        json.dump({"tag": tag, "source": f"profiles/{tag}_summary.md (ncu --set full, one launch, C2 B=64)",
+                   "dram_bytes_per_launch": traffic}, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
 if os.path.isfile(lau):
     rows = [r for r in csv.reader(open(lau)) if r and r[0].isdigit() or (r and r[0] == "ID")]
     hdr = rows[0]
