@@ -380,6 +380,8 @@ class FaceVertsFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, topo: TopologyConsts, verts):
+        if verts.dim() != 3 or verts.shape[1] != topo.V or verts.shape[2] != 3:
+            raise ValueError(f"verts must be (N, {topo.V}, 3) for this topology, got {tuple(verts.shape)}")
         verts = _cu(verts)
         N = verts.shape[0]
         fv = torch.empty(N * topo.F, 3, 3, dtype=F32, device=verts.device)

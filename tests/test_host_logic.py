@@ -65,3 +65,62 @@ def test_workspace_size_queries_are_host_only_and_consistent():
     t = L.HfrTopology()
     t.V, t.F = 778, 1538
     assert lib.hfr_geom_rec_partial_floats(C.byref(t), 64) == 64 * 3 * 1538 * 6
+
+
+def test_pack_tex_basis_layout_and_cache():
+    """ops.pack_tex_basis: (n,T,T,3) -> texel-major (T*T, 12*ceil(n/4)) records, component k / channel c at 3k + c, zero
+    padded (HfrShadeParams.tex_basis_stride); built once per basis tensor and rebuilt when the tensor is modified."""
+    from hifihr_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    for n in (1, 4, 10):
+        b = torch.randn(n, 5, 7, 3, generator=g)
+        p = ops.pack_tex_basis(b)
+        stride = 12 * ((n + 3) // 4)
+        assert p.shape == (35, stride) and p.dtype == torch.float32 and p.is_contiguous()
+        for k in range(n):
+            assert torch.equal(p[:, 3 * k:3 * k + 3].reshape(5, 7, 3), b[k])
+        assert (p[:, 3 * n:] == 0).all()
+        assert ops.pack_tex_basis(b) is p            # cached on the tensor
+        b.mul_(2.0)                                  # in-place change bumps the version counter
+        q = ops.pack_tex_basis(b)
+        assert q is not p and torch.equal(q[:, :3].reshape(5, 7, 3), b[0])
+
+
+def test_fused_step_output_layouts():
+    """One flat output buffer per step (a single device->host copy): loss sums, then d/d(pose), d/d(shape) and - for the
+    NIMBLE-shaped step - d/d(texture coefficients).  Construction is host logic; launching on CPU tensors raises."""
+    import hifihr_b200 as hf
+    from hifihr_b200 import _lib as L
+    m = hf.FusedHandStep(2, image_size=32, texture_size=16, device="cpu")
+    assert m.out.numel() == L.LOSS_NSUMS + 2 * 2 + 2 * (48 + 10)
+    assert m.g_pose.shape == (2, 48) and m.g_betas.shape == (2, 10) and m.g_tex_params is None
+    assert m.g_texture.shape == (1, 16, 16, 3) and m.root_out == 9
+    s = hf.FusedNimbleStep(2, image_size=32, texture_size=16, device="cpu")
+    assert s.out.numel() == L.LOSS_NSUMS + 2 * 2 + 2 * (33 + 20 + 10)
+    assert s.g_pose.shape == (2, 33) and s.g_betas.shape == (2, 20) and s.g_tex_params.shape == (2, 10)
+    assert s.g_texture is None and s.root_out == -1 and not s.tiled          # frozen mean map, no root centring
+    assert s.params.tex_pca == 10 and s.params.tex_basis_stride == 36 and s.tex_basis.shape == (16 * 16, 36)
+    # views alias the flat buffer and follow flip_outputs()
+    a = s.g_tex_params.data_ptr()
+    s.flip_outputs()
+    assert s.g_tex_params.data_ptr() != a
+    s.flip_outputs()
+    assert s.g_tex_params.data_ptr() == a
+    z = torch.zeros(2, 3)
+    with pytest.raises(ValueError):                  # the texture coefficients are a required input of the NIMBLE step
+        s.forward(z, z, z, z, z, z, z, z, z)
+    with pytest.raises(ValueError):
+        m.forward(z, z, z, z, z, z, z, z, z, tex_params=z)
+    with pytest.raises(L.HfrError):                  # no CPU path
+        s.forward(torch.zeros(2, 33), torch.zeros(2, 20), z, z, z, z, z, torch.zeros(2, 3, 32, 32), torch.zeros(2, 32, 32),
+                  tex_params=torch.zeros(2, 10))
+
+
+def test_face_verts_function_has_no_cpu_path():
+    from hifihr_b200 import _lib as L
+    from hifihr_b200 import ops
+    from hifihr_b200.structures import topology_for
+    faces = torch.tensor([[0, 1, 2], [2, 1, 3]])
+    topo = topology_for(faces, 4, torch.device("cpu"))
+    with pytest.raises(L.HfrError):
+        ops.FaceVertsFunction.apply(topo, torch.zeros(1, 4, 3))
