@@ -33,6 +33,19 @@ HFR_HD float hfr_seg_dist2(float px, float py, float ax, float ay, float bx, flo
   return XADD(XMUL(dx, dx), XMUL(dy, dy));
 }
 
+// Exact early rejection for blur_radius == 0 (only a pixel INSIDE the face can be rasterised): true when the pixel is
+// certainly not inside.  b_i = e_i / area (IEEE division) is <= 0 - or NaN - as soon as e_i is zero, NaN, or differs in
+// sign from a non-zero area (a quotient never changes sign; it may underflow to +-0, which is not > 0 either), and the
+// perspective-corrected coordinate b_i z_j z_k / max(sum, eps) with z > 0 keeps that sign.  False means "run the exact
+// math" (hfr_raster_bary decides), never "inside".  area as hfr_raster_bary takes it; v = the 9 packed face floats.
+HFR_HD bool hfr_edge_sign_outside(float px, float py, float x0, float y0, float x1, float y1, float x2, float y2, float area) {
+  const float e0 = hfr_edge(px, py, x1, y1, x2, y2), e1 = hfr_edge(px, py, x2, y2, x0, y0), e2 = hfr_edge(px, py, x0, y0, x1, y1);
+  const bool pos = area > 0.0f;
+  return (area > 0.0f || area < 0.0f) &&
+         (!(e0 > 0.0f || e0 < 0.0f) || !(e1 > 0.0f || e1 < 0.0f) || !(e2 > 0.0f || e2 < 0.0f) ||
+          (e0 > 0.0f) != pos || (e1 > 0.0f) != pos || (e2 > 0.0f) != pos);
+}
+
 // Face-only validity (independent of the pixel): z in front, non-degenerate, not culled.
 HFR_HD bool hfr_face_valid(const float* v, int cull_backfaces) {
   const float zmin = hfr_min3(v[2], v[5], v[8]);

@@ -372,14 +372,7 @@ __device__ __forceinline__ void raster_tile(const HfrRasterArgs& a, const uint32
               }
               const float4* r4 = reinterpret_cast<const float4*>(sm.rec + r * kRecFloats);
               const float4 q0 = r4[0], q1 = r4[1];   // x0 y0 z0 x1 | y1 z1 x2 y2
-              const float e0 = hfr_edge(xf, yf, q0.w, q1.x, q1.z, q1.w), e1 = hfr_edge(xf, yf, q1.z, q1.w, q0.x, q0.y),
-                          e2 = hfr_edge(xf, yf, q0.x, q0.y, q0.w, q1.x);
-              const float ar = q3.y;
-              const bool pos = ar > 0.0f;
-              const bool out = (ar > 0.0f || ar < 0.0f) &&
-                               (!(e0 > 0.0f || e0 < 0.0f) || !(e1 > 0.0f || e1 < 0.0f) || !(e2 > 0.0f || e2 < 0.0f) ||
-                                (e0 > 0.0f) != pos || (e1 > 0.0f) != pos || (e2 > 0.0f) != pos);
-              if (out) continue;
+              if (hfr_edge_sign_outside(xf, yf, q0.x, q0.y, q0.w, q1.x, q1.z, q1.w, q3.y)) continue;
               ri = r;
               break;
             }

@@ -14,6 +14,21 @@ extern "C" {
 void emul_rodrigues_fwd(const float* v, float* R, int n) { for (int i = 0; i < n; ++i) hfr_rodrigues_fwd(v + 3 * i, R + 9 * i); }
 void emul_rodrigues_bwd(const float* v, const float* g, float* gv, int n) { for (int i = 0; i < n; ++i) hfr_rodrigues_bwd(v + 3 * i, g + 9 * i, gv + 3 * i); }
 
+// the exact edge-sign rejection of the K = 1 / blur 0 walk against the full evaluation: for every (pixel, face) pair
+// returns bit 0 = filter says "certainly outside", bit 1 = the exact math says inside (valid face, pz >= 0)
+void emul_sign_filter(const float* fv, const float* pxy, int n, int pc, unsigned char* out) {
+  for (int i = 0; i < n; ++i) {
+    const float* v = fv + 9 * i;
+    const float px = pxy[2 * i], py = pxy[2 * i + 1];
+    const float area = XADD(hfr_edge(v[6], v[7], v[0], v[1], v[3], v[4]), HFR_KEPS);
+    const bool reject = hfr_edge_sign_outside(px, py, v[0], v[1], v[3], v[4], v[6], v[7], area);
+    float pz, bc[3];
+    bool inside = false;
+    const bool ok = hfr_raster_bary(px, py, v, area, pc, 0, &pz, bc, &inside);
+    out[i] = (unsigned char)((reject ? 1 : 0) | ((ok && inside) ? 2 : 0));
+  }
+}
+
 // naive loop over one mesh using the device evaluation function
 void emul_raster(const float* fv, int64_t F, int H, int W, int K, float blur, int pc, int clip, int cull,
                  int64_t* p2f, float* zb, float* ba, float* ds) {

@@ -229,3 +229,39 @@ def test_pca_texture_math_matches_autograd():
     lib.emul_tex_pca(ptr(f(mean)), ptr(bs), ptr(f(params)), npc, Ht, Wt, M, ptr(f(uv)), ptr(f(gs)), ptr(o), ptr(guv), ptr(gp), -stride)
     assert np.array_equal(o, res[1][0]) and np.array_equal(gp, res[1][2])
     assert np.abs(guv - uv.grad.numpy()).max() < 1e-3 * max(1, uv.grad.abs().max().item())
+
+
+def test_edge_sign_filter_never_rejects_an_inside_pixel():
+    """The K = 1 / blur_radius = 0 walk of the rasterizer rejects a candidate when one edge function is zero or differs in
+    sign from the face area (raster_math.cuh hfr_edge_sign_outside) and only then skips the exact coverage math.  Fuzz of
+    that claim on the host build of the same header: the filter never fires on a pair the exact math calls inside -
+    random faces, pixels on edges and vertices, sliver / tiny / huge faces, denormal-sized edge functions, z down to 1e-6,
+    both windings, with and without perspective correction."""
+    g = np.random.default_rng(7)
+    n = 400_000
+    fv = g.uniform(-1.2, 1.2, (n, 3, 3)).astype(np.float32)
+    fv[..., 2] = g.uniform(0.05, 3.0, (n, 3)).astype(np.float32)
+    k = n // 8
+    fv[k:2 * k, :, :2] *= np.float32(1e-3)                       # tiny faces around the origin
+    fv[2 * k:3 * k, 2, :2] = fv[2 * k:3 * k, 0, :2] + (fv[2 * k:3 * k, 1, :2] - fv[2 * k:3 * k, 0, :2]) * np.float32(0.5) \
+        + g.normal(0, 1e-7, (k, 2)).astype(np.float32)           # slivers: third vertex (almost) on the opposite edge
+    fv[3 * k:4 * k, :, :2] *= np.float32(1e-18)                  # edge functions in the denormal range
+    fv[4 * k:5 * k, :, 2] = g.uniform(1e-6, 1e-4, (k, 3)).astype(np.float32)   # depths next to the validity threshold
+    fv[5 * k:6 * k, :, :2] = np.round(fv[5 * k:6 * k, :, :2] * 8) / 8          # vertices on a coarse grid ...
+    pxy = g.uniform(-1.2, 1.2, (n, 2)).astype(np.float32)
+    pxy[5 * k:6 * k] = np.round(pxy[5 * k:6 * k] * 8) / 8                      # ... and pixels on the same grid (exact zeros)
+    pxy[k:2 * k] *= np.float32(1e-3)
+    pxy[3 * k:4 * k] *= np.float32(1e-18)
+    w = g.dirichlet([1, 1, 1], 2 * k).astype(np.float32)                       # pixels INSIDE their face (convex combinations)
+    pxy[6 * k:8 * k] = np.einsum("nc,ncd->nd", w, fv[6 * k:8 * k, :, :2])
+    pxy[7 * k:7 * k + 1000] = fv[7 * k:7 * k + 1000, 0, :2]                    # exactly on a vertex
+    fv = np.ascontiguousarray(fv.reshape(n, 9))
+    pxy = np.ascontiguousarray(pxy)
+    for pc in (0, 1):
+        out = np.zeros(n, np.uint8)
+        lib.emul_sign_filter(ptr(fv), ptr(pxy), n, pc, ptr(out))
+        assert not np.any(out == 3), f"filter rejected {int((out == 3).sum())} inside pairs (pc={pc})"
+        # the test is not vacuous: it rejects most outside pairs and the inside class is well populated
+        assert (out == 2).sum() > n // 10 and (out == 1).sum() > n // 4
+        # what it lets through although the pixel is outside is rare (ties, underflow): the exact math then decides
+        assert (out == 0).sum() < n // 20
