@@ -29,6 +29,21 @@ void emul_sign_filter(const float* fv, const float* pxy, int n, int pc, unsigned
   }
 }
 
+// depth of every (pixel, face) pair as the fine pass computes it (clip = 1: clamped barycentrics; clip = 0: as given);
+// out_pz = pz, flags bit 0 = accepted by hfr_raster_bary (pz >= 0), bit 1 = inside, bit 2 = the face is valid (only valid
+// faces reach the fine pass: the setup kernel gives the others an empty tile range)
+void emul_pair_depth(const float* fv, const float* pxy, int n, int pc, int clip, float* out_pz, unsigned char* flags) {
+  for (int i = 0; i < n; ++i) {
+    const float* v = fv + 9 * i;
+    const float area = XADD(hfr_edge(v[6], v[7], v[0], v[1], v[3], v[4]), HFR_KEPS);
+    float pz = 0.f, bc[3];
+    bool inside = false;
+    const bool ok = hfr_raster_bary(pxy[2 * i], pxy[2 * i + 1], v, area, pc, clip, &pz, bc, &inside);
+    out_pz[i] = pz;
+    flags[i] = (unsigned char)((ok ? 1 : 0) | (inside ? 2 : 0) | (hfr_face_valid(v, 0) ? 4 : 0));
+  }
+}
+
 // naive loop over one mesh using the device evaluation function
 void emul_raster(const float* fv, int64_t F, int H, int W, int K, float blur, int pc, int clip, int cull,
                  int64_t* p2f, float* zb, float* ba, float* ds) {

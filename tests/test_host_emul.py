@@ -265,3 +265,49 @@ def test_edge_sign_filter_never_rejects_an_inside_pixel():
         assert (out == 2).sum() > n // 10 and (out == 1).sum() > n // 4
         # what it lets through although the pixel is outside is rare (ties, underflow): the exact math then decides
         assert (out == 0).sum() < n // 20
+
+
+def test_depth_cull_bound_holds_for_convex_combinations():
+    """The fine pass skips a face whose nearest vertex, shrunk by 1e-5 (raster_tile.cuh: zmin * 0.99999), is not in front
+    of a pixel's K-th depth, and stops at the first depth bucket with that property.  That is exact only if the depth the
+    coverage math would produce can never be smaller: pz must be a convex combination of the vertex depths, up to fp32
+    rounding.  Fuzz on the host build of the same math (slivers, depth ratios of 1e4 inside one face, pixels next to edges
+    and vertices): the bound holds whenever the barycentrics are renormalised - perspective correction (every camera of the
+    reference is a PerspectiveCameras: models_res_nimble.py:183-186) or clamping (blur > 0).
+
+    KNOWN LIMITATION, pinned here: with perspective_correct=False AND blur_radius=0 PyTorch3D's barycentrics are e_i / (area +
+    1e-8) and sum to area / (area + 1e-8) < 1, so a face of NDC area below ~1e-3 yields pz slightly BELOW a convex
+    combination (a sliver of area 2e-8: half of it) and the cull could drop it where PyTorch3D keeps it.  No path of the
+    reference rasterises that way; the functional `rasterize_meshes(..., perspective_correct=False,
+    blur_radius=0)` does."""
+    g = np.random.default_rng(11)
+    n = 300_000
+    fv = g.uniform(-1.2, 1.2, (n, 3, 3)).astype(np.float32)
+    fv[..., 2] = np.exp(g.uniform(np.log(0.02), np.log(200.0), (n, 3))).astype(np.float32)   # depth ratios up to 1e4
+    k = n // 4
+    fv[:k, 2, :2] = fv[:k, 0, :2] + (fv[:k, 1, :2] - fv[:k, 0, :2]) * np.float32(0.3) + g.normal(0, 1e-6, (k, 2)).astype(np.float32)
+    w = g.dirichlet([0.3, 0.3, 0.3], n).astype(np.float32)          # many pixels close to edges and vertices
+    pxy = np.einsum("nc,ncd->nd", w, fv[:, :, :2]).astype(np.float32)
+    pxy[k:2 * k] += g.normal(0, 0.05, (k, 2)).astype(np.float32)    # some outside: clamped barycentrics
+    fvf = np.ascontiguousarray(fv.reshape(n, 9))
+    pxy = np.ascontiguousarray(pxy)
+    zmin = fv[..., 2].min(1)
+    # faces whose doubled area is within fp32 noise of the validity threshold (|area| <= 1e-8 is invalid) are left out: their
+    # edge functions are rounding noise of magnitude 1e-8 .. 1e-7, the reference's own depth there is garbage (all clamped
+    # coordinates 0 -> pz = 0)
+    d = fv.astype(np.float64)
+    fa = (d[:, 2, 0] - d[:, 0, 0]) * (d[:, 1, 1] - d[:, 0, 1]) - (d[:, 2, 1] - d[:, 0, 1]) * (d[:, 1, 0] - d[:, 0, 0])
+    regular = np.abs(fa) >= 1e-6
+
+    def violations(pc, clip):
+        pz, fl = np.zeros(n, np.float32), np.zeros(n, np.uint8)
+        lib.emul_pair_depth(ptr(fvf), ptr(pxy), n, pc, clip, ptr(pz), ptr(fl))
+        sel = regular & (fl & 1).astype(bool) & ((fl & 4) != 0) & (((fl & 2) != 0) | bool(clip))     # pairs the cull is applied to
+        assert sel.sum() > n // 4
+        return sel & ~(pz >= np.float32(0.99999) * zmin)
+
+    for pc, clip in ((1, 0), (1, 1), (0, 1)):
+        bad = violations(pc, clip)
+        assert not bad.any(), (pc, clip, int(bad.sum()))
+    bad = violations(0, 0)
+    assert bad.any() and bad[:k].sum() == bad.sum()        # only the slivers of the first block, never a regular face of this set
