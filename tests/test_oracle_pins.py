@@ -200,6 +200,43 @@ def test_raster_known_answers_single_triangle():
     assert (raster_c.rasterize_naive(bad, [0], [2], 8, 1e-3, 2)[0] == -1).all()
 
 
+@pytest.mark.parametrize("pc", [True, False])
+def test_raster_restatements_agree_on_pixel_centred_vertices(pc):
+    """The scene of tests/test_gpu_round2b.py::test_hard_k1_pixel_centres_on_edges_and_vertices on the CPU side: triangles
+    whose vertices ARE pixel centres, both windings (many edge functions exactly zero).  The scalar C restatement and the
+    vectorised torch restatement of PyTorch3D's rasterizer agree bit for bit there, and a pixel centre on a shared diagonal
+    belongs to neither triangle (strict `> 0`)."""
+    S = 16
+    c = lambda i: (2.0 * i + 1.0) / S - 1.0  # noqa: E731
+    g = torch.Generator().manual_seed(5)
+    tris = []
+    for _ in range(60):
+        ij = torch.randint(0, S, (3, 2), generator=g)
+        z = 1.0 + torch.rand(3, generator=g) * 2.0
+        t = [[c(int(ij[k, 0])), c(int(ij[k, 1])), float(z[k])] for k in range(3)]
+        tris.append(t)
+        tris.append([t[0], t[2], t[1]])
+    fv = torch.tensor(tris, dtype=torch.float32)
+    for K in (1, 3):
+        a = raster_c.rasterize_naive(fv, [0], [fv.shape[0]], S, 0.0, K, perspective_correct=pc)
+        b = p3d.rasterize_meshes(fv, [0], [fv.shape[0]], S, 0.0, K, perspective_correct=pc)
+        assert (a[0] == b.pix_to_face).all() and (a[1] == b.zbuf).all() and (a[2] == b.bary_coords).all() and (a[3] == b.dists).all()
+        assert (a[0] >= 0).any()
+    two = torch.tensor([[[c(2), c(2), 1.5], [c(12), c(2), 1.5], [c(2), c(12), 1.5]],
+                        [[c(12), c(12), 1.5], [c(2), c(12), 1.5], [c(12), c(2), 1.5]]])
+    p2f = raster_c.rasterize_naive(two, [0], [2], S, 0.0, 1, perspective_correct=pc)[0][0, ..., 0]
+    xs = p3d.pixel_centers(S, S)[1]
+    ys = p3d.pixel_centers(S, S)[0]
+    on_diag = 0
+    for yi in range(S):
+        for xi in range(S):
+            x, y = float(xs[xi]) if xs.dim() == 1 else float(xs[yi, xi]), float(ys[yi]) if ys.dim() == 1 else float(ys[yi, xi])
+            if abs((x - c(12)) + (y - c(2))) < 1e-9 and c(2) < x < c(12):      # on the diagonal x + y = c(2) + c(12), strictly between its ends
+                on_diag += 1
+                assert int(p2f[yi, xi]) == -1
+    assert on_diag >= 5 and (p2f == 0).any() and (p2f == 1).any()
+
+
 def test_soft_blend_known_answer():
     """One fragment exactly on an edge (dist 0): prob 0.5 -> alpha 0.5; empty pixel -> background, alpha 0."""
     p2f = torch.tensor([[[[0, -1]], [[-1, -1]]]])
